@@ -1,0 +1,233 @@
+/*
+ * polyred_cuda.h — C ABI of libpolyred_cuda.so, the B200 (sm_100a) backend for
+ * polyred's render pass `render.NewRenderer(...).Render()`.
+ *
+ * Every citation below is a path:line inside the reference tree (poly.red).
+ *
+ * The ABI is deliberately purego-friendly (reference FFI style:
+ * gpu/backend_gl_lib_linux.go:19-26, gpu/backend_gl.go:236-283): every export
+ * takes and returns integers / pointers only (purego.SyscallN passes uintptr),
+ * floats travel inside fixed-layout little-endian POD structs, and every struct
+ * starts with `abi_version`.
+ *
+ * What each call replaces in the reference:
+ *   prc_open / prc_close      gpu.Open / Device.Close (gpu/device.go:77-89) as used by
+ *                             render.GPU(dev) (render/options.go:103-110)
+ *   prc_scene_upload          the per-frame walk of Geometry.Triangles()/Materials()
+ *                             (render/raster.go:241-270) — done once, scene stays in HBM
+ *   prc_shadow_reset          the zeroing of shadow depth maps in initShadowMaps()
+ *                             (render/shadow.go:33-90) reached from NewRenderer/Options
+ *   prc_render                (*Renderer).Render() (render/raster.go:155-199): passShadows,
+ *                             passForward (cpuForwardPass/draw/drawClipped), passDeferred
+ *                             (shade, FragmentShader, shadingVisibility, AO), passAntialiasing
+ *                             (GammaCorrection) — one whole-frame call instead of the three
+ *                             runPass seams (render/raster.go:67-76, 223, 300, 370)
+ *   prc_read_gbuffer          buffer.FragmentBuffer.Get (buffer/buffer.go:209-219), parity only
+ *   prc_read_shadowmap        shadowInfo.depths (render/shadow.go:26-31), parity only
+ *   prc_get_timings           profiling.Timed under render.Debug (render/raster.go:156-161)
+ *
+ * Error convention: every export returns int32 (0 = PRC_OK, <0 = error). There is NO CPU
+ * fallback (the reference falls back per pass, render/raster.go:68-75; north_star forbids it):
+ * the caller must surface the error. prc_last_error(ctx) returns a ctx-owned string valid
+ * until the next call on that ctx. Thread-compatibility: one call at a time per ctx, from
+ * any OS thread (each export does cudaSetDevice itself).
+ */
+#ifndef POLYRED_CUDA_H
+#define POLYRED_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRC_ABI_VERSION 1u
+
+/* error codes */
+#define PRC_OK 0
+#define PRC_ERR_INVALID -1      /* bad argument / abi_version mismatch */
+#define PRC_ERR_CUDA -2         /* CUDA runtime error, see prc_last_error */
+#define PRC_ERR_UNSUPPORTED -3  /* scene/option the path does not implement (no fallback) */
+#define PRC_ERR_NO_SCENE -4
+#define PRC_ERR_NCCL -5
+
+/* prc_material.flags (material.Standard, material/material.go:23-30) */
+#define PRC_MAT_FLAT_SHADING 1u
+#define PRC_MAT_AMBIENT_OCCLUSION 2u
+#define PRC_MAT_RECEIVE_SHADOW 4u
+#define PRC_MAT_NIL 8u          /* table slot holds a non-BlinnPhong material (raster.go:254): use vertex colour */
+#define PRC_MAT_NO_MIPMAP 16u   /* Texture.useMipmap == false (buffer/texture.go:104-106) */
+
+/* prc_light.kind (shader/blinn_cpu.go:72-80) */
+#define PRC_LIGHT_POINT 0u
+#define PRC_LIGHT_DIRECTIONAL 1u
+
+/* prc_frame.flags */
+#define PRC_FRAME_PERSPECT 1u     /* option.Perspect (render/options.go:49-56) */
+#define PRC_FRAME_SHADOWMAP 2u    /* render.ShadowMap(true) */
+#define PRC_FRAME_GAMMA 4u        /* render.GammaCorrection(true) */
+#define PRC_FRAME_KEEP_GBUFFER 8u /* keep the G-buffer for prc_read_gbuffer (parity/debug) */
+#define PRC_FRAME_NO_READBACK 16u /* leave the RGBA on the device (rgba_out may be NULL) */
+
+/* Colours are packed R | G<<8 | B<<16 | A<<24 (image/color.RGBA byte order in memory). */
+
+/* material.BlinnPhong (material/material.go:44-52) as tabulated into Renderer.matTable
+ * (render/raster.go:252-256). `texture` indexes prc_scene textures; <0 is invalid for a
+ * non-NIL material (the reference would nil-deref). */
+typedef struct prc_material {
+  uint32_t diffuse_rgba;
+  uint32_t specular_rgba;
+  float shininess;
+  int32_t texture;
+  uint32_t flags;
+  uint32_t _pad;
+} prc_material;
+
+/* buffer.Texture (buffer/texture.go:28-69): a finished RGBA8 mip chain. Level l of texture t
+ * is level index tex_first_level[t] + l; its texels start at tex_data + level_offset[idx]
+ * (bytes), row-major, stride 4*level_w[idx]. The chain is an INPUT (the host builds it with
+ * the reference's own imageutil.Resize). */
+typedef struct prc_scene {
+  uint32_t abi_version;
+  uint32_t flags;
+  uint64_t n_tris;
+  /* Triangle soup in draw order = scene.IterObjects order x Geometry.Triangles() order
+   * (render/raster.go:241-270). primitive.Vertex (geometry/primitive/vertex.go:15-21):
+   * Pos.W is taken as 1 and Nor.W as 0 (what every reference loader produces,
+   * model/load.go:162-170). */
+  const float* pos;       /* [n_tris][3 verts][xyz]  */
+  const float* nor;       /* [n_tris][3 verts][xyz]  */
+  const float* uv;        /* [n_tris][3 verts][uv]   */
+  const uint32_t* col;    /* [n_tris][3 verts] RGBA8 */
+  const int32_t* mat;     /* [n_tris] FLAT material id = base + local (raster.go:259-262); <0: vertex colour */
+  uint32_t n_objects;
+  uint32_t n_materials;
+  const uint64_t* obj_tri_start; /* [n_objects+1] triangle range of each Geometry */
+  const prc_material* materials; /* [n_materials] the flat matTable */
+  uint32_t n_textures;
+  uint32_t n_tex_levels;
+  const uint32_t* tex_first_level; /* [n_textures+1] */
+  const uint32_t* level_w;         /* [n_tex_levels] */
+  const uint32_t* level_h;         /* [n_tex_levels] */
+  const uint64_t* level_offset;    /* [n_tex_levels] byte offset into tex_data */
+  const uint8_t* tex_data;
+  uint64_t tex_bytes;
+} prc_scene;
+
+/* Per-Geometry uniforms, computed by the host exactly as cpuForwardPass does
+ * (render/raster.go:242-243, 382): trans = Proj.MulM(View).MulM(Model),
+ * normal = Model.Inv().T(). Row-major X00..X33 (math/mat4.go:36-43). */
+typedef struct prc_object_xf {
+  float trans[16];
+  float normal[16];
+} prc_object_xf;
+
+/* light.Source (light/interface.go:30-37). For a shadow-casting light the host also passes
+ * the light camera fitted by initShadowMaps (render/shadow.go:41-86): view, proj, and per
+ * object shadow_trans = lightProj.MulM(lightView).MulM(Model) (render/shadow.go:155). */
+typedef struct prc_light {
+  uint32_t kind;
+  uint32_t cast_shadow;
+  float pos[3]; /* Position() for point, Dir() for directional */
+  float intensity;
+  uint32_t color_rgba;
+  uint32_t _pad;
+  float view[16];
+  float proj[16];
+  const float* shadow_trans; /* [n_objects][16], NULL unless cast_shadow */
+} prc_light;
+
+typedef struct prc_frame {
+  uint32_t abi_version;
+  uint32_t flags;
+  uint32_t width, height; /* render.Size; MSAA must be 1 */
+  uint32_t n_objects;
+  uint32_t n_lights;      /* light sources in Scene.Lights() order (scene/scene.go:35-47) */
+  uint32_t n_ambient;
+  uint32_t background_rgba;
+  const prc_object_xf* objects;
+  const prc_light* lights;
+  const float* ambient_intensity; /* [n_ambient] Environment.Intensity() */
+  float viewport[16];          /* math.ViewportMatrix(w,h) (math/math.go:270-277) */
+  float viewport_inv[16];      /* mvp.ViewportInv (render/raster.go:246) */
+  float proj_inv[16];          /* mvp.ProjInv (raster.go:245) */
+  float view_inv[16];          /* mvp.ViewInv (raster.go:244) */
+  float viewport_to_world[16]; /* ViewInv.MulM(ProjInv).MulM(VPInv) (raster.go:287) */
+  float cam_pos[3];            /* Camera.Position() */
+  float _pad0;
+  uint8_t gamma_lut[256];      /* u8 -> u8 table of shader.GammaCorrection (shader/gamma.go:13-18) */
+  /* Multi-GPU screen partition: this ctx shades rows [row0, row1) of SCREEN y (0 = bottom,
+   * buffer.go:213). row0 = 0,row1 = height on one GPU. */
+  uint32_t row0, row1;
+} prc_frame;
+
+/* Parity/debug view of the G-buffer in SCREEN coordinates: element [y*width + x] is what
+ * FragmentBuffer.Get(x, y) returns (buffer/buffer.go:209-219). Any pointer may be NULL. */
+typedef struct prc_gbuffer_host {
+  uint32_t abi_version;
+  uint32_t _pad;
+  uint8_t* ok;      /* Fragment.Ok */
+  int32_t* tri;     /* index of the winning triangle in prc_scene order, -1 if !ok */
+  int32_t* sub;     /* 0 = drawn unclipped; k>=1 = k-th fan triangle of clipTriangle (clipping.go:73) */
+  float* depth;     /* Fragment.Depth */
+  float* uv;        /* [2] U,V */
+  float* dudv;      /* [2] Du,Dv */
+  float* nor;       /* [3] */
+  float* facenor;   /* [3] */
+  float* wpos;      /* [3] WordPos */
+  uint32_t* col;    /* RGBA8 */
+  int32_t* mat;     /* MaterialID */
+} prc_gbuffer_host;
+
+typedef struct prc_timings {
+  uint32_t abi_version;
+  uint32_t _pad;
+  float shadow_ms;  /* passShadows, all casting lights */
+  float forward_ms; /* passForward: geometry + raster (+ G-buffer resolve when kept) */
+  float shade_ms;   /* passDeferred + gamma */
+  float total_ms;   /* device time of the whole frame, excluding host copies */
+  uint64_t n_valid_tris;  /* triangles passing Triangle.IsValid */
+  uint64_t n_nan_frags;   /* fragments with NaN depth seen by the raster (bug-list 8), not resolved by key */
+  uint64_t gpu_launches;  /* kernels launched by the last prc_render */
+} prc_timings;
+
+typedef struct prc_ctx prc_ctx;
+
+uint32_t prc_abi_version(void);
+int32_t prc_device_count(void);
+/* Opens a context on CUDA device `device`. */
+int32_t prc_open(int32_t device, prc_ctx** out);
+int32_t prc_close(prc_ctx* ctx);
+const char* prc_last_error(prc_ctx* ctx);
+/* Copies the scene into HBM (host arrays are borrowed for the call only) and precomputes
+ * Triangle.IsValid (geometry/primitive/triangle.go:63-80), which is frame-invariant. */
+int32_t prc_scene_upload(prc_ctx* ctx, const prc_scene* scene);
+/* Zeroes the persistent shadow depth maps (they are never cleared by Render(),
+ * render/shadow.go:221-228; only NewRenderer/Options re-create them). */
+int32_t prc_shadow_reset(prc_ctx* ctx);
+/* Renders one frame. rgba_out: caller-owned width*height*4 bytes in image order
+ * (row r = screen y = height-1-r, buffer.go:160-166, 225). With row0/row1 set, only image
+ * rows of that strip are written. */
+int32_t prc_render(prc_ctx* ctx, const prc_frame* frame, uint8_t* rgba_out);
+int32_t prc_read_gbuffer(prc_ctx* ctx, prc_gbuffer_host* out);
+int32_t prc_read_shadowmap(prc_ctx* ctx, uint32_t light, float* out /* [width*height], idx = x + y*width */);
+int32_t prc_get_timings(prc_ctx* ctx, prc_timings* out);
+
+/* ---- multi-GPU plumbing (one process per GPU; collectives are driven by the host through
+ * torch.distributed/NCCL on these device pointers, on the stream returned here) ---- */
+/* Device pointer + byte size of the RGBA8 image (image order) and of shadow map `light`. */
+int32_t prc_device_image(prc_ctx* ctx, uint64_t* dev_ptr, uint64_t* bytes);
+int32_t prc_device_shadowmap(prc_ctx* ctx, uint32_t light, uint64_t* dev_ptr, uint64_t* bytes);
+/* Split frame: phase 1 = shadow passes for the lights/rows this rank owns; the host then
+ * all-gathers the maps; phase 2 = forward + deferred for rows [row0,row1). */
+int32_t prc_render_shadows(prc_ctx* ctx, const prc_frame* frame, uint32_t light_mask,
+                           uint32_t srow0, uint32_t srow1);
+int32_t prc_render_main(prc_ctx* ctx, const prc_frame* frame, uint8_t* rgba_out);
+/* cudaStream_t the ctx launches on (as uint64) so the host can order NCCL after it. */
+int32_t prc_stream(prc_ctx* ctx, uint64_t* stream);
+int32_t prc_sync(prc_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POLYRED_CUDA_H */

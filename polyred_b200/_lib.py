@@ -1,0 +1,152 @@
+"""ctypes binding of libpolyred_cuda.so (include/polyred_cuda.h).
+
+There is NO fallback: if the shared library is missing or a call fails, an exception is
+raised (north_star: no CPU fallback; the reference's per-pass fallback, render/raster.go:68-75,
+is deliberately not mirrored)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi as A
+
+_LIB = None
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libpolyred_cuda.so")
+
+
+class PolyredCudaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libpolyred_cuda: error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise PolyredCudaError(A.PRC_ERR_INVALID, f"{LIB_PATH} not built (run `python -c 'import __graft_entry__ as g; g.build()'`); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        L.prc_abi_version.restype = C.c_uint32
+        L.prc_device_count.restype = C.c_int32
+        L.prc_open.argtypes = [C.c_int32, C.POINTER(vp)]
+        L.prc_close.argtypes = [vp]
+        L.prc_last_error.argtypes = [vp]
+        L.prc_last_error.restype = C.c_char_p
+        L.prc_scene_upload.argtypes = [vp, C.POINTER(A.prc_scene)]
+        L.prc_shadow_reset.argtypes = [vp]
+        L.prc_render.argtypes = [vp, C.POINTER(A.prc_frame), vp]
+        L.prc_read_gbuffer.argtypes = [vp, C.POINTER(A.prc_gbuffer_host)]
+        L.prc_read_shadowmap.argtypes = [vp, C.c_uint32, vp]
+        L.prc_get_timings.argtypes = [vp, C.POINTER(A.prc_timings)]
+        L.prc_device_image.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.prc_device_shadowmap.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.prc_render_shadows.argtypes = [vp, C.POINTER(A.prc_frame), C.c_uint32, C.c_uint32, C.c_uint32]
+        L.prc_render_main.argtypes = [vp, C.POINTER(A.prc_frame), vp]
+        L.prc_stream.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.prc_sync.argtypes = [vp]
+        for name in ("prc_open", "prc_close", "prc_scene_upload", "prc_shadow_reset", "prc_render", "prc_read_gbuffer",
+                     "prc_read_shadowmap", "prc_get_timings", "prc_device_image", "prc_device_shadowmap",
+                     "prc_render_shadows", "prc_render_main", "prc_stream", "prc_sync"):
+            getattr(L, name).restype = C.c_int32
+        if L.prc_abi_version() != A.PRC_ABI_VERSION:
+            raise PolyredCudaError(A.PRC_ERR_INVALID, "ABI version mismatch")
+        _LIB = L
+    return _LIB
+
+
+def _ptr(a, ty):
+    return a.ctypes.data_as(C.POINTER(ty))
+
+
+class Backend:
+    """Common surface of a render backend: the CUDA library here, the CPU oracle in tests/."""
+
+    prefix = "prc"
+
+    def __init__(self, L, handle):
+        self.L, self.h = L, handle
+
+    def _f(self, name):
+        return getattr(self.L, f"{self.prefix}_{name}")
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PolyredCudaError(rc, (self._f("last_error")(self.h) or b"").decode())
+
+    def close(self):
+        if self.h:
+            self._f("close")(self.h)
+            self.h = None
+
+    def scene_upload(self, sd):
+        self._check(self._f("scene_upload")(self.h, C.byref(sd.struct)))
+
+    def shadow_reset(self):
+        self._check(self._f("shadow_reset")(self.h))
+
+    def render(self, fd, out: np.ndarray | None):
+        self._check(self._f("render")(self.h, C.byref(fd.struct), out.ctypes.data if out is not None else None))
+
+    def timings(self) -> A.prc_timings:
+        t = A.prc_timings()
+        self._check(self._f("get_timings")(self.h, C.byref(t)))
+        return t
+
+    def read_gbuffer(self, w, h):
+        n = w * h
+        g = {
+            "ok": np.zeros(n, np.uint8), "tri": np.zeros(n, np.int32), "sub": np.zeros(n, np.int32),
+            "depth": np.zeros(n, np.float32), "uv": np.zeros((n, 2), np.float32), "dudv": np.zeros((n, 2), np.float32),
+            "nor": np.zeros((n, 3), np.float32), "facenor": np.zeros((n, 3), np.float32), "wpos": np.zeros((n, 3), np.float32),
+            "col": np.zeros(n, np.uint32), "mat": np.zeros(n, np.int32),
+        }
+        s = A.prc_gbuffer_host(abi_version=A.PRC_ABI_VERSION)
+        s.ok = _ptr(g["ok"], C.c_uint8); s.tri = _ptr(g["tri"], C.c_int32); s.sub = _ptr(g["sub"], C.c_int32)
+        s.depth = _ptr(g["depth"], C.c_float); s.uv = _ptr(g["uv"], C.c_float); s.dudv = _ptr(g["dudv"], C.c_float)
+        s.nor = _ptr(g["nor"], C.c_float); s.facenor = _ptr(g["facenor"], C.c_float); s.wpos = _ptr(g["wpos"], C.c_float)
+        s.col = _ptr(g["col"], C.c_uint32); s.mat = _ptr(g["mat"], C.c_int32)
+        self._check(self._f("read_gbuffer")(self.h, C.byref(s)))
+        return {k: v.reshape((h, w) + v.shape[1:]) for k, v in g.items()}
+
+    def read_shadowmap(self, light, w, h):
+        out = np.zeros((h, w), np.float32)
+        self._check(self._f("read_shadowmap")(self.h, light, out.ctypes.data))
+        return out
+
+
+class CudaBackend(Backend):
+    def __init__(self, device: int = 0):
+        L = lib()
+        h = C.c_void_p()
+        rc = L.prc_open(device, C.byref(h))
+        if rc != 0:
+            raise PolyredCudaError(rc, f"prc_open(device={device}) failed (is a CUDA device visible? there is no CPU fallback)")
+        super().__init__(L, h)
+        self.device = device
+
+    def device_image(self):
+        p, n = C.c_uint64(), C.c_uint64()
+        self._check(self.L.prc_device_image(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def device_shadowmap(self, light):
+        p, n = C.c_uint64(), C.c_uint64()
+        self._check(self.L.prc_device_shadowmap(self.h, light, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def render_shadows(self, fd, light_mask, row0, row1):
+        self._check(self.L.prc_render_shadows(self.h, C.byref(fd.struct), light_mask, row0, row1))
+
+    def render_main(self, fd, out):
+        self._check(self.L.prc_render_main(self.h, C.byref(fd.struct), out.ctypes.data if out is not None else None))
+
+    def stream(self):
+        s = C.c_uint64()
+        self._check(self.L.prc_stream(self.h, C.byref(s)))
+        return s.value
+
+    def sync(self):
+        self._check(self.L.prc_sync(self.h))
