@@ -189,7 +189,21 @@ typedef struct prc_timings {
   uint64_t n_valid_tris;  /* triangles passing Triangle.IsValid */
   uint64_t n_nan_frags;   /* fragments with NaN depth seen by the raster (bug-list 8), not resolved by key */
   uint64_t gpu_launches;  /* kernels launched by the last prc_render */
+  /* per kernel class, CUDA-event time on the launching stream, summed over the frame:
+   * 0 geom+raster (shadow lights)  1 geom+raster (camera)  2 clip  3 binning (count+scan+fill)
+   * 4 tile raster (shadow)  5 tile raster (camera)  6 resolve  7 shade */
+  float kernel_ms[8];
+  uint32_t kernel_launches[8];
 } prc_timings;
+
+#define PRC_K_GEOM_SHADOW 0
+#define PRC_K_GEOM_CAMERA 1
+#define PRC_K_CLIP 2
+#define PRC_K_BIN 3
+#define PRC_K_TILE_SHADOW 4
+#define PRC_K_TILE_CAMERA 5
+#define PRC_K_RESOLVE 6
+#define PRC_K_SHADE 7
 
 typedef struct prc_ctx prc_ctx;
 

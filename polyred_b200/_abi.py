@@ -141,7 +141,12 @@ class prc_timings(C.Structure):
         ("n_valid_tris", C.c_uint64),
         ("n_nan_frags", C.c_uint64),
         ("gpu_launches", C.c_uint64),
+        ("kernel_ms", C.c_float * 8),
+        ("kernel_launches", C.c_uint32 * 8),
     ]
+
+
+KERNEL_CLASSES = ("geom_raster_shadow", "geom_raster_camera", "clip", "binning", "tile_raster_shadow", "tile_raster_camera", "resolve", "shade")
 
 
 def pack_rgba(c) -> int:

@@ -1,0 +1,600 @@
+// polyred_cuda.cu — C ABI (include/polyred_cuda.h) over the sm_100a kernels in prc_kernels.cuh.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -shared -Xcompiler -fPIC
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "prc_kernels.cuh"
+
+using namespace prc;
+
+namespace {
+
+struct DBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+
+struct prc_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  bool exact = true;  // PRC_FMA=exact|fast (see DESIGN.md "Arithmetic contract")
+
+  // scene
+  bool has_scene = false;
+  DevScene S{};
+  std::vector<DBuf*> scene_bufs;
+  DBuf d_pos, d_nor, d_uv, d_col, d_mat, d_meta, d_mats, d_objstart, d_texfirst, d_lw, d_lh, d_loff, d_tex;
+  uint32_t n_objects = 0;
+  unsigned long long n_valid = 0;
+  bool any_ao = false;
+
+  // frame buffers
+  int W = 0, H = 0;
+  DBuf d_keys, d_ga, d_gb, d_gc, d_gd, d_ao, d_image, d_special, d_counters;
+  DBuf d_large, d_clipq, d_tilecount, d_tilestart, d_cursor, d_bins;
+  DBuf d_xf, d_lights, d_ambient, d_gamma;
+  std::vector<DBuf> d_shadow_trans;  // per light
+  std::vector<DBuf> d_shadow;        // per light, persistent
+  unsigned int large_cap = 0, clip_cap = 0, bins_cap = 0;
+  AoConsts ao{};
+  void* h_pinned = nullptr;  // pinned staging for the RGBA readback
+  size_t h_pinned_cap = 0;
+  Counters* h_counters = nullptr;  // pinned
+
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  // per-kernel-class event pairs of the current frame
+  std::vector<cudaEvent_t> evpool;
+  struct Span { int cls; size_t a, b; };
+  std::vector<Span> spans;
+  size_t ev_used = 0;
+  prc_timings tm{};
+  unsigned long long launches = 0;
+  bool gbuffer_valid = false;
+  uint32_t n_lights_alloc = 0;
+};
+
+namespace {
+
+#define CK(call)                                                                             \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                         \
+      return PRC_ERR_CUDA;                                                                   \
+    }                                                                                        \
+  } while (0)
+
+int32_t ensure(prc_ctx* ctx, DBuf& b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return PRC_OK;
+  if (b.p) CK(cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  if (bytes == 0) bytes = 16;
+  CK(cudaMalloc(&b.p, bytes));
+  b.cap = bytes;
+  return PRC_OK;
+}
+#define ENSURE(buf, bytes)                         \
+  do {                                             \
+    int32_t r_ = ensure(ctx, buf, bytes);          \
+    if (r_ != PRC_OK) return r_;                   \
+  } while (0)
+
+int32_t upload(prc_ctx* ctx, DBuf& b, const void* src, size_t bytes) {
+  ENSURE(b, bytes);
+  if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return PRC_OK;
+}
+#define UPLOAD(buf, src, bytes)                    \
+  do {                                             \
+    int32_t r_ = upload(ctx, buf, src, bytes);     \
+    if (r_ != PRC_OK) return r_;                   \
+  } while (0)
+
+void free_buf(DBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+// CUDA-event bracket around one kernel class (timed on the launching stream)
+struct KTimer {
+  prc_ctx* ctx;
+  size_t a;
+  int cls;
+  KTimer(prc_ctx* c, int k) : ctx(c), cls(k) {
+    while (ctx->evpool.size() < ctx->ev_used + 2) { cudaEvent_t e; cudaEventCreate(&e); ctx->evpool.push_back(e); }
+    a = ctx->ev_used;
+    ctx->ev_used += 2;
+    cudaEventRecord(ctx->evpool[a], ctx->stream);
+  }
+  ~KTimer() {
+    cudaEventRecord(ctx->evpool[a + 1], ctx->stream);
+    ctx->spans.push_back({cls, a, a + 1});
+  }
+};
+
+inline unsigned int cdiv(unsigned long long a, unsigned int b) { return (unsigned int)((a + b - 1) / b); }
+
+// ---- one raster pass (camera or one shadow light) --------------------------------------------
+template <bool E, bool SHADOW>
+int32_t raster_pass(prc_ctx* ctx, const DevFrame& F, const float* shadow_trans, float* smap) {
+  cudaStream_t st = ctx->stream;
+  Counters* cnt = (Counters*)ctx->d_counters.p;
+  // reset n_large / n_clip / n_bin_total (keep n_nan accumulating over the frame)
+  CK(cudaMemsetAsync(cnt, 0, offsetof(Counters, n_nan), st));
+  const int tiles_x = (F.W + PRC_TILE - 1) / PRC_TILE, tiles_y = (F.H + PRC_TILE - 1) / PRC_TILE;
+  const int n_tiles = tiles_x * tiles_y;
+  unsigned long long* keys = (unsigned long long*)ctx->d_keys.p;
+  LargeRec* large = (LargeRec*)ctx->d_large.p;
+  unsigned int* clipq = (unsigned int*)ctx->d_clipq.p;
+  if (ctx->S.n_tris) {
+    KTimer kt(ctx, SHADOW ? PRC_K_GEOM_SHADOW : PRC_K_GEOM_CAMERA);
+    k_geom_raster<E, SHADOW><<<cdiv(ctx->S.n_tris, PRC_GEOM_THREADS), PRC_GEOM_THREADS, 0, st>>>(ctx->S, F, shadow_trans, keys, smap, large, ctx->large_cap,
+                                                                                                     clipq, ctx->clip_cap, cnt);
+    ctx->launches++;
+  }
+  // counters -> host (n_clip, n_large decide the launch sizes of the rare paths)
+  CK(cudaMemcpyAsync(ctx->h_counters, cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (ctx->h_counters->large_overflow) { ctx->err = "internal queue overflow (large/clip)"; return PRC_ERR_UNSUPPORTED; }
+  if (!SHADOW && ctx->h_counters->n_clip) {
+    { KTimer kt(ctx, PRC_K_CLIP);
+    k_clip_raster<E><<<cdiv(ctx->h_counters->n_clip, 128), 128, 0, st>>>(ctx->S, F, clipq, keys, large, ctx->large_cap, cnt); }
+    ctx->launches++;
+    CK(cudaMemcpyAsync(ctx->h_counters, cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (ctx->h_counters->large_overflow) { ctx->err = "internal queue overflow (large)"; return PRC_ERR_UNSUPPORTED; }
+  }
+  const unsigned int n_large = ctx->h_counters->n_large;
+  if (n_large) {
+    unsigned int* tile_count = (unsigned int*)ctx->d_tilecount.p;
+    unsigned int* tile_start = (unsigned int*)ctx->d_tilestart.p;
+    unsigned int* cursor = (unsigned int*)ctx->d_cursor.p;
+    CK(cudaMemsetAsync(tile_count, 0, (size_t)n_tiles * 4, st));
+    { KTimer kt(ctx, PRC_K_BIN);
+    k_bin_count<<<cdiv((unsigned long long)n_large * 32, 256), 256, 0, st>>>(large, cnt, ctx->large_cap, tiles_x, tile_count);
+    k_scan<<<1, 1024, 0, st>>>(tile_count, tile_start, cursor, n_tiles, cnt); }
+    ctx->launches += 2;
+    CK(cudaMemcpyAsync(ctx->h_counters, cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const unsigned int total = ctx->h_counters->n_bin_total;
+    if (total > ctx->bins_cap) {
+      ENSURE(ctx->d_bins, (size_t)total * 4 * 5 / 4);
+      ctx->bins_cap = (unsigned int)(ctx->d_bins.cap / 4);
+    }
+    { KTimer kt(ctx, PRC_K_BIN);
+    k_bin_fill<<<cdiv((unsigned long long)n_large * 32, 256), 256, 0, st>>>(large, cnt, ctx->large_cap, tiles_x, cursor, (unsigned int*)ctx->d_bins.p,
+                                                                            ctx->bins_cap); }
+    const int r0 = SHADOW ? F.row0 : F.rr0, r1 = SHADOW ? F.row1 : F.rr1;
+    { KTimer kt(ctx, SHADOW ? PRC_K_TILE_SHADOW : PRC_K_TILE_CAMERA);
+    k_tile_raster<E, SHADOW><<<n_tiles, PRC_TILE * PRC_TILE, 0, st>>>(large, tile_start, (unsigned int*)ctx->d_bins.p, tiles_x, F.W, F.H, r0, r1, keys, smap, cnt); }
+    ctx->launches += 2;
+  }
+  CK(cudaGetLastError());
+  return PRC_OK;
+}
+
+int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
+  if (!fr || fr->abi_version != PRC_ABI_VERSION) { ctx->err = "prc_frame: bad abi_version"; return PRC_ERR_INVALID; }
+  if (!ctx->has_scene) { ctx->err = "no scene uploaded"; return PRC_ERR_NO_SCENE; }
+  if (fr->n_objects != ctx->n_objects) { ctx->err = "prc_frame.n_objects differs from the uploaded scene"; return PRC_ERR_INVALID; }
+  if (fr->width == 0 || fr->height == 0 || fr->width > 32760 || fr->height > 32760) { ctx->err = "bad frame size"; return PRC_ERR_INVALID; }
+  if (fr->row1 > fr->height || fr->row0 >= fr->row1) { ctx->err = "bad row range"; return PRC_ERR_INVALID; }
+  for (uint32_t i = 0; i < fr->n_lights; i++) {
+    if (fr->lights[i].kind > PRC_LIGHT_DIRECTIONAL) { ctx->err = "unsupported light kind"; return PRC_ERR_UNSUPPORTED; }
+    if (fr->lights[i].cast_shadow && !fr->lights[i].shadow_trans) { ctx->err = "casting light without shadow_trans"; return PRC_ERR_INVALID; }
+  }
+  const int W = fr->width, H = fr->height;
+  const size_t npx = (size_t)W * H;
+  cudaStream_t st = ctx->stream;
+  if (W != ctx->W || H != ctx->H || fr->n_lights != ctx->n_lights_alloc) {
+    // resetBufs + initShadowMaps: new size => fresh (zero) shadow maps
+    for (auto& b : ctx->d_shadow) free_buf(b);
+    ctx->d_shadow.assign(fr->n_lights, DBuf());
+    for (auto& b : ctx->d_shadow_trans) free_buf(b);
+    ctx->d_shadow_trans.assign(fr->n_lights, DBuf());
+    ctx->W = W; ctx->H = H; ctx->n_lights_alloc = fr->n_lights;
+    ctx->gbuffer_valid = false;
+  }
+  ENSURE(ctx->d_keys, npx * 8);
+  ENSURE(ctx->d_ga, npx * 16); ENSURE(ctx->d_gb, npx * 16); ENSURE(ctx->d_gc, npx * 16); ENSURE(ctx->d_gd, npx * 16);
+  if (ctx->any_ao) ENSURE(ctx->d_ao, npx * 4);
+  ENSURE(ctx->d_image, npx * 4);
+  ENSURE(ctx->d_special, 16);
+  const int n_tiles = ((W + PRC_TILE - 1) / PRC_TILE) * ((H + PRC_TILE - 1) / PRC_TILE);
+  ENSURE(ctx->d_tilecount, (size_t)n_tiles * 4); ENSURE(ctx->d_tilestart, (size_t)(n_tiles + 1) * 4); ENSURE(ctx->d_cursor, (size_t)n_tiles * 4);
+  if (!ctx->d_bins.p) { ENSURE(ctx->d_bins, (size_t)4 << 20); ctx->bins_cap = (unsigned int)(ctx->d_bins.cap / 4); }
+  for (uint32_t i = 0; i < fr->n_lights; i++) {
+    if (fr->lights[i].cast_shadow && (fr->flags & PRC_FRAME_SHADOWMAP) && !ctx->d_shadow[i].p) {
+      ENSURE(ctx->d_shadow[i], npx * 4);
+      CK(cudaMemsetAsync(ctx->d_shadow[i].p, 0, npx * 4, st));
+    }
+  }
+  // uniforms
+  UPLOAD(ctx->d_xf, fr->objects, (size_t)fr->n_objects * sizeof(prc_object_xf));
+  std::vector<DevLight> hl(fr->n_lights);
+  for (uint32_t i = 0; i < fr->n_lights; i++) {
+    const prc_light& l = fr->lights[i];
+    DevLight& d = hl[i];
+    d.kind = l.kind;
+    d.cast_shadow = (l.cast_shadow && (fr->flags & PRC_FRAME_SHADOWMAP)) ? 1u : 0u;
+    memcpy(d.pos, l.pos, 12);
+    d.intensity = l.intensity;
+    d.color = l.color_rgba;
+    memcpy(d.view, l.view, 64);
+    memcpy(d.proj, l.proj, 64);
+    d.shadow_map = (float*)ctx->d_shadow[i].p;
+    if (d.cast_shadow) UPLOAD(ctx->d_shadow_trans[i], l.shadow_trans, (size_t)fr->n_objects * 64);
+  }
+  UPLOAD(ctx->d_lights, hl.data(), hl.size() * sizeof(DevLight));
+  UPLOAD(ctx->d_ambient, fr->ambient_intensity, (size_t)fr->n_ambient * 4);
+  UPLOAD(ctx->d_gamma, fr->gamma_lut, 256);
+  CK(cudaStreamSynchronize(st));  // hl is a stack temporary
+  F.W = W; F.H = H;
+  F.row0 = fr->row0; F.row1 = fr->row1;
+  // AO marches up to 99 pixels from the shaded pixel (material/ao.go:44-46): widen the rasterised rows
+  const int halo = ctx->any_ao ? 100 : 0;
+  F.rr0 = std::max(0, (int)fr->row0 - halo);
+  F.rr1 = std::min(H, (int)fr->row1 + halo);
+  F.flags = fr->flags;
+  F.n_lights = fr->n_lights; F.n_ambient = fr->n_ambient;
+  F.background = fr->background_rgba;
+  memcpy(F.viewport, fr->viewport, 64); memcpy(F.viewport_inv, fr->viewport_inv, 64);
+  memcpy(F.proj_inv, fr->proj_inv, 64); memcpy(F.view_inv, fr->view_inv, 64); memcpy(F.vtw, fr->viewport_to_world, 64);
+  memcpy(F.cam, fr->cam_pos, 12);
+  F.xf = (const prc_object_xf*)ctx->d_xf.p;
+  F.lights = (const DevLight*)ctx->d_lights.p;
+  F.ambient = (const float*)ctx->d_ambient.p;
+  F.gamma = (const uint8_t*)ctx->d_gamma.p;
+  return PRC_OK;
+}
+
+template <bool E>
+int32_t do_shadows(prc_ctx* ctx, const prc_frame* fr, DevFrame F, uint32_t light_mask, int srow0, int srow1) {
+  if (!(fr->flags & PRC_FRAME_SHADOWMAP)) return PRC_OK;
+  F.row0 = srow0; F.row1 = srow1;
+  for (uint32_t i = 0; i < fr->n_lights; i++) {
+    if (!fr->lights[i].cast_shadow || !((light_mask >> (i & 31)) & 1u)) continue;
+    int32_t r = raster_pass<E, true>(ctx, F, (const float*)ctx->d_shadow_trans[i].p, (float*)ctx->d_shadow[i].p);
+    if (r != PRC_OK) return r;
+  }
+  return PRC_OK;
+}
+
+template <bool E>
+int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F) {
+  cudaStream_t st = ctx->stream;
+  const size_t npx = (size_t)F.W * F.H;
+  // clear the visibility keys of the rasterised rows (+ pixel (0,0))
+  CK(cudaMemsetAsync((unsigned long long*)ctx->d_keys.p + (size_t)F.rr0 * F.W, 0, (size_t)(F.rr1 - F.rr0) * F.W * 8, st));
+  if (F.rr0 > 0) CK(cudaMemsetAsync(ctx->d_keys.p, 0, 8, st));
+  (void)npx;
+  int32_t r = raster_pass<E, false>(ctx, F, nullptr, nullptr);
+  if (r != PRC_OK) return r;
+  CK(cudaEventRecord(ctx->ev[2], st));
+  GBuf G{(float4*)ctx->d_ga.p, (float4*)ctx->d_gb.p, (float4*)ctx->d_gc.p, (float4*)ctx->d_gd.p, ctx->any_ao ? (float*)ctx->d_ao.p : nullptr};
+  const unsigned long long* keys = (const unsigned long long*)ctx->d_keys.p;
+  dim3 rg((F.W + 31) / 32, (F.rr1 - F.rr0 + 3) / 4);
+  { KTimer kt(ctx, PRC_K_RESOLVE);
+  k_resolve<E><<<rg, 128, 0, st>>>(ctx->S, F, keys, G);
+  ctx->launches++;
+  if (F.rr0 > 0) { k_resolve00<E><<<1, 1, 0, st>>>(ctx->S, F, keys, G); ctx->launches++; } }
+  { KTimer kt(ctx, PRC_K_SHADE);
+  k_shade_special<E><<<1, 32, 0, st>>>(ctx->S, F, ctx->ao, keys, G, (uint32_t*)ctx->d_special.p);
+  dim3 sg((F.W + 31) / 32, (F.row1 - F.row0 + 3) / 4);
+  k_shade<E><<<sg, 128, 0, st>>>(ctx->S, F, ctx->ao, keys, G, (const uint32_t*)ctx->d_special.p, (uint32_t*)ctx->d_image.p); }
+  ctx->launches += 2;
+  CK(cudaGetLastError());
+  ctx->gbuffer_valid = true;
+  return PRC_OK;
+}
+
+int32_t readback_image(prc_ctx* ctx, const DevFrame& F, uint8_t* rgba_out) {
+  if (!rgba_out) return PRC_OK;
+  // image rows of the strip: screen rows [row0,row1) -> image rows [H-row1, H-row0)
+  const size_t off = (size_t)(F.H - F.row1) * F.W * 4, bytes = (size_t)(F.row1 - F.row0) * F.W * 4;
+  if (ctx->h_pinned_cap < bytes) {
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    ctx->h_pinned = nullptr;
+    CK(cudaMallocHost(&ctx->h_pinned, bytes));
+    ctx->h_pinned_cap = bytes;
+  }
+  CK(cudaMemcpyAsync(ctx->h_pinned, (uint8_t*)ctx->d_image.p + off, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  memcpy(rgba_out + off, ctx->h_pinned, bytes);
+  return PRC_OK;
+}
+
+int32_t finish_timings(prc_ctx* ctx) {
+  CK(cudaStreamSynchronize(ctx->stream));
+  float a = 0, b = 0, c = 0, d = 0;
+  cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
+  cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
+  cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]);
+  cudaEventElapsedTime(&d, ctx->ev[0], ctx->ev[3]);
+  ctx->tm.abi_version = PRC_ABI_VERSION;
+  ctx->tm.shadow_ms = a; ctx->tm.forward_ms = b; ctx->tm.shade_ms = c; ctx->tm.total_ms = d;
+  ctx->tm.n_valid_tris = ctx->n_valid;
+  CK(cudaMemcpy(ctx->h_counters, ctx->d_counters.p, sizeof(Counters), cudaMemcpyDeviceToHost));
+  ctx->tm.n_nan_frags = ctx->h_counters->n_nan;
+  ctx->tm.gpu_launches = ctx->launches;
+  for (int k = 0; k < 8; k++) { ctx->tm.kernel_ms[k] = 0; ctx->tm.kernel_launches[k] = 0; }
+  for (auto& sp : ctx->spans) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->evpool[sp.a], ctx->evpool[sp.b]);
+    ctx->tm.kernel_ms[sp.cls] += ms;
+    ctx->tm.kernel_launches[sp.cls]++;
+  }
+  ctx->spans.clear();
+  ctx->ev_used = 0;
+  return PRC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t prc_abi_version(void) { return PRC_ABI_VERSION; }
+
+int32_t prc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int32_t prc_open(int32_t device, prc_ctx** out) {
+  if (!out) return PRC_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return PRC_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return PRC_ERR_CUDA;
+  prc_ctx* ctx = new prc_ctx();
+  ctx->device = device;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PRC_ERR_CUDA; }
+  for (auto& e : ctx->ev) cudaEventCreate(&e);
+  cudaMallocHost((void**)&ctx->h_counters, sizeof(Counters));
+  cudaMalloc(&ctx->d_counters.p, sizeof(Counters));
+  ctx->d_counters.cap = sizeof(Counters);
+  cudaMemset(ctx->d_counters.p, 0, sizeof(Counters));
+  const char* mode = getenv("PRC_FMA");
+  ctx->exact = !(mode && strcmp(mode, "fast") == 0);
+  // AO constants (material/ao.go:28-32): a accumulates float32(Pi/4) in float32; Cos/Sin via float64.
+  const float pi = 3.14159265358979323846f, q = pi / 4;
+  float a = 0.0f;
+  for (int k = 0; k < 8; k++) {
+    ctx->ao.cosv[k] = (float)std::cos((double)a);
+    ctx->ao.sinv[k] = (float)std::sin((double)a);
+    a += q;
+  }
+  ctx->ao.half_pi = pi / 2;
+  ctx->ao.four_pi = pi * 4;
+  *out = ctx;
+  return PRC_OK;
+}
+
+int32_t prc_close(prc_ctx* ctx) {
+  if (!ctx) return PRC_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DBuf* all[] = {&ctx->d_pos, &ctx->d_nor, &ctx->d_uv, &ctx->d_col, &ctx->d_mat, &ctx->d_meta, &ctx->d_mats, &ctx->d_objstart, &ctx->d_texfirst,
+                 &ctx->d_lw, &ctx->d_lh, &ctx->d_loff, &ctx->d_tex, &ctx->d_keys, &ctx->d_ga, &ctx->d_gb, &ctx->d_gc, &ctx->d_gd, &ctx->d_ao,
+                 &ctx->d_image, &ctx->d_special, &ctx->d_counters, &ctx->d_large, &ctx->d_clipq, &ctx->d_tilecount, &ctx->d_tilestart, &ctx->d_cursor,
+                 &ctx->d_bins, &ctx->d_xf, &ctx->d_lights, &ctx->d_ambient, &ctx->d_gamma};
+  for (DBuf* b : all) free_buf(*b);
+  for (auto& b : ctx->d_shadow) free_buf(b);
+  for (auto& b : ctx->d_shadow_trans) free_buf(b);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+  for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : ctx->evpool) cudaEventDestroy(e);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return PRC_OK;
+}
+
+const char* prc_last_error(prc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+int32_t prc_set_exact_fma(prc_ctx* ctx, int32_t exact) {
+  if (!ctx) return PRC_ERR_INVALID;
+  ctx->exact = exact != 0;
+  return PRC_OK;
+}
+
+int32_t prc_scene_upload(prc_ctx* ctx, const prc_scene* s) {
+  if (!ctx) return PRC_ERR_INVALID;
+  if (!s || s->abi_version != PRC_ABI_VERSION) { ctx->err = "prc_scene: bad abi_version"; return PRC_ERR_INVALID; }
+  if (s->n_tris >= (1ull << 29)) { ctx->err = "too many triangles (limit 2^29)"; return PRC_ERR_UNSUPPORTED; }
+  if (s->n_objects >= (1u << 24)) { ctx->err = "too many objects (limit 2^24)"; return PRC_ERR_UNSUPPORTED; }
+  for (uint32_t i = 0; i < s->n_materials; i++) {
+    const prc_material& m = s->materials[i];
+    if (!(m.flags & PRC_MAT_NIL) && (m.texture < 0 || (uint32_t)m.texture >= s->n_textures)) { ctx->err = "material without texture"; return PRC_ERR_INVALID; }
+  }
+  CK(cudaSetDevice(ctx->device));
+  ctx->has_scene = false;
+  const uint64_t n = s->n_tris;
+  UPLOAD(ctx->d_pos, s->pos, n * 36 + 16);  // +16: the float4 staging loop may read up to the 16-byte boundary
+  UPLOAD(ctx->d_nor, s->nor, n * 36);
+  UPLOAD(ctx->d_uv, s->uv, n * 24);
+  UPLOAD(ctx->d_col, s->col, n * 12);
+  UPLOAD(ctx->d_mat, s->mat, n * 4);
+  UPLOAD(ctx->d_mats, s->materials, (size_t)s->n_materials * sizeof(prc_material));
+  UPLOAD(ctx->d_objstart, s->obj_tri_start, (size_t)(s->n_objects + 1) * 8);
+  UPLOAD(ctx->d_texfirst, s->tex_first_level, (size_t)(s->n_textures + 1) * 4);
+  UPLOAD(ctx->d_lw, s->level_w, (size_t)s->n_tex_levels * 4);
+  UPLOAD(ctx->d_lh, s->level_h, (size_t)s->n_tex_levels * 4);
+  UPLOAD(ctx->d_loff, s->level_offset, (size_t)s->n_tex_levels * 8);
+  UPLOAD(ctx->d_tex, s->tex_data, s->tex_bytes);
+  ENSURE(ctx->d_meta, n * 4);
+  ctx->large_cap = (unsigned int)std::min<uint64_t>(n + 65536, 0xFFFFFFF0ull);
+  ctx->clip_cap = (unsigned int)std::min<uint64_t>(n + 16, 0xFFFFFFF0ull);
+  ENSURE(ctx->d_large, (size_t)ctx->large_cap * sizeof(LargeRec));
+  ENSURE(ctx->d_clipq, (size_t)ctx->clip_cap * 4);
+  ctx->any_ao = false;
+  for (uint32_t i = 0; i < s->n_materials; i++)
+    if (!(s->materials[i].flags & PRC_MAT_NIL) && (s->materials[i].flags & PRC_MAT_AMBIENT_OCCLUSION)) ctx->any_ao = true;
+  // Triangle.IsValid + object index, once per scene
+  Counters* cnt = (Counters*)ctx->d_counters.p;
+  CK(cudaMemsetAsync(cnt, 0, sizeof(Counters), ctx->stream));
+  if (n) k_validate<<<cdiv(n, 256), 256, 0, ctx->stream>>>((const float*)ctx->d_pos.p, (const uint64_t*)ctx->d_objstart.p, s->n_objects, n,
+                                                           (uint32_t*)ctx->d_meta.p, &cnt->n_valid);
+  CK(cudaMemcpyAsync(ctx->h_counters, cnt, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  ctx->n_valid = ctx->h_counters->n_valid;
+  DevScene& S = ctx->S;
+  S.pos = (const float*)ctx->d_pos.p; S.nor = (const float*)ctx->d_nor.p; S.uv = (const float*)ctx->d_uv.p;
+  S.col = (const uint32_t*)ctx->d_col.p; S.mat = (const int32_t*)ctx->d_mat.p; S.meta = (const uint32_t*)ctx->d_meta.p;
+  S.n_tris = n;
+  S.mats = (const prc_material*)ctx->d_mats.p; S.n_mats = s->n_materials;
+  S.tex_first = (const uint32_t*)ctx->d_texfirst.p; S.level_w = (const uint32_t*)ctx->d_lw.p; S.level_h = (const uint32_t*)ctx->d_lh.p;
+  S.level_off = (const uint64_t*)ctx->d_loff.p; S.tex_data = (const uint8_t*)ctx->d_tex.p;
+  ctx->n_objects = s->n_objects;
+  ctx->has_scene = true;
+  ctx->gbuffer_valid = false;
+  return PRC_OK;
+}
+
+int32_t prc_shadow_reset(prc_ctx* ctx) {
+  if (!ctx) return PRC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  for (auto& b : ctx->d_shadow)
+    if (b.p) CK(cudaMemsetAsync(b.p, 0, (size_t)ctx->W * ctx->H * 4, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PRC_OK;
+}
+
+int32_t prc_render_shadows(prc_ctx* ctx, const prc_frame* fr, uint32_t light_mask, uint32_t srow0, uint32_t srow1) {
+  if (!ctx) return PRC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  DevFrame F;
+  int32_t r = build_frame(ctx, fr, F);
+  if (r != PRC_OK) return r;
+  if (srow1 > fr->height || srow0 >= srow1) { ctx->err = "bad shadow row range"; return PRC_ERR_INVALID; }
+  ctx->launches = 0;
+  CK(cudaMemsetAsync(&((Counters*)ctx->d_counters.p)->n_nan, 0, 8, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  r = ctx->exact ? do_shadows<true>(ctx, fr, F, light_mask, srow0, srow1) : do_shadows<false>(ctx, fr, F, light_mask, srow0, srow1);
+  if (r != PRC_OK) return r;
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  return PRC_OK;
+}
+
+int32_t prc_render_main(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out) {
+  if (!ctx) return PRC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  DevFrame F;
+  int32_t r = build_frame(ctx, fr, F);
+  if (r != PRC_OK) return r;
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  r = ctx->exact ? do_main<true>(ctx, fr, F) : do_main<false>(ctx, fr, F);
+  if (r != PRC_OK) return r;
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  if (!(fr->flags & PRC_FRAME_NO_READBACK)) {
+    r = readback_image(ctx, F, rgba_out);
+    if (r != PRC_OK) return r;
+  }
+  return finish_timings(ctx);
+}
+
+int32_t prc_render(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out) {
+  if (!ctx) return PRC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  DevFrame F;
+  int32_t r = build_frame(ctx, fr, F);
+  if (r != PRC_OK) return r;
+  ctx->launches = 0;
+  CK(cudaMemsetAsync(&((Counters*)ctx->d_counters.p)->n_nan, 0, 8, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  r = ctx->exact ? do_shadows<true>(ctx, fr, F, 0xFFFFFFFFu, 0, F.H) : do_shadows<false>(ctx, fr, F, 0xFFFFFFFFu, 0, F.H);
+  if (r != PRC_OK) return r;
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  r = ctx->exact ? do_main<true>(ctx, fr, F) : do_main<false>(ctx, fr, F);
+  if (r != PRC_OK) return r;
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  if (!(fr->flags & PRC_FRAME_NO_READBACK)) {
+    r = readback_image(ctx, F, rgba_out);
+    if (r != PRC_OK) return r;
+  }
+  return finish_timings(ctx);
+}
+
+int32_t prc_read_gbuffer(prc_ctx* ctx, prc_gbuffer_host* g) {
+  if (!ctx || !g) return PRC_ERR_INVALID;
+  if (!ctx->gbuffer_valid) { ctx->err = "no G-buffer (render a frame first)"; return PRC_ERR_INVALID; }
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)ctx->W * ctx->H;
+  std::vector<unsigned long long> keys(n);
+  std::vector<float4> a(n), b(n), c(n), d(n);
+  CK(cudaMemcpy(keys.data(), ctx->d_keys.p, n * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(a.data(), ctx->d_ga.p, n * 16, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(b.data(), ctx->d_gb.p, n * 16, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(c.data(), ctx->d_gc.p, n * 16, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(d.data(), ctx->d_gd.p, n * 16, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; i++) {
+    const bool ok = keys[i] != 0;
+    const uint32_t seq = 0xFFFFFFFFu - (uint32_t)keys[i];
+    if (g->ok) g->ok[i] = ok;
+    if (g->tri) g->tri[i] = ok ? (int32_t)(seq >> 3) : -1;
+    if (g->sub) g->sub[i] = ok ? (int32_t)(seq & 7u) : 0;
+    if (g->depth) g->depth[i] = ok ? a[i].x : 0.0f;
+    if (g->uv) { g->uv[2 * i] = ok ? a[i].y : 0.0f; g->uv[2 * i + 1] = ok ? a[i].z : 0.0f; }
+    if (g->dudv) { g->dudv[2 * i] = ok ? a[i].w : 0.0f; g->dudv[2 * i + 1] = ok ? b[i].x : 0.0f; }
+    if (g->nor) { g->nor[3 * i] = ok ? b[i].y : 0.0f; g->nor[3 * i + 1] = ok ? b[i].z : 0.0f; g->nor[3 * i + 2] = ok ? b[i].w : 0.0f; }
+    if (g->facenor) { g->facenor[3 * i] = ok ? c[i].x : 0.0f; g->facenor[3 * i + 1] = ok ? c[i].y : 0.0f; g->facenor[3 * i + 2] = ok ? c[i].z : 0.0f; }
+    if (g->wpos) { g->wpos[3 * i] = ok ? c[i].w : 0.0f; g->wpos[3 * i + 1] = ok ? d[i].x : 0.0f; g->wpos[3 * i + 2] = ok ? d[i].y : 0.0f; }
+    if (g->col) { uint32_t u; memcpy(&u, &d[i].z, 4); g->col[i] = ok ? u : 0u; }
+    if (g->mat) { int32_t m; memcpy(&m, &d[i].w, 4); g->mat[i] = ok ? m : 0; }
+  }
+  return PRC_OK;
+}
+
+int32_t prc_read_shadowmap(prc_ctx* ctx, uint32_t light, float* out) {
+  if (!ctx || !out) return PRC_ERR_INVALID;
+  if (light >= ctx->d_shadow.size() || !ctx->d_shadow[light].p) { ctx->err = "no such shadow map"; return PRC_ERR_INVALID; }
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpy(out, ctx->d_shadow[light].p, (size_t)ctx->W * ctx->H * 4, cudaMemcpyDeviceToHost));
+  return PRC_OK;
+}
+
+int32_t prc_get_timings(prc_ctx* ctx, prc_timings* out) {
+  if (!ctx || !out) return PRC_ERR_INVALID;
+  *out = ctx->tm;
+  return PRC_OK;
+}
+
+int32_t prc_device_image(prc_ctx* ctx, uint64_t* dev_ptr, uint64_t* bytes) {
+  if (!ctx || !ctx->d_image.p) return PRC_ERR_INVALID;
+  *dev_ptr = (uint64_t)(uintptr_t)ctx->d_image.p;
+  *bytes = (uint64_t)ctx->W * ctx->H * 4;
+  return PRC_OK;
+}
+
+int32_t prc_device_shadowmap(prc_ctx* ctx, uint32_t light, uint64_t* dev_ptr, uint64_t* bytes) {
+  if (!ctx || light >= ctx->d_shadow.size() || !ctx->d_shadow[light].p) return PRC_ERR_INVALID;
+  *dev_ptr = (uint64_t)(uintptr_t)ctx->d_shadow[light].p;
+  *bytes = (uint64_t)ctx->W * ctx->H * 4;
+  return PRC_OK;
+}
+
+int32_t prc_stream(prc_ctx* ctx, uint64_t* stream) {
+  if (!ctx) return PRC_ERR_INVALID;
+  *stream = (uint64_t)(uintptr_t)ctx->stream;
+  return PRC_OK;
+}
+
+int32_t prc_sync(prc_ctx* ctx) {
+  if (!ctx) return PRC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PRC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,832 @@
+// prc_kernels.cuh — sm_100a kernels of the render pass. See DESIGN.md for the pipeline.
+//
+// Pipeline of one frame (all on one stream):
+//   [per casting light]  k_geom_raster<SHADOW>  -> small triangles rasterised in-thread with atomicMax on
+//                                                  the shadow map, large ones queued as setup records
+//                        k_bin_count/k_scan/k_bin_fill/k_tile_raster<SHADOW> for the queued records
+//   k_geom_raster<CAMERA>  -> visibility keys (depth, ~draw sequence) by 64-bit atomicMax; clip queue; large queue
+//   k_clip_raster          -> Sutherland-Hodgman fan for triangles straddling the viewport
+//   k_bin_* / k_tile_raster<CAMERA>
+//   k_resolve              -> key -> G-buffer attributes (4 x float4 per pixel)
+//   k_shade_special, k_shade -> Blinn-Phong + shadow lookup + AO + gamma -> RGBA8 (image order)
+#pragma once
+#include "../../include/polyred_cuda.h"
+#include "prc_math.cuh"
+
+namespace prc {
+
+#define PRC_TILE 16
+#define PRC_SMALL_MAX_PIXELS 36  // bbox area up to which a triangle is rasterised by its own thread
+
+struct DevScene {
+  const float* pos;
+  const float* nor;
+  const float* uv;
+  const uint32_t* col;
+  const int32_t* mat;
+  const uint32_t* meta;  // bit31 = !IsValid, bits 0..23 = object index
+  uint64_t n_tris;
+  const prc_material* mats;
+  uint32_t n_mats;
+  const uint32_t* tex_first;
+  const uint32_t* level_w;
+  const uint32_t* level_h;
+  const uint64_t* level_off;
+  const uint8_t* tex_data;
+};
+
+struct DevLight {
+  uint32_t kind, cast_shadow;
+  float pos[3];
+  float intensity;
+  uint32_t color;
+  float view[16], proj[16];
+  float* shadow_map;  // W*H floats (persistent)
+};
+
+struct DevFrame {
+  int W, H;
+  int row0, row1;  // rows shaded by this context
+  int rr0, rr1;    // rows rasterised (row0/row1 widened by the AO halo)
+  uint32_t flags;
+  uint32_t n_lights, n_ambient;
+  uint32_t background;
+  float viewport[16], viewport_inv[16], proj_inv[16], view_inv[16], vtw[16];
+  float cam[3];
+  const prc_object_xf* xf;   // per object trans / normal
+  const DevLight* lights;
+  const float* ambient;
+  const uint8_t* gamma;
+};
+
+struct LargeRec {  // setup record of a triangle handed to the tile path (48 B)
+  float x1, y1, z1, x2, y2, z2, x3, y3, z3;
+  uint32_t seq;
+  short bx0, by0, bx1, by1;  // clamped pixel bbox, inclusive
+};
+
+struct Counters {
+  unsigned int n_large;
+  unsigned int n_clip;
+  unsigned int large_overflow;
+  unsigned int n_bin_total;
+  unsigned long long n_nan;
+  unsigned long long n_valid;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Triangle setup shared by every stage (render/raster.go:380-444, render/shadow.go:152-178)
+// ---------------------------------------------------------------------------------------------
+struct ScreenTri {
+  V4 p1, p2, p3;  // after Apply(Viewport).Pos()
+  float cw1, cw2, cw3;  // clip-space W of the three vertices (for recipw)
+};
+
+enum { TRI_CULLED = 0, TRI_DIRECT = 1, TRI_CLIP = 2 };
+
+// transform + viewport + back-face + AABB tests. `clip_allowed`=false is the shadow pass (no clipping,
+// cullViewFrustum only — render/cull.go:15-24).
+template <bool E>
+__device__ __forceinline__ int tri_setup(const float* __restrict__ trans, const float* __restrict__ viewport, float Wf, float Hf,
+                                         const float* p, bool clip_allowed, ScreenTri& s) {
+  V4 a = mulv(trans, V4{p[0], p[1], p[2], 1.0f});
+  V4 b = mulv(trans, V4{p[3], p[4], p[5], 1.0f});
+  V4 c = mulv(trans, V4{p[6], p[7], p[8], 1.0f});
+  s.cw1 = a.w; s.cw2 = b.w; s.cw3 = c.w;
+  s.p1 = pos4(apply4<E>(a, viewport));
+  s.p2 = pos4(apply4<E>(b, viewport));
+  s.p3 = pos4(apply4<E>(c, viewport));
+  // cullBackFace (render/cull.go:26-28)
+  V4 e1 = sub4(s.p2, s.p1), e2 = sub4(s.p3, s.p1);
+  if (fma32<E>(e1.x, e2.y, -(e1.y * e2.x)) < 0.0f) return TRI_CULLED;
+  // AABB.Intersect with the viewport box (geometry/primitive/box.go:32-41; maxZ uses Max.Y of the receiver)
+  float mnx = go_min3(s.p1.x, s.p2.x, s.p3.x), mxx = go_max3(s.p1.x, s.p2.x, s.p3.x);
+  float mny = go_min3(s.p1.y, s.p2.y, s.p3.y), mxy = go_max3(s.p1.y, s.p2.y, s.p3.y);
+  float mnz = go_min3(s.p1.z, s.p2.z, s.p3.z), mxz = go_max3(s.p1.z, s.p2.z, s.p3.z);
+  float minX = go_max(0.0f, mnx), minY = go_max(0.0f, mny), minZ = go_max(-1.0f, mnz);
+  float maxX = go_min(Wf, mxx), maxY = go_min(Hf, mxy), maxZ = go_min(Hf, mxz);
+  if (!(minX <= maxX && minY <= maxY && minZ <= maxZ)) return TRI_CULLED;
+  if (!clip_allowed) return TRI_DIRECT;
+  // AABB.Contains for the three vertices (box.go:61-75)
+  bool in = true;
+  const V4* vs[3] = {&s.p1, &s.p2, &s.p3};
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const V4& v = *vs[i];
+    in = in && less_eq(0.0f, v.x) && less_eq(0.0f, v.y) && less_eq(-1.0f, v.z) && less_eq(v.x, Wf) && less_eq(v.y, Hf) && less_eq(v.z, 1.0f);
+  }
+  return in ? TRI_DIRECT : TRI_CLIP;
+}
+
+// pixel bbox of drawClipped/drawDepth (raster.go:473-477): int(Round(min)-1) .. int(Round(max)+1), clamped
+__device__ __forceinline__ bool pixel_bbox(const V4& p1, const V4& p2, const V4& p3, int W, int r0, int r1, int& x0, int& y0, int& x1, int& y1) {
+  float mnx = go_min3(p1.x, p2.x, p3.x), mxx = go_max3(p1.x, p2.x, p3.x);
+  float mny = go_min3(p1.y, p2.y, p3.y), mxy = go_max3(p1.y, p2.y, p3.y);
+  long long xa = go_int(roundf(mnx) - 1.0f), xb = go_int(roundf(mxx) + 1.0f);
+  long long ya = go_int(roundf(mny) - 1.0f), yb = go_int(roundf(mxy) + 1.0f);
+  if (xa < 0) xa = 0;
+  if (ya < r0) ya = r0;
+  if (xb > W - 1) xb = W - 1;
+  if (yb > r1 - 1) yb = r1 - 1;
+  x0 = (int)xa; y0 = (int)ya; x1 = (int)xb; y1 = (int)yb;
+  return xa <= xb && ya <= yb;
+}
+
+// ---- Sutherland-Hodgman in screen space (render/clipping.go:18-65) ----
+template <bool E>
+__device__ __forceinline__ bool in_front(const V4& ppos, const V4& pnor, const V4& v) { return dot4<E>(sub4(v, ppos), pnor) > 0.0f; }
+template <bool E>
+__device__ __forceinline__ V4 isect(const V4& ppos, const V4& pnor, const V4& v0, const V4& v1) {
+  V4 u = sub4(v1, v0);
+  V4 w = sub4(v0, ppos);
+  float d = dot4<E>(pnor, u);
+  float n = -dot4<E>(pnor, w);
+  float s = __fdiv_rn(n, d);
+  return add4(v0, V4{u.x * s, u.y * s, u.z * s, u.w * s});
+}
+template <bool E>
+__device__ int clip_polygon(const ScreenTri& t, float Wf, float Hf, V4* out /*[12]*/) {
+  V4 a[12], b[12];
+  int na = 3;
+  a[0] = t.p1; a[1] = t.p2; a[2] = t.p3;
+  for (int k = 0; k < 6; k++) {
+    V4 ppos, pnor;
+    switch (k) {
+      case 0: ppos = V4{Wf, 0, 0, 1}; pnor = V4{-1, 0, 0, 1}; break;
+      case 1: ppos = V4{0, 0, 0, 1}; pnor = V4{1, 0, 0, 1}; break;
+      case 2: ppos = V4{0, Hf, 0, 1}; pnor = V4{0, -1, 0, 1}; break;
+      case 3: ppos = V4{0, 0, 0, 1}; pnor = V4{0, 1, 0, 1}; break;
+      case 4: ppos = V4{0, 0, 1, 1}; pnor = V4{0, 0, -1, 1}; break;
+      default: ppos = V4{0, 0, -1, 1}; pnor = V4{0, 0, 1, 1}; break;
+    }
+    if (na == 0) return 0;
+    int nb = 0;
+    V4 s = a[na - 1];
+    for (int i = 0; i < na; i++) {
+      V4 e = a[i];
+      bool ein = in_front<E>(ppos, pnor, e), sin_ = in_front<E>(ppos, pnor, s);
+      if (ein) {
+        if (!sin_ && nb < 12) b[nb++] = isect<E>(ppos, pnor, s, e);
+        if (nb < 12) b[nb++] = e;
+      } else if (sin_) {
+        if (nb < 12) b[nb++] = isect<E>(ppos, pnor, s, e);
+      }
+      s = e;
+    }
+    na = nb;
+    for (int i = 0; i < nb; i++) a[i] = b[i];
+  }
+  for (int i = 0; i < na; i++) out[i] = a[i];
+  return na;
+}
+// position of one fan vertex (clipping.go:80-85): barycentric of the clip point w.r.t. the original triangle
+template <bool E>
+__device__ __forceinline__ void clip_bary(const ScreenTri& t, const V4& c, float b[3]) {
+  BarySetup bs = bary_setup<E>(t.p1.x, t.p1.y, t.p2.x, t.p2.y, t.p3.x, t.p3.y);
+  bary_eval<E>(bs, c.x, c.y, b[0], b[1], b[2]);
+}
+__device__ __forceinline__ V4 clip_pos(const ScreenTri& t, const float b[3]) {
+  return V4{b[0] * t.p1.x + b[1] * t.p2.x + b[2] * t.p3.x, b[0] * t.p1.y + b[1] * t.p2.y + b[2] * t.p3.y,
+            b[0] * t.p1.z + b[1] * t.p2.z + b[2] * t.p3.z, 1.0f};
+}
+
+// ---------------------------------------------------------------------------------------------
+// in-thread rasterisation of one (small) screen triangle
+// ---------------------------------------------------------------------------------------------
+template <bool E, bool SHADOW>
+__device__ __forceinline__ void raster_one(const V4& p1, const V4& p2, const V4& p3, int x0, int y0, int x1, int y1, uint32_t seq, int W,
+                                           unsigned long long* __restrict__ keys, float* __restrict__ smap, Counters* cnt) {
+  BarySetup bs = bary_setup<E>(p1.x, p1.y, p2.x, p2.y, p3.x, p3.y);
+  for (int y = y0; y <= y1; y++) {
+    float py = (float)y + 0.5f;
+    for (int x = x0; x <= x1; x++) {
+      float px = (float)x + 0.5f;
+      float w1, w2, w3;
+      bary_eval<E>(bs, px, py, w1, w2, w3);
+      if (w1 < -PRC_EPS || w2 < -PRC_EPS || w3 < -PRC_EPS) continue;
+      float z = w1 * p1.z + w2 * p2.z + w3 * p3.z;
+      if (isnan(z)) { atomicAdd(&cnt->n_nan, 1ULL); continue; }
+      size_t idx = (size_t)y * W + x;
+      if (SHADOW) {
+        // shadowDepthTest (shadow.go:221-228): store iff !(z <= stored); stored starts at 0 and only grows,
+        // so only z > 0 can ever be stored and positive floats order like their int bits.
+        if (z > 0.0f && z > smap[idx]) atomicMax((int*)&smap[idx], __float_as_int(z));
+      } else {
+        unsigned long long key = ((unsigned long long)depth_key(z) << 32) | (unsigned long long)(0xFFFFFFFFu - seq);
+        if (key > keys[idx]) atomicMax(&keys[idx], key);
+      }
+    }
+  }
+}
+
+// pixel (0,0) is needed on every rank (uncovered pixels shade G(0,0), raster.go:326): when the raster rows do
+// not include row 0 it is evaluated separately.
+template <bool E>
+__device__ __forceinline__ void raster_pixel00(const V4& p1, const V4& p2, const V4& p3, uint32_t seq, unsigned long long* keys, Counters* cnt) {
+  int x0, y0, x1, y1;
+  if (!pixel_bbox(p1, p2, p3, 1, 0, 1, x0, y0, x1, y1)) return;
+  raster_one<E, false>(p1, p2, p3, 0, 0, 0, 0, seq, 1 << 30, keys, nullptr, cnt);
+}
+
+template <bool E, bool SHADOW>
+__device__ __forceinline__ void emit_tri(const V4& p1, const V4& p2, const V4& p3, uint32_t seq, const DevFrame& F, int r0, int r1,
+                                         unsigned long long* keys, float* smap, LargeRec* large, unsigned int large_cap, Counters* cnt) {
+  int x0, y0, x1, y1;
+  if (!SHADOW && r0 > 0) raster_pixel00<E>(p1, p2, p3, seq, keys, cnt);
+  if (!pixel_bbox(p1, p2, p3, F.W, r0, r1, x0, y0, x1, y1)) return;
+  int area = (x1 - x0 + 1) * (y1 - y0 + 1);
+  if (area <= PRC_SMALL_MAX_PIXELS) {
+    raster_one<E, SHADOW>(p1, p2, p3, x0, y0, x1, y1, seq, F.W, keys, smap, cnt);
+  } else {
+    unsigned int slot = atomicAdd(&cnt->n_large, 1u);
+    if (slot >= large_cap) { atomicExch(&cnt->large_overflow, 1u); return; }
+    LargeRec r;
+    r.x1 = p1.x; r.y1 = p1.y; r.z1 = p1.z; r.x2 = p2.x; r.y2 = p2.y; r.z2 = p2.z; r.x3 = p3.x; r.y3 = p3.y; r.z3 = p3.z;
+    r.seq = seq; r.bx0 = (short)x0; r.by0 = (short)y0; r.bx1 = (short)x1; r.by1 = (short)y1;
+    large[slot] = r;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: per-triangle transform / cull / classify / small raster.  One thread per triangle; positions are staged
+// through shared memory with 128-bit loads (the [n][9] float layout is not 16-byte aligned per triangle).
+// ---------------------------------------------------------------------------------------------
+#define PRC_GEOM_THREADS 256
+template <bool E, bool SHADOW>
+__global__ void __launch_bounds__(PRC_GEOM_THREADS) k_geom_raster(DevScene S, DevFrame F, const float* __restrict__ shadow_trans /*[n_obj][16]*/,
+                                                                     unsigned long long* keys, float* smap, LargeRec* large, unsigned int large_cap,
+                                                                     unsigned int* clipq, unsigned int clip_cap, Counters* cnt) {
+  __shared__ __align__(16) float sp[PRC_GEOM_THREADS * 9];
+  const unsigned long long base = (unsigned long long)blockIdx.x * PRC_GEOM_THREADS;
+  const unsigned long long nleft = S.n_tris - base;
+  const int nt = nleft < PRC_GEOM_THREADS ? (int)nleft : PRC_GEOM_THREADS;
+  {
+    // base*9 floats = base*36 bytes, base is a multiple of 256 -> 16-byte aligned
+    const float4* src = reinterpret_cast<const float4*>(S.pos + base * 9);
+    float4* dst = reinterpret_cast<float4*>(sp);
+    const int nvec = (nt * 9) / 4;
+    for (int i = threadIdx.x; i < nvec; i += PRC_GEOM_THREADS) dst[i] = __ldg(src + i);
+    for (int i = nvec * 4 + threadIdx.x; i < nt * 9; i += PRC_GEOM_THREADS) sp[i] = S.pos[base * 9 + i];
+  }
+  __syncthreads();
+  if ((int)threadIdx.x >= nt) return;
+  const unsigned long long tri = base + threadIdx.x;
+  const uint32_t meta = S.meta[tri];
+  if (meta & 0x80000000u) return;  // !IsValid
+  const uint32_t obj = meta & 0x00FFFFFFu;
+  const float* trans = SHADOW ? (shadow_trans + (size_t)obj * 16) : F.xf[obj].trans;
+  float p[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) p[i] = sp[threadIdx.x * 9 + i];
+  ScreenTri st;
+  int cls = tri_setup<E>(trans, F.viewport, (float)F.W, (float)F.H, p, !SHADOW, st);
+  if (cls == TRI_CULLED) return;
+  if (cls == TRI_CLIP) {
+    unsigned int slot = atomicAdd(&cnt->n_clip, 1u);
+    if (slot < clip_cap) clipq[slot] = (unsigned int)tri;
+    else atomicExch(&cnt->large_overflow, 1u);
+    return;
+  }
+  const int r0 = SHADOW ? F.row0 : F.rr0, r1 = SHADOW ? F.row1 : F.rr1;
+  emit_tri<E, SHADOW>(st.p1, st.p2, st.p3, (uint32_t)tri * 8u, F, r0, r1, keys, smap, large, large_cap, cnt);
+}
+
+// K2: triangles straddling the viewport: clip, fan, emit (raster.go:438-443)
+template <bool E>
+__global__ void k_clip_raster(DevScene S, DevFrame F, const unsigned int* __restrict__ clipq, unsigned long long* keys, LargeRec* large,
+                              unsigned int large_cap, Counters* cnt) {
+  unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned int n = cnt->n_clip;
+  if (i >= n) return;
+  const unsigned int tri = clipq[i];
+  const uint32_t obj = S.meta[tri] & 0x00FFFFFFu;
+  float p[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) p[k] = S.pos[(size_t)tri * 9 + k];
+  ScreenTri st;
+  tri_setup<E>(F.xf[obj].trans, F.viewport, (float)F.W, (float)F.H, p, true, st);
+  V4 poly[12];
+  int nc = clip_polygon<E>(st, (float)F.W, (float)F.H, poly);
+  if (nc < 3) return;
+  float b0[3];
+  clip_bary<E>(st, poly[0], b0);
+  V4 q0 = clip_pos(st, b0);
+  for (int k = 2; k < nc && k <= 8; k++) {
+    float b1[3], b2[3];
+    clip_bary<E>(st, poly[k - 1], b1);
+    clip_bary<E>(st, poly[k], b2);
+    V4 q1 = clip_pos(st, b1), q2 = clip_pos(st, b2);
+    emit_tri<E, false>(q0, q1, q2, tri * 8u + (uint32_t)(k - 1), F, F.rr0, F.rr1, keys, nullptr, large, large_cap, cnt);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile path for large triangles: bin count -> scan -> fill -> per-tile raster (one thread per pixel)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_bin_count(const LargeRec* __restrict__ large, const Counters* cnt, unsigned int cap, int tiles_x, unsigned int* tile_count) {
+  const unsigned int n = min(cnt->n_large, cap);
+  const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const LargeRec r = large[warp];
+  const int tx0 = r.bx0 / PRC_TILE, tx1 = r.bx1 / PRC_TILE, ty0 = r.by0 / PRC_TILE, ty1 = r.by1 / PRC_TILE;
+  const int nx = tx1 - tx0 + 1, nt = nx * (ty1 - ty0 + 1);
+  for (int t = lane; t < nt; t += 32) atomicAdd(&tile_count[(ty0 + t / nx) * tiles_x + tx0 + t % nx], 1u);
+}
+// exclusive scan of tile_count -> tile_start (single block; <= 130k tiles at 8K)
+__global__ void k_scan(const unsigned int* __restrict__ in, unsigned int* out, unsigned int* cursor, int n, Counters* cnt) {
+  __shared__ unsigned int part[1024];
+  const int per = (n + 1023) / 1024;
+  const int b = threadIdx.x * per, e = min(n, b + per);
+  unsigned int s = 0;
+  for (int i = b; i < e; i++) s += in[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    unsigned int v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  unsigned int run = threadIdx.x ? part[threadIdx.x - 1] : 0;
+  for (int i = b; i < e; i++) { out[i] = run; cursor[i] = run; run += in[i]; }
+  if (threadIdx.x == 1023) { out[n] = part[1023]; cnt->n_bin_total = part[1023]; }
+}
+__global__ void k_bin_fill(const LargeRec* __restrict__ large, const Counters* cnt, unsigned int cap, int tiles_x, unsigned int* cursor,
+                           unsigned int* bins, unsigned int bins_cap) {
+  const unsigned int n = min(cnt->n_large, cap);
+  const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const LargeRec r = large[warp];
+  const int tx0 = r.bx0 / PRC_TILE, tx1 = r.bx1 / PRC_TILE, ty0 = r.by0 / PRC_TILE, ty1 = r.by1 / PRC_TILE;
+  const int nx = tx1 - tx0 + 1, nt = nx * (ty1 - ty0 + 1);
+  for (int t = lane; t < nt; t += 32) {
+    unsigned int slot = atomicAdd(&cursor[(ty0 + t / nx) * tiles_x + tx0 + t % nx], 1u);
+    if (slot < bins_cap) bins[slot] = warp;
+  }
+}
+
+struct TileRec {
+  BarySetup bs;
+  float z1, z2, z3;
+  uint32_t seq;
+  short bx0, by0, bx1, by1;
+};
+template <bool E, bool SHADOW>
+__global__ void __launch_bounds__(PRC_TILE * PRC_TILE) k_tile_raster(const LargeRec* __restrict__ large, const unsigned int* __restrict__ tile_start,
+                                                                      const unsigned int* __restrict__ bins, int tiles_x, int W, int H, int r0, int r1,
+                                                                      unsigned long long* keys, float* smap, Counters* cnt) {
+  const int tile = blockIdx.x;
+  const unsigned int b = tile_start[tile], e = tile_start[tile + 1];
+  if (b == e) return;
+  __shared__ TileRec recs[128];
+  const int tx = tile % tiles_x, ty = tile / tiles_x;
+  const int x = tx * PRC_TILE + (threadIdx.x & (PRC_TILE - 1)), y = ty * PRC_TILE + (threadIdx.x / PRC_TILE);
+  const float px = (float)x + 0.5f, py = (float)y + 0.5f;
+  const bool live = x < W && y >= r0 && y < r1;
+  unsigned long long best = 0;
+  float bestz = 0.0f;
+  unsigned long long nan_local = 0;
+  for (unsigned int base = b; base < e; base += 128) {
+    const int nb = min(128u, e - base);
+    __syncthreads();
+    if ((int)threadIdx.x < nb) {
+      const LargeRec r = large[bins[base + threadIdx.x]];
+      TileRec t;
+      t.bs = bary_setup<E>(r.x1, r.y1, r.x2, r.y2, r.x3, r.y3);
+      t.z1 = r.z1; t.z2 = r.z2; t.z3 = r.z3; t.seq = r.seq;
+      t.bx0 = r.bx0; t.by0 = r.by0; t.bx1 = r.bx1; t.by1 = r.by1;
+      recs[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (!live) continue;
+    for (int j = 0; j < nb; j++) {
+      const TileRec& t = recs[j];
+      if (x < t.bx0 || x > t.bx1 || y < t.by0 || y > t.by1) continue;
+      float w1, w2, w3;
+      bary_eval<E>(t.bs, px, py, w1, w2, w3);
+      if (w1 < -PRC_EPS || w2 < -PRC_EPS || w3 < -PRC_EPS) continue;
+      float z = w1 * t.z1 + w2 * t.z2 + w3 * t.z3;
+      if (isnan(z)) { nan_local++; continue; }
+      if (SHADOW) {
+        if (z > bestz) bestz = z;
+      } else {
+        unsigned long long key = ((unsigned long long)depth_key(z) << 32) | (unsigned long long)(0xFFFFFFFFu - t.seq);
+        if (key > best) best = key;
+      }
+    }
+  }
+  if (nan_local) atomicAdd(&cnt->n_nan, nan_local);
+  if (!live) return;
+  const size_t idx = (size_t)y * W + x;
+  if (SHADOW) {
+    if (bestz > 0.0f && bestz > smap[idx]) atomicMax((int*)&smap[idx], __float_as_int(bestz));
+  } else {
+    if (best > keys[idx]) atomicMax(&keys[idx], best);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: resolve — visibility key -> fragment attributes (drawClipped, raster.go:462-572)
+// G-buffer layout: 4 x float4 per pixel
+//   ga = (depth, u, v, du)  gb = (dv, nx, ny, nz)  gc = (fx, fy, fz, wx)  gd = (wy, wz, col bits, mat bits)
+// ---------------------------------------------------------------------------------------------
+struct Frag {
+  bool ok;
+  int X, Y;
+  float depth, u, v, du, dv;
+  V4 nor, facenor, wpos;
+  uint32_t col;
+  int32_t mat;
+};
+
+struct VtxAttr { V4 pos, nor; float u, v; uint32_t col; };
+
+template <bool E>
+__device__ void resolve_fragment(const DevScene& S, const DevFrame& F, uint32_t seq, int x, int y, Frag& f) {
+  const uint32_t tri = seq >> 3, sub = seq & 7u;
+  const uint32_t obj = S.meta[tri] & 0x00FFFFFFu;
+  const float* trans = F.xf[obj].trans;
+  const float* nrm = F.xf[obj].normal;
+  float p[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) p[k] = __ldg(S.pos + (size_t)tri * 9 + k);
+  ScreenTri st;
+  tri_setup<E>(trans, F.viewport, (float)F.W, (float)F.H, p, true, st);
+  const bool persp = (F.flags & PRC_FRAME_PERSPECT) != 0;
+  float rw1 = 1.0f, rw2 = 1.0f, rw3 = 1.0f;
+  if (persp) { rw1 = __fdiv_rn(-1.0f, st.cw1); rw2 = __fdiv_rn(-1.0f, st.cw2); rw3 = __fdiv_rn(-1.0f, st.cw3); }
+  VtxAttr v[3];
+  v[0].pos = st.p1; v[1].pos = st.p2; v[2].pos = st.p3;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const float* n = S.nor + (size_t)tri * 9 + k * 3;
+    v[k].nor = apply4<E>(V4{__ldg(n), __ldg(n + 1), __ldg(n + 2), 0.0f}, nrm);
+    v[k].u = __ldg(S.uv + (size_t)tri * 6 + k * 2);
+    v[k].v = __ldg(S.uv + (size_t)tri * 6 + k * 2 + 1);
+    v[k].col = __ldg(S.col + (size_t)tri * 3 + k);
+  }
+  const int32_t material_id = __ldg(S.mat + tri);
+  if (sub != 0) {
+    // clipTriangle (clipping.go:67-157): fan vertex attributes by screen-space barycentrics of the parent
+    V4 poly[12];
+    clip_polygon<E>(st, (float)F.W, (float)F.H, poly);
+    const int which[3] = {0, (int)sub, (int)sub + 1};
+    VtxAttr c[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      float b[3];
+      clip_bary<E>(st, poly[which[k]], b);
+      c[k].pos = clip_pos(st, b);
+      c[k].u = b[0] * v[0].u + b[1] * v[1].u + b[2] * v[2].u;
+      c[k].v = b[0] * v[0].v + b[1] * v[1].v + b[2] * v[2].v;
+      c[k].nor = V4{b[0] * v[0].nor.x + b[1] * v[1].nor.x + b[2] * v[2].nor.x, b[0] * v[0].nor.y + b[1] * v[1].nor.y + b[2] * v[2].nor.y,
+                    b[0] * v[0].nor.z + b[1] * v[1].nor.z + b[2] * v[2].nor.z, 0.0f};
+      uint32_t cc = 0;
+#pragma unroll
+      for (int ch = 0; ch < 4; ch++)
+        cc |= go_u8(clampf(b[0] * (float)chan(v[0].col, ch) + b[1] * (float)chan(v[1].col, ch) + b[2] * (float)chan(v[2].col, ch), 0.0f, 255.0f)) << (8 * ch);
+      c[k].col = cc;
+    }
+    v[0] = c[0]; v[1] = c[1]; v[2] = c[2];
+  }
+  // un-project without dividing by W (raster.go:467-469)
+  V4 m1 = apply4<E>(apply4<E>(apply4<E>(v[0].pos, F.viewport_inv), F.proj_inv), F.view_inv);
+  V4 m2 = apply4<E>(apply4<E>(apply4<E>(v[1].pos, F.viewport_inv), F.proj_inv), F.view_inv);
+  V4 m3 = apply4<E>(apply4<E>(apply4<E>(v[2].pos, F.viewport_inv), F.proj_inv), F.view_inv);
+  f.facenor = unit4<E>(cross4<E>(sub4(m2, m1), sub4(m3, m1)));
+  BarySetup bs = bary_setup<E>(v[0].pos.x, v[0].pos.y, v[1].pos.x, v[1].pos.y, v[2].pos.x, v[2].pos.y);
+  const float px = (float)x + 0.5f, py = (float)y + 0.5f;
+  float b0, b1, b2;
+  bary_eval<E>(bs, px, py, b0, b1, b2);
+  f.ok = true; f.X = x; f.Y = y;
+  f.depth = b0 * v[0].pos.z + b1 * v[1].pos.z + b2 * v[2].pos.z;
+  float wc1 = rw1 * b0, wc2 = rw2 * b1, wc3 = rw3 * b2;
+  float norm = 1.0f;
+  if (persp) norm = __fdiv_rn(1.0f, (wc1 + wc2 + wc3));
+  f.u = (wc1 * v[0].u + wc2 * v[1].u + wc3 * v[2].u) * norm;
+  f.v = (wc1 * v[0].v + wc2 * v[1].v + wc3 * v[2].v) * norm;
+  f.du = 0.0f; f.dv = 0.0f;
+  if (material_id >= 0) {  // raster.go:517-535
+    float x0, x1, x2, y0, y1, y2;
+    bary_eval<E>(bs, px + 1.0f, py, x0, x1, x2);
+    float wc1x = rw1 * x0, wc2x = rw2 * x1, wc3x = rw3 * x2;
+    float normx = __fdiv_rn(1.0f, (wc1x + wc2x + wc3x));
+    bary_eval<E>(bs, px, py + 1.0f, y0, y1, y2);
+    float wc1y = rw1 * y0, wc2y = rw2 * y1, wc3y = rw3 * y2;
+    float normy = __fdiv_rn(1.0f, (wc1y + wc2y + wc3y));
+    float uvdU = (wc1x * v[0].u + wc2x * v[1].u + wc3x * v[2].u) * normx;
+    float uvdX = (wc1x * v[0].v + wc2x * v[1].v + wc3x * v[2].v) * normx;
+    float uvdV = (wc1y * v[0].u + wc2y * v[1].u + wc3y * v[2].u) * normy;
+    float uvdY = (wc1y * v[0].v + wc2y * v[1].v + wc3y * v[2].v) * normy;
+    f.du = (uvdU - f.u) * (uvdU - f.u) + (uvdX - f.v) * (uvdX - f.v);
+    f.dv = (uvdV - f.u) * (uvdV - f.u) + (uvdY - f.v) * (uvdY - f.v);
+  }
+  f.nor = unit4<E>(V4{b0 * v[0].nor.x + b1 * v[1].nor.x + b2 * v[2].nor.x, b0 * v[0].nor.y + b1 * v[1].nor.y + b2 * v[2].nor.y,
+                      b0 * v[0].nor.z + b1 * v[1].nor.z + b2 * v[2].nor.z, 0.0f});
+  f.wpos = V4{b0 * m1.x + b1 * m2.x + b2 * m3.x, b0 * m1.y + b1 * m2.y + b2 * m3.y, b0 * m1.z + b1 * m2.z + b2 * m3.z, 1.0f};
+  uint32_t col = 0;
+#pragma unroll
+  for (int ch = 0; ch < 4; ch++)
+    col |= go_u8(clampf((wc1 * (float)chan(v[0].col, ch) + wc2 * (float)chan(v[1].col, ch) + wc3 * (float)chan(v[2].col, ch)) * norm, 0.0f, 255.0f)) << (8 * ch);
+  f.col = col;
+  f.mat = material_id;
+}
+
+struct GBuf {
+  float4 *ga, *gb, *gc, *gd;
+  float* ao_depth;  // ok ? depth : -1 (material/ao.go:56-63)
+};
+
+__device__ __forceinline__ void gbuf_store(const GBuf& G, size_t idx, const Frag& f) {
+  G.ga[idx] = make_float4(f.depth, f.u, f.v, f.du);
+  G.gb[idx] = make_float4(f.dv, f.nor.x, f.nor.y, f.nor.z);
+  G.gc[idx] = make_float4(f.facenor.x, f.facenor.y, f.facenor.z, f.wpos.x);
+  G.gd[idx] = make_float4(f.wpos.y, f.wpos.z, __uint_as_float(f.col), __int_as_float(f.mat));
+}
+__device__ __forceinline__ void gbuf_load(const GBuf& G, size_t idx, Frag& f) {
+  float4 a = G.ga[idx], b = G.gb[idx], c = G.gc[idx], d = G.gd[idx];
+  f.depth = a.x; f.u = a.y; f.v = a.z; f.du = a.w; f.dv = b.x;
+  f.nor = V4{b.y, b.z, b.w, 0.0f};
+  f.facenor = V4{c.x, c.y, c.z, 0.0f};
+  f.wpos = V4{c.w, d.x, d.y, 1.0f};
+  f.col = __float_as_uint(d.z);
+  f.mat = __float_as_int(d.w);
+}
+
+template <bool E>
+__global__ void __launch_bounds__(128) k_resolve(DevScene S, DevFrame F, const unsigned long long* __restrict__ keys, GBuf G) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = F.rr0 + blockIdx.y * 4 + (threadIdx.x >> 5);
+  if (x >= F.W || y >= F.rr1) return;
+  const size_t idx = (size_t)y * F.W + x;
+  const unsigned long long key = keys[idx];
+  if (key == 0) {
+    if (G.ao_depth) G.ao_depth[idx] = -1.0f;
+    return;
+  }
+  Frag f;
+  resolve_fragment<E>(S, F, 0xFFFFFFFFu - (uint32_t)key, x, y, f);
+  gbuf_store(G, idx, f);
+  if (G.ao_depth) G.ao_depth[idx] = f.depth;
+}
+// pixel (0,0) when it lies outside the rasterised rows (multi-GPU strips)
+template <bool E>
+__global__ void k_resolve00(DevScene S, DevFrame F, const unsigned long long* __restrict__ keys, GBuf G) {
+  const unsigned long long key = keys[0];
+  if (key == 0) return;
+  Frag f;
+  resolve_fragment<E>(S, F, 0xFFFFFFFFu - (uint32_t)key, 0, 0, f);
+  gbuf_store(G, 0, f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: deferred shading (render/raster.go:324-359, shader/blinn_cpu.go:24-106, buffer/texture.go:83-187,
+//     render/shadow.go:230-283, material/ao.go:20-73, shader/gamma.go:13-18)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rgba_at(const DevScene& S, uint32_t lvl, long long x, long long y) {
+  const long long w = S.level_w[lvl], h = S.level_h[lvl];
+  if (x < 0 || y < 0 || x >= w || y >= h) return 0u;
+  return __ldg(reinterpret_cast<const uint32_t*>(S.tex_data + S.level_off[lvl]) + (size_t)y * w + x);
+}
+__device__ uint32_t query_bilinear(const DevScene& S, uint32_t lvl, float u, float v) {
+  const long long dx = S.level_w[lvl], dy = S.level_h[lvl];
+  if (dx == 1 && dy == 1) return rgba_at(S, lvl, 0, 0);
+  float x = u * ((float)dx - 1.0f), y = v * ((float)dy - 1.0f);
+  float x0 = floorf(x), y0 = floorf(y);
+  long long i = go_int(x0), j = go_int(y0);
+  uint32_t p1 = rgba_at(S, lvl, i, j);
+  uint32_t p2 = (i < dx - 1) ? rgba_at(S, lvl, i + 1, j) : p1;
+  uint32_t i1 = lerpc(p1, p2, x - x0);
+  uint32_t p3 = (j < dy - 1) ? rgba_at(S, lvl, i, j + 1) : p1;
+  uint32_t p4 = (i < dx - 1 && j < dy - 1) ? rgba_at(S, lvl, i + 1, j + 1) : p1;
+  uint32_t i2 = lerpc(p3, p4, x - x0);
+  return lerpc(i1, i2, y - y0);
+}
+__device__ __forceinline__ void go_modf(float f, float& ip, float& fp) {
+  ip = truncf(f);
+  fp = isinf(f) ? NAN : f - ip;  // exact for finite f; Modf(+-Inf) = +-Inf, NaN
+  if (f == 0.0f) fp = f;
+}
+__device__ uint32_t tex_query(const DevScene& S, const prc_material& m, float lod, float u, float v) {
+  const uint32_t first = S.tex_first[m.texture];
+  const int nlev = (int)(S.tex_first[m.texture + 1] - first);
+  float iu, iv;
+  go_modf(u, iu, u);
+  if (iu != 0.0f && u == 0.0f) u = 1.0f;
+  if (u < 0.0f) u = 1.0f - u;
+  go_modf(v, iv, v);
+  if (iv != 0.0f && v == 0.0f) v = 1.0f;
+  if (v < 0.0f) v = 1.0f - v;
+  if (m.flags & PRC_MAT_NO_MIPMAP) {
+    float dx = (float)S.level_w[first], dy = (float)S.level_h[first];
+    if (dx == 1.0f && dy == 1.0f) return rgba_at(S, first, 0, 0);
+    return rgba_at(S, first, go_int(floorf(u * (dx - 1.0f))), go_int(floorf(v * (dy - 1.0f))));
+  }
+  if (lod < 0.0f) lod = 0.0f;
+  else if (lod >= (float)nlev) lod = (float)(nlev - 1);
+  if (lod <= 1.0f) return query_bilinear(S, first, u, v);
+  lod -= 1.0f;
+  long long h = go_int(floorf(lod));
+  long long l = h + 1;
+  if (l >= nlev) return query_bilinear(S, first + (uint32_t)h, u, v);
+  float p = lod - (float)h;
+  if (approx_eq(p, 0.0f)) return query_bilinear(S, first + (uint32_t)h, u, v);
+  uint32_t L1 = query_bilinear(S, first + (uint32_t)h, u, v);
+  uint32_t L2 = query_bilinear(S, first + (uint32_t)l, u, v);
+  return lerpc(L1, L2, p);
+}
+// math.Log2 via float64 (math/math.go:122-124); Go: Frexp, exact for powers of two, else Log(frac)*(1/Ln2)+exp
+__device__ __forceinline__ float go_log2(float x) {
+  int e;
+  double fr = frexp((double)x, &e);
+  if (fr == 0.5) return (float)(e - 1);
+  return (float)(log(fr) * (1.0 / 0.693147180559945309417232121458176568) + (double)e);
+}
+__device__ __forceinline__ float go_pow(float x, float y) { return (float)pow((double)x, (double)y); }
+
+template <bool E>
+__device__ uint32_t fragment_shader(const DevScene& S, const DevFrame& F, const prc_material& m, const Frag& info) {
+  float lod = 0.0f;
+  if (!(m.flags & PRC_MAT_NO_MIPMAP)) {
+    float siz = (float)S.level_w[S.tex_first[m.texture]] * __fsqrt_rn(go_max(info.du, info.dv));
+    if (siz < 1.0f) siz = 1.0f;
+    lod = go_log2(siz);
+  }
+  const uint32_t col = tex_query(S, m, lod, info.u, 1.0f - info.v);
+  if (F.n_lights == 0) return col;
+  const float cr = (float)chan(col, 0), cg = (float)chan(col, 1), cb = (float)chan(col, 2);
+  float LaR = 0, LaG = 0, LaB = 0;
+  for (uint32_t e = 0; e < F.n_ambient; e++) {
+    const float I = F.ambient[e];
+    LaR += I * cr; LaG += I * cg; LaB += I * cb;
+  }
+  float LdR = 0, LdG = 0, LdB = 0, LsR = 0, LsG = 0, LsB = 0;
+  const V4 n = (m.flags & PRC_MAT_FLAT_SHADING) ? info.facenor : info.nor;
+  const V4 x = info.wpos;
+  const V4 Vv = unit4<E>(sub4(V4{F.cam[0], F.cam[1], F.cam[2], 1.0f}, x));
+  for (uint32_t li = 0; li < F.n_lights; li++) {
+    const DevLight& l = F.lights[li];
+    V4 L = V4{0, 0, 0, 0};
+    float I = 0.0f;
+    if (l.kind == PRC_LIGHT_POINT) {
+      V4 Ldir = sub4(V4{l.pos[0], l.pos[1], l.pos[2], 1.0f}, x);
+      float ln = len4<E>(Ldir);
+      float inv = __fdiv_rn(1.0f, ln);
+      L = V4{Ldir.x * inv, Ldir.y * inv, Ldir.z * inv, Ldir.w * inv};
+      I = __fdiv_rn(l.intensity, ln);
+    } else if (l.kind == PRC_LIGHT_DIRECTIONAL) {
+      L = V4{l.pos[0] * -1.0f, l.pos[1] * -1.0f, l.pos[2] * -1.0f, 0.0f};
+      I = l.intensity;
+    }
+    V4 Hh = unit4<E>(add4(L, Vv));
+    float Ld = clampf(dot4<E>(n, L), 0.0f, 1.0f);
+    float Ls = go_pow(clampf(dot4<E>(n, Hh), 0.0f, 1.0f), m.shininess);
+    LdR += Ld * cr * I; LdG += Ld * cg * I; LdB += Ld * cb * I;
+    LsR += Ls * (float)chan(l.color, 0) * I; LsG += Ls * (float)chan(l.color, 1) * I; LsB += Ls * (float)chan(l.color, 2) * I;
+  }
+  float r = roundf(LaR + __fdiv_rn((float)chan(m.diffuse_rgba, 0) * LdR, 255.0f) + __fdiv_rn((float)chan(m.specular_rgba, 0) * LsR, 255.0f));
+  float g = roundf(LaG + __fdiv_rn((float)chan(m.diffuse_rgba, 1) * LdG, 255.0f) + __fdiv_rn((float)chan(m.specular_rgba, 1) * LsG, 255.0f));
+  float b = roundf(LaB + __fdiv_rn((float)chan(m.diffuse_rgba, 2) * LdB, 255.0f) + __fdiv_rn((float)chan(m.specular_rgba, 2) * LsB, 255.0f));
+  return go_u8(clampf(r, 0.0f, 255.0f)) | (go_u8(clampf(g, 0.0f, 255.0f)) << 8) | (go_u8(clampf(b, 0.0f, 255.0f)) << 16) |
+         (go_u8(clampf((float)chan(col, 3), 0.0f, 255.0f)) << 24);
+}
+
+template <bool E>
+__device__ bool shading_visibility(const DevFrame& F, const DevLight& l, const Frag& info) {
+  if (!l.cast_shadow) return true;
+  V4 sc = pos4(apply4<E>(apply4<E>(apply4<E>(apply4<E>(V4{(float)info.X, (float)info.Y, info.depth, 1.0f}, F.vtw), l.view), l.proj), F.viewport));
+  long long lx = go_int(sc.x), ly = go_int(sc.y);
+  long long idx = (long long)((unsigned long long)lx + (unsigned long long)ly * (unsigned long long)F.W);
+  if (idx > 0 && idx < (long long)F.W * F.H) {
+    float shadowZ = l.shadow_map[idx];
+    if (sc.z < shadowZ - 0.03f) return true;
+  }
+  return false;
+}
+
+struct AoConsts { float cosv[8], sinv[8]; float half_pi, four_pi; };
+
+__device__ float max_elevation(const DevFrame& F, const float* __restrict__ ao_depth, int X, int Y, float dirX, float dirY) {
+  // max over t of Atan(e_t/d_t) == Atan(max over t of e_t/d_t): Atan and the float32 rounding are monotone and
+  // Go's Max is NaN-propagating on both sides, so one atan per direction reproduces ao.go:40-73 exactly.
+  const float pxf = (float)X, pyf = (float)Y;
+  float m = 0.0f;
+  const float traceDepth = ao_depth[(size_t)Y * F.W + X];
+  for (int ti = 0; ti < 100; ti++) {
+    const float t = (float)ti;
+    float cx = pxf + dirX * t, cy = pyf + dirY * t;
+    long long ix = go_int(cx), iy = go_int(cy);
+    if (ix < 0 || iy < 0 || ix >= F.W || iy >= F.H) break;
+    float dxv = pxf - cx, dyv = pyf - cy;
+    // Vec4.Len of (dx, dy, 0, 0): FMA(dx,dx, FMA(dy,dy, FMA(0,0, 0*0)))
+    float dist = __fsqrt_rn(fma32<true>(dxv, dxv, fma32<true>(dyv, dyv, 0.0f)));
+    if (dist < 1.0f) continue;
+    float elevation = ao_depth[(size_t)iy * F.W + ix] - traceDepth;
+    m = go_max(m, __fdiv_rn(elevation, dist));
+  }
+  return (float)atan((double)m);
+}
+__device__ uint32_t ao_shade(const DevFrame& F, const AoConsts& A, const float* __restrict__ ao_depth, int X, int Y, uint32_t col) {
+  float total = 0.0f;
+#pragma unroll 1
+  for (int k = 0; k < 8; k++) total += A.half_pi - max_elevation(F, ao_depth, X, Y, A.cosv[k], A.sinv[k]);
+  total = __fdiv_rn(total, A.four_pi);
+  total = go_pow(total, 10000.0f);
+  return go_u8(total * (float)chan(col, 0)) | (go_u8(total * (float)chan(col, 1)) << 8) | (go_u8(total * (float)chan(col, 2)) << 16) | (col & 0xff000000u);
+}
+
+__device__ __forceinline__ const prc_material* mat_at(const DevScene& S, int32_t id) {  // gpudeferred.go:77-82
+  if (id < 0 || (uint32_t)id >= S.n_mats) return nullptr;
+  const prc_material* m = S.mats + id;
+  return (m->flags & PRC_MAT_NIL) ? nullptr : m;
+}
+
+// (*Renderer).shade for a fragment `frag` (own X,Y,mat) whose G-buffer record is `info`
+template <bool E>
+__device__ uint32_t shade_pixel(const DevScene& S, const DevFrame& F, const AoConsts& A, const float* ao_depth, const Frag& info, int fragX, int fragY,
+                                int32_t frag_mat) {
+  uint32_t col = info.col;
+  const prc_material* mat = mat_at(S, frag_mat);
+  if (mat != nullptr) {
+    col = fragment_shader<E>(S, F, *mat, info);
+    if ((F.flags & PRC_FRAME_SHADOWMAP) && (mat->flags & PRC_MAT_RECEIVE_SHADOW)) {
+      float visibles = 0.0f;
+      for (uint32_t i = 0; i < F.n_lights; i++)
+        if (shading_visibility<E>(F, F.lights[i], info)) visibles += 1.0f;
+      float w = go_pow(0.5f, visibles);
+      col = go_u8((float)chan(col, 0) * w) | (go_u8((float)chan(col, 1) * w) << 8) | (go_u8((float)chan(col, 2) * w) << 16) | (col & 0xff000000u);
+    }
+    if (mat->flags & PRC_MAT_AMBIENT_OCCLUSION) col = ao_shade(F, A, ao_depth, fragX, fragY, col);
+  }
+  return col;
+}
+
+// special[0] = colour of pixel (0,0) (pre-gamma), special[1] = colour of every uncovered pixel (bug-list 3:
+// an uncovered pixel carries a zero Fragment, so shade() reads G(0,0) with MaterialID 0 — raster.go:326-332)
+template <bool E>
+__global__ void k_shade_special(DevScene S, DevFrame F, AoConsts A, const unsigned long long* __restrict__ keys, GBuf G, uint32_t* special) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (keys[0] == 0) {
+    special[0] = F.background;
+    special[1] = F.background;
+    return;
+  }
+  Frag info;
+  gbuf_load(G, 0, info);
+  info.ok = true; info.X = 0; info.Y = 0;
+  uint32_t c00 = shade_pixel<E>(S, F, A, G.ao_depth, info, 0, 0, info.mat);
+  special[0] = c00;
+  info.col = c00;  // UnsafeSet wrote the shaded colour back into fragments[(0,0)] (raster_screen.go:86)
+  special[1] = shade_pixel<E>(S, F, A, G.ao_depth, info, 0, 0, 0);
+}
+
+template <bool E>
+__global__ void __launch_bounds__(128) k_shade(DevScene S, DevFrame F, AoConsts A, const unsigned long long* __restrict__ keys, GBuf G,
+                                               const uint32_t* __restrict__ special, uint32_t* __restrict__ image) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = F.row0 + blockIdx.y * 4 + (threadIdx.x >> 5);
+  if (x >= F.W || y >= F.row1) return;
+  const size_t idx = (size_t)y * F.W + x;
+  uint32_t col;
+  if (x == 0 && y == 0) col = special[0];
+  else if (keys[idx] == 0) col = special[1];
+  else {
+    Frag info;
+    gbuf_load(G, idx, info);
+    info.ok = true; info.X = x; info.Y = y;
+    col = shade_pixel<E>(S, F, A, G.ao_depth, info, x, y, info.mat);
+  }
+  if (F.flags & PRC_FRAME_GAMMA)
+    col = (uint32_t)F.gamma[chan(col, 0)] | ((uint32_t)F.gamma[chan(col, 1)] << 8) | ((uint32_t)F.gamma[chan(col, 2)] << 16) | (col & 0xff000000u);
+  image[(size_t)(F.H - 1 - y) * F.W + x] = col;  // image row r = screen y = H-1-r (buffer.go:225)
+}
+
+// ---------------------------------------------------------------------------------------------
+// upload-time kernels
+// ---------------------------------------------------------------------------------------------
+// Triangle.IsValid (geometry/primitive/triangle.go:63-80); always evaluated with the exact FMA.
+__global__ void k_validate(const float* __restrict__ pos, const uint64_t* __restrict__ obj_start, uint32_t n_obj, uint64_t n, uint32_t* meta,
+                           unsigned long long* n_valid) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // object of triangle i: binary search over obj_start
+  uint32_t lo = 0, hi = n_obj;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (obj_start[mid] <= i) lo = mid; else hi = mid;
+  }
+  const float* p = pos + i * 9;
+  V4 p1{p[0], p[1], p[2], 1.0f}, p2{p[3], p[4], p[5], 1.0f}, p3{p[6], p[7], p[8], 1.0f};
+  V4 a = sub4(p2, p1), b = sub4(p3, p1);
+  bool valid = true;
+  if (approx_eq(a.x, 0.0f) && approx_eq(a.y, 0.0f) && approx_eq(a.z, 0.0f)) valid = false;
+  if (approx_eq(b.x, 0.0f) && approx_eq(b.y, 0.0f) && approx_eq(b.z, 0.0f)) valid = false;
+  if (valid) {
+    float d = __fdiv_rn(dot4<true>(a, b), (len4<true>(a) * len4<true>(b)));
+    valid = !approx_eq(d, 1.0f) && !approx_eq(d, -1.0f);
+  }
+  meta[i] = lo | (valid ? 0u : 0x80000000u);
+  if (valid) atomicAdd(n_valid, 1ULL);
+}
+
+}  // namespace prc

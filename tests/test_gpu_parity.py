@@ -1,0 +1,88 @@
+"""-m gpu: CUDA path vs the CPU oracle on identical inputs, through the C ABI (libpolyred_cuda.so)."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from polyred_b200 import camera, light, material, render, scene, synth
+from parity_util import assert_bit_exact, assert_north_star_gate, compare_frames, make_renderers
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _exact(monkeypatch):
+    monkeypatch.setenv("PRC_FMA", "exact")
+
+
+def _report(name, st):
+    print(f"\n[{name}] " + " ".join(f"{k}={v}" for k, v in st.items()))
+
+
+def test_c1_mesh_point_light():
+    """BASELINE config 1 (reduced mesh): one closed mesh, point light + ambient, no shadows."""
+    s, cam = synth.mesh_scene(subdiv=60, aspect=1.6)
+    g, c = make_renderers(s, cam, 400, 250)
+    st, ig, ic = compare_frames(g, c, 400, 250)
+    _report("c1", st)
+    assert_bit_exact(st)
+    assert st["rgba_px_diff"] == 0, st
+
+
+def test_c2_shadow_ao_gamma_clipped_ground():
+    """BASELINE config 2 (reduced): mesh + ground quad that straddles the viewport (clip path),
+    non-casting directional + casting point light, shadow map, AO, gamma."""
+    s, cam = synth.mesh_scene(subdiv=40, with_ground=True, shadows=True, ao=True)
+    g, c = make_renderers(s, cam, 320, 200, shadow=True, gamma=True)
+    st, ig, ic = compare_frames(g, c, 320, 200, n_lights_cast=(1,))
+    _report("c2", st)
+    assert_bit_exact(st)
+    assert st["shadow1_written"] > 0
+    # AO goes through atan/pow(.,10000) in float64 on both sides (libm vs CUDA): allow 1 LSB
+    assert_north_star_gate(st)
+
+
+def test_c3_city_eight_lights_four_casting():
+    """BASELINE config 3 (reduced): ground heightfield + instanced meshes, 8 materials, 8 point
+    lights of which 4 cast shadows; micro-triangles dominate."""
+    s, cam = synth.city_scene(n_objects=25, obj_stacks=20, obj_slices=20, ground_cells=60, tex_size=64)
+    g, c = make_renderers(s, cam, 480, 270, shadow=True, gamma=True)
+    st, ig, ic = compare_frames(g, c, 480, 270, n_lights_cast=(0, 2, 4, 6))
+    _report("c3", st)
+    assert_bit_exact(st)
+    assert_north_star_gate(st)
+    assert st["rgba_px_diff"] == 0, st
+
+
+def test_persistent_shadow_maps_and_second_frame():
+    """Shadow maps are never cleared by Render() (render/shadow.go:221-228): a second frame of a
+    static scene is identical, and prc_shadow_reset zeroes them."""
+    s, cam = synth.city_scene(n_objects=9, obj_stacks=10, obj_slices=10, ground_cells=20, tex_size=32)
+    g, c = make_renderers(s, cam, 240, 135, shadow=True)
+    a = g.Render()
+    b = g.Render()
+    assert np.array_equal(a, b)
+    assert np.array_equal(a, c.Render())
+
+
+def test_fast_fma_mode_within_gate(monkeypatch):
+    """PRC_FMA=fast uses single-rounding fmaf where the reference uses a float64 FMA rounded to
+    float32: the north_star gate (not bit-exactness) is asserted and the tie count reported."""
+    monkeypatch.setenv("PRC_FMA", "fast")
+    s, cam = synth.city_scene(n_objects=25, obj_stacks=20, obj_slices=20, ground_cells=60, tex_size=64)
+    g, c = make_renderers(s, cam, 480, 270, shadow=True, gamma=True)
+    st, ig, ic = compare_frames(g, c, 480, 270, n_lights_cast=(0, 2, 4, 6))
+    _report("c3-fast", st)
+    assert_north_star_gate(st, tie_budget=8)
+
+
+def test_errors_surface_no_fallback():
+    from polyred_b200._lib import PolyredCudaError, CudaBackend
+    from polyred_b200 import _abi as A
+    import ctypes as C
+    be = CudaBackend(0)
+    fr = A.prc_frame(abi_version=A.PRC_ABI_VERSION, width=16, height=16, row1=16)
+    with pytest.raises(PolyredCudaError):
+        be._check(be.L.prc_render(be.h, C.byref(fr), None))  # no scene uploaded
+    be.close()
