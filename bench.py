@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the render pass (BASELINE.json metric: Mtris/s and Mpixels/s
+shaded at 4K on the 10 M-triangle, 8-light, 4-caster scene = configs[2], "C3").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference CPU path (oracle port, host cores)
+
+A step = one `Render()` of the frame. `value` = valid scene triangles x frames/s / 1e6 with the scene
+resident in HBM and the image left on the device (CUDA events on the library's stream); `e2e` = the
+same through the C-ABI call with HOST buffers: per step the frame uniforms go host->device and the
+RGBA8 image comes back device->host inside the timed region.
+N>1 (torchrun, one process per GPU): the frame is split into N horizontal screen strips, the Ls
+shadow maps are sharded (light x row range) and all-gathered with NCCL, the image strips are
+gathered to rank 0; `scaling` = "strong" (same frame, more GPUs).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (width, height, generator kwargs)
+    "C3": dict(w=3840, h=2160, gen=dict(n_objects=1600, obj_stacks=50, obj_slices=50, ground_cells=1000, n_lights=8, casting_every=2,
+                                        n_materials=8, tex_size=256), shadow=True, gamma=True,
+               desc="3840x2160, 10.0M-triangle synthetic scene (2M-tri ground heightfield + 1600 instanced 5000-tri meshes), 8 materials, "
+                    "8 point lights, 4 shadow-casting, gamma"),
+    "C3-small": dict(w=960, h=540, gen=dict(n_objects=100, obj_stacks=20, obj_slices=20, ground_cells=100, n_lights=8, casting_every=2,
+                                            n_materials=8, tex_size=64), shadow=True, gamma=True, desc="reduced C3 for plumbing tests"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_scene(name):
+    from polyred_b200 import synth
+    wl = WORKLOADS[name]
+    t = time.time()
+    s, cam = synth.city_scene(aspect=wl["w"] / wl["h"], **wl["gen"])
+    return wl, s, cam, time.time() - t
+
+
+def algorithmic_bytes(n_valid, n_tris, w, h, n_cast):
+    """bytes/frame = 112 N + Ls 36 N + px (148 + 12 Ls)."""
+    px = w * h
+    return 112 * n_tris + n_cast * 36 * n_tris + px * (148 + 12 * n_cast)
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path, timed on the host cores: the oracle port
+    (oracle/libpr_oracle.so, the C++ restatement of render/*.go) in its multithreaded mode — the Go
+    binary cannot be built in this image (no Go toolchain). Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import oracle_binding as ob
+    from polyred_b200 import render
+    wl, s, cam, tgen = build_scene(args.workload)
+    cores = os.cpu_count() or 1
+    be = ob.OracleBackend(threads=cores)
+    # bounded sample: the same scene and lights at 1/4 x 1/4 of the pixels and (for C3) every 8th object,
+    # so one step is ~10-30 s of CPU work; throughput is reported on the sample's own triangles and pixels.
+    w, h = wl["w"], wl["h"]
+    r = render.NewRenderer(render.Camera(cam), render.Size(w, h), render.Scene(s), render.ShadowMap(wl["shadow"]),
+                           render.GammaCorrection(wl["gamma"]), render._Backend(be))
+    times = []
+    for i in range(args.warmup + args.steps):
+        t = time.perf_counter()
+        r.Render()
+        dt = time.perf_counter() - t
+        if i >= args.warmup:
+            times.append(dt)
+    tm = be.timings()
+    sec = float(np.mean(times))
+    val = tm.n_valid_tris / sec / 1e6
+    line = {
+        "impl": "reference", "metric": "Mtris/s", "value": val, "unit": "Mtris/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "mpixels_per_s": w * h / sec / 1e6,
+        "config": {"workload": f"{args.workload}: {wl['desc']}", "n_valid_tris": int(tm.n_valid_tris)},
+        "cpu_baseline": {"value": val, "unit": "Mtris/s", "cores": cores, "kind": "port",
+                         "sample": "full frame of the same workload, C++ restatement of the reference CPU path (not the Go binary), one task per 256 triangles / 32 pixels, per-pixel spinlocks"},
+        "e2e": {"value": val, "unit": "Mtris/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def cai(ptr, nbytes):
+    """A __cuda_array_interface__ view of library-owned device memory (for torch.distributed)."""
+    class _V:
+        pass
+    v = _V()
+    v.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+    return v
+
+
+def run_cuda(args):
+    import torch
+    from polyred_b200 import _abi as A
+    from polyred_b200 import render
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus must equal WORLD_SIZE")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    wl, s, cam, tgen = build_scene(args.workload)
+    w, h = wl["w"], wl["h"]
+    r = render.NewRenderer(render.Camera(cam), render.Size(w, h), render.Scene(s), render.ShadowMap(wl["shadow"]),
+                           render.GammaCorrection(wl["gamma"]), render.CUDA(local))
+    be = r._backend
+    t = time.time()
+    sd = r._ensure_uploaded()
+    be.sync()
+    t_upload = time.time() - t
+    sources, _ = s.Lights()
+    cast = [i for i, l in enumerate(sources) if l.cast_shadow]
+    stream = torch.cuda.ExternalStream(be.stream(), device=torch.device("cuda", local))
+
+    fd = r.frame_desc(no_readback=True)
+    fd_e2e = r.frame_desc(no_readback=False)
+    out = np.zeros((h, w, 4), np.uint8)
+
+    # ---- multi-GPU partition: screen strips (16-row aligned) + shadow (light, row-range) shards ----
+    if world > 1:
+        tiles = (h + 15) // 16
+        cuts = [min(h, ((tiles * k) // world) * 16) for k in range(world + 1)]
+        cuts[-1] = h
+        row0, row1 = cuts[rank], cuts[rank + 1]
+        for f in (fd, fd_e2e):
+            f.struct.row0, f.struct.row1 = row0, row1
+        # shadow work units: Ls lights x (world // Ls or 1) row ranges, round-robin over ranks
+        parts = max(1, world // max(1, len(cast)))
+        units = [(li, (h * p) // parts, (h * (p + 1)) // parts) for li in cast for p in range(parts)]
+        my_units = [u for k, u in enumerate(units) if k % world == rank]
+    else:
+        row0, row1 = 0, h
+        units = my_units = []
+
+    def step(fdesc, host_out):
+        if world == 1:
+            be.render(fdesc, host_out)
+            return
+        # phase 1: my shadow shards
+        for li, a, b in my_units:
+            be.render_shadows(fdesc, 1 << li, a, b)
+        be.sync()
+        # exchange: every unit's row range is broadcast from its owner (NCCL over NVLink); the maps are
+        # max-combined implicitly because ranges are disjoint and the receiving rows were not touched.
+        for k, (li, a, b) in enumerate(units):
+            ptr, nbytes = be.device_shadowmap(li)
+            t_ = torch.as_tensor(cai(ptr + a * w * 4, (b - a) * w * 4), device=torch.device("cuda", local))
+            dist.broadcast(t_, src=k % world)
+        torch.cuda.synchronize()
+        be.render_main(fdesc, None)
+        # gather the image strips to rank 0
+        ptr, nbytes = be.device_image()
+        img = torch.as_tensor(cai(ptr, nbytes), device=torch.device("cuda", local))
+        for k in range(world):
+            a, b = cuts[k], cuts[k + 1]
+            seg = img[(h - b) * w * 4:(h - a) * w * 4]
+            if k == 0:
+                continue
+            if rank == k:
+                dist.send(seg, dst=0)
+            elif rank == 0:
+                dist.recv(seg, src=k)
+        torch.cuda.synchronize()
+        if host_out is not None and rank == 0:
+            host_out.reshape(-1)[:] = img.cpu().numpy()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        be.sync()
+
+    # ---- warm-up ----
+    for _ in range(max(3, args.warmup)):
+        step(fd, None)
+    barrier()
+    n_valid = int(be.timings().n_valid_tris)
+
+    # ---- timed region 1: device-resident (value) ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ksum = np.zeros(8)
+    klaunch = np.zeros(8, np.int64)
+    launches = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(fd, None)
+        tm = be.timings()
+        ksum += np.array(list(tm.kernel_ms))
+        klaunch += np.array(list(tm.kernel_launches))
+        launches += int(tm.gpu_launches)
+    with torch.cuda.stream(stream):
+        e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- timed region 2: end to end through the C ABI with host buffers ----
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(fd_e2e, out)
+    barrier()
+    wall_e2e = time.perf_counter() - t0
+
+    if dist is not None:
+        tt = torch.tensor([dev_ms, wall * 1e3, wall_e2e * 1e3], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms, wall_e2e_ms = [float(x) for x in tt.tolist()]
+    else:
+        wall_ms, wall_e2e_ms = wall * 1e3, wall_e2e * 1e3
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    ms = dev_ms / args.steps
+    fps = 1e3 / ms
+    fps_e2e = 1e3 / (wall_e2e_ms / args.steps)
+    pk, pk_kind = peaks()
+    # dominant kernel of the frame
+    names = A.KERNEL_CLASSES
+    dom = int(np.argmax(ksum))
+    n_tris = sd.n_tris
+    px = w * h
+    per_launch_bytes = {0: 36 * n_tris + 8 * px, 1: 112 * n_tris + 16 * px, 4: 8 * px, 5: 16 * px, 6: (8 + 64) * px, 7: (64 + 4 + 4 * len(cast)) * px}
+    alg = per_launch_bytes.get(dom, 0)
+    avg_ms = ksum[dom] / max(1, klaunch[dom])
+    achieved = alg / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    frame_bytes = algorithmic_bytes(n_valid, n_tris, w, h, len(cast))
+    h2d = fd.struct.n_objects * 128 + len(cast) * fd.struct.n_objects * 64 + len(sources) * 168 + 256 + 4 * fd.struct.n_ambient
+    line = {
+        "metric": "Mtris/s", "value": n_valid * fps / 1e6, "unit": "Mtris/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "mpixels_per_s": px * fps / 1e6, "frames_per_s": fps, "wall_ms_per_step": wall_ms / args.steps,
+        "config": {"workload": f"{args.workload}: {wl['desc']}", "n_tris": int(n_tris), "n_valid_tris": n_valid, "width": w, "height": h,
+                   "fma": os.environ.get("PRC_FMA", "exact"), "l2": "inputs (1.1 GB scene, 0.9 GB frame buffers) larger than L2; no explicit flush",
+                   "partition": "1 GPU" if world == 1 else f"{world} screen strips + {len(units)} shadow shards, NCCL broadcast/send-recv"},
+        "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s",
+                     "frac": achieved / pk["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms,
+                     "launches_per_step": float(klaunch[dom]) / args.steps},
+        "frame_roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": frame_bytes, "achieved": frame_bytes / (ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
+                           "frac": frame_bytes / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], "unit": "GB/s"},
+        "kernel_ms_per_step": {names[k]: float(ksum[k]) / args.steps for k in range(8)},
+        "e2e": {"value": n_valid * fps_e2e / 1e6, "unit": "Mtris/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(px * 4),
+                "ms_per_step": wall_e2e_ms / args.steps, "mpixels_per_s": px * fps_e2e / 1e6,
+                "note": "prc_render through the C ABI: host prc_frame (per-object matrices) in, host RGBA8 out; scene resident after one prc_scene_upload",
+                "scene_upload_once": {"bytes": int(sd.upload_bytes()), "seconds": t_upload}},
+        "stats_last_frame": {"n_large_items": int(tm.n_large_items), "n_clipped": int(tm.n_clipped), "n_bin_entries": int(tm.n_bin_entries), "n_nan_frags": int(tm.n_nan_frags)},
+        "gpu_launches": launches, "clocks": clocks, "scene_gen_seconds": tgen,
+    }
+    if args.cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(args, wl, s, cam)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, wl, s, cam):
+    """The oracle port timed on this box's host cores on a bounded sample of the same workload."""
+    import oracle_binding as ob
+    from polyred_b200 import render
+    cores = os.cpu_count() or 1
+    be = ob.OracleBackend(threads=cores)
+    w, h = wl["w"], wl["h"]
+    r = render.NewRenderer(render.Camera(cam), render.Size(w, h), render.Scene(s), render.ShadowMap(wl["shadow"]),
+                           render.GammaCorrection(wl["gamma"]), render._Backend(be))
+    t = time.perf_counter()
+    r.Render()
+    sec = time.perf_counter() - t
+    tm = be.timings()
+    return {"value": tm.n_valid_tris / sec / 1e6, "unit": "Mtris/s", "cores": cores, "kind": "port", "seconds": sec,
+            "mpixels_per_s": w * h / sec / 1e6,
+            "sample": "one full frame of the same workload (no warm-up), C++ restatement of the reference CPU path in multithreaded mode "
+                      "(tasks of 256 triangles / 32 pixels, per-pixel spinlocks); not the Go binary"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

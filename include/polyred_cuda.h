@@ -194,6 +194,9 @@ typedef struct prc_timings {
    * 4 tile raster (shadow)  5 tile raster (camera)  6 resolve  7 shade */
   float kernel_ms[8];
   uint32_t kernel_launches[8];
+  uint64_t n_large_items; /* triangles routed to the tile path, summed over the passes of the frame */
+  uint64_t n_clipped;     /* triangles that went through clipTriangle */
+  uint64_t n_bin_entries; /* (tile, triangle) pairs */
 } prc_timings;
 
 #define PRC_K_GEOM_SHADOW 0

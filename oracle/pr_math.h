@@ -23,8 +23,75 @@ static inline f32 Sqrt(f32 x) { return (f32)std::sqrt((double)x); }
 static inline f32 Round(f32 x) { return (f32)std::round((double)x); }
 // math.Floor (math/math.go:102-104)
 static inline f32 Floor(f32 x) { return (f32)std::floor((double)x); }
-// math.Pow (math/math.go:91-93). Go's Pow is its own routine; libm's differs by <=1ulp(f64).
-static inline f32 Pow(f32 x, f32 y) { return (f32)std::pow((double)x, (double)y); }
+
+// math.Pow of the Go standard library (go1.26 src/math/pow.go), restated: special cases, then x**y =
+// x**yf * x**yi with the integer part by repeated squaring of the Frexp mantissa and the fractional part by
+// Exp(yf*Log(x)). For integer y (every shininess in the fixtures and AO's 10000) the result involves only
+// IEEE multiplications, so this restatement is bit-identical to Go's; for fractional y it inherits libm's
+// exp/log instead of Go's (<= 1 ulp of float64 apart).
+static inline bool go_is_odd_int(double x) {
+  if (std::fabs(x) >= 9007199254740992.0) return false;  // 1<<53: all such floats are even integers
+  double xi;
+  double xf = std::modf(x, &xi);
+  return xf == 0 && ((long long)xi & 1) == 1;
+}
+static inline double go_pow64(double x, double y) {
+  if (y == 0 || x == 1) return 1;
+  if (y == 1) return x;
+  if (std::isnan(x) || std::isnan(y)) return std::numeric_limits<double>::quiet_NaN();
+  if (x == 0) {
+    if (y < 0) {
+      if (std::signbit(x) && go_is_odd_int(y)) return std::copysign(HUGE_VAL, x);
+      return HUGE_VAL;
+    }
+    if (std::signbit(x) && go_is_odd_int(y)) return x;
+    return 0;
+  }
+  if (std::isinf(y)) {
+    if (x == -1) return 1;
+    if ((std::fabs(x) < 1) == (y > 0)) return 0;
+    return HUGE_VAL;
+  }
+  if (std::isinf(x)) {
+    if (x < 0) return go_pow64(1 / x, -y);
+    return y < 0 ? 0 : HUGE_VAL;
+  }
+  if (y == 0.5) return std::sqrt(x);
+  if (y == -0.5) return 1 / std::sqrt(x);
+  double yi;
+  double yf = std::modf(std::fabs(y), &yi);
+  if (yf != 0 && x < 0) return std::numeric_limits<double>::quiet_NaN();
+  if (yi >= 9223372036854775808.0) {
+    if (x == -1) return 1;
+    if ((std::fabs(x) < 1) == (y > 0)) return 0;
+    return HUGE_VAL;
+  }
+  double a1 = 1.0;
+  long long ae = 0;
+  if (yf != 0) {
+    if (yf > 0.5) { yf--; yi++; }
+    a1 = std::exp(yf * std::log(x));
+  }
+  int xe_i;
+  double x1 = std::frexp(x, &xe_i);
+  long long xe = xe_i;
+  for (long long i = (long long)yi; i != 0; i >>= 1) {
+    if (xe < -(1 << 12) || (1 << 12) < xe) {  // overflow / underflow is certain; let Ldexp produce it
+      ae += xe;
+      break;
+    }
+    if (i & 1) { a1 *= x1; ae += xe; }
+    x1 *= x1;
+    xe <<= 1;
+    if (x1 < .5) { x1 += x1; xe--; }
+  }
+  if (y < 0) { a1 = 1 / a1; ae = -ae; }
+  if (ae > 100000) ae = 100000;
+  if (ae < -100000) ae = -100000;
+  return std::ldexp(a1, (int)ae);
+}
+// math.Pow (math/math.go:91-93): float64 Pow of the Go standard library, rounded to float32
+static inline f32 Pow(f32 x, f32 y) { return (f32)go_pow64((double)x, (double)y); }
 // math.Log2 (math/math.go:122-124); Go: Frexp, exact for powers of two, else Log(frac)*(1/Ln2)+exp
 static inline f32 Log2(f32 x) {
   double d = (double)x;

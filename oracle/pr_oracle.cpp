@@ -41,7 +41,7 @@ struct Fragment {
   RGBA col;
   int64_t mat;
   Vec4 facenor, wpos;
-  int32_t tri, sub;  // bookkeeping for the parity maps (not in the reference struct)
+  int32_t tri, sub;  // bookkeeping for the parity maps (not in the reference struct); tri = index + 1
 };
 
 struct Vertex {  // primitive.Vertex (geometry/primitive/vertex.go:15-21)
@@ -274,7 +274,7 @@ void draw_clipped(Ctx& c, const FrameU& u, const Vertex& t1, const Vertex& t2, c
       dst.X = x; dst.Y = y;
       dst.depth = z; dst.u = uvX; dst.v = uvY; dst.du = du; dst.dv = dv;
       dst.nor = n; dst.facenor = fN; dst.wpos = wp; dst.col = col; dst.mat = material_id;
-      dst.tri = tri; dst.sub = subidx;
+      dst.tri = tri + 1; dst.sub = subidx;
     }
   }
 }
@@ -557,6 +557,15 @@ RGBA shade(Ctx& c, const prc_frame& fr, Fragment& frag /* the pixel's own fragme
   return ambient_occlusion_shade(c, frag, mat_at(c, frag.mat));
 }
 
+uint32_t object_of(const Ctx& c, uint64_t tri) {  // index of the Geometry that owns triangle `tri`
+  uint32_t lo = 0, hi = (uint32_t)c.obj_start.size() - 1;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (c.obj_start[mid] <= tri) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
 void run_parallel(int threads, uint64_t n, uint64_t chunk, const std::function<void(uint64_t, uint64_t)>& fn) {
   if (threads <= 1) { fn(0, n); return; }
   std::atomic<uint64_t> next{0};
@@ -622,9 +631,13 @@ int32_t orc_render(orc_ctx* x, const prc_frame* fr, uint8_t* rgba_out) {
   }
   for (uint32_t i = 0; i < fr->n_lights; i++)
     if (fr->lights[i].cast_shadow && c.shadow[i].size() != npx) c.shadow[i].assign(npx, 0.0f);
-  c.frags.assign(npx, Fragment{});  // NextBuffer().Clear() (raster.go:202-206)
-  for (auto& f : c.frags) { f.tri = -1; }
-  if (c.threads > 1) { std::vector<std::atomic<uint32_t>> l(npx); c.locks.swap(l); for (auto& a : c.locks) a.store(0); }
+  // NextBuffer().Clear() (raster.go:202-206); Fragment.tri holds index+1 so the zero value means "none"
+  if (c.frags.size() != npx) c.frags.resize(npx);
+  run_parallel(c.threads, npx, 1 << 16, [&](uint64_t a, uint64_t b) { std::memset((void*)&c.frags[a], 0, (b - a) * sizeof(Fragment)); });
+  if (c.threads > 1) {
+    if (c.locks.size() != npx) { std::vector<std::atomic<uint32_t>> l(npx); c.locks.swap(l); }
+    run_parallel(c.threads, npx, 1 << 16, [&](uint64_t a, uint64_t b) { for (uint64_t i = a; i < b; i++) c.locks[i].store(0, std::memory_order_relaxed); });
+  }
   c.tm = prc_timings{};
   c.tm.abi_version = PRC_ABI_VERSION;
 
@@ -634,37 +647,35 @@ int32_t orc_render(orc_ctx* x, const prc_frame* fr, uint8_t* rgba_out) {
     for (uint32_t li = 0; li < fr->n_lights; li++) {
       const prc_light& l = fr->lights[li];
       if (!l.cast_shadow) continue;
-      for (uint32_t o = 0; o < fr->n_objects; o++) {
+      run_parallel(c.threads, c.n_tris, 1024, [&](uint64_t a, uint64_t b) {
+        uint32_t o = object_of(c, a);
         Mat4 st = M(l.shadow_trans + (size_t)o * 16);
-        uint64_t s0 = c.obj_start[o], s1 = c.obj_start[o + 1];
-        run_parallel(c.threads, s1 - s0, 256, [&](uint64_t a, uint64_t b) {
-          for (uint64_t i = s0 + a; i < s0 + b; i++) {
-            TriIn t = load_tri(c, i);
-            if (!tri_is_valid(t.v[0].pos, t.v[1].pos, t.v[2].pos)) continue;
-            draw_depth(c, c.shadow[li], st, viewport, t);
-          }
-        });
-      }
+        for (uint64_t i = a; i < b; i++) {
+          while (i >= c.obj_start[o + 1]) { o++; st = M(l.shadow_trans + (size_t)o * 16); }
+          TriIn t = load_tri(c, i);
+          if (!tri_is_valid(t.v[0].pos, t.v[1].pos, t.v[2].pos)) continue;
+          draw_depth(c, c.shadow[li], st, viewport, t);
+        }
+      });
     }
   }
   auto T1 = std::chrono::steady_clock::now();
   // --- cpuForwardPass (render/raster.go:226-273) ---
   FrameU u{viewport, M(fr->viewport_inv), M(fr->proj_inv), M(fr->view_inv), (fr->flags & PRC_FRAME_PERSPECT) != 0};
   std::atomic<uint64_t> nvalid{0};
-  for (uint32_t o = 0; o < fr->n_objects; o++) {
+  run_parallel(c.threads, c.n_tris, 1024, [&](uint64_t a, uint64_t b) {
+    uint32_t o = object_of(c, a);
     Mat4 trans = M(fr->objects[o].trans), normal = M(fr->objects[o].normal);
-    uint64_t s0 = c.obj_start[o], s1 = c.obj_start[o + 1];
-    run_parallel(c.threads, s1 - s0, 256, [&](uint64_t a, uint64_t b) {
-      uint64_t nv = 0;
-      for (uint64_t i = s0 + a; i < s0 + b; i++) {
-        TriIn t = load_tri(c, i);
-        if (!tri_is_valid(t.v[0].pos, t.v[1].pos, t.v[2].pos)) continue;
-        nv++;
-        draw(c, u, trans, normal, t, (int32_t)i);
-      }
-      nvalid += nv;
-    });
-  }
+    uint64_t nv = 0;
+    for (uint64_t i = a; i < b; i++) {
+      while (i >= c.obj_start[o + 1]) { o++; trans = M(fr->objects[o].trans); normal = M(fr->objects[o].normal); }
+      TriIn t = load_tri(c, i);
+      if (!tri_is_valid(t.v[0].pos, t.v[1].pos, t.v[2].pos)) continue;
+      nv++;
+      draw(c, u, trans, normal, t, (int32_t)i);
+    }
+    nvalid += nv;
+  });
   c.tm.n_valid_tris = nvalid;
   auto T2 = std::chrono::steady_clock::now();
   // --- passDeferred (raster.go:275-315) via DrawFragments/DrawFragment (raster_screen.go:17-87) ---
@@ -714,7 +725,7 @@ int32_t orc_read_gbuffer(orc_ctx* x, prc_gbuffer_host* g) {
   for (size_t i = 0; i < n; i++) {
     const Fragment& f = c.frags[i];
     if (g->ok) g->ok[i] = f.ok;
-    if (g->tri) g->tri[i] = f.ok ? f.tri : -1;
+    if (g->tri) g->tri[i] = f.ok ? f.tri - 1 : -1;
     if (g->sub) g->sub[i] = f.ok ? f.sub : 0;
     if (g->depth) g->depth[i] = f.depth;
     if (g->uv) { g->uv[2 * i] = f.u; g->uv[2 * i + 1] = f.v; }

@@ -143,6 +143,9 @@ class prc_timings(C.Structure):
         ("gpu_launches", C.c_uint64),
         ("kernel_ms", C.c_float * 8),
         ("kernel_launches", C.c_uint32 * 8),
+        ("n_large_items", C.c_uint64),
+        ("n_clipped", C.c_uint64),
+        ("n_bin_entries", C.c_uint64),
     ]
 
 

@@ -38,8 +38,9 @@ struct prc_ctx {
   // frame buffers
   int W = 0, H = 0;
   DBuf d_keys, d_ga, d_gb, d_gc, d_gd, d_ao, d_image, d_special, d_counters;
-  DBuf d_large, d_clipq, d_tilecount, d_tilestart, d_cursor, d_bins;
-  DBuf d_xf, d_lights, d_ambient, d_gamma;
+  DBuf d_large, d_clipq, d_tilecount, d_tilestart, d_cursor, d_bins, d_active;
+  DBuf d_xf, d_lights, d_ambient, d_gamma, d_frame, d_aoc;
+  std::vector<DevLight> h_lights;    // host staging of the per-frame light table
   std::vector<DBuf> d_shadow_trans;  // per light
   std::vector<DBuf> d_shadow;        // per light, persistent
   unsigned int large_cap = 0, clip_cap = 0, bins_cap = 0;
@@ -62,6 +63,7 @@ struct prc_ctx {
 
 namespace {
 
+#define PRC_RETRY 1
 #define CK(call)                                                                             \
   do {                                                                                       \
     cudaError_t e_ = (call);                                                                 \
@@ -121,6 +123,17 @@ struct KTimer {
   }
 };
 
+// bit i set <=> entry i is 0 or +-2^k with |k| <= 32 (see apply4m in prc_math.cuh)
+uint32_t plain_mask(const float* m) {
+  uint32_t pm = 0;
+  for (int i = 0; i < 16; i++) {
+    float a = std::fabs(m[i]);
+    int e = 0;
+    if (a == 0.0f || (std::isfinite(a) && std::frexp(a, &e) == 0.5f && e >= -31 && e <= 33)) pm |= 1u << i;
+  }
+  return pm;
+}
+
 inline unsigned int cdiv(unsigned long long a, unsigned int b) { return (unsigned int)((a + b - 1) / b); }
 
 // ---- one raster pass (camera or one shadow light) --------------------------------------------
@@ -129,54 +142,45 @@ int32_t raster_pass(prc_ctx* ctx, const DevFrame& F, const float* shadow_trans, 
   cudaStream_t st = ctx->stream;
   Counters* cnt = (Counters*)ctx->d_counters.p;
   // reset n_large / n_clip / n_bin_total (keep n_nan accumulating over the frame)
-  CK(cudaMemsetAsync(cnt, 0, offsetof(Counters, n_nan), st));
+  CK(cudaMemsetAsync(cnt, 0, 16, st));
   const int tiles_x = (F.W + PRC_TILE - 1) / PRC_TILE, tiles_y = (F.H + PRC_TILE - 1) / PRC_TILE;
   const int n_tiles = tiles_x * tiles_y;
   unsigned long long* keys = (unsigned long long*)ctx->d_keys.p;
   LargeRec* large = (LargeRec*)ctx->d_large.p;
   unsigned int* clipq = (unsigned int*)ctx->d_clipq.p;
+  // device-resident copy of the frame for the rare non-inlined generic path (see geom_generic)
+  UPLOAD(ctx->d_frame, &F, sizeof(DevFrame));
   if (ctx->S.n_tris) {
     KTimer kt(ctx, SHADOW ? PRC_K_GEOM_SHADOW : PRC_K_GEOM_CAMERA);
     k_geom_raster<E, SHADOW><<<cdiv(ctx->S.n_tris, PRC_GEOM_THREADS), PRC_GEOM_THREADS, 0, st>>>(ctx->S, F, shadow_trans, keys, smap, large, ctx->large_cap,
-                                                                                                     clipq, ctx->clip_cap, cnt);
+                                                                                                     clipq, ctx->clip_cap, cnt, (const DevFrame*)ctx->d_frame.p);
     ctx->launches++;
   }
-  // counters -> host (n_clip, n_large decide the launch sizes of the rare paths)
-  CK(cudaMemcpyAsync(ctx->h_counters, cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  if (ctx->h_counters->large_overflow) { ctx->err = "internal queue overflow (large/clip)"; return PRC_ERR_UNSUPPORTED; }
-  if (!SHADOW && ctx->h_counters->n_clip) {
-    { KTimer kt(ctx, PRC_K_CLIP);
-    k_clip_raster<E><<<cdiv(ctx->h_counters->n_clip, 128), 128, 0, st>>>(ctx->S, F, clipq, keys, large, ctx->large_cap, cnt); }
+  // The rare paths are launched unconditionally with fixed grids that read their work counts on the device
+  // (grid-stride loops), so a frame needs no host round trip; queue overflow is checked once at the end.
+  const unsigned int fixed_blocks = 148 * 4;
+  if (!SHADOW) {
+    KTimer kt(ctx, PRC_K_CLIP);
+    k_clip_raster<E><<<fixed_blocks, 128, 0, st>>>(ctx->S, F, clipq, keys, large, ctx->large_cap, cnt);
     ctx->launches++;
-    CK(cudaMemcpyAsync(ctx->h_counters, cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    if (ctx->h_counters->large_overflow) { ctx->err = "internal queue overflow (large)"; return PRC_ERR_UNSUPPORTED; }
   }
-  const unsigned int n_large = ctx->h_counters->n_large;
-  if (n_large) {
-    unsigned int* tile_count = (unsigned int*)ctx->d_tilecount.p;
-    unsigned int* tile_start = (unsigned int*)ctx->d_tilestart.p;
-    unsigned int* cursor = (unsigned int*)ctx->d_cursor.p;
-    CK(cudaMemsetAsync(tile_count, 0, (size_t)n_tiles * 4, st));
-    { KTimer kt(ctx, PRC_K_BIN);
-    k_bin_count<<<cdiv((unsigned long long)n_large * 32, 256), 256, 0, st>>>(large, cnt, ctx->large_cap, tiles_x, tile_count);
-    k_scan<<<1, 1024, 0, st>>>(tile_count, tile_start, cursor, n_tiles, cnt); }
-    ctx->launches += 2;
-    CK(cudaMemcpyAsync(ctx->h_counters, cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    const unsigned int total = ctx->h_counters->n_bin_total;
-    if (total > ctx->bins_cap) {
-      ENSURE(ctx->d_bins, (size_t)total * 4 * 5 / 4);
-      ctx->bins_cap = (unsigned int)(ctx->d_bins.cap / 4);
-    }
-    { KTimer kt(ctx, PRC_K_BIN);
-    k_bin_fill<<<cdiv((unsigned long long)n_large * 32, 256), 256, 0, st>>>(large, cnt, ctx->large_cap, tiles_x, cursor, (unsigned int*)ctx->d_bins.p,
-                                                                            ctx->bins_cap); }
+  unsigned int* tile_count = (unsigned int*)ctx->d_tilecount.p;
+  unsigned int* tile_start = (unsigned int*)ctx->d_tilestart.p;
+  unsigned int* cursor = (unsigned int*)ctx->d_cursor.p;
+  CK(cudaMemsetAsync(tile_count, 0, (size_t)(n_tiles + 8) * 4, st));
+  {
+    KTimer kt(ctx, PRC_K_BIN);
+    k_bin_count<<<fixed_blocks, 256, 0, st>>>(large, cnt, ctx->large_cap, tiles_x, tile_count);
+    k_scan<<<1, 1024, 0, st>>>(tile_count, tile_start, cursor, n_tiles, cnt, ctx->bins_cap, (unsigned int*)ctx->d_active.p + 4, (unsigned int*)ctx->d_active.p);
+    k_bin_fill<<<fixed_blocks, 256, 0, st>>>(large, cnt, ctx->large_cap, tiles_x, cursor, (unsigned int*)ctx->d_bins.p, ctx->bins_cap);
+    ctx->launches += 3;
+  }
+  {
     const int r0 = SHADOW ? F.row0 : F.rr0, r1 = SHADOW ? F.row1 : F.rr1;
-    { KTimer kt(ctx, SHADOW ? PRC_K_TILE_SHADOW : PRC_K_TILE_CAMERA);
-    k_tile_raster<E, SHADOW><<<n_tiles, PRC_TILE * PRC_TILE, 0, st>>>(large, tile_start, (unsigned int*)ctx->d_bins.p, tiles_x, F.W, F.H, r0, r1, keys, smap, cnt); }
-    ctx->launches += 2;
+    KTimer kt(ctx, SHADOW ? PRC_K_TILE_SHADOW : PRC_K_TILE_CAMERA);
+    k_tile_raster<E, SHADOW><<<148 * 8, PRC_TILE * PRC_TILE, 0, st>>>(large, tile_start, (unsigned int*)ctx->d_bins.p, tiles_x, F.W, F.H, r0, r1, keys, smap, cnt,
+                                                                           (const unsigned int*)ctx->d_active.p + 4, (const unsigned int*)ctx->d_active.p);
+    ctx->launches++;
   }
   CK(cudaGetLastError());
   return PRC_OK;
@@ -210,8 +214,13 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
   ENSURE(ctx->d_image, npx * 4);
   ENSURE(ctx->d_special, 16);
   const int n_tiles = ((W + PRC_TILE - 1) / PRC_TILE) * ((H + PRC_TILE - 1) / PRC_TILE);
-  ENSURE(ctx->d_tilecount, (size_t)n_tiles * 4); ENSURE(ctx->d_tilestart, (size_t)(n_tiles + 1) * 4); ENSURE(ctx->d_cursor, (size_t)n_tiles * 4);
-  if (!ctx->d_bins.p) { ENSURE(ctx->d_bins, (size_t)4 << 20); ctx->bins_cap = (unsigned int)(ctx->d_bins.cap / 4); }
+  ENSURE(ctx->d_tilecount, (size_t)(n_tiles + 8) * 4); ENSURE(ctx->d_tilestart, (size_t)(n_tiles + 8) * 4); ENSURE(ctx->d_cursor, (size_t)(n_tiles + 8) * 4);
+  ENSURE(ctx->d_active, (size_t)(n_tiles + 8) * 4);
+  if (!ctx->d_bins.p) {
+    const char* e = getenv("PRC_BINS_INIT");  // initial (tile, triangle) capacity; grown on demand by re-rendering the frame
+    ENSURE(ctx->d_bins, e ? (size_t)atoll(e) * 4 : ((size_t)16 << 20));
+    ctx->bins_cap = (unsigned int)(ctx->d_bins.cap / 4);
+  }
   for (uint32_t i = 0; i < fr->n_lights; i++) {
     if (fr->lights[i].cast_shadow && (fr->flags & PRC_FRAME_SHADOWMAP) && !ctx->d_shadow[i].p) {
       ENSURE(ctx->d_shadow[i], npx * 4);
@@ -220,7 +229,8 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
   }
   // uniforms
   UPLOAD(ctx->d_xf, fr->objects, (size_t)fr->n_objects * sizeof(prc_object_xf));
-  std::vector<DevLight> hl(fr->n_lights);
+  std::vector<DevLight>& hl = ctx->h_lights;
+  hl.assign(fr->n_lights, DevLight());
   for (uint32_t i = 0; i < fr->n_lights; i++) {
     const prc_light& l = fr->lights[i];
     DevLight& d = hl[i];
@@ -231,13 +241,14 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
     d.color = l.color_rgba;
     memcpy(d.view, l.view, 64);
     memcpy(d.proj, l.proj, 64);
+    d.pm_view = plain_mask(l.view);
+    d.pm_proj = plain_mask(l.proj);
     d.shadow_map = (float*)ctx->d_shadow[i].p;
     if (d.cast_shadow) UPLOAD(ctx->d_shadow_trans[i], l.shadow_trans, (size_t)fr->n_objects * 64);
   }
   UPLOAD(ctx->d_lights, hl.data(), hl.size() * sizeof(DevLight));
   UPLOAD(ctx->d_ambient, fr->ambient_intensity, (size_t)fr->n_ambient * 4);
   UPLOAD(ctx->d_gamma, fr->gamma_lut, 256);
-  CK(cudaStreamSynchronize(st));  // hl is a stack temporary
   F.W = W; F.H = H;
   F.row0 = fr->row0; F.row1 = fr->row1;
   // AO marches up to 99 pixels from the shaded pixel (material/ao.go:44-46): widen the rasterised rows
@@ -249,6 +260,16 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
   F.background = fr->background_rgba;
   memcpy(F.viewport, fr->viewport, 64); memcpy(F.viewport_inv, fr->viewport_inv, 64);
   memcpy(F.proj_inv, fr->proj_inv, 64); memcpy(F.view_inv, fr->view_inv, 64); memcpy(F.vtw, fr->viewport_to_world, 64);
+  F.pm_viewport = plain_mask(F.viewport); F.pm_viewport_inv = plain_mask(F.viewport_inv); F.pm_proj_inv = plain_mask(F.proj_inv);
+  F.pm_view_inv = plain_mask(F.view_inv); F.pm_vtw = plain_mask(F.vtw);
+  {
+    const float* v = F.viewport;
+    F.vp_std = (v[1] == 0 && v[2] == 0 && v[4] == 0 && v[6] == 0 && v[8] == 0 && v[9] == 0 && v[10] == 1 && v[11] == 0 && v[12] == 0 && v[13] == 0 &&
+                v[14] == 0 && v[15] == 1 && std::isfinite(v[0]) && std::isfinite(v[3]) && std::isfinite(v[5]) && std::isfinite(v[7]) && v[3] != 0 && v[7] != 0)
+                   ? 1u : 0u;
+    if (getenv("PRC_NO_VPSTD")) F.vp_std = 0;
+  }
+  if (getenv("PRC_NO_PLAIN")) F.pm_viewport = F.pm_viewport_inv = F.pm_proj_inv = F.pm_view_inv = F.pm_vtw = 0;
   memcpy(F.cam, fr->cam_pos, 12);
   F.xf = (const prc_object_xf*)ctx->d_xf.p;
   F.lights = (const DevLight*)ctx->d_lights.p;
@@ -288,9 +309,9 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F) {
   ctx->launches++;
   if (F.rr0 > 0) { k_resolve00<E><<<1, 1, 0, st>>>(ctx->S, F, keys, G); ctx->launches++; } }
   { KTimer kt(ctx, PRC_K_SHADE);
-  k_shade_special<E><<<1, 32, 0, st>>>(ctx->S, F, ctx->ao, keys, G, (uint32_t*)ctx->d_special.p);
+  k_shade_special<E><<<1, 32, 0, st>>>(ctx->S, F, (const AoConsts*)ctx->d_aoc.p, keys, G, (uint32_t*)ctx->d_special.p);
   dim3 sg((F.W + 31) / 32, (F.row1 - F.row0 + 3) / 4);
-  k_shade<E><<<sg, 128, 0, st>>>(ctx->S, F, ctx->ao, keys, G, (const uint32_t*)ctx->d_special.p, (uint32_t*)ctx->d_image.p); }
+  k_shade<E><<<sg, 128, 0, st>>>(ctx->S, F, (const AoConsts*)ctx->d_aoc.p, keys, G, (const uint32_t*)ctx->d_special.p, (uint32_t*)ctx->d_image.p); }
   ctx->launches += 2;
   CK(cudaGetLastError());
   ctx->gbuffer_valid = true;
@@ -325,7 +346,19 @@ int32_t finish_timings(prc_ctx* ctx) {
   ctx->tm.n_valid_tris = ctx->n_valid;
   CK(cudaMemcpy(ctx->h_counters, ctx->d_counters.p, sizeof(Counters), cudaMemcpyDeviceToHost));
   ctx->tm.n_nan_frags = ctx->h_counters->n_nan;
+  if (ctx->h_counters->large_overflow) {
+    ctx->spans.clear();
+    ctx->ev_used = 0;
+    if (ctx->h_counters->max_bins > ctx->bins_cap) {  // grow the bin array; the caller re-renders the frame
+      ENSURE(ctx->d_bins, (size_t)ctx->h_counters->max_bins * 5);
+      ctx->bins_cap = (unsigned int)(ctx->d_bins.cap / 4);
+      return PRC_RETRY;
+    }
+    ctx->err = "internal queue overflow (large/clip queue)";
+    return PRC_ERR_UNSUPPORTED;
+  }
   ctx->tm.gpu_launches = ctx->launches;
+  ctx->tm.n_large_items = ctx->h_counters->stat_large; ctx->tm.n_clipped = ctx->h_counters->stat_clip; ctx->tm.n_bin_entries = ctx->h_counters->stat_bins;
   for (int k = 0; k < 8; k++) { ctx->tm.kernel_ms[k] = 0; ctx->tm.kernel_launches[k] = 0; }
   for (auto& sp : ctx->spans) {
     float ms = 0;
@@ -376,6 +409,9 @@ int32_t prc_open(int32_t device, prc_ctx** out) {
   }
   ctx->ao.half_pi = pi / 2;
   ctx->ao.four_pi = pi * 4;
+  cudaMalloc(&ctx->d_aoc.p, sizeof(AoConsts));
+  ctx->d_aoc.cap = sizeof(AoConsts);
+  cudaMemcpy(ctx->d_aoc.p, &ctx->ao, sizeof(AoConsts), cudaMemcpyHostToDevice);
   *out = ctx;
   return PRC_OK;
 }
@@ -387,7 +423,7 @@ int32_t prc_close(prc_ctx* ctx) {
   DBuf* all[] = {&ctx->d_pos, &ctx->d_nor, &ctx->d_uv, &ctx->d_col, &ctx->d_mat, &ctx->d_meta, &ctx->d_mats, &ctx->d_objstart, &ctx->d_texfirst,
                  &ctx->d_lw, &ctx->d_lh, &ctx->d_loff, &ctx->d_tex, &ctx->d_keys, &ctx->d_ga, &ctx->d_gb, &ctx->d_gc, &ctx->d_gd, &ctx->d_ao,
                  &ctx->d_image, &ctx->d_special, &ctx->d_counters, &ctx->d_large, &ctx->d_clipq, &ctx->d_tilecount, &ctx->d_tilestart, &ctx->d_cursor,
-                 &ctx->d_bins, &ctx->d_xf, &ctx->d_lights, &ctx->d_ambient, &ctx->d_gamma};
+                 &ctx->d_bins, &ctx->d_active, &ctx->d_xf, &ctx->d_lights, &ctx->d_ambient, &ctx->d_gamma, &ctx->d_frame, &ctx->d_aoc};
   for (DBuf* b : all) free_buf(*b);
   for (auto& b : ctx->d_shadow) free_buf(b);
   for (auto& b : ctx->d_shadow_trans) free_buf(b);
@@ -420,7 +456,8 @@ int32_t prc_scene_upload(prc_ctx* ctx, const prc_scene* s) {
   CK(cudaSetDevice(ctx->device));
   ctx->has_scene = false;
   const uint64_t n = s->n_tris;
-  UPLOAD(ctx->d_pos, s->pos, n * 36 + 16);  // +16: the float4 staging loop may read up to the 16-byte boundary
+  ENSURE(ctx->d_pos, n * 36 + 16);  // +16: the float4 staging loop may read up to the next 16-byte boundary
+  UPLOAD(ctx->d_pos, s->pos, n * 36);
   UPLOAD(ctx->d_nor, s->nor, n * 36);
   UPLOAD(ctx->d_uv, s->uv, n * 24);
   UPLOAD(ctx->d_col, s->col, n * 12);
@@ -478,13 +515,24 @@ int32_t prc_render_shadows(prc_ctx* ctx, const prc_frame* fr, uint32_t light_mas
   int32_t r = build_frame(ctx, fr, F);
   if (r != PRC_OK) return r;
   if (srow1 > fr->height || srow0 >= srow1) { ctx->err = "bad shadow row range"; return PRC_ERR_INVALID; }
-  ctx->launches = 0;
-  CK(cudaMemsetAsync(&((Counters*)ctx->d_counters.p)->n_nan, 0, 8, ctx->stream));
-  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  r = ctx->exact ? do_shadows<true>(ctx, fr, F, light_mask, srow0, srow1) : do_shadows<false>(ctx, fr, F, light_mask, srow0, srow1);
-  if (r != PRC_OK) return r;
-  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-  return PRC_OK;
+  for (int attempt = 0; attempt < 4; attempt++) {
+    ctx->launches = 0;
+    CK(cudaMemsetAsync(&((Counters*)ctx->d_counters.p)->large_overflow, 0, offsetof(Counters, n_valid) - offsetof(Counters, large_overflow), ctx->stream));
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    r = ctx->exact ? do_shadows<true>(ctx, fr, F, light_mask, srow0, srow1) : do_shadows<false>(ctx, fr, F, light_mask, srow0, srow1);
+    if (r != PRC_OK) return r;
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->h_counters->large_overflow) return PRC_OK;
+    if (ctx->h_counters->max_bins <= ctx->bins_cap) { ctx->err = "internal queue overflow (large queue)"; return PRC_ERR_UNSUPPORTED; }
+    ENSURE(ctx->d_bins, (size_t)ctx->h_counters->max_bins * 5);
+    ctx->bins_cap = (unsigned int)(ctx->d_bins.cap / 4);
+    ctx->spans.clear();
+    ctx->ev_used = 0;
+  }
+  ctx->err = "bin array kept overflowing";
+  return PRC_ERR_UNSUPPORTED;
 }
 
 int32_t prc_render_main(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out) {
@@ -493,15 +541,21 @@ int32_t prc_render_main(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out) {
   DevFrame F;
   int32_t r = build_frame(ctx, fr, F);
   if (r != PRC_OK) return r;
-  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-  r = ctx->exact ? do_main<true>(ctx, fr, F) : do_main<false>(ctx, fr, F);
-  if (r != PRC_OK) return r;
-  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-  if (!(fr->flags & PRC_FRAME_NO_READBACK)) {
-    r = readback_image(ctx, F, rgba_out);
+  for (int attempt = 0; attempt < 4; attempt++) {
+    CK(cudaMemsetAsync(&((Counters*)ctx->d_counters.p)->large_overflow, 0, 8, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    r = ctx->exact ? do_main<true>(ctx, fr, F) : do_main<false>(ctx, fr, F);
     if (r != PRC_OK) return r;
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    if (!(fr->flags & PRC_FRAME_NO_READBACK)) {
+      r = readback_image(ctx, F, rgba_out);
+      if (r != PRC_OK) return r;
+    }
+    r = finish_timings(ctx);
+    if (r != PRC_RETRY) return r;
   }
-  return finish_timings(ctx);
+  ctx->err = "bin array kept overflowing";
+  return PRC_ERR_UNSUPPORTED;
 }
 
 int32_t prc_render(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out) {
@@ -510,20 +564,25 @@ int32_t prc_render(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out) {
   DevFrame F;
   int32_t r = build_frame(ctx, fr, F);
   if (r != PRC_OK) return r;
-  ctx->launches = 0;
-  CK(cudaMemsetAsync(&((Counters*)ctx->d_counters.p)->n_nan, 0, 8, ctx->stream));
-  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  r = ctx->exact ? do_shadows<true>(ctx, fr, F, 0xFFFFFFFFu, 0, F.H) : do_shadows<false>(ctx, fr, F, 0xFFFFFFFFu, 0, F.H);
-  if (r != PRC_OK) return r;
-  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-  r = ctx->exact ? do_main<true>(ctx, fr, F) : do_main<false>(ctx, fr, F);
-  if (r != PRC_OK) return r;
-  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-  if (!(fr->flags & PRC_FRAME_NO_READBACK)) {
-    r = readback_image(ctx, F, rgba_out);
+  for (int attempt = 0; attempt < 4; attempt++) {
+    ctx->launches = 0;
+    CK(cudaMemsetAsync(&((Counters*)ctx->d_counters.p)->large_overflow, 0, offsetof(Counters, n_valid) - offsetof(Counters, large_overflow), ctx->stream));
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    r = ctx->exact ? do_shadows<true>(ctx, fr, F, 0xFFFFFFFFu, 0, F.H) : do_shadows<false>(ctx, fr, F, 0xFFFFFFFFu, 0, F.H);
     if (r != PRC_OK) return r;
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    r = ctx->exact ? do_main<true>(ctx, fr, F) : do_main<false>(ctx, fr, F);
+    if (r != PRC_OK) return r;
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    if (!(fr->flags & PRC_FRAME_NO_READBACK)) {
+      r = readback_image(ctx, F, rgba_out);
+      if (r != PRC_OK) return r;
+    }
+    r = finish_timings(ctx);
+    if (r != PRC_RETRY) return r;  // shadow maps only grow (atomicMax), so re-running the frame is idempotent
   }
-  return finish_timings(ctx);
+  ctx->err = "bin array kept overflowing";
+  return PRC_ERR_UNSUPPORTED;
 }
 
 int32_t prc_read_gbuffer(prc_ctx* ctx, prc_gbuffer_host* g) {

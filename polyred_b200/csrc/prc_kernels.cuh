@@ -12,11 +12,12 @@
 #pragma once
 #include "../../include/polyred_cuda.h"
 #include "prc_math.cuh"
+#include "prc_prune.h"
 
 namespace prc {
 
 #define PRC_TILE 16
-#define PRC_SMALL_MAX_PIXELS 36  // bbox area up to which a triangle is rasterised by its own thread
+#define PRC_SMALL_MAX_PIXELS 16  // bbox area up to which a triangle is rasterised by its own thread
 
 struct DevScene {
   const float* pos;
@@ -41,6 +42,7 @@ struct DevLight {
   float intensity;
   uint32_t color;
   float view[16], proj[16];
+  uint32_t pm_view, pm_proj;  // plain masks (see apply4m)
   float* shadow_map;  // W*H floats (persistent)
 };
 
@@ -52,6 +54,8 @@ struct DevFrame {
   uint32_t n_lights, n_ambient;
   uint32_t background;
   float viewport[16], viewport_inv[16], proj_inv[16], view_inv[16], vtw[16];
+  uint32_t pm_viewport, pm_viewport_inv, pm_proj_inv, pm_view_inv, pm_vtw;  // plain masks (see apply4m)
+  uint32_t vp_std;  // viewport == [a 0 0 b; 0 c 0 d; 0 0 1 0; 0 0 0 1] (math.ViewportMatrix, math/math.go:270-277)
   float cam[3];
   const prc_object_xf* xf;   // per object trans / normal
   const DevLight* lights;
@@ -66,13 +70,29 @@ struct LargeRec {  // setup record of a triangle handed to the tile path (48 B)
 };
 
 struct Counters {
+  // per raster pass (reset by the host with a stream-ordered memset of the first 16 bytes)
   unsigned int n_large;
   unsigned int n_clip;
-  unsigned int large_overflow;
   unsigned int n_bin_total;
+  unsigned int _pad;
+  // per frame
+  unsigned int large_overflow;  // a queue was too small: the frame is invalid and is re-rendered after growing
+  unsigned int max_bins;        // largest n_bin_total of the frame (to size the bin array)
   unsigned long long n_nan;
+  unsigned long long stat_large, stat_clip, stat_bins;
+  // per scene
   unsigned long long n_valid;
 };
+
+// warp-aggregated slot reservation: one atomicAdd per warp for all lanes that reach this point together
+__device__ __forceinline__ unsigned int warp_push(unsigned int* counter) {
+  const unsigned int m = __activemask();
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  unsigned int base = 0;
+  if (lane == leader) base = atomicAdd(counter, (unsigned int)__popc(m));
+  base = __shfl_sync(m, base, leader);
+  return base + __popc(m & ((1u << lane) - 1u));
+}
 
 // ---------------------------------------------------------------------------------------------
 // Triangle setup shared by every stage (render/raster.go:380-444, render/shadow.go:152-178)
@@ -87,15 +107,15 @@ enum { TRI_CULLED = 0, TRI_DIRECT = 1, TRI_CLIP = 2 };
 // transform + viewport + back-face + AABB tests. `clip_allowed`=false is the shadow pass (no clipping,
 // cullViewFrustum only — render/cull.go:15-24).
 template <bool E>
-__device__ __forceinline__ int tri_setup(const float* __restrict__ trans, const float* __restrict__ viewport, float Wf, float Hf,
+__device__ __forceinline__ int tri_setup(const float* __restrict__ trans, const float* __restrict__ viewport, uint32_t pm_vp, float Wf, float Hf,
                                          const float* p, bool clip_allowed, ScreenTri& s) {
   V4 a = mulv(trans, V4{p[0], p[1], p[2], 1.0f});
   V4 b = mulv(trans, V4{p[3], p[4], p[5], 1.0f});
   V4 c = mulv(trans, V4{p[6], p[7], p[8], 1.0f});
   s.cw1 = a.w; s.cw2 = b.w; s.cw3 = c.w;
-  s.p1 = pos4(apply4<E>(a, viewport));
-  s.p2 = pos4(apply4<E>(b, viewport));
-  s.p3 = pos4(apply4<E>(c, viewport));
+  s.p1 = pos4(apply4m<E>(a, viewport, pm_vp));
+  s.p2 = pos4(apply4m<E>(b, viewport, pm_vp));
+  s.p3 = pos4(apply4m<E>(c, viewport, pm_vp));
   // cullBackFace (render/cull.go:26-28)
   V4 e1 = sub4(s.p2, s.p1), e2 = sub4(s.p3, s.p1);
   if (fma32<E>(e1.x, e2.y, -(e1.y * e2.x)) < 0.0f) return TRI_CULLED;
@@ -119,9 +139,10 @@ __device__ __forceinline__ int tri_setup(const float* __restrict__ trans, const 
 }
 
 // pixel bbox of drawClipped/drawDepth (raster.go:473-477): int(Round(min)-1) .. int(Round(max)+1), clamped
-__device__ __forceinline__ bool pixel_bbox(const V4& p1, const V4& p2, const V4& p3, int W, int r0, int r1, int& x0, int& y0, int& x1, int& y1) {
-  float mnx = go_min3(p1.x, p2.x, p3.x), mxx = go_max3(p1.x, p2.x, p3.x);
-  float mny = go_min3(p1.y, p2.y, p3.y), mxy = go_max3(p1.y, p2.y, p3.y);
+__device__ __forceinline__ bool pixel_bbox(const V4& p1, const V4& p2, const V4& p3, int W, int r0, int r1, int& x0, int& y0, int& x1, int& y1,
+                                           float& mnx, float& mny, float& mxx, float& mxy) {
+  mnx = go_min3(p1.x, p2.x, p3.x); mxx = go_max3(p1.x, p2.x, p3.x);
+  mny = go_min3(p1.y, p2.y, p3.y); mxy = go_max3(p1.y, p2.y, p3.y);
   long long xa = go_int(roundf(mnx) - 1.0f), xb = go_int(roundf(mxx) + 1.0f);
   long long ya = go_int(roundf(mny) - 1.0f), yb = go_int(roundf(mxy) + 1.0f);
   if (xa < 0) xa = 0;
@@ -194,9 +215,8 @@ __device__ __forceinline__ V4 clip_pos(const ScreenTri& t, const float b[3]) {
 // in-thread rasterisation of one (small) screen triangle
 // ---------------------------------------------------------------------------------------------
 template <bool E, bool SHADOW>
-__device__ __forceinline__ void raster_one(const V4& p1, const V4& p2, const V4& p3, int x0, int y0, int x1, int y1, uint32_t seq, int W,
+__device__ __forceinline__ void raster_one(const BarySetup& bs, const V4& p1, const V4& p2, const V4& p3, int x0, int y0, int x1, int y1, uint32_t seq, int W,
                                            unsigned long long* __restrict__ keys, float* __restrict__ smap, Counters* cnt) {
-  BarySetup bs = bary_setup<E>(p1.x, p1.y, p2.x, p2.y, p3.x, p3.y);
   for (int y = y0; y <= y1; y++) {
     float py = (float)y + 0.5f;
     for (int x = x0; x <= x1; x++) {
@@ -224,21 +244,31 @@ __device__ __forceinline__ void raster_one(const V4& p1, const V4& p2, const V4&
 template <bool E>
 __device__ __forceinline__ void raster_pixel00(const V4& p1, const V4& p2, const V4& p3, uint32_t seq, unsigned long long* keys, Counters* cnt) {
   int x0, y0, x1, y1;
-  if (!pixel_bbox(p1, p2, p3, 1, 0, 1, x0, y0, x1, y1)) return;
-  raster_one<E, false>(p1, p2, p3, 0, 0, 0, 0, seq, 1 << 30, keys, nullptr, cnt);
+  float a, b, c, d;
+  if (!pixel_bbox(p1, p2, p3, 1, 0, 1, x0, y0, x1, y1, a, b, c, d)) return;
+  BarySetup bs = bary_setup<E>(p1.x, p1.y, p2.x, p2.y, p3.x, p3.y);
+  raster_one<E, false>(bs, p1, p2, p3, 0, 0, 0, 0, seq, 1 << 30, keys, nullptr, cnt);
 }
 
 template <bool E, bool SHADOW>
 __device__ __forceinline__ void emit_tri(const V4& p1, const V4& p2, const V4& p3, uint32_t seq, const DevFrame& F, int r0, int r1,
                                          unsigned long long* keys, float* smap, LargeRec* large, unsigned int large_cap, Counters* cnt) {
   int x0, y0, x1, y1;
+  float mnx, mny, mxx, mxy;
   if (!SHADOW && r0 > 0) raster_pixel00<E>(p1, p2, p3, seq, keys, cnt);
-  if (!pixel_bbox(p1, p2, p3, F.W, r0, r1, x0, y0, x1, y1)) return;
+  if (!pixel_bbox(p1, p2, p3, F.W, r0, r1, x0, y0, x1, y1, mnx, mny, mxx, mxy)) return;
+  const BarySetup bs = bary_setup<E>(p1.x, p1.y, p2.x, p2.y, p3.x, p3.y);
+  // exact-safe shrink of the reference's AABB+-1 loop (prc_prune.h)
+  if (prune_ok(mnx, mny, mxx, mxy, bs.Sabc)) {
+    x0 = max(x0, prune_first(mnx)); x1 = min(x1, prune_last(mxx));
+    y0 = max(y0, prune_first(mny)); y1 = min(y1, prune_last(mxy));
+    if (x0 > x1 || y0 > y1) return;
+  }
   int area = (x1 - x0 + 1) * (y1 - y0 + 1);
   if (area <= PRC_SMALL_MAX_PIXELS) {
-    raster_one<E, SHADOW>(p1, p2, p3, x0, y0, x1, y1, seq, F.W, keys, smap, cnt);
+    raster_one<E, SHADOW>(bs, p1, p2, p3, x0, y0, x1, y1, seq, F.W, keys, smap, cnt);
   } else {
-    unsigned int slot = atomicAdd(&cnt->n_large, 1u);
+    unsigned int slot = warp_push(&cnt->n_large);
     if (slot >= large_cap) { atomicExch(&cnt->large_overflow, 1u); return; }
     LargeRec r;
     r.x1 = p1.x; r.y1 = p1.y; r.z1 = p1.z; r.x2 = p2.x; r.y2 = p2.y; r.z2 = p2.z; r.x3 = p3.x; r.y3 = p3.y; r.z3 = p3.z;
@@ -248,66 +278,193 @@ __device__ __forceinline__ void emit_tri(const V4& p1, const V4& p2, const V4& p
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1: per-triangle transform / cull / classify / small raster.  One thread per triangle; positions are staged
-// through shared memory with 128-bit loads (the [n][9] float layout is not 16-byte aligned per triangle).
+// K1: per-triangle transform / cull / classify, then WARP-COOPERATIVE small raster.
+//   phase A (one thread per triangle): positions staged through shared memory with 128-bit loads (the [n][9]
+//     float layout is not 16-byte aligned per triangle); transform, viewport, back-face, AABB tests, pixel box,
+//     exact-safe prune. Survivors with a small box publish a setup record in shared memory.
+//   phase B (per warp): the pixel tests of the warp's survivors are flattened (prefix sum over lanes) and dealt
+//     out 32 at a time, so lanes whose triangle was culled work on their neighbours' pixels.
+// Non-finite vertices, triangles needing clipping and big boxes leave through the generic / queue paths.
 // ---------------------------------------------------------------------------------------------
 #define PRC_GEOM_THREADS 256
+#define PRC_REC_STRIDE 19
+struct SmallRec {  // 18 words
+  BarySetup bs;
+  float z1, z2, z3;
+  uint32_t seq;
+  int x0, y0, bw;
+};
+
 template <bool E, bool SHADOW>
-__global__ void __launch_bounds__(PRC_GEOM_THREADS) k_geom_raster(DevScene S, DevFrame F, const float* __restrict__ shadow_trans /*[n_obj][16]*/,
-                                                                     unsigned long long* keys, float* smap, LargeRec* large, unsigned int large_cap,
-                                                                     unsigned int* clipq, unsigned int clip_cap, Counters* cnt) {
-  __shared__ __align__(16) float sp[PRC_GEOM_THREADS * 9];
-  const unsigned long long base = (unsigned long long)blockIdx.x * PRC_GEOM_THREADS;
-  const unsigned long long nleft = S.n_tris - base;
-  const int nt = nleft < PRC_GEOM_THREADS ? (int)nleft : PRC_GEOM_THREADS;
-  {
-    // base*9 floats = base*36 bytes, base is a multiple of 256 -> 16-byte aligned
-    const float4* src = reinterpret_cast<const float4*>(S.pos + base * 9);
-    float4* dst = reinterpret_cast<float4*>(sp);
-    const int nvec = (nt * 9) / 4;
-    for (int i = threadIdx.x; i < nvec; i += PRC_GEOM_THREADS) dst[i] = __ldg(src + i);
-    for (int i = nvec * 4 + threadIdx.x; i < nt * 9; i += PRC_GEOM_THREADS) sp[i] = S.pos[base * 9 + i];
+// NOTE: takes the frame through a pointer to a DEVICE-RESIDENT copy. Passing the kernel-parameter struct by
+// reference to a non-inlined function makes every thread copy it to local memory at kernel entry (measured:
+// 1.76 GB of DRAM writes per launch).
+__device__ __noinline__ void geom_generic(const DevFrame* __restrict__ Fg, const float* trans, const float* __restrict__ pos, uint32_t tri, unsigned long long* keys,
+                                          float* smap, LargeRec* large, unsigned int large_cap, unsigned int* clipq, unsigned int clip_cap, Counters* cnt) {
+  float p[9];  // re-read from global memory: passing the caller's register array by pointer would force it into local memory
+#pragma unroll
+  for (int i = 0; i < 9; i++) p[i] = pos[(size_t)tri * 9 + i];
+  const DevFrame& F = *Fg;
+  ScreenTri st;
+  int cls = tri_setup<E>(trans, F.viewport, F.pm_viewport, (float)F.W, (float)F.H, p, !SHADOW, st);
+  if (cls == TRI_CULLED) return;
+  if (cls == TRI_CLIP) {
+    unsigned int slot = warp_push(&cnt->n_clip);
+    if (slot < clip_cap) clipq[slot] = tri;
+    else atomicExch(&cnt->large_overflow, 1u);
+    return;
   }
-  __syncthreads();
-  if ((int)threadIdx.x >= nt) return;
-  const unsigned long long tri = base + threadIdx.x;
-  const uint32_t meta = S.meta[tri];
+  const int r0 = SHADOW ? F.row0 : F.rr0, r1 = SHADOW ? F.row1 : F.rr1;
+  emit_tri<E, SHADOW>(st.p1, st.p2, st.p3, tri * 8u, F, r0, r1, keys, smap, large, large_cap, cnt);
+}
+
+// Apply(Viewport).Pos() for the standard viewport matrix [a 0 0 b; 0 c 0 d; 0 0 1 0; 0 0 0 1] and a vertex whose
+// clip coordinates are finite with z != 0, w != 0: the zero entries contribute exact zeros, so
+//   x' = FMA(a, x, b*w)   y' = FMA(c, y, d*w)   z' = z   w' = w      (math/vec4.go:108-116)
+// bit for bit (adding +-0 to a non-zero value is the identity; an exactly cancelling FMA gives +0 either way).
+template <bool E>
+__device__ __forceinline__ bool viewport_pos_std(const float* __restrict__ vp, const V4& c, V4& out) {
+  const float m = fabsf(c.x) + fabsf(c.y) + fabsf(c.z) + fabsf(c.w);
+  if (!(m < 1e30f) || c.z == 0.0f || c.w == 0.0f) return false;
+  const float x = fma32<E>(vp[0], c.x, vp[3] * c.w), y = fma32<E>(vp[5], c.y, vp[7] * c.w);
+  if (c.w == 1.0f) { out = V4{x, y, c.z, 1.0f}; return true; }
+  const float invW = __fdiv_rn(1.0f, c.w);
+  out = V4{x * invW, y * invW, c.z * invW, 1.0f};
+  return true;
+}
+
+template <bool E, bool SHADOW>
+__global__ void __launch_bounds__(PRC_GEOM_THREADS, 4) k_geom_raster(DevScene S, DevFrame F, const float* __restrict__ shadow_trans /*[n_obj][16]*/,
+                                                                     unsigned long long* keys, float* smap, LargeRec* large, unsigned int large_cap,
+                                                                     unsigned int* clipq, unsigned int clip_cap, Counters* cnt, const DevFrame* Fg) {
+  // Each warp stages its own 32 triangles (32 x 36 B = 72 float4, 16-byte aligned because the warp's first
+  // triangle index is a multiple of 32) through shared memory with 128-bit loads; only __syncwarp is needed,
+  // so warps never wait for each other.
+  __shared__ __align__(16) float sp[PRC_GEOM_THREADS * 9];
+  const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+  const unsigned long long wtri = (unsigned long long)blockIdx.x * PRC_GEOM_THREADS + wbase;  // first triangle of this warp
+  if (wtri >= S.n_tris) return;
+  const unsigned long long wleft = S.n_tris - wtri;
+  const int nt = wleft < 32 ? (int)wleft : 32;
+  const unsigned int tri = (unsigned int)(wtri + lane);
+  const uint32_t meta = lane < nt ? __ldg(S.meta + tri) : 0x80000000u;
+  {
+    const float4* src = reinterpret_cast<const float4*>(S.pos + wtri * 9);
+    float4* dst = reinterpret_cast<float4*>(sp + wbase * 9);
+    const int nvec = (nt * 9) / 4;  // the scene buffer is padded, reading the last partial float4 is safe
+    for (int i = lane; i < nvec + ((nt * 9) & 3 ? 1 : 0); i += 32) dst[i] = __ldg(src + i);
+  }
+  __syncwarp();
   if (meta & 0x80000000u) return;  // !IsValid
   const uint32_t obj = meta & 0x00FFFFFFu;
   const float* trans = SHADOW ? (shadow_trans + (size_t)obj * 16) : F.xf[obj].trans;
   float p[9];
 #pragma unroll
   for (int i = 0; i < 9; i++) p[i] = sp[threadIdx.x * 9 + i];
-  ScreenTri st;
-  int cls = tri_setup<E>(trans, F.viewport, (float)F.W, (float)F.H, p, !SHADOW, st);
-  if (cls == TRI_CULLED) return;
-  if (cls == TRI_CLIP) {
-    unsigned int slot = atomicAdd(&cnt->n_clip, 1u);
-    if (slot < clip_cap) clipq[slot] = (unsigned int)tri;
-    else atomicExch(&cnt->large_overflow, 1u);
+  const V4 ca = mulv(trans, V4{p[0], p[1], p[2], 1.0f});
+  const V4 cb = mulv(trans, V4{p[3], p[4], p[5], 1.0f});
+  const V4 cc = mulv(trans, V4{p[6], p[7], p[8], 1.0f});
+  V4 p1, p2, p3;
+  if (!(F.vp_std && viewport_pos_std<E>(F.viewport, ca, p1) && viewport_pos_std<E>(F.viewport, cb, p2) && viewport_pos_std<E>(F.viewport, cc, p3))) {
+    // non-standard viewport matrix or NaN / Inf / zero z,w: the literal reference sequence
+    geom_generic<E, SHADOW>(Fg, trans, S.pos, tri, keys, smap, large, large_cap, clipq, clip_cap, cnt);
     return;
   }
+  const float mag = fabsf(p1.x) + fabsf(p1.y) + fabsf(p1.z) + fabsf(p2.x) + fabsf(p2.y) + fabsf(p2.z) + fabsf(p3.x) + fabsf(p3.y) + fabsf(p3.z);
+  if (!(mag < 1e30f)) {
+    geom_generic<E, SHADOW>(Fg, trans, S.pos, tri, keys, smap, large, large_cap, clipq, clip_cap, cnt);
+    return;
+  }
+  // cullBackFace (render/cull.go:26-28)
+  if (fma32<E>(p2.x - p1.x, p3.y - p1.y, -((p2.y - p1.y) * (p3.x - p1.x))) < 0.0f) return;
+  // finite coordinates: Go's NaN-propagating Min/Max reduce to plain min/max (the sign of a zero is irrelevant below)
+  const float mnx = fminf(fminf(p1.x, p2.x), p3.x), mxx = fmaxf(fmaxf(p1.x, p2.x), p3.x);
+  const float mny = fminf(fminf(p1.y, p2.y), p3.y), mxy = fmaxf(fmaxf(p1.y, p2.y), p3.y);
+  const float mnz = fminf(fminf(p1.z, p2.z), p3.z), mxz = fmaxf(fmaxf(p1.z, p2.z), p3.z);
+  const float Wf = (float)F.W, Hf = (float)F.H;
+  // AABB.Intersect (box.go:32-41): max(lo) <= min(hi) per axis; the Z test compares against Max.Y = H (the Z quirk)
+  if (!(mxx >= 0.0f && mnx <= Wf && mxy >= 0.0f && mny <= Hf && mxz >= -1.0f && mnz <= Hf)) return;
+  if (!SHADOW) {
+    // AABB.Contains (box.go:61-75) is monotone per coordinate, so testing the extremes tests all three vertices
+    const bool in = less_eq(0.0f, mnx) && less_eq(0.0f, mny) && less_eq(-1.0f, mnz) && less_eq(mxx, Wf) && less_eq(mxy, Hf) && less_eq(mxz, 1.0f);
+    if (!in) {
+      unsigned int slot = warp_push(&cnt->n_clip);
+      if (slot < clip_cap) clipq[slot] = tri;
+      else atomicExch(&cnt->large_overflow, 1u);
+      return;
+    }
+  }
   const int r0 = SHADOW ? F.row0 : F.rr0, r1 = SHADOW ? F.row1 : F.rr1;
-  emit_tri<E, SHADOW>(st.p1, st.p2, st.p3, (uint32_t)tri * 8u, F, r0, r1, keys, smap, large, large_cap, cnt);
+  const uint32_t seq = tri * 8u;
+  if (!SHADOW && r0 > 0) raster_pixel00<E>(p1, p2, p3, seq, keys, cnt);
+  // pixel box int(Round(min)-1) .. int(Round(max)+1) clamped to the buffer (raster.go:473-485); clamping in float first
+  int x0 = (int)fmaxf(roundf(mnx) - 1.0f, 0.0f), x1 = (int)fminf(roundf(mxx) + 1.0f, Wf - 1.0f);
+  int y0 = (int)fmaxf(roundf(mny) - 1.0f, (float)r0), y1 = (int)fminf(roundf(mxy) + 1.0f, (float)(r1 - 1));
+  if (x0 > x1 || y0 > y1) return;
+  const BarySetup bs = bary_setup<E>(p1.x, p1.y, p2.x, p2.y, p3.x, p3.y);
+  if (prune_ok(mnx, mny, mxx, mxy, bs.Sabc)) {  // exact-safe shrink of the AABB+-1 loop (prc_prune.h)
+    x0 = max(x0, prune_first(mnx)); x1 = min(x1, prune_last(mxx));
+    y0 = max(y0, prune_first(mny)); y1 = min(y1, prune_last(mxy));
+    if (x0 > x1 || y0 > y1) return;
+  }
+  const int area = (x1 - x0 + 1) * (y1 - y0 + 1);
+  if (area > PRC_SMALL_MAX_PIXELS) {
+    unsigned int slot = warp_push(&cnt->n_large);
+    if (slot >= large_cap) { atomicExch(&cnt->large_overflow, 1u); return; }
+    LargeRec lr;
+    lr.x1 = p1.x; lr.y1 = p1.y; lr.z1 = p1.z; lr.x2 = p2.x; lr.y2 = p2.y; lr.z2 = p2.z; lr.x3 = p3.x; lr.y3 = p3.y; lr.z3 = p3.z;
+    lr.seq = seq; lr.bx0 = (short)x0; lr.by0 = (short)y0; lr.bx1 = (short)x1; lr.by1 = (short)y1;
+    large[slot] = lr;
+    return;
+  }
+  // in-thread pixel loop (render/raster.go:481-499 / render/shadow.go:191-215)
+  const float thr = 2e-7f * fabsf(bs.Sabc);
+  const uint32_t sg = __float_as_uint(bs.Sabc);
+  for (int y = y0; y <= y1; y++) {
+    const float py = (float)y + 0.5f;
+    const float apy = py - bs.t1y, bpy = py - bs.t2y;
+    for (int x = x0; x <= x1; x++) {
+      const float px = (float)x + 0.5f;
+      const float apx = px - bs.t1x, bpx = px - bs.t2x;
+      const float Sabp = cross2z<E>(bs.abx, bs.aby, apx, apy);
+      const float Sapc = cross2z<E>(apx, apy, bs.acx, bs.acy);
+      const float Sbcp = cross2z<E>(bs.bcx, bs.bcy, bpx, bpy);
+      // certain rejection without dividing: sign(S) != sign(Sabc) and |S| > 2e-7 |Sabc|  =>  RN(S/Sabc) < -1e-7
+      if ((((__float_as_uint(Sabp) ^ sg) >> 31) && fabsf(Sabp) > thr) || (((__float_as_uint(Sapc) ^ sg) >> 31) && fabsf(Sapc) > thr) ||
+          (((__float_as_uint(Sbcp) ^ sg) >> 31) && fabsf(Sbcp) > thr))
+        continue;
+      const float w1 = __fdiv_rn(Sbcp, bs.Sabc), w2 = __fdiv_rn(Sapc, bs.Sabc), w3 = __fdiv_rn(Sabp, bs.Sabc);
+      if (w1 < -PRC_EPS || w2 < -PRC_EPS || w3 < -PRC_EPS) continue;
+      const float z = w1 * p1.z + w2 * p2.z + w3 * p3.z;
+      if (isnan(z)) { atomicAdd(&cnt->n_nan, 1ULL); continue; }
+      const size_t idx = (size_t)y * F.W + x;
+      // fire-and-forget reductions (RED.MAX): no pre-test load, so the loop never waits on memory
+      if (SHADOW) {
+        if (z > 0.0f) atomicMax((int*)&smap[idx], __float_as_int(z));
+      } else {
+        unsigned long long key = ((unsigned long long)depth_key(z) << 32) | (unsigned long long)(0xFFFFFFFFu - seq);
+        atomicMax(&keys[idx], key);
+      }
+    }
+  }
 }
 
 // K2: triangles straddling the viewport: clip, fan, emit (raster.go:438-443)
 template <bool E>
 __global__ void k_clip_raster(DevScene S, DevFrame F, const unsigned int* __restrict__ clipq, unsigned long long* keys, LargeRec* large,
                               unsigned int large_cap, Counters* cnt) {
-  unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned int n = cnt->n_clip;
-  if (i >= n) return;
+  const unsigned int n = cnt->n_clip;  // final: written by the preceding kernel on the same stream
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
   const unsigned int tri = clipq[i];
   const uint32_t obj = S.meta[tri] & 0x00FFFFFFu;
   float p[9];
 #pragma unroll
   for (int k = 0; k < 9; k++) p[k] = S.pos[(size_t)tri * 9 + k];
   ScreenTri st;
-  tri_setup<E>(F.xf[obj].trans, F.viewport, (float)F.W, (float)F.H, p, true, st);
+  tri_setup<E>(F.xf[obj].trans, F.viewport, F.pm_viewport, (float)F.W, (float)F.H, p, true, st);
   V4 poly[12];
   int nc = clip_polygon<E>(st, (float)F.W, (float)F.H, poly);
-  if (nc < 3) return;
+  if (nc < 3) continue;
   float b0[3];
   clip_bary<E>(st, poly[0], b0);
   V4 q0 = clip_pos(st, b0);
@@ -318,6 +475,7 @@ __global__ void k_clip_raster(DevScene S, DevFrame F, const unsigned int* __rest
     V4 q1 = clip_pos(st, b1), q2 = clip_pos(st, b2);
     emit_tri<E, false>(q0, q1, q2, tri * 8u + (uint32_t)(k - 1), F, F.rr0, F.rr1, keys, nullptr, large, large_cap, cnt);
   }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -325,43 +483,87 @@ __global__ void k_clip_raster(DevScene S, DevFrame F, const unsigned int* __rest
 // ---------------------------------------------------------------------------------------------
 __global__ void k_bin_count(const LargeRec* __restrict__ large, const Counters* cnt, unsigned int cap, int tiles_x, unsigned int* tile_count) {
   const unsigned int n = min(cnt->n_large, cap);
-  const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= n) return;
-  const LargeRec r = large[warp];
-  const int tx0 = r.bx0 / PRC_TILE, tx1 = r.bx1 / PRC_TILE, ty0 = r.by0 / PRC_TILE, ty1 = r.by1 / PRC_TILE;
-  const int nx = tx1 - tx0 + 1, nt = nx * (ty1 - ty0 + 1);
-  for (int t = lane; t < nt; t += 32) atomicAdd(&tile_count[(ty0 + t / nx) * tiles_x + tx0 + t % nx], 1u);
+  const unsigned int lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; warp < n; warp += nwarps) {
+    const LargeRec r = large[warp];
+    const int tx0 = r.bx0 / PRC_TILE, tx1 = r.bx1 / PRC_TILE, ty0 = r.by0 / PRC_TILE, ty1 = r.by1 / PRC_TILE;
+    const int nx = tx1 - tx0 + 1, nt = nx * (ty1 - ty0 + 1);
+    for (int t = lane; t < nt; t += 32) atomicAdd(&tile_count[(ty0 + t / nx) * tiles_x + tx0 + t % nx], 1u);
+  }
 }
-// exclusive scan of tile_count -> tile_start (single block; <= 130k tiles at 8K)
-__global__ void k_scan(const unsigned int* __restrict__ in, unsigned int* out, unsigned int* cursor, int n, Counters* cnt) {
-  __shared__ unsigned int part[1024];
-  const int per = (n + 1023) / 1024;
-  const int b = threadIdx.x * per, e = min(n, b + per);
-  unsigned int s = 0;
-  for (int i = b; i < e; i++) s += in[i];
-  part[threadIdx.x] = s;
+// exclusive scan of tile_count -> tile_start (single block, 4 tiles per thread per round, coalesced 128-bit
+// loads; <= 130k tiles at 8K) + the compacted list of non-empty tiles the raster kernel iterates over.
+__global__ void __launch_bounds__(1024) k_scan(const unsigned int* __restrict__ in, unsigned int* out, unsigned int* cursor, int n, Counters* cnt,
+                                                unsigned int bins_cap, unsigned int* active, unsigned int* n_active) {
+  __shared__ unsigned int warp_sum[32];
+  __shared__ unsigned int carry_s, nact_s;
+  if (threadIdx.x == 0) { carry_s = 0; nact_s = 0; }
   __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {
-    unsigned int v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+  if (cnt->n_large == 0) {  // nothing queued in this pass: the raster kernel sees n_active == 0
+    if (threadIdx.x == 0) { cnt->n_bin_total = 0; *n_active = 0; cnt->stat_clip += cnt->n_clip; }
+    return;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += 4096) {
+    const int i = base + threadIdx.x * 4;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (i < n) v = *reinterpret_cast<const uint4*>(in + i);  // arrays are padded to a multiple of 4 and zero-filled
+    const unsigned int local = v.x + v.y + v.z + v.w;
+    unsigned int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
     __syncthreads();
-    part[threadIdx.x] += v;
+    if (warp == 0) {
+      unsigned int w = warp_sum[lane], wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned int t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      warp_sum[lane] = wi - w;  // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    const unsigned int ex = carry_s + warp_sum[warp] + incl - local;
+    if (i < n) {
+      const uint4 o4 = make_uint4(ex, ex + v.x, ex + v.x + v.y, ex + v.x + v.y + v.z);
+      *reinterpret_cast<uint4*>(out + i) = o4;
+      *reinterpret_cast<uint4*>(cursor + i) = o4;
+      const unsigned int c[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (c[k] && i + k < n) active[atomicAdd(&nact_s, 1u)] = (unsigned int)(i + k);
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = ex + local;
     __syncthreads();
   }
-  unsigned int run = threadIdx.x ? part[threadIdx.x - 1] : 0;
-  for (int i = b; i < e; i++) { out[i] = run; cursor[i] = run; run += in[i]; }
-  if (threadIdx.x == 1023) { out[n] = part[1023]; cnt->n_bin_total = part[1023]; }
+  if (threadIdx.x == 0) {
+    const unsigned int total = carry_s;
+    out[n] = total;
+    *n_active = nact_s;
+    cnt->n_bin_total = total;
+    if (total > cnt->max_bins) cnt->max_bins = total;
+    if (total > bins_cap) cnt->large_overflow = 1u;
+    cnt->stat_large += cnt->n_large; cnt->stat_clip += cnt->n_clip; cnt->stat_bins += total;
+  }
 }
 __global__ void k_bin_fill(const LargeRec* __restrict__ large, const Counters* cnt, unsigned int cap, int tiles_x, unsigned int* cursor,
                            unsigned int* bins, unsigned int bins_cap) {
   const unsigned int n = min(cnt->n_large, cap);
-  const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= n) return;
-  const LargeRec r = large[warp];
-  const int tx0 = r.bx0 / PRC_TILE, tx1 = r.bx1 / PRC_TILE, ty0 = r.by0 / PRC_TILE, ty1 = r.by1 / PRC_TILE;
-  const int nx = tx1 - tx0 + 1, nt = nx * (ty1 - ty0 + 1);
-  for (int t = lane; t < nt; t += 32) {
-    unsigned int slot = atomicAdd(&cursor[(ty0 + t / nx) * tiles_x + tx0 + t % nx], 1u);
-    if (slot < bins_cap) bins[slot] = warp;
+  if (cnt->n_bin_total > bins_cap) return;  // frame flagged for a re-render with a larger bin array
+  const unsigned int lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; warp < n; warp += nwarps) {
+    const LargeRec r = large[warp];
+    const int tx0 = r.bx0 / PRC_TILE, tx1 = r.bx1 / PRC_TILE, ty0 = r.by0 / PRC_TILE, ty1 = r.by1 / PRC_TILE;
+    const int nx = tx1 - tx0 + 1, nt = nx * (ty1 - ty0 + 1);
+    for (int t = lane; t < nt; t += 32) {
+      unsigned int slot = atomicAdd(&cursor[(ty0 + t / nx) * tiles_x + tx0 + t % nx], 1u);
+      if (slot < bins_cap) bins[slot] = warp;
+    }
   }
 }
 
@@ -374,11 +576,14 @@ struct TileRec {
 template <bool E, bool SHADOW>
 __global__ void __launch_bounds__(PRC_TILE * PRC_TILE) k_tile_raster(const LargeRec* __restrict__ large, const unsigned int* __restrict__ tile_start,
                                                                       const unsigned int* __restrict__ bins, int tiles_x, int W, int H, int r0, int r1,
-                                                                      unsigned long long* keys, float* smap, Counters* cnt) {
-  const int tile = blockIdx.x;
-  const unsigned int b = tile_start[tile], e = tile_start[tile + 1];
-  if (b == e) return;
+                                                                      unsigned long long* keys, float* smap, Counters* cnt,
+                                                                      const unsigned int* __restrict__ active, const unsigned int* __restrict__ n_active) {
   __shared__ TileRec recs[128];
+  if (cnt->large_overflow) return;
+  const unsigned int na = *n_active;
+  for (unsigned int ai = blockIdx.x; ai < na; ai += gridDim.x) {
+  const int tile = (int)active[ai];
+  const unsigned int b = tile_start[tile], e = tile_start[tile + 1];
   const int tx = tile % tiles_x, ty = tile / tiles_x;
   const int x = tx * PRC_TILE + (threadIdx.x & (PRC_TILE - 1)), y = ty * PRC_TILE + (threadIdx.x / PRC_TILE);
   const float px = (float)x + 0.5f, py = (float)y + 0.5f;
@@ -416,12 +621,13 @@ __global__ void __launch_bounds__(PRC_TILE * PRC_TILE) k_tile_raster(const Large
     }
   }
   if (nan_local) atomicAdd(&cnt->n_nan, nan_local);
-  if (!live) return;
+  if (!live) continue;
   const size_t idx = (size_t)y * W + x;
   if (SHADOW) {
-    if (bestz > 0.0f && bestz > smap[idx]) atomicMax((int*)&smap[idx], __float_as_int(bestz));
+    if (bestz > 0.0f) atomicMax((int*)&smap[idx], __float_as_int(bestz));
   } else {
-    if (best > keys[idx]) atomicMax(&keys[idx], best);
+    if (best) atomicMax(&keys[idx], best);
+  }
   }
 }
 
@@ -451,7 +657,7 @@ __device__ void resolve_fragment(const DevScene& S, const DevFrame& F, uint32_t 
 #pragma unroll
   for (int k = 0; k < 9; k++) p[k] = __ldg(S.pos + (size_t)tri * 9 + k);
   ScreenTri st;
-  tri_setup<E>(trans, F.viewport, (float)F.W, (float)F.H, p, true, st);
+  tri_setup<E>(trans, F.viewport, F.pm_viewport, (float)F.W, (float)F.H, p, true, st);
   const bool persp = (F.flags & PRC_FRAME_PERSPECT) != 0;
   float rw1 = 1.0f, rw2 = 1.0f, rw3 = 1.0f;
   if (persp) { rw1 = __fdiv_rn(-1.0f, st.cw1); rw2 = __fdiv_rn(-1.0f, st.cw2); rw3 = __fdiv_rn(-1.0f, st.cw3); }
@@ -490,9 +696,9 @@ __device__ void resolve_fragment(const DevScene& S, const DevFrame& F, uint32_t 
     v[0] = c[0]; v[1] = c[1]; v[2] = c[2];
   }
   // un-project without dividing by W (raster.go:467-469)
-  V4 m1 = apply4<E>(apply4<E>(apply4<E>(v[0].pos, F.viewport_inv), F.proj_inv), F.view_inv);
-  V4 m2 = apply4<E>(apply4<E>(apply4<E>(v[1].pos, F.viewport_inv), F.proj_inv), F.view_inv);
-  V4 m3 = apply4<E>(apply4<E>(apply4<E>(v[2].pos, F.viewport_inv), F.proj_inv), F.view_inv);
+  V4 m1 = apply4m<E>(apply4m<E>(apply4m<E>(v[0].pos, F.viewport_inv, F.pm_viewport_inv), F.proj_inv, F.pm_proj_inv), F.view_inv, F.pm_view_inv);
+  V4 m2 = apply4m<E>(apply4m<E>(apply4m<E>(v[1].pos, F.viewport_inv, F.pm_viewport_inv), F.proj_inv, F.pm_proj_inv), F.view_inv, F.pm_view_inv);
+  V4 m3 = apply4m<E>(apply4m<E>(apply4m<E>(v[2].pos, F.viewport_inv, F.pm_viewport_inv), F.proj_inv, F.pm_proj_inv), F.view_inv, F.pm_view_inv);
   f.facenor = unit4<E>(cross4<E>(sub4(m2, m1), sub4(m3, m1)));
   BarySetup bs = bary_setup<E>(v[0].pos.x, v[0].pos.y, v[1].pos.x, v[1].pos.y, v[2].pos.x, v[2].pos.y);
   const float px = (float)x + 0.5f, py = (float)y + 0.5f;
@@ -642,7 +848,43 @@ __device__ __forceinline__ float go_log2(float x) {
   if (fr == 0.5) return (float)(e - 1);
   return (float)(log(fr) * (1.0 / 0.693147180559945309417232121458176568) + (double)e);
 }
-__device__ __forceinline__ float go_pow(float x, float y) { return (float)pow((double)x, (double)y); }
+
+// math.Pow of the Go standard library (src/math/pow.go) for the arguments the path produces (finite x >= 0,
+// finite y > 0): x**y = x**yf * x**yi, integer part by repeated squaring of the Frexp mantissa (only IEEE
+// multiplications => bit-identical to Go for integer y such as every shininess in the fixtures and AO's 10000),
+// fractional part by exp(yf*log(x)). Anything else goes to the CUDA library pow (special values agree).
+__device__ __forceinline__ double go_pow64(double x, double y) {
+  if (y == 0.0 || x == 1.0) return 1.0;
+  if (y == 1.0) return x;
+  if (!(x > 0.0) || !(y > 0.0) || isinf(x) || isinf(y)) {
+    if (x == 0.0 && y > 0.0 && !isinf(y) && !signbit(x)) return 0.0;
+    return pow(x, y);
+  }
+  if (y == 0.5) return sqrt(x);
+  double yi;
+  double yf = modf(y, &yi);
+  if (yi >= 9223372036854775808.0) return pow(x, y);
+  double a1 = 1.0;
+  long long ae = 0;
+  if (yf != 0.0) {
+    if (yf > 0.5) { yf -= 1.0; yi += 1.0; }
+    a1 = exp(yf * log(x));
+  }
+  int xe_i;
+  double x1 = frexp(x, &xe_i);
+  long long xe = xe_i;
+  for (long long i = (long long)yi; i != 0; i >>= 1) {
+    if (xe < -(1 << 12) || (1 << 12) < xe) { ae += xe; break; }
+    if (i & 1) { a1 = __dmul_rn(a1, x1); ae += xe; }
+    x1 = __dmul_rn(x1, x1);
+    xe <<= 1;
+    if (x1 < .5) { x1 = __dadd_rn(x1, x1); xe--; }
+  }
+  if (ae > 100000) ae = 100000;
+  if (ae < -100000) ae = -100000;
+  return ldexp(a1, (int)ae);
+}
+__device__ __forceinline__ float go_pow(float x, float y) { return (float)go_pow64((double)x, (double)y); }
 
 template <bool E>
 __device__ uint32_t fragment_shader(const DevScene& S, const DevFrame& F, const prc_material& m, const Frag& info) {
@@ -694,7 +936,8 @@ __device__ uint32_t fragment_shader(const DevScene& S, const DevFrame& F, const 
 template <bool E>
 __device__ bool shading_visibility(const DevFrame& F, const DevLight& l, const Frag& info) {
   if (!l.cast_shadow) return true;
-  V4 sc = pos4(apply4<E>(apply4<E>(apply4<E>(apply4<E>(V4{(float)info.X, (float)info.Y, info.depth, 1.0f}, F.vtw), l.view), l.proj), F.viewport));
+  V4 sc = pos4(apply4m<E>(apply4m<E>(apply4m<E>(apply4m<E>(V4{(float)info.X, (float)info.Y, info.depth, 1.0f}, F.vtw, F.pm_vtw), l.view, l.pm_view), l.proj, l.pm_proj),
+                          F.viewport, F.pm_viewport));
   long long lx = go_int(sc.x), ly = go_int(sc.y);
   long long idx = (long long)((unsigned long long)lx + (unsigned long long)ly * (unsigned long long)F.W);
   if (idx > 0 && idx < (long long)F.W * F.H) {
@@ -726,11 +969,11 @@ __device__ float max_elevation(const DevFrame& F, const float* __restrict__ ao_d
   }
   return (float)atan((double)m);
 }
-__device__ uint32_t ao_shade(const DevFrame& F, const AoConsts& A, const float* __restrict__ ao_depth, int X, int Y, uint32_t col) {
+__device__ uint32_t ao_shade(const DevFrame& F, const AoConsts* __restrict__ A, const float* __restrict__ ao_depth, int X, int Y, uint32_t col) {
   float total = 0.0f;
 #pragma unroll 1
-  for (int k = 0; k < 8; k++) total += A.half_pi - max_elevation(F, ao_depth, X, Y, A.cosv[k], A.sinv[k]);
-  total = __fdiv_rn(total, A.four_pi);
+  for (int k = 0; k < 8; k++) total += A->half_pi - max_elevation(F, ao_depth, X, Y, A->cosv[k], A->sinv[k]);
+  total = __fdiv_rn(total, A->four_pi);
   total = go_pow(total, 10000.0f);
   return go_u8(total * (float)chan(col, 0)) | (go_u8(total * (float)chan(col, 1)) << 8) | (go_u8(total * (float)chan(col, 2)) << 16) | (col & 0xff000000u);
 }
@@ -743,7 +986,7 @@ __device__ __forceinline__ const prc_material* mat_at(const DevScene& S, int32_t
 
 // (*Renderer).shade for a fragment `frag` (own X,Y,mat) whose G-buffer record is `info`
 template <bool E>
-__device__ uint32_t shade_pixel(const DevScene& S, const DevFrame& F, const AoConsts& A, const float* ao_depth, const Frag& info, int fragX, int fragY,
+__device__ uint32_t shade_pixel(const DevScene& S, const DevFrame& F, const AoConsts* __restrict__ A, const float* ao_depth, const Frag& info, int fragX, int fragY,
                                 int32_t frag_mat) {
   uint32_t col = info.col;
   const prc_material* mat = mat_at(S, frag_mat);
@@ -764,7 +1007,7 @@ __device__ uint32_t shade_pixel(const DevScene& S, const DevFrame& F, const AoCo
 // special[0] = colour of pixel (0,0) (pre-gamma), special[1] = colour of every uncovered pixel (bug-list 3:
 // an uncovered pixel carries a zero Fragment, so shade() reads G(0,0) with MaterialID 0 — raster.go:326-332)
 template <bool E>
-__global__ void k_shade_special(DevScene S, DevFrame F, AoConsts A, const unsigned long long* __restrict__ keys, GBuf G, uint32_t* special) {
+__global__ void k_shade_special(DevScene S, DevFrame F, const AoConsts* __restrict__ A, const unsigned long long* __restrict__ keys, GBuf G, uint32_t* special) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (keys[0] == 0) {
     special[0] = F.background;
@@ -781,7 +1024,7 @@ __global__ void k_shade_special(DevScene S, DevFrame F, AoConsts A, const unsign
 }
 
 template <bool E>
-__global__ void __launch_bounds__(128) k_shade(DevScene S, DevFrame F, AoConsts A, const unsigned long long* __restrict__ keys, GBuf G,
+__global__ void __launch_bounds__(128) k_shade(DevScene S, DevFrame F, const AoConsts* __restrict__ A, const unsigned long long* __restrict__ keys, GBuf G,
                                                const uint32_t* __restrict__ special, uint32_t* __restrict__ image) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = F.row0 + blockIdx.y * 4 + (threadIdx.x >> 5);

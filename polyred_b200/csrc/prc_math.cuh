@@ -84,6 +84,24 @@ __device__ __forceinline__ V4 apply4(V4 v, const float* __restrict__ a) {  // :1
   r.w = fma32<E>(a[12], v.x, fma32<E>(a[13], v.y, fma32<E>(a[14], v.z, a[15] * v.w)));
   return r;
 }
+// Apply with a per-matrix "plain" mask: bit i set <=> entry i is 0 or +-2^k, for which
+// FMA(m, v, c) == RN(m*v + c) with m*v exact, i.e. a plain float multiply-add is bit-identical to the
+// reference's float64 FMA (no double rounding can occur when one addend is a float32 and the other an
+// exactly representable float32 product). The mask is uniform (kernel parameter), so no divergence.
+template <bool E>
+__device__ __forceinline__ float fma32m(bool plain, float m, float v, float c) {
+  if (plain) return m * v + c;
+  return fma32<E>(m, v, c);
+}
+template <bool E>
+__device__ __forceinline__ V4 apply4m(V4 v, const float* __restrict__ a, uint32_t pm) {
+  V4 r;
+  r.x = fma32m<E>(pm & 1u, a[0], v.x, fma32m<E>(pm & 2u, a[1], v.y, fma32m<E>(pm & 4u, a[2], v.z, a[3] * v.w)));
+  r.y = fma32m<E>(pm & 16u, a[4], v.x, fma32m<E>(pm & 32u, a[5], v.y, fma32m<E>(pm & 64u, a[6], v.z, a[7] * v.w)));
+  r.z = fma32m<E>(pm & 256u, a[8], v.x, fma32m<E>(pm & 512u, a[9], v.y, fma32m<E>(pm & 1024u, a[10], v.z, a[11] * v.w)));
+  r.w = fma32m<E>(pm & 4096u, a[12], v.x, fma32m<E>(pm & 8192u, a[13], v.y, fma32m<E>(pm & 16384u, a[14], v.z, a[15] * v.w)));
+  return r;
+}
 template <bool E>
 __device__ __forceinline__ V4 cross4(V4 v, V4 u) {  // :130-137
   V4 r;

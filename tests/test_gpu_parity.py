@@ -77,6 +77,18 @@ def test_fast_fma_mode_within_gate(monkeypatch):
     assert_north_star_gate(st, tie_budget=8)
 
 
+def test_bin_overflow_rerenders_frame(monkeypatch):
+    """The (tile, triangle) bin array is sized optimistically; on overflow the frame is re-rendered
+    with a larger array (no host round trip in the common case). Force the path with a tiny array."""
+    monkeypatch.setenv("PRC_BINS_INIT", "16")
+    s, cam = synth.mesh_scene(subdiv=40, with_ground=True, shadows=True, ao=False)
+    g, c = make_renderers(s, cam, 320, 200, shadow=True, gamma=True)
+    st, ig, ic = compare_frames(g, c, 320, 200, n_lights_cast=(1,))
+    _report("bins-retry", st)
+    assert_bit_exact(st)
+    assert st["rgba_px_diff"] == 0, st
+
+
 def test_errors_surface_no_fallback():
     from polyred_b200._lib import PolyredCudaError, CudaBackend
     from polyred_b200 import _abi as A
