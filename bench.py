@@ -183,17 +183,14 @@ def run_cuda(args):
     out = np.zeros((h, w, 4), np.uint8)
 
     # ---- multi-GPU partition: screen strips (16-row aligned) + shadow (light, row-range) shards ----
+    from polyred_b200 import partition
     if world > 1:
-        tiles = (h + 15) // 16
-        cuts = [min(h, ((tiles * k) // world) * 16) for k in range(world + 1)]
-        cuts[-1] = h
+        cuts = partition.strips(h, world)
         row0, row1 = cuts[rank], cuts[rank + 1]
         for f in (fd, fd_e2e):
             f.struct.row0, f.struct.row1 = row0, row1
-        # shadow work units: Ls lights x (world // Ls or 1) row ranges, round-robin over ranks
-        parts = max(1, world // max(1, len(cast)))
-        units = [(li, (h * p) // parts, (h * (p + 1)) // parts) for li in cast for p in range(parts)]
-        my_units = [u for k, u in enumerate(units) if k % world == rank]
+        units = partition.shadow_units(h, world, cast)   # (light, row0, row1, owner)
+        my_units = [u for u in units if u[3] == rank]
     else:
         row0, row1 = 0, h
         units = my_units = []
@@ -203,25 +200,23 @@ def run_cuda(args):
             be.render(fdesc, host_out)
             return
         # phase 1: my shadow shards
-        for li, a, b in my_units:
+        for li, a, b, _ in my_units:
             be.render_shadows(fdesc, 1 << li, a, b)
         be.sync()
         # exchange: every unit's row range is broadcast from its owner (NCCL over NVLink); the maps are
         # max-combined implicitly because ranges are disjoint and the receiving rows were not touched.
-        for k, (li, a, b) in enumerate(units):
+        for li, a, b, owner in units:
             ptr, nbytes = be.device_shadowmap(li)
             t_ = torch.as_tensor(cai(ptr + a * w * 4, (b - a) * w * 4), device=torch.device("cuda", local))
-            dist.broadcast(t_, src=k % world)
+            dist.broadcast(t_, src=owner)
         torch.cuda.synchronize()
         be.render_main(fdesc, None)
         # gather the image strips to rank 0
         ptr, nbytes = be.device_image()
         img = torch.as_tensor(cai(ptr, nbytes), device=torch.device("cuda", local))
-        for k in range(world):
-            a, b = cuts[k], cuts[k + 1]
-            seg = img[(h - b) * w * 4:(h - a) * w * 4]
-            if k == 0:
-                continue
+        for k in range(1, world):
+            ia, ib = partition.image_rows(h, cuts[k], cuts[k + 1])
+            seg = img[ia * w * 4:ib * w * 4]
             if rank == k:
                 dist.send(seg, dst=0)
             elif rank == 0:

@@ -1,0 +1,89 @@
+"""CPU: host-side mirror of the renderer front end (scene traversal, flat material table, uniforms)."""
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+from polyred_b200 import _abi as A
+from polyred_b200 import camera, gomath as gm, light, material, render, scene, synth
+
+
+def _tri(n=1, z=0.0):
+    return np.tile(np.array([[[0, 0, z], [1, 0, z], [0, 1, z]]], np.float32), (n, 1, 1))
+
+
+def test_traversal_order_and_matrix_chain():
+    """scene/core.go:86-111, 157-219: root leaves get root.ModelMatrix(); grouped leaves get root*group chain;
+    the renderer then multiplies by the geometry's own matrix (render/raster.go:242)."""
+    a, b, c = scene.Geometry(_tri()), scene.Geometry(_tri()), scene.Geometry(_tri())
+    g = scene.Group(b)
+    g.Translate(1, 2, 3)
+    inner = scene.Group(c)
+    inner.Scale(2, 2, 2)
+    g.Add(inner)
+    s = scene.Scene(a, light.Point(), g)
+    geos = s.geometries()
+    assert [x[0] for x in geos] == [a, b, c]
+    assert np.array_equal(geos[0][1], gm.identity())
+    assert np.array_equal(geos[1][1], g.ModelMatrix())
+    assert np.array_equal(geos[2][1], gm.mulm(g.ModelMatrix(), inner.ModelMatrix()))
+
+
+def test_flat_material_table_matches_cpuForwardPass():
+    """render/raster.go:252-262: flat id = base + local, negative ids stay negative, table = concatenation."""
+    m0, m1, m2 = (material.BlinnPhong(texture=material.Texture.uniform((i, i, i, 255))) for i in (1, 2, 3))
+    g0 = scene.Geometry(_tri(3), mat=[0, 1, -1], materials=[m0, m1])
+    g1 = scene.Geometry(_tri(2), mat=[0, -1], materials=[m2])
+    sd = render.SceneDesc(scene.Scene(g0, g1))
+    assert sd.mat.tolist() == [0, 1, -1, 2, -1]
+    assert sd.obj_start.tolist() == [0, 3, 5]
+    assert sd.struct.n_materials == 3 and sd.struct.n_textures == 3
+
+
+def test_lights_order_and_center():
+    p, d, amb = light.Point(position=(1, 2, 3)), light.Directional(direction=(0, -2, 0)), light.Ambient(intensity=0.5)
+    s = scene.Scene(amb, d, scene.Geometry(_tri()), p)
+    src, env = s.Lights()
+    assert src == [d, p] and env == [amb]
+    assert np.allclose(d.direction, [0, -1, 0])
+    # Scene.Center (scene/scene.go:49-52): model-space AABB of ALL root objects, lights included
+    assert np.allclose(s.Center(), [(0 + 1) / 2, (0 + 2) / 2, (0 + 3) / 2])
+
+
+def test_frame_uniforms_follow_the_reference_formulas():
+    s, cam = synth.city_scene(n_objects=3, obj_stacks=4, obj_slices=4, ground_cells=2, tex_size=8)
+    r = render.NewRenderer(render.Camera(cam), render.Size(64, 36), render.Scene(s), render.ShadowMap(True), render._Backend(ob.OracleBackend()))
+    fd = r.frame_desc()
+    f = fd.struct
+    assert f.flags & A.PRC_FRAME_PERSPECT and f.flags & A.PRC_FRAME_SHADOWMAP
+    view, proj, vp = cam.ViewMatrix(), cam.ProjMatrix(), gm.viewport_matrix(64, 36)
+    geos = s.geometries()
+    model = gm.mulm(geos[2][1], geos[2][0].ModelMatrix())
+    want_trans = gm.mulm(gm.mulm(proj, view), model)
+    assert np.array_equal(np.array(f.objects[2].trans[:], np.float32).reshape(4, 4), want_trans)
+    assert np.array_equal(np.array(f.objects[2].normal[:], np.float32).reshape(4, 4), gm.transpose(gm.inv(model)))
+    assert np.array_equal(np.array(f.viewport_to_world[:], np.float32).reshape(4, 4), gm.mulm(gm.mulm(gm.inv(view), gm.inv(proj)), gm.inv(vp)))
+    # lights 0,2,4,6 cast; each casting point light has an orthographic camera fitted to the view frustum (shadow.go:41-86)
+    assert [f.lights[i].cast_shadow for i in range(8)] == [1, 0, 1, 0, 1, 0, 1, 0]
+    assert isinstance(r._light_cams[0], camera.Orthographic) and r._light_cams[1] is None
+
+
+def test_casting_directional_light_is_an_error_not_a_guess():
+    """render/shadow.go:67-86,123: only *light.Point gets a light camera; a casting Directional panics."""
+    s = scene.Scene(light.Directional(cast_shadow=True), scene.Geometry(_tri(), materials=[material.Default()]))
+    with pytest.raises(NotImplementedError):
+        render.NewRenderer(render.Camera(camera.Perspective()), render.Scene(s), render.ShadowMap(True), render._Backend(ob.OracleBackend()))
+
+
+def test_unsupported_options_raise():
+    s = scene.Scene(scene.Geometry(_tri(), materials=[material.Default()]))
+    with pytest.raises(NotImplementedError):
+        render.NewRenderer(render.Camera(camera.Perspective()), render.Scene(s), render.MSAA(2), render._Backend(ob.OracleBackend()))
+
+
+def test_oracle_is_deterministic_and_mt_mode_agrees_without_ties():
+    s, cam = synth.mesh_scene(subdiv=12)
+    a = render.NewRenderer(render.Camera(cam), render.Size(96, 60), render.Scene(s), render._Backend(ob.OracleBackend())).Render()
+    b = render.NewRenderer(render.Camera(cam), render.Size(96, 60), render.Scene(s), render._Backend(ob.OracleBackend())).Render()
+    c = render.NewRenderer(render.Camera(cam), render.Size(96, 60), render.Scene(s), render._Backend(ob.OracleBackend(threads=4))).Render()
+    assert np.array_equal(a, b)
+    assert (np.abs(a.astype(int) - c.astype(int)).max(axis=2) > 0).mean() < 0.01  # Workers>1 only differs at depth ties

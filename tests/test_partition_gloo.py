@@ -1,0 +1,78 @@
+"""CPU, world_size 2 over gloo: the multi-GPU host logic (screen strips, shadow shards, image gather)
+reassembles exactly the single-process result."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from polyred_b200 import partition
+
+
+def test_strips_and_units_cover_everything_once():
+    for h in (2160, 1080, 270, 100, 17):
+        for world in (1, 2, 4, 8):
+            cuts = partition.strips(h, world)
+            assert cuts[0] == 0 and cuts[-1] == h and all(a <= b for a, b in zip(cuts, cuts[1:]))
+            assert all(c % 16 == 0 for c in cuts[:-1])
+            units = partition.shadow_units(h, world, [0, 2, 4, 6])
+            for li in (0, 2, 4, 6):
+                rows = sorted((a, b) for l, a, b, _ in units if l == li)
+                assert rows[0][0] == 0 and rows[-1][1] == h and all(x[1] == y[0] for x, y in zip(rows, rows[1:]))
+            if world == 8:
+                assert sorted(o for *_, o in units) == list(range(8))  # one equal shard per GPU (C3)
+    assert partition.image_rows(2160, 0, 272) == (1888, 2160)
+
+
+def _worker(rank, world, port, h, w, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(5)
+    full_img = rng.integers(0, 255, size=(h, w, 4), dtype=np.uint8)      # what one GPU would render
+    full_maps = {li: rng.random((h, w)).astype(np.float32) for li in (0, 2)}
+    cuts = partition.strips(h, world)
+    units = partition.shadow_units(h, world, [0, 2])
+    # phase 1: each rank "rasterises" only its shadow units, then every unit is broadcast from its owner
+    maps = {li: np.zeros((h, w), np.float32) for li in (0, 2)}
+    for li, a, b, owner in units:
+        if owner == rank:
+            maps[li][a:b] = full_maps[li][a:b]
+    for li, a, b, owner in units:
+        t = torch.from_numpy(maps[li][a:b])
+        dist.broadcast(t, src=owner)
+    ok_maps = all(np.array_equal(maps[li], full_maps[li]) for li in (0, 2))
+    # phase 2: each rank "shades" its strip; strips are gathered to rank 0 in image order
+    img = np.zeros((h, w, 4), np.uint8)
+    r0, r1 = partition.image_rows(h, cuts[rank], cuts[rank + 1])
+    img[r0:r1] = full_img[r0:r1]
+    for k in range(1, world):
+        a, b = partition.image_rows(h, cuts[k], cuts[k + 1])
+        seg = torch.from_numpy(img[a:b])
+        if rank == k:
+            dist.send(seg, dst=0)
+        elif rank == 0:
+            dist.recv(seg, src=k)
+    ok_img = np.array_equal(img, full_img) if rank == 0 else True
+    q.put((rank, ok_maps, ok_img))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_exchange_reassembles_the_frame():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 100, 40, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(m and i for _, m, i in res), res
