@@ -139,7 +139,7 @@ def run_reference(args):
                          "sample": "full frame of the same workload, C++ restatement of the reference CPU path (not the Go binary), one task per 256 triangles / 32 pixels, per-pixel spinlocks"},
         "e2e": {"value": val, "unit": "Mtris/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def cai(ptr, nbytes):
@@ -182,48 +182,21 @@ def run_cuda(args):
     fd_e2e = r.frame_desc(no_readback=False)
     out = np.zeros((h, w, 4), np.uint8)
 
-    # ---- multi-GPU partition: screen strips (16-row aligned) + shadow (light, row-range) shards ----
-    from polyred_b200 import partition
+    # ---- multi-GPU partition: screen strips + shadow (light, row-range) shards (polyred_b200/distributed.py) ----
+    df = None
+    units = []
     if world > 1:
-        cuts = partition.strips(h, world)
-        row0, row1 = cuts[rank], cuts[rank + 1]
-        for f in (fd, fd_e2e):
-            f.struct.row0, f.struct.row1 = row0, row1
-        units = partition.shadow_units(h, world, cast)   # (light, row0, row1, owner)
-        my_units = [u for u in units if u[3] == rank]
-    else:
-        row0, row1 = 0, h
-        units = my_units = []
+        from polyred_b200.distributed import DistributedFrame
+        df = DistributedFrame(r, rank, world, local)
+        df.prepare(fd)
+        df.prepare(fd_e2e)
+        units = df.units
 
     def step(fdesc, host_out):
         if world == 1:
             be.render(fdesc, host_out)
-            return
-        # phase 1: my shadow shards
-        for li, a, b, _ in my_units:
-            be.render_shadows(fdesc, 1 << li, a, b)
-        be.sync()
-        # exchange: every unit's row range is broadcast from its owner (NCCL over NVLink); the maps are
-        # max-combined implicitly because ranges are disjoint and the receiving rows were not touched.
-        for li, a, b, owner in units:
-            ptr, nbytes = be.device_shadowmap(li)
-            t_ = torch.as_tensor(cai(ptr + a * w * 4, (b - a) * w * 4), device=torch.device("cuda", local))
-            dist.broadcast(t_, src=owner)
-        torch.cuda.synchronize()
-        be.render_main(fdesc, None)
-        # gather the image strips to rank 0
-        ptr, nbytes = be.device_image()
-        img = torch.as_tensor(cai(ptr, nbytes), device=torch.device("cuda", local))
-        for k in range(1, world):
-            ia, ib = partition.image_rows(h, cuts[k], cuts[k + 1])
-            seg = img[ia * w * 4:ib * w * 4]
-            if rank == k:
-                dist.send(seg, dst=0)
-            elif rank == 0:
-                dist.recv(seg, src=k)
-        torch.cuda.synchronize()
-        if host_out is not None and rank == 0:
-            host_out.reshape(-1)[:] = img.cpu().numpy()
+        else:
+            df.render(fdesc, host_out)
 
     def barrier():
         if dist is not None:
@@ -318,7 +291,7 @@ def run_cuda(args):
     }
     if args.cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args, wl, s, cam)
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -342,7 +315,20 @@ def cpu_baseline(args, wl, s, cam):
                       "(tasks of 256 triangles / 32 pixels, per-pixel spinlocks); not the Go binary"}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, warnings) to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # libraries that print to fd 1 (e.g. "NCCL version ...") must not corrupt the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

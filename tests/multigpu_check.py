@@ -1,0 +1,45 @@
+"""Run under torchrun on N GPUs: the N-GPU frame must be bit-identical to rank 0's own 1-GPU frame.
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tests/multigpu_check.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from polyred_b200 import render, synth
+    from polyred_b200.distributed import DistributedFrame
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = True
+    for name, (s, cam), w, h in (
+        ("city", synth.city_scene(n_objects=64, obj_stacks=16, obj_slices=16, ground_cells=80, tex_size=64), 960, 540),
+        ("c2-ao", synth.mesh_scene(subdiv=40, with_ground=True, shadows=True, ao=True), 320, 200),
+    ):
+        opts = [render.Camera(cam), render.Size(w, h), render.Scene(s), render.ShadowMap(True), render.GammaCorrection(True)]
+        r = render.NewRenderer(*opts, render.CUDA(local))
+        r._ensure_uploaded()
+        df = DistributedFrame(r, rank, world, local)
+        out = np.zeros((h, w, 4), np.uint8)
+        for _ in range(2):
+            df.render(df.prepare(r.frame_desc(no_readback=True)), out)
+        if rank == 0:
+            ref = render.NewRenderer(*opts, render.CUDA(local)).Render()
+            nd = int((np.abs(out.astype(int) - ref.astype(int)).max(axis=2) > 0).sum())
+            print(f"[multigpu_check] {name} {w}x{h} world={world}: pixels differing from the 1-GPU frame = {nd}")
+            ok = ok and nd == 0
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0 and not ok:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()
