@@ -181,6 +181,7 @@ def run_cuda(args):
     fd = r.frame_desc(no_readback=True)
     fd_e2e = r.frame_desc(no_readback=False)
     out = np.zeros((h, w, 4), np.uint8)
+    e2e_out = [None, out]
 
     # ---- multi-GPU partition: screen strips + shadow (light, row-range) shards (polyred_b200/distributed.py) ----
     df = None
@@ -194,9 +195,13 @@ def run_cuda(args):
 
     def step(fdesc, host_out):
         if world == 1:
-            be.render(fdesc, host_out)
+            # e2e: rgba_out = NULL + prc_host_image = the frame DMA'd into the library's page-locked double buffer and
+            # read in place by the caller (what the Go shim does); the device-resident leg passes PRC_FRAME_NO_READBACK
+            be.render(fdesc, None)
+            if host_out is not None:
+                host_out[0] = be.host_image(w, h)
         else:
-            df.render(fdesc, host_out)
+            df.render(fdesc, host_out[1] if host_out is not None else None)
 
     def barrier():
         if dist is not None:
@@ -239,7 +244,7 @@ def run_cuda(args):
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step(fd_e2e, out)
+        step(fd_e2e, e2e_out)
     barrier()
     wall_e2e = time.perf_counter() - t0
 
@@ -274,7 +279,7 @@ def run_cuda(args):
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "mpixels_per_s": px * fps / 1e6, "frames_per_s": fps, "wall_ms_per_step": wall_ms / args.steps,
         "config": {"workload": f"{args.workload}: {wl['desc']}", "n_tris": int(n_tris), "n_valid_tris": n_valid, "width": w, "height": h,
-                   "fma": os.environ.get("PRC_FMA", "exact"), "l2": "inputs (1.1 GB scene, 0.9 GB frame buffers) larger than L2; no explicit flush",
+                   "fma": os.environ.get("PRC_FMA", "mixed"), "l2": "inputs (1.1 GB scene, 0.9 GB frame buffers) larger than L2; no explicit flush",
                    "partition": "1 GPU" if world == 1 else f"{world} screen strips + {len(units)} shadow shards, NCCL broadcast/send-recv"},
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s",
                      "frac": achieved / pk["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms,

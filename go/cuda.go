@@ -109,7 +109,7 @@ type prcFrame struct {
 
 type cudaBackend struct {
 	lib                                                                  uintptr
-	fnOpen, fnClose, fnLastError, fnSceneUpload, fnShadowReset, fnRender uintptr
+	fnOpen, fnClose, fnLastError, fnSceneUpload, fnShadowReset, fnRender, fnHostImage uintptr
 	ctx                                                                  uintptr
 
 	// flattened scene, kept alive while the library borrows it during prc_scene_upload
@@ -139,7 +139,7 @@ func openCUDA(device int) *cudaBackend {
 	}
 	b := &cudaBackend{lib: lib,
 		fnOpen: sym("prc_open"), fnClose: sym("prc_close"), fnLastError: sym("prc_last_error"),
-		fnSceneUpload: sym("prc_scene_upload"), fnShadowReset: sym("prc_shadow_reset"), fnRender: sym("prc_render")}
+		fnSceneUpload: sym("prc_scene_upload"), fnShadowReset: sym("prc_shadow_reset"), fnRender: sym("prc_render"), fnHostImage: sym("prc_host_image")}
 	if v, _, _ := purego.SyscallN(sym("prc_abi_version")); uint32(v) != prcABIVersion {
 		panic("render: libpolyred_cuda.so ABI version mismatch")
 	}
@@ -341,12 +341,15 @@ func (r *Renderer) renderCUDA() *image.RGBA {
 	for i := 0; i < 256; i++ { // shader.GammaCorrection (shader/gamma.go:13-18) as a table
 		f.GammaLUT[i] = uint8(color.FromLinear2sRGB(float32(i)/0xff)*0xff + 0.5)
 	}
-	if r.outBuf == nil || r.outBuf.Bounds().Dx() != w || r.outBuf.Bounds().Dy() != h {
-		r.outBuf = image.NewRGBA(image.Rect(0, 0, w, h))
-	}
-	rc, _, _ := purego.SyscallN(b.fnRender, b.ctx, uintptr(unsafe.Pointer(&f)), uintptr(unsafe.Pointer(unsafe.SliceData(r.outBuf.Pix))))
+	// rgba_out == NULL: the frame lands in the library's page-locked double buffer and is wrapped in place
+	// (zero copy). Like the reference's own double buffer (raster.go:86,201-206) it is valid until two frames later.
+	rc, _, _ := purego.SyscallN(b.fnRender, b.ctx, uintptr(unsafe.Pointer(&f)), 0)
 	runtime.KeepAlive(objs); runtime.KeepAlive(lights); runtime.KeepAlive(amb); runtime.KeepAlive(shadowTrans)
 	b.check(rc, "prc_render")
+	var ptr, n uint64
+	rc, _, _ = purego.SyscallN(b.fnHostImage, b.ctx, uintptr(unsafe.Pointer(&ptr)), uintptr(unsafe.Pointer(&n)))
+	b.check(rc, "prc_host_image")
+	r.outBuf = &image.RGBA{Pix: unsafe.Slice((*uint8)(unsafe.Pointer(uintptr(ptr))), int(n)), Stride: 4 * w, Rect: image.Rect(0, 0, w, h)}
 	r.passGPU["forward"], r.passGPU["deferred"], r.passGPU["gamma"] = true, true, true
 	return r.outBuf
 }

@@ -226,6 +226,10 @@ int32_t prc_shadow_reset(prc_ctx* ctx);
  * (row r = screen y = height-1-r, buffer.go:160-166, 225). With row0/row1 set, only image
  * rows of that strip are written. */
 int32_t prc_render(prc_ctx* ctx, const prc_frame* frame, uint8_t* rgba_out);
+/* Zero-copy result: with rgba_out == NULL the frame is left in one of two library-owned page-locked host images
+ * used alternately (the reference's double buffer, render/raster.go:86,201-206: the returned *image.RGBA aliases
+ * the buffer until two frames later). Returns that image (width*height*4 bytes, image order). */
+int32_t prc_host_image(prc_ctx* ctx, uint64_t* host_ptr, uint64_t* bytes);
 int32_t prc_read_gbuffer(prc_ctx* ctx, prc_gbuffer_host* out);
 int32_t prc_read_shadowmap(prc_ctx* ctx, uint32_t light, float* out /* [width*height], idx = x + y*width */);
 int32_t prc_get_timings(prc_ctx* ctx, prc_timings* out);

@@ -45,11 +45,12 @@ def lib():
         L.prc_device_shadowmap.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.prc_render_shadows.argtypes = [vp, C.POINTER(A.prc_frame), C.c_uint32, C.c_uint32, C.c_uint32]
         L.prc_render_main.argtypes = [vp, C.POINTER(A.prc_frame), vp]
+        L.prc_host_image.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.prc_stream.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.prc_sync.argtypes = [vp]
         for name in ("prc_open", "prc_close", "prc_scene_upload", "prc_shadow_reset", "prc_render", "prc_read_gbuffer",
                      "prc_read_shadowmap", "prc_get_timings", "prc_device_image", "prc_device_shadowmap",
-                     "prc_render_shadows", "prc_render_main", "prc_stream", "prc_sync"):
+                     "prc_render_shadows", "prc_render_main", "prc_stream", "prc_sync", "prc_host_image"):
             getattr(L, name).restype = C.c_int32
         if L.prc_abi_version() != A.PRC_ABI_VERSION:
             raise PolyredCudaError(A.PRC_ERR_INVALID, "ABI version mismatch")
@@ -126,6 +127,17 @@ class CudaBackend(Backend):
             raise PolyredCudaError(rc, f"prc_open(device={device}) failed (is a CUDA device visible? there is no CPU fallback)")
         super().__init__(L, h)
         self.device = device
+
+    def host_image(self, w, h) -> np.ndarray:
+        """The last frame, in place in the library's page-locked double buffer (no copy)."""
+        p, n = C.c_uint64(), C.c_uint64()
+        self._check(self.L.prc_host_image(self.h, C.byref(p), C.byref(n)))
+        key = (p.value, n.value, w, h)
+        views = self.__dict__.setdefault("_host_views", {})
+        if key not in views:
+            buf = (C.c_uint8 * n.value).from_address(p.value)
+            views[key] = np.frombuffer(buf, dtype=np.uint8).reshape(h, w, 4)
+        return views[key]
 
     def device_image(self):
         p, n = C.c_uint64(), C.c_uint64()

@@ -24,7 +24,10 @@ struct prc_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   std::string err;
-  bool exact = true;  // PRC_FMA=exact|fast (see DESIGN.md "Arithmetic contract")
+  // PRC_FMA = exact | mixed (default) | fast, see DESIGN.md "Arithmetic contract":
+  //   exact: every math.FMA is a float64 fma rounded to float32; mixed: exact for everything that decides the
+  //   G-buffer and the shadow maps (geometry, raster, resolve), fmaf in the deferred shading; fast: fmaf everywhere.
+  bool exact = true, exact_shade = false;
 
   // scene
   bool has_scene = false;
@@ -38,15 +41,19 @@ struct prc_ctx {
   // frame buffers
   int W = 0, H = 0;
   DBuf d_keys, d_ga, d_gb, d_gc, d_gd, d_ao, d_image, d_special, d_counters;
-  DBuf d_large, d_clipq, d_tilecount, d_tilestart, d_cursor, d_bins, d_active;
+  DBuf d_large, d_clipq, d_tilecount, d_tilestart, d_cursor, d_bins, d_active, d_chunksum, d_targets, d_frame_sh;
+  uint32_t n_targets = 1;
+  uint32_t target_of_light[64] = {0};
   DBuf d_xf, d_lights, d_ambient, d_gamma, d_frame, d_aoc;
   std::vector<DevLight> h_lights;    // host staging of the per-frame light table
+  TileTargets h_targets{};
   std::vector<DBuf> d_shadow_trans;  // per light
   std::vector<DBuf> d_shadow;        // per light, persistent
   unsigned int large_cap = 0, clip_cap = 0, bins_cap = 0;
   AoConsts ao{};
-  void* h_pinned = nullptr;  // pinned staging for the RGBA readback
-  size_t h_pinned_cap = 0;
+  uint8_t* h_img[2] = {nullptr, nullptr};  // page-locked host images, used alternately
+  size_t h_img_cap = 0;
+  int h_img_cur = 0;
   Counters* h_counters = nullptr;  // pinned
 
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -136,52 +143,66 @@ uint32_t plain_mask(const float* m) {
 
 inline unsigned int cdiv(unsigned long long a, unsigned int b) { return (unsigned int)((a + b - 1) / b); }
 
-// ---- one raster pass (camera or one shadow light) --------------------------------------------
+// ---- one raster pass (camera or one shadow light): geometry + in-thread small raster; large triangles and
+// (camera only) triangles needing clipping are queued. No host round trip. -----------------------------------
 template <bool E, bool SHADOW>
-int32_t raster_pass(prc_ctx* ctx, const DevFrame& F, const float* shadow_trans, float* smap) {
+int32_t raster_pass(prc_ctx* ctx, const DevFrame& F, const GeomViews& V) {
   cudaStream_t st = ctx->stream;
   Counters* cnt = (Counters*)ctx->d_counters.p;
-  // reset n_large / n_clip / n_bin_total (keep n_nan accumulating over the frame)
-  CK(cudaMemsetAsync(cnt, 0, 16, st));
-  const int tiles_x = (F.W + PRC_TILE - 1) / PRC_TILE, tiles_y = (F.H + PRC_TILE - 1) / PRC_TILE;
-  const int n_tiles = tiles_x * tiles_y;
   unsigned long long* keys = (unsigned long long*)ctx->d_keys.p;
   LargeRec* large = (LargeRec*)ctx->d_large.p;
   unsigned int* clipq = (unsigned int*)ctx->d_clipq.p;
   // device-resident copy of the frame for the rare non-inlined generic path (see geom_generic)
-  UPLOAD(ctx->d_frame, &F, sizeof(DevFrame));
+  DBuf& fb = SHADOW ? ctx->d_frame_sh : ctx->d_frame;
+  UPLOAD(fb, &F, sizeof(DevFrame));
   if (ctx->S.n_tris) {
     KTimer kt(ctx, SHADOW ? PRC_K_GEOM_SHADOW : PRC_K_GEOM_CAMERA);
-    k_geom_raster<E, SHADOW><<<cdiv(ctx->S.n_tris, PRC_GEOM_THREADS), PRC_GEOM_THREADS, 0, st>>>(ctx->S, F, shadow_trans, keys, smap, large, ctx->large_cap,
-                                                                                                     clipq, ctx->clip_cap, cnt, (const DevFrame*)ctx->d_frame.p);
+    k_geom_raster<E, SHADOW><<<cdiv(ctx->S.n_tris, PRC_GEOM_THREADS), PRC_GEOM_THREADS, 0, st>>>(ctx->S, F, V, keys, large, ctx->large_cap, clipq, ctx->clip_cap,
+                                                                                                     cnt, (const DevFrame*)fb.p);
     ctx->launches++;
   }
-  // The rare paths are launched unconditionally with fixed grids that read their work counts on the device
-  // (grid-stride loops), so a frame needs no host round trip; queue overflow is checked once at the end.
-  const unsigned int fixed_blocks = 148 * 4;
   if (!SHADOW) {
+    // fixed grid, reads its work count on the device (grid-stride loop)
     KTimer kt(ctx, PRC_K_CLIP);
-    k_clip_raster<E><<<fixed_blocks, 128, 0, st>>>(ctx->S, F, clipq, keys, large, ctx->large_cap, cnt);
+    k_clip_raster<E><<<148 * 4, 128, 0, st>>>(ctx->S, F, clipq, keys, large, ctx->large_cap, cnt);
     ctx->launches++;
   }
+  CK(cudaGetLastError());
+  return PRC_OK;
+}
+
+// ---- tile path, once per frame (or per phase in the split multi-GPU API) for everything queued so far --------
+template <bool E>
+int32_t flush_large(prc_ctx* ctx, const DevFrame& F) {
+  cudaStream_t st = ctx->stream;
+  Counters* cnt = (Counters*)ctx->d_counters.p;
+  const int tiles_x = (F.W + PRC_TILE - 1) / PRC_TILE, tiles_y = (F.H + PRC_TILE - 1) / PRC_TILE;
+  const int n_tiles = tiles_x * tiles_y, n_vt = n_tiles * (int)ctx->n_targets;
+  const unsigned int n_chunks = (unsigned int)((n_vt + 1 + 4095) / 4096);
   unsigned int* tile_count = (unsigned int*)ctx->d_tilecount.p;
   unsigned int* tile_start = (unsigned int*)ctx->d_tilestart.p;
   unsigned int* cursor = (unsigned int*)ctx->d_cursor.p;
-  CK(cudaMemsetAsync(tile_count, 0, (size_t)(n_tiles + 8) * 4, st));
+  unsigned int* active_hdr = (unsigned int*)ctx->d_active.p;
+  LargeRec* large = (LargeRec*)ctx->d_large.p;
+  CK(cudaMemsetAsync(tile_count, 0, (size_t)n_chunks * 4096 * 4, st));
+  CK(cudaMemsetAsync(active_hdr, 0, 16, st));
   {
     KTimer kt(ctx, PRC_K_BIN);
-    k_bin_count<<<fixed_blocks, 256, 0, st>>>(large, cnt, ctx->large_cap, tiles_x, tile_count);
-    k_scan<<<1, 1024, 0, st>>>(tile_count, tile_start, cursor, n_tiles, cnt, ctx->bins_cap, (unsigned int*)ctx->d_active.p + 4, (unsigned int*)ctx->d_active.p);
-    k_bin_fill<<<fixed_blocks, 256, 0, st>>>(large, cnt, ctx->large_cap, tiles_x, cursor, (unsigned int*)ctx->d_bins.p, ctx->bins_cap);
-    ctx->launches += 3;
+    k_bin_count<<<148 * 4, 256, 0, st>>>(large, cnt, ctx->large_cap, tiles_x, n_tiles, tile_count);
+    k_scan_sums<<<n_chunks, 1024, 0, st>>>(tile_count, (unsigned int*)ctx->d_chunksum.p, cnt);
+    k_scan_apply<<<n_chunks, 1024, 0, st>>>(tile_count, tile_start, cursor, (const unsigned int*)ctx->d_chunksum.p, cnt, ctx->bins_cap, ctx->large_cap,
+                                            active_hdr + 4, active_hdr);
+    k_bin_fill<<<148 * 4, 256, 0, st>>>(large, cnt, ctx->large_cap, tiles_x, n_tiles, cursor, (unsigned int*)ctx->d_bins.p, ctx->bins_cap);
+    ctx->launches += 4;
   }
   {
-    const int r0 = SHADOW ? F.row0 : F.rr0, r1 = SHADOW ? F.row1 : F.rr1;
-    KTimer kt(ctx, SHADOW ? PRC_K_TILE_SHADOW : PRC_K_TILE_CAMERA);
-    k_tile_raster<E, SHADOW><<<148 * 8, PRC_TILE * PRC_TILE, 0, st>>>(large, tile_start, (unsigned int*)ctx->d_bins.p, tiles_x, F.W, F.H, r0, r1, keys, smap, cnt,
-                                                                           (const unsigned int*)ctx->d_active.p + 4, (const unsigned int*)ctx->d_active.p);
+    KTimer kt(ctx, PRC_K_TILE_CAMERA);
+    k_tile_raster<E><<<148 * 8, PRC_TILE * PRC_TILE, 0, st>>>(large, tile_start, (unsigned int*)ctx->d_bins.p, tiles_x, n_tiles, F.W, F.H,
+                                                               (unsigned long long*)ctx->d_keys.p, (const TileTargets*)ctx->d_targets.p, cnt, active_hdr + 4, active_hdr);
     ctx->launches++;
   }
+  // the queue is consumed: the next phase starts an empty one (stats were accumulated by k_scan_apply)
+  CK(cudaMemsetAsync(cnt, 0, 16, st));
   CK(cudaGetLastError());
   return PRC_OK;
 }
@@ -214,8 +235,25 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
   ENSURE(ctx->d_image, npx * 4);
   ENSURE(ctx->d_special, 16);
   const int n_tiles = ((W + PRC_TILE - 1) / PRC_TILE) * ((H + PRC_TILE - 1) / PRC_TILE);
-  ENSURE(ctx->d_tilecount, (size_t)(n_tiles + 8) * 4); ENSURE(ctx->d_tilestart, (size_t)(n_tiles + 8) * 4); ENSURE(ctx->d_cursor, (size_t)(n_tiles + 8) * 4);
-  ENSURE(ctx->d_active, (size_t)(n_tiles + 8) * 4);
+  // targets of the tile path: 0 = camera, 1 + k = k-th casting light
+  {
+
+    uint32_t nt = 1;
+    for (uint32_t i = 0; i < fr->n_lights && i < 64; i++) {
+      ctx->target_of_light[i] = 0;
+      if (fr->lights[i].cast_shadow && (fr->flags & PRC_FRAME_SHADOWMAP)) {
+        if (nt > 32) { ctx->err = "more than 32 shadow-casting lights"; return PRC_ERR_UNSUPPORTED; }
+        ctx->target_of_light[i] = nt;
+        nt++;
+      }
+    }
+    ctx->n_targets = nt;
+    const size_t n_vt_pad = (((size_t)n_tiles * nt + 1 + 4095) / 4096) * 4096;
+    ENSURE(ctx->d_tilecount, n_vt_pad * 4); ENSURE(ctx->d_tilestart, n_vt_pad * 4); ENSURE(ctx->d_cursor, n_vt_pad * 4);
+    ENSURE(ctx->d_active, (n_vt_pad + 8) * 4);
+    ENSURE(ctx->d_chunksum, 1024 * 4);
+    ENSURE(ctx->d_targets, sizeof(TileTargets));
+  }
   if (!ctx->d_bins.p) {
     const char* e = getenv("PRC_BINS_INIT");  // initial (tile, triangle) capacity; grown on demand by re-rendering the frame
     ENSURE(ctx->d_bins, e ? (size_t)atoll(e) * 4 : ((size_t)16 << 20));
@@ -247,6 +285,12 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
     if (d.cast_shadow) UPLOAD(ctx->d_shadow_trans[i], l.shadow_trans, (size_t)fr->n_objects * 64);
   }
   UPLOAD(ctx->d_lights, hl.data(), hl.size() * sizeof(DevLight));
+  {
+    ctx->h_targets = TileTargets{};
+    for (uint32_t i = 0; i < fr->n_lights && i < 64; i++)
+      if (ctx->target_of_light[i]) ctx->h_targets.smap[ctx->target_of_light[i]] = (float*)ctx->d_shadow[i].p;
+    UPLOAD(ctx->d_targets, &ctx->h_targets, sizeof(TileTargets));
+  }
   UPLOAD(ctx->d_ambient, fr->ambient_intensity, (size_t)fr->n_ambient * 4);
   UPLOAD(ctx->d_gamma, fr->gamma_lut, 256);
   F.W = W; F.H = H;
@@ -279,14 +323,27 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
 }
 
 template <bool E>
-int32_t do_shadows(prc_ctx* ctx, const prc_frame* fr, DevFrame F, uint32_t light_mask, int srow0, int srow1) {
+int32_t do_shadows(prc_ctx* ctx, const prc_frame* fr, DevFrame F, uint32_t light_mask, int srow0, int srow1, bool flush) {
   if (!(fr->flags & PRC_FRAME_SHADOWMAP)) return PRC_OK;
   F.row0 = srow0; F.row1 = srow1;
+  GeomViews V{};
+  const int per_sweep = getenv("PRC_SHADOW_FUSE") ? std::max(1, std::min(8, atoi(getenv("PRC_SHADOW_FUSE")))) : 8;
   for (uint32_t i = 0; i < fr->n_lights; i++) {
     if (!fr->lights[i].cast_shadow || !((light_mask >> (i & 31)) & 1u)) continue;
-    int32_t r = raster_pass<E, true>(ctx, F, (const float*)ctx->d_shadow_trans[i].p, (float*)ctx->d_shadow[i].p);
+    V.trans[V.n] = (const float*)ctx->d_shadow_trans[i].p;
+    V.smap[V.n] = (float*)ctx->d_shadow[i].p;
+    V.target[V.n] = ctx->target_of_light[i];
+    if (++V.n == per_sweep) {  // the shadow passes of up to 8 lights share one sweep over the triangles
+      int32_t r = raster_pass<E, true>(ctx, F, V);
+      if (r != PRC_OK) return r;
+      V.n = 0;
+    }
+  }
+  if (V.n) {
+    int32_t r = raster_pass<E, true>(ctx, F, V);
     if (r != PRC_OK) return r;
   }
+  if (flush) return flush_large<E>(ctx, F);
   return PRC_OK;
 }
 
@@ -298,20 +355,30 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F) {
   CK(cudaMemsetAsync((unsigned long long*)ctx->d_keys.p + (size_t)F.rr0 * F.W, 0, (size_t)(F.rr1 - F.rr0) * F.W * 8, st));
   if (F.rr0 > 0) CK(cudaMemsetAsync(ctx->d_keys.p, 0, 8, st));
   (void)npx;
-  int32_t r = raster_pass<E, false>(ctx, F, nullptr, nullptr);
+  GeomViews V0{};
+  V0.n = 1;
+  int32_t r = raster_pass<E, false>(ctx, F, V0);
+  if (r != PRC_OK) return r;
+  r = flush_large<E>(ctx, F);  // also rasterises what the shadow passes of this frame queued
   if (r != PRC_OK) return r;
   CK(cudaEventRecord(ctx->ev[2], st));
   GBuf G{(float4*)ctx->d_ga.p, (float4*)ctx->d_gb.p, (float4*)ctx->d_gc.p, (float4*)ctx->d_gd.p, ctx->any_ao ? (float*)ctx->d_ao.p : nullptr};
   const unsigned long long* keys = (const unsigned long long*)ctx->d_keys.p;
   dim3 rg((F.W + 31) / 32, (F.rr1 - F.rr0 + 3) / 4);
   { KTimer kt(ctx, PRC_K_RESOLVE);
-  k_resolve<E><<<rg, 128, 0, st>>>(ctx->S, F, keys, G);
+  if (ctx->exact_shade) k_resolve<E, E><<<rg, 128, 0, st>>>(ctx->S, F, keys, G); else k_resolve<E, false><<<rg, 128, 0, st>>>(ctx->S, F, keys, G);
   ctx->launches++;
-  if (F.rr0 > 0) { k_resolve00<E><<<1, 1, 0, st>>>(ctx->S, F, keys, G); ctx->launches++; } }
+  if (F.rr0 > 0) { if (ctx->exact_shade) k_resolve00<E, E><<<1, 1, 0, st>>>(ctx->S, F, keys, G); else k_resolve00<E, false><<<1, 1, 0, st>>>(ctx->S, F, keys, G); ctx->launches++; } }
   { KTimer kt(ctx, PRC_K_SHADE);
-  k_shade_special<E><<<1, 32, 0, st>>>(ctx->S, F, (const AoConsts*)ctx->d_aoc.p, keys, G, (uint32_t*)ctx->d_special.p);
+  if (ctx->exact_shade) {
+  k_shade_special<true><<<1, 32, 0, st>>>(ctx->S, F, (const AoConsts*)ctx->d_aoc.p, keys, G, (uint32_t*)ctx->d_special.p);
   dim3 sg((F.W + 31) / 32, (F.row1 - F.row0 + 3) / 4);
-  k_shade<E><<<sg, 128, 0, st>>>(ctx->S, F, (const AoConsts*)ctx->d_aoc.p, keys, G, (const uint32_t*)ctx->d_special.p, (uint32_t*)ctx->d_image.p); }
+  k_shade<true><<<sg, 128, 0, st>>>(ctx->S, F, (const AoConsts*)ctx->d_aoc.p, keys, G, (const uint32_t*)ctx->d_special.p, (uint32_t*)ctx->d_image.p);
+  } else {
+  k_shade_special<false><<<1, 32, 0, st>>>(ctx->S, F, (const AoConsts*)ctx->d_aoc.p, keys, G, (uint32_t*)ctx->d_special.p);
+  dim3 sg((F.W + 31) / 32, (F.row1 - F.row0 + 3) / 4);
+  k_shade<false><<<sg, 128, 0, st>>>(ctx->S, F, (const AoConsts*)ctx->d_aoc.p, keys, G, (const uint32_t*)ctx->d_special.p, (uint32_t*)ctx->d_image.p);
+  } }
   ctx->launches += 2;
   CK(cudaGetLastError());
   ctx->gbuffer_valid = true;
@@ -319,18 +386,30 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F) {
 }
 
 int32_t readback_image(prc_ctx* ctx, const DevFrame& F, uint8_t* rgba_out) {
-  if (!rgba_out) return PRC_OK;
   // image rows of the strip: screen rows [row0,row1) -> image rows [H-row1, H-row0)
   const size_t off = (size_t)(F.H - F.row1) * F.W * 4, bytes = (size_t)(F.row1 - F.row0) * F.W * 4;
-  if (ctx->h_pinned_cap < bytes) {
-    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-    ctx->h_pinned = nullptr;
-    CK(cudaMallocHost(&ctx->h_pinned, bytes));
-    ctx->h_pinned_cap = bytes;
+  const size_t total = (size_t)F.W * F.H * 4;
+  // Two library-owned page-locked images used alternately, like the reference's double buffer (raster.go:86,
+  // 201-206): the device->host copy is one DMA at PCIe speed; a caller that passes rgba_out == NULL reads the
+  // frame in place through prc_host_image (zero copy, valid until two frames later), one that passes its own
+  // buffer pays an extra host memcpy.
+  if (ctx->h_img_cap < total) {
+    for (auto& p : ctx->h_img) { if (p) { cudaHostUnregister(p); free(p); } p = nullptr; }
+    for (auto& p : ctx->h_img) {
+      // first-touched by this thread (NUMA-local), then page-locked
+      void* q = nullptr;
+      if (posix_memalign(&q, 4096, (total + 4095) & ~(size_t)4095) != 0) { ctx->err = "out of host memory"; return PRC_ERR_CUDA; }
+      memset(q, 0, total);
+      p = (uint8_t*)q;
+      CK(cudaHostRegister(p, (total + 4095) & ~(size_t)4095, cudaHostRegisterDefault));
+    }
+    ctx->h_img_cap = total;
   }
-  CK(cudaMemcpyAsync(ctx->h_pinned, (uint8_t*)ctx->d_image.p + off, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->h_img_cur ^= 1;
+  uint8_t* dst = ctx->h_img[ctx->h_img_cur];
+  CK(cudaMemcpyAsync(dst + off, (uint8_t*)ctx->d_image.p + off, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  memcpy(rgba_out + off, ctx->h_pinned, bytes);
+  if (rgba_out) memcpy(rgba_out + off, dst + off, bytes);
   return PRC_OK;
 }
 
@@ -349,11 +428,19 @@ int32_t finish_timings(prc_ctx* ctx) {
   if (ctx->h_counters->large_overflow) {
     ctx->spans.clear();
     ctx->ev_used = 0;
+    bool grown = false;
     if (ctx->h_counters->max_bins > ctx->bins_cap) {  // grow the bin array; the caller re-renders the frame
       ENSURE(ctx->d_bins, (size_t)ctx->h_counters->max_bins * 5);
       ctx->bins_cap = (unsigned int)(ctx->d_bins.cap / 4);
-      return PRC_RETRY;
+      grown = true;
     }
+    if (ctx->h_counters->stat_large > ctx->large_cap) {  // large-triangle queue (stat_large = records pushed over the frame)
+      const size_t want = (size_t)ctx->h_counters->stat_large * 5 / 4 + 1024;
+      ENSURE(ctx->d_large, want * sizeof(LargeRec));
+      ctx->large_cap = (unsigned int)std::min<size_t>(ctx->d_large.cap / sizeof(LargeRec), 0xFFFFFFF0u);
+      grown = true;
+    }
+    if (grown) return PRC_RETRY;
     ctx->err = "internal queue overflow (large/clip queue)";
     return PRC_ERR_UNSUPPORTED;
   }
@@ -399,6 +486,7 @@ int32_t prc_open(int32_t device, prc_ctx** out) {
   cudaMemset(ctx->d_counters.p, 0, sizeof(Counters));
   const char* mode = getenv("PRC_FMA");
   ctx->exact = !(mode && strcmp(mode, "fast") == 0);
+  ctx->exact_shade = mode && strcmp(mode, "exact") == 0;
   // AO constants (material/ao.go:28-32): a accumulates float32(Pi/4) in float32; Cos/Sin via float64.
   const float pi = 3.14159265358979323846f, q = pi / 4;
   float a = 0.0f;
@@ -423,11 +511,11 @@ int32_t prc_close(prc_ctx* ctx) {
   DBuf* all[] = {&ctx->d_pos, &ctx->d_nor, &ctx->d_uv, &ctx->d_col, &ctx->d_mat, &ctx->d_meta, &ctx->d_mats, &ctx->d_objstart, &ctx->d_texfirst,
                  &ctx->d_lw, &ctx->d_lh, &ctx->d_loff, &ctx->d_tex, &ctx->d_keys, &ctx->d_ga, &ctx->d_gb, &ctx->d_gc, &ctx->d_gd, &ctx->d_ao,
                  &ctx->d_image, &ctx->d_special, &ctx->d_counters, &ctx->d_large, &ctx->d_clipq, &ctx->d_tilecount, &ctx->d_tilestart, &ctx->d_cursor,
-                 &ctx->d_bins, &ctx->d_active, &ctx->d_xf, &ctx->d_lights, &ctx->d_ambient, &ctx->d_gamma, &ctx->d_frame, &ctx->d_aoc};
+                 &ctx->d_bins, &ctx->d_active, &ctx->d_chunksum, &ctx->d_targets, &ctx->d_frame_sh, &ctx->d_xf, &ctx->d_lights, &ctx->d_ambient, &ctx->d_gamma, &ctx->d_frame, &ctx->d_aoc};
   for (DBuf* b : all) free_buf(*b);
   for (auto& b : ctx->d_shadow) free_buf(b);
   for (auto& b : ctx->d_shadow_trans) free_buf(b);
-  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  for (auto& p : ctx->h_img) if (p) { cudaHostUnregister(p); free(p); }
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   for (auto& e : ctx->evpool) cudaEventDestroy(e);
@@ -441,6 +529,7 @@ const char* prc_last_error(prc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null
 int32_t prc_set_exact_fma(prc_ctx* ctx, int32_t exact) {
   if (!ctx) return PRC_ERR_INVALID;
   ctx->exact = exact != 0;
+  ctx->exact_shade = exact != 0;
   return PRC_OK;
 }
 
@@ -470,7 +559,7 @@ int32_t prc_scene_upload(prc_ctx* ctx, const prc_scene* s) {
   UPLOAD(ctx->d_loff, s->level_offset, (size_t)s->n_tex_levels * 8);
   UPLOAD(ctx->d_tex, s->tex_data, s->tex_bytes);
   ENSURE(ctx->d_meta, n * 4);
-  ctx->large_cap = (unsigned int)std::min<uint64_t>(n + 65536, 0xFFFFFFF0ull);
+  ctx->large_cap = (unsigned int)std::min<uint64_t>(std::max<uint64_t>(n / 4, 1u << 20), 0xFFFFFFF0ull);  // grown on demand (frame re-render)
   ctx->clip_cap = (unsigned int)std::min<uint64_t>(n + 16, 0xFFFFFFF0ull);
   ENSURE(ctx->d_large, (size_t)ctx->large_cap * sizeof(LargeRec));
   ENSURE(ctx->d_clipq, (size_t)ctx->clip_cap * 4);
@@ -517,17 +606,26 @@ int32_t prc_render_shadows(prc_ctx* ctx, const prc_frame* fr, uint32_t light_mas
   if (srow1 > fr->height || srow0 >= srow1) { ctx->err = "bad shadow row range"; return PRC_ERR_INVALID; }
   for (int attempt = 0; attempt < 4; attempt++) {
     ctx->launches = 0;
-    CK(cudaMemsetAsync(&((Counters*)ctx->d_counters.p)->large_overflow, 0, offsetof(Counters, n_valid) - offsetof(Counters, large_overflow), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, offsetof(Counters, n_valid), ctx->stream));
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    r = ctx->exact ? do_shadows<true>(ctx, fr, F, light_mask, srow0, srow1) : do_shadows<false>(ctx, fr, F, light_mask, srow0, srow1);
+    r = ctx->exact ? do_shadows<true>(ctx, fr, F, light_mask, srow0, srow1, true) : do_shadows<false>(ctx, fr, F, light_mask, srow0, srow1, true);
     if (r != PRC_OK) return r;
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (!ctx->h_counters->large_overflow) return PRC_OK;
-    if (ctx->h_counters->max_bins <= ctx->bins_cap) { ctx->err = "internal queue overflow (large queue)"; return PRC_ERR_UNSUPPORTED; }
-    ENSURE(ctx->d_bins, (size_t)ctx->h_counters->max_bins * 5);
-    ctx->bins_cap = (unsigned int)(ctx->d_bins.cap / 4);
+    bool grown = false;
+    if (ctx->h_counters->max_bins > ctx->bins_cap) {
+      ENSURE(ctx->d_bins, (size_t)ctx->h_counters->max_bins * 5);
+      ctx->bins_cap = (unsigned int)(ctx->d_bins.cap / 4);
+      grown = true;
+    }
+    if (ctx->h_counters->stat_large > ctx->large_cap) {
+      ENSURE(ctx->d_large, ((size_t)ctx->h_counters->stat_large * 5 / 4 + 1024) * sizeof(LargeRec));
+      ctx->large_cap = (unsigned int)std::min<size_t>(ctx->d_large.cap / sizeof(LargeRec), 0xFFFFFFF0u);
+      grown = true;
+    }
+    if (!grown) { ctx->err = "internal queue overflow (clip queue)"; return PRC_ERR_UNSUPPORTED; }
     ctx->spans.clear();
     ctx->ev_used = 0;
   }
@@ -542,7 +640,7 @@ int32_t prc_render_main(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out) {
   int32_t r = build_frame(ctx, fr, F);
   if (r != PRC_OK) return r;
   for (int attempt = 0; attempt < 4; attempt++) {
-    CK(cudaMemsetAsync(&((Counters*)ctx->d_counters.p)->large_overflow, 0, 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 16 + 8, ctx->stream));
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     r = ctx->exact ? do_main<true>(ctx, fr, F) : do_main<false>(ctx, fr, F);
     if (r != PRC_OK) return r;
@@ -566,9 +664,9 @@ int32_t prc_render(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out) {
   if (r != PRC_OK) return r;
   for (int attempt = 0; attempt < 4; attempt++) {
     ctx->launches = 0;
-    CK(cudaMemsetAsync(&((Counters*)ctx->d_counters.p)->large_overflow, 0, offsetof(Counters, n_valid) - offsetof(Counters, large_overflow), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, offsetof(Counters, n_valid), ctx->stream));
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    r = ctx->exact ? do_shadows<true>(ctx, fr, F, 0xFFFFFFFFu, 0, F.H) : do_shadows<false>(ctx, fr, F, 0xFFFFFFFFu, 0, F.H);
+    r = ctx->exact ? do_shadows<true>(ctx, fr, F, 0xFFFFFFFFu, 0, F.H, false) : do_shadows<false>(ctx, fr, F, 0xFFFFFFFFu, 0, F.H, false);
     if (r != PRC_OK) return r;
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     r = ctx->exact ? do_main<true>(ctx, fr, F) : do_main<false>(ctx, fr, F);
@@ -639,6 +737,13 @@ int32_t prc_device_image(prc_ctx* ctx, uint64_t* dev_ptr, uint64_t* bytes) {
 int32_t prc_device_shadowmap(prc_ctx* ctx, uint32_t light, uint64_t* dev_ptr, uint64_t* bytes) {
   if (!ctx || light >= ctx->d_shadow.size() || !ctx->d_shadow[light].p) return PRC_ERR_INVALID;
   *dev_ptr = (uint64_t)(uintptr_t)ctx->d_shadow[light].p;
+  *bytes = (uint64_t)ctx->W * ctx->H * 4;
+  return PRC_OK;
+}
+
+int32_t prc_host_image(prc_ctx* ctx, uint64_t* host_ptr, uint64_t* bytes) {
+  if (!ctx || !ctx->h_img[ctx->h_img_cur]) return PRC_ERR_INVALID;
+  *host_ptr = (uint64_t)(uintptr_t)ctx->h_img[ctx->h_img_cur];
   *bytes = (uint64_t)ctx->W * ctx->H * 4;
   return PRC_OK;
 }

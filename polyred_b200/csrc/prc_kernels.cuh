@@ -63,10 +63,11 @@ struct DevFrame {
   const uint8_t* gamma;
 };
 
-struct LargeRec {  // setup record of a triangle handed to the tile path (48 B)
+struct LargeRec {  // setup record of a triangle handed to the tile path (52 B)
   float x1, y1, z1, x2, y2, z2, x3, y3, z3;
   uint32_t seq;
   short bx0, by0, bx1, by1;  // clamped pixel bbox, inclusive
+  uint32_t target;           // 0 = camera visibility keys, 1 + k = shadow map of the k-th casting light
 };
 
 struct Counters {
@@ -252,7 +253,7 @@ __device__ __forceinline__ void raster_pixel00(const V4& p1, const V4& p2, const
 
 template <bool E, bool SHADOW>
 __device__ __forceinline__ void emit_tri(const V4& p1, const V4& p2, const V4& p3, uint32_t seq, const DevFrame& F, int r0, int r1,
-                                         unsigned long long* keys, float* smap, LargeRec* large, unsigned int large_cap, Counters* cnt) {
+                                         unsigned long long* keys, float* smap, LargeRec* large, unsigned int large_cap, uint32_t target, Counters* cnt) {
   int x0, y0, x1, y1;
   float mnx, mny, mxx, mxy;
   if (!SHADOW && r0 > 0) raster_pixel00<E>(p1, p2, p3, seq, keys, cnt);
@@ -272,7 +273,7 @@ __device__ __forceinline__ void emit_tri(const V4& p1, const V4& p2, const V4& p
     if (slot >= large_cap) { atomicExch(&cnt->large_overflow, 1u); return; }
     LargeRec r;
     r.x1 = p1.x; r.y1 = p1.y; r.z1 = p1.z; r.x2 = p2.x; r.y2 = p2.y; r.z2 = p2.z; r.x3 = p3.x; r.y3 = p3.y; r.z3 = p3.z;
-    r.seq = seq; r.bx0 = (short)x0; r.by0 = (short)y0; r.bx1 = (short)x1; r.by1 = (short)y1;
+    r.seq = seq; r.bx0 = (short)x0; r.by0 = (short)y0; r.bx1 = (short)x1; r.by1 = (short)y1; r.target = target;
     large[slot] = r;
   }
 }
@@ -300,7 +301,7 @@ template <bool E, bool SHADOW>
 // reference to a non-inlined function makes every thread copy it to local memory at kernel entry (measured:
 // 1.76 GB of DRAM writes per launch).
 __device__ __noinline__ void geom_generic(const DevFrame* __restrict__ Fg, const float* trans, const float* __restrict__ pos, uint32_t tri, unsigned long long* keys,
-                                          float* smap, LargeRec* large, unsigned int large_cap, unsigned int* clipq, unsigned int clip_cap, Counters* cnt) {
+                                          float* smap, LargeRec* large, unsigned int large_cap, uint32_t target, unsigned int* clipq, unsigned int clip_cap, Counters* cnt) {
   float p[9];  // re-read from global memory: passing the caller's register array by pointer would force it into local memory
 #pragma unroll
   for (int i = 0; i < 9; i++) p[i] = pos[(size_t)tri * 9 + i];
@@ -315,7 +316,7 @@ __device__ __noinline__ void geom_generic(const DevFrame* __restrict__ Fg, const
     return;
   }
   const int r0 = SHADOW ? F.row0 : F.rr0, r1 = SHADOW ? F.row1 : F.rr1;
-  emit_tri<E, SHADOW>(st.p1, st.p2, st.p3, tri * 8u, F, r0, r1, keys, smap, large, large_cap, cnt);
+  emit_tri<E, SHADOW>(st.p1, st.p2, st.p3, tri * 8u, F, r0, r1, keys, smap, large, large_cap, target, cnt);
 }
 
 // Apply(Viewport).Pos() for the standard viewport matrix [a 0 0 b; 0 c 0 d; 0 0 1 0; 0 0 0 1] and a vertex whose
@@ -333,46 +334,23 @@ __device__ __forceinline__ bool viewport_pos_std(const float* __restrict__ vp, c
   return true;
 }
 
+// One raster pass ("view") of one triangle: transform, cull, classify, small raster (see k_geom_raster).
 template <bool E, bool SHADOW>
-__global__ void __launch_bounds__(PRC_GEOM_THREADS, 4) k_geom_raster(DevScene S, DevFrame F, const float* __restrict__ shadow_trans /*[n_obj][16]*/,
-                                                                     unsigned long long* keys, float* smap, LargeRec* large, unsigned int large_cap,
-                                                                     unsigned int* clipq, unsigned int clip_cap, Counters* cnt, const DevFrame* Fg) {
-  // Each warp stages its own 32 triangles (32 x 36 B = 72 float4, 16-byte aligned because the warp's first
-  // triangle index is a multiple of 32) through shared memory with 128-bit loads; only __syncwarp is needed,
-  // so warps never wait for each other.
-  __shared__ __align__(16) float sp[PRC_GEOM_THREADS * 9];
-  const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
-  const unsigned long long wtri = (unsigned long long)blockIdx.x * PRC_GEOM_THREADS + wbase;  // first triangle of this warp
-  if (wtri >= S.n_tris) return;
-  const unsigned long long wleft = S.n_tris - wtri;
-  const int nt = wleft < 32 ? (int)wleft : 32;
-  const unsigned int tri = (unsigned int)(wtri + lane);
-  const uint32_t meta = lane < nt ? __ldg(S.meta + tri) : 0x80000000u;
-  {
-    const float4* src = reinterpret_cast<const float4*>(S.pos + wtri * 9);
-    float4* dst = reinterpret_cast<float4*>(sp + wbase * 9);
-    const int nvec = (nt * 9) / 4;  // the scene buffer is padded, reading the last partial float4 is safe
-    for (int i = lane; i < nvec + ((nt * 9) & 3 ? 1 : 0); i += 32) dst[i] = __ldg(src + i);
-  }
-  __syncwarp();
-  if (meta & 0x80000000u) return;  // !IsValid
-  const uint32_t obj = meta & 0x00FFFFFFu;
-  const float* trans = SHADOW ? (shadow_trans + (size_t)obj * 16) : F.xf[obj].trans;
-  float p[9];
-#pragma unroll
-  for (int i = 0; i < 9; i++) p[i] = sp[threadIdx.x * 9 + i];
+__device__ __forceinline__ void geom_view(const DevScene& S, const DevFrame& F, const float* __restrict__ trans, const float* p, const unsigned int tri,
+                                          unsigned long long* keys, float* smap, LargeRec* large, unsigned int large_cap, unsigned int* clipq,
+                                          unsigned int clip_cap, Counters* cnt, const DevFrame* Fg, uint32_t target) {
   const V4 ca = mulv(trans, V4{p[0], p[1], p[2], 1.0f});
   const V4 cb = mulv(trans, V4{p[3], p[4], p[5], 1.0f});
   const V4 cc = mulv(trans, V4{p[6], p[7], p[8], 1.0f});
   V4 p1, p2, p3;
   if (!(F.vp_std && viewport_pos_std<E>(F.viewport, ca, p1) && viewport_pos_std<E>(F.viewport, cb, p2) && viewport_pos_std<E>(F.viewport, cc, p3))) {
     // non-standard viewport matrix or NaN / Inf / zero z,w: the literal reference sequence
-    geom_generic<E, SHADOW>(Fg, trans, S.pos, tri, keys, smap, large, large_cap, clipq, clip_cap, cnt);
+    geom_generic<E, SHADOW>(Fg, trans, S.pos, tri, keys, smap, large, large_cap, target, clipq, clip_cap, cnt);
     return;
   }
   const float mag = fabsf(p1.x) + fabsf(p1.y) + fabsf(p1.z) + fabsf(p2.x) + fabsf(p2.y) + fabsf(p2.z) + fabsf(p3.x) + fabsf(p3.y) + fabsf(p3.z);
   if (!(mag < 1e30f)) {
-    geom_generic<E, SHADOW>(Fg, trans, S.pos, tri, keys, smap, large, large_cap, clipq, clip_cap, cnt);
+    geom_generic<E, SHADOW>(Fg, trans, S.pos, tri, keys, smap, large, large_cap, target, clipq, clip_cap, cnt);
     return;
   }
   // cullBackFace (render/cull.go:26-28)
@@ -413,7 +391,7 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, 4) k_geom_raster(DevScene S,
     if (slot >= large_cap) { atomicExch(&cnt->large_overflow, 1u); return; }
     LargeRec lr;
     lr.x1 = p1.x; lr.y1 = p1.y; lr.z1 = p1.z; lr.x2 = p2.x; lr.y2 = p2.y; lr.z2 = p2.z; lr.x3 = p3.x; lr.y3 = p3.y; lr.z3 = p3.z;
-    lr.seq = seq; lr.bx0 = (short)x0; lr.by0 = (short)y0; lr.bx1 = (short)x1; lr.by1 = (short)y1;
+    lr.seq = seq; lr.bx0 = (short)x0; lr.by0 = (short)y0; lr.bx1 = (short)x1; lr.by1 = (short)y1; lr.target = target;
     large[slot] = lr;
     return;
   }
@@ -426,6 +404,15 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, 4) k_geom_raster(DevScene S,
     for (int x = x0; x <= x1; x++) {
       const float px = (float)x + 0.5f;
       const float apx = px - bs.t1x, bpx = px - bs.t2x;
+      if (E) {
+        // cheap certain rejection first: the single-rounding fmaf value is within 1 ulp of the reference's
+        // double-rounded one, so |S_fmaf| > 4e-7 |Sabc| with the wrong sign implies |S| > 2e-7 |Sabc| below
+        const float thr2 = thr + thr;
+        const float q0 = cross2z<false>(bs.abx, bs.aby, apx, apy), q1 = cross2z<false>(apx, apy, bs.acx, bs.acy), q2 = cross2z<false>(bs.bcx, bs.bcy, bpx, bpy);
+        if ((((__float_as_uint(q0) ^ sg) >> 31) && fabsf(q0) > thr2) || (((__float_as_uint(q1) ^ sg) >> 31) && fabsf(q1) > thr2) ||
+            (((__float_as_uint(q2) ^ sg) >> 31) && fabsf(q2) > thr2))
+          continue;
+      }
       const float Sabp = cross2z<E>(bs.abx, bs.aby, apx, apy);
       const float Sapc = cross2z<E>(apx, apy, bs.acx, bs.acy);
       const float Sbcp = cross2z<E>(bs.bcx, bs.bcy, bpx, bpy);
@@ -446,6 +433,50 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, 4) k_geom_raster(DevScene S,
         atomicMax(&keys[idx], key);
       }
     }
+  }
+}
+
+// Shadow passes of several lights share one sweep over the triangles (positions are loaded and staged once).
+struct GeomViews {
+  int n;
+  const float* trans[8];  // per view: [n_obj][16] light trans (shadow) — unused for the camera (F.xf)
+  float* smap[8];
+  uint32_t target[8];
+};
+
+template <bool E, bool SHADOW>
+__global__ void __launch_bounds__(PRC_GEOM_THREADS, 4) k_geom_raster(DevScene S, DevFrame F, GeomViews V,
+                                                                     unsigned long long* keys, LargeRec* large, unsigned int large_cap,
+                                                                     unsigned int* clipq, unsigned int clip_cap, Counters* cnt, const DevFrame* Fg) {
+  // Each warp stages its own 32 triangles (32 x 36 B = 72 float4, 16-byte aligned because the warp's first
+  // triangle index is a multiple of 32) through shared memory with 128-bit loads; only __syncwarp is needed,
+  // so warps never wait for each other.
+  __shared__ __align__(16) float sp[PRC_GEOM_THREADS * 9];
+  const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+  const unsigned long long wtri = (unsigned long long)blockIdx.x * PRC_GEOM_THREADS + wbase;  // first triangle of this warp
+  if (wtri >= S.n_tris) return;
+  const unsigned long long wleft = S.n_tris - wtri;
+  const int nt = wleft < 32 ? (int)wleft : 32;
+  const unsigned int tri = (unsigned int)(wtri + lane);
+  const uint32_t meta = lane < nt ? __ldg(S.meta + tri) : 0x80000000u;
+  {
+    const float4* src = reinterpret_cast<const float4*>(S.pos + wtri * 9);
+    float4* dst = reinterpret_cast<float4*>(sp + wbase * 9);
+    const int nvec = (nt * 9) / 4;  // the scene buffer is padded, reading the last partial float4 is safe
+    for (int i = lane; i < nvec + ((nt * 9) & 3 ? 1 : 0); i += 32) dst[i] = __ldg(src + i);
+  }
+  __syncwarp();
+  if (meta & 0x80000000u) return;  // !IsValid
+  const uint32_t obj = meta & 0x00FFFFFFu;
+  float p[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) p[i] = sp[threadIdx.x * 9 + i];
+  if (SHADOW) {
+#pragma unroll 1
+    for (int v = 0; v < V.n; v++)
+      geom_view<E, true>(S, F, V.trans[v] + (size_t)obj * 16, p, tri, keys, V.smap[v], large, large_cap, clipq, clip_cap, cnt, Fg, V.target[v]);
+  } else {
+    geom_view<E, false>(S, F, F.xf[obj].trans, p, tri, keys, nullptr, large, large_cap, clipq, clip_cap, cnt, Fg, 0u);
   }
 }
 
@@ -473,95 +504,110 @@ __global__ void k_clip_raster(DevScene S, DevFrame F, const unsigned int* __rest
     clip_bary<E>(st, poly[k - 1], b1);
     clip_bary<E>(st, poly[k], b2);
     V4 q1 = clip_pos(st, b1), q2 = clip_pos(st, b2);
-    emit_tri<E, false>(q0, q1, q2, tri * 8u + (uint32_t)(k - 1), F, F.rr0, F.rr1, keys, nullptr, large, large_cap, cnt);
+    emit_tri<E, false>(q0, q1, q2, tri * 8u + (uint32_t)(k - 1), F, F.rr0, F.rr1, keys, nullptr, large, large_cap, 0u, cnt);
   }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// tile path for large triangles: bin count -> scan -> fill -> per-tile raster (one thread per pixel)
+// tile path for large triangles, ONCE per frame for all raster passes: every queued record carries its
+// target (camera keys or a shadow map); bins are indexed by virtual tile = target * n_tiles + tile.
+//   k_bin_count -> k_scan_sums -> k_scan_apply (+ list of non-empty virtual tiles) -> k_bin_fill -> k_tile_raster
 // ---------------------------------------------------------------------------------------------
-__global__ void k_bin_count(const LargeRec* __restrict__ large, const Counters* cnt, unsigned int cap, int tiles_x, unsigned int* tile_count) {
+__global__ void k_bin_count(const LargeRec* __restrict__ large, const Counters* cnt, unsigned int cap, int tiles_x, int n_tiles, unsigned int* tile_count) {
   const unsigned int n = min(cnt->n_large, cap);
   const unsigned int lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; warp < n; warp += nwarps) {
     const LargeRec r = large[warp];
+    unsigned int* tc = tile_count + (size_t)r.target * n_tiles;
     const int tx0 = r.bx0 / PRC_TILE, tx1 = r.bx1 / PRC_TILE, ty0 = r.by0 / PRC_TILE, ty1 = r.by1 / PRC_TILE;
     const int nx = tx1 - tx0 + 1, nt = nx * (ty1 - ty0 + 1);
-    for (int t = lane; t < nt; t += 32) atomicAdd(&tile_count[(ty0 + t / nx) * tiles_x + tx0 + t % nx], 1u);
+    for (int t = lane; t < nt; t += 32) atomicAdd(&tc[(ty0 + t / nx) * tiles_x + tx0 + t % nx], 1u);
   }
 }
-// exclusive scan of tile_count -> tile_start (single block, 4 tiles per thread per round, coalesced 128-bit
-// loads; <= 130k tiles at 8K) + the compacted list of non-empty tiles the raster kernel iterates over.
-__global__ void __launch_bounds__(1024) k_scan(const unsigned int* __restrict__ in, unsigned int* out, unsigned int* cursor, int n, Counters* cnt,
-                                                unsigned int bins_cap, unsigned int* active, unsigned int* n_active) {
-  __shared__ unsigned int warp_sum[32];
-  __shared__ unsigned int carry_s, nact_s;
-  if (threadIdx.x == 0) { carry_s = 0; nact_s = 0; }
-  __syncthreads();
-  if (cnt->n_large == 0) {  // nothing queued in this pass: the raster kernel sees n_active == 0
-    if (threadIdx.x == 0) { cnt->n_bin_total = 0; *n_active = 0; cnt->stat_clip += cnt->n_clip; }
-    return;
-  }
+// exclusive scan over the virtual tiles in chunks of 4096 (4 per thread, 128-bit loads; arrays are padded to a
+// multiple of 4096 and zero-filled): pass 1 = chunk sums, pass 2 = scan within the chunk + chunk offset.
+__device__ __forceinline__ unsigned int block_scan_1024(unsigned int local, unsigned int* warp_sum, unsigned int& total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int base = 0; base < n; base += 4096) {
-    const int i = base + threadIdx.x * 4;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (i < n) v = *reinterpret_cast<const uint4*>(in + i);  // arrays are padded to a multiple of 4 and zero-filled
-    const unsigned int local = v.x + v.y + v.z + v.w;
-    unsigned int incl = local;
+  unsigned int incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_sum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned int w = warp_sum[lane], wi = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
+      unsigned int t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
     }
-    if (lane == 31) warp_sum[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      unsigned int w = warp_sum[lane], wi = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        unsigned int t = __shfl_up_sync(0xffffffffu, wi, o);
-        if (lane >= o) wi += t;
-      }
-      warp_sum[lane] = wi - w;  // exclusive prefix of the warp totals
-    }
-    __syncthreads();
-    const unsigned int ex = carry_s + warp_sum[warp] + incl - local;
-    if (i < n) {
-      const uint4 o4 = make_uint4(ex, ex + v.x, ex + v.x + v.y, ex + v.x + v.y + v.z);
-      *reinterpret_cast<uint4*>(out + i) = o4;
-      *reinterpret_cast<uint4*>(cursor + i) = o4;
-      const unsigned int c[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-        if (c[k] && i + k < n) active[atomicAdd(&nact_s, 1u)] = (unsigned int)(i + k);
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = ex + local;
+    warp_sum[lane] = wi - w;
+    if (lane == 31) warp_sum[32] = wi;
+  }
+  __syncthreads();
+  total = warp_sum[32];
+  return warp_sum[warp] + incl - local;  // exclusive prefix of this thread within the block
+}
+__global__ void __launch_bounds__(1024) k_scan_sums(const unsigned int* __restrict__ in, unsigned int* chunk_sum, const Counters* cnt) {
+  __shared__ unsigned int warp_sum[33];
+  if (cnt->n_large == 0) return;
+  const uint4 v = *reinterpret_cast<const uint4*>(in + (size_t)blockIdx.x * 4096 + threadIdx.x * 4);
+  unsigned int total;
+  block_scan_1024(v.x + v.y + v.z + v.w, warp_sum, total);
+  if (threadIdx.x == 0) chunk_sum[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(1024) k_scan_apply(const unsigned int* __restrict__ in, unsigned int* out, unsigned int* cursor,
+                                                      const unsigned int* __restrict__ chunk_sum, Counters* cnt, unsigned int bins_cap, unsigned int large_cap,
+                                                      unsigned int* active, unsigned int* n_active) {
+  __shared__ unsigned int warp_sum[33];
+  __shared__ unsigned int base_s, grand_s;
+  if (cnt->n_large == 0) {  // nothing queued this frame: n_active stays 0 (host memset)
+    if (blockIdx.x == 0 && threadIdx.x == 0) { cnt->n_bin_total = 0; cnt->stat_clip += cnt->n_clip; }
+    return;
+  }
+  // offset of this chunk = sum of the previous chunk sums (gridDim.x <= 1024 chunks)
+  {
+    unsigned int c = threadIdx.x < gridDim.x ? chunk_sum[threadIdx.x] : 0u;
+    unsigned int tot;
+    const unsigned int ex = block_scan_1024(c, warp_sum, tot);
+    if (threadIdx.x == blockIdx.x) base_s = ex;
+    if (threadIdx.x == 0) grand_s = tot;
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    const unsigned int total = carry_s;
-    out[n] = total;
-    *n_active = nact_s;
+  const size_t i = (size_t)blockIdx.x * 4096 + threadIdx.x * 4;
+  const uint4 v = *reinterpret_cast<const uint4*>(in + i);
+  unsigned int tot;
+  const unsigned int ex = base_s + block_scan_1024(v.x + v.y + v.z + v.w, warp_sum, tot);
+  const uint4 o4 = make_uint4(ex, ex + v.x, ex + v.x + v.y, ex + v.x + v.y + v.z);
+  *reinterpret_cast<uint4*>(out + i) = o4;
+  *reinterpret_cast<uint4*>(cursor + i) = o4;
+  const unsigned int c[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (c[k]) active[atomicAdd(n_active, 1u)] = (unsigned int)(i + k);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const unsigned int total = grand_s;
     cnt->n_bin_total = total;
     if (total > cnt->max_bins) cnt->max_bins = total;
-    if (total > bins_cap) cnt->large_overflow = 1u;
+    if (total > bins_cap || cnt->n_large > large_cap) cnt->large_overflow = 1u;
     cnt->stat_large += cnt->n_large; cnt->stat_clip += cnt->n_clip; cnt->stat_bins += total;
   }
 }
-__global__ void k_bin_fill(const LargeRec* __restrict__ large, const Counters* cnt, unsigned int cap, int tiles_x, unsigned int* cursor,
+__global__ void k_bin_fill(const LargeRec* __restrict__ large, const Counters* cnt, unsigned int cap, int tiles_x, int n_tiles, unsigned int* cursor,
                            unsigned int* bins, unsigned int bins_cap) {
   const unsigned int n = min(cnt->n_large, cap);
   if (cnt->n_bin_total > bins_cap) return;  // frame flagged for a re-render with a larger bin array
   const unsigned int lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; warp < n; warp += nwarps) {
     const LargeRec r = large[warp];
+    unsigned int* cur = cursor + (size_t)r.target * n_tiles;
     const int tx0 = r.bx0 / PRC_TILE, tx1 = r.bx1 / PRC_TILE, ty0 = r.by0 / PRC_TILE, ty1 = r.by1 / PRC_TILE;
     const int nx = tx1 - tx0 + 1, nt = nx * (ty1 - ty0 + 1);
     for (int t = lane; t < nt; t += 32) {
-      unsigned int slot = atomicAdd(&cursor[(ty0 + t / nx) * tiles_x + tx0 + t % nx], 1u);
+      unsigned int slot = atomicAdd(&cur[(ty0 + t / nx) * tiles_x + tx0 + t % nx], 1u);
       if (slot < bins_cap) bins[slot] = warp;
     }
   }
@@ -573,61 +619,64 @@ struct TileRec {
   uint32_t seq;
   short bx0, by0, bx1, by1;
 };
-template <bool E, bool SHADOW>
+struct TileTargets { float* smap[33]; };  // [1 + k] = shadow map of the k-th casting light
+template <bool E>
 __global__ void __launch_bounds__(PRC_TILE * PRC_TILE) k_tile_raster(const LargeRec* __restrict__ large, const unsigned int* __restrict__ tile_start,
-                                                                      const unsigned int* __restrict__ bins, int tiles_x, int W, int H, int r0, int r1,
-                                                                      unsigned long long* keys, float* smap, Counters* cnt,
+                                                                      const unsigned int* __restrict__ bins, int tiles_x, int n_tiles, int W, int H,
+                                                                      unsigned long long* keys, const TileTargets* __restrict__ targets, Counters* cnt,
                                                                       const unsigned int* __restrict__ active, const unsigned int* __restrict__ n_active) {
   __shared__ TileRec recs[128];
   if (cnt->large_overflow) return;
   const unsigned int na = *n_active;
   for (unsigned int ai = blockIdx.x; ai < na; ai += gridDim.x) {
-  const int tile = (int)active[ai];
-  const unsigned int b = tile_start[tile], e = tile_start[tile + 1];
-  const int tx = tile % tiles_x, ty = tile / tiles_x;
-  const int x = tx * PRC_TILE + (threadIdx.x & (PRC_TILE - 1)), y = ty * PRC_TILE + (threadIdx.x / PRC_TILE);
-  const float px = (float)x + 0.5f, py = (float)y + 0.5f;
-  const bool live = x < W && y >= r0 && y < r1;
-  unsigned long long best = 0;
-  float bestz = 0.0f;
-  unsigned long long nan_local = 0;
-  for (unsigned int base = b; base < e; base += 128) {
-    const int nb = min(128u, e - base);
-    __syncthreads();
-    if ((int)threadIdx.x < nb) {
-      const LargeRec r = large[bins[base + threadIdx.x]];
-      TileRec t;
-      t.bs = bary_setup<E>(r.x1, r.y1, r.x2, r.y2, r.x3, r.y3);
-      t.z1 = r.z1; t.z2 = r.z2; t.z3 = r.z3; t.seq = r.seq;
-      t.bx0 = r.bx0; t.by0 = r.by0; t.bx1 = r.bx1; t.by1 = r.by1;
-      recs[threadIdx.x] = t;
-    }
-    __syncthreads();
-    if (!live) continue;
-    for (int j = 0; j < nb; j++) {
-      const TileRec& t = recs[j];
-      if (x < t.bx0 || x > t.bx1 || y < t.by0 || y > t.by1) continue;
-      float w1, w2, w3;
-      bary_eval<E>(t.bs, px, py, w1, w2, w3);
-      if (w1 < -PRC_EPS || w2 < -PRC_EPS || w3 < -PRC_EPS) continue;
-      float z = w1 * t.z1 + w2 * t.z2 + w3 * t.z3;
-      if (isnan(z)) { nan_local++; continue; }
-      if (SHADOW) {
-        if (z > bestz) bestz = z;
-      } else {
-        unsigned long long key = ((unsigned long long)depth_key(z) << 32) | (unsigned long long)(0xFFFFFFFFu - t.seq);
-        if (key > best) best = key;
+    const int vtile = (int)active[ai];
+    const int target = vtile / n_tiles, tile = vtile - target * n_tiles;
+    const unsigned int b = tile_start[vtile], e = tile_start[vtile + 1];
+    const int tx = tile % tiles_x, ty = tile / tiles_x;
+    const int x = tx * PRC_TILE + (threadIdx.x & (PRC_TILE - 1)), y = ty * PRC_TILE + (threadIdx.x / PRC_TILE);
+    const float px = (float)x + 0.5f, py = (float)y + 0.5f;
+    const bool live = x < W && y < H;
+    const bool shadow = target != 0;
+    unsigned long long best = 0;
+    float bestz = 0.0f;
+    unsigned long long nan_local = 0;
+    for (unsigned int base = b; base < e; base += 128) {
+      const int nb = min(128u, e - base);
+      __syncthreads();
+      if ((int)threadIdx.x < nb) {
+        const LargeRec r = large[bins[base + threadIdx.x]];
+        TileRec t;
+        t.bs = bary_setup<E>(r.x1, r.y1, r.x2, r.y2, r.x3, r.y3);
+        t.z1 = r.z1; t.z2 = r.z2; t.z3 = r.z3; t.seq = r.seq;
+        t.bx0 = r.bx0; t.by0 = r.by0; t.bx1 = r.bx1; t.by1 = r.by1;
+        recs[threadIdx.x] = t;
+      }
+      __syncthreads();
+      if (!live) continue;
+      for (int j = 0; j < nb; j++) {
+        const TileRec& t = recs[j];
+        if (x < t.bx0 || x > t.bx1 || y < t.by0 || y > t.by1) continue;  // the record's box is already clamped to the pass's rows
+        float w1, w2, w3;
+        bary_eval<E>(t.bs, px, py, w1, w2, w3);
+        if (w1 < -PRC_EPS || w2 < -PRC_EPS || w3 < -PRC_EPS) continue;
+        float z = w1 * t.z1 + w2 * t.z2 + w3 * t.z3;
+        if (isnan(z)) { nan_local++; continue; }
+        if (shadow) {
+          if (z > bestz) bestz = z;
+        } else {
+          unsigned long long key = ((unsigned long long)depth_key(z) << 32) | (unsigned long long)(0xFFFFFFFFu - t.seq);
+          if (key > best) best = key;
+        }
       }
     }
-  }
-  if (nan_local) atomicAdd(&cnt->n_nan, nan_local);
-  if (!live) continue;
-  const size_t idx = (size_t)y * W + x;
-  if (SHADOW) {
-    if (bestz > 0.0f) atomicMax((int*)&smap[idx], __float_as_int(bestz));
-  } else {
-    if (best) atomicMax(&keys[idx], best);
-  }
+    if (nan_local) atomicAdd(&cnt->n_nan, nan_local);
+    if (!live) continue;
+    const size_t idx = (size_t)y * W + x;
+    if (shadow) {
+      if (bestz > 0.0f) atomicMax((int*)&targets->smap[target][idx], __float_as_int(bestz));
+    } else {
+      if (best) atomicMax(&keys[idx], best);
+    }
   }
 }
 
@@ -647,7 +696,9 @@ struct Frag {
 
 struct VtxAttr { V4 pos, nor; float u, v; uint32_t col; };
 
-template <bool E>
+// E: arithmetic of everything that decides position / depth; EA: arithmetic of the shading-only attributes
+// (normals, world position, face normal, du/dv). PRC_FMA=mixed runs <true, false>.
+template <bool E, bool EA>
 __device__ void resolve_fragment(const DevScene& S, const DevFrame& F, uint32_t seq, int x, int y, Frag& f) {
   const uint32_t tri = seq >> 3, sub = seq & 7u;
   const uint32_t obj = S.meta[tri] & 0x00FFFFFFu;
@@ -666,7 +717,7 @@ __device__ void resolve_fragment(const DevScene& S, const DevFrame& F, uint32_t 
 #pragma unroll
   for (int k = 0; k < 3; k++) {
     const float* n = S.nor + (size_t)tri * 9 + k * 3;
-    v[k].nor = apply4<E>(V4{__ldg(n), __ldg(n + 1), __ldg(n + 2), 0.0f}, nrm);
+    v[k].nor = apply4<EA>(V4{__ldg(n), __ldg(n + 1), __ldg(n + 2), 0.0f}, nrm);
     v[k].u = __ldg(S.uv + (size_t)tri * 6 + k * 2);
     v[k].v = __ldg(S.uv + (size_t)tri * 6 + k * 2 + 1);
     v[k].col = __ldg(S.col + (size_t)tri * 3 + k);
@@ -696,10 +747,10 @@ __device__ void resolve_fragment(const DevScene& S, const DevFrame& F, uint32_t 
     v[0] = c[0]; v[1] = c[1]; v[2] = c[2];
   }
   // un-project without dividing by W (raster.go:467-469)
-  V4 m1 = apply4m<E>(apply4m<E>(apply4m<E>(v[0].pos, F.viewport_inv, F.pm_viewport_inv), F.proj_inv, F.pm_proj_inv), F.view_inv, F.pm_view_inv);
-  V4 m2 = apply4m<E>(apply4m<E>(apply4m<E>(v[1].pos, F.viewport_inv, F.pm_viewport_inv), F.proj_inv, F.pm_proj_inv), F.view_inv, F.pm_view_inv);
-  V4 m3 = apply4m<E>(apply4m<E>(apply4m<E>(v[2].pos, F.viewport_inv, F.pm_viewport_inv), F.proj_inv, F.pm_proj_inv), F.view_inv, F.pm_view_inv);
-  f.facenor = unit4<E>(cross4<E>(sub4(m2, m1), sub4(m3, m1)));
+  V4 m1 = apply4m<EA>(apply4m<EA>(apply4m<EA>(v[0].pos, F.viewport_inv, F.pm_viewport_inv), F.proj_inv, F.pm_proj_inv), F.view_inv, F.pm_view_inv);
+  V4 m2 = apply4m<EA>(apply4m<EA>(apply4m<EA>(v[1].pos, F.viewport_inv, F.pm_viewport_inv), F.proj_inv, F.pm_proj_inv), F.view_inv, F.pm_view_inv);
+  V4 m3 = apply4m<EA>(apply4m<EA>(apply4m<EA>(v[2].pos, F.viewport_inv, F.pm_viewport_inv), F.proj_inv, F.pm_proj_inv), F.view_inv, F.pm_view_inv);
+  f.facenor = unit4<EA>(cross4<EA>(sub4(m2, m1), sub4(m3, m1)));
   BarySetup bs = bary_setup<E>(v[0].pos.x, v[0].pos.y, v[1].pos.x, v[1].pos.y, v[2].pos.x, v[2].pos.y);
   const float px = (float)x + 0.5f, py = (float)y + 0.5f;
   float b0, b1, b2;
@@ -714,10 +765,10 @@ __device__ void resolve_fragment(const DevScene& S, const DevFrame& F, uint32_t 
   f.du = 0.0f; f.dv = 0.0f;
   if (material_id >= 0) {  // raster.go:517-535
     float x0, x1, x2, y0, y1, y2;
-    bary_eval<E>(bs, px + 1.0f, py, x0, x1, x2);
+    bary_eval<EA>(bs, px + 1.0f, py, x0, x1, x2);
     float wc1x = rw1 * x0, wc2x = rw2 * x1, wc3x = rw3 * x2;
     float normx = __fdiv_rn(1.0f, (wc1x + wc2x + wc3x));
-    bary_eval<E>(bs, px, py + 1.0f, y0, y1, y2);
+    bary_eval<EA>(bs, px, py + 1.0f, y0, y1, y2);
     float wc1y = rw1 * y0, wc2y = rw2 * y1, wc3y = rw3 * y2;
     float normy = __fdiv_rn(1.0f, (wc1y + wc2y + wc3y));
     float uvdU = (wc1x * v[0].u + wc2x * v[1].u + wc3x * v[2].u) * normx;
@@ -727,7 +778,7 @@ __device__ void resolve_fragment(const DevScene& S, const DevFrame& F, uint32_t 
     f.du = (uvdU - f.u) * (uvdU - f.u) + (uvdX - f.v) * (uvdX - f.v);
     f.dv = (uvdV - f.u) * (uvdV - f.u) + (uvdY - f.v) * (uvdY - f.v);
   }
-  f.nor = unit4<E>(V4{b0 * v[0].nor.x + b1 * v[1].nor.x + b2 * v[2].nor.x, b0 * v[0].nor.y + b1 * v[1].nor.y + b2 * v[2].nor.y,
+  f.nor = unit4<EA>(V4{b0 * v[0].nor.x + b1 * v[1].nor.x + b2 * v[2].nor.x, b0 * v[0].nor.y + b1 * v[1].nor.y + b2 * v[2].nor.y,
                       b0 * v[0].nor.z + b1 * v[1].nor.z + b2 * v[2].nor.z, 0.0f});
   f.wpos = V4{b0 * m1.x + b1 * m2.x + b2 * m3.x, b0 * m1.y + b1 * m2.y + b2 * m3.y, b0 * m1.z + b1 * m2.z + b2 * m3.z, 1.0f};
   uint32_t col = 0;
@@ -759,7 +810,7 @@ __device__ __forceinline__ void gbuf_load(const GBuf& G, size_t idx, Frag& f) {
   f.mat = __float_as_int(d.w);
 }
 
-template <bool E>
+template <bool E, bool EA>
 __global__ void __launch_bounds__(128) k_resolve(DevScene S, DevFrame F, const unsigned long long* __restrict__ keys, GBuf G) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = F.rr0 + blockIdx.y * 4 + (threadIdx.x >> 5);
@@ -771,17 +822,17 @@ __global__ void __launch_bounds__(128) k_resolve(DevScene S, DevFrame F, const u
     return;
   }
   Frag f;
-  resolve_fragment<E>(S, F, 0xFFFFFFFFu - (uint32_t)key, x, y, f);
+  resolve_fragment<E, EA>(S, F, 0xFFFFFFFFu - (uint32_t)key, x, y, f);
   gbuf_store(G, idx, f);
   if (G.ao_depth) G.ao_depth[idx] = f.depth;
 }
 // pixel (0,0) when it lies outside the rasterised rows (multi-GPU strips)
-template <bool E>
+template <bool E, bool EA>
 __global__ void k_resolve00(DevScene S, DevFrame F, const unsigned long long* __restrict__ keys, GBuf G) {
   const unsigned long long key = keys[0];
   if (key == 0) return;
   Frag f;
-  resolve_fragment<E>(S, F, 0xFFFFFFFFu - (uint32_t)key, 0, 0, f);
+  resolve_fragment<E, EA>(S, F, 0xFFFFFFFFu - (uint32_t)key, 0, 0, f);
   gbuf_store(G, 0, f);
 }
 
@@ -853,7 +904,7 @@ __device__ __forceinline__ float go_log2(float x) {
 // finite y > 0): x**y = x**yf * x**yi, integer part by repeated squaring of the Frexp mantissa (only IEEE
 // multiplications => bit-identical to Go for integer y such as every shininess in the fixtures and AO's 10000),
 // fractional part by exp(yf*log(x)). Anything else goes to the CUDA library pow (special values agree).
-__device__ __forceinline__ double go_pow64(double x, double y) {
+__device__ __noinline__ double go_pow64(double x, double y) {
   if (y == 0.0 || x == 1.0) return 1.0;
   if (y == 1.0) return x;
   if (!(x > 0.0) || !(y > 0.0) || isinf(x) || isinf(y)) {
@@ -873,6 +924,17 @@ __device__ __forceinline__ double go_pow64(double x, double y) {
   int xe_i;
   double x1 = frexp(x, &xe_i);
   long long xe = xe_i;
+  if (yi < 2147483648.0) {  // the common case in 32-bit integer arithmetic (same sequence of operations)
+    int xe32 = xe_i, ae32 = 0;
+    for (unsigned int i = (unsigned int)yi; i != 0; i >>= 1) {
+      if (xe32 < -(1 << 12) || (1 << 12) < xe32) { ae32 += xe32; break; }
+      if (i & 1) { a1 = __dmul_rn(a1, x1); ae32 += xe32; }
+      x1 = __dmul_rn(x1, x1);
+      xe32 <<= 1;
+      if (x1 < .5) { x1 = __dadd_rn(x1, x1); xe32--; }
+    }
+    ae = ae32;
+  } else
   for (long long i = (long long)yi; i != 0; i >>= 1) {
     if (xe < -(1 << 12) || (1 << 12) < xe) { ae += xe; break; }
     if (i & 1) { a1 = __dmul_rn(a1, x1); ae += xe; }
@@ -949,30 +1011,30 @@ __device__ bool shading_visibility(const DevFrame& F, const DevLight& l, const F
 
 struct AoConsts { float cosv[8], sinv[8]; float half_pi, four_pi; };
 
-__device__ float max_elevation(const DevFrame& F, const float* __restrict__ ao_depth, int X, int Y, float dirX, float dirY) {
+__device__ __forceinline__ float max_elevation(int W, int H, const float* __restrict__ ao_depth, int X, int Y, float dirX, float dirY) {
   // max over t of Atan(e_t/d_t) == Atan(max over t of e_t/d_t): Atan and the float32 rounding are monotone and
   // Go's Max is NaN-propagating on both sides, so one atan per direction reproduces ao.go:40-73 exactly.
   const float pxf = (float)X, pyf = (float)Y;
   float m = 0.0f;
-  const float traceDepth = ao_depth[(size_t)Y * F.W + X];
+  const float traceDepth = ao_depth[(size_t)Y * W + X];
   for (int ti = 0; ti < 100; ti++) {
     const float t = (float)ti;
     float cx = pxf + dirX * t, cy = pyf + dirY * t;
     long long ix = go_int(cx), iy = go_int(cy);
-    if (ix < 0 || iy < 0 || ix >= F.W || iy >= F.H) break;
+    if (ix < 0 || iy < 0 || ix >= W || iy >= H) break;
     float dxv = pxf - cx, dyv = pyf - cy;
     // Vec4.Len of (dx, dy, 0, 0): FMA(dx,dx, FMA(dy,dy, FMA(0,0, 0*0)))
     float dist = __fsqrt_rn(fma32<true>(dxv, dxv, fma32<true>(dyv, dyv, 0.0f)));
     if (dist < 1.0f) continue;
-    float elevation = ao_depth[(size_t)iy * F.W + ix] - traceDepth;
+    float elevation = ao_depth[(size_t)iy * W + ix] - traceDepth;
     m = go_max(m, __fdiv_rn(elevation, dist));
   }
   return (float)atan((double)m);
 }
-__device__ uint32_t ao_shade(const DevFrame& F, const AoConsts* __restrict__ A, const float* __restrict__ ao_depth, int X, int Y, uint32_t col) {
+__device__ __noinline__ uint32_t ao_shade(int W, int H, const AoConsts* __restrict__ A, const float* __restrict__ ao_depth, int X, int Y, uint32_t col) {
   float total = 0.0f;
 #pragma unroll 1
-  for (int k = 0; k < 8; k++) total += A->half_pi - max_elevation(F, ao_depth, X, Y, A->cosv[k], A->sinv[k]);
+  for (int k = 0; k < 8; k++) total += A->half_pi - max_elevation(W, H, ao_depth, X, Y, A->cosv[k], A->sinv[k]);
   total = __fdiv_rn(total, A->four_pi);
   total = go_pow(total, 10000.0f);
   return go_u8(total * (float)chan(col, 0)) | (go_u8(total * (float)chan(col, 1)) << 8) | (go_u8(total * (float)chan(col, 2)) << 16) | (col & 0xff000000u);
@@ -999,7 +1061,7 @@ __device__ uint32_t shade_pixel(const DevScene& S, const DevFrame& F, const AoCo
       float w = go_pow(0.5f, visibles);
       col = go_u8((float)chan(col, 0) * w) | (go_u8((float)chan(col, 1) * w) << 8) | (go_u8((float)chan(col, 2) * w) << 16) | (col & 0xff000000u);
     }
-    if (mat->flags & PRC_MAT_AMBIENT_OCCLUSION) col = ao_shade(F, A, ao_depth, fragX, fragY, col);
+    if (mat->flags & PRC_MAT_AMBIENT_OCCLUSION) col = ao_shade(F.W, F.H, A, ao_depth, fragX, fragY, col);
   }
   return col;
 }

@@ -252,6 +252,11 @@ class Renderer:
                 raise NotImplementedError("render: a shadow-casting Directional light has no light camera in the reference (it panics)")
         self._backend_shadow_reset = True
 
+    def InvalidateScene(self):
+        """Forget the flattened scene (geometry, materials, model matrices, lights): the next Render() re-flattens
+        and re-uploads it. The reference walks the scene graph every frame; this mirror caches it."""
+        self._scene_desc = None
+
     # -- flatten + uniforms
     def scene_desc(self) -> SceneDesc:
         if self._scene_desc is None or self._scene_desc_for is not self.cfg.Scene:
@@ -271,18 +276,24 @@ class Renderer:
         view_inv, proj_inv, vp_inv = gm.inv(view), gm.inv(proj), gm.inv(vp)
         nobj = sd.n_objects
         if nobj:
-            chain = np.stack([m for _, m in sd.geos])
-            own = np.stack([g.ModelMatrix() for g, _ in sd.geos])
-            model = gm.mulm(chain, own)                    # raster.go:242
-            normal = gm.transpose(gm.inv(model))           # raster.go:243
+            # Model / Normal depend on the scene graph only: computed once per flattened scene (the reference
+            # recomputes them every frame, raster.go:242-243; call InvalidateScene() after moving an object)
+            if getattr(sd, "_static_xf", None) is None:
+                chain = np.stack([m for _, m in sd.geos])
+                own = np.stack([g.ModelMatrix() for g, _ in sd.geos])
+                m_ = gm.mulm(chain, own)                   # raster.go:242
+                sd._static_xf = (m_, gm.transpose(gm.inv(m_)))  # raster.go:243
+                sd._lights = c.Scene.Lights()
+            model, normal = sd._static_xf
             trans = gm.mulm(gm.mulm(proj, view)[None], model)  # raster.go:382
         else:
             model = normal = trans = np.zeros((0, 4, 4), np.float32)
+            sd._lights = c.Scene.Lights()
         objs = (A.prc_object_xf * max(1, nobj))()
         flat = np.concatenate([trans.reshape(nobj, 16), normal.reshape(nobj, 16)], axis=1).astype(np.float32) if nobj else np.zeros((0, 32), np.float32)
         C.memmove(objs, flat.ctypes.data, flat.nbytes)
         fd.keep.append(objs)
-        sources, envs = c.Scene.Lights()
+        sources, envs = sd._lights
         lights = (A.prc_light * max(1, len(sources)))()
         for i, l in enumerate(sources):
             pl = lights[i]
@@ -336,8 +347,14 @@ class Renderer:
             raise ValueError("render: Scene and Camera are required")
         self._ensure_uploaded()
         fd = self.frame_desc(keep_gbuffer=keep_gbuffer)
-        out = np.zeros((c.Height, c.Width, 4), np.uint8)
-        self._backend.render(fd, out)
+        if hasattr(self._backend, "host_image"):
+            # zero copy: the frame is read in place from the library's page-locked double buffer, which — like the
+            # reference's (raster.go:86,201-206) — stays valid until two frames later
+            self._backend.render(fd, None)
+            out = self._backend.host_image(c.Width, c.Height)
+        else:
+            out = np.zeros((c.Height, c.Width, 4), np.uint8)
+            self._backend.render(fd, out)
         self._last_frame = fd
         return out
 

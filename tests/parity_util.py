@@ -80,6 +80,20 @@ def assert_bit_exact(st):
             assert v == 0, (k, st)
 
 
+def assert_mixed(st, attr_ulp=8):
+    """PRC_FMA=mixed (default): everything that decides coverage, triangle id, depth, perspective-correct UV and the
+    shadow maps is bit-exact; the shading-only attributes (normal, face normal, world position) may differ from
+    the float64-FMA reference by double-rounding cases of fmaf (a few ulp after normalisation)."""
+    assert st["valid_gpu"] == st["valid_cpu"], st
+    assert st["coverage_xor"] == 0 and st["tri_mismatch"] == 0 and st["sub_mismatch"] == 0, st
+    assert st["depth_max_ulp"] == 0 and st["uv_max_ulp"] == 0 and st["mat_mismatch"] == 0, st
+    for k in ("nor", "facenor", "wpos"):
+        assert st[f"{k}_max_ulp"] <= attr_ulp, (k, st)
+    for k, v in st.items():
+        if k.startswith("shadow") and k.endswith("max_ulp"):
+            assert v == 0, (k, st)
+
+
 def assert_north_star_gate(st, tie_budget=0):
     """north_star: coverage + tri-ID bit-exact apart from a stated count of edge-tie pixels, depth
     within 1 ulp, RGBA8 within 1/255 on >= 99.9 % of pixels."""

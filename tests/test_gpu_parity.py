@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from polyred_b200 import camera, light, material, render, scene, synth
-from parity_util import assert_bit_exact, assert_north_star_gate, compare_frames, make_renderers
+from parity_util import assert_bit_exact, assert_mixed, assert_north_star_gate, compare_frames, make_renderers
 
 pytestmark = pytest.mark.gpu
 
@@ -64,6 +64,25 @@ def test_persistent_shadow_maps_and_second_frame():
     b = g.Render()
     assert np.array_equal(a, b)
     assert np.array_equal(a, c.Render())
+
+
+def test_default_mixed_mode_gbuffer_exact_rgba_within_gate(monkeypatch):
+    """Default PRC_FMA=mixed: coverage, triangle ids, depth, UV and the shadow maps use the exact float64-FMA
+    emulation (bit-exact asserted); shading-only attributes and the deferred shading use fmaf (a few ulp /
+    north_star RGBA gate asserted, differences reported)."""
+    monkeypatch.delenv("PRC_FMA", raising=False)
+    s, cam = synth.city_scene(n_objects=25, obj_stacks=20, obj_slices=20, ground_cells=60, tex_size=64)
+    g, c = make_renderers(s, cam, 480, 270, shadow=True, gamma=True)
+    st, ig, ic = compare_frames(g, c, 480, 270, n_lights_cast=(0, 2, 4, 6))
+    _report("c3-mixed", st)
+    assert_mixed(st)
+    assert_north_star_gate(st)
+    s, cam = synth.mesh_scene(subdiv=40, with_ground=True, shadows=True, ao=True)
+    g, c = make_renderers(s, cam, 320, 200, shadow=True, gamma=True)
+    st, ig, ic = compare_frames(g, c, 320, 200, n_lights_cast=(1,))
+    _report("c2-mixed", st)
+    assert_mixed(st)
+    assert_north_star_gate(st)
 
 
 def test_fast_fma_mode_within_gate(monkeypatch):
