@@ -44,6 +44,7 @@ struct prc_ctx {
   DBuf d_large, d_clipq, d_tilecount, d_tilestart, d_cursor, d_bins, d_active, d_chunksum, d_targets, d_frame_sh;
   uint32_t n_targets = 1;
   uint32_t target_of_light[64] = {0};
+  bool light_affine[64] = {false};
   DBuf d_xf, d_lights, d_ambient, d_gamma, d_frame, d_aoc;
   std::vector<DevLight> h_lights;    // host staging of the per-frame light table
   TileTargets h_targets{};
@@ -282,7 +283,15 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
     d.pm_view = plain_mask(l.view);
     d.pm_proj = plain_mask(l.proj);
     d.shadow_map = (float*)ctx->d_shadow[i].p;
-    if (d.cast_shadow) UPLOAD(ctx->d_shadow_trans[i], l.shadow_trans, (size_t)fr->n_objects * 64);
+    if (d.cast_shadow) {
+      UPLOAD(ctx->d_shadow_trans[i], l.shadow_trans, (size_t)fr->n_objects * 64);
+      bool aff = true;
+      for (uint32_t o = 0; o < fr->n_objects && aff; o++) {
+        const float* m = l.shadow_trans + (size_t)o * 16;
+        aff = m[12] == 0.0f && m[13] == 0.0f && m[14] == 0.0f && m[15] == 1.0f;
+      }
+      if (i < 64) ctx->light_affine[i] = aff && !getenv("PRC_NO_AFFINE");
+    }
   }
   UPLOAD(ctx->d_lights, hl.data(), hl.size() * sizeof(DevLight));
   {
@@ -330,6 +339,7 @@ int32_t do_shadows(prc_ctx* ctx, const prc_frame* fr, DevFrame F, uint32_t light
   const int per_sweep = getenv("PRC_SHADOW_FUSE") ? std::max(1, std::min(8, atoi(getenv("PRC_SHADOW_FUSE")))) : 8;
   for (uint32_t i = 0; i < fr->n_lights; i++) {
     if (!fr->lights[i].cast_shadow || !((light_mask >> (i & 31)) & 1u)) continue;
+    if (ctx->light_affine[i & 63]) V.affine |= 1u << V.n;
     V.trans[V.n] = (const float*)ctx->d_shadow_trans[i].p;
     V.smap[V.n] = (float*)ctx->d_shadow[i].p;
     V.target[V.n] = ctx->target_of_light[i];
@@ -337,6 +347,7 @@ int32_t do_shadows(prc_ctx* ctx, const prc_frame* fr, DevFrame F, uint32_t light
       int32_t r = raster_pass<E, true>(ctx, F, V);
       if (r != PRC_OK) return r;
       V.n = 0;
+      V.affine = 0;
     }
   }
   if (V.n) {

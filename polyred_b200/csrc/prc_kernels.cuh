@@ -336,12 +336,20 @@ __device__ __forceinline__ bool viewport_pos_std(const float* __restrict__ vp, c
 
 // One raster pass ("view") of one triangle: transform, cull, classify, small raster (see k_geom_raster).
 template <bool E, bool SHADOW>
-__device__ __forceinline__ void geom_view(const DevScene& S, const DevFrame& F, const float* __restrict__ trans, const float* p, const unsigned int tri,
+__device__ __forceinline__ void geom_view(const DevScene& S, const DevFrame& F, const float* __restrict__ trans, const bool affine, const float* p,
+                                          const unsigned int tri,
                                           unsigned long long* keys, float* smap, LargeRec* large, unsigned int large_cap, unsigned int* clipq,
                                           unsigned int clip_cap, Counters* cnt, const DevFrame* Fg, uint32_t target) {
-  const V4 ca = mulv(trans, V4{p[0], p[1], p[2], 1.0f});
-  const V4 cb = mulv(trans, V4{p[3], p[4], p[5], 1.0f});
-  const V4 cc = mulv(trans, V4{p[6], p[7], p[8], 1.0f});
+  V4 ca, cb, cc;
+  if (SHADOW && affine) {
+    // last row of trans is exactly (0,0,0,1) (orthographic light camera x affine model): w = 0*x + 0*y + 0*z + 1*1 = 1
+    // for finite x,y,z; non-finite coordinates make x/y/z non-finite too and are caught by the finite test below
+    ca = mulv3(trans, p[0], p[1], p[2]); cb = mulv3(trans, p[3], p[4], p[5]); cc = mulv3(trans, p[6], p[7], p[8]);
+  } else {
+    ca = mulv(trans, V4{p[0], p[1], p[2], 1.0f});
+    cb = mulv(trans, V4{p[3], p[4], p[5], 1.0f});
+    cc = mulv(trans, V4{p[6], p[7], p[8], 1.0f});
+  }
   V4 p1, p2, p3;
   if (!(F.vp_std && viewport_pos_std<E>(F.viewport, ca, p1) && viewport_pos_std<E>(F.viewport, cb, p2) && viewport_pos_std<E>(F.viewport, cc, p3))) {
     // non-standard viewport matrix or NaN / Inf / zero z,w: the literal reference sequence
@@ -439,6 +447,7 @@ __device__ __forceinline__ void geom_view(const DevScene& S, const DevFrame& F, 
 // Shadow passes of several lights share one sweep over the triangles (positions are loaded and staged once).
 struct GeomViews {
   int n;
+  uint32_t affine;  // bit v: every object's trans of view v has last row (0,0,0,1) (checked on the host)
   const float* trans[8];  // per view: [n_obj][16] light trans (shadow) — unused for the camera (F.xf)
   float* smap[8];
   uint32_t target[8];
@@ -468,15 +477,15 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, 4) k_geom_raster(DevScene S,
   __syncwarp();
   if (meta & 0x80000000u) return;  // !IsValid
   const uint32_t obj = meta & 0x00FFFFFFu;
-  float p[9];
-#pragma unroll
-  for (int i = 0; i < 9; i++) p[i] = sp[threadIdx.x * 9 + i];
+  // the staged positions stay in shared memory and are re-read per view (cheaper than keeping 9 registers
+  // alive across the view loop, which the 64-register cap turns into local-memory traffic)
+  const float* p = sp + threadIdx.x * 9;
   if (SHADOW) {
 #pragma unroll 1
     for (int v = 0; v < V.n; v++)
-      geom_view<E, true>(S, F, V.trans[v] + (size_t)obj * 16, p, tri, keys, V.smap[v], large, large_cap, clipq, clip_cap, cnt, Fg, V.target[v]);
+      geom_view<E, true>(S, F, V.trans[v] + (size_t)obj * 16, (V.affine >> v) & 1, p, tri, keys, V.smap[v], large, large_cap, clipq, clip_cap, cnt, Fg, V.target[v]);
   } else {
-    geom_view<E, false>(S, F, F.xf[obj].trans, p, tri, keys, nullptr, large, large_cap, clipq, clip_cap, cnt, Fg, 0u);
+    geom_view<E, false>(S, F, F.xf[obj].trans, false, p, tri, keys, nullptr, large, large_cap, clipq, clip_cap, cnt, Fg, 0u);
   }
 }
 
@@ -922,7 +931,17 @@ __device__ __noinline__ double go_pow64(double x, double y) {
     a1 = exp(yf * log(x));
   }
   int xe_i;
-  double x1 = frexp(x, &xe_i);
+  double x1;
+  {
+    // Frexp by bit manipulation for normal x (x is finite and > 0 here); the library call handles subnormals
+    const int hi = __double2hiint(x), e = (hi >> 20) & 0x7FF;
+    if (e != 0) {
+      xe_i = e - 1022;
+      x1 = __hiloint2double((hi & (int)0x800FFFFF) | (1022 << 20), __double2loint(x));
+    } else {
+      x1 = frexp(x, &xe_i);
+    }
+  }
   long long xe = xe_i;
   if (yi < 2147483648.0) {  // the common case in 32-bit integer arithmetic (same sequence of operations)
     int xe32 = xe_i, ae32 = 0;
@@ -933,6 +952,8 @@ __device__ __noinline__ double go_pow64(double x, double y) {
       xe32 <<= 1;
       if (x1 < .5) { x1 = __dadd_rn(x1, x1); xe32--; }
     }
+    // Ldexp: a1 >= 2^-32 (at most 31 mantissa products), so for -980 < ae <= 0 scaling by 2^ae stays normal and is exact
+    if (ae32 > -980 && ae32 <= 0 && a1 < 1e100) return __dmul_rn(a1, __hiloint2double((ae32 + 1023) << 20, 0));
     ae = ae32;
   } else
   for (long long i = (long long)yi; i != 0; i >>= 1) {
@@ -1000,6 +1021,14 @@ __device__ bool shading_visibility(const DevFrame& F, const DevLight& l, const F
   if (!l.cast_shadow) return true;
   V4 sc = pos4(apply4m<E>(apply4m<E>(apply4m<E>(apply4m<E>(V4{(float)info.X, (float)info.Y, info.depth, 1.0f}, F.vtw, F.pm_vtw), l.view, l.pm_view), l.proj, l.pm_proj),
                           F.viewport, F.pm_viewport));
+  if (fabsf(sc.x) < 5e8f && fabsf(sc.y) * (float)F.W < 1.5e9f) {  // 32-bit fast path: int(x) + int(y)*W cannot overflow
+    const int idx = __float2int_rz(sc.x) + __float2int_rz(sc.y) * F.W;
+    if (idx > 0 && idx < F.W * F.H) {
+      float shadowZ = l.shadow_map[idx];
+      if (sc.z < shadowZ - 0.03f) return true;
+    }
+    return false;
+  }
   long long lx = go_int(sc.x), ly = go_int(sc.y);
   long long idx = (long long)((unsigned long long)lx + (unsigned long long)ly * (unsigned long long)F.W);
   if (idx > 0 && idx < (long long)F.W * F.H) {

@@ -125,6 +125,15 @@ __device__ __forceinline__ V4 mulv(const float* __restrict__ m, V4 v) {
   r.w = m[12] * v.x + m[13] * v.y + m[14] * v.z + m[15] * v.w;
   return r;
 }
+// Mat4.MulV for a point (w = 1) when the caller knows the result's w is exactly 1 (last row (0,0,0,1))
+__device__ __forceinline__ V4 mulv3(const float* __restrict__ m, float x, float y, float z) {
+  V4 r;
+  r.x = m[0] * x + m[1] * y + m[2] * z + m[3];
+  r.y = m[4] * x + m[5] * y + m[6] * z + m[7];
+  r.z = m[8] * x + m[9] * y + m[10] * z + m[11];
+  r.w = 1.0f;
+  return r;
+}
 template <bool E>
 __device__ __forceinline__ float cross2z(float vx, float vy, float ux, float uy) {  // Vec3.Cross .Z (math/vec3.go:113-120)
   return fma32<E>(vx, uy, -(vy * ux));
@@ -165,8 +174,10 @@ __device__ __forceinline__ uint32_t lerpc(uint32_t from, uint32_t to, float t) {
   uint32_t r = 0;
 #pragma unroll
   for (int i = 0; i < 4; i++) {
+    // from,to in [0,255] and t in [0,1) keep the value inside [0,255], where Go's uint8(float32) is a plain
+    // truncation; a NaN t gives NaN -> 0 in both Go (CVTTSS2SL low byte) and CUDA (cvt.rzi of NaN is 0)
     float f = (float)chan(from, i), g = (float)chan(to, i);
-    r |= go_u8(f + t * (g - f)) << (8 * i);
+    r |= ((uint32_t)__float2int_rz(f + t * (g - f)) & 0xffu) << (8 * i);
   }
   return r;
 }

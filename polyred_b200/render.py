@@ -359,6 +359,20 @@ class Renderer:
         return out
 
 
+def RenderViews(r: Renderer, cameras) -> list:
+    """BASELINE config 5 (multi-view): the same scene from several cameras. Each view goes through
+    Options(Camera(c)) exactly as a reference caller would, which re-fits the light cameras to the new view
+    frustum and zeroes the shadow maps (render/options.go:125-141, bug-list 5), then Render(). The flattened
+    scene stays resident in HBM across views."""
+    out = []
+    for cam in cameras:
+        sd = r._scene_desc
+        r.Options(Camera(cam))
+        r._scene_desc = sd          # Options() drops the flattened scene; the geometry did not change
+        out.append(r.Render().copy())
+    return out
+
+
 def NewRenderer(*opts) -> Renderer:
     """render.NewRenderer (render/raster.go:84-143)."""
     return Renderer(*opts)

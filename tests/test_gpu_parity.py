@@ -96,6 +96,36 @@ def test_fast_fma_mode_within_gate(monkeypatch):
     assert_north_star_gate(st, tie_budget=8)
 
 
+def test_c4_no_shadow_single_light_large_frame():
+    """BASELINE config 4 flavour (reduced): one point light + ambient, no shadows/AO, larger frame so that the
+    ground triangles take the tile path while the instanced meshes stay on the in-thread path."""
+    s, cam = synth.city_scene(n_objects=36, obj_stacks=24, obj_slices=24, ground_cells=12, n_lights=1, casting_every=0, tex_size=64, receive_shadow=False)
+    g, c = make_renderers(s, cam, 1280, 720)
+    st, ig, ic = compare_frames(g, c, 1280, 720)
+    _report("c4", st)
+    assert_bit_exact(st)
+    assert st["rgba_px_diff"] == 0, st
+    assert g._backend.timings().n_large_items > 0
+
+
+def test_c5_multi_view_shadows_refit_per_view():
+    """BASELINE config 5 flavour (reduced): the same scene from 3 orbit cameras; the light cameras are re-fitted
+    and the shadow maps zeroed per view (bug-list 5), the scene stays resident."""
+    import oracle_binding as ob
+    from polyred_b200._lib import CudaBackend
+    cams = []
+    for k in range(3):
+        s, cam = synth.city_scene(n_objects=16, obj_stacks=12, obj_slices=12, ground_cells=30, tex_size=32, cam_angle=2 * math.pi * k / 3, cam_radius=2.6, cam_height=1.1)
+        cams.append(cam)
+    opts = [render.Camera(cams[0]), render.Size(320, 180), render.Scene(s), render.ShadowMap(True), render.GammaCorrection(True)]
+    rg = render.NewRenderer(*opts, render.CUDA(0))
+    rc = render.NewRenderer(*opts, render._Backend(ob.OracleBackend()))
+    vg, vc = render.RenderViews(rg, cams), render.RenderViews(rc, cams)
+    for a, b in zip(vg, vc):
+        assert np.array_equal(a, b)
+    assert not np.array_equal(vg[0], vg[1])
+
+
 def test_bin_overflow_rerenders_frame(monkeypatch):
     """The (tile, triangle) bin array is sized optimistically; on overflow the frame is re-rendered
     with a larger array (no host round trip in the common case). Force the path with a tiny array."""
