@@ -68,6 +68,8 @@ extern "C" {
 #define PRC_FRAME_GAMMA 4u        /* render.GammaCorrection(true) */
 #define PRC_FRAME_KEEP_GBUFFER 8u /* keep the G-buffer for prc_read_gbuffer (parity/debug) */
 #define PRC_FRAME_NO_READBACK 16u /* leave the RGBA on the device (rgba_out may be NULL) */
+#define PRC_FRAME_UNIFORMS_RESIDENT 32u /* the arrays behind objects/lights/shadow_trans/ambient/gamma are unchanged since
+                                           the previous call on this ctx: skip their host->device copies (split-phase calls) */
 
 /* Colours are packed R | G<<8 | B<<16 | A<<24 (image/color.RGBA byte order in memory). */
 
@@ -243,7 +245,18 @@ int32_t prc_device_shadowmap(prc_ctx* ctx, uint32_t light, uint64_t* dev_ptr, ui
  * all-gathers the maps; phase 2 = forward + deferred for rows [row0,row1). */
 int32_t prc_render_shadows(prc_ctx* ctx, const prc_frame* frame, uint32_t light_mask,
                            uint32_t srow0, uint32_t srow1);
+/* Same, for n (light, row range) units in one call: up to 8 units share one sweep over the triangles. */
+int32_t prc_render_shadow_units(prc_ctx* ctx, const prc_frame* frame, uint32_t n, const uint32_t* light, const uint32_t* row0,
+                                const uint32_t* row1);
 int32_t prc_render_main(prc_ctx* ctx, const prc_frame* frame, uint8_t* rgba_out);
+/* prc_render_main in two halves, so the host can overlap the shadow-map exchange with the camera pass:
+ * forward = geometry + raster + resolve for rows [row0,row1) (asynchronous, needs no shadow map);
+ * deferred = shading (+ readback), synchronises. */
+int32_t prc_render_forward(prc_ctx* ctx, const prc_frame* frame);
+int32_t prc_render_deferred(prc_ctx* ctx, const prc_frame* frame, uint8_t* rgba_out);
+/* All shadow maps of the casting lights (casting order, [Ls][height][width] float32) as ONE device range, so the
+ * exchange is a single in-place all-gather; `capacity` >= bytes includes padding for equal-sized chunks. */
+int32_t prc_device_shadow_all(prc_ctx* ctx, uint64_t* dev_ptr, uint64_t* bytes, uint64_t* capacity);
 /* cudaStream_t the ctx launches on (as uint64) so the host can order NCCL after it. */
 int32_t prc_stream(prc_ctx* ctx, uint64_t* stream);
 int32_t prc_sync(prc_ctx* ctx);

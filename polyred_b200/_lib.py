@@ -45,12 +45,17 @@ def lib():
         L.prc_device_shadowmap.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.prc_render_shadows.argtypes = [vp, C.POINTER(A.prc_frame), C.c_uint32, C.c_uint32, C.c_uint32]
         L.prc_render_main.argtypes = [vp, C.POINTER(A.prc_frame), vp]
+        L.prc_render_shadow_units.argtypes = [vp, C.POINTER(A.prc_frame), C.c_uint32, vp, vp, vp]
+        L.prc_render_forward.argtypes = [vp, C.POINTER(A.prc_frame)]
+        L.prc_render_deferred.argtypes = [vp, C.POINTER(A.prc_frame), vp]
+        L.prc_device_shadow_all.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.prc_host_image.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.prc_stream.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.prc_sync.argtypes = [vp]
         for name in ("prc_open", "prc_close", "prc_scene_upload", "prc_shadow_reset", "prc_render", "prc_read_gbuffer",
                      "prc_read_shadowmap", "prc_get_timings", "prc_device_image", "prc_device_shadowmap",
-                     "prc_render_shadows", "prc_render_main", "prc_stream", "prc_sync", "prc_host_image"):
+                     "prc_render_shadows", "prc_render_main", "prc_stream", "prc_sync", "prc_host_image", "prc_render_forward",
+                     "prc_render_deferred", "prc_device_shadow_all", "prc_render_shadow_units"):
             getattr(L, name).restype = C.c_int32
         if L.prc_abi_version() != A.PRC_ABI_VERSION:
             raise PolyredCudaError(A.PRC_ERR_INVALID, "ABI version mismatch")
@@ -152,8 +157,28 @@ class CudaBackend(Backend):
     def render_shadows(self, fd, light_mask, row0, row1):
         self._check(self.L.prc_render_shadows(self.h, C.byref(fd.struct), light_mask, row0, row1))
 
+    def render_shadow_units(self, fd, units):
+        """units: [(light, row0, row1)] — one fused sweep per 8 units."""
+        n = len(units)
+        if not n:
+            return
+        a = np.array(units, dtype=np.uint32).reshape(n, 3)
+        li, r0, r1 = (np.ascontiguousarray(a[:, k]) for k in range(3))
+        self._check(self.L.prc_render_shadow_units(self.h, C.byref(fd.struct), n, li.ctypes.data, r0.ctypes.data, r1.ctypes.data))
+
     def render_main(self, fd, out):
         self._check(self.L.prc_render_main(self.h, C.byref(fd.struct), out.ctypes.data if out is not None else None))
+
+    def render_forward(self, fd):
+        self._check(self.L.prc_render_forward(self.h, C.byref(fd.struct)))
+
+    def render_deferred(self, fd, out):
+        self._check(self.L.prc_render_deferred(self.h, C.byref(fd.struct), out.ctypes.data if out is not None else None))
+
+    def device_shadow_all(self):
+        p, n, cap = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self.L.prc_device_shadow_all(self.h, C.byref(p), C.byref(n), C.byref(cap)))
+        return p.value, n.value, cap.value
 
     def stream(self):
         s = C.c_uint64()

@@ -301,7 +301,8 @@ template <bool E, bool SHADOW>
 // reference to a non-inlined function makes every thread copy it to local memory at kernel entry (measured:
 // 1.76 GB of DRAM writes per launch).
 __device__ __noinline__ void geom_generic(const DevFrame* __restrict__ Fg, const float* trans, const float* __restrict__ pos, uint32_t tri, unsigned long long* keys,
-                                          float* smap, LargeRec* large, unsigned int large_cap, uint32_t target, unsigned int* clipq, unsigned int clip_cap, Counters* cnt) {
+                                          float* smap, LargeRec* large, unsigned int large_cap, uint32_t target, unsigned int* clipq, unsigned int clip_cap, Counters* cnt,
+                                          int vr0, int vr1) {
   float p[9];  // re-read from global memory: passing the caller's register array by pointer would force it into local memory
 #pragma unroll
   for (int i = 0; i < 9; i++) p[i] = pos[(size_t)tri * 9 + i];
@@ -315,7 +316,7 @@ __device__ __noinline__ void geom_generic(const DevFrame* __restrict__ Fg, const
     else atomicExch(&cnt->large_overflow, 1u);
     return;
   }
-  const int r0 = SHADOW ? F.row0 : F.rr0, r1 = SHADOW ? F.row1 : F.rr1;
+  const int r0 = SHADOW ? vr0 : F.rr0, r1 = SHADOW ? vr1 : F.rr1;
   emit_tri<E, SHADOW>(st.p1, st.p2, st.p3, tri * 8u, F, r0, r1, keys, smap, large, large_cap, target, cnt);
 }
 
@@ -339,7 +340,7 @@ template <bool E, bool SHADOW>
 __device__ __forceinline__ void geom_view(const DevScene& S, const DevFrame& F, const float* __restrict__ trans, const bool affine, const float* p,
                                           const unsigned int tri,
                                           unsigned long long* keys, float* smap, LargeRec* large, unsigned int large_cap, unsigned int* clipq,
-                                          unsigned int clip_cap, Counters* cnt, const DevFrame* Fg, uint32_t target) {
+                                          unsigned int clip_cap, Counters* cnt, const DevFrame* Fg, uint32_t target, const int vr0, const int vr1) {
   V4 ca, cb, cc;
   if (SHADOW && affine) {
     // last row of trans is exactly (0,0,0,1) (orthographic light camera x affine model): w = 0*x + 0*y + 0*z + 1*1 = 1
@@ -353,12 +354,12 @@ __device__ __forceinline__ void geom_view(const DevScene& S, const DevFrame& F, 
   V4 p1, p2, p3;
   if (!(F.vp_std && viewport_pos_std<E>(F.viewport, ca, p1) && viewport_pos_std<E>(F.viewport, cb, p2) && viewport_pos_std<E>(F.viewport, cc, p3))) {
     // non-standard viewport matrix or NaN / Inf / zero z,w: the literal reference sequence
-    geom_generic<E, SHADOW>(Fg, trans, S.pos, tri, keys, smap, large, large_cap, target, clipq, clip_cap, cnt);
+    geom_generic<E, SHADOW>(Fg, trans, S.pos, tri, keys, smap, large, large_cap, target, clipq, clip_cap, cnt, vr0, vr1);
     return;
   }
   const float mag = fabsf(p1.x) + fabsf(p1.y) + fabsf(p1.z) + fabsf(p2.x) + fabsf(p2.y) + fabsf(p2.z) + fabsf(p3.x) + fabsf(p3.y) + fabsf(p3.z);
   if (!(mag < 1e30f)) {
-    geom_generic<E, SHADOW>(Fg, trans, S.pos, tri, keys, smap, large, large_cap, target, clipq, clip_cap, cnt);
+    geom_generic<E, SHADOW>(Fg, trans, S.pos, tri, keys, smap, large, large_cap, target, clipq, clip_cap, cnt, vr0, vr1);
     return;
   }
   // cullBackFace (render/cull.go:26-28)
@@ -380,7 +381,7 @@ __device__ __forceinline__ void geom_view(const DevScene& S, const DevFrame& F, 
       return;
     }
   }
-  const int r0 = SHADOW ? F.row0 : F.rr0, r1 = SHADOW ? F.row1 : F.rr1;
+  const int r0 = SHADOW ? vr0 : F.rr0, r1 = SHADOW ? vr1 : F.rr1;
   const uint32_t seq = tri * 8u;
   if (!SHADOW && r0 > 0) raster_pixel00<E>(p1, p2, p3, seq, keys, cnt);
   // pixel box int(Round(min)-1) .. int(Round(max)+1) clamped to the buffer (raster.go:473-485); clamping in float first
@@ -451,6 +452,7 @@ struct GeomViews {
   const float* trans[8];  // per view: [n_obj][16] light trans (shadow) — unused for the camera (F.xf)
   float* smap[8];
   uint32_t target[8];
+  int r0[8], r1[8];  // rows of the shadow map this view rasterises
 };
 
 template <bool E, bool SHADOW>
@@ -483,9 +485,10 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, 4) k_geom_raster(DevScene S,
   if (SHADOW) {
 #pragma unroll 1
     for (int v = 0; v < V.n; v++)
-      geom_view<E, true>(S, F, V.trans[v] + (size_t)obj * 16, (V.affine >> v) & 1, p, tri, keys, V.smap[v], large, large_cap, clipq, clip_cap, cnt, Fg, V.target[v]);
+      geom_view<E, true>(S, F, V.trans[v] + (size_t)obj * 16, (V.affine >> v) & 1, p, tri, keys, V.smap[v], large, large_cap, clipq, clip_cap, cnt, Fg, V.target[v],
+                         V.r0[v], V.r1[v]);
   } else {
-    geom_view<E, false>(S, F, F.xf[obj].trans, false, p, tri, keys, nullptr, large, large_cap, clipq, clip_cap, cnt, Fg, 0u);
+    geom_view<E, false>(S, F, F.xf[obj].trans, false, p, tri, keys, nullptr, large, large_cap, clipq, clip_cap, cnt, Fg, 0u, 0, 0);
   }
 }
 

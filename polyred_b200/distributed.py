@@ -3,10 +3,11 @@
 The reference has no multi-GPU path. Partition (north_star): the scene is replicated, the
 screen is cut into N horizontal strips (16-row aligned), the Ls shadow maps are cut into (light, row
 range) shards dealt round-robin. Per frame:
-  1. every rank rasterises its shadow shards into its local copy of the maps   (prc_render_shadows)
-  2. each shard is broadcast from its owner into the other ranks' maps         (NCCL, device pointers)
-  3. every rank runs forward + deferred for its strip                          (prc_render_main)
-  4. the RGBA8 strips are sent to rank 0's image buffer                        (NCCL send/recv)
+  1. every rank rasterises its chunk of the stacked shadow maps                (prc_render_shadows)
+  2. ONE in-place NCCL all-gather over the library's contiguous shadow buffer  (prc_device_shadow_all), asynchronous
+  3. meanwhile: camera geometry + raster + resolve for this rank's strip       (prc_render_forward)
+  4. shading once the maps have arrived                                        (prc_render_deferred)
+  5. the RGBA8 strips are sent to rank 0's image buffer                        (NCCL batched send/recv)
 The result is bit-identical to the 1-GPU frame: atomicMax keys / depth maxima do not depend on who
 rasterised what, and every rank also rasterises pixel (0,0) (bug-list 3) and the AO halo rows.
 """
@@ -36,8 +37,12 @@ class DistributedFrame:
         sources, _ = c.Scene.Lights()
         self.cast = [i for i, l in enumerate(sources) if l.cast_shadow] if c.ShadowMap else []
         self.cuts = partition.strips(self.h, world)
+        self.chunk, _ = partition.shadow_chunks(self.h, world, len(self.cast))
         self.units = partition.shadow_units(self.h, world, self.cast)
+        self.stream = torch.cuda.ExternalStream(self.be.stream(), device=self.device)
         self._views = {}
+        import os
+        self.overlap = os.environ.get("PRC_MGPU_OVERLAP", "1") != "0"
 
     def prepare(self, fd):
         fd.struct.row0, fd.struct.row1 = self.cuts[self.rank], self.cuts[self.rank + 1]
@@ -52,25 +57,42 @@ class DistributedFrame:
     def render(self, fd, host_out: np.ndarray | None = None):
         import torch.distributed as dist
         torch, be, w, h = self.torch, self.be, self.w, self.h
-        for li, a, b, owner in self.units:
-            if owner == self.rank:
-                be.render_shadows(fd, 1 << li, a, b)
-        if self.units:
-            be.sync()
-            for li, a, b, owner in self.units:
-                ptr, _ = be.device_shadowmap(li)
-                dist.broadcast(self._view(ptr + a * w * 4, (b - a) * w * 4), src=owner)
-            torch.cuda.synchronize()
-        be.render_main(fd, None)
-        ptr, nbytes = be.device_image()
-        img = self._view(ptr, nbytes)
-        for k in range(1, self.world):
-            ia, ib = partition.image_rows(h, self.cuts[k], self.cuts[k + 1])
-            seg = img[ia * w * 4:ib * w * 4]
-            if self.rank == k:
-                dist.send(seg, dst=0)
-            elif self.rank == 0:
-                dist.recv(seg, src=k)
-        torch.cuda.synchronize()
-        if host_out is not None and self.rank == 0:
-            host_out.reshape(-1)[:] = img.cpu().numpy()
+        with torch.cuda.stream(self.stream):  # NCCL orders itself after / before the library's stream
+            work = None
+            if self.cast:
+                be.render_shadow_units(fd, [(li, a, b) for li, a, b, owner in self.units if owner == self.rank])
+                ptr, nbytes, cap = be.device_shadow_all()
+                cb = self.chunk * w * 4
+                assert cb * self.world <= cap, "shadow buffer padding too small for this world size"
+                full = self._view(ptr, cb * self.world)
+                # one in-place all-gather: every rank contributes the stacked rows it rasterised
+                work = dist.all_gather_into_tensor(full, full[self.rank * cb:(self.rank + 1) * cb], async_op=True)
+                if not self.overlap:
+                    work.wait()
+                    work = None
+            from . import _abi as A
+            flags = fd.struct.flags
+            if self.cast:
+                fd.struct.flags = flags | A.PRC_FRAME_UNIFORMS_RESIDENT  # uploaded by prc_render_shadows above
+            be.render_forward(fd)      # camera geometry + raster + resolve overlap the exchange
+            if work is not None:
+                work.wait()
+            fd.struct.flags = flags | A.PRC_FRAME_UNIFORMS_RESIDENT
+            be.render_deferred(fd, None)
+            fd.struct.flags = flags
+            ptr, nbytes = be.device_image()
+            img = self._view(ptr, nbytes)
+            ops = []
+            for k in range(1, self.world):
+                ia, ib = partition.image_rows(h, self.cuts[k], self.cuts[k + 1])
+                seg = img[ia * w * 4:ib * w * 4]
+                if self.rank == k:
+                    ops.append(dist.P2POp(dist.isend, seg, 0))
+                elif self.rank == 0:
+                    ops.append(dist.P2POp(dist.irecv, seg, k))
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+            self.stream.synchronize()
+            if host_out is not None and self.rank == 0:
+                host_out.reshape(-1)[:] = img.cpu().numpy()

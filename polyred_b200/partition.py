@@ -16,16 +16,29 @@ def strips(height: int, world: int) -> list[int]:
     return cuts
 
 
+def shadow_chunks(height: int, world: int, n_cast: int) -> tuple[int, list[list[tuple[int, int, int]]]]:
+    """The Ls shadow maps are one stacked [Ls*H][W] array cut into `world` equal chunks of `chunk` stacked rows
+    (the last may be short): rank k rasterises exactly its chunk and ONE in-place all-gather completes every
+    rank's copy. Returns (chunk, per-rank list of (casting index, row0, row1)). C3 on 8 GPUs: half a light each."""
+    total = n_cast * height
+    chunk = (total + world - 1) // world if world else 0
+    per_rank = []
+    for k in range(world):
+        a, b = min(total, k * chunk), min(total, (k + 1) * chunk)
+        units = []
+        while a < b:
+            li, r0 = divmod(a, height)
+            r1 = min(height, r0 + (b - a))
+            units.append((li, r0, r1))
+            a += r1 - r0
+        per_rank.append(units)
+    return chunk, per_rank
+
+
 def shadow_units(height: int, world: int, casting: list[int]) -> list[tuple[int, int, int, int]]:
-    """Work units (light, row0, row1, owner_rank): each casting light's map is cut into
-    max(1, world // Ls) row ranges and dealt round-robin, so every rank rasterises the same number
-    of shadow texels when Ls divides world (C3: 4 lights x 2 halves on 8 GPUs)."""
-    parts = max(1, world // max(1, len(casting)))
-    units = []
-    for li in casting:
-        for p in range(parts):
-            units.append((li, (height * p) // parts, (height * (p + 1)) // parts))
-    return [(li, a, b, k % world) for k, (li, a, b) in enumerate(units)]
+    """Flat list of (light id, row0, row1, owner rank) over all ranks (see shadow_chunks)."""
+    _, per_rank = shadow_chunks(height, world, len(casting))
+    return [(casting[ci], a, b, k) for k, units in enumerate(per_rank) for ci, a, b in units]
 
 
 def image_rows(height: int, row0: int, row1: int) -> tuple[int, int]:
