@@ -213,6 +213,10 @@ def run_cuda(args):
         torch.cuda.synchronize()
         be.sync()
 
+    # clocks / throttle reasons are sampled from the warm-up on (the timed region of a 2 ms frame is only tens of ms long)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     # ---- warm-up ----
     for _ in range(max(3, args.warmup)):
         step(fd, None)
@@ -222,9 +226,6 @@ def run_cuda(args):
     n_valid = int(be.timings().n_valid_tris)
 
     # ---- timed region 1: device-resident (value) ----
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ksum = np.zeros(8)
     klaunch = np.zeros(8, np.int64)
     launches = 0
@@ -282,6 +283,11 @@ def run_cuda(args):
     avg_ms = ksum[dom] / max(1, klaunch[dom])
     achieved = alg / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     frame_bytes = algorithmic_bytes(n_valid, n_tris, w, h, len(cast))
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this command (profiles/)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    if world == 1 and args.workload == "C3" and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(names[dom], {}).get("dram_bytes_per_launch")
     h2d = fd.struct.n_objects * 128 + len(cast) * fd.struct.n_objects * 64 + len(sources) * 168 + 256 + 4 * fd.struct.n_ambient
     line = {
         "metric": "Mtris/s", "value": n_valid * fps / 1e6, "unit": "Mtris/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -291,7 +297,7 @@ def run_cuda(args):
                    "fma": os.environ.get("PRC_FMA", "mixed"), "l2": "inputs (1.1 GB scene, 0.9 GB frame buffers) larger than L2; no explicit flush",
                    "partition": "1 GPU" if world == 1 else f"{world} screen strips + {len(units)} shadow shards (one in-place NCCL all-gather overlapped with the camera pass, batched send/recv of the image strips)"},
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s",
-                     "frac": achieved / pk["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms,
+                     "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms,
                      "launches_per_step": float(klaunch[dom]) / args.steps},
         "frame_roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": frame_bytes, "achieved": frame_bytes / (ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
                            "frac": frame_bytes / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], "unit": "GB/s"},
