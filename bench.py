@@ -295,7 +295,7 @@ def run_cuda(args):
         "mpixels_per_s": px * fps / 1e6, "frames_per_s": fps, "wall_ms_per_step": wall_ms / args.steps,
         "config": {"workload": f"{args.workload}: {wl['desc']}", "n_tris": int(n_tris), "n_valid_tris": n_valid, "width": w, "height": h,
                    "fma": os.environ.get("PRC_FMA", "mixed"), "l2": "inputs (1.1 GB scene, 0.9 GB frame buffers) larger than L2; no explicit flush",
-                   "partition": "1 GPU" if world == 1 else f"{world} screen strips + {len(units)} shadow shards (one in-place NCCL all-gather overlapped with the camera pass, batched send/recv of the image strips)"},
+                   "partition": "1 GPU" if world == 1 else f"{world} screen strips + {len(units)} shadow shards (one in-place NCCL all-gather overlapped with the camera pass, one in-place all-gather of the image strips)"},
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s",
                      "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms,
                      "launches_per_step": float(klaunch[dom]) / args.steps},

@@ -238,8 +238,9 @@ int32_t prc_get_timings(prc_ctx* ctx, prc_timings* out);
 
 /* ---- multi-GPU plumbing (one process per GPU; collectives are driven by the host through
  * torch.distributed/NCCL on these device pointers, on the stream returned here) ---- */
-/* Device pointer + byte size of the RGBA8 image (image order) and of shadow map `light`. */
-int32_t prc_device_image(prc_ctx* ctx, uint64_t* dev_ptr, uint64_t* bytes);
+/* Device pointer + byte size of the RGBA8 image (image order; `capacity` >= bytes includes the padding that lets
+ * N equal strips be all-gathered in place) and of shadow map `light`. */
+int32_t prc_device_image(prc_ctx* ctx, uint64_t* dev_ptr, uint64_t* bytes, uint64_t* capacity);
 int32_t prc_device_shadowmap(prc_ctx* ctx, uint32_t light, uint64_t* dev_ptr, uint64_t* bytes);
 /* Split frame: phase 1 = shadow passes for the lights/rows this rank owns; the host then
  * all-gathers the maps; phase 2 = forward + deferred for rows [row0,row1). */

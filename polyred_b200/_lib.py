@@ -41,7 +41,7 @@ def lib():
         L.prc_read_gbuffer.argtypes = [vp, C.POINTER(A.prc_gbuffer_host)]
         L.prc_read_shadowmap.argtypes = [vp, C.c_uint32, vp]
         L.prc_get_timings.argtypes = [vp, C.POINTER(A.prc_timings)]
-        L.prc_device_image.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.prc_device_image.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.prc_device_shadowmap.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.prc_render_shadows.argtypes = [vp, C.POINTER(A.prc_frame), C.c_uint32, C.c_uint32, C.c_uint32]
         L.prc_render_main.argtypes = [vp, C.POINTER(A.prc_frame), vp]
@@ -145,9 +145,9 @@ class CudaBackend(Backend):
         return views[key]
 
     def device_image(self):
-        p, n = C.c_uint64(), C.c_uint64()
-        self._check(self.L.prc_device_image(self.h, C.byref(p), C.byref(n)))
-        return p.value, n.value
+        p, n, cap = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self.L.prc_device_image(self.h, C.byref(p), C.byref(n), C.byref(cap)))
+        return p.value, n.value, cap.value
 
     def device_shadowmap(self, light):
         p, n = C.c_uint64(), C.c_uint64()

@@ -45,7 +45,8 @@ struct prc_ctx {
   uint32_t n_targets = 1;
   uint32_t target_of_light[64] = {0};
   bool light_affine[64] = {false};
-  DBuf d_xf, d_lights, d_ambient, d_gamma, d_frame, d_aoc;
+  DBuf d_xf, d_lights, d_ambient, d_gamma, d_frame, d_aoc, d_chunkbox, d_vis;
+  uint32_t n_chunks = 0;
   std::vector<DevLight> h_lights;    // host staging of the per-frame light table
   TileTargets h_targets{};
   std::vector<DBuf> d_shadow_trans;  // per light
@@ -153,13 +154,29 @@ inline unsigned int cdiv(unsigned long long a, unsigned int b) { return (unsigne
 // ---- one raster pass (camera or one shadow light): geometry + in-thread small raster; large triangles and
 // (camera only) triangles needing clipping are queued. No host round trip. -----------------------------------
 template <bool E, bool SHADOW>
-int32_t raster_pass(prc_ctx* ctx, const DevFrame& F, const GeomViews& V) {
+int32_t raster_pass(prc_ctx* ctx, const DevFrame& F, const GeomViews& Vin) {
   cudaStream_t st = ctx->stream;
   Counters* cnt = (Counters*)ctx->d_counters.p;
   unsigned long long* keys = (unsigned long long*)ctx->d_keys.p;
   LargeRec* large = (LargeRec*)ctx->d_large.p;
   unsigned int* clipq = (unsigned int*)ctx->d_clipq.p;
   DBuf& fb = ctx->d_frame;  // device-resident copy of the frame for the rare generic path (uploaded by build_frame)
+  GeomViews V = Vin;
+  if (ctx->S.n_tris && !getenv("PRC_NO_CHUNK_CULL")) {
+    // chunk culling pays when a view covers only part of the rows (multi-GPU strips / shadow shards)
+    const int nv = SHADOW ? V.n : 1;
+    for (int v = 0; v < nv; v++) {
+      const int r0 = SHADOW ? V.r0[v] : F.rr0, r1 = SHADOW ? V.r1[v] : F.rr1;
+      if (r0 <= 0 && r1 >= F.H && !getenv("PRC_FORCE_CHUNK_CULL")) continue;
+      unsigned char* vis = (unsigned char*)ctx->d_vis.p + (size_t)(SHADOW ? 1 + v : 0) * ctx->n_chunks;
+      const float* tb = SHADOW ? V.trans[v] : (const float*)ctx->d_xf.p;
+      k_chunk_cull<<<cdiv(ctx->n_chunks, 256), 256, 0, st>>>((const ChunkBox*)ctx->d_chunkbox.p, ctx->n_chunks, tb, SHADOW ? 16 : 32,
+                                                             (const float*)((const char*)fb.p + offsetof(DevFrame, viewport)), F.W, F.H, r0, r1,
+                                                             (!SHADOW && r0 > 0) ? 1 : 0, vis);
+      V.vis[v] = vis;
+      ctx->launches++;
+    }
+  }
   if (ctx->S.n_tris) {
     KTimer kt(ctx, SHADOW ? PRC_K_GEOM_SHADOW : PRC_K_GEOM_CAMERA);
     k_geom_raster<E, SHADOW><<<cdiv(ctx->S.n_tris, PRC_GEOM_THREADS), PRC_GEOM_THREADS, 0, st>>>(ctx->S, F, V, keys, large, ctx->large_cap, clipq, ctx->clip_cap,
@@ -237,7 +254,7 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
   ENSURE(ctx->d_keys, npx * 8);
   ENSURE(ctx->d_ga, npx * 16); ENSURE(ctx->d_gb, npx * 16); ENSURE(ctx->d_gc, npx * 16); ENSURE(ctx->d_gd, npx * 16);
   if (ctx->any_ao) ENSURE(ctx->d_ao, npx * 4);
-  ENSURE(ctx->d_image, npx * 4);
+  ENSURE(ctx->d_image, npx * 4 + (size_t)64 * W * 4);  // slack: the multi-GPU image all-gather uses equal, padded strips
   ENSURE(ctx->d_special, 16);
   const int n_tiles = ((W + PRC_TILE - 1) / PRC_TILE) * ((H + PRC_TILE - 1) / PRC_TILE);
   // targets of the tile path: 0 = camera, 1 + k = k-th casting light
@@ -569,7 +586,7 @@ int32_t prc_close(prc_ctx* ctx) {
   DBuf* all[] = {&ctx->d_pos, &ctx->d_nor, &ctx->d_uv, &ctx->d_col, &ctx->d_mat, &ctx->d_meta, &ctx->d_mats, &ctx->d_objstart, &ctx->d_texfirst,
                  &ctx->d_lw, &ctx->d_lh, &ctx->d_loff, &ctx->d_tex, &ctx->d_keys, &ctx->d_ga, &ctx->d_gb, &ctx->d_gc, &ctx->d_gd, &ctx->d_ao,
                  &ctx->d_image, &ctx->d_special, &ctx->d_counters, &ctx->d_large, &ctx->d_clipq, &ctx->d_tilecount, &ctx->d_tilestart, &ctx->d_cursor,
-                 &ctx->d_bins, &ctx->d_active, &ctx->d_chunksum, &ctx->d_targets, &ctx->d_frame_sh, &ctx->d_xf, &ctx->d_lights, &ctx->d_ambient, &ctx->d_gamma, &ctx->d_frame, &ctx->d_aoc};
+                 &ctx->d_bins, &ctx->d_active, &ctx->d_chunksum, &ctx->d_targets, &ctx->d_frame_sh, &ctx->d_xf, &ctx->d_lights, &ctx->d_ambient, &ctx->d_gamma, &ctx->d_frame, &ctx->d_aoc, &ctx->d_chunkbox, &ctx->d_vis};
   for (DBuf* b : all) free_buf(*b);
   free_buf(ctx->d_shadow_all);
   for (auto& b : ctx->d_shadow_trans) free_buf(b);
@@ -629,6 +646,10 @@ int32_t prc_scene_upload(prc_ctx* ctx, const prc_scene* s) {
   CK(cudaMemsetAsync(cnt, 0, sizeof(Counters), ctx->stream));
   if (n) k_validate<<<cdiv(n, 256), 256, 0, ctx->stream>>>((const float*)ctx->d_pos.p, (const uint64_t*)ctx->d_objstart.p, s->n_objects, n,
                                                            (uint32_t*)ctx->d_meta.p, &cnt->n_valid);
+  ctx->n_chunks = cdiv(n, PRC_GEOM_THREADS);
+  ENSURE(ctx->d_chunkbox, (size_t)std::max<uint32_t>(1, ctx->n_chunks) * sizeof(ChunkBox));
+  ENSURE(ctx->d_vis, (size_t)std::max<uint32_t>(1, ctx->n_chunks) * 9);
+  if (n) k_chunk_aabb<<<ctx->n_chunks, 256, 0, ctx->stream>>>((const float*)ctx->d_pos.p, (const uint32_t*)ctx->d_meta.p, n, (ChunkBox*)ctx->d_chunkbox.p);
   CK(cudaMemcpyAsync(ctx->h_counters, cnt, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
@@ -844,10 +865,11 @@ int32_t prc_get_timings(prc_ctx* ctx, prc_timings* out) {
   return PRC_OK;
 }
 
-int32_t prc_device_image(prc_ctx* ctx, uint64_t* dev_ptr, uint64_t* bytes) {
+int32_t prc_device_image(prc_ctx* ctx, uint64_t* dev_ptr, uint64_t* bytes, uint64_t* capacity) {
   if (!ctx || !ctx->d_image.p) return PRC_ERR_INVALID;
   *dev_ptr = (uint64_t)(uintptr_t)ctx->d_image.p;
   *bytes = (uint64_t)ctx->W * ctx->H * 4;
+  *capacity = (uint64_t)ctx->d_image.cap;
   return PRC_OK;
 }
 

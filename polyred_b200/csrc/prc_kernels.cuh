@@ -460,6 +460,7 @@ struct GeomViews {
   float* smap[8];
   uint32_t target[8];
   int r0[8], r1[8];  // rows of the shadow map this view rasterises
+  const unsigned char* vis[8];  // per view: [n_chunks] 0 = no triangle of this 256-triangle chunk can touch the view's rows / screen
 };
 
 template <bool E, bool SHADOW>
@@ -473,6 +474,13 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_
   const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
   const unsigned long long wtri = (unsigned long long)blockIdx.x * PRC_GEOM_THREADS + wbase;  // first triangle of this warp
   if (wtri >= S.n_tris) return;
+  // chunk culling (k_chunk_cull): skip the staging entirely when no view can be touched by this chunk
+  {
+    bool any = false;
+    const int nv = SHADOW ? V.n : 1;
+    for (int v = 0; v < nv; v++) any = any || V.vis[v] == nullptr || V.vis[v][blockIdx.x] != 0;
+    if (!any) return;
+  }
   const unsigned long long wleft = S.n_tris - wtri;
   const int nt = wleft < 32 ? (int)wleft : 32;
   const unsigned int tri = (unsigned int)(wtri + lane);
@@ -491,9 +499,11 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_
   const float* p = sp + threadIdx.x * 9;
   if (SHADOW) {
 #pragma unroll 1
-    for (int v = 0; v < V.n; v++)
+    for (int v = 0; v < V.n; v++) {
+      if (V.vis[v] != nullptr && V.vis[v][blockIdx.x] == 0) continue;
       geom_view<E, true>(S, F, V.trans[v] + (size_t)obj * 16, (V.affine >> v) & 1, p, tri, keys, V.smap[v], large, large_cap, clipq, clip_cap, cnt, Fg, V.target[v],
                          V.r0[v], V.r1[v]);
+    }
   } else {
     geom_view<E, false>(S, F, F.xf[obj].trans, false, p, tri, keys, nullptr, large, large_cap, clipq, clip_cap, cnt, Fg, 0u, 0, 0);
   }
@@ -1144,6 +1154,87 @@ __global__ void __launch_bounds__(128) k_shade(DevScene S, DevFrame F, const AoC
   if (F.flags & PRC_FRAME_GAMMA)
     col = (uint32_t)F.gamma[chan(col, 0)] | ((uint32_t)F.gamma[chan(col, 1)] << 8) | ((uint32_t)F.gamma[chan(col, 2)] << 16) | (col & 0xff000000u);
   image[(size_t)(F.H - 1 - y) * F.W + x] = col;  // image row r = screen y = H-1-r (buffer.go:225)
+}
+
+// ---------------------------------------------------------------------------------------------
+// chunk culling: a chunk = the 256 consecutive triangles one CTA of k_geom_raster handles.
+//   upload:    k_chunk_aabb  -> model-space AABB of the chunk + its object (or "mixed" when it spans objects)
+//   per view:  k_chunk_cull  -> 0 when no triangle of the chunk can produce a fragment in the view's pixel rows / on
+//              screen. Exactness: the screen position of every vertex inside the box lies in the convex hull of the
+//              eight projected corners when all corners have clip w of one sign (projective maps preserve convexity);
+//              the test uses a margin of 2 px + 1e-3 relative for the float rounding of the reference sequence, and the
+//              reference's own pixel loop reaches at most 1.5 px beyond a triangle's bbox. Anything else stays visible.
+// ---------------------------------------------------------------------------------------------
+struct ChunkBox { float mn[3], mx[3]; uint32_t obj; uint32_t mixed; };
+
+__global__ void __launch_bounds__(256) k_chunk_aabb(const float* __restrict__ pos, const uint32_t* __restrict__ meta, uint64_t n, ChunkBox* out) {
+  __shared__ float smn[8][3], smx[8][3];
+  __shared__ uint32_t sobj[2];
+  const uint64_t tri = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+  if (tri < n) {
+    for (int k = 0; k < 3; k++)
+      for (int c = 0; c < 3; c++) {
+        const float v = pos[tri * 9 + k * 3 + c];
+        mn[c] = fminf(mn[c], v); mx[c] = fmaxf(mx[c], v);
+        if (!(fabsf(v) < 3e38f)) { mn[c] = -INFINITY; mx[c] = INFINITY; }  // NaN / Inf vertex: unbounded box
+      }
+  }
+  for (int c = 0; c < 3; c++)
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+      mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+    }
+  if ((threadIdx.x & 31) == 0)
+    for (int c = 0; c < 3; c++) { smn[threadIdx.x >> 5][c] = mn[c]; smx[threadIdx.x >> 5][c] = mx[c]; }
+  const uint64_t last = min(n - 1, (uint64_t)blockIdx.x * 256 + 255);
+  if (threadIdx.x == 0) { sobj[0] = meta[(uint64_t)blockIdx.x * 256] & 0x00FFFFFFu; sobj[1] = meta[last] & 0x00FFFFFFu; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ChunkBox b;
+    for (int c = 0; c < 3; c++) {
+      b.mn[c] = smn[0][c]; b.mx[c] = smx[0][c];
+      for (int w = 1; w < 8; w++) { b.mn[c] = fminf(b.mn[c], smn[w][c]); b.mx[c] = fmaxf(b.mx[c], smx[w][c]); }
+    }
+    b.obj = sobj[0];
+    b.mixed = sobj[0] != sobj[1];  // triangles are grouped by object, so equal ends mean one object
+    out[blockIdx.x] = b;
+  }
+}
+
+// trans_base: [n_obj] matrices with `stride` floats between objects (F.xf -> 32, shadow_trans -> 16)
+__global__ void k_chunk_cull(const ChunkBox* __restrict__ boxes, uint32_t n_chunks, const float* __restrict__ trans_base, int stride,
+                             const float* __restrict__ viewport, int W, int H, int r0, int r1, int need_pixel00, unsigned char* vis) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_chunks) return;
+  const ChunkBox b = boxes[i];
+  unsigned char v = 1;
+  if (!b.mixed && b.mn[0] > -3e38f && b.mx[0] < 3e38f && b.mn[1] > -3e38f && b.mx[1] < 3e38f && b.mn[2] > -3e38f && b.mx[2] < 3e38f) {
+    const float* m = trans_base + (size_t)b.obj * stride;
+    float xmin = 3.4e38f, xmax = -3.4e38f, ymin = 3.4e38f, ymax = -3.4e38f, wmin = 3.4e38f, wmax = -3.4e38f;
+    bool finite = true;
+    for (int k = 0; k < 8; k++) {
+      const float x = (k & 1) ? b.mx[0] : b.mn[0], y = (k & 2) ? b.mx[1] : b.mn[1], z = (k & 4) ? b.mx[2] : b.mn[2];
+      const float cx = m[0] * x + m[1] * y + m[2] * z + m[3], cy = m[4] * x + m[5] * y + m[6] * z + m[7];
+      const float cw = m[12] * x + m[13] * y + m[14] * z + m[15];
+      // Apply(Viewport).Pos(): sx = (vp00*cx + vp03*cw)/cw
+      const float sx = (viewport[0] * cx + viewport[3] * cw) / cw, sy = (viewport[5] * cy + viewport[7] * cw) / cw;
+      finite = finite && fabsf(sx) < 1e30f && fabsf(sy) < 1e30f;
+      xmin = fminf(xmin, sx); xmax = fmaxf(xmax, sx); ymin = fminf(ymin, sy); ymax = fmaxf(ymax, sy);
+      wmin = fminf(wmin, cw); wmax = fmaxf(wmax, cw);
+    }
+    // all corners strictly on one side of w = 0, with head-room against rounding
+    const float wabs = fmaxf(fabsf(wmin), fabsf(wmax));
+    const bool one_side = (wmin > 1e-4f * wabs && wmin > 0.0f) || (wmax < -1e-4f * wabs && wmax < 0.0f);
+    if (finite && one_side) {
+      const float mx_ = 4.0f + 1e-3f * fmaxf(fmaxf(fabsf(xmin), fabsf(xmax)), fmaxf(fabsf(ymin), fabsf(ymax)));
+      const bool hit_rows = ymax + mx_ >= (float)r0 && ymin - mx_ <= (float)r1;
+      const bool hit_cols = xmax + mx_ >= 0.0f && xmin - mx_ <= (float)W;
+      const bool hit00 = need_pixel00 && xmin - mx_ <= 1.0f && ymin - mx_ <= 1.0f && xmax + mx_ >= 0.0f && ymax + mx_ >= 0.0f;
+      v = ((hit_rows && hit_cols) || hit00) ? 1 : 0;
+    }
+  }
+  vis[i] = v;
 }
 
 // ---------------------------------------------------------------------------------------------

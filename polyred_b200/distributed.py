@@ -1,13 +1,13 @@
 """One frame over N GPUs, one process per GPU (torch.distributed / NCCL over NVLink for the plumbing).
 
 The reference has no multi-GPU path. Partition (north_star): the scene is replicated, the
-screen is cut into N horizontal strips (16-row aligned), the Ls shadow maps are cut into (light, row
+screen is cut into N equal horizontal strips, the Ls shadow maps are cut into (light, row
 range) shards dealt round-robin. Per frame:
   1. every rank rasterises its chunk of the stacked shadow maps                (prc_render_shadows)
   2. ONE in-place NCCL all-gather over the library's contiguous shadow buffer  (prc_device_shadow_all), asynchronous
   3. meanwhile: camera geometry + raster + resolve for this rank's strip       (prc_render_forward)
   4. shading once the maps have arrived                                        (prc_render_deferred)
-  5. the RGBA8 strips are sent to rank 0's image buffer                        (NCCL batched send/recv)
+  5. ONE in-place all-gather over the image buffer assembles the frame         (prc_device_image; equal strips)
 The result is bit-identical to the 1-GPU frame: atomicMax keys / depth maxima do not depend on who
 rasterised what, and every rank also rasterises pixel (0,0) (bug-list 3) and the AO halo rows.
 """
@@ -36,7 +36,7 @@ class DistributedFrame:
         self.w, self.h = c.Width, c.Height
         sources, _ = c.Scene.Lights()
         self.cast = [i for i, l in enumerate(sources) if l.cast_shadow] if c.ShadowMap else []
-        self.cuts = partition.strips(self.h, world)
+        self.img_chunk, self.rows = partition.strips(self.h, world)
         self.chunk, _ = partition.shadow_chunks(self.h, world, len(self.cast))
         self.units = partition.shadow_units(self.h, world, self.cast)
         self.stream = torch.cuda.ExternalStream(self.be.stream(), device=self.device)
@@ -45,7 +45,7 @@ class DistributedFrame:
         self.overlap = os.environ.get("PRC_MGPU_OVERLAP", "1") != "0"
 
     def prepare(self, fd):
-        fd.struct.row0, fd.struct.row1 = self.cuts[self.rank], self.cuts[self.rank + 1]
+        fd.struct.row0, fd.struct.row1 = self.rows[self.rank]
         return fd
 
     def _view(self, ptr, nbytes):
@@ -80,19 +80,12 @@ class DistributedFrame:
             fd.struct.flags = flags | A.PRC_FRAME_UNIFORMS_RESIDENT
             be.render_deferred(fd, None)
             fd.struct.flags = flags
-            ptr, nbytes = be.device_image()
-            img = self._view(ptr, nbytes)
-            ops = []
-            for k in range(1, self.world):
-                ia, ib = partition.image_rows(h, self.cuts[k], self.cuts[k + 1])
-                seg = img[ia * w * 4:ib * w * 4]
-                if self.rank == k:
-                    ops.append(dist.P2POp(dist.isend, seg, 0))
-                elif self.rank == 0:
-                    ops.append(dist.P2POp(dist.irecv, seg, k))
-            if ops:
-                for req in dist.batch_isend_irecv(ops):
-                    req.wait()
+            ptr, nbytes, cap = be.device_image()
+            cb = self.img_chunk * w * 4
+            assert cb * self.world <= cap, "image buffer padding too small for this world size"
+            full = self._view(ptr, cb * self.world)
+            # one in-place all-gather assembles the frame (every rank, rank 0 included, ends up with the image)
+            dist.all_gather_into_tensor(full, full[self.rank * cb:(self.rank + 1) * cb])
             self.stream.synchronize()
             if host_out is not None and self.rank == 0:
-                host_out.reshape(-1)[:] = img.cpu().numpy()
+                host_out.reshape(-1)[:] = full[:nbytes].cpu().numpy()

@@ -8,12 +8,16 @@ from __future__ import annotations
 TILE = 16
 
 
-def strips(height: int, world: int) -> list[int]:
-    """world+1 row cuts; strip k = screen rows [cuts[k], cuts[k+1]), 16-row aligned except the last."""
-    tiles = (height + TILE - 1) // TILE
-    cuts = [min(height, ((tiles * k) // world) * TILE) for k in range(world + 1)]
-    cuts[-1] = height
-    return cuts
+def strips(height: int, world: int) -> tuple[int, list[tuple[int, int]]]:
+    """Equal strips of `chunk` IMAGE rows, rank k owning image rows [k*chunk, (k+1)*chunk) (the last may be short),
+    so that ONE in-place all-gather over the image buffer assembles the frame on every rank (rank 0 included).
+    Returns (chunk, [(screen row0, screen row1)] per rank); image row r = screen y = H-1-r (buffer.go:225)."""
+    chunk = (height + world - 1) // world
+    out = []
+    for k in range(world):
+        i0, i1 = min(height, k * chunk), min(height, (k + 1) * chunk)
+        out.append((height - i1, height - i0))
+    return chunk, out
 
 
 def shadow_chunks(height: int, world: int, n_cast: int) -> tuple[int, list[list[tuple[int, int, int]]]]:

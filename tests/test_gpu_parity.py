@@ -126,6 +126,25 @@ def test_c5_multi_view_shadows_refit_per_view():
     assert not np.array_equal(vg[0], vg[1])
 
 
+def test_chunk_culling_is_exact(monkeypatch):
+    """Chunk culling (k_chunk_cull) skips 256-triangle chunks that cannot touch a view's rows / the screen. It is
+    enabled automatically for partial-row views (multi-GPU); forced here on full frames, including a camera that
+    leaves most of the scene off screen and the clipped-ground scene."""
+    monkeypatch.setenv("PRC_FORCE_CHUNK_CULL", "1")
+    s, cam = synth.city_scene(n_objects=25, obj_stacks=20, obj_slices=20, ground_cells=60, tex_size=64, cam_radius=1.2, cam_height=0.5)
+    g, c = make_renderers(s, cam, 480, 270, shadow=True, gamma=True)
+    st, ig, ic = compare_frames(g, c, 480, 270, n_lights_cast=(0, 2, 4, 6))
+    _report("cull-close", st)
+    assert_bit_exact(st)
+    assert st["rgba_px_diff"] == 0, st
+    s, cam = synth.mesh_scene(subdiv=40, with_ground=True, shadows=True, ao=False)
+    g, c = make_renderers(s, cam, 320, 200, shadow=True, gamma=True)
+    st, ig, ic = compare_frames(g, c, 320, 200, n_lights_cast=(1,))
+    _report("cull-clip", st)
+    assert_bit_exact(st)
+    assert st["rgba_px_diff"] == 0, st
+
+
 def test_bin_overflow_rerenders_frame(monkeypatch):
     """The (tile, triangle) bin array is sized optimistically; on overflow the frame is re-rendered
     with a larger array (no host round trip in the common case). Force the path with a tiny array."""

@@ -15,9 +15,11 @@ from polyred_b200 import partition
 def test_strips_and_units_cover_everything_once():
     for h in (2160, 1080, 270, 100, 17):
         for world in (1, 2, 4, 8):
-            cuts = partition.strips(h, world)
-            assert cuts[0] == 0 and cuts[-1] == h and all(a <= b for a, b in zip(cuts, cuts[1:]))
-            assert all(c % 16 == 0 for c in cuts[:-1])
+            chunk, rows = partition.strips(h, world)
+            assert chunk * world >= h and chunk * world - h < world
+            covered = sorted(rows)
+            assert covered[0][0] == 0 and covered[-1][1] == h and all(a[1] == b[0] for a, b in zip(covered, covered[1:]) if a != b or a[1] > a[0])
+            assert rows[0][1] == h  # rank 0 owns the TOP image rows
             units = partition.shadow_units(h, world, [0, 2, 4, 6])
             for li in (0, 2, 4, 6):
                 rows = sorted((a, b) for l, a, b, _ in units if l == li)
@@ -36,7 +38,7 @@ def _worker(rank, world, port, h, w, q):
     rng = np.random.default_rng(5)
     full_img = rng.integers(0, 255, size=(h, w, 4), dtype=np.uint8)      # what one GPU would render
     full_maps = {li: rng.random((h, w)).astype(np.float32) for li in (0, 2)}
-    cuts = partition.strips(h, world)
+    chunk, rows = partition.strips(h, world)
     units = partition.shadow_units(h, world, [0, 2])
     # phase 1: each rank "rasterises" only its shadow units, then every unit is broadcast from its owner
     maps = {li: np.zeros((h, w), np.float32) for li in (0, 2)}
@@ -47,18 +49,13 @@ def _worker(rank, world, port, h, w, q):
         t = torch.from_numpy(maps[li][a:b])
         dist.broadcast(t, src=owner)
     ok_maps = all(np.array_equal(maps[li], full_maps[li]) for li in (0, 2))
-    # phase 2: each rank "shades" its strip; strips are gathered to rank 0 in image order
-    img = np.zeros((h, w, 4), np.uint8)
-    r0, r1 = partition.image_rows(h, cuts[rank], cuts[rank + 1])
+    # phase 2: each rank "shades" its strip; ONE all-gather of equal (padded) strips assembles the frame everywhere
+    img = np.zeros((chunk * world, w, 4), np.uint8)
+    r0, r1 = partition.image_rows(h, *rows[rank])
     img[r0:r1] = full_img[r0:r1]
-    for k in range(1, world):
-        a, b = partition.image_rows(h, cuts[k], cuts[k + 1])
-        seg = torch.from_numpy(img[a:b])
-        if rank == k:
-            dist.send(seg, dst=0)
-        elif rank == 0:
-            dist.recv(seg, src=k)
-    ok_img = np.array_equal(img, full_img) if rank == 0 else True
+    parts = [torch.zeros((chunk, w, 4), dtype=torch.uint8) for _ in range(world)]
+    dist.all_gather(parts, torch.from_numpy(img[rank * chunk:(rank + 1) * chunk].copy()))
+    ok_img = np.array_equal(torch.cat(parts).numpy()[:h], full_img)
     q.put((rank, ok_maps, ok_img))
     dist.barrier()
     dist.destroy_process_group()

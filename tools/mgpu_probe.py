@@ -31,15 +31,10 @@ for _ in range(N):
         timed('forward', lambda: be.render_forward(fd))
         timed('deferred', lambda: be.render_deferred(fd, None))
         fd.struct.flags &= ~A.PRC_FRAME_UNIFORMS_RESIDENT
-        ptr, nbytes = be.device_image(); img = df._view(ptr, nbytes)
+        ptr, nbytes, cap = be.device_image(); icb = df.img_chunk * w * 4
+        img = df._view(ptr, icb * world)
         def gather():
-            ops = []
-            for k in range(1, world):
-                ia, ib = partition.image_rows(h, df.cuts[k], df.cuts[k + 1]); seg = img[ia * w * 4:ib * w * 4]
-                if rank == k: ops.append(dist.P2POp(dist.isend, seg, 0))
-                elif rank == 0: ops.append(dist.P2POp(dist.irecv, seg, k))
-            if ops:
-                for q in dist.batch_isend_irecv(ops): q.wait()
+            dist.all_gather_into_tensor(img, img[rank * icb:(rank + 1) * icb])
         timed('img_gather', gather)
     timed('whole_frame', lambda: df.render(fd, None))
 if rank == 0:
