@@ -205,7 +205,9 @@ def run_cuda(args):
             if host_out is not None:
                 host_out[0] = be.host_image(w, h)
         else:
-            df.render(fdesc, host_out[1] if host_out is not None else None)
+            img = df.render(fdesc, host_out is not None)
+            if host_out is not None:
+                host_out[0] = img
 
     def barrier():
         if dist is not None:

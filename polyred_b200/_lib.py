@@ -13,7 +13,7 @@ import numpy as np
 from . import _abi as A
 
 _LIB = None
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libpolyred_cuda.so")
+LIB_PATH = os.environ.get("PRC_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libpolyred_cuda.so")  # PRC_LIB: a tuning build of the same library
 
 
 class PolyredCudaError(RuntimeError):

@@ -45,8 +45,9 @@ struct prc_ctx {
   uint32_t n_targets = 1;
   uint32_t target_of_light[64] = {0};
   bool light_affine[64] = {false};
-  DBuf d_xf, d_lights, d_ambient, d_gamma, d_frame, d_aoc, d_chunkbox, d_vis;
+  DBuf d_xf, d_lights, d_ambient, d_gamma, d_frame, d_aoc, d_chunkbox, d_vis, d_cverts, d_cvoff, d_lidx;
   uint32_t n_chunks = 0;
+  uint64_t n_cverts = 0;  // distinct chunk-local vertices (k_chunk_dedupe)
   std::vector<DevLight> h_lights;    // host staging of the per-frame light table
   TileTargets h_targets{};
   std::vector<DBuf> d_shadow_trans;  // per light
@@ -179,8 +180,13 @@ int32_t raster_pass(prc_ctx* ctx, const DevFrame& F, const GeomViews& Vin) {
   }
   if (ctx->S.n_tris) {
     KTimer kt(ctx, SHADOW ? PRC_K_GEOM_SHADOW : PRC_K_GEOM_CAMERA);
-    k_geom_raster<E, SHADOW><<<cdiv(ctx->S.n_tris, PRC_GEOM_THREADS), PRC_GEOM_THREADS, 0, st>>>(ctx->S, F, V, keys, large, ctx->large_cap, clipq, ctx->clip_cap,
-                                                                                                     cnt, (const DevFrame*)fb.p);
+    static const bool v1 = getenv("PRC_GEOM_V1") != nullptr;  // A/B switch: the per-triangle kernel without vertex sharing
+    if (v1)
+      k_geom_raster_v1<E, SHADOW><<<cdiv(ctx->S.n_tris, PRC_GEOM_THREADS), PRC_GEOM_THREADS, 0, st>>>(ctx->S, F, V, keys, large, ctx->large_cap, clipq,
+                                                                                                          ctx->clip_cap, cnt, (const DevFrame*)fb.p);
+    else
+      k_geom_raster<E, SHADOW><<<cdiv(ctx->S.n_tris, PRC_GEOM_THREADS), PRC_GEOM_THREADS, 0, st>>>(ctx->S, F, V, keys, large, ctx->large_cap, clipq, ctx->clip_cap,
+                                                                                                       cnt, (const DevFrame*)fb.p);
     ctx->launches++;
   }
   if (!SHADOW) {
@@ -586,7 +592,7 @@ int32_t prc_close(prc_ctx* ctx) {
   DBuf* all[] = {&ctx->d_pos, &ctx->d_nor, &ctx->d_uv, &ctx->d_col, &ctx->d_mat, &ctx->d_meta, &ctx->d_mats, &ctx->d_objstart, &ctx->d_texfirst,
                  &ctx->d_lw, &ctx->d_lh, &ctx->d_loff, &ctx->d_tex, &ctx->d_keys, &ctx->d_ga, &ctx->d_gb, &ctx->d_gc, &ctx->d_gd, &ctx->d_ao,
                  &ctx->d_image, &ctx->d_special, &ctx->d_counters, &ctx->d_large, &ctx->d_clipq, &ctx->d_tilecount, &ctx->d_tilestart, &ctx->d_cursor,
-                 &ctx->d_bins, &ctx->d_active, &ctx->d_chunksum, &ctx->d_targets, &ctx->d_frame_sh, &ctx->d_xf, &ctx->d_lights, &ctx->d_ambient, &ctx->d_gamma, &ctx->d_frame, &ctx->d_aoc, &ctx->d_chunkbox, &ctx->d_vis};
+                 &ctx->d_bins, &ctx->d_active, &ctx->d_chunksum, &ctx->d_targets, &ctx->d_frame_sh, &ctx->d_xf, &ctx->d_lights, &ctx->d_ambient, &ctx->d_gamma, &ctx->d_frame, &ctx->d_aoc, &ctx->d_chunkbox, &ctx->d_vis, &ctx->d_cverts, &ctx->d_cvoff, &ctx->d_lidx};
   for (DBuf* b : all) free_buf(*b);
   free_buf(ctx->d_shadow_all);
   for (auto& b : ctx->d_shadow_trans) free_buf(b);
@@ -651,13 +657,35 @@ int32_t prc_scene_upload(prc_ctx* ctx, const prc_scene* s) {
   ENSURE(ctx->d_vis, (size_t)std::max<uint32_t>(1, ctx->n_chunks) * 9);
   if (n) k_chunk_aabb<<<ctx->n_chunks, 256, 0, ctx->stream>>>((const float*)ctx->d_pos.p, (const uint32_t*)ctx->d_meta.p, n, (ChunkBox*)ctx->d_chunkbox.p);
   CK(cudaMemcpyAsync(ctx->h_counters, cnt, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  // chunk-local vertex sharing (k_chunk_dedupe): count, scan on the host (n/256 integers, once per scene), fill
+  ENSURE(ctx->d_cvoff, (size_t)(ctx->n_chunks + 1) * 4);
+  ENSURE(ctx->d_lidx, std::max<uint64_t>(1, n) * 4);
+  uint64_t n_cverts = 0;
+  {
+    std::vector<uint32_t> off((size_t)ctx->n_chunks + 1, 0u);
+    if (n) {
+      k_chunk_dedupe<<<ctx->n_chunks, 256, 0, ctx->stream>>>((const float*)ctx->d_pos.p, (const uint32_t*)ctx->d_meta.p, n, nullptr, (uint32_t*)ctx->d_cvoff.p,
+                                                             nullptr, nullptr);
+      CK(cudaMemcpyAsync(off.data(), ctx->d_cvoff.p, (size_t)ctx->n_chunks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      for (uint32_t c = 0; c < ctx->n_chunks; c++) { const uint32_t k = off[c]; off[c] = (uint32_t)n_cverts; n_cverts += k; }
+      off[ctx->n_chunks] = (uint32_t)n_cverts;  // < 3 * 2^29 fits 32 bits
+    }
+    CK(cudaMemcpyAsync(ctx->d_cvoff.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ENSURE(ctx->d_cverts, std::max<uint64_t>(1, n_cverts) * 16);
+    if (n)
+      k_chunk_dedupe<<<ctx->n_chunks, 256, 0, ctx->stream>>>((const float*)ctx->d_pos.p, (const uint32_t*)ctx->d_meta.p, n, (const uint32_t*)ctx->d_cvoff.p,
+                                                             nullptr, (float4*)ctx->d_cverts.p, (uint32_t*)ctx->d_lidx.p);
+    CK(cudaStreamSynchronize(ctx->stream));  // `off` is pageable host memory
+  }
+  ctx->n_cverts = n_cverts;
   CK(cudaGetLastError());
   ctx->n_valid = ctx->h_counters->n_valid;
   DevScene& S = ctx->S;
   S.pos = (const float*)ctx->d_pos.p; S.nor = (const float*)ctx->d_nor.p; S.uv = (const float*)ctx->d_uv.p;
   S.col = (const uint32_t*)ctx->d_col.p; S.mat = (const int32_t*)ctx->d_mat.p; S.meta = (const uint32_t*)ctx->d_meta.p;
   S.n_tris = n;
+  S.cverts = (const float4*)ctx->d_cverts.p; S.cvoff = (const uint32_t*)ctx->d_cvoff.p; S.lidx = (const uint32_t*)ctx->d_lidx.p;
   S.mats = (const prc_material*)ctx->d_mats.p; S.n_mats = s->n_materials;
   S.tex_first = (const uint32_t*)ctx->d_texfirst.p; S.level_w = (const uint32_t*)ctx->d_lw.p; S.level_h = (const uint32_t*)ctx->d_lh.p;
   S.level_off = (const uint64_t*)ctx->d_loff.p; S.tex_data = (const uint8_t*)ctx->d_tex.p;

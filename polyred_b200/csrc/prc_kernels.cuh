@@ -26,6 +26,12 @@ struct DevScene {
   const uint32_t* col;
   const int32_t* mat;
   const uint32_t* meta;  // bit31 = !IsValid, bits 0..23 = object index
+  // chunk-local shared vertices (k_chunk_dedupe): chunk c = triangles [256c, 256c+256) owns the distinct (position, object)
+  // pairs cverts[cvoff[c] .. cvoff[c+1]) = (x, y, z, object bits); lidx[tri] = three 10-bit indices into them
+  // (0xFFFFFFFF for a triangle failing IsValid)
+  const float4* cverts;
+  const uint32_t* cvoff;
+  const uint32_t* lidx;
   uint64_t n_tris;
   const prc_material* mats;
   uint32_t n_mats;
@@ -464,7 +470,7 @@ struct GeomViews {
 };
 
 template <bool E, bool SHADOW>
-__global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_raster(DevScene S, DevFrame F, GeomViews V,
+__global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_raster_v1(DevScene S, DevFrame F, GeomViews V,
                                                                      unsigned long long* keys, LargeRec* large, unsigned int large_cap,
                                                                      unsigned int* clipq, unsigned int clip_cap, Counters* cnt, const DevFrame* Fg) {
   // Each warp stages its own 32 triangles (32 x 36 B = 72 float4, 16-byte aligned because the warp's first
@@ -506,6 +512,196 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_
     }
   } else {
     geom_view<E, false>(S, F, F.xf[obj].trans, false, p, tri, keys, nullptr, large, large_cap, clipq, clip_cap, cnt, Fg, 0u, 0, 0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 (v2): one CTA per 256-triangle chunk, three phases per view, all operands in shared memory.
+//   phase 1  the chunk's DISTINCT vertices (k_chunk_dedupe: ~0.6-0.7 per triangle instead of 3) are transformed
+//            to screen space once: Mat4.MulV + Apply(Viewport).Pos() depend only on (position, object matrix),
+//            so sharing the result between the triangles of a chunk is bit-exact;
+//   phase 2  one thread per triangle gathers its three screen vertices, runs the cull / classify / exact-prune
+//            sequence; survivors with a small pixel box append one 16-bit entry per candidate pixel to a CTA queue
+//            (large boxes -> tile queue, clipping -> clip queue, NaN/Inf/zero w -> geom_generic, as before);
+//   phase 3  the queue is consumed by ALL threads, one candidate pixel each: the in-thread pixel loops ran with
+//            ~3.5 of 32 lanes active (ncu), the queue runs full warps.
+// Several shadow views share the vertex fetch; the camera pass is the same kernel with one view.
+// ---------------------------------------------------------------------------------------------
+#define PRC_QCAP 2048
+template <bool E, bool SHADOW>
+__device__ __forceinline__ void small_pixel(const float p1x, const float p1y, const float p1z, const float p2x, const float p2y, const float p2z,
+                                            const float p3x, const float p3y, const float p3z, const int x, const int y, const uint32_t seq, const int W,
+                                            unsigned long long* keys, float* smap, Counters* cnt) {
+  const BarySetup bs = bary_setup<E>(p1x, p1y, p2x, p2y, p3x, p3y);
+  const float thr = 2e-7f * fabsf(bs.Sabc);
+  const uint32_t sg = __float_as_uint(bs.Sabc);
+  const float px = (float)x + 0.5f, py = (float)y + 0.5f;
+  const float apx = px - bs.t1x, bpx = px - bs.t2x, apy = py - bs.t1y, bpy = py - bs.t2y;
+  if (E) {
+    // cheap certain rejection first: the single-rounding fmaf value is within 1 ulp of the reference's
+    // double-rounded one, so |S_fmaf| > 4e-7 |Sabc| with the wrong sign implies |S| > 2e-7 |Sabc| below
+    const float thr2 = thr + thr;
+    const float q0 = cross2z<false>(bs.abx, bs.aby, apx, apy), q1 = cross2z<false>(apx, apy, bs.acx, bs.acy), q2 = cross2z<false>(bs.bcx, bs.bcy, bpx, bpy);
+    if ((((__float_as_uint(q0) ^ sg) >> 31) && fabsf(q0) > thr2) || (((__float_as_uint(q1) ^ sg) >> 31) && fabsf(q1) > thr2) ||
+        (((__float_as_uint(q2) ^ sg) >> 31) && fabsf(q2) > thr2))
+      return;
+  }
+  const float Sabp = cross2z<E>(bs.abx, bs.aby, apx, apy);
+  const float Sapc = cross2z<E>(apx, apy, bs.acx, bs.acy);
+  const float Sbcp = cross2z<E>(bs.bcx, bs.bcy, bpx, bpy);
+  // certain rejection without dividing: sign(S) != sign(Sabc) and |S| > 2e-7 |Sabc|  =>  RN(S/Sabc) < -1e-7
+  if ((((__float_as_uint(Sabp) ^ sg) >> 31) && fabsf(Sabp) > thr) || (((__float_as_uint(Sapc) ^ sg) >> 31) && fabsf(Sapc) > thr) ||
+      (((__float_as_uint(Sbcp) ^ sg) >> 31) && fabsf(Sbcp) > thr))
+    return;
+  const float w1 = __fdiv_rn(Sbcp, bs.Sabc), w2 = __fdiv_rn(Sapc, bs.Sabc), w3 = __fdiv_rn(Sabp, bs.Sabc);
+  if (w1 < -PRC_EPS || w2 < -PRC_EPS || w3 < -PRC_EPS) return;
+  const float z = w1 * p1z + w2 * p2z + w3 * p3z;
+  if (isnan(z)) { atomicAdd(&cnt->n_nan, 1ULL); return; }
+  const size_t idx = (size_t)y * W + x;
+  // fire-and-forget reductions (RED.MAX): no pre-test load, so nothing waits on memory
+  if (SHADOW) {
+    if (z > 0.0f) atomicMax((int*)&smap[idx], __float_as_int(z));
+  } else {
+    unsigned long long key = ((unsigned long long)depth_key(z) << 32) | (unsigned long long)(0xFFFFFFFFu - seq);
+    atomicMax(&keys[idx], key);
+  }
+}
+
+struct GeomSmem {
+  float x[768], y[768], z[768];  // screen-space distinct vertices of the chunk (NaN x = "take the literal path")
+  uint32_t idx[PRC_GEOM_THREADS];  // per triangle with queued candidates: its three local vertex indices
+  uint32_t box[PRC_GEOM_THREADS];  // x0 | y0 << 16 of its pixel box
+  unsigned short q[PRC_QCAP];      // candidate = triangle slot | dx << 8 | dy << 12
+  unsigned int qn, qv;             // reserved / valid entries
+};
+
+// phase 2 for one triangle
+template <bool E, bool SHADOW>
+__device__ __forceinline__ void geom_classify(const DevScene& S, const DevFrame& F, GeomSmem& sm, const uint32_t li, const unsigned int tri,
+                                              const float* __restrict__ trans_base, const int trans_stride,
+                                              unsigned long long* keys, float* smap, LargeRec* large, unsigned int large_cap, unsigned int* clipq,
+                                              unsigned int clip_cap, Counters* cnt, const DevFrame* Fg, uint32_t target, const int vr0, const int vr1) {
+  const uint32_t i0 = li & 1023u, i1 = (li >> 10) & 1023u, i2 = (li >> 20) & 1023u;
+  const float p1x = sm.x[i0], p1y = sm.y[i0], p1z = sm.z[i0];
+  const float p2x = sm.x[i1], p2y = sm.y[i1], p2z = sm.z[i1];
+  const float p3x = sm.x[i2], p3y = sm.y[i2], p3z = sm.z[i2];
+  const float mag = fabsf(p1x) + fabsf(p1y) + fabsf(p1z) + fabsf(p2x) + fabsf(p2y) + fabsf(p2z) + fabsf(p3x) + fabsf(p3y) + fabsf(p3z);
+  if (!(mag < 1e30f)) {
+    // non-standard viewport matrix or NaN / Inf / zero z,w somewhere: the literal reference sequence from the soup
+    const uint32_t obj = __ldg(S.meta + tri) & 0x00FFFFFFu;
+    geom_generic<E, SHADOW>(Fg, trans_base + (size_t)obj * trans_stride, S.pos, tri, keys, smap, large, large_cap, target, clipq, clip_cap, cnt, vr0, vr1);
+    return;
+  }
+  // cullBackFace (render/cull.go:26-28): FMA(e1.x, e2.y, -(e1.y*e2.x)) < 0, the same expression as Barycoord's Sabc
+  const float Sabc = cross2z<E>(p2x - p1x, p2y - p1y, p3x - p1x, p3y - p1y);
+  if (Sabc < 0.0f) return;
+  // finite coordinates: Go's NaN-propagating Min/Max reduce to plain min/max (the sign of a zero is irrelevant below)
+  const float mnx = fminf(fminf(p1x, p2x), p3x), mxx = fmaxf(fmaxf(p1x, p2x), p3x);
+  const float mny = fminf(fminf(p1y, p2y), p3y), mxy = fmaxf(fmaxf(p1y, p2y), p3y);
+  const float mnz = fminf(fminf(p1z, p2z), p3z), mxz = fmaxf(fmaxf(p1z, p2z), p3z);
+  const float Wf = (float)F.W, Hf = (float)F.H;
+  // AABB.Intersect (box.go:32-41): max(lo) <= min(hi) per axis; the Z test compares against Max.Y = H (the Z quirk)
+  if (!(mxx >= 0.0f && mnx <= Wf && mxy >= 0.0f && mny <= Hf && mxz >= -1.0f && mnz <= Hf)) return;
+  if (!SHADOW) {
+    // AABB.Contains (box.go:61-75) is monotone per coordinate, so testing the extremes tests all three vertices
+    const bool in = less_eq(0.0f, mnx) && less_eq(0.0f, mny) && less_eq(-1.0f, mnz) && less_eq(mxx, Wf) && less_eq(mxy, Hf) && less_eq(mxz, 1.0f);
+    if (!in) {
+      unsigned int slot = warp_push(&cnt->n_clip);
+      if (slot < clip_cap) clipq[slot] = tri;
+      else atomicExch(&cnt->large_overflow, 1u);
+      return;
+    }
+  }
+  const int r0 = SHADOW ? vr0 : F.rr0, r1 = SHADOW ? vr1 : F.rr1;
+  const uint32_t seq = tri * 8u;
+  if (!SHADOW && r0 > 0) raster_pixel00<E>(V4{p1x, p1y, p1z, 1.0f}, V4{p2x, p2y, p2z, 1.0f}, V4{p3x, p3y, p3z, 1.0f}, seq, keys, cnt);
+  int x0, x1, y0, y1;
+  if (prune_ok(mnx, mny, mxx, mxy, Sabc)) {
+    // exact-safe shrink of the AABB+-1 loop (prc_prune.h). The pruned box [ceil(min-.5-M), floor(max-.5+M)] always lies
+    // inside the reference's int(Round(min)-1) .. int(Round(max)+1), so the latter need not be computed here.
+    x0 = max(0, prune_first(mnx)); x1 = min(F.W - 1, prune_last(mxx));
+    y0 = max(r0, prune_first(mny)); y1 = min(r1 - 1, prune_last(mxy));
+  } else {
+    // pixel box int(Round(min)-1) .. int(Round(max)+1) clamped to the buffer (raster.go:473-485); clamping in float first
+    x0 = (int)fmaxf(roundf(mnx) - 1.0f, 0.0f); x1 = (int)fminf(roundf(mxx) + 1.0f, Wf - 1.0f);
+    y0 = (int)fmaxf(roundf(mny) - 1.0f, (float)r0); y1 = (int)fminf(roundf(mxy) + 1.0f, (float)(r1 - 1));
+  }
+  if (x0 > x1 || y0 > y1) return;
+  const int bw = x1 - x0 + 1, area = bw * (y1 - y0 + 1);
+  if (area > PRC_SMALL_MAX_PIXELS) {
+    unsigned int slot = warp_push(&cnt->n_large);
+    if (slot >= large_cap) { atomicExch(&cnt->large_overflow, 1u); return; }
+    LargeRec lr;
+    lr.x1 = p1x; lr.y1 = p1y; lr.z1 = p1z; lr.x2 = p2x; lr.y2 = p2y; lr.z2 = p2z; lr.x3 = p3x; lr.y3 = p3y; lr.z3 = p3z;
+    lr.seq = seq; lr.bx0 = (short)x0; lr.by0 = (short)y0; lr.bx1 = (short)x1; lr.by1 = (short)y1; lr.target = target;
+    large[slot] = lr;
+    return;
+  }
+  // candidate pixels of the box (render/raster.go:481-499 / render/shadow.go:191-215) -> CTA queue
+  const unsigned int base = atomicAdd(&sm.qn, (unsigned int)area);
+  if (base + area <= PRC_QCAP) {
+    atomicMax(&sm.qv, base + area);
+    sm.idx[threadIdx.x] = li;
+    sm.box[threadIdx.x] = (uint32_t)x0 | ((uint32_t)y0 << 16);
+    int dx = 0, dy = 0;
+    for (int j = 0; j < area; j++) {
+      sm.q[base + j] = (unsigned short)(threadIdx.x | (dx << 8) | (dy << 12));
+      if (++dx == bw) { dx = 0; dy++; }
+    }
+  } else {
+    // queue full (many multi-pixel triangles in one chunk): this triangle's pixels in-thread
+    for (int y = y0; y <= y1; y++)
+      for (int x = x0; x <= x1; x++) small_pixel<E, SHADOW>(p1x, p1y, p1z, p2x, p2y, p2z, p3x, p3y, p3z, x, y, seq, F.W, keys, smap, cnt);
+  }
+}
+
+template <bool E, bool SHADOW>
+__global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_raster(DevScene S, DevFrame F, GeomViews V,
+                                                                     unsigned long long* keys, LargeRec* large, unsigned int large_cap,
+                                                                     unsigned int* clipq, unsigned int clip_cap, Counters* cnt, const DevFrame* Fg) {
+  __shared__ GeomSmem sm;
+  const unsigned long long tri64 = (unsigned long long)blockIdx.x * PRC_GEOM_THREADS + threadIdx.x;
+  const unsigned int tri = (unsigned int)tri64;
+  const uint32_t li = tri64 < S.n_tris ? __ldg(S.lidx + tri) : 0xFFFFFFFFu;
+  const uint32_t voff = __ldg(S.cvoff + blockIdx.x), nv = __ldg(S.cvoff + blockIdx.x + 1) - voff;
+  const int n_views = SHADOW ? V.n : 1;
+#pragma unroll 1
+  for (int v = 0; v < n_views; v++) {
+    // chunk culling (k_chunk_cull): no triangle of this chunk can touch the view's rows / screen
+    if (V.vis[v] != nullptr && V.vis[v][blockIdx.x] == 0) continue;  // uniform over the CTA
+    const float* trans_base = SHADOW ? V.trans[v] : reinterpret_cast<const float*>(F.xf);
+    const int trans_stride = SHADOW ? 16 : (int)(sizeof(prc_object_xf) / sizeof(float));
+    const bool affine = SHADOW && ((V.affine >> v) & 1);
+    if (threadIdx.x == 0) { sm.qn = 0; sm.qv = 0; }
+    // ---- phase 1: distinct vertices -> screen space
+    for (uint32_t k = threadIdx.x; k < nv; k += PRC_GEOM_THREADS) {
+      const float4 q = __ldg(S.cverts + voff + k);
+      const float* trans = trans_base + (size_t)__float_as_uint(q.w) * trans_stride;
+      V4 c, p{0.0f, 0.0f, 0.0f, 1.0f};
+      // affine: last row of trans is exactly (0,0,0,1) (orthographic light camera x affine model): w = 0*x+0*y+0*z+1*1 = 1
+      // for finite x,y,z; non-finite coordinates make x/y/z non-finite too and are caught by the finite test in phase 2
+      if (affine) c = mulv3(trans, q.x, q.y, q.z);
+      else c = mulv(trans, V4{q.x, q.y, q.z, 1.0f});
+      if (!(F.vp_std && viewport_pos_std<E>(F.viewport, c, p))) p.x = __int_as_float(0x7fc00000);
+      sm.x[k] = p.x; sm.y[k] = p.y; sm.z[k] = p.z;
+    }
+    __syncthreads();
+    // ---- phase 2: one thread per triangle
+    if (li != 0xFFFFFFFFu)
+      geom_classify<E, SHADOW>(S, F, sm, li, tri, trans_base, trans_stride, keys, SHADOW ? V.smap[v] : nullptr, large, large_cap, clipq, clip_cap, cnt, Fg,
+                               SHADOW ? V.target[v] : 0u, SHADOW ? V.r0[v] : 0, SHADOW ? V.r1[v] : 0);
+    __syncthreads();
+    // ---- phase 3: one thread per candidate pixel
+    const unsigned int nq = sm.qv;
+    for (unsigned int c = threadIdx.x; c < nq; c += PRC_GEOM_THREADS) {
+      const uint32_t e = sm.q[c], t = e & 255u;
+      const uint32_t ti = sm.idx[t], box = sm.box[t];
+      const uint32_t i0 = ti & 1023u, i1 = (ti >> 10) & 1023u, i2 = (ti >> 20) & 1023u;
+      small_pixel<E, SHADOW>(sm.x[i0], sm.y[i0], sm.z[i0], sm.x[i1], sm.y[i1], sm.z[i1], sm.x[i2], sm.y[i2], sm.z[i2],
+                             (int)(box & 0xFFFFu) + (int)((e >> 8) & 15u), (int)(box >> 16) + (int)(e >> 12),
+                             (blockIdx.x * PRC_GEOM_THREADS + t) * 8u, F.W, keys, SHADOW ? V.smap[v] : nullptr, cnt);
+    }
+    __syncthreads();
   }
 }
 
@@ -1240,6 +1436,75 @@ __global__ void k_chunk_cull(const ChunkBox* __restrict__ boxes, uint32_t n_chun
 // ---------------------------------------------------------------------------------------------
 // upload-time kernels
 // ---------------------------------------------------------------------------------------------
+// Chunk-local vertex sharing: the distinct (position bits, object) pairs among the 768 vertices of a 256-triangle
+// chunk, numbered in order of first appearance (deterministic: a group's representative is its smallest vertex
+// number). Pass 1 (cverts == nullptr) only counts; the host scans the counts; pass 2 writes vertices + indices.
+__global__ void __launch_bounds__(256) k_chunk_dedupe(const float* __restrict__ pos, const uint32_t* __restrict__ meta, uint64_t n,
+                                                      const uint32_t* __restrict__ cvoff, uint32_t* nv_out, float4* cverts, uint32_t* lidx) {
+  __shared__ uint32_t kx[768], ky[768], kz[768], ko[768];
+  __shared__ int slot[1024];
+  __shared__ unsigned short num[768];
+  __shared__ uint32_t wsum[8];
+  const uint64_t tri = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  const bool have = tri < n;
+  const uint32_t m = have ? meta[tri] : 0x80000000u;
+  const bool valid = !(m & 0x80000000u);
+  for (int i = threadIdx.x; i < 1024; i += 256) slot[i] = 0x7fffffff;
+  for (int k = 0; k < 3; k++) {
+    const int i = threadIdx.x * 3 + k;
+    kx[i] = have ? __float_as_uint(pos[tri * 9 + k * 3 + 0]) : 0u;
+    ky[i] = have ? __float_as_uint(pos[tri * 9 + k * 3 + 1]) : 0u;
+    kz[i] = have ? __float_as_uint(pos[tri * 9 + k * 3 + 2]) : 0u;
+    ko[i] = m & 0x00FFFFFFu;
+  }
+  __syncthreads();
+  int hs[3];
+  for (int k = 0; k < 3; k++) {
+    const int i = threadIdx.x * 3 + k;
+    hs[k] = -1;
+    if (!valid) continue;
+    uint32_t h = (kx[i] * 0x9E3779B1u) ^ (ky[i] * 0x85EBCA77u) ^ (kz[i] * 0xC2B2AE3Du) ^ (ko[i] * 0x27D4EB2Fu);
+    h = (h ^ (h >> 15)) * 0x2C1B3C6Du;
+    h = (h >> 22) & 1023u;
+    for (;;) {
+      const int old = atomicCAS(&slot[h], 0x7fffffff, i);
+      if (old == 0x7fffffff) break;  // claimed an empty slot for this key
+      if (kx[old] == kx[i] && ky[old] == ky[i] && kz[old] == kz[i] && ko[old] == ko[i]) { atomicMin(&slot[h], i); break; }
+      h = (h + 1) & 1023u;  // 768 keys at most in 1024 slots: the probe always terminates
+    }
+    hs[k] = (int)h;
+  }
+  __syncthreads();
+  int rep[3], cnt = 0;
+  for (int k = 0; k < 3; k++) {
+    rep[k] = hs[k] >= 0 ? slot[hs[k]] : -1;
+    if (rep[k] == (int)threadIdx.x * 3 + k) cnt++;
+  }
+  // exclusive scan of cnt over the CTA
+  uint32_t inc = cnt;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if ((threadIdx.x & 31) >= o) inc += t;
+  }
+  if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+  __syncthreads();
+  uint32_t base = inc - cnt, total = 0;
+  for (int w = 0; w < 8; w++) { if (w < (int)(threadIdx.x >> 5)) base += wsum[w]; total += wsum[w]; }
+  for (int k = 0; k < 3; k++)
+    if (rep[k] == (int)threadIdx.x * 3 + k) num[rep[k]] = (unsigned short)base++;
+  __syncthreads();
+  if (cverts == nullptr) {
+    if (threadIdx.x == 0) nv_out[blockIdx.x] = total;
+    return;
+  }
+  const uint32_t off = cvoff[blockIdx.x];
+  for (int k = 0; k < 3; k++) {
+    const int i = threadIdx.x * 3 + k;
+    if (rep[k] == i) cverts[off + num[i]] = make_float4(__uint_as_float(kx[i]), __uint_as_float(ky[i]), __uint_as_float(kz[i]), __uint_as_float(ko[i]));
+  }
+  if (have) lidx[tri] = valid ? ((uint32_t)num[rep[0]] | ((uint32_t)num[rep[1]] << 10) | ((uint32_t)num[rep[2]] << 20)) : 0xFFFFFFFFu;
+}
+
 // Triangle.IsValid (geometry/primitive/triangle.go:63-80); always evaluated with the exact FMA.
 __global__ void k_validate(const float* __restrict__ pos, const uint64_t* __restrict__ obj_start, uint32_t n_obj, uint64_t n, uint32_t* meta,
                            unsigned long long* n_valid) {

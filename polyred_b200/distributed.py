@@ -41,6 +41,7 @@ class DistributedFrame:
         self.units = partition.shadow_units(self.h, world, self.cast)
         self.stream = torch.cuda.ExternalStream(self.be.stream(), device=self.device)
         self._views = {}
+        self._host = self._host_np = None
         import os
         self.overlap = os.environ.get("PRC_MGPU_OVERLAP", "1") != "0"
 
@@ -54,7 +55,8 @@ class DistributedFrame:
             self._views[key] = self.torch.as_tensor(_cai(ptr, nbytes), device=self.device)
         return self._views[key]
 
-    def render(self, fd, host_out: np.ndarray | None = None):
+    def render(self, fd, host_out: bool = False):
+        """Render one frame over all ranks. host_out=True: rank 0 returns the (H, W, 4) u8 image in page-locked host memory."""
         import torch.distributed as dist
         torch, be, w, h = self.torch, self.be, self.w, self.h
         with torch.cuda.stream(self.stream):  # NCCL orders itself after / before the library's stream
@@ -86,6 +88,13 @@ class DistributedFrame:
             full = self._view(ptr, cb * self.world)
             # one in-place all-gather assembles the frame (every rank, rank 0 included, ends up with the image)
             dist.all_gather_into_tensor(full, full[self.rank * cb:(self.rank + 1) * cb])
+            if host_out and self.rank == 0:
+                # page-locked staging owned by this object, returned as a numpy view (no extra host memcpy)
+                if self._host is None or self._host.numel() != nbytes:
+                    self._host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+                    self._host_np = self._host.numpy().reshape(h, w, 4)
+                self._host.copy_(full[:nbytes], non_blocking=True)
+                self.stream.synchronize()
+                return self._host_np
             self.stream.synchronize()
-            if host_out is not None and self.rank == 0:
-                host_out.reshape(-1)[:] = full[:nbytes].cpu().numpy()
+            return None

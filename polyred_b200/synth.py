@@ -34,6 +34,12 @@ def checker_texture(size=256, seed=2, tint=(255, 255, 255)):
     return material.Texture(img, use_mipmap=True)
 
 
+def quads(t1, t2):
+    """A quad mesh as a triangle list: the two triangles (V1,V2,V3), (V1,V3,V4) of each quad are consecutive, the
+    order Quad.Triangles emits them in (geometry/primitive/quad.go:55-63)."""
+    return np.stack([t1, t2], axis=1).reshape((-1,) + t1.shape[1:]).astype(np.float32)
+
+
 def sphere_mesh(stacks=50, slices=50, seed=1, bump=0.15):
     """Closed lat-long mesh, 2*stacks*slices triangles (pole triangles are degenerate and are
     rejected by Triangle.IsValid, as in any lat-long .obj). Radius displaced by smooth noise."""
@@ -60,9 +66,9 @@ def sphere_mesh(stacks=50, slices=50, seed=1, bump=0.15):
         return A[ii + di, jj + dj]
 
     # counter-clockwise seen from outside
-    pos = np.concatenate([tri(at(P, 0, 0), at(P, 0, 1), at(P, 1, 1)), tri(at(P, 0, 0), at(P, 1, 1), at(P, 1, 0))]).astype(np.float32)
-    nor = np.concatenate([tri(at(N, 0, 0), at(N, 0, 1), at(N, 1, 1)), tri(at(N, 0, 0), at(N, 1, 1), at(N, 1, 0))]).astype(np.float32)
-    uv = np.concatenate([tri(at(UV, 0, 0), at(UV, 0, 1), at(UV, 1, 1)), tri(at(UV, 0, 0), at(UV, 1, 1), at(UV, 1, 0))]).astype(np.float32)
+    pos = quads(tri(at(P, 0, 0), at(P, 0, 1), at(P, 1, 1)), tri(at(P, 0, 0), at(P, 1, 1), at(P, 1, 0)))
+    nor = quads(tri(at(N, 0, 0), at(N, 0, 1), at(N, 1, 1)), tri(at(N, 0, 0), at(N, 1, 1), at(N, 1, 0)))
+    uv = quads(tri(at(UV, 0, 0), at(UV, 0, 1), at(UV, 1, 1)), tri(at(UV, 0, 0), at(UV, 1, 1), at(UV, 1, 0)))
     return pos, nor, uv
 
 
@@ -89,9 +95,9 @@ def ground_mesh(cells=1000, half=1.0, seed=3, amp=0.02, uv_tiles=1.0):
         return np.stack([a0, b0, c0], axis=1)
 
     # counter-clockwise seen from +y
-    pos = np.concatenate([tri(at(P, 0, 0), at(P, 0, 1), at(P, 1, 1)), tri(at(P, 0, 0), at(P, 1, 1), at(P, 1, 0))]).astype(np.float32)
-    nor = np.concatenate([tri(at(N, 0, 0), at(N, 0, 1), at(N, 1, 1)), tri(at(N, 0, 0), at(N, 1, 1), at(N, 1, 0))]).astype(np.float32)
-    uv = np.concatenate([tri(at(UV, 0, 0), at(UV, 0, 1), at(UV, 1, 1)), tri(at(UV, 0, 0), at(UV, 1, 1), at(UV, 1, 0))]).astype(np.float32)
+    pos = quads(tri(at(P, 0, 0), at(P, 0, 1), at(P, 1, 1)), tri(at(P, 0, 0), at(P, 1, 1), at(P, 1, 0)))
+    nor = quads(tri(at(N, 0, 0), at(N, 0, 1), at(N, 1, 1)), tri(at(N, 0, 0), at(N, 1, 1), at(N, 1, 0)))
+    uv = quads(tri(at(UV, 0, 0), at(UV, 0, 1), at(UV, 1, 1)), tri(at(UV, 0, 0), at(UV, 1, 1), at(UV, 1, 0)))
     return pos, nor, uv
 
 

@@ -27,9 +27,8 @@ def main():
         r = render.NewRenderer(*opts, render.CUDA(local))
         r._ensure_uploaded()
         df = DistributedFrame(r, rank, world, local)
-        out = np.zeros((h, w, 4), np.uint8)
         for _ in range(2):
-            df.render(df.prepare(r.frame_desc(no_readback=True)), out)
+            out = df.render(df.prepare(r.frame_desc(no_readback=True)), True)
         if rank == 0:
             ref = render.NewRenderer(*opts, render.CUDA(local)).Render()
             nd = int((np.abs(out.astype(int) - ref.astype(int)).max(axis=2) > 0).sum())
