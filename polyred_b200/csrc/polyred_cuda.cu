@@ -239,7 +239,7 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
   if (!fr || fr->abi_version != PRC_ABI_VERSION) { ctx->err = "prc_frame: bad abi_version"; return PRC_ERR_INVALID; }
   if (!ctx->has_scene) { ctx->err = "no scene uploaded"; return PRC_ERR_NO_SCENE; }
   if (fr->n_objects != ctx->n_objects) { ctx->err = "prc_frame.n_objects differs from the uploaded scene"; return PRC_ERR_INVALID; }
-  if (fr->width == 0 || fr->height == 0 || fr->width > 32760 || fr->height > 32760) { ctx->err = "bad frame size"; return PRC_ERR_INVALID; }
+  if (fr->width == 0 || fr->height == 0 || fr->width > 16384 || fr->height > 16384) { ctx->err = "bad frame size"; return PRC_ERR_INVALID; }
   if (fr->row1 > fr->height || fr->row0 >= fr->row1) { ctx->err = "bad row range"; return PRC_ERR_INVALID; }
   for (uint32_t i = 0; i < fr->n_lights; i++) {
     if (fr->lights[i].kind > PRC_LIGHT_DIRECTIONAL) { ctx->err = "unsupported light kind"; return PRC_ERR_UNSUPPORTED; }
@@ -326,6 +326,14 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
     memcpy(d.proj, l.proj, 64);
     d.pm_view = plain_mask(l.view);
     d.pm_proj = plain_mask(l.proj);
+    {
+      // rigid view [R t; 0 0 0 1] and perspective projection [a 0 0 0; 0 b 0 0; 0 0 c d; 0 0 -1 0] (math.Mat4 LookAt / Perspective)
+      const float *v = l.view, *q = l.proj;
+      bool ok = v[12] == 0 && v[13] == 0 && v[14] == 0 && v[15] == 1 && q[1] == 0 && q[2] == 0 && q[3] == 0 && q[4] == 0 && q[6] == 0 && q[7] == 0 &&
+                q[8] == 0 && q[9] == 0 && q[12] == 0 && q[13] == 0 && q[14] == -1 && q[15] == 0;
+      for (int k = 0; k < 16; k++) ok = ok && std::isfinite(v[k]) && std::isfinite(q[k]);
+      d.persp_cam = (ok && !getenv("PRC_NO_PERSP_CAM")) ? 1u : 0u;
+    }
     d.shadow_map = ctx->shadow_ptr[i];
     if (d.cast_shadow && !resident) {
       UPLOAD(ctx->d_shadow_trans[i], l.shadow_trans, (size_t)fr->n_objects * 64);

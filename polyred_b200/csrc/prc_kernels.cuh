@@ -13,6 +13,7 @@
 #include "../../include/polyred_cuda.h"
 #include "prc_math.cuh"
 #include "prc_prune.h"
+#include "prc_pow.h"
 
 namespace prc {
 
@@ -49,6 +50,7 @@ struct DevLight {
   uint32_t color;
   float view[16], proj[16];
   uint32_t pm_view, pm_proj;  // plain masks (see apply4m)
+  uint32_t persp_cam;         // view = [R t; 0 0 0 1], proj = [a 0 0 0; 0 b 0 0; 0 0 c d; 0 0 -1 0], all finite
   float* shadow_map;  // W*H floats (persistent)
 };
 
@@ -568,33 +570,53 @@ __device__ __forceinline__ void small_pixel(const float p1x, const float p1y, co
 }
 
 struct GeomSmem {
-  float x[768], y[768], z[768];  // screen-space distinct vertices of the chunk (NaN x = "take the literal path")
+  float x[2][768], y[2][768], z[2][768];  // screen-space distinct vertices of the chunk, double-buffered over views (NaN x = "take the literal path")
   uint32_t idx[PRC_GEOM_THREADS];  // per triangle with queued candidates: its three local vertex indices
-  uint32_t box[PRC_GEOM_THREADS];  // x0 | y0 << 16 of its pixel box
-  unsigned short q[PRC_QCAP];      // candidate = triangle slot | dx << 8 | dy << 12
-  unsigned int qn, qv;             // reserved / valid entries
+  uint32_t box[PRC_GEOM_THREADS];  // x0 | y0 << 14 | (box width - 1) << 28 of its pixel box
+  unsigned short q[PRC_QCAP];      // candidate = triangle slot | pixel number within the box << 8
+  unsigned int qn[2], qv[2];       // reserved / valid entries, alternating between consecutive views
 };
+__constant__ unsigned short c_recip256[17] = {0, 256, 128, 86, 64, 52, 43, 37, 32, 29, 26, 24, 22, 20, 19, 18, 16};  // ceil(256 / bw): (j * r) >> 8 == j / bw for j < 16
+
+// phase 1: the chunk's distinct vertices -> screen space of one view
+template <bool E, bool SHADOW>
+__device__ __forceinline__ void geom_vertices(const DevScene& S, const DevFrame& F, float* __restrict__ sx, float* __restrict__ sy, float* __restrict__ sz,
+                                              const uint32_t voff, const uint32_t nv, const float* __restrict__ trans_base, const int trans_stride, const bool affine) {
+  for (uint32_t k = threadIdx.x; k < nv; k += PRC_GEOM_THREADS) {
+    const float4 q = __ldg(S.cverts + voff + k);
+    const float* trans = trans_base + (size_t)__float_as_uint(q.w) * trans_stride;
+    V4 c, p{0.0f, 0.0f, 0.0f, 1.0f};
+    // affine: last row of trans is exactly (0,0,0,1) (orthographic light camera x affine model): w = 0*x+0*y+0*z+1*1 = 1
+    // for finite x,y,z; non-finite coordinates make x/y/z non-finite too and are caught by the magnitude test below
+    if (affine) c = mulv3(trans, q.x, q.y, q.z);
+    else c = mulv(trans, V4{q.x, q.y, q.z, 1.0f});
+    // literal path (geom_generic, per triangle) for: a non-standard viewport matrix, zero z or w, NaN / Inf, or
+    // coordinates so large that differences of two of them could overflow
+    if (!(F.vp_std && viewport_pos_std<E>(F.viewport, c, p)) || !(fabsf(p.x) + fabsf(p.y) + fabsf(p.z) < 3e29f)) p.x = __int_as_float(0x7fc00000);
+    sx[k] = p.x; sy[k] = p.y; sz[k] = p.z;
+  }
+}
 
 // phase 2 for one triangle
 template <bool E, bool SHADOW>
-__device__ __forceinline__ void geom_classify(const DevScene& S, const DevFrame& F, GeomSmem& sm, const uint32_t li, const unsigned int tri,
+__device__ __forceinline__ void geom_classify(const DevScene& S, const DevFrame& F, GeomSmem& sm, const int buf, const int qsel, const uint32_t li, const unsigned int tri,
                                               const float* __restrict__ trans_base, const int trans_stride,
                                               unsigned long long* keys, float* smap, LargeRec* large, unsigned int large_cap, unsigned int* clipq,
                                               unsigned int clip_cap, Counters* cnt, const DevFrame* Fg, uint32_t target, const int vr0, const int vr1) {
   const uint32_t i0 = li & 1023u, i1 = (li >> 10) & 1023u, i2 = (li >> 20) & 1023u;
-  const float p1x = sm.x[i0], p1y = sm.y[i0], p1z = sm.z[i0];
-  const float p2x = sm.x[i1], p2y = sm.y[i1], p2z = sm.z[i1];
-  const float p3x = sm.x[i2], p3y = sm.y[i2], p3z = sm.z[i2];
-  const float mag = fabsf(p1x) + fabsf(p1y) + fabsf(p1z) + fabsf(p2x) + fabsf(p2y) + fabsf(p2z) + fabsf(p3x) + fabsf(p3y) + fabsf(p3z);
-  if (!(mag < 1e30f)) {
-    // non-standard viewport matrix or NaN / Inf / zero z,w somewhere: the literal reference sequence from the soup
+  const float* sx = sm.x[buf]; const float* sy = sm.y[buf]; const float* sz = sm.z[buf];
+  const float p1x = sx[i0], p2x = sx[i1], p3x = sx[i2];
+  const float fin = p1x + p2x + p3x;  // NaN iff a vertex was flagged in phase 1 (finite coordinates are < 3e29: no overflow)
+  if (fin != fin) {
     const uint32_t obj = __ldg(S.meta + tri) & 0x00FFFFFFu;
     geom_generic<E, SHADOW>(Fg, trans_base + (size_t)obj * trans_stride, S.pos, tri, keys, smap, large, large_cap, target, clipq, clip_cap, cnt, vr0, vr1);
     return;
   }
+  const float p1y = sy[i0], p2y = sy[i1], p3y = sy[i2];
   // cullBackFace (render/cull.go:26-28): FMA(e1.x, e2.y, -(e1.y*e2.x)) < 0, the same expression as Barycoord's Sabc
   const float Sabc = cross2z<E>(p2x - p1x, p2y - p1y, p3x - p1x, p3y - p1y);
   if (Sabc < 0.0f) return;
+  const float p1z = sz[i0], p2z = sz[i1], p3z = sz[i2];
   // finite coordinates: Go's NaN-propagating Min/Max reduce to plain min/max (the sign of a zero is irrelevant below)
   const float mnx = fminf(fminf(p1x, p2x), p3x), mxx = fmaxf(fmaxf(p1x, p2x), p3x);
   const float mny = fminf(fminf(p1y, p2y), p3y), mxy = fmaxf(fmaxf(p1y, p2y), p3y);
@@ -638,16 +660,14 @@ __device__ __forceinline__ void geom_classify(const DevScene& S, const DevFrame&
     return;
   }
   // candidate pixels of the box (render/raster.go:481-499 / render/shadow.go:191-215) -> CTA queue
-  const unsigned int base = atomicAdd(&sm.qn, (unsigned int)area);
+  const unsigned int base = atomicAdd(&sm.qn[qsel], (unsigned int)area);
   if (base + area <= PRC_QCAP) {
-    atomicMax(&sm.qv, base + area);
+    atomicMax(&sm.qv[qsel], base + area);
     sm.idx[threadIdx.x] = li;
-    sm.box[threadIdx.x] = (uint32_t)x0 | ((uint32_t)y0 << 16);
-    int dx = 0, dy = 0;
-    for (int j = 0; j < area; j++) {
-      sm.q[base + j] = (unsigned short)(threadIdx.x | (dx << 8) | (dy << 12));
-      if (++dx == bw) { dx = 0; dy++; }
-    }
+    sm.box[threadIdx.x] = (uint32_t)x0 | ((uint32_t)y0 << 14) | ((uint32_t)(bw - 1) << 28);
+    unsigned short e = (unsigned short)threadIdx.x;
+    unsigned short* q = sm.q + base;
+    for (int j = 0; j < area; j++, e += 256) q[j] = e;
   } else {
     // queue full (many multi-pixel triangles in one chunk): this triangle's pixels in-thread
     for (int y = y0; y <= y1; y++)
@@ -655,8 +675,11 @@ __device__ __forceinline__ void geom_classify(const DevScene& S, const DevFrame&
   }
 }
 
+// __grid_constant__: the per-view arrays are indexed with a run-time view number; without it the whole parameter
+// struct is copied to local memory by every thread (ncu: 11 % of the kernel's instructions, STL at entry).
 template <bool E, bool SHADOW>
-__global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_raster(DevScene S, DevFrame F, GeomViews V,
+__global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_raster(const __grid_constant__ DevScene S, const __grid_constant__ DevFrame F,
+                                                                     const __grid_constant__ GeomViews V,
                                                                      unsigned long long* keys, LargeRec* large, unsigned int large_cap,
                                                                      unsigned int* clipq, unsigned int clip_cap, Counters* cnt, const DevFrame* Fg) {
   __shared__ GeomSmem sm;
@@ -665,43 +688,49 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_
   const uint32_t li = tri64 < S.n_tris ? __ldg(S.lidx + tri) : 0xFFFFFFFFu;
   const uint32_t voff = __ldg(S.cvoff + blockIdx.x), nv = __ldg(S.cvoff + blockIdx.x + 1) - voff;
   const int n_views = SHADOW ? V.n : 1;
+  const int trans_stride = SHADOW ? 16 : (int)(sizeof(prc_object_xf) / sizeof(float));
+  // views this chunk can touch (k_chunk_cull; uniform over the CTA)
+  uint32_t todo = 0;
+  for (int v = 0; v < n_views; v++)
+    if (V.vis[v] == nullptr || V.vis[v][blockIdx.x] != 0) todo |= 1u << v;
+  if (!todo) return;
+  if (threadIdx.x == 0) { sm.qn[0] = sm.qn[1] = 0; sm.qv[0] = sm.qv[1] = 0; }
+  int v = __ffs(todo) - 1, buf = 0;
+  todo &= todo - 1;
+  geom_vertices<E, SHADOW>(S, F, sm.x[0], sm.y[0], sm.z[0], voff, nv, SHADOW ? V.trans[v] : reinterpret_cast<const float*>(F.xf), trans_stride,
+                           SHADOW && ((V.affine >> v) & 1));
+  __syncthreads();
 #pragma unroll 1
-  for (int v = 0; v < n_views; v++) {
-    // chunk culling (k_chunk_cull): no triangle of this chunk can touch the view's rows / screen
-    if (V.vis[v] != nullptr && V.vis[v][blockIdx.x] == 0) continue;  // uniform over the CTA
+  for (;;) {
     const float* trans_base = SHADOW ? V.trans[v] : reinterpret_cast<const float*>(F.xf);
-    const int trans_stride = SHADOW ? 16 : (int)(sizeof(prc_object_xf) / sizeof(float));
-    const bool affine = SHADOW && ((V.affine >> v) & 1);
-    if (threadIdx.x == 0) { sm.qn = 0; sm.qv = 0; }
-    // ---- phase 1: distinct vertices -> screen space
-    for (uint32_t k = threadIdx.x; k < nv; k += PRC_GEOM_THREADS) {
-      const float4 q = __ldg(S.cverts + voff + k);
-      const float* trans = trans_base + (size_t)__float_as_uint(q.w) * trans_stride;
-      V4 c, p{0.0f, 0.0f, 0.0f, 1.0f};
-      // affine: last row of trans is exactly (0,0,0,1) (orthographic light camera x affine model): w = 0*x+0*y+0*z+1*1 = 1
-      // for finite x,y,z; non-finite coordinates make x/y/z non-finite too and are caught by the finite test in phase 2
-      if (affine) c = mulv3(trans, q.x, q.y, q.z);
-      else c = mulv(trans, V4{q.x, q.y, q.z, 1.0f});
-      if (!(F.vp_std && viewport_pos_std<E>(F.viewport, c, p))) p.x = __int_as_float(0x7fc00000);
-      sm.x[k] = p.x; sm.y[k] = p.y; sm.z[k] = p.z;
-    }
-    __syncthreads();
+    float* smap = SHADOW ? V.smap[v] : nullptr;
     // ---- phase 2: one thread per triangle
     if (li != 0xFFFFFFFFu)
-      geom_classify<E, SHADOW>(S, F, sm, li, tri, trans_base, trans_stride, keys, SHADOW ? V.smap[v] : nullptr, large, large_cap, clipq, clip_cap, cnt, Fg,
+      geom_classify<E, SHADOW>(S, F, sm, buf, buf, li, tri, trans_base, trans_stride, keys, smap, large, large_cap, clipq, clip_cap, cnt, Fg,
                                SHADOW ? V.target[v] : 0u, SHADOW ? V.r0[v] : 0, SHADOW ? V.r1[v] : 0);
     __syncthreads();
-    // ---- phase 3: one thread per candidate pixel
-    const unsigned int nq = sm.qv;
-    for (unsigned int c = threadIdx.x; c < nq; c += PRC_GEOM_THREADS) {
-      const uint32_t e = sm.q[c], t = e & 255u;
-      const uint32_t ti = sm.idx[t], box = sm.box[t];
-      const uint32_t i0 = ti & 1023u, i1 = (ti >> 10) & 1023u, i2 = (ti >> 20) & 1023u;
-      small_pixel<E, SHADOW>(sm.x[i0], sm.y[i0], sm.z[i0], sm.x[i1], sm.y[i1], sm.z[i1], sm.x[i2], sm.y[i2], sm.z[i2],
-                             (int)(box & 0xFFFFu) + (int)((e >> 8) & 15u), (int)(box >> 16) + (int)(e >> 12),
-                             (blockIdx.x * PRC_GEOM_THREADS + t) * 8u, F.W, keys, SHADOW ? V.smap[v] : nullptr, cnt);
+    // ---- phase 3 of this view (one thread per candidate pixel) overlapped with phase 1 of the next view (other buffer)
+    const unsigned int nq = sm.qv[buf];
+    const int vn = todo ? __ffs(todo) - 1 : -1;
+    todo &= todo - 1;
+    if (threadIdx.x == 0) { sm.qn[buf ^ 1] = 0; sm.qv[buf ^ 1] = 0; }  // last read before the barrier above
+    if (vn >= 0)
+      geom_vertices<E, SHADOW>(S, F, sm.x[buf ^ 1], sm.y[buf ^ 1], sm.z[buf ^ 1], voff, nv, V.trans[vn], trans_stride, (V.affine >> vn) & 1);
+    {
+      const float* sx = sm.x[buf]; const float* sy = sm.y[buf]; const float* sz = sm.z[buf];
+      for (unsigned int c = threadIdx.x; c < nq; c += PRC_GEOM_THREADS) {
+        const uint32_t e = sm.q[c], t = e & 255u, j = e >> 8;
+        const uint32_t ti = sm.idx[t], box = sm.box[t];
+        const uint32_t i0 = ti & 1023u, i1 = (ti >> 10) & 1023u, i2 = (ti >> 20) & 1023u;
+        const uint32_t bw = (box >> 28) + 1u, dy = (j * c_recip256[bw]) >> 8, dx = j - dy * bw;
+        small_pixel<E, SHADOW>(sx[i0], sy[i0], sz[i0], sx[i1], sy[i1], sz[i1], sx[i2], sy[i2], sz[i2],
+                               (int)((box & 0x3FFFu) + dx), (int)(((box >> 14) & 0x3FFFu) + dy),
+                               (blockIdx.x * PRC_GEOM_THREADS + t) * 8u, F.W, keys, smap, cnt);
+      }
     }
+    if (vn < 0) break;
     __syncthreads();
+    v = vn; buf ^= 1;
   }
 }
 
@@ -1183,7 +1212,10 @@ __device__ __noinline__ double go_pow64(double x, double y) {
   if (ae < -100000) ae = -100000;
   return ldexp(a1, (int)ae);
 }
-__device__ __forceinline__ float go_pow(float x, float y) { return (float)go_pow64((double)x, (double)y); }
+__device__ __forceinline__ float go_pow(float x, float y) {
+  if (pow_int_unit_ok(x, y)) return pow_int_unit(x, y);  // integer shininess, base in (0,1]: bit-identical shortcut (prc_pow.h)
+  return (float)go_pow64((double)x, (double)y);
+}
 
 template <bool E>
 __device__ uint32_t fragment_shader(const DevScene& S, const DevFrame& F, const prc_material& m, const Frag& info) {
@@ -1236,7 +1268,22 @@ template <bool E>
 __device__ bool shading_visibility(const DevFrame& F, const DevLight& l, const V4& world) {
   if (!l.cast_shadow) return true;
   // `world` = (X, Y, Depth, 1).Apply(ViewportToWorld) is the same for every light (hoisted by the caller)
-  V4 sc = pos4(apply4m<E>(apply4m<E>(apply4m<E>(world, l.view, l.pm_view), l.proj, l.pm_proj), F.viewport, F.pm_viewport));
+  V4 sc;
+  if (!E && l.persp_cam && F.vp_std && world.w == 1.0f && fabsf(world.x) + fabsf(world.y) + fabsf(world.z) < 1e30f) {
+    // single-rounding FMA mode only: with the zero / one entries of a rigid view, a perspective projection and the
+    // standard viewport, FMA(0, v, c) = c and FMA(m, v, +-0) = m*v for finite v, so the 48 FMAs of the three Apply calls
+    // collapse to the 21 operations below with the same values (only the sign of an exact zero can differ)
+    const float* a = l.view;
+    const float vx = fma32<false>(a[0], world.x, fma32<false>(a[1], world.y, fma32<false>(a[2], world.z, a[3])));
+    const float vy = fma32<false>(a[4], world.x, fma32<false>(a[5], world.y, fma32<false>(a[6], world.z, a[7])));
+    const float vz = fma32<false>(a[8], world.x, fma32<false>(a[9], world.y, fma32<false>(a[10], world.z, a[11])));
+    const float* q = l.proj;
+    const float px = q[0] * vx, py = q[5] * vy, pz = fma32<false>(q[10], vz, q[11]), pw = -vz;
+    const float* vp = F.viewport;
+    sc = pos4(V4{fma32<false>(vp[0], px, vp[3] * pw), fma32<false>(vp[5], py, vp[7] * pw), pz, pw});
+  } else {
+    sc = pos4(apply4m<E>(apply4m<E>(apply4m<E>(world, l.view, l.pm_view), l.proj, l.pm_proj), F.viewport, F.pm_viewport));
+  }
   if (fabsf(sc.x) < 5e8f && fabsf(sc.y) * (float)F.W < 1.5e9f) {  // 32-bit fast path: int(x) + int(y)*W cannot overflow
     const int idx = __float2int_rz(sc.x) + __float2int_rz(sc.y) * F.W;
     if (idx > 0 && idx < F.W * F.H) {

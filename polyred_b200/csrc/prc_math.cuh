@@ -90,7 +90,8 @@ __device__ __forceinline__ V4 apply4(V4 v, const float* __restrict__ a) {  // :1
 // exactly representable float32 product). The mask is uniform (kernel parameter), so no divergence.
 template <bool E>
 __device__ __forceinline__ float fma32m(bool plain, float m, float v, float c) {
-  if (plain) return m * v + c;
+  // without the exact FMA the fused single-rounding result already equals the plain one for such entries
+  if (E && plain) return m * v + c;
   return fma32<E>(m, v, c);
 }
 template <bool E>

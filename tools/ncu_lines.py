@@ -23,6 +23,7 @@ for b in blocks:
     if want and want not in (b["fn"] or ""):
         continue
     h = b["hdr"]; iI = h.index("Instructions Executed"); iS = h.index("# Samples"); iT = h.index("Thread Instructions Executed")
+    b["rows"] = [r for r in b["rows"] if len(r) > max(iI, iS, iT) and (r[iI] or "0").isdigit()]
     tot = sum(int(r[iI] or 0) for r in b["rows"]); tots = sum(int(r[iS] or 0) for r in b["rows"])
     print(f"=== {b['fn'][:110]}  [{b['file'].split('/')[-1]}]  warp-inst {tot}  samples {tots}")
     rows = sorted(b["rows"], key=lambda r: -int(r[iI] or 0))[:top]
