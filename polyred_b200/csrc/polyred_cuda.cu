@@ -175,6 +175,7 @@ int32_t raster_pass(prc_ctx* ctx, const DevFrame& F, const GeomViews& Vin) {
                                                              (const float*)((const char*)fb.p + offsetof(DevFrame, viewport)), F.W, F.H, r0, r1,
                                                              (!SHADOW && r0 > 0) ? 1 : 0, vis);
       V.vis[v] = vis;
+      V.any_vis = 1;
       ctx->launches++;
     }
   }

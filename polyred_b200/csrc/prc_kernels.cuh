@@ -297,7 +297,7 @@ __device__ __forceinline__ void emit_tri(const V4& p1, const V4& p2, const V4& p
 // ---------------------------------------------------------------------------------------------
 #define PRC_GEOM_THREADS 256
 #ifndef PRC_GEOM_MIN_BLOCKS
-#define PRC_GEOM_MIN_BLOCKS 5  // 48 registers: measured 3 % faster than 4 (64 registers) despite ~60 B of spills
+#define PRC_GEOM_MIN_BLOCKS 8  // 32 registers, full occupancy: measured 1.29 ms/frame vs 1.34 (6 CTAs, 40 regs) and 1.40 (5 CTAs, 48 regs); more resident CTAs hide the phase barriers
 #endif
 #define PRC_REC_STRIDE 19
 struct SmallRec {  // 18 words
@@ -469,6 +469,7 @@ struct GeomViews {
   uint32_t target[8];
   int r0[8], r1[8];  // rows of the shadow map this view rasterises
   const unsigned char* vis[8];  // per view: [n_chunks] 0 = no triangle of this 256-triangle chunk can touch the view's rows / screen
+  int any_vis;                  // some vis[v] is set
 };
 
 template <bool E, bool SHADOW>
@@ -667,7 +668,12 @@ __device__ __forceinline__ void geom_classify(const DevScene& S, const DevFrame&
     sm.box[threadIdx.x] = (uint32_t)x0 | ((uint32_t)y0 << 14) | ((uint32_t)(bw - 1) << 28);
     unsigned short e = (unsigned short)threadIdx.x;
     unsigned short* q = sm.q + base;
-    for (int j = 0; j < area; j++, e += 256) q[j] = e;
+    q[0] = e;  // most survivors cover one or two candidate pixels
+    if (area > 1) {
+      q[1] = (unsigned short)(e + 256);
+      e += 512;
+      for (int j = 2; j < area; j++, e += 256) q[j] = e;
+    }
   } else {
     // queue full (many multi-pixel triangles in one chunk): this triangle's pixels in-thread
     for (int y = y0; y <= y1; y++)
@@ -690,10 +696,13 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_
   const int n_views = SHADOW ? V.n : 1;
   const int trans_stride = SHADOW ? 16 : (int)(sizeof(prc_object_xf) / sizeof(float));
   // views this chunk can touch (k_chunk_cull; uniform over the CTA)
-  uint32_t todo = 0;
-  for (int v = 0; v < n_views; v++)
-    if (V.vis[v] == nullptr || V.vis[v][blockIdx.x] != 0) todo |= 1u << v;
-  if (!todo) return;
+  uint32_t todo = (1u << n_views) - 1u;
+  if (V.any_vis) {
+    todo = 0;
+    for (int v = 0; v < n_views; v++)
+      if (V.vis[v] == nullptr || V.vis[v][blockIdx.x] != 0) todo |= 1u << v;
+    if (!todo) return;
+  }
   if (threadIdx.x == 0) { sm.qn[0] = sm.qn[1] = 0; sm.qv[0] = sm.qv[1] = 0; }
   int v = __ffs(todo) - 1, buf = 0;
   todo &= todo - 1;
@@ -718,7 +727,8 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_
       geom_vertices<E, SHADOW>(S, F, sm.x[buf ^ 1], sm.y[buf ^ 1], sm.z[buf ^ 1], voff, nv, V.trans[vn], trans_stride, (V.affine >> vn) & 1);
     {
       const float* sx = sm.x[buf]; const float* sy = sm.y[buf]; const float* sz = sm.z[buf];
-      for (unsigned int c = threadIdx.x; c < nq; c += PRC_GEOM_THREADS) {
+      // dealt from the LAST warp down: the first warps are the ones busy with the next view's vertices
+      for (unsigned int c = PRC_GEOM_THREADS - 1 - threadIdx.x; c < nq; c += PRC_GEOM_THREADS) {
         const uint32_t e = sm.q[c], t = e & 255u, j = e >> 8;
         const uint32_t ti = sm.idx[t], box = sm.box[t];
         const uint32_t i0 = ti & 1023u, i1 = (ti >> 10) & 1023u, i2 = (ti >> 20) & 1023u;
