@@ -328,12 +328,17 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
     d.pm_view = plain_mask(l.view);
     d.pm_proj = plain_mask(l.proj);
     {
-      // rigid view [R t; 0 0 0 1] and perspective projection [a 0 0 0; 0 b 0 0; 0 0 c d; 0 0 -1 0] (math.Mat4 LookAt / Perspective)
+      // rigid view [R t; 0 0 0 1] with a perspective [a 0 0 0; 0 b 0 0; 0 0 c d; 0 0 -1 0] (1) or an orthographic
+      // [a 0 0 b; 0 c 0 d; 0 0 e f; 0 0 0 1] (2) projection (math.Mat4 LookAt / Perspective / Orthographic; initShadowMaps
+      // fits an orthographic light camera, render/shadow.go:67-86)
       const float *v = l.view, *q = l.proj;
-      bool ok = v[12] == 0 && v[13] == 0 && v[14] == 0 && v[15] == 1 && q[1] == 0 && q[2] == 0 && q[3] == 0 && q[4] == 0 && q[6] == 0 && q[7] == 0 &&
-                q[8] == 0 && q[9] == 0 && q[12] == 0 && q[13] == 0 && q[14] == -1 && q[15] == 0;
-      for (int k = 0; k < 16; k++) ok = ok && std::isfinite(v[k]) && std::isfinite(q[k]);
-      d.persp_cam = (ok && !getenv("PRC_NO_PERSP_CAM")) ? 1u : 0u;
+      bool fin = true;
+      for (int k = 0; k < 16; k++) fin = fin && std::isfinite(v[k]) && std::isfinite(q[k]);
+      const bool rigid = v[12] == 0 && v[13] == 0 && v[14] == 0 && v[15] == 1;
+      const bool persp = q[1] == 0 && q[2] == 0 && q[3] == 0 && q[4] == 0 && q[6] == 0 && q[7] == 0 && q[8] == 0 && q[9] == 0 && q[12] == 0 && q[13] == 0 &&
+                         q[14] == -1 && q[15] == 0;
+      const bool ortho = q[1] == 0 && q[2] == 0 && q[4] == 0 && q[6] == 0 && q[8] == 0 && q[9] == 0 && q[12] == 0 && q[13] == 0 && q[14] == 0 && q[15] == 1;
+      d.persp_cam = (!fin || !rigid || getenv("PRC_NO_PERSP_CAM")) ? 0u : persp ? 1u : ortho ? 2u : 0u;
     }
     d.shadow_map = ctx->shadow_ptr[i];
     if (d.cast_shadow && !resident) {
@@ -377,6 +382,12 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
                 v[14] == 0 && v[15] == 1 && std::isfinite(v[0]) && std::isfinite(v[3]) && std::isfinite(v[5]) && std::isfinite(v[7]) && v[3] != 0 && v[7] != 0)
                    ? 1u : 0u;
     if (getenv("PRC_NO_VPSTD")) F.vp_std = 0;
+    const float *a = F.viewport_inv, *q = F.proj_inv, *r = F.view_inv;
+    bool ok = a[1] == 0 && a[2] == 0 && a[4] == 0 && a[6] == 0 && a[8] == 0 && a[9] == 0 && a[10] == 1 && a[11] == 0 && a[12] == 0 && a[13] == 0 && a[14] == 0 &&
+              a[15] == 1 && q[1] == 0 && q[2] == 0 && q[3] == 0 && q[4] == 0 && q[6] == 0 && q[7] == 0 && q[8] == 0 && q[9] == 0 && q[10] == 0 && q[12] == 0 &&
+              q[13] == 0 && r[12] == 0 && r[13] == 0 && r[14] == 0 && r[15] == 1;
+    for (int k = 0; k < 16; k++) ok = ok && std::isfinite(a[k]) && std::isfinite(q[k]) && std::isfinite(r[k]);
+    F.unproj_std = (ok && !getenv("PRC_NO_UNPROJ_STD")) ? 1u : 0u;
   }
   if (getenv("PRC_NO_PLAIN")) F.pm_viewport = F.pm_viewport_inv = F.pm_proj_inv = F.pm_view_inv = F.pm_vtw = 0;
   memcpy(F.cam, fr->cam_pos, 12);

@@ -50,7 +50,7 @@ struct DevLight {
   uint32_t color;
   float view[16], proj[16];
   uint32_t pm_view, pm_proj;  // plain masks (see apply4m)
-  uint32_t persp_cam;         // view = [R t; 0 0 0 1], proj = [a 0 0 0; 0 b 0 0; 0 0 c d; 0 0 -1 0], all finite
+  uint32_t persp_cam;         // rigid view with 1 = perspective, 2 = orthographic projection, all entries finite (0 = anything else)
   float* shadow_map;  // W*H floats (persistent)
 };
 
@@ -63,6 +63,7 @@ struct DevFrame {
   uint32_t background;
   float viewport[16], viewport_inv[16], proj_inv[16], view_inv[16], vtw[16];
   uint32_t pm_viewport, pm_viewport_inv, pm_proj_inv, pm_view_inv, pm_vtw;  // plain masks (see apply4m)
+  uint32_t unproj_std;  // viewport_inv = [a 0 0 b; 0 c 0 d; 0 0 1 0; 0 0 0 1], proj_inv = [e 0 0 0; 0 f 0 0; 0 0 0 g; 0 0 h i], view_inv = [R t; 0 0 0 1], all finite
   uint32_t vp_std;  // viewport == [a 0 0 b; 0 c 0 d; 0 0 1 0; 0 0 0 1] (math.ViewportMatrix, math/math.go:270-277)
   float cam[3];
   const prc_object_xf* xf;   // per object trans / normal
@@ -962,6 +963,19 @@ struct VtxAttr { V4 pos, nor; float u, v; uint32_t col; };
 
 // E: arithmetic of everything that decides position / depth; EA: arithmetic of the shading-only attributes
 // (normals, world position, face normal, du/dv). PRC_FMA=mixed runs <true, false>.
+// (x, y, z, 1).Apply(ViewportInv).Apply(ProjInv).Apply(ViewInv) for the matrix shapes flagged by DevFrame.unproj_std
+__device__ __forceinline__ V4 unproject_std(const DevFrame& F, const V4& p) {
+  const float *a = F.viewport_inv, *q = F.proj_inv, *r = F.view_inv;
+  const float x1 = __fmaf_rn(a[0], p.x, a[3]), y1 = __fmaf_rn(a[5], p.y, a[7]), z1 = p.z;
+  const float x2 = q[0] * x1, y2 = q[5] * y1, z2 = q[11], w2 = __fmaf_rn(q[14], z1, q[15]);
+  V4 o;
+  o.x = __fmaf_rn(r[0], x2, __fmaf_rn(r[1], y2, __fmaf_rn(r[2], z2, r[3] * w2)));
+  o.y = __fmaf_rn(r[4], x2, __fmaf_rn(r[5], y2, __fmaf_rn(r[6], z2, r[7] * w2)));
+  o.z = __fmaf_rn(r[8], x2, __fmaf_rn(r[9], y2, __fmaf_rn(r[10], z2, r[11] * w2)));
+  o.w = w2;
+  return o;
+}
+
 template <bool E, bool EA>
 __device__ void resolve_fragment(const DevScene& S, const DevFrame& F, uint32_t seq, int x, int y, Frag& f) {
   const uint32_t tri = seq >> 3, sub = seq & 7u;
@@ -1011,9 +1025,18 @@ __device__ void resolve_fragment(const DevScene& S, const DevFrame& F, uint32_t 
     v[0] = c[0]; v[1] = c[1]; v[2] = c[2];
   }
   // un-project without dividing by W (raster.go:467-469)
-  V4 m1 = apply4m<EA>(apply4m<EA>(apply4m<EA>(v[0].pos, F.viewport_inv, F.pm_viewport_inv), F.proj_inv, F.pm_proj_inv), F.view_inv, F.pm_view_inv);
-  V4 m2 = apply4m<EA>(apply4m<EA>(apply4m<EA>(v[1].pos, F.viewport_inv, F.pm_viewport_inv), F.proj_inv, F.pm_proj_inv), F.view_inv, F.pm_view_inv);
-  V4 m3 = apply4m<EA>(apply4m<EA>(apply4m<EA>(v[2].pos, F.viewport_inv, F.pm_viewport_inv), F.proj_inv, F.pm_proj_inv), F.view_inv, F.pm_view_inv);
+  V4 m1, m2, m3;
+  if (!EA && F.unproj_std && v[0].pos.w == 1.0f && v[1].pos.w == 1.0f && v[2].pos.w == 1.0f &&
+      fabsf(v[0].pos.x) + fabsf(v[0].pos.y) + fabsf(v[0].pos.z) + fabsf(v[1].pos.x) + fabsf(v[1].pos.y) + fabsf(v[1].pos.z) + fabsf(v[2].pos.x) +
+              fabsf(v[2].pos.y) + fabsf(v[2].pos.z) < 1e30f) {
+    // single-rounding FMA mode: the zero / one entries of the three inverse matrices make 31 of the 48 FMAs per vertex
+    // identities (FMA(0, v, c) = c, FMA(m, v, +-0) = m*v for finite v); same values, only the sign of an exact zero can differ
+    m1 = unproject_std(F, v[0].pos); m2 = unproject_std(F, v[1].pos); m3 = unproject_std(F, v[2].pos);
+  } else {
+    m1 = apply4m<EA>(apply4m<EA>(apply4m<EA>(v[0].pos, F.viewport_inv, F.pm_viewport_inv), F.proj_inv, F.pm_proj_inv), F.view_inv, F.pm_view_inv);
+    m2 = apply4m<EA>(apply4m<EA>(apply4m<EA>(v[1].pos, F.viewport_inv, F.pm_viewport_inv), F.proj_inv, F.pm_proj_inv), F.view_inv, F.pm_view_inv);
+    m3 = apply4m<EA>(apply4m<EA>(apply4m<EA>(v[2].pos, F.viewport_inv, F.pm_viewport_inv), F.proj_inv, F.pm_proj_inv), F.view_inv, F.pm_view_inv);
+  }
   f.facenor = unit4<EA>(cross4<EA>(sub4(m2, m1), sub4(m3, m1)));
   BarySetup bs = bary_setup<E>(v[0].pos.x, v[0].pos.y, v[1].pos.x, v[1].pos.y, v[2].pos.x, v[2].pos.y);
   const float px = (float)x + 0.5f, py = (float)y + 0.5f;
@@ -1074,8 +1097,11 @@ __device__ __forceinline__ void gbuf_load(const GBuf& G, size_t idx, Frag& f) {
   f.mat = __float_as_int(d.w);
 }
 
+#ifndef PRC_RESOLVE_MIN_BLOCKS
+#define PRC_RESOLVE_MIN_BLOCKS 8  // 64 registers: latency-bound gathers, measured 0.168 ms vs 0.198 at 88 registers
+#endif
 template <bool E, bool EA>
-__global__ void __launch_bounds__(128) k_resolve(DevScene S, DevFrame F, const unsigned long long* __restrict__ keys, GBuf G) {
+__global__ void __launch_bounds__(128, PRC_RESOLVE_MIN_BLOCKS) k_resolve(DevScene S, DevFrame F, const unsigned long long* __restrict__ keys, GBuf G) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = F.rr0 + blockIdx.y * 4 + (threadIdx.x >> 5);
   if (x >= F.W || y >= F.rr1) return;
@@ -1280,17 +1306,22 @@ __device__ bool shading_visibility(const DevFrame& F, const DevLight& l, const V
   // `world` = (X, Y, Depth, 1).Apply(ViewportToWorld) is the same for every light (hoisted by the caller)
   V4 sc;
   if (!E && l.persp_cam && F.vp_std && world.w == 1.0f && fabsf(world.x) + fabsf(world.y) + fabsf(world.z) < 1e30f) {
-    // single-rounding FMA mode only: with the zero / one entries of a rigid view, a perspective projection and the
+    // single-rounding FMA mode only: with the zero / one entries of a rigid view, a perspective / orthographic projection and the
     // standard viewport, FMA(0, v, c) = c and FMA(m, v, +-0) = m*v for finite v, so the 48 FMAs of the three Apply calls
-    // collapse to the 21 operations below with the same values (only the sign of an exact zero can differ)
+    // collapse to the 14-21 operations below with the same values (only the sign of an exact zero can differ)
     const float* a = l.view;
     const float vx = fma32<false>(a[0], world.x, fma32<false>(a[1], world.y, fma32<false>(a[2], world.z, a[3])));
     const float vy = fma32<false>(a[4], world.x, fma32<false>(a[5], world.y, fma32<false>(a[6], world.z, a[7])));
     const float vz = fma32<false>(a[8], world.x, fma32<false>(a[9], world.y, fma32<false>(a[10], world.z, a[11])));
     const float* q = l.proj;
-    const float px = q[0] * vx, py = q[5] * vy, pz = fma32<false>(q[10], vz, q[11]), pw = -vz;
     const float* vp = F.viewport;
-    sc = pos4(V4{fma32<false>(vp[0], px, vp[3] * pw), fma32<false>(vp[5], py, vp[7] * pw), pz, pw});
+    if (l.persp_cam == 1u) {
+      const float px = q[0] * vx, py = q[5] * vy, pz = fma32<false>(q[10], vz, q[11]), pw = -vz;
+      sc = pos4(V4{fma32<false>(vp[0], px, vp[3] * pw), fma32<false>(vp[5], py, vp[7] * pw), pz, pw});
+    } else {  // orthographic: w stays 1, Pos() does not divide
+      const float px = fma32<false>(q[0], vx, q[3]), py = fma32<false>(q[5], vy, q[7]), pz = fma32<false>(q[10], vz, q[11]);
+      sc = V4{fma32<false>(vp[0], px, vp[3]), fma32<false>(vp[5], py, vp[7]), pz, 1.0f};
+    }
   } else {
     sc = pos4(apply4m<E>(apply4m<E>(apply4m<E>(world, l.view, l.pm_view), l.proj, l.pm_proj), F.viewport, F.pm_viewport));
   }
@@ -1388,8 +1419,11 @@ __global__ void k_shade_special(DevScene S, DevFrame F, const AoConsts* __restri
   special[1] = shade_pixel<E>(S, F, A, G.ao_depth, info, 0, 0, 0);
 }
 
+#ifndef PRC_SHADE_MIN_BLOCKS
+#define PRC_SHADE_MIN_BLOCKS 8  // 64 registers: measured 0.313 ms vs 0.355 at 76 registers
+#endif
 template <bool E>
-__global__ void __launch_bounds__(128) k_shade(DevScene S, DevFrame F, const AoConsts* __restrict__ A, const unsigned long long* __restrict__ keys, GBuf G,
+__global__ void __launch_bounds__(128, PRC_SHADE_MIN_BLOCKS) k_shade(DevScene S, DevFrame F, const AoConsts* __restrict__ A, const unsigned long long* __restrict__ keys, GBuf G,
                                                const uint32_t* __restrict__ special, uint32_t* __restrict__ image) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = F.row0 + blockIdx.y * 4 + (threadIdx.x >> 5);
