@@ -644,6 +644,8 @@ int32_t orc_render(orc_ctx* x, const prc_frame* fr, uint8_t* rgba_out) {
   const Mat4 viewport = M(fr->viewport);
   // --- passShadows (render/shadow.go:92-150), per light in order ---
   if (fr->flags & PRC_FRAME_SHADOWMAP) {
+    if (fr->flags & PRC_FRAME_SHADOW_RESET)  // Options() between two views zeroes the maps (render/options.go:125-141)
+      for (auto& d : c.shadow) std::fill(d.begin(), d.end(), 0.0f);
     for (uint32_t li = 0; li < fr->n_lights; li++) {
       const prc_light& l = fr->lights[li];
       if (!l.cast_shadow) continue;

@@ -27,6 +27,7 @@ PRC_FRAME_GAMMA = 4
 PRC_FRAME_KEEP_GBUFFER = 8
 PRC_FRAME_NO_READBACK = 16
 PRC_FRAME_UNIFORMS_RESIDENT = 32
+PRC_FRAME_SHADOW_RESET = 64
 
 F16 = C.c_float * 16
 F3 = C.c_float * 3

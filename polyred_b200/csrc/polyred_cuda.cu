@@ -410,6 +410,7 @@ struct ShadowUnit { uint32_t light; int r0, r1; };
 template <bool E>
 int32_t do_shadows(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, const std::vector<ShadowUnit>& units, bool flush) {
   if (!(fr->flags & PRC_FRAME_SHADOWMAP)) return PRC_OK;
+  if ((fr->flags & PRC_FRAME_SHADOW_RESET) && ctx->d_shadow_all.p) CK(cudaMemsetAsync(ctx->d_shadow_all.p, 0, ctx->d_shadow_all.cap, ctx->stream));
   GeomViews V{};
   const int per_sweep = getenv("PRC_SHADOW_FUSE") ? std::max(1, std::min(8, atoi(getenv("PRC_SHADOW_FUSE")))) : 8;
   for (const ShadowUnit& u : units) {

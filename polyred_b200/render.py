@@ -359,6 +359,22 @@ class Renderer:
         return out
 
 
+def ViewFrames(r: Renderer, cameras) -> list:
+    """The per-view uniforms of RenderViews() as FrameDescs, for callers that submit the views back to back
+    (tools/multiview_bench.py): each carries PRC_FRAME_SHADOW_RESET, the stream-ordered form of the shadow-map
+    zeroing Options() does between views, so no host synchronisation separates two views."""
+    out = []
+    for cam in cameras:
+        sd = r._scene_desc
+        r.Options(Camera(cam))
+        r._scene_desc = sd
+        r._backend_shadow_reset = False
+        fd = r.frame_desc()
+        fd.struct.flags |= A.PRC_FRAME_SHADOW_RESET
+        out.append(fd)
+    return out
+
+
 def RenderViews(r: Renderer, cameras) -> list:
     """BASELINE config 5 (multi-view): the same scene from several cameras. Each view goes through
     Options(Camera(c)) exactly as a reference caller would, which re-fits the light cameras to the new view

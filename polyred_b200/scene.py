@@ -39,8 +39,12 @@ class Geometry(gm.TransformContext):
 
     def aabb(self):
         """mesh AABB in MODEL space (geometry/mesh/mesh_triangle.go:44-48)."""
-        p = self.pos.reshape(-1, 3)
-        return p.min(axis=0).astype(np.float32), p.max(axis=0).astype(np.float32)
+        c = getattr(self, "_aabb_cache", None)
+        if c is None or c[0] is not self.pos:  # the vertex array is immutable once attached; cached per array object
+            p = self.pos.reshape(-1, 3)
+            c = (self.pos, p.min(axis=0).astype(np.float32), p.max(axis=0).astype(np.float32))
+            self._aabb_cache = c
+        return c[1].copy(), c[2].copy()
 
 
 class Group(gm.TransformContext):

@@ -148,9 +148,14 @@ def city_scene(n_objects=1600, obj_stacks=50, obj_slices=50, ground_cells=1000, 
             g.Scale(sc, sc, sc)
             g.Translate(cx, sc * 0.9 + 0.02, cz)
             s.Add(g)
-    cam = camera.Perspective(position=(cam_radius * math.sin(cam_angle), cam_height, cam_radius * math.cos(cam_angle)), target=(0, 0, 0),
-                             up=(0, 1, 0), fov=45, aspect=aspect, near=0.5, far=6.0)
-    return s, cam
+    return s, orbit_camera(cam_angle, cam_radius, cam_height, aspect)
+
+
+def orbit_camera(cam_angle=0.0, cam_radius=2.5, cam_height=1.3, aspect=16.0 / 9.0):
+    """The city_scene camera: on a circle of `cam_radius` around the scene centre at `cam_height`, looking at the origin
+    (C5 = 256 of these, angle 2 pi k / 256)."""
+    return camera.Perspective(position=(cam_radius * math.sin(cam_angle), cam_height, cam_radius * math.cos(cam_angle)), target=(0, 0, 0),
+                              up=(0, 1, 0), fov=45, aspect=aspect, near=0.5, far=6.0)
 
 
 def mesh_scene(subdiv=187, with_ground=False, shadows=False, ao=False, aspect=1.6):

@@ -126,6 +126,29 @@ def test_c5_multi_view_shadows_refit_per_view():
     assert not np.array_equal(vg[0], vg[1])
 
 
+def test_c5_view_frames_submitted_back_to_back():
+    """ViewFrames(): the same views as RenderViews(), submitted without a host sync in between (PRC_FRAME_SHADOW_RESET
+    zeroes the shadow maps in stream order); CUDA and oracle both honour the flag."""
+    import oracle_binding as ob
+    cams = []
+    for k in range(3):
+        s, cam = synth.city_scene(n_objects=16, obj_stacks=12, obj_slices=12, ground_cells=30, tex_size=32, cam_angle=2 * math.pi * k / 3, cam_radius=2.6, cam_height=1.1)
+        cams.append(cam)
+    opts = [render.Camera(cams[0]), render.Size(320, 180), render.Scene(s), render.ShadowMap(True), render.GammaCorrection(True)]
+    rg = render.NewRenderer(*opts, render.CUDA(0))
+    want = render.RenderViews(rg, cams)
+    rg2 = render.NewRenderer(*opts, render.CUDA(0))
+    rg2._ensure_uploaded()
+    rc = render.NewRenderer(*opts, render._Backend(ob.OracleBackend()))
+    rc._ensure_uploaded()
+    for fd, fc, w in zip(render.ViewFrames(rg2, cams), render.ViewFrames(rc, cams), want):
+        rg2._backend.render(fd, None)
+        assert np.array_equal(rg2._backend.host_image(320, 180), w)
+        out = np.zeros((180, 320, 4), np.uint8)
+        rc._backend.render(fc, out)
+        assert np.array_equal(out, w)
+
+
 def test_chunk_culling_is_exact(monkeypatch):
     """Chunk culling (k_chunk_cull) skips 256-triangle chunks that cannot touch a view's rows / the screen. It is
     enabled automatically for partial-row views (multi-GPU); forced here on full frames, including a camera that

@@ -87,3 +87,24 @@ def test_oracle_is_deterministic_and_mt_mode_agrees_without_ties():
     c = render.NewRenderer(render.Camera(cam), render.Size(96, 60), render.Scene(s), render._Backend(ob.OracleBackend(threads=4))).Render()
     assert np.array_equal(a, b)
     assert (np.abs(a.astype(int) - c.astype(int)).max(axis=2) > 0).mean() < 0.01  # Workers>1 only differs at depth ties
+
+
+def test_view_frames_match_render_views_on_the_oracle():
+    """ViewFrames() (PRC_FRAME_SHADOW_RESET, views submitted back to back) gives the frames RenderViews() gives
+    (Options(Camera) + Render per view) — checked on the CPU oracle; the CUDA twin is in test_gpu_parity.py."""
+    import math
+    import oracle_binding as ob
+    from polyred_b200 import render, synth
+    cams = []
+    for k in range(2):
+        s, cam = synth.city_scene(n_objects=6, obj_stacks=8, obj_slices=8, ground_cells=12, tex_size=16, cam_angle=2 * math.pi * k / 2, cam_radius=2.6, cam_height=1.1)
+        cams.append(cam)
+    opts = [render.Camera(cams[0]), render.Size(96, 54), render.Scene(s), render.ShadowMap(True), render.GammaCorrection(True)]
+    want = render.RenderViews(render.NewRenderer(*opts, render._Backend(ob.OracleBackend())), cams)
+    rc = render.NewRenderer(*opts, render._Backend(ob.OracleBackend()))
+    rc._ensure_uploaded()
+    for fd, w in zip(render.ViewFrames(rc, cams), want):
+        out = np.zeros((54, 96, 4), np.uint8)
+        rc._backend.render(fd, out)
+        assert np.array_equal(out, w)
+    assert not np.array_equal(want[0], want[1])

@@ -14,7 +14,7 @@ r = render.NewRenderer(render.Camera(cam), render.Size(w, h), render.Scene(s), r
 be = r._backend; r._ensure_uploaded()
 df = DistributedFrame(r, rank, world, local)
 fd = df.prepare(r.frame_desc(no_readback=True))
-for _ in range(3): df.render(fd, None)
+for _ in range(3): df.render(fd, False)
 def sync():
     torch.cuda.synchronize(); be.sync()
 T = {}
@@ -36,7 +36,20 @@ for _ in range(N):
         def gather():
             dist.all_gather_into_tensor(img, img[rank * icb:(rank + 1) * icb])
         timed('img_gather', gather)
-    timed('whole_frame', lambda: df.render(fd, None))
+    timed('whole_frame', lambda: df.render(fd, False))
+    fd.struct.flags |= A.PRC_FRAME_UNIFORMS_RESIDENT
+    timed('whole_frame_resident', lambda: df.render(fd, False))
+    fd.struct.flags &= ~A.PRC_FRAME_UNIFORMS_RESIDENT
+    def comm_only():
+        with torch.cuda.stream(df.stream):
+            dist.all_gather_into_tensor(full, full[rank * cb:(rank + 1) * cb])
+            dist.all_gather_into_tensor(img, img[rank * icb:(rank + 1) * icb])
+    timed('comm_only', comm_only)
+    timed('barrier_only', lambda: None)
+allT = [None] * world
+dist.all_gather_object(allT, T)
 if rank == 0:
-    print({k: round(v / N, 3) for k, v in T.items()})
+    print("rank0", {k: round(v / N, 3) for k, v in T.items()})
+    print("max  ", {k: round(max(t[k] for t in allT) / N, 3) for k in T})
+    print("min  ", {k: round(min(t[k] for t in allT) / N, 3) for k in T})
 dist.barrier(); dist.destroy_process_group()
