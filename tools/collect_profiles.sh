@@ -13,3 +13,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 45 -c 30 --csv --lo
 # full capture of the geometry/raster kernels (shadow sweep + camera) and the shading kernels of one frame
 ncu --set full --clock-control none --import-source on -k regex:"k_geom_raster|k_resolve|k_shade" -s 5 -c 5 -o $OUT/prof_${TAG} python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1
 tail -2 $OUT/ncu_full.log
+# C5 multi-view throughput on one GPU (the N>1 points come from a --gpus N box, tools/multiview_bench.py under torchrun)
+python tools/multiview_bench.py --views 256 --repeat 2 > $OUT/multiview_1.json 2> $OUT/multiview_1.err
+python tools/bench_brief.py final < $OUT/bench_${TAG}.json

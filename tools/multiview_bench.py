@@ -27,12 +27,12 @@ def main():
     import bench
     from polyred_b200 import render, synth
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    real_stdout = os.dup(1); os.dup2(2, 1)  # NCCL banners etc. must not corrupt the JSON line
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    real_stdout = os.dup(1); os.dup2(2, 1)  # NCCL banners etc. must not corrupt the JSON line
     wl = bench.WORKLOADS[args.workload]
     w, h = args.width, args.height
     s, cam0 = synth.city_scene(aspect=w / h, **wl["gen"])
