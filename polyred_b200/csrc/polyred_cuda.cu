@@ -9,6 +9,8 @@
 
 #include "prc_kernels.cuh"
 
+#define PRC_SHADE_BANDS 8  // row bands of the shading pass when the frame is read back (copy of band k overlaps shading of band k+1)
+
 using namespace prc;
 
 namespace {
@@ -64,6 +66,10 @@ struct prc_ctx {
   Counters* h_counters = nullptr;  // pinned
 
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  // readback overlapped with shading: the image leaves in row bands on a second stream while the next band is shaded
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_band[PRC_SHADE_BANDS] = {}, ev_copied = nullptr;
+  uint8_t* rb_dst = nullptr;  // page-locked destination of this frame's image (nullptr: no readback)
   // per-kernel-class event pairs of the current frame
   std::vector<cudaEvent_t> evpool;
   struct Span { int cls; size_t a, b; };
@@ -453,6 +459,9 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, int phases
     if (F.rr0 > 0) CK(cudaMemsetAsync(ctx->d_keys.p, 0, 8, st));
   }
   (void)npx;
+  // one kernel for resolve + shading when nothing reads the G-buffer afterwards (k_resolve_shade)
+  static const bool no_fused = getenv("PRC_NO_FUSED_SHADE") != nullptr;
+  const bool fused = phases == 3 && !(fr->flags & PRC_FRAME_KEEP_GBUFFER) && !ctx->any_ao && !no_fused;
   GBuf G{(float4*)ctx->d_ga.p, (float4*)ctx->d_gb.p, (float4*)ctx->d_gc.p, (float4*)ctx->d_gd.p, ctx->any_ao ? (float*)ctx->d_ao.p : nullptr};
   const unsigned long long* keys = (const unsigned long long*)ctx->d_keys.p;
   if (phases & 1) {
@@ -465,36 +474,62 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, int phases
   CK(cudaEventRecordWithFlags(ctx->ev[2], st, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   dim3 rg((F.W + 31) / 32, (F.rr1 - F.rr0 + 3) / 4);
   { KTimer kt(ctx, PRC_K_RESOLVE);
+  if (!fused) {
   if (ctx->exact_shade) k_resolve<E, E><<<rg, 128, 0, st>>>(ctx->S, F, keys, G); else k_resolve<E, false><<<rg, 128, 0, st>>>(ctx->S, F, keys, G);
   ctx->launches++;
-  if (F.rr0 > 0) { if (ctx->exact_shade) k_resolve00<E, E><<<1, 1, 0, st>>>(ctx->S, F, keys, G); else k_resolve00<E, false><<<1, 1, 0, st>>>(ctx->S, F, keys, G); ctx->launches++; } }
+  }
+  if (F.rr0 > 0 || fused) { if (ctx->exact_shade) k_resolve00<E, E><<<1, 1, 0, st>>>(ctx->S, F, keys, G); else k_resolve00<E, false><<<1, 1, 0, st>>>(ctx->S, F, keys, G); ctx->launches++; } }
   }
   if (phases & 2) {
   { KTimer kt(ctx, PRC_K_SHADE);
-  if (ctx->exact_shade) {
-  k_shade_special<true><<<1, 32, 0, st>>>(ctx->S, F, (const AoConsts*)ctx->d_aoc.p, keys, G, (uint32_t*)ctx->d_special.p);
-  dim3 sg((F.W + 31) / 32, (F.row1 - F.row0 + 3) / 4);
-  k_shade<true><<<sg, 128, 0, st>>>(ctx->S, F, (const AoConsts*)ctx->d_aoc.p, keys, G, (const uint32_t*)ctx->d_special.p, (uint32_t*)ctx->d_image.p);
-  } else {
-  k_shade_special<false><<<1, 32, 0, st>>>(ctx->S, F, (const AoConsts*)ctx->d_aoc.p, keys, G, (uint32_t*)ctx->d_special.p);
-  dim3 sg((F.W + 31) / 32, (F.row1 - F.row0 + 3) / 4);
-  k_shade<false><<<sg, 128, 0, st>>>(ctx->S, F, (const AoConsts*)ctx->d_aoc.p, keys, G, (const uint32_t*)ctx->d_special.p, (uint32_t*)ctx->d_image.p);
-  } }
-  ctx->launches += 2;
-  ctx->gbuffer_valid = true;
+  const AoConsts* aoc = (const AoConsts*)ctx->d_aoc.p;
+  if (ctx->exact_shade) k_shade_special<true><<<1, 32, 0, st>>>(ctx->S, F, aoc, keys, G, (uint32_t*)ctx->d_special.p);
+  else k_shade_special<false><<<1, 32, 0, st>>>(ctx->S, F, aoc, keys, G, (uint32_t*)ctx->d_special.p);
+  // With a readback pending the strip is shaded in PRC_SHADE_BANDS row bands, top image rows first; each band's
+  // device->host DMA runs on the copy stream while the next band is shaded (only the last band's copy is exposed).
+  const int rows = F.row1 - F.row0;
+  const int nb = (ctx->rb_dst && rows >= 64 * PRC_SHADE_BANDS) ? PRC_SHADE_BANDS : 1;
+  const int band = ((rows + nb - 1) / nb + 3) & ~3;
+  for (int b = 0; b < nb; b++) {
+    DevFrame Fb = F;
+    Fb.row1 = F.row1 - b * band;  // image row r = screen y = H-1-r: the highest screen rows are the first image rows
+    Fb.row0 = std::max(F.row0, Fb.row1 - band);
+    if (Fb.row0 >= Fb.row1) break;
+    dim3 sg((F.W + 31) / 32, (Fb.row1 - Fb.row0 + 3) / 4);
+    if (fused) {
+      if (ctx->exact_shade) k_resolve_shade<E, E><<<sg, 128, 0, st>>>(ctx->S, Fb, aoc, keys, (const uint32_t*)ctx->d_special.p, (uint32_t*)ctx->d_image.p);
+      else k_resolve_shade<E, false><<<sg, 128, 0, st>>>(ctx->S, Fb, aoc, keys, (const uint32_t*)ctx->d_special.p, (uint32_t*)ctx->d_image.p);
+    } else if (ctx->exact_shade) k_shade<true><<<sg, 128, 0, st>>>(ctx->S, Fb, aoc, keys, G, (const uint32_t*)ctx->d_special.p, (uint32_t*)ctx->d_image.p);
+    else k_shade<false><<<sg, 128, 0, st>>>(ctx->S, Fb, aoc, keys, G, (const uint32_t*)ctx->d_special.p, (uint32_t*)ctx->d_image.p);
+    ctx->launches++;
+    if (ctx->rb_dst) {
+      const size_t off = (size_t)(F.H - Fb.row1) * F.W * 4, bytes = (size_t)(Fb.row1 - Fb.row0) * F.W * 4;
+      CK(cudaEventRecord(ctx->ev_band[b], st));
+      CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band[b], 0));
+      CK(cudaMemcpyAsync(ctx->rb_dst + off, (uint8_t*)ctx->d_image.p + off, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
+  }
+  if (ctx->rb_dst) {  // the frame's stream ends after the last copy
+    CK(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+    CK(cudaStreamWaitEvent(st, ctx->ev_copied, 0));
+  }
+  }
+  ctx->launches += 1;
+  ctx->gbuffer_valid = !fused;
   }
   CK(cudaGetLastError());
   return PRC_OK;
 }
 
-int32_t readback_image(prc_ctx* ctx, const DevFrame& F, uint8_t* rgba_out) {
-  // image rows of the strip: screen rows [row0,row1) -> image rows [H-row1, H-row0)
-  const size_t off = (size_t)(F.H - F.row1) * F.W * 4, bytes = (size_t)(F.row1 - F.row0) * F.W * 4;
-  const size_t total = (size_t)F.W * F.H * 4;
-  // Two library-owned page-locked images used alternately, like the reference's double buffer (raster.go:86,
-  // 201-206): the device->host copy is one DMA at PCIe speed; a caller that passes rgba_out == NULL reads the
-  // frame in place through prc_host_image (zero copy, valid until two frames later), one that passes its own
-  // buffer pays an extra host memcpy.
+// Two library-owned page-locked images used alternately, like the reference's double buffer (raster.go:86,
+// 201-206): the device->host copy is DMA at PCIe speed; a caller that passes rgba_out == NULL reads the frame in
+// place through prc_host_image (zero copy, valid until two frames later), one that passes its own buffer pays an
+// extra host memcpy. readback_begin() picks this frame's buffer BEFORE the frame is enqueued (do_main issues the
+// copies band by band behind the shading kernels); readback_end() waits for them.
+int32_t readback_begin(prc_ctx* ctx, const prc_frame* fr) {
+  ctx->rb_dst = nullptr;
+  if (fr->flags & PRC_FRAME_NO_READBACK) return PRC_OK;
+  const size_t total = (size_t)fr->width * fr->height * 4;
   if (ctx->h_img_cap < total) {
     for (auto& p : ctx->h_img) { if (p) { cudaHostUnregister(p); free(p); } p = nullptr; }
     for (auto& p : ctx->h_img) {
@@ -508,10 +543,15 @@ int32_t readback_image(prc_ctx* ctx, const DevFrame& F, uint8_t* rgba_out) {
     ctx->h_img_cap = total;
   }
   ctx->h_img_cur ^= 1;
-  uint8_t* dst = ctx->h_img[ctx->h_img_cur];
-  CK(cudaMemcpyAsync(dst + off, (uint8_t*)ctx->d_image.p + off, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  if (rgba_out) memcpy(rgba_out + off, dst + off, bytes);
+  ctx->rb_dst = ctx->h_img[ctx->h_img_cur];
+  return PRC_OK;
+}
+
+int32_t readback_end(prc_ctx* ctx, const DevFrame& F, uint8_t* rgba_out) {
+  // image rows of the strip: screen rows [row0,row1) -> image rows [H-row1, H-row0)
+  const size_t off = (size_t)(F.H - F.row1) * F.W * 4, bytes = (size_t)(F.row1 - F.row0) * F.W * 4;
+  CK(cudaStreamSynchronize(ctx->stream));  // the copies were joined into the frame's stream by do_main
+  if (rgba_out && ctx->rb_dst) memcpy(rgba_out + off, ctx->rb_dst + off, bytes);
   return PRC_OK;
 }
 
@@ -581,7 +621,10 @@ int32_t prc_open(int32_t device, prc_ctx** out) {
   prc_ctx* ctx = new prc_ctx();
   ctx->device = device;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PRC_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PRC_ERR_CUDA; }
   for (auto& e : ctx->ev) cudaEventCreate(&e);
+  for (auto& e : ctx->ev_band) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming);
   cudaMallocHost((void**)&ctx->h_counters, sizeof(Counters));
   cudaMalloc(&ctx->d_counters.p, sizeof(Counters));
   ctx->d_counters.cap = sizeof(Counters);
@@ -621,6 +664,9 @@ int32_t prc_close(prc_ctx* ctx) {
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   for (auto& e : ctx->evpool) cudaEventDestroy(e);
+  for (auto& e : ctx->ev_band) if (e) cudaEventDestroy(e);
+  if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return PRC_OK;
@@ -779,6 +825,8 @@ int32_t prc_render_main(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out) {
   DevFrame F;
   int32_t r = build_frame(ctx, fr, F);
   if (r != PRC_OK) return r;
+  r = readback_begin(ctx, fr);
+  if (r != PRC_OK) return r;
   for (int attempt = 0; attempt < 4; attempt++) {
     CK(cudaMemsetAsync(ctx->d_counters.p, 0, 16 + 8, ctx->stream));
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -786,7 +834,7 @@ int32_t prc_render_main(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out) {
     if (r != PRC_OK) return r;
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     if (!(fr->flags & PRC_FRAME_NO_READBACK)) {
-      r = readback_image(ctx, F, rgba_out);
+      r = readback_end(ctx, F, rgba_out);
       if (r != PRC_OK) return r;
     }
     r = finish_timings(ctx);
@@ -805,6 +853,7 @@ int32_t prc_render_forward(prc_ctx* ctx, const prc_frame* fr) {
   DevFrame F;
   int32_t r = build_frame(ctx, fr, F);
   if (r != PRC_OK) return r;
+  ctx->rb_dst = nullptr;
   CK(cudaMemsetAsync(ctx->d_counters.p, 0, 16 + 8, ctx->stream));
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   return ctx->exact ? do_main<true>(ctx, fr, F, 1) : do_main<false>(ctx, fr, F, 1);
@@ -816,11 +865,13 @@ int32_t prc_render_deferred(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out
   DevFrame F;
   int32_t r = build_frame(ctx, fr, F);
   if (r != PRC_OK) return r;
+  r = readback_begin(ctx, fr);
+  if (r != PRC_OK) return r;
   r = ctx->exact ? do_main<true>(ctx, fr, F, 2) : do_main<false>(ctx, fr, F, 2);
   if (r != PRC_OK) return r;
   CK(cudaEventRecord(ctx->ev[3], ctx->stream));
   if (!(fr->flags & PRC_FRAME_NO_READBACK)) {
-    r = readback_image(ctx, F, rgba_out);
+    r = readback_end(ctx, F, rgba_out);
     if (r != PRC_OK) return r;
   }
   r = finish_timings(ctx);
@@ -854,13 +905,15 @@ int32_t prc_render(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out) {
   DevFrame F;
   int32_t r = build_frame(ctx, fr, F);
   if (r != PRC_OK) return r;
+  r = readback_begin(ctx, fr);
+  if (r != PRC_OK) return r;
   // (A CUDA-graph replay of the ~35 stream operations of a frame was measured: 1.894 vs 1.886 ms — the gaps between
   // the kernels are device-side launch latency, not host enqueue time, so the frame is launched directly.)
   for (int attempt = 0; attempt < 4; attempt++) {
     r = enqueue_frame(ctx, fr, F);
     if (r != PRC_OK) return r;
     if (!(fr->flags & PRC_FRAME_NO_READBACK)) {
-      r = readback_image(ctx, F, rgba_out);
+      r = readback_end(ctx, F, rgba_out);
       if (r != PRC_OK) return r;
     }
     r = finish_timings(ctx);

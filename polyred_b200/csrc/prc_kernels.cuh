@@ -615,8 +615,13 @@ __device__ __forceinline__ void geom_classify(const DevScene& S, const DevFrame&
     return;
   }
   const float p1y = sy[i0], p2y = sy[i1], p3y = sy[i2];
-  // cullBackFace (render/cull.go:26-28): FMA(e1.x, e2.y, -(e1.y*e2.x)) < 0, the same expression as Barycoord's Sabc
-  const float Sabc = cross2z<E>(p2x - p1x, p2y - p1y, p3x - p1x, p3y - p1y);
+  // cullBackFace (render/cull.go:26-28): FMA(e1.x, e2.y, -(e1.y*e2.x)) < 0, the same expression as Barycoord's Sabc.
+  // Only its SIGN is needed here, and the single-rounding FMA has the sign of the exactly computed value just like the
+  // reference's double-rounded one (both round the same exact number, neither can round a non-zero value of this
+  // magnitude to zero); a zero or subnormal result takes the exact route. The pruning test below tolerates the 1-ulp
+  // difference (its threshold has orders of magnitude of slack, prc_prune.h); phase 3 recomputes Sabc exactly.
+  float Sabc = cross2z<false>(p2x - p1x, p2y - p1y, p3x - p1x, p3y - p1y);
+  if (E && !(fabsf(Sabc) >= 1.17549435e-38f)) Sabc = cross2z<true>(p2x - p1x, p2y - p1y, p3x - p1x, p3y - p1y);
   if (Sabc < 0.0f) return;
   const float p1z = sz[i0], p2z = sz[i1], p3z = sz[i2];
   // finite coordinates: Go's NaN-propagating Min/Max reduce to plain min/max (the sign of a zero is irrelevant below)
@@ -1437,6 +1442,37 @@ __global__ void __launch_bounds__(128, PRC_SHADE_MIN_BLOCKS) k_shade(DevScene S,
     gbuf_load(G, idx, info);
     info.ok = true; info.X = x; info.Y = y;
     col = shade_pixel<E>(S, F, A, G.ao_depth, info, x, y, info.mat);
+  }
+  if (F.flags & PRC_FRAME_GAMMA)
+    col = (uint32_t)F.gamma[chan(col, 0)] | ((uint32_t)F.gamma[chan(col, 1)] << 8) | ((uint32_t)F.gamma[chan(col, 2)] << 16) | (col & 0xff000000u);
+  image[(size_t)(F.H - 1 - y) * F.W + x] = col;  // image row r = screen y = H-1-r (buffer.go:225)
+}
+
+// K3+K4 fused: visibility key -> attributes -> colour in one kernel, without the 64 B/pixel G-buffer round trip. The
+// attribute gathers of k_resolve are latency bound and the shading arithmetic of k_shade is issue bound; in one kernel
+// warps in either stage cover for each other. Used when nothing needs the G-buffer afterwards: no PRC_FRAME_KEEP_GBUFFER
+// and no ambient-occlusion material (AO reads its neighbours' depths, i.e. needs every pixel resolved first). Pixel (0,0)
+// is resolved beforehand by k_resolve00 for k_shade_special. Same device functions, same values as the two-kernel path.
+#ifndef PRC_FUSED_MIN_BLOCKS
+#define PRC_FUSED_MIN_BLOCKS 8
+#endif
+template <bool E, bool ES>
+__global__ void __launch_bounds__(128, PRC_FUSED_MIN_BLOCKS) k_resolve_shade(DevScene S, DevFrame F, const AoConsts* __restrict__ A, const unsigned long long* __restrict__ keys,
+                                                       const uint32_t* __restrict__ special, uint32_t* __restrict__ image) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = F.row0 + blockIdx.y * 4 + (threadIdx.x >> 5);
+  if (x >= F.W || y >= F.row1) return;
+  const size_t idx = (size_t)y * F.W + x;
+  const unsigned long long key = keys[idx];
+  uint32_t col;
+  if (x == 0 && y == 0) col = special[0];
+  else if (key == 0) col = special[1];
+  else {
+    Frag info;
+    resolve_fragment<E, ES>(S, F, 0xFFFFFFFFu - (uint32_t)key, x, y, info);
+    info.nor.w = 0.0f; info.facenor.w = 0.0f; info.wpos.w = 1.0f;  // what a G-buffer round trip keeps (gbuf_load)
+    info.ok = true; info.X = x; info.Y = y;
+    col = shade_pixel<ES>(S, F, A, nullptr, info, x, y, info.mat);
   }
   if (F.flags & PRC_FRAME_GAMMA)
     col = (uint32_t)F.gamma[chan(col, 0)] | ((uint32_t)F.gamma[chan(col, 1)] << 8) | ((uint32_t)F.gamma[chan(col, 2)] << 16) | (col & 0xff000000u);

@@ -149,6 +149,23 @@ def test_c5_view_frames_submitted_back_to_back():
         assert np.array_equal(out, w)
 
 
+@pytest.mark.parametrize("mode", ["exact", "mixed", "fast"])
+def test_fused_resolve_shade_equals_two_kernel_path(monkeypatch, mode):
+    """Without PRC_FRAME_KEEP_GBUFFER (and without AO materials) resolve and shading run as ONE kernel that never writes
+    the G-buffer (k_resolve_shade); the frame must be byte-identical to the two-kernel path, and in exact mode to the oracle."""
+    import oracle_binding as ob
+    monkeypatch.setenv("PRC_FMA", mode)
+    s, cam = synth.city_scene(n_objects=36, obj_stacks=16, obj_slices=16, ground_cells=60, tex_size=64)
+    opts = [render.Camera(cam), render.Size(640, 360), render.Scene(s), render.ShadowMap(True), render.GammaCorrection(True)]
+    rg = render.NewRenderer(*opts, render.CUDA(0))
+    fused = rg.Render().copy()
+    two = rg.Render(keep_gbuffer=True).copy()
+    assert np.array_equal(fused, two)
+    if mode == "exact":
+        want = render.NewRenderer(*opts, render._Backend(ob.OracleBackend())).Render()
+        assert np.array_equal(fused, want)
+
+
 def test_chunk_culling_is_exact(monkeypatch):
     """Chunk culling (k_chunk_cull) skips 256-triangle chunks that cannot touch a view's rows / the screen. It is
     enabled automatically for partial-row views (multi-GPU); forced here on full frames, including a camera that
