@@ -264,6 +264,11 @@ int32_t prc_device_shadow_all(prc_ctx* ctx, uint64_t* dev_ptr, uint64_t* bytes, 
 int32_t prc_stream(prc_ctx* ctx, uint64_t* stream);
 int32_t prc_sync(prc_ctx* ctx);
 
+/* Arithmetic mode of this context, overriding the PRC_FMA environment variable read by prc_open:
+ * exact != 0 -> math.FMA[float32] emulated bit-exactly everywhere (float64 fma rounded to float32, math/math.go FMA),
+ * exact == 0 -> single-rounding fmaf everywhere ("fast"). The default, "mixed", is only selectable through PRC_FMA. */
+int32_t prc_set_exact_fma(prc_ctx* ctx, int32_t exact);
+
 #ifdef __cplusplus
 }
 #endif

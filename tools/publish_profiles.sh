@@ -6,7 +6,7 @@ G=gpurun_out; P=profiles
 for f in bench_${TAG}.json bench_exact_${TAG}.json bench_fast_${TAG}.json bench_reference_${TAG}.json launches_${TAG}.csv multiview_1.json; do cp $G/$f $P/$f; done
 python tools/ncu_summary.py $G/prof_${TAG}.ncu-rep k_geom_raster 30 > $P/ncu_geom_raster_${TAG}.txt 2>/dev/null
 python tools/ncu_summary.py $G/prof_${TAG}.ncu-rep k_resolve 20 > $P/ncu_resolve_${TAG}.txt 2>/dev/null
-python tools/ncu_summary.py $G/prof_${TAG}.ncu-rep k_shade 25 > $P/ncu_shade_${TAG}.txt 2>/dev/null
+python tools/ncu_summary.py $G/prof_${TAG}.ncu-rep "k_shade|k_resolve_shade" 25 > $P/ncu_shade_${TAG}.txt 2>/dev/null
 python tools/ncu_lines.py $G/prof_${TAG}.ncu-rep k_geom_raster 40 "(bool)1, (bool)1" > $P/ncu_geom_raster_lines_${TAG}.txt 2>/dev/null
 python - <<PY
 import csv, io, json, subprocess
@@ -22,7 +22,7 @@ cls = {}
 for r in rows[2:]:
     k = r[ik]
     name = ("geom_raster_shadow" if "k_geom_raster" in k and "true, true" in k.replace("(bool)1", "true").replace("(bool)0", "false").replace("<1, 1>", "<true, true>") else
-            "geom_raster_camera" if "k_geom_raster" in k else "resolve" if "k_resolve<" in k or "k_resolve(" in k else "shade" if "k_shade<" in k or "k_shade(" in k else None)
+            "geom_raster_camera" if "k_geom_raster" in k else "shade" if "k_resolve_shade" in k else "resolve" if "k_resolve<" in k or "k_resolve(" in k else "shade" if "k_shade<" in k or "k_shade(" in k else None)
     if name is None or "special" in k or "resolve00" in k: continue
     b = to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw])
     c = cls.setdefault(name, {"dram_bytes_per_launch": 0.0, "launches_sampled": 0})
