@@ -280,7 +280,12 @@ def run_cuda(args):
     n_tris = sd.n_tris
     px = w * h
     n_fused = max(1, int(round(len(cast) * args.steps / max(1, klaunch[0]))))  # shadow lights sharing one sweep
-    per_launch_bytes = {0: n_fused * (36 * n_tris + 8 * px), 1: 112 * n_tris + 16 * px, 4: 8 * px, 5: 16 * px, 6: (8 + 64) * px, 7: (64 + 4 + 4 * len(cast)) * px}
+    # 1 GPU, no AO material, no KEEP_GBUFFER: resolve and shading run as ONE kernel (k_resolve_shade, timed in the "shade"
+    # class); it is charged the algorithmic bytes of both stages, G-buffer round trip included
+    one_kernel_shade = world == 1 and not os.environ.get("PRC_NO_FUSED_SHADE") and not any(
+        getattr(m, "ambient_occlusion", False) for m in sd.materials)
+    shade_bytes = (64 + 4 + 4 * len(cast)) * px + ((8 + 64) * px if one_kernel_shade else 0)
+    per_launch_bytes = {0: n_fused * (36 * n_tris + 8 * px), 1: 112 * n_tris + 16 * px, 4: 8 * px, 5: 16 * px, 6: (8 + 64) * px, 7: shade_bytes}
     alg = per_launch_bytes.get(dom, 0)
     avg_ms = ksum[dom] / max(1, klaunch[dom])
     achieved = alg / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
@@ -298,7 +303,7 @@ def run_cuda(args):
         "config": {"workload": f"{args.workload}: {wl['desc']}", "n_tris": int(n_tris), "n_valid_tris": n_valid, "width": w, "height": h,
                    "fma": os.environ.get("PRC_FMA", "mixed"), "l2": "inputs (1.1 GB scene, 0.9 GB frame buffers) larger than L2; no explicit flush",
                    "partition": "1 GPU" if world == 1 else f"{world} screen strips + {len(units)} shadow shards (one in-place NCCL all-gather overlapped with the camera pass, one in-place all-gather of the image strips)"},
-        "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": ("resolve_shade (k_resolve_shade, one kernel)" if (dom == 7 and one_kernel_shade) else names[dom]), "achieved": achieved, "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s",
                      "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms,
                      "launches_per_step": float(klaunch[dom]) / args.steps},
         "frame_roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": frame_bytes, "achieved": frame_bytes / (ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],

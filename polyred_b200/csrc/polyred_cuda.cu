@@ -329,6 +329,7 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
     memcpy(d.pos, l.pos, 12);
     d.intensity = l.intensity;
     d.color = l.color_rgba;
+    for (int k = 0; k < 3; k++) d.colf[k] = (float)((l.color_rgba >> (8 * k)) & 0xffu);
     memcpy(d.view, l.view, 64);
     memcpy(d.proj, l.proj, 64);
     d.pm_view = plain_mask(l.view);

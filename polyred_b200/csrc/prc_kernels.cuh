@@ -48,6 +48,7 @@ struct DevLight {
   float pos[3];
   float intensity;
   uint32_t color;
+  float colf[3];  // the colour channels as float32 (converted once on the host instead of per light per pixel)
   float view[16], proj[16];
   uint32_t pm_view, pm_proj;  // plain masks (see apply4m)
   uint32_t persp_cam;         // rigid view with 1 = perspective, 2 = orthographic projection, all entries finite (0 = anything else)
@@ -1141,10 +1142,23 @@ __device__ __forceinline__ uint32_t rgba_at(const DevScene& S, uint32_t lvl, lon
   return __ldg(reinterpret_cast<const uint32_t*>(S.tex_data + S.level_off[lvl]) + (size_t)y * w + x);
 }
 __device__ uint32_t query_bilinear(const DevScene& S, uint32_t lvl, float u, float v) {
-  const long long dx = S.level_w[lvl], dy = S.level_h[lvl];
-  if (dx == 1 && dy == 1) return rgba_at(S, lvl, 0, 0);
-  float x = u * ((float)dx - 1.0f), y = v * ((float)dy - 1.0f);
+  const uint32_t wx = S.level_w[lvl], wy = S.level_h[lvl];
+  if (wx == 1 && wy == 1) return rgba_at(S, lvl, 0, 0);
+  float x = u * ((float)wx - 1.0f), y = v * ((float)wy - 1.0f);
   float x0 = floorf(x), y0 = floorf(y);
+  if (x0 >= 0.0f && y0 >= 0.0f && x0 < 1.0e9f && y0 < 1.0e9f && wx < 0x40000000u && wy < 0x40000000u) {
+    // the usual case in 32-bit integers: same texel indices, same bounds tests as the 64-bit sequence below
+    const uint32_t i = (uint32_t)__float2int_rz(x0), j = (uint32_t)__float2int_rz(y0);
+    const uint32_t* tex = reinterpret_cast<const uint32_t*>(S.tex_data + S.level_off[lvl]);
+    const bool in_i = i < wx, in_j = j < wy, in_i1 = i + 1 < wx, in_j1 = j + 1 < wy;  // i, j >= 0 here
+    const uint32_t p1 = (in_i && in_j) ? __ldg(tex + (size_t)j * wx + i) : 0u;
+    const uint32_t p2 = in_i1 ? (in_j ? __ldg(tex + (size_t)j * wx + i + 1) : 0u) : p1;
+    const uint32_t p3 = in_j1 ? (in_i ? __ldg(tex + (size_t)(j + 1) * wx + i) : 0u) : p1;
+    const uint32_t p4 = (in_i1 && in_j1) ? __ldg(tex + (size_t)(j + 1) * wx + i + 1) : p1;
+    const float tx = x - x0;
+    return lerpc(lerpc(p1, p2, tx), lerpc(p3, p4, tx), y - y0);
+  }
+  const long long dx = wx, dy = wy;
   long long i = go_int(x0), j = go_int(y0);
   uint32_t p1 = rgba_at(S, lvl, i, j);
   uint32_t p2 = (i < dx - 1) ? rgba_at(S, lvl, i + 1, j) : p1;
@@ -1296,7 +1310,7 @@ __device__ uint32_t fragment_shader(const DevScene& S, const DevFrame& F, const 
     float Ld = clampf(dot4<E>(n, L), 0.0f, 1.0f);
     float Ls = go_pow(clampf(dot4<E>(n, Hh), 0.0f, 1.0f), m.shininess);
     LdR += Ld * cr * I; LdG += Ld * cg * I; LdB += Ld * cb * I;
-    LsR += Ls * (float)chan(l.color, 0) * I; LsG += Ls * (float)chan(l.color, 1) * I; LsB += Ls * (float)chan(l.color, 2) * I;
+    LsR += Ls * l.colf[0] * I; LsG += Ls * l.colf[1] * I; LsB += Ls * l.colf[2] * I;  // colf[k] = float32(chan(color, k))
   }
   float r = roundf(LaR + __fdiv_rn((float)chan(m.diffuse_rgba, 0) * LdR, 255.0f) + __fdiv_rn((float)chan(m.specular_rgba, 0) * LsR, 255.0f));
   float g = roundf(LaG + __fdiv_rn((float)chan(m.diffuse_rgba, 1) * LdG, 255.0f) + __fdiv_rn((float)chan(m.specular_rgba, 1) * LsG, 255.0f));

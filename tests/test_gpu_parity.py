@@ -166,6 +166,29 @@ def test_fused_resolve_shade_equals_two_kernel_path(monkeypatch, mode):
         assert np.array_equal(fused, want)
 
 
+def test_candidate_queue_overflow_and_unshared_vertices(monkeypatch):
+    """k_geom_raster corner cases, bit-exact against the oracle: (a) a ground of ~3-pixel cells seen from above gives every
+    256-triangle chunk ~3000 candidate pixels, more than the CTA queue holds (PRC_QCAP = 2048), so part of each chunk takes
+    the in-thread fallback; (b) the same mesh with every triangle's vertices jittered apart shares NO vertex (768 distinct
+    vertices per chunk, the worst case of the chunk-local vertex table)."""
+    monkeypatch.setenv("PRC_FMA", "exact")
+    s, _ = synth.city_scene(n_objects=0, ground_cells=150, tex_size=32)
+    cam = camera.Perspective(position=(0.0, 2.6, 0.05), target=(0, 0, 0), up=(0, 1, 0), fov=45, aspect=16 / 9, near=0.5, far=6.0)
+    g, c = make_renderers(s, cam, 960, 540, shadow=True, gamma=True)
+    st, ig, ic = compare_frames(g, c, 960, 540, n_lights_cast=(0, 2, 4, 6))
+    _report("queue-overflow", st)
+    assert_bit_exact(st)
+    assert st["rgba_px_diff"] == 0 and st["covered"] > 100000, st
+    geo = [o for o in s.root.leaves() if hasattr(o, "pos")][0]
+    rng = np.random.default_rng(7)
+    geo.pos = (geo.pos + rng.uniform(-1e-4, 1e-4, size=geo.pos.shape)).astype(np.float32)
+    g, c = make_renderers(s, cam, 960, 540, shadow=True, gamma=True)
+    st, ig, ic = compare_frames(g, c, 960, 540, n_lights_cast=(0, 2, 4, 6))
+    _report("unshared-vertices", st)
+    assert_bit_exact(st)
+    assert st["rgba_px_diff"] == 0, st
+
+
 def test_chunk_culling_is_exact(monkeypatch):
     """Chunk culling (k_chunk_cull) skips 256-triangle chunks that cannot touch a view's rows / the screen. It is
     enabled automatically for partial-row views (multi-GPU); forced here on full frames, including a camera that
