@@ -187,13 +187,8 @@ int32_t raster_pass(prc_ctx* ctx, const DevFrame& F, const GeomViews& Vin) {
   }
   if (ctx->S.n_tris) {
     KTimer kt(ctx, SHADOW ? PRC_K_GEOM_SHADOW : PRC_K_GEOM_CAMERA);
-    static const bool v1 = getenv("PRC_GEOM_V1") != nullptr;  // A/B switch: the per-triangle kernel without vertex sharing
-    if (v1)
-      k_geom_raster_v1<E, SHADOW><<<cdiv(ctx->S.n_tris, PRC_GEOM_THREADS), PRC_GEOM_THREADS, 0, st>>>(ctx->S, F, V, keys, large, ctx->large_cap, clipq,
-                                                                                                          ctx->clip_cap, cnt, (const DevFrame*)fb.p);
-    else
-      k_geom_raster<E, SHADOW><<<cdiv(ctx->S.n_tris, PRC_GEOM_THREADS), PRC_GEOM_THREADS, 0, st>>>(ctx->S, F, V, keys, large, ctx->large_cap, clipq, ctx->clip_cap,
-                                                                                                       cnt, (const DevFrame*)fb.p);
+    k_geom_raster<E, SHADOW><<<cdiv(ctx->S.n_tris, PRC_GEOM_THREADS), PRC_GEOM_THREADS, 0, st>>>(ctx->S, F, V, keys, large, ctx->large_cap, clipq, ctx->clip_cap,
+                                                                                                     cnt, (const DevFrame*)fb.p);
     ctx->launches++;
   }
   if (!SHADOW) {
@@ -461,7 +456,7 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, int phases
   }
   (void)npx;
   // one kernel for resolve + shading when nothing reads the G-buffer afterwards (k_resolve_shade)
-  static const bool no_fused = getenv("PRC_NO_FUSED_SHADE") != nullptr;
+  const bool no_fused = getenv("PRC_NO_FUSED_SHADE") != nullptr;
   const bool fused = phases == 3 && !(fr->flags & PRC_FRAME_KEEP_GBUFFER) && !ctx->any_ao && !no_fused;
   GBuf G{(float4*)ctx->d_ga.p, (float4*)ctx->d_gb.p, (float4*)ctx->d_gc.p, (float4*)ctx->d_gd.p, ctx->any_ao ? (float*)ctx->d_ao.p : nullptr};
   const unsigned long long* keys = (const unsigned long long*)ctx->d_keys.p;

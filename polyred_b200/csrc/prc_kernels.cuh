@@ -1,14 +1,15 @@
 // prc_kernels.cuh — sm_100a kernels of the render pass. See DESIGN.md for the pipeline.
 //
-// Pipeline of one frame (all on one stream):
-//   [per casting light]  k_geom_raster<SHADOW>  -> small triangles rasterised in-thread with atomicMax on
-//                                                  the shadow map, large ones queued as setup records
-//                        k_bin_count/k_scan/k_bin_fill/k_tile_raster<SHADOW> for the queued records
-//   k_geom_raster<CAMERA>  -> visibility keys (depth, ~draw sequence) by 64-bit atomicMax; clip queue; large queue
-//   k_clip_raster          -> Sutherland-Hodgman fan for triangles straddling the viewport
-//   k_bin_* / k_tile_raster<CAMERA>
-//   k_resolve              -> key -> G-buffer attributes (4 x float4 per pixel)
-//   k_shade_special, k_shade -> Blinn-Phong + shadow lookup + AO + gamma -> RGBA8 (image order)
+// Pipeline of one frame (all on one stream, no host round trip):
+//   [k_chunk_cull]           per partial-row view (multi-GPU): which 256-triangle chunks can touch the view's rows
+//   k_geom_raster<SHADOW>    all casting lights in one sweep: shared vertices -> screen, cull/classify, candidate-pixel
+//                            queue -> atomicMax on the shadow maps; large boxes queued as setup records with a target
+//   k_geom_raster<CAMERA>    same for the camera -> visibility keys (depth, ~draw sequence) by 64-bit atomicMax; clip queue
+//   k_clip_raster            Sutherland-Hodgman fan for triangles straddling the viewport
+//   k_bin_* / k_tile_raster  once per frame for every queued record (camera keys and shadow maps)
+//   k_resolve00, k_shade_special   pixel (0,0) (the uncovered-pixel quirk)
+//   k_resolve_shade          key -> attributes -> Blinn-Phong + shadow lookup + gamma -> RGBA8 (image order), or
+//   k_resolve + k_shade      the same through the G-buffer (KEEP_GBUFFER, AO materials, split-phase multi-GPU frames)
 #pragma once
 #include "../../include/polyred_cuda.h"
 #include "prc_math.cuh"
@@ -18,7 +19,7 @@
 namespace prc {
 
 #define PRC_TILE 16
-#define PRC_SMALL_MAX_PIXELS 16  // bbox area up to which a triangle is rasterised by its own thread
+#define PRC_SMALL_MAX_PIXELS 16  // pixel-box area up to which a triangle goes through the CTA candidate queue (larger: tile path)
 
 struct DevScene {
   const float* pos;
@@ -288,27 +289,10 @@ __device__ __forceinline__ void emit_tri(const V4& p1, const V4& p2, const V4& p
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// K1: per-triangle transform / cull / classify, then WARP-COOPERATIVE small raster.
-//   phase A (one thread per triangle): positions staged through shared memory with 128-bit loads (the [n][9]
-//     float layout is not 16-byte aligned per triangle); transform, viewport, back-face, AABB tests, pixel box,
-//     exact-safe prune. Survivors with a small box publish a setup record in shared memory.
-//   phase B (per warp): the pixel tests of the warp's survivors are flattened (prefix sum over lanes) and dealt
-//     out 32 at a time, so lanes whose triangle was culled work on their neighbours' pixels.
-// Non-finite vertices, triangles needing clipping and big boxes leave through the generic / queue paths.
-// ---------------------------------------------------------------------------------------------
 #define PRC_GEOM_THREADS 256
 #ifndef PRC_GEOM_MIN_BLOCKS
 #define PRC_GEOM_MIN_BLOCKS 8  // 32 registers, full occupancy: measured 1.29 ms/frame vs 1.34 (6 CTAs, 40 regs) and 1.40 (5 CTAs, 48 regs); more resident CTAs hide the phase barriers
 #endif
-#define PRC_REC_STRIDE 19
-struct SmallRec {  // 18 words
-  BarySetup bs;
-  float z1, z2, z3;
-  uint32_t seq;
-  int x0, y0, bw;
-};
-
 template <bool E, bool SHADOW>
 // NOTE: takes the frame through a pointer to a DEVICE-RESIDENT copy. Passing the kernel-parameter struct by
 // reference to a non-inlined function makes every thread copy it to local memory at kernel entry (measured:
@@ -349,120 +333,7 @@ __device__ __forceinline__ bool viewport_pos_std(const float* __restrict__ vp, c
   return true;
 }
 
-// One raster pass ("view") of one triangle: transform, cull, classify, small raster (see k_geom_raster).
-template <bool E, bool SHADOW>
-__device__ __forceinline__ void geom_view(const DevScene& S, const DevFrame& F, const float* __restrict__ trans, const bool affine, const float* p,
-                                          const unsigned int tri,
-                                          unsigned long long* keys, float* smap, LargeRec* large, unsigned int large_cap, unsigned int* clipq,
-                                          unsigned int clip_cap, Counters* cnt, const DevFrame* Fg, uint32_t target, const int vr0, const int vr1) {
-  V4 ca, cb, cc;
-  if (SHADOW && affine) {
-    // last row of trans is exactly (0,0,0,1) (orthographic light camera x affine model): w = 0*x + 0*y + 0*z + 1*1 = 1
-    // for finite x,y,z; non-finite coordinates make x/y/z non-finite too and are caught by the finite test below
-    ca = mulv3(trans, p[0], p[1], p[2]); cb = mulv3(trans, p[3], p[4], p[5]); cc = mulv3(trans, p[6], p[7], p[8]);
-  } else {
-    ca = mulv(trans, V4{p[0], p[1], p[2], 1.0f});
-    cb = mulv(trans, V4{p[3], p[4], p[5], 1.0f});
-    cc = mulv(trans, V4{p[6], p[7], p[8], 1.0f});
-  }
-  V4 p1, p2, p3;
-  if (!(F.vp_std && viewport_pos_std<E>(F.viewport, ca, p1) && viewport_pos_std<E>(F.viewport, cb, p2) && viewport_pos_std<E>(F.viewport, cc, p3))) {
-    // non-standard viewport matrix or NaN / Inf / zero z,w: the literal reference sequence
-    geom_generic<E, SHADOW>(Fg, trans, S.pos, tri, keys, smap, large, large_cap, target, clipq, clip_cap, cnt, vr0, vr1);
-    return;
-  }
-  const float mag = fabsf(p1.x) + fabsf(p1.y) + fabsf(p1.z) + fabsf(p2.x) + fabsf(p2.y) + fabsf(p2.z) + fabsf(p3.x) + fabsf(p3.y) + fabsf(p3.z);
-  if (!(mag < 1e30f)) {
-    geom_generic<E, SHADOW>(Fg, trans, S.pos, tri, keys, smap, large, large_cap, target, clipq, clip_cap, cnt, vr0, vr1);
-    return;
-  }
-  // cullBackFace (render/cull.go:26-28)
-  if (fma32<E>(p2.x - p1.x, p3.y - p1.y, -((p2.y - p1.y) * (p3.x - p1.x))) < 0.0f) return;
-  // finite coordinates: Go's NaN-propagating Min/Max reduce to plain min/max (the sign of a zero is irrelevant below)
-  const float mnx = fminf(fminf(p1.x, p2.x), p3.x), mxx = fmaxf(fmaxf(p1.x, p2.x), p3.x);
-  const float mny = fminf(fminf(p1.y, p2.y), p3.y), mxy = fmaxf(fmaxf(p1.y, p2.y), p3.y);
-  const float mnz = fminf(fminf(p1.z, p2.z), p3.z), mxz = fmaxf(fmaxf(p1.z, p2.z), p3.z);
-  const float Wf = (float)F.W, Hf = (float)F.H;
-  // AABB.Intersect (box.go:32-41): max(lo) <= min(hi) per axis; the Z test compares against Max.Y = H (the Z quirk)
-  if (!(mxx >= 0.0f && mnx <= Wf && mxy >= 0.0f && mny <= Hf && mxz >= -1.0f && mnz <= Hf)) return;
-  if (!SHADOW) {
-    // AABB.Contains (box.go:61-75) is monotone per coordinate, so testing the extremes tests all three vertices
-    const bool in = less_eq(0.0f, mnx) && less_eq(0.0f, mny) && less_eq(-1.0f, mnz) && less_eq(mxx, Wf) && less_eq(mxy, Hf) && less_eq(mxz, 1.0f);
-    if (!in) {
-      unsigned int slot = warp_push(&cnt->n_clip);
-      if (slot < clip_cap) clipq[slot] = tri;
-      else atomicExch(&cnt->large_overflow, 1u);
-      return;
-    }
-  }
-  const int r0 = SHADOW ? vr0 : F.rr0, r1 = SHADOW ? vr1 : F.rr1;
-  const uint32_t seq = tri * 8u;
-  if (!SHADOW && r0 > 0) raster_pixel00<E>(p1, p2, p3, seq, keys, cnt);
-  const BarySetup bs = bary_setup<E>(p1.x, p1.y, p2.x, p2.y, p3.x, p3.y);
-  int x0, x1, y0, y1;
-  if (prune_ok(mnx, mny, mxx, mxy, bs.Sabc)) {
-    // exact-safe shrink of the AABB+-1 loop (prc_prune.h). The pruned box [ceil(min-.5-M), floor(max-.5+M)] always lies
-    // inside the reference's int(Round(min)-1) .. int(Round(max)+1), so the latter need not be computed here.
-    x0 = max(0, prune_first(mnx)); x1 = min(F.W - 1, prune_last(mxx));
-    y0 = max(r0, prune_first(mny)); y1 = min(r1 - 1, prune_last(mxy));
-  } else {
-    // pixel box int(Round(min)-1) .. int(Round(max)+1) clamped to the buffer (raster.go:473-485); clamping in float first
-    x0 = (int)fmaxf(roundf(mnx) - 1.0f, 0.0f); x1 = (int)fminf(roundf(mxx) + 1.0f, Wf - 1.0f);
-    y0 = (int)fmaxf(roundf(mny) - 1.0f, (float)r0); y1 = (int)fminf(roundf(mxy) + 1.0f, (float)(r1 - 1));
-  }
-  if (x0 > x1 || y0 > y1) return;
-  const int area = (x1 - x0 + 1) * (y1 - y0 + 1);
-  if (area > PRC_SMALL_MAX_PIXELS) {
-    unsigned int slot = warp_push(&cnt->n_large);
-    if (slot >= large_cap) { atomicExch(&cnt->large_overflow, 1u); return; }
-    LargeRec lr;
-    lr.x1 = p1.x; lr.y1 = p1.y; lr.z1 = p1.z; lr.x2 = p2.x; lr.y2 = p2.y; lr.z2 = p2.z; lr.x3 = p3.x; lr.y3 = p3.y; lr.z3 = p3.z;
-    lr.seq = seq; lr.bx0 = (short)x0; lr.by0 = (short)y0; lr.bx1 = (short)x1; lr.by1 = (short)y1; lr.target = target;
-    large[slot] = lr;
-    return;
-  }
-  // in-thread pixel loop (render/raster.go:481-499 / render/shadow.go:191-215)
-  const float thr = 2e-7f * fabsf(bs.Sabc);
-  const uint32_t sg = __float_as_uint(bs.Sabc);
-  for (int y = y0; y <= y1; y++) {
-    const float py = (float)y + 0.5f;
-    const float apy = py - bs.t1y, bpy = py - bs.t2y;
-    for (int x = x0; x <= x1; x++) {
-      const float px = (float)x + 0.5f;
-      const float apx = px - bs.t1x, bpx = px - bs.t2x;
-      if (E) {
-        // cheap certain rejection first: the single-rounding fmaf value is within 1 ulp of the reference's
-        // double-rounded one, so |S_fmaf| > 4e-7 |Sabc| with the wrong sign implies |S| > 2e-7 |Sabc| below
-        const float thr2 = thr + thr;
-        const float q0 = cross2z<false>(bs.abx, bs.aby, apx, apy), q1 = cross2z<false>(apx, apy, bs.acx, bs.acy), q2 = cross2z<false>(bs.bcx, bs.bcy, bpx, bpy);
-        if ((((__float_as_uint(q0) ^ sg) >> 31) && fabsf(q0) > thr2) || (((__float_as_uint(q1) ^ sg) >> 31) && fabsf(q1) > thr2) ||
-            (((__float_as_uint(q2) ^ sg) >> 31) && fabsf(q2) > thr2))
-          continue;
-      }
-      const float Sabp = cross2z<E>(bs.abx, bs.aby, apx, apy);
-      const float Sapc = cross2z<E>(apx, apy, bs.acx, bs.acy);
-      const float Sbcp = cross2z<E>(bs.bcx, bs.bcy, bpx, bpy);
-      // certain rejection without dividing: sign(S) != sign(Sabc) and |S| > 2e-7 |Sabc|  =>  RN(S/Sabc) < -1e-7
-      if ((((__float_as_uint(Sabp) ^ sg) >> 31) && fabsf(Sabp) > thr) || (((__float_as_uint(Sapc) ^ sg) >> 31) && fabsf(Sapc) > thr) ||
-          (((__float_as_uint(Sbcp) ^ sg) >> 31) && fabsf(Sbcp) > thr))
-        continue;
-      const float w1 = __fdiv_rn(Sbcp, bs.Sabc), w2 = __fdiv_rn(Sapc, bs.Sabc), w3 = __fdiv_rn(Sabp, bs.Sabc);
-      if (w1 < -PRC_EPS || w2 < -PRC_EPS || w3 < -PRC_EPS) continue;
-      const float z = w1 * p1.z + w2 * p2.z + w3 * p3.z;
-      if (isnan(z)) { atomicAdd(&cnt->n_nan, 1ULL); continue; }
-      const size_t idx = (size_t)y * F.W + x;
-      // fire-and-forget reductions (RED.MAX): no pre-test load, so the loop never waits on memory
-      if (SHADOW) {
-        if (z > 0.0f) atomicMax((int*)&smap[idx], __float_as_int(z));
-      } else {
-        unsigned long long key = ((unsigned long long)depth_key(z) << 32) | (unsigned long long)(0xFFFFFFFFu - seq);
-        atomicMax(&keys[idx], key);
-      }
-    }
-  }
-}
-
-// Shadow passes of several lights share one sweep over the triangles (positions are loaded and staged once).
+// Shadow passes of several lights share one sweep over the triangles (the chunk's vertices are fetched once per CTA).
 struct GeomViews {
   int n;
   uint32_t affine;  // bit v: every object's trans of view v has last row (0,0,0,1) (checked on the host)
@@ -474,54 +345,8 @@ struct GeomViews {
   int any_vis;                  // some vis[v] is set
 };
 
-template <bool E, bool SHADOW>
-__global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_raster_v1(DevScene S, DevFrame F, GeomViews V,
-                                                                     unsigned long long* keys, LargeRec* large, unsigned int large_cap,
-                                                                     unsigned int* clipq, unsigned int clip_cap, Counters* cnt, const DevFrame* Fg) {
-  // Each warp stages its own 32 triangles (32 x 36 B = 72 float4, 16-byte aligned because the warp's first
-  // triangle index is a multiple of 32) through shared memory with 128-bit loads; only __syncwarp is needed,
-  // so warps never wait for each other.
-  __shared__ __align__(16) float sp[PRC_GEOM_THREADS * 9];
-  const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
-  const unsigned long long wtri = (unsigned long long)blockIdx.x * PRC_GEOM_THREADS + wbase;  // first triangle of this warp
-  if (wtri >= S.n_tris) return;
-  // chunk culling (k_chunk_cull): skip the staging entirely when no view can be touched by this chunk
-  {
-    bool any = false;
-    const int nv = SHADOW ? V.n : 1;
-    for (int v = 0; v < nv; v++) any = any || V.vis[v] == nullptr || V.vis[v][blockIdx.x] != 0;
-    if (!any) return;
-  }
-  const unsigned long long wleft = S.n_tris - wtri;
-  const int nt = wleft < 32 ? (int)wleft : 32;
-  const unsigned int tri = (unsigned int)(wtri + lane);
-  const uint32_t meta = lane < nt ? __ldg(S.meta + tri) : 0x80000000u;
-  {
-    const float4* src = reinterpret_cast<const float4*>(S.pos + wtri * 9);
-    float4* dst = reinterpret_cast<float4*>(sp + wbase * 9);
-    const int nvec = (nt * 9) / 4;  // the scene buffer is padded, reading the last partial float4 is safe
-    for (int i = lane; i < nvec + ((nt * 9) & 3 ? 1 : 0); i += 32) dst[i] = __ldg(src + i);
-  }
-  __syncwarp();
-  if (meta & 0x80000000u) return;  // !IsValid
-  const uint32_t obj = meta & 0x00FFFFFFu;
-  // the staged positions stay in shared memory and are re-read per view (cheaper than keeping 9 registers
-  // alive across the view loop, which the 64-register cap turns into local-memory traffic)
-  const float* p = sp + threadIdx.x * 9;
-  if (SHADOW) {
-#pragma unroll 1
-    for (int v = 0; v < V.n; v++) {
-      if (V.vis[v] != nullptr && V.vis[v][blockIdx.x] == 0) continue;
-      geom_view<E, true>(S, F, V.trans[v] + (size_t)obj * 16, (V.affine >> v) & 1, p, tri, keys, V.smap[v], large, large_cap, clipq, clip_cap, cnt, Fg, V.target[v],
-                         V.r0[v], V.r1[v]);
-    }
-  } else {
-    geom_view<E, false>(S, F, F.xf[obj].trans, false, p, tri, keys, nullptr, large, large_cap, clipq, clip_cap, cnt, Fg, 0u, 0, 0);
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
-// K1 (v2): one CTA per 256-triangle chunk, three phases per view, all operands in shared memory.
+// K1: one CTA per 256-triangle chunk, three phases per view, all operands in shared memory.
 //   phase 1  the chunk's DISTINCT vertices (k_chunk_dedupe: ~0.6-0.7 per triangle instead of 3) are transformed
 //            to screen space once: Mat4.MulV + Apply(Viewport).Pos() depend only on (position, object matrix),
 //            so sharing the result between the triangles of a chunk is bit-exact;

@@ -166,6 +166,25 @@ def test_fused_resolve_shade_equals_two_kernel_path(monkeypatch, mode):
         assert np.array_equal(fused, want)
 
 
+@pytest.mark.parametrize("mode", ["exact", "mixed"])
+def test_shortcuts_equal_the_literal_sequences(monkeypatch, mode):
+    """Every arithmetic shortcut of DESIGN.md 4 switched off (plain masks, standard-viewport collapse, affine light
+    transforms, structured shadow lookup / unprojection, fused resolve+shade: all vertices then take geom_generic, the
+    literal transcription) must give the same frame as the default build of the same FMA mode; in exact mode both equal
+    the oracle bit for bit."""
+    monkeypatch.setenv("PRC_FMA", mode)
+    s, cam = synth.city_scene(n_objects=25, obj_stacks=14, obj_slices=14, ground_cells=40, tex_size=64)
+    opts = [render.Camera(cam), render.Size(480, 270), render.Scene(s), render.ShadowMap(True), render.GammaCorrection(True)]
+    fast_path = render.NewRenderer(*opts, render.CUDA(0)).Render().copy()
+    for k in ("PRC_NO_PLAIN", "PRC_NO_VPSTD", "PRC_NO_AFFINE", "PRC_NO_PERSP_CAM", "PRC_NO_UNPROJ_STD", "PRC_NO_FUSED_SHADE"):
+        monkeypatch.setenv(k, "1")
+    literal = render.NewRenderer(*opts, render.CUDA(0)).Render().copy()
+    assert np.array_equal(fast_path, literal)
+    if mode == "exact":
+        import oracle_binding as ob
+        assert np.array_equal(literal, render.NewRenderer(*opts, render._Backend(ob.OracleBackend())).Render())
+
+
 def test_candidate_queue_overflow_and_unshared_vertices(monkeypatch):
     """k_geom_raster corner cases, bit-exact against the oracle: (a) a ground of ~3-pixel cells seen from above gives every
     256-triangle chunk ~3000 candidate pixels, more than the CTA queue holds (PRC_QCAP = 2048), so part of each chunk takes
