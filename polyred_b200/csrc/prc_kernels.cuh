@@ -807,9 +807,10 @@ __device__ __forceinline__ V4 unproject_std(const DevFrame& F, const V4& p) {
   return o;
 }
 
-template <bool E, bool EA>
-__device__ void resolve_fragment(const DevScene& S, const DevFrame& F, uint32_t seq, int x, int y, Frag& f) {
-  const uint32_t tri = seq >> 3, sub = seq & 7u;
+// FAN = false: the caller guarantees seq & 7 == 0 (an unclipped triangle) and the clipper is compiled out.
+template <bool E, bool EA, bool FAN>
+__device__ __forceinline__ void resolve_fragment_impl(const DevScene& S, const DevFrame& F, uint32_t seq, int x, int y, Frag& f) {
+  const uint32_t tri = seq >> 3, sub = FAN ? (seq & 7u) : 0u;
   const uint32_t obj = S.meta[tri] & 0x00FFFFFFu;
   const float* trans = F.xf[obj].trans;
   const float* nrm = F.xf[obj].normal;
@@ -832,7 +833,7 @@ __device__ void resolve_fragment(const DevScene& S, const DevFrame& F, uint32_t 
     v[k].col = __ldg(S.col + (size_t)tri * 3 + k);
   }
   const int32_t material_id = __ldg(S.mat + tri);
-  if (sub != 0) {
+  if (FAN && sub != 0) {
     // clipTriangle (clipping.go:67-157): fan vertex attributes by screen-space barycentrics of the parent
     V4 poly[12];
     clip_polygon<E>(st, (float)F.W, (float)F.H, poly);
@@ -907,6 +908,22 @@ __device__ void resolve_fragment(const DevScene& S, const DevFrame& F, uint32_t 
   f.mat = material_id;
 }
 
+// Fragments of clipped (fan) triangles are rare; their path (Sutherland-Hodgman + re-derived attributes, ~2000
+// instructions and 400 B of local arrays) lives in one non-inlined function so that the hot kernels stay small enough for
+// the instruction cache (ncu: 22 % of k_resolve_shade's stall samples were instruction fetches). The kernels take their
+// parameter structs as __grid_constant__, so passing their addresses here does not copy them to local memory.
+template <bool E, bool EA>
+__device__ __noinline__ Frag resolve_fragment_fan(const DevScene* S, const DevFrame* F, uint32_t seq, int x, int y) {
+  Frag f;
+  resolve_fragment_impl<E, EA, true>(*S, *F, seq, x, y, f);
+  return f;
+}
+template <bool E, bool EA>
+__device__ __forceinline__ void resolve_fragment(const DevScene& S, const DevFrame& F, uint32_t seq, int x, int y, Frag& f) {
+  if (seq & 7u) f = resolve_fragment_fan<E, EA>(&S, &F, seq, x, y);
+  else resolve_fragment_impl<E, EA, false>(S, F, seq, x, y, f);
+}
+
 struct GBuf {
   float4 *ga, *gb, *gc, *gd;
   float* ao_depth;  // ok ? depth : -1 (material/ao.go:56-63)
@@ -932,7 +949,7 @@ __device__ __forceinline__ void gbuf_load(const GBuf& G, size_t idx, Frag& f) {
 #define PRC_RESOLVE_MIN_BLOCKS 8  // 64 registers: latency-bound gathers, measured 0.168 ms vs 0.198 at 88 registers
 #endif
 template <bool E, bool EA>
-__global__ void __launch_bounds__(128, PRC_RESOLVE_MIN_BLOCKS) k_resolve(DevScene S, DevFrame F, const unsigned long long* __restrict__ keys, GBuf G) {
+__global__ void __launch_bounds__(128, PRC_RESOLVE_MIN_BLOCKS) k_resolve(const __grid_constant__ DevScene S, const __grid_constant__ DevFrame F, const unsigned long long* __restrict__ keys, GBuf G) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = F.rr0 + blockIdx.y * 4 + (threadIdx.x >> 5);
   if (x >= F.W || y >= F.rr1) return;
@@ -949,7 +966,7 @@ __global__ void __launch_bounds__(128, PRC_RESOLVE_MIN_BLOCKS) k_resolve(DevScen
 }
 // pixel (0,0) when it lies outside the rasterised rows (multi-GPU strips)
 template <bool E, bool EA>
-__global__ void k_resolve00(DevScene S, DevFrame F, const unsigned long long* __restrict__ keys, GBuf G) {
+__global__ void k_resolve00(const __grid_constant__ DevScene S, const __grid_constant__ DevFrame F, const unsigned long long* __restrict__ keys, GBuf G) {
   const unsigned long long key = keys[0];
   if (key == 0) return;
   Frag f;
@@ -1247,7 +1264,7 @@ __device__ uint32_t shade_pixel(const DevScene& S, const DevFrame& F, const AoCo
 // special[0] = colour of pixel (0,0) (pre-gamma), special[1] = colour of every uncovered pixel (bug-list 3:
 // an uncovered pixel carries a zero Fragment, so shade() reads G(0,0) with MaterialID 0 — raster.go:326-332)
 template <bool E>
-__global__ void k_shade_special(DevScene S, DevFrame F, const AoConsts* __restrict__ A, const unsigned long long* __restrict__ keys, GBuf G, uint32_t* special) {
+__global__ void k_shade_special(const __grid_constant__ DevScene S, const __grid_constant__ DevFrame F, const AoConsts* __restrict__ A, const unsigned long long* __restrict__ keys, GBuf G, uint32_t* special) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (keys[0] == 0) {
     special[0] = F.background;
@@ -1267,7 +1284,7 @@ __global__ void k_shade_special(DevScene S, DevFrame F, const AoConsts* __restri
 #define PRC_SHADE_MIN_BLOCKS 8  // 64 registers: measured 0.313 ms vs 0.355 at 76 registers
 #endif
 template <bool E>
-__global__ void __launch_bounds__(128, PRC_SHADE_MIN_BLOCKS) k_shade(DevScene S, DevFrame F, const AoConsts* __restrict__ A, const unsigned long long* __restrict__ keys, GBuf G,
+__global__ void __launch_bounds__(128, PRC_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DevScene S, const __grid_constant__ DevFrame F, const AoConsts* __restrict__ A, const unsigned long long* __restrict__ keys, GBuf G,
                                                const uint32_t* __restrict__ special, uint32_t* __restrict__ image) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = F.row0 + blockIdx.y * 4 + (threadIdx.x >> 5);
@@ -1296,7 +1313,7 @@ __global__ void __launch_bounds__(128, PRC_SHADE_MIN_BLOCKS) k_shade(DevScene S,
 #define PRC_FUSED_MIN_BLOCKS 8
 #endif
 template <bool E, bool ES>
-__global__ void __launch_bounds__(128, PRC_FUSED_MIN_BLOCKS) k_resolve_shade(DevScene S, DevFrame F, const AoConsts* __restrict__ A, const unsigned long long* __restrict__ keys,
+__global__ void __launch_bounds__(128, PRC_FUSED_MIN_BLOCKS) k_resolve_shade(const __grid_constant__ DevScene S, const __grid_constant__ DevFrame F, const AoConsts* __restrict__ A, const unsigned long long* __restrict__ keys,
                                                        const uint32_t* __restrict__ special, uint32_t* __restrict__ image) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = F.row0 + blockIdx.y * 4 + (threadIdx.x >> 5);
