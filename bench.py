@@ -36,6 +36,11 @@ WORKLOADS = {
                                         n_materials=8, tex_size=256), shadow=True, gamma=True,
                desc="3840x2160, 10.0M-triangle synthetic scene (2M-tri ground heightfield + 1600 instanced 5000-tri meshes), 8 materials, "
                     "8 point lights, 4 shadow-casting, gamma"),
+    # BASELINE configs[3]; not a bench line (the bench line is C3): `--workload C4 --no-cpu-baseline` records one data point
+    "C4": dict(w=7680, h=4320, gen=dict(n_objects=18000, obj_stacks=50, obj_slices=50, ground_cells=2236, n_lights=1, casting_every=0,
+                                        n_materials=8, tex_size=256), shadow=False, gamma=False,
+               desc="7680x4320, 100.0M-triangle synthetic scene (10M-tri ground heightfield + 18000 instanced 5000-tri meshes), 8 materials, "
+                    "1 point light + ambient, no shadows, no gamma"),
     "C3-small": dict(w=960, h=540, gen=dict(n_objects=100, obj_stacks=20, obj_slices=20, ground_cells=100, n_lights=8, casting_every=2,
                                             n_materials=8, tex_size=64), shadow=True, gamma=True, desc="reduced C3 for plumbing tests"),
 }
