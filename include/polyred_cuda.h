@@ -144,7 +144,7 @@ typedef struct prc_light {
 typedef struct prc_frame {
   uint32_t abi_version;
   uint32_t flags;
-  uint32_t width, height; /* render.Size; MSAA must be 1 */
+  uint32_t width, height; /* size of the frame buffer = render.Size x MSAA (render/raster.go:149); see `msaa` */
   uint32_t n_objects;
   uint32_t n_lights;      /* light sources in Scene.Lights() order (scene/scene.go:35-47) */
   uint32_t n_ambient;
@@ -158,7 +158,9 @@ typedef struct prc_frame {
   float view_inv[16];          /* mvp.ViewInv (raster.go:244) */
   float viewport_to_world[16]; /* ViewInv.MulM(ProjInv).MulM(VPInv) (raster.go:287) */
   float cam_pos[3];            /* Camera.Position() */
-  float _pad0;
+  uint32_t msaa;               /* render.MSAA(n), 0 or 1 = off (render/options.go:66). n > 1: width/height above are n times render.Size,
+                                * the cull / clip box is n times LARGER again (the double-MSAA quirk, raster.go:416-423,438-439,
+                                * cull.go:17) and the frame handed back is imageutil.Resize()d to (width/n, height/n) (raster.go:377) */
   uint8_t gamma_lut[256];      /* u8 -> u8 table of shader.GammaCorrection (shader/gamma.go:13-18) */
   /* Multi-GPU screen partition: this ctx shades rows [row0, row1) of SCREEN y (0 = bottom,
    * buffer.go:213). row0 = 0,row1 = height on one GPU. */

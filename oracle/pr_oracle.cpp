@@ -67,6 +67,7 @@ struct Ctx {
 
   // frame state
   int W = 0, H = 0;
+  int msaa = 1;                          // render.MSAA(n): W, H above are already n times render.Size (raster.go:149)
   std::vector<Fragment> frags;           // FragmentBuffer.fragments, stored in SCREEN coords [y*W+x]
   std::vector<std::vector<f32>> shadow;  // shadowInfo.depths per light (render/shadow.go:26-31)
   std::vector<std::atomic<uint32_t>> locks;  // MT baseline only (spinlock per pixel, buffer.go:96)
@@ -309,7 +310,8 @@ void draw(Ctx& c, const FrameU& u, const Mat4& trans, const Mat4& normal, const 
   t3.pos = pos(apply(t3.pos, u.viewport));
   if (cross(sub(t2.pos, t1.pos), sub(t3.pos, t1.pos)).z < 0) return;  // cullBackFace cull.go:26-28
 
-  AABB vp{Vec3{0, 0, -1}, Vec3{(f32)c.W, (f32)c.H, 1}};  // :416-423 (MSAA=1)
+  // :416-423: Max = (MSAA*buf.Dx, MSAA*buf.Dy, 1) where buf is already MSAA times the output size (the double-MSAA quirk)
+  AABB vp{Vec3{0, 0, -1}, Vec3{(f32)(c.msaa * c.W), (f32)(c.msaa * c.H), 1}};
   AABB tb = aabb3(t1.pos, t2.pos, t3.pos);
   if (!aabb_intersect(vp, tb)) return;
   if (aabb_contains(vp, t1.pos) && aabb_contains(vp, t2.pos) && aabb_contains(vp, t3.pos)) {
@@ -318,7 +320,7 @@ void draw(Ctx& c, const FrameU& u, const Mat4& trans, const Mat4& normal, const 
   }
   Vec4 pts[3] = {t1.pos, t2.pos, t3.pos};
   Vec4 clips[16];
-  int nc = sutherland_hodgman(pts, 3, (f32)c.W, (f32)c.H, clips);
+  int nc = sutherland_hodgman(pts, 3, (f32)(c.msaa * c.W), (f32)(c.msaa * c.H), clips);  // raster.go:438-439
   for (int i = 2; i < nc; i++) {  // clipTriangle fan, clipping.go:73; parent's recipw reused (raster.go:440-443)
     Vertex a = clip_vertex(clips[0], t1, t2, t3);
     Vertex b = clip_vertex(clips[i - 1], t1, t2, t3);
@@ -333,8 +335,8 @@ void draw_depth(Ctx& c, std::vector<f32>& depths, const Mat4& strans, const Mat4
   Vec4 p2 = pos(apply(mulv(strans, t.v[1].pos), viewport));
   Vec4 p3 = pos(apply(mulv(strans, t.v[2].pos), viewport));
   if (cross(sub(p2, p1), sub(p3, p1)).z < 0) return;
-  // cullViewFrustum cull.go:15-24: NewAABB((W,H,1),(0,0,0),(0,0,-1))
-  AABB vp{Vec3{0, 0, -1}, Vec3{(f32)c.W, (f32)c.H, 1}};
+  // cullViewFrustum cull.go:15-24: NewAABB((MSAA*W,MSAA*H,1),(0,0,0),(0,0,-1))
+  AABB vp{Vec3{0, 0, -1}, Vec3{(f32)(c.msaa * c.W), (f32)(c.msaa * c.H), 1}};
   AABB tb = aabb3(p1, p2, p3);
   if (!aabb_intersect(vp, tb)) return;
   int64_t xmin = go_int(Round(tb.mn.x) - 1);
@@ -616,6 +618,67 @@ int32_t orc_shadow_reset(orc_ctx* x) {
   return PRC_OK;
 }
 
+// ---------- imageutil.Resize (internal/imageutil/resize.go:16-164), width and height both given ----------
+// createWeights8 (:146-164): int16 coefficients in [-256, 256] of the `linear` kernel (:64-70), float32 arithmetic
+static void create_weights8(int dy, int filter_length, f32 scale, std::vector<int16_t>& coeffs, std::vector<int>& start, int& flen) {
+  flen = filter_length * (int)go_int(Max2((f32)std::ceil((double)scale), 1.0f));  // math.Ceil via float64 (math/math.go)
+  const f32 filter_factor = Min2(1.0f / scale, 1.0f);
+  coeffs.assign((size_t)dy * flen, 0);
+  start.assign(dy, 0);
+  for (int y = 0; y < dy; y++) {
+    f32 interp = scale * ((f32)y + 0.5f) - 0.5f;
+    start[y] = (int)go_int(interp) - flen / 2 + 1;
+    interp -= (f32)start[y];
+    for (int i = 0; i < flen; i++) {
+      f32 in = (interp - (f32)i) * filter_factor;
+      in = Abs(in);
+      const f32 k = in <= 1 ? 1 - in : 0;          // linear
+      coeffs[(size_t)y * flen + i] = (int16_t)go_int(k * 256);
+    }
+  }
+}
+// resizeRGBA (:72-111): `in` has in_w x in_h pixels; output pixel (x, y) of the TRANSPOSED result filters input row x
+// around column start[y]; out has out_w = in_h columns and out_h = dy rows
+static void resize_pass(const uint8_t* in, int in_w, int in_h, uint8_t* out, int dy, const std::vector<int16_t>& coeffs, const std::vector<int>& start, int flen) {
+  const int maxX = in_w - 1;
+  for (int x = 0; x < in_h; x++) {
+    const uint8_t* row = in + (size_t)x * in_w * 4;
+    for (int y = 0; y < dy; y++) {
+      int32_t acc[4] = {0, 0, 0, 0}, sum = 0;
+      for (int i = 0; i < flen; i++) {
+        const int32_t coeff = coeffs[(size_t)y * flen + i];
+        if (coeff == 0) continue;
+        int xi = start[y] + i;
+        if ((unsigned)xi < (unsigned)maxX) xi *= 4;
+        else if (xi >= maxX) xi = 4 * maxX;
+        else xi = 0;
+        for (int ch = 0; ch < 4; ch++) acc[ch] += coeff * (int32_t)row[xi + ch];
+        sum += coeff;
+      }
+      uint8_t* o = out + ((size_t)y * in_h + x) * 4;
+      for (int ch = 0; ch < 4; ch++) {
+        int v = acc[ch] / sum;  // Go and C both truncate toward zero
+        o[ch] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+      }
+    }
+  }
+}
+static void resize_rgba(const uint8_t* img, int iw, int ih, uint8_t* out, int ow, int oh) {
+  if (ow == iw && oh == ih) { std::memcpy(out, img, (size_t)iw * ih * 4); return; }  // :26-28
+  const f32 scaleX = (f32)iw / (f32)ow, scaleY = (f32)ih / (f32)oh;                    // calcFactors :114-131
+  std::vector<uint8_t> temp((size_t)ih * ow * 4);                                       // transposed: ih columns, ow rows
+  std::vector<int16_t> coeffs; std::vector<int> start; int flen;
+  create_weights8(ow, 2, scaleX, coeffs, start, flen);
+  resize_pass(img, iw, ih, temp.data(), ow, coeffs, start, flen);
+  create_weights8(oh, 2, scaleY, coeffs, start, flen);
+  resize_pass(temp.data(), ih, ow, out, oh, coeffs, start, flen);
+}
+extern "C" int32_t orc_resize(const uint8_t* img, int32_t iw, int32_t ih, uint8_t* out, int32_t ow, int32_t oh) {
+  if (!img || !out || iw <= 0 || ih <= 0 || ow <= 0 || oh <= 0) return PRC_ERR_INVALID;
+  resize_rgba(img, iw, ih, out, ow, oh);
+  return PRC_OK;
+}
+
 // (*Renderer).Render (render/raster.go:155-199)
 int32_t orc_render(orc_ctx* x, const prc_frame* fr, uint8_t* rgba_out) {
   Ctx& c = x->c;
@@ -625,6 +688,8 @@ int32_t orc_render(orc_ctx* x, const prc_frame* fr, uint8_t* rgba_out) {
   auto T0 = std::chrono::steady_clock::now();
   const int W = fr->width, H = fr->height;
   const size_t npx = (size_t)W * H;
+  c.msaa = fr->msaa > 1 ? (int)fr->msaa : 1;
+  if (W % c.msaa || H % c.msaa) { c.err = "frame size is not a multiple of msaa"; return PRC_ERR_INVALID; }
   if (c.W != W || c.H != H || c.shadow.size() != fr->n_lights) {  // resetBufs + initShadowMaps
     c.W = W; c.H = H;
     c.shadow.assign(fr->n_lights, std::vector<f32>());
@@ -714,8 +779,14 @@ int32_t orc_render(orc_ctx* x, const prc_frame* fr, uint8_t* rgba_out) {
   }
   auto T3 = std::chrono::steady_clock::now();
   // buf.Image(): image row r = screen y = H-1-r (buffer.go:160-166, 225)
-  if (rgba_out)
+  if (rgba_out && c.msaa == 1)
     for (int r = 0; r < H; r++) std::memcpy(rgba_out + (size_t)r * W * 4, &color[(size_t)(H - 1 - r) * W], (size_t)W * 4);
+  if (rgba_out && c.msaa > 1) {
+    // r.outBuf = imageutil.Resize(cfg.Width, cfg.Height, CurrBuffer().Image()) (raster.go:377)
+    std::vector<uint8_t> big((size_t)W * H * 4);
+    for (int r = 0; r < H; r++) std::memcpy(big.data() + (size_t)r * W * 4, &color[(size_t)(H - 1 - r) * W], (size_t)W * 4);
+    resize_rgba(big.data(), W, H, rgba_out, W / c.msaa, H / c.msaa);
+  }
   auto ms = [](auto a, auto b) { return std::chrono::duration<float, std::milli>(b - a).count(); };
   c.tm.shadow_ms = ms(T0, T1); c.tm.forward_ms = ms(T1, T2); c.tm.shade_ms = ms(T2, T3); c.tm.total_ms = ms(T0, T3);
   return PRC_OK;

@@ -107,7 +107,7 @@ class prc_frame(C.Structure):
         ("view_inv", F16),
         ("viewport_to_world", F16),
         ("cam_pos", F3),
-        ("_pad0", C.c_float),
+        ("msaa", C.c_uint32),
         ("gamma_lut", C.c_uint8 * 256),
         ("row0", C.c_uint32),
         ("row1", C.c_uint32),

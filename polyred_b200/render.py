@@ -215,8 +215,8 @@ class Renderer:
 
     def _validate(self):
         c = self.cfg
-        if c.MSAA != 1:
-            raise NotImplementedError("render: MSAA != 1 is not on the CUDA path yet (SURVEY 8f-1)")
+        if not (1 <= c.MSAA <= 8):
+            raise ValueError("render: MSAA must be in 1..8")
         if c.BlendFunc is not None or c.Format != 0:
             raise NotImplementedError("render: Blending / PixelFormat(BGRA) are not on the CUDA path (SURVEY 8f-4)")
 
@@ -328,6 +328,7 @@ class Renderer:
         lut = imageutil.gamma_lut_u8()
         C.memmove(s.gamma_lut, lut.ctypes.data, 256)
         s.row0, s.row1 = 0, H
+        s.msaa = c.MSAA  # W, H above are the supersampled buffer (raster.go:149); the backend resizes to Width x Height (raster.go:377)
         return fd
 
     def _ensure_uploaded(self):

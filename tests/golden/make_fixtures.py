@@ -6,7 +6,8 @@ the committed outputs are what the tests read (the GPU box has no /root/referenc
                       buffer/texture_test.go (24 Texture.Query colours), math/interpolate_test.go,
                       math/mat_test.go, camera/camera_test.go, geometry/primitive/{box,triangle}_test.go
   assets/             the few small input assets those tests and the soft goldens need
-  ref_renders/        MSAA(1) renders committed in the reference (soft goldens)
+  ref_renders/        renders committed in the reference (soft goldens): MSAA(1) ground/perspect/gopher,
+                      MSAA(2) bunny (examples/out/bunny.png, internal/examples/bunny_test.go)
   scene_gopher.npz    gopher.obj as flattened by polyred_b200.model.Load (the .obj is 2.6 MB of text)
 """
 import json
@@ -101,7 +102,11 @@ def copy_assets():
     # bunny.mtl references a 0.7 MB texture the fixtures do not need: keep the material, drop the map
     mtl = open(f"{REF}/internal/testdata/bunny.mtl").read()
     open(os.path.join(HERE, "assets", "bunny.mtl"), "w").write("\n".join(l for l in mtl.splitlines() if not l.startswith("map_Kd")) + "\n")
-    for src, dst in (("examples/out/ground.png", "ground.png"), ("examples/out/perspect.png", "perspect.png"), ("examples/out/gopher.png", "gopher.png"),
+    # the textured bunny of internal/examples/bunny_test.go (MSAA(2) golden): original .mtl + its 1024x1024 texture
+    os.makedirs(os.path.join(HERE, "assets", "bunny_textured"), exist_ok=True)
+    for f in ("bunny.obj", "bunny.mtl", "bunny.png"):
+        shutil.copy(f"{REF}/internal/testdata/{f}", os.path.join(HERE, "assets", "bunny_textured", f))
+    for src, dst in (("examples/out/ground.png", "ground.png"), ("examples/out/perspect.png", "perspect.png"), ("examples/out/gopher.png", "gopher.png"), ("examples/out/bunny.png", "bunny_msaa2.png"),
                      ("examples/benchmark/shadow-0.png", "benchmark_shadow-0.png")):
         shutil.copy(f"{REF}/internal/{src}", os.path.join(HERE, "ref_renders", dst))
     # benchmark.png: only its coverage (alpha) is a usable golden (rendered by older shading code)

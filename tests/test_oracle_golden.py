@@ -85,6 +85,44 @@ def test_gopher_png():
     assert white_g > 4000 and abs(white_g - white_o) <= 0.02 * white_g  # MaterialID -1 faces pass the white vertex colour through
 
 
+def test_bunny_png_msaa2():
+    """internal/examples/bunny_test.go:21-60 -> examples/out/bunny.png: MSAA(2) (render at 1920x1080 with the double-MSAA
+    cull box, then imageutil.Resize to 960x540), textured Blinn-Phong with shininess 250, point + ambient light.
+    Alpha (coverage after the fixed-point bilinear downsample, texture alpha included) is identical in every pixel; every
+    fully covered pixel is within 1 LSB (99.4 % identical). The golden's partially covered pixels carry un-darkened RGB
+    (rendered by an older downsample), so their colour is not compared."""
+    s = scene.Scene(light.Point(intensity=200, color=(255, 255, 255, 255), position=(-200, 250, 600)), light.Ambient(intensity=0.7))
+    m = model.Load(os.path.join(A, "bunny_textured", "bunny.obj"))
+    m.Scale(1500, 1500, 1500)
+    m.Translate(-700, -5, 350)
+    s.Add(m)
+    cam = camera.Perspective(position=(-550, 194, 734), target=(-1000, 0, 0), up=(0, 1, 1), fov=45, aspect=np.float32(960) / np.float32(540), near=100, far=600)
+    r = render.NewRenderer(render.Camera(cam), render.Size(960, 540), render.Scene(s), render.MSAA(2), render.ShadowMap(True), render._Backend(ob.OracleBackend()))
+    img = r.Render()
+    gold = _golden("bunny_msaa2.png")
+    assert img.shape == gold.shape == (540, 960, 4)
+    assert np.array_equal(img[..., 3], gold[..., 3]) and int((gold[..., 3] > 0).sum()) == 133101
+    full = gold[..., 3] == 255
+    d = np.abs(img[..., :3].astype(int) - gold[..., :3].astype(int)).max(axis=2)[full]
+    assert int(full.sum()) == 129733 and int(d.max()) <= 1 and int((d > 0).sum()) <= 800
+
+
+def test_resize_restatements_agree():
+    """imageutil.Resize: the oracle's C++ restatement (orc_resize, used for the MSAA downsample) against the numpy
+    restatement that is pinned by the reference's mip-chain goldens (test_oracle_kat.py), on random images: integer
+    MSAA factors, a mip-style 2^k reduction, non-integer scales and the identity."""
+    import ctypes as C
+    from polyred_b200 import imageutil
+    L = ob.load()
+    rng = np.random.default_rng(5)
+    for (iw, ih, ow, oh) in ((64, 48, 32, 24), (96, 60, 32, 20), (128, 128, 16, 16), (100, 70, 37, 29), (50, 40, 50, 40), (33, 17, 11, 5), (40, 30, 80, 45)):
+        img = rng.integers(0, 256, size=(ih, iw, 4), dtype=np.uint8)
+        want = imageutil.resize(ow, oh, img)
+        got = np.zeros((oh, ow, 4), np.uint8)
+        assert L.orc_resize(img.ctypes.data_as(C.c_void_p), iw, ih, got.ctypes.data_as(C.c_void_p), ow, oh) == 0
+        assert np.array_equal(got, want), (iw, ih, ow, oh)
+
+
 def _benchmark_scene(center=None):
     s = scene.Scene(light.Point(intensity=7, color=(0, 0, 0, 255), position=(4, 4, 2), cast_shadow=True), light.Ambient(intensity=0.5))
     m1 = model.Load(os.path.join(A, "bunny.obj"))
