@@ -102,7 +102,7 @@ type prcFrame struct {
 	Viewport, ViewportInv, ProjInv        [16]float32
 	ViewInv, ViewportToWorld              [16]float32
 	CamPos                                [3]float32
-	_                                     float32
+	MSAA                                  uint32 // render.MSAA(n); Width/Height above are n times render.Size (raster.go:149)
 	GammaLUT                              [256]uint8
 	Row0, Row1                            uint32
 }
@@ -262,8 +262,8 @@ func (r *Renderer) renderCUDA() *image.RGBA {
 		b = openCUDA(r.cfg.cudaDevice)
 		r.cuda = b
 	}
-	if r.cfg.MSAA != 1 || r.cfg.BlendFunc != nil {
-		panic("render: CUDA backend supports MSAA(1) and no Blending")
+	if r.cfg.BlendFunc != nil {
+		panic("render: CUDA backend does not support Blending")
 	}
 	if b.uploadedFor != r.cfg.Scene {
 		b.uploadScene(r.cfg.Scene)
@@ -273,7 +273,8 @@ func (r *Renderer) renderCUDA() *image.RGBA {
 		b.check(rc, "prc_shadow_reset")
 		r.cudaShadowDirty = false
 	}
-	w, h := r.cfg.Width, r.cfg.Height
+	// the frame buffer is MSAA times render.Size (resetBufs, raster.go:149); the library resizes back (raster.go:377)
+	w, h := r.cfg.Width*r.cfg.MSAA, r.cfg.Height*r.cfg.MSAA
 	view, proj := r.cfg.Camera.ViewMatrix(), r.cfg.Camera.ProjMatrix()
 	vp := math.ViewportMatrix(float32(w), float32(h))
 	viewInv, projInv, vpInv := view.Inv(), proj.Inv(), vp.Inv()
@@ -326,7 +327,7 @@ func (r *Renderer) renderCUDA() *image.RGBA {
 		NObjects: uint32(len(objs)), NLights: uint32(len(ls)), NAmbient: uint32(len(es)), Backgrnd: rgba(r.cfg.Background),
 		Objects: unsafe.Pointer(unsafe.SliceData(objs)), Lights: unsafe.Pointer(unsafe.SliceData(lights)), Ambient: unsafe.Pointer(unsafe.SliceData(amb)),
 		Viewport: mat16(vp), ViewportInv: mat16(vpInv), ProjInv: mat16(projInv), ViewInv: mat16(viewInv),
-		ViewportToWorld: mat16(viewInv.MulM(projInv).MulM(vpInv)), Row0: 0, Row1: uint32(h)}
+		ViewportToWorld: mat16(viewInv.MulM(projInv).MulM(vpInv)), Row0: 0, Row1: uint32(h), MSAA: uint32(r.cfg.MSAA)}
 	c := r.cfg.Camera.Position()
 	f.CamPos = [3]float32{c.X, c.Y, c.Z}
 	if r.cfg.Perspect {
@@ -349,7 +350,8 @@ func (r *Renderer) renderCUDA() *image.RGBA {
 	var ptr, n uint64
 	rc, _, _ = purego.SyscallN(b.fnHostImage, b.ctx, uintptr(unsafe.Pointer(&ptr)), uintptr(unsafe.Pointer(&n)))
 	b.check(rc, "prc_host_image")
-	r.outBuf = &image.RGBA{Pix: unsafe.Slice((*uint8)(unsafe.Pointer(uintptr(ptr))), int(n)), Stride: 4 * w, Rect: image.Rect(0, 0, w, h)}
+	ow, oh := r.cfg.Width, r.cfg.Height
+	r.outBuf = &image.RGBA{Pix: unsafe.Slice((*uint8)(unsafe.Pointer(uintptr(ptr))), int(n)), Stride: 4 * ow, Rect: image.Rect(0, 0, ow, oh)}
 	r.passGPU["forward"], r.passGPU["deferred"], r.passGPU["gamma"] = true, true, true
 	return r.outBuf
 }

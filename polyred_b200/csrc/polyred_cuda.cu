@@ -70,6 +70,10 @@ struct prc_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_band[PRC_SHADE_BANDS] = {}, ev_copied = nullptr;
   uint8_t* rb_dst = nullptr;  // page-locked destination of this frame's image (nullptr: no readback)
+  // MSAA: the shaded frame is W x H = msaa x the output; k_resize writes the (W/msaa) x (H/msaa) frame that is handed back
+  int msaa = 1;
+  DBuf d_image_out, d_rz_cx, d_rz_sx, d_rz_cy, d_rz_sy;
+  int rz_key[4] = {0, 0, 0, 0}, rz_flx = 0, rz_fly = 0;
   // per-kernel-class event pairs of the current frame
   std::vector<cudaEvent_t> evpool;
   struct Span { int cls; size_t a, b; };
@@ -249,6 +253,10 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
   }
   const int W = fr->width, H = fr->height;
   const size_t npx = (size_t)W * H;
+  const int msaa = fr->msaa > 1 ? (int)fr->msaa : 1;
+  if (msaa > 8 || W % msaa || H % msaa) { ctx->err = "msaa must be 1..8 and divide the frame size"; return PRC_ERR_INVALID; }
+  if (msaa > 1 && (fr->row0 != 0 || fr->row1 != fr->height)) { ctx->err = "MSAA with a partial row range (multi-GPU strips) is not supported"; return PRC_ERR_UNSUPPORTED; }
+  ctx->msaa = msaa;
   cudaStream_t st = ctx->stream;
   if (W != ctx->W || H != ctx->H || fr->n_lights != ctx->n_lights_alloc) {
     // resetBufs + initShadowMaps: new size => fresh (zero) shadow maps
@@ -366,6 +374,7 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
   }
   ctx->uniforms_valid = true;
   F.W = W; F.H = H;
+  F.cullW = (float)(msaa * W); F.cullH = (float)(msaa * H);
   F.row0 = fr->row0; F.row1 = fr->row1;
   // AO marches up to 99 pixels from the shaded pixel (material/ao.go:44-46): widen the rasterised rows
   const int halo = ctx->any_ao ? 100 : 0;
@@ -445,6 +454,47 @@ std::vector<ShadowUnit> units_from_mask(const prc_frame* fr, uint32_t light_mask
   return u;
 }
 
+// createWeights8 (internal/imageutil/resize.go:146-164) with the `linear` kernel (:64-70): float32 arithmetic in the
+// reference's order (host code is not FMA-contracted), int16 coefficients in [-256, 256].
+static void make_weights8(int dy, int filter_length, float scale, std::vector<short>& coeffs, std::vector<int>& start, int& flen) {
+  const float cs = (float)std::ceil((double)scale);
+  flen = filter_length * (int)(cs > 1.0f ? cs : 1.0f);
+  const float inv = 1.0f / scale;
+  const float filter_factor = inv < 1.0f ? inv : 1.0f;
+  coeffs.assign((size_t)dy * flen, 0);
+  start.assign(dy, 0);
+  for (int y = 0; y < dy; y++) {
+    volatile float t = (float)y + 0.5f;
+    volatile float m = scale * t;
+    float interp = m - 0.5f;
+    start[y] = (int)interp - flen / 2 + 1;
+    interp -= (float)start[y];
+    for (int i = 0; i < flen; i++) {
+      volatile float d = interp - (float)i;
+      float in = std::fabs(d * filter_factor);
+      volatile float k = in <= 1.0f ? 1.0f - in : 0.0f;
+      coeffs[(size_t)y * flen + i] = (short)(int)(k * 256.0f);
+    }
+  }
+}
+
+// device tables of the MSAA downsample (iw x ih -> ow x oh), rebuilt only when the sizes change
+static int32_t ensure_resize_tables(prc_ctx* ctx, int iw, int ih, int ow, int oh) {
+  if (ctx->rz_key[0] == iw && ctx->rz_key[1] == ih && ctx->rz_key[2] == ow && ctx->rz_key[3] == oh) return PRC_OK;
+  std::vector<short> cx, cy;
+  std::vector<int> sx, sy;
+  make_weights8(ow, 2, (float)iw / (float)ow, cx, sx, ctx->rz_flx);  // calcFactors (:114-131) with both sizes given
+  make_weights8(oh, 2, (float)ih / (float)oh, cy, sy, ctx->rz_fly);
+  CK(cudaStreamSynchronize(ctx->stream));  // a previous frame may still read the old tables
+  UPLOAD(ctx->d_rz_cx, cx.data(), cx.size() * sizeof(short));
+  UPLOAD(ctx->d_rz_sx, sx.data(), sx.size() * sizeof(int));
+  UPLOAD(ctx->d_rz_cy, cy.data(), cy.size() * sizeof(short));
+  UPLOAD(ctx->d_rz_sy, sy.data(), sy.size() * sizeof(int));
+  CK(cudaStreamSynchronize(ctx->stream));  // the vectors above are pageable host memory
+  ctx->rz_key[0] = iw; ctx->rz_key[1] = ih; ctx->rz_key[2] = ow; ctx->rz_key[3] = oh;
+  return PRC_OK;
+}
+
 template <bool E>
 int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, int phases = 3 /* bit0: forward (+resolve), bit1: deferred */) {
   cudaStream_t st = ctx->stream;
@@ -484,7 +534,7 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, int phases
   // With a readback pending the strip is shaded in PRC_SHADE_BANDS row bands, top image rows first; each band's
   // device->host DMA runs on the copy stream while the next band is shaded (only the last band's copy is exposed).
   const int rows = F.row1 - F.row0;
-  const int nb = (ctx->rb_dst && rows >= 64 * PRC_SHADE_BANDS) ? PRC_SHADE_BANDS : 1;
+  const int nb = (ctx->rb_dst && ctx->msaa == 1 && rows >= 64 * PRC_SHADE_BANDS) ? PRC_SHADE_BANDS : 1;
   const int band = ((rows + nb - 1) / nb + 3) & ~3;
   for (int b = 0; b < nb; b++) {
     DevFrame Fb = F;
@@ -498,16 +548,28 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, int phases
     } else if (ctx->exact_shade) k_shade<true><<<sg, 128, 0, st>>>(ctx->S, Fb, aoc, keys, G, (const uint32_t*)ctx->d_special.p, (uint32_t*)ctx->d_image.p);
     else k_shade<false><<<sg, 128, 0, st>>>(ctx->S, Fb, aoc, keys, G, (const uint32_t*)ctx->d_special.p, (uint32_t*)ctx->d_image.p);
     ctx->launches++;
-    if (ctx->rb_dst) {
+    if (ctx->rb_dst && ctx->msaa == 1) {
       const size_t off = (size_t)(F.H - Fb.row1) * F.W * 4, bytes = (size_t)(Fb.row1 - Fb.row0) * F.W * 4;
       CK(cudaEventRecord(ctx->ev_band[b], st));
       CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band[b], 0));
       CK(cudaMemcpyAsync(ctx->rb_dst + off, (uint8_t*)ctx->d_image.p + off, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
     }
   }
-  if (ctx->rb_dst) {  // the frame's stream ends after the last copy
+  if (ctx->rb_dst && ctx->msaa == 1) {  // the frame's stream ends after the last copy
     CK(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
     CK(cudaStreamWaitEvent(st, ctx->ev_copied, 0));
+  }
+  if (ctx->msaa > 1) {
+    // passAntialiasing (raster.go:377): r.outBuf = imageutil.Resize(cfg.Width, cfg.Height, CurrBuffer().Image())
+    const int ow = F.W / ctx->msaa, oh = F.H / ctx->msaa;
+    int32_t rr = ensure_resize_tables(ctx, F.W, F.H, ow, oh);
+    if (rr != PRC_OK) return rr;
+    ENSURE(ctx->d_image_out, (size_t)ow * oh * 4);
+    k_resize<<<dim3((ow + 31) / 32, (oh + 7) / 8), 256, 0, st>>>((const uint32_t*)ctx->d_image.p, F.W, F.H, (uint32_t*)ctx->d_image_out.p, ow, oh,
+                                                                 (const short*)ctx->d_rz_cx.p, (const int*)ctx->d_rz_sx.p, ctx->rz_flx,
+                                                                 (const short*)ctx->d_rz_cy.p, (const int*)ctx->d_rz_sy.p, ctx->rz_fly);
+    ctx->launches++;
+    if (ctx->rb_dst) CK(cudaMemcpyAsync(ctx->rb_dst, ctx->d_image_out.p, (size_t)ow * oh * 4, cudaMemcpyDeviceToHost, st));
   }
   }
   ctx->launches += 1;
@@ -525,7 +587,8 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, int phases
 int32_t readback_begin(prc_ctx* ctx, const prc_frame* fr) {
   ctx->rb_dst = nullptr;
   if (fr->flags & PRC_FRAME_NO_READBACK) return PRC_OK;
-  const size_t total = (size_t)fr->width * fr->height * 4;
+  const uint32_t ms = fr->msaa > 1 ? fr->msaa : 1;
+  const size_t total = (size_t)(fr->width / ms) * (fr->height / ms) * 4;  // the frame handed back (after the MSAA downsample)
   if (ctx->h_img_cap < total) {
     for (auto& p : ctx->h_img) { if (p) { cudaHostUnregister(p); free(p); } p = nullptr; }
     for (auto& p : ctx->h_img) {
@@ -545,7 +608,8 @@ int32_t readback_begin(prc_ctx* ctx, const prc_frame* fr) {
 
 int32_t readback_end(prc_ctx* ctx, const DevFrame& F, uint8_t* rgba_out) {
   // image rows of the strip: screen rows [row0,row1) -> image rows [H-row1, H-row0)
-  const size_t off = (size_t)(F.H - F.row1) * F.W * 4, bytes = (size_t)(F.row1 - F.row0) * F.W * 4;
+  size_t off = (size_t)(F.H - F.row1) * F.W * 4, bytes = (size_t)(F.row1 - F.row0) * F.W * 4;
+  if (ctx->msaa > 1) { off = 0; bytes = (size_t)(F.W / ctx->msaa) * (F.H / ctx->msaa) * 4; }
   CK(cudaStreamSynchronize(ctx->stream));  // the copies were joined into the frame's stream by do_main
   if (rgba_out && ctx->rb_dst) memcpy(rgba_out + off, ctx->rb_dst + off, bytes);
   return PRC_OK;
@@ -652,7 +716,7 @@ int32_t prc_close(prc_ctx* ctx) {
   DBuf* all[] = {&ctx->d_pos, &ctx->d_nor, &ctx->d_uv, &ctx->d_col, &ctx->d_mat, &ctx->d_meta, &ctx->d_mats, &ctx->d_objstart, &ctx->d_texfirst,
                  &ctx->d_lw, &ctx->d_lh, &ctx->d_loff, &ctx->d_tex, &ctx->d_keys, &ctx->d_ga, &ctx->d_gb, &ctx->d_gc, &ctx->d_gd, &ctx->d_ao,
                  &ctx->d_image, &ctx->d_special, &ctx->d_counters, &ctx->d_large, &ctx->d_clipq, &ctx->d_tilecount, &ctx->d_tilestart, &ctx->d_cursor,
-                 &ctx->d_bins, &ctx->d_active, &ctx->d_chunksum, &ctx->d_targets, &ctx->d_frame_sh, &ctx->d_xf, &ctx->d_lights, &ctx->d_ambient, &ctx->d_gamma, &ctx->d_frame, &ctx->d_aoc, &ctx->d_chunkbox, &ctx->d_vis, &ctx->d_cverts, &ctx->d_cvoff, &ctx->d_lidx};
+                 &ctx->d_bins, &ctx->d_active, &ctx->d_chunksum, &ctx->d_targets, &ctx->d_frame_sh, &ctx->d_xf, &ctx->d_lights, &ctx->d_ambient, &ctx->d_gamma, &ctx->d_frame, &ctx->d_aoc, &ctx->d_chunkbox, &ctx->d_vis, &ctx->d_cverts, &ctx->d_cvoff, &ctx->d_lidx, &ctx->d_image_out, &ctx->d_rz_cx, &ctx->d_rz_sx, &ctx->d_rz_cy, &ctx->d_rz_sy};
   for (DBuf* b : all) free_buf(*b);
   free_buf(ctx->d_shadow_all);
   for (auto& b : ctx->d_shadow_trans) free_buf(b);
@@ -989,7 +1053,7 @@ int32_t prc_device_shadow_all(prc_ctx* ctx, uint64_t* dev_ptr, uint64_t* bytes, 
 int32_t prc_host_image(prc_ctx* ctx, uint64_t* host_ptr, uint64_t* bytes) {
   if (!ctx || !ctx->h_img[ctx->h_img_cur]) return PRC_ERR_INVALID;
   *host_ptr = (uint64_t)(uintptr_t)ctx->h_img[ctx->h_img_cur];
-  *bytes = (uint64_t)ctx->W * ctx->H * 4;
+  *bytes = (uint64_t)(ctx->W / ctx->msaa) * (ctx->H / ctx->msaa) * 4;
   return PRC_OK;
 }
 

@@ -57,7 +57,8 @@ struct DevLight {
 };
 
 struct DevFrame {
-  int W, H;
+  int W, H;        // frame buffer = render.Size x MSAA
+  float cullW, cullH;  // MSAA*W, MSAA*H: the box of the viewport cull / clip tests (the double-MSAA quirk, raster.go:416-423,438-439, cull.go:17)
   int row0, row1;  // rows shaded by this context
   int rr0, rr1;    // rows rasterised (row0/row1 widened by the AO halo)
   uint32_t flags;
@@ -305,7 +306,7 @@ __device__ __noinline__ void geom_generic(const DevFrame* __restrict__ Fg, const
   for (int i = 0; i < 9; i++) p[i] = pos[(size_t)tri * 9 + i];
   const DevFrame& F = *Fg;
   ScreenTri st;
-  int cls = tri_setup<E>(trans, F.viewport, F.pm_viewport, (float)F.W, (float)F.H, p, !SHADOW, st);
+  int cls = tri_setup<E>(trans, F.viewport, F.pm_viewport, F.cullW, F.cullH, p, !SHADOW, st);
   if (cls == TRI_CULLED) return;
   if (cls == TRI_CLIP) {
     unsigned int slot = warp_push(&cnt->n_clip);
@@ -454,7 +455,7 @@ __device__ __forceinline__ void geom_classify(const DevScene& S, const DevFrame&
   const float mnx = fminf(fminf(p1x, p2x), p3x), mxx = fmaxf(fmaxf(p1x, p2x), p3x);
   const float mny = fminf(fminf(p1y, p2y), p3y), mxy = fmaxf(fmaxf(p1y, p2y), p3y);
   const float mnz = fminf(fminf(p1z, p2z), p3z), mxz = fmaxf(fmaxf(p1z, p2z), p3z);
-  const float Wf = (float)F.W, Hf = (float)F.H;
+  const float Wf = F.cullW, Hf = F.cullH;
   // AABB.Intersect (box.go:32-41): max(lo) <= min(hi) per axis; the Z test compares against Max.Y = H (the Z quirk)
   if (!(mxx >= 0.0f && mnx <= Wf && mxy >= 0.0f && mny <= Hf && mxz >= -1.0f && mnz <= Hf)) return;
   if (!SHADOW) {
@@ -478,7 +479,7 @@ __device__ __forceinline__ void geom_classify(const DevScene& S, const DevFrame&
     y0 = max(r0, prune_first(mny)); y1 = min(r1 - 1, prune_last(mxy));
   } else {
     // pixel box int(Round(min)-1) .. int(Round(max)+1) clamped to the buffer (raster.go:473-485); clamping in float first
-    x0 = (int)fmaxf(roundf(mnx) - 1.0f, 0.0f); x1 = (int)fminf(roundf(mxx) + 1.0f, Wf - 1.0f);
+    x0 = (int)fmaxf(roundf(mnx) - 1.0f, 0.0f); x1 = (int)fminf(roundf(mxx) + 1.0f, (float)(F.W - 1));
     y0 = (int)fmaxf(roundf(mny) - 1.0f, (float)r0); y1 = (int)fminf(roundf(mxy) + 1.0f, (float)(r1 - 1));
   }
   if (x0 > x1 || y0 > y1) return;
@@ -588,9 +589,9 @@ __global__ void k_clip_raster(DevScene S, DevFrame F, const unsigned int* __rest
 #pragma unroll
   for (int k = 0; k < 9; k++) p[k] = S.pos[(size_t)tri * 9 + k];
   ScreenTri st;
-  tri_setup<E>(F.xf[obj].trans, F.viewport, F.pm_viewport, (float)F.W, (float)F.H, p, true, st);
+  tri_setup<E>(F.xf[obj].trans, F.viewport, F.pm_viewport, F.cullW, F.cullH, p, true, st);
   V4 poly[12];
-  int nc = clip_polygon<E>(st, (float)F.W, (float)F.H, poly);
+  int nc = clip_polygon<E>(st, F.cullW, F.cullH, poly);
   if (nc < 3) continue;
   float b0[3];
   clip_bary<E>(st, poly[0], b0);
@@ -818,7 +819,7 @@ __device__ __forceinline__ void resolve_fragment_impl(const DevScene& S, const D
 #pragma unroll
   for (int k = 0; k < 9; k++) p[k] = __ldg(S.pos + (size_t)tri * 9 + k);
   ScreenTri st;
-  tri_setup<E>(trans, F.viewport, F.pm_viewport, (float)F.W, (float)F.H, p, true, st);
+  tri_setup<E>(trans, F.viewport, F.pm_viewport, F.cullW, F.cullH, p, true, st);
   const bool persp = (F.flags & PRC_FRAME_PERSPECT) != 0;
   float rw1 = 1.0f, rw2 = 1.0f, rw3 = 1.0f;
   if (persp) { rw1 = __fdiv_rn(-1.0f, st.cw1); rw2 = __fdiv_rn(-1.0f, st.cw2); rw3 = __fdiv_rn(-1.0f, st.cw3); }
@@ -836,7 +837,7 @@ __device__ __forceinline__ void resolve_fragment_impl(const DevScene& S, const D
   if (FAN && sub != 0) {
     // clipTriangle (clipping.go:67-157): fan vertex attributes by screen-space barycentrics of the parent
     V4 poly[12];
-    clip_polygon<E>(st, (float)F.W, (float)F.H, poly);
+    clip_polygon<E>(st, F.cullW, F.cullH, poly);
     const int which[3] = {0, (int)sub, (int)sub + 1};
     VtxAttr c[3];
 #pragma unroll
@@ -1333,6 +1334,47 @@ __global__ void __launch_bounds__(128, PRC_FUSED_MIN_BLOCKS) k_resolve_shade(con
   if (F.flags & PRC_FRAME_GAMMA)
     col = (uint32_t)F.gamma[chan(col, 0)] | ((uint32_t)F.gamma[chan(col, 1)] << 8) | ((uint32_t)F.gamma[chan(col, 2)] << 16) | (col & 0xff000000u);
   image[(size_t)(F.H - 1 - y) * F.W + x] = col;  // image row r = screen y = H-1-r (buffer.go:225)
+}
+
+// ---------------------------------------------------------------------------------------------
+// passAntialiasing's downsample (render/raster.go:377): imageutil.Resize (internal/imageutil/resize.go:16-117), the
+// two-pass fixed-point bilinear filter, both passes in one kernel. The reference filters rows into an 8-bit TRANSPOSED
+// temporary and then filters that; the value of temporary pixel (row r, out column c) depends only on input row r, so each
+// output pixel recomputes the `fl_y` temporaries it needs (8-bit rounding and clamping included) instead of storing them.
+// Coefficients / start offsets come from createWeights8 (:146-164), computed on the host in float32 (make_weights8).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resize(const uint32_t* __restrict__ in, int iw, int ih, uint32_t* __restrict__ out, int ow, int oh,
+                                                const short* __restrict__ cx, const int* __restrict__ sx, int flx,
+                                                const short* __restrict__ cy, const int* __restrict__ sy, int fly) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= ow || y >= oh) return;
+  const int maxX = iw - 1, maxY = ih - 1;
+  int acc[4] = {0, 0, 0, 0}, sum = 0;
+  for (int j = 0; j < fly; j++) {
+    const int cj = cy[y * fly + j];
+    if (cj == 0) continue;
+    int r = sy[y] + j;  // row of the temporary = input row (resizeRGBA's index clamp, :88-95)
+    r = ((unsigned)r < (unsigned)maxY) ? r : (r >= maxY ? maxY : 0);
+    const uint32_t* row = in + (size_t)r * iw;
+    int t[4] = {0, 0, 0, 0}, ts = 0;
+    for (int i = 0; i < flx; i++) {
+      const int ci = cx[x * flx + i];
+      if (ci == 0) continue;
+      int c = sx[x] + i;
+      c = ((unsigned)c < (unsigned)maxX) ? c : (c >= maxX ? maxX : 0);
+      const uint32_t p = __ldg(row + c);
+#pragma unroll
+      for (int ch = 0; ch < 4; ch++) t[ch] += ci * (int)((p >> (8 * ch)) & 0xffu);
+      ts += ci;
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) acc[ch] += cj * min(max(t[ch] / ts, 0), 255);  // the temporary is uint8(Clamp(sum/coeffsum, 0, 255))
+    sum += cj;
+  }
+  uint32_t o = 0;
+#pragma unroll
+  for (int ch = 0; ch < 4; ch++) o |= (uint32_t)min(max(acc[ch] / sum, 0), 255) << (8 * ch);
+  out[(size_t)y * ow + x] = o;
 }
 
 // ---------------------------------------------------------------------------------------------

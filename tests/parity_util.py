@@ -7,12 +7,12 @@ import numpy as np
 from polyred_b200 import render
 
 
-def make_renderers(scene, cam, w, h, shadow=False, gamma=False, cuda_device=0, background=(0, 0, 0, 0)):
+def make_renderers(scene, cam, w, h, shadow=False, gamma=False, cuda_device=0, background=(0, 0, 0, 0), msaa=1):
     import oracle_binding as ob
     from polyred_b200._lib import CudaBackend
 
     opts = [render.Camera(cam), render.Size(w, h), render.Scene(scene), render.ShadowMap(shadow), render.GammaCorrection(gamma),
-            render.Background(background)]
+            render.Background(background), render.MSAA(msaa)]
     r_gpu = render.NewRenderer(*opts, render.CUDA(cuda_device))
     r_cpu = render.NewRenderer(*opts, render._Backend(ob.OracleBackend()))
     return r_gpu, r_cpu

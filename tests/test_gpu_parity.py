@@ -166,6 +166,25 @@ def test_fused_resolve_shade_equals_two_kernel_path(monkeypatch, mode):
         assert np.array_equal(fused, want)
 
 
+@pytest.mark.parametrize("msaa", [2, 3])
+def test_msaa_supersample_and_resize(monkeypatch, msaa):
+    """render.MSAA(n) = frame buffer n times render.Size, cull / clip box n times larger AGAIN (the
+    double-MSAA quirk: triangles up to n screens away are neither culled nor clipped), then imageutil.Resize (two-pass
+    fixed-point bilinear, k_resize) down to render.Size. The supersampled G-buffer and shadow maps and the downsampled
+    frame are bit-identical to the oracle's; the camera is close enough that part of the scene lies outside the screen."""
+    monkeypatch.setenv("PRC_FMA", "exact")
+    s, cam = synth.city_scene(n_objects=25, obj_stacks=14, obj_slices=14, ground_cells=40, tex_size=64, cam_radius=1.4, cam_height=0.6)
+    w, h = 320, 180
+    g, c = make_renderers(s, cam, w, h, shadow=True, gamma=True, msaa=msaa)
+    st, ig, ic = compare_frames(g, c, w * msaa, h * msaa, n_lights_cast=(0, 2, 4, 6))
+    _report(f"msaa{msaa}", st)
+    assert ig.shape == (h, w, 4) and ic.shape == (h, w, 4)
+    assert_bit_exact(st)
+    assert st["rgba_px_diff"] == 0, st
+    # the fused (no G-buffer) path gives the same downsampled frame
+    assert np.array_equal(g.Render(), ig)
+
+
 @pytest.mark.parametrize("mode", ["exact", "mixed"])
 def test_shortcuts_equal_the_literal_sequences(monkeypatch, mode):
     """Every arithmetic shortcut of DESIGN.md 4 switched off (plain masks, standard-viewport collapse, affine light

@@ -76,8 +76,15 @@ def test_casting_directional_light_is_an_error_not_a_guess():
 
 def test_unsupported_options_raise():
     s = scene.Scene(scene.Geometry(_tri(), materials=[material.Default()]))
+    with pytest.raises(NotImplementedError):  # not on this path
+        render.NewRenderer(render.Camera(camera.Perspective()), render.Scene(s), render.PixelFormat(1), render._Backend(ob.OracleBackend()))
     with pytest.raises(NotImplementedError):
-        render.NewRenderer(render.Camera(camera.Perspective()), render.Scene(s), render.MSAA(2), render._Backend(ob.OracleBackend()))
+        render.NewRenderer(render.Camera(camera.Perspective()), render.Scene(s), render.Blending(lambda d, s: s), render._Backend(ob.OracleBackend()))
+    with pytest.raises(ValueError):
+        render.NewRenderer(render.Camera(camera.Perspective()), render.Scene(s), render.MSAA(0), render._Backend(ob.OracleBackend()))
+    # MSAA itself is supported: the frame comes back at render.Size
+    r = render.NewRenderer(render.Camera(camera.Perspective()), render.Size(40, 30), render.Scene(s), render.MSAA(2), render._Backend(ob.OracleBackend()))
+    assert r.Render().shape == (30, 40, 4)
 
 
 def test_oracle_is_deterministic_and_mt_mode_agrees_without_ties():
