@@ -235,6 +235,7 @@ class TransformContext:
         self._rotation = Quaternion(1, 0, 0, 0)
         self._internal = identity()
         self._need = False
+        self._version = getattr(self, "_version", 0) + 1  # bumped by every mutation: lets a renderer see that a model matrix moved
 
     def ModelMatrix(self):
         if self._need:
@@ -245,10 +246,12 @@ class TransformContext:
     def Scale(self, sx, sy, sz):
         self._internal = mulm(mat4(sx, 0, 0, 0, 0, sy, 0, 0, 0, 0, sz, 0, 0, 0, 0, 1), self._internal)
         self._need = True
+        self._version += 1
 
     def Translate(self, tx, ty, tz):
         self._internal = mulm(mat4(1, 0, 0, tx, 0, 1, 0, ty, 0, 0, 1, tz, 0, 0, 0, 1), self._internal)
         self._need = True
+        self._version += 1
 
     def Rotate(self, direction, angle):
         u = v3_unit(direction)
@@ -258,6 +261,7 @@ class TransformContext:
         q = Quaternion(cosa, sina * u[0], sina * u[1], sina * u[2])
         self._rotation = q.mul(self._rotation)
         self._need = True
+        self._version += 1
 
     def RotateX(self, angle):
         self.Rotate(v3(1, 0, 0), angle)

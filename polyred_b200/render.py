@@ -254,16 +254,26 @@ class Renderer:
 
     def InvalidateScene(self):
         """Forget the flattened scene (geometry, materials, model matrices, lights): the next Render() re-flattens
-        and re-uploads it. The reference walks the scene graph every frame; this mirror caches it."""
+        and re-uploads it. Needed only after editing a vertex / material array IN PLACE: adding or removing objects and
+        moving TransformContexts are detected automatically (Scene.signature)."""
         self._scene_desc = None
 
     # -- flatten + uniforms
     def scene_desc(self) -> SceneDesc:
-        if self._scene_desc is None or self._scene_desc_for is not self.cfg.Scene:
-            self._scene_desc = SceneDesc(self.cfg.Scene)
+        """The flattened scene, cached: rebuilt (and re-uploaded) when the Scene object or its membership
+        changes; when only a TransformContext moved, just the per-object matrices are recomputed — the reference walks the
+        scene graph and rebuilds everything every frame (raster.go:241-270)."""
+        sig = self.cfg.Scene.signature()
+        sd = self._scene_desc
+        if sd is None or self._scene_desc_for is not self.cfg.Scene or sd._membership != sig[0]:
+            sd = self._scene_desc = SceneDesc(self.cfg.Scene)
+            sd._membership = sig[0]
             self._scene_desc_for = self.cfg.Scene
             self._scene_uploaded_to = None
-        return self._scene_desc
+        if getattr(sd, "_transforms", None) != sig[1]:
+            sd._static_xf = None  # recomputed by frame_desc()
+            sd._transforms = sig[1]
+        return sd
 
     def frame_desc(self, keep_gbuffer=False, no_readback=False) -> FrameDesc:
         c = self.cfg
@@ -279,8 +289,9 @@ class Renderer:
             # Model / Normal depend on the scene graph only: computed once per flattened scene (the reference
             # recomputes them every frame, raster.go:242-243; call InvalidateScene() after moving an object)
             if getattr(sd, "_static_xf", None) is None:
-                chain = np.stack([m for _, m in sd.geos])
-                own = np.stack([g.ModelMatrix() for g, _ in sd.geos])
+                geos = c.Scene.geometries()  # fresh walk: group transforms above the leaves may have moved (same leaves, Scene.signature)
+                chain = np.stack([m for _, m in geos])
+                own = np.stack([g.ModelMatrix() for g, _ in geos])
                 m_ = gm.mulm(chain, own)                   # raster.go:242
                 sd._static_xf = (m_, gm.transpose(gm.inv(m_)))  # raster.go:243
                 sd._lights = c.Scene.Lights()

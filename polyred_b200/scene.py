@@ -137,6 +137,28 @@ class Scene:
         self.IterObjects(visit)
         return src, env
 
+    def signature(self):
+        """(membership, transforms): what a renderer caches against. `membership` changes when an object is
+        added to / removed from the graph or a geometry gets new vertex arrays (=> re-flatten and re-upload); `transforms`
+        changes when any TransformContext on the way to a leaf was scaled / translated / rotated (=> only the per-object
+        matrices are recomputed; the triangle soup stays resident)."""
+        ids, ver = [], 0
+
+        def walk(g):
+            nonlocal ver
+            ver += g._version
+            ids.append(id(g))
+            for o in g.objects:
+                if isinstance(o, Group):
+                    walk(o)
+                else:
+                    ids.append(id(o))
+                    ver += getattr(o, "_version", 0)
+                    if isinstance(o, Geometry):
+                        ids.append(id(o.pos))
+        walk(self.root)
+        return hash(tuple(ids)), ver
+
     def Center(self):
         """Scene.Center (scene/scene.go:49-52): centre of the root AABB — model-space AABBs of
         ALL root objects, lights included."""

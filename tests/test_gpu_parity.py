@@ -185,6 +185,31 @@ def test_msaa_supersample_and_resize(monkeypatch, msaa):
     assert np.array_equal(g.Render(), ig)
 
 
+def test_bunny_msaa2_against_the_reference_render(monkeypatch):
+    """The CUDA path against the reference's own published MSAA(2) render (internal/examples/bunny_test.go ->
+    examples/out/bunny.png, the fixture test_oracle_golden.py pins the oracle with): alpha identical in every pixel,
+    fully covered pixels within 1 LSB — and the whole frame byte-identical to the oracle's."""
+    import oracle_binding as ob
+    from PIL import Image
+    from polyred_b200 import model
+    monkeypatch.setenv("PRC_FMA", "exact")
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    s = scene.Scene(light.Point(intensity=200, color=(255, 255, 255, 255), position=(-200, 250, 600)), light.Ambient(intensity=0.7))
+    m = model.Load(os.path.join(G, "assets", "bunny_textured", "bunny.obj"))
+    m.Scale(1500, 1500, 1500)
+    m.Translate(-700, -5, 350)
+    s.Add(m)
+    cam = camera.Perspective(position=(-550, 194, 734), target=(-1000, 0, 0), up=(0, 1, 1), fov=45, aspect=np.float32(960) / np.float32(540), near=100, far=600)
+    opts = [render.Camera(cam), render.Size(960, 540), render.Scene(s), render.MSAA(2), render.ShadowMap(True)]
+    img = render.NewRenderer(*opts, render.CUDA(0)).Render()
+    gold = np.array(Image.open(os.path.join(G, "ref_renders", "bunny_msaa2.png")))
+    assert np.array_equal(img[..., 3], gold[..., 3])
+    full = gold[..., 3] == 255
+    d = np.abs(img[..., :3].astype(int) - gold[..., :3].astype(int)).max(axis=2)[full]
+    assert int(d.max()) <= 1 and int((d > 0).sum()) <= 800
+    assert np.array_equal(img, render.NewRenderer(*opts, render._Backend(ob.OracleBackend())).Render())
+
+
 @pytest.mark.parametrize("mode", ["exact", "mixed"])
 def test_shortcuts_equal_the_literal_sequences(monkeypatch, mode):
     """Every arithmetic shortcut of DESIGN.md 4 switched off (plain masks, standard-viewport collapse, affine light

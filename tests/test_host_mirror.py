@@ -115,3 +115,38 @@ def test_view_frames_match_render_views_on_the_oracle():
         rc._backend.render(fd, out)
         assert np.array_equal(out, w)
     assert not np.array_equal(want[0], want[1])
+
+
+def test_scene_cache_tracks_transforms_and_membership():
+    """the flattened scene is uploaded once; moving a TransformContext only recomputes the per-object
+    matrices (no upload), adding an object re-flattens and re-uploads — all without InvalidateScene()."""
+    class Counting(ob.OracleBackend):
+        uploads = 0
+
+        def scene_upload(self, sd):
+            Counting.uploads += 1
+            return super().scene_upload(sd)
+
+    s, cam = synth.mesh_scene(subdiv=10)
+    be = Counting()
+    r = render.NewRenderer(render.Camera(cam), render.Size(96, 60), render.Scene(s), render._Backend(be))
+    a = r.Render().copy()
+    b = r.Render().copy()
+    assert Counting.uploads == 1 and np.array_equal(a, b)
+    geo = s.geometries()[0][0]
+    geo.Translate(0.3, 0.1, 0.0)
+    c = r.Render().copy()
+    assert Counting.uploads == 1 and not np.array_equal(a, c)          # matrices moved, soup stayed resident
+    fresh = render.NewRenderer(render.Camera(cam), render.Size(96, 60), render.Scene(s), render._Backend(ob.OracleBackend())).Render()
+    assert np.array_equal(c, fresh)                                     # same frame as a renderer that never cached
+    s.root.Scale(0.5, 0.5, 0.5)                                         # a group transform above the leaf
+    d = r.Render().copy()
+    assert Counting.uploads == 1 and not np.array_equal(c, d)
+    extra, _ = synth.mesh_scene(subdiv=6)
+    g2 = extra.geometries()[0][0]
+    g2.Translate(-0.8, 0.0, 0.0)
+    s.Add(g2)
+    e = r.Render().copy()
+    assert Counting.uploads == 2 and not np.array_equal(d, e)           # membership changed: re-flattened and re-uploaded
+    fresh = render.NewRenderer(render.Camera(cam), render.Size(96, 60), render.Scene(s), render._Backend(ob.OracleBackend())).Render()
+    assert np.array_equal(e, fresh)
