@@ -17,6 +17,7 @@ import (
 
 	"github.com/ebitengine/purego"
 
+	"poly.red/buffer"
 	"poly.red/camera"
 	"poly.red/color"
 	"poly.red/geometry"
@@ -54,6 +55,9 @@ const (
 	prcFrameGamma
 	prcFrameKeepGBuffer
 	prcFrameNoReadback
+	prcFrameUniformsResident
+	prcFrameShadowReset
+	prcFrameBGRA
 )
 
 // ---- fixed-layout mirrors of include/polyred_cuda.h (little-endian, 8-byte aligned) ----
@@ -338,6 +342,9 @@ func (r *Renderer) renderCUDA() *image.RGBA {
 	}
 	if r.cfg.GammaCorrect {
 		f.Flags |= prcFrameGamma
+	}
+	if r.cfg.Format == buffer.PixelFormatBGRA {
+		f.Flags |= prcFrameBGRA
 	}
 	for i := 0; i < 256; i++ { // shader.GammaCorrection (shader/gamma.go:13-18) as a table
 		f.GammaLUT[i] = uint8(color.FromLinear2sRGB(float32(i)/0xff)*0xff + 0.5)

@@ -70,6 +70,7 @@ extern "C" {
 #define PRC_FRAME_NO_READBACK 16u /* leave the RGBA on the device (rgba_out may be NULL) */
 #define PRC_FRAME_UNIFORMS_RESIDENT 32u /* the arrays behind objects/lights/shadow_trans/ambient/gamma are unchanged since
                                            the previous call on this ctx: skip their host->device copies (split-phase calls) */
+#define PRC_FRAME_BGRA 128u        /* render.PixelFormat(buffer.PixelFormatBGRA): colour bytes stored B,G,R,A (buffer/buffer.go:242-263) */
 #define PRC_FRAME_SHADOW_RESET 64u /* zero the shadow maps at the start of this frame, stream-ordered: what Options()
                                      * does between views (render/options.go:125-141), without prc_shadow_reset's host sync */
 

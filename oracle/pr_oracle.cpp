@@ -778,6 +778,8 @@ int32_t orc_render(orc_ctx* x, const prc_frame* fr, uint8_t* rgba_out) {
     });
   }
   auto T3 = std::chrono::steady_clock::now();
+  if (fr->flags & PRC_FRAME_BGRA)  // PixelFormatBGRA: Set() stores the colour bytes as B,G,R,A (buffer.go:242-251)
+    for (size_t j = 0; j < npx; j++) color[j] = (color[j] & 0xff00ff00u) | ((color[j] & 0xffu) << 16) | ((color[j] >> 16) & 0xffu);
   // buf.Image(): image row r = screen y = H-1-r (buffer.go:160-166, 225)
   if (rgba_out && c.msaa == 1)
     for (int r = 0; r < H; r++) std::memcpy(rgba_out + (size_t)r * W * 4, &color[(size_t)(H - 1 - r) * W], (size_t)W * 4);

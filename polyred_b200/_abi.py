@@ -28,6 +28,7 @@ PRC_FRAME_KEEP_GBUFFER = 8
 PRC_FRAME_NO_READBACK = 16
 PRC_FRAME_UNIFORMS_RESIDENT = 32
 PRC_FRAME_SHADOW_RESET = 64
+PRC_FRAME_BGRA = 128
 
 F16 = C.c_float * 16
 F3 = C.c_float * 3

@@ -1302,6 +1302,7 @@ __global__ void __launch_bounds__(128, PRC_SHADE_MIN_BLOCKS) k_shade(const __gri
   }
   if (F.flags & PRC_FRAME_GAMMA)
     col = (uint32_t)F.gamma[chan(col, 0)] | ((uint32_t)F.gamma[chan(col, 1)] << 8) | ((uint32_t)F.gamma[chan(col, 2)] << 16) | (col & 0xff000000u);
+  if (F.flags & PRC_FRAME_BGRA) col = __byte_perm(col, 0, 0x3012);  // PixelFormatBGRA: bytes B,G,R,A (buffer.go:242-251)
   image[(size_t)(F.H - 1 - y) * F.W + x] = col;  // image row r = screen y = H-1-r (buffer.go:225)
 }
 
@@ -1333,6 +1334,7 @@ __global__ void __launch_bounds__(128, PRC_FUSED_MIN_BLOCKS) k_resolve_shade(con
   }
   if (F.flags & PRC_FRAME_GAMMA)
     col = (uint32_t)F.gamma[chan(col, 0)] | ((uint32_t)F.gamma[chan(col, 1)] << 8) | ((uint32_t)F.gamma[chan(col, 2)] << 16) | (col & 0xff000000u);
+  if (F.flags & PRC_FRAME_BGRA) col = __byte_perm(col, 0, 0x3012);  // PixelFormatBGRA: bytes B,G,R,A (buffer.go:242-251)
   image[(size_t)(F.H - 1 - y) * F.W + x] = col;  // image row r = screen y = H-1-r (buffer.go:225)
 }
 

@@ -217,8 +217,10 @@ class Renderer:
         c = self.cfg
         if not (1 <= c.MSAA <= 8):
             raise ValueError("render: MSAA must be in 1..8")
-        if c.BlendFunc is not None or c.Format != 0:
-            raise NotImplementedError("render: Blending / PixelFormat(BGRA) are not on the CUDA path (SURVEY 8f-4)")
+        if c.BlendFunc is not None:
+            raise NotImplementedError("render: Blending is not on the CUDA path (SURVEY 8f-4)")
+        if c.Format not in (0, 1):
+            raise ValueError("render: PixelFormat must be PixelFormatRGBA (0) or PixelFormatBGRA (1)")
 
     # -- render/options.go:125-141
     def Options(self, *opts):
@@ -326,7 +328,7 @@ class Renderer:
         fd.keep.append(amb)
         s.flags = ((A.PRC_FRAME_PERSPECT if c.Perspect else 0) | (A.PRC_FRAME_SHADOWMAP if c.ShadowMap else 0)
                    | (A.PRC_FRAME_GAMMA if c.GammaCorrect else 0) | (A.PRC_FRAME_KEEP_GBUFFER if keep_gbuffer else 0)
-                   | (A.PRC_FRAME_NO_READBACK if no_readback else 0))
+                   | (A.PRC_FRAME_NO_READBACK if no_readback else 0) | (A.PRC_FRAME_BGRA if c.Format == 1 else 0))
         s.width, s.height = W, H
         s.n_objects, s.n_lights, s.n_ambient = nobj, len(sources), len(envs)
         s.background_rgba = A.pack_rgba(c.Background)

@@ -185,6 +185,18 @@ def test_msaa_supersample_and_resize(monkeypatch, msaa):
     assert np.array_equal(g.Render(), ig)
 
 
+def test_pixel_format_bgra():
+    """PRC_FRAME_BGRA on the CUDA path (fused and two-kernel shading, with and without MSAA) = the RGBA frame with red
+    and blue swapped, as in the oracle."""
+    s, cam = synth.city_scene(n_objects=9, obj_stacks=10, obj_slices=10, ground_cells=20, tex_size=32)
+    for msaa in (1, 2):
+        opts = [render.Camera(cam), render.Size(320, 180), render.Scene(s), render.ShadowMap(True), render.GammaCorrection(True), render.MSAA(msaa)]
+        rgba = render.NewRenderer(*opts, render.CUDA(0)).Render().copy()
+        rb = render.NewRenderer(*opts, render.PixelFormat(1), render.CUDA(0))
+        assert np.array_equal(rb.Render(), rgba[..., [2, 1, 0, 3]])
+        assert np.array_equal(rb.Render(keep_gbuffer=True), rgba[..., [2, 1, 0, 3]])
+
+
 def test_bunny_msaa2_against_the_reference_render(monkeypatch):
     """The CUDA path against the reference's own published MSAA(2) render (internal/examples/bunny_test.go ->
     examples/out/bunny.png, the fixture test_oracle_golden.py pins the oracle with): alpha identical in every pixel,

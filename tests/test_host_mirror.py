@@ -76,9 +76,9 @@ def test_casting_directional_light_is_an_error_not_a_guess():
 
 def test_unsupported_options_raise():
     s = scene.Scene(scene.Geometry(_tri(), materials=[material.Default()]))
+    with pytest.raises(ValueError):
+        render.NewRenderer(render.Camera(camera.Perspective()), render.Scene(s), render.PixelFormat(2), render._Backend(ob.OracleBackend()))
     with pytest.raises(NotImplementedError):  # not on this path
-        render.NewRenderer(render.Camera(camera.Perspective()), render.Scene(s), render.PixelFormat(1), render._Backend(ob.OracleBackend()))
-    with pytest.raises(NotImplementedError):
         render.NewRenderer(render.Camera(camera.Perspective()), render.Scene(s), render.Blending(lambda d, s: s), render._Backend(ob.OracleBackend()))
     with pytest.raises(ValueError):
         render.NewRenderer(render.Camera(camera.Perspective()), render.Scene(s), render.MSAA(0), render._Backend(ob.OracleBackend()))
@@ -150,3 +150,12 @@ def test_scene_cache_tracks_transforms_and_membership():
     assert Counting.uploads == 2 and not np.array_equal(d, e)           # membership changed: re-flattened and re-uploaded
     fresh = render.NewRenderer(render.Camera(cam), render.Size(96, 60), render.Scene(s), render._Backend(ob.OracleBackend())).Render()
     assert np.array_equal(e, fresh)
+
+
+def test_pixel_format_bgra_swaps_red_and_blue():
+    """render.PixelFormat(buffer.PixelFormatBGRA): the colour bytes are stored B,G,R,A (buffer/buffer.go:242-251)."""
+    s, cam = synth.mesh_scene(subdiv=10)
+    opts = [render.Camera(cam), render.Size(96, 60), render.Scene(s), render.GammaCorrection(True), render.MSAA(2)]
+    rgba = render.NewRenderer(*opts, render._Backend(ob.OracleBackend())).Render()
+    bgra = render.NewRenderer(*opts, render.PixelFormat(1), render._Backend(ob.OracleBackend())).Render()
+    assert np.array_equal(bgra, rgba[..., [2, 1, 0, 3]]) and not np.array_equal(bgra, rgba)
