@@ -41,6 +41,12 @@ WORKLOADS = {
                                         n_materials=8, tex_size=256), shadow=False, gamma=False,
                desc="7680x4320, 100.0M-triangle synthetic scene (10M-tri ground heightfield + 18000 instanced 5000-tri meshes), 8 materials, "
                     "1 point light + ambient, no shadows, no gamma"),
+    # BASELINE configs[0] / configs[1] (parity-test cases; `--workload C1|C2` records a data point)
+    "C1": dict(w=800, h=500, mesh=dict(subdiv=187), shadow=False, gamma=False,
+               desc="800x500, 69 938-triangle closed mesh, textured Blinn-Phong, 1 point light + ambient, no shadows"),
+    "C2": dict(w=1920, h=1080, mesh=dict(subdiv=187, with_ground=True, shadows=True, ao=True), shadow=True, gamma=True,
+               desc="1920x1080, 69 938-triangle mesh + ground quad, directional + shadow-casting point light, shadow map, "
+                    "ambient occlusion on every material, gamma"),
     "C3-small": dict(w=960, h=540, gen=dict(n_objects=100, obj_stacks=20, obj_slices=20, ground_cells=100, n_lights=8, casting_every=2,
                                             n_materials=8, tex_size=64), shadow=True, gamma=True, desc="reduced C3 for plumbing tests"),
 }
@@ -99,7 +105,10 @@ def build_scene(name):
     from polyred_b200 import synth
     wl = WORKLOADS[name]
     t = time.time()
-    s, cam = synth.city_scene(aspect=wl["w"] / wl["h"], **wl["gen"])
+    if "mesh" in wl:
+        s, cam = synth.mesh_scene(aspect=wl["w"] / wl["h"], **wl["mesh"])
+    else:
+        s, cam = synth.city_scene(aspect=wl["w"] / wl["h"], **wl["gen"])
     return wl, s, cam, time.time() - t
 
 

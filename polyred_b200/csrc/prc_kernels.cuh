@@ -1206,23 +1206,76 @@ __device__ bool shading_visibility(const DevFrame& F, const DevLight& l, const V
 
 struct AoConsts { float cosv[8], sinv[8]; float half_pi, four_pi; };
 
+// the literal arithmetic of one AO sample (ao.go:47-70) once it is known to lie inside the buffer
+__device__ __forceinline__ float ao_sample(float m, float pxf, float pyf, float cx, float cy, float elevation) {
+  const float dxv = pxf - cx, dyv = pyf - cy;
+  // Vec4.Len of (dx, dy, 0, 0): FMA(dx,dx, FMA(dy,dy, FMA(0,0, 0*0))); the inner FMA(dy,dy,0) rounds the exact product
+  // once to float64 (exact, 48 bits) and once to float32, i.e. it is the plain float32 product
+  const float dist = __fsqrt_rn(fma32<true>(dxv, dxv, dyv * dyv));
+  if (dist < 1.0f) return m;
+  return go_max(m, __fdiv_rn(elevation, dist));
+}
+// trunc(c) for 0 <= c < 2^22 without a conversion-pipe instruction: the mantissa of c + 2^23 added with round-toward-zero
+__device__ __forceinline__ int trunc_pos(float c) { return __float_as_int(__fadd_rz(c, 8388608.0f)) & 0x7FFFFF; }
+
 __device__ __forceinline__ float max_elevation(int W, int H, const float* __restrict__ ao_depth, int X, int Y, float dirX, float dirY) {
   // max over t of Atan(e_t/d_t) == Atan(max over t of e_t/d_t): Atan and the float32 rounding are monotone and
   // Go's Max is NaN-propagating on both sides, so one atan per direction reproduces ao.go:40-73 exactly.
+  // The 99 samples of a ray are filtered before the literal arithmetic (exact FMA, sqrt, IEEE divide, Go Max):
+  //   * t = 0 is the fragment itself: inside the buffer, distance 0 < 1 -> `continue` (ao.go:52-54);
+  //   * a sample that is not higher than the fragment (elevation <= 0) cannot raise the running maximum m >= 0;
+  //   * the sample distance is |dir| t up to the rounding of cur = p + dir*t on the pixel grid: |distance - t| < 7.1e-4 for
+  //     coordinates below 16384 (half an ulp, 2^-11, per axis), so for t >= 2 elevation/distance < (elevation/t) * 1.002
+  //     and a sample whose approximate quotient times 1.002 is below m cannot raise it either (RN is monotone).
+  // Only the few remaining candidates (typically the silhouette of the nearest occluder) run the literal sequence.
+  // The first `tsafe` samples cannot leave the buffer (|dir| <= 1: sample t stays within t + 1 pixels of the fragment), so
+  // they run without bounds tests and the loop can be unrolled (independent depth loads in flight).
   const float pxf = (float)X, pyf = (float)Y;
   float m = 0.0f;
-  const float traceDepth = ao_depth[(size_t)Y * W + X];
-  for (int ti = 0; ti < 100; ti++) {
-    const float t = (float)ti;
-    float cx = pxf + dirX * t, cy = pyf + dirY * t;
-    long long ix = go_int(cx), iy = go_int(cy);
-    if (ix < 0 || iy < 0 || ix >= W || iy >= H) break;
-    float dxv = pxf - cx, dyv = pyf - cy;
-    // Vec4.Len of (dx, dy, 0, 0): FMA(dx,dx, FMA(dy,dy, FMA(0,0, 0*0)))
-    float dist = __fsqrt_rn(fma32<true>(dxv, dxv, fma32<true>(dyv, dyv, 0.0f)));
-    if (dist < 1.0f) continue;
-    float elevation = ao_depth[(size_t)iy * W + ix] - traceDepth;
-    m = go_max(m, __fdiv_rn(elevation, dist));
+  const float traceDepth = ao_depth[Y * W + X];  // W*H <= 2^28
+  int tsafe = 99;
+  if (dirX > 0.0f) tsafe = min(tsafe, W - 2 - X); else if (dirX < 0.0f) tsafe = min(tsafe, X - 1);
+  if (dirY > 0.0f) tsafe = min(tsafe, H - 2 - Y); else if (dirY < 0.0f) tsafe = min(tsafe, Y - 1);
+  if (!(fabsf(dirX) <= 1.0001f && fabsf(dirY) <= 1.0001f)) tsafe = 0;  // (never for Cos/Sin; keeps the argument honest)
+  float t = 0.0f;
+  int ti = 1;
+  if (tsafe >= 1) {  // t = 1: no filter (the distance can round to just below 1)
+    t = 1.0f;
+    const float cx = pxf + dirX, cy = pyf + dirY;
+    m = ao_sample(m, pxf, pyf, cx, cy, ao_depth[trunc_pos(cy) * W + trunc_pos(cx)] - traceDepth);
+    ti = 2;
+  }
+#pragma unroll 4
+  for (; ti <= tsafe; ti++) {
+    t += 1.0f;  // exact: the reference's float32 loop counter (ao.go:46)
+    const float cx = pxf + dirX * t, cy = pyf + dirY * t;
+    const float elevation = ao_depth[trunc_pos(cy) * W + trunc_pos(cx)] - traceDepth;
+    if (elevation == elevation) {  // (a NaN elevation takes the literal path: Max propagates it)
+      if (!(elevation > 0.0f)) continue;
+      if (__fdividef(elevation, t) * 1.002f < m) continue;
+    }
+    m = ao_sample(m, pxf, pyf, cx, cy, elevation);
+  }
+  for (; ti < 100; ti++) {
+    t += 1.0f;
+    const float cx = pxf + dirX * t, cy = pyf + dirY * t;
+    int ix, iy;
+    if (fabsf(cx) < 4.0e6f && fabsf(cy) < 4.0e6f) {
+      // int(cur.X), int(cur.Y) truncate toward zero: anything <= -1 is outside the buffer, (-1, 0) maps to pixel 0
+      if (cx <= -1.0f || cy <= -1.0f) break;
+      ix = trunc_pos(fabsf(cx)); iy = trunc_pos(fabsf(cy));
+      if (ix >= W || iy >= H) break;
+    } else {
+      const long long lx = go_int(cx), ly = go_int(cy);
+      if (lx < 0 || ly < 0 || lx >= W || ly >= H) break;
+      ix = (int)lx; iy = (int)ly;
+    }
+    const float elevation = ao_depth[iy * W + ix] - traceDepth;
+    if (ti >= 2 && elevation == elevation) {
+      if (!(elevation > 0.0f)) continue;
+      if (__fdividef(elevation, t) * 1.002f < m) continue;
+    }
+    m = ao_sample(m, pxf, pyf, cx, cy, elevation);
   }
   return (float)atan((double)m);
 }
