@@ -524,13 +524,17 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, int phases
   if (ctx->exact_shade) k_resolve<E, E><<<rg, 128, 0, st>>>(ctx->S, F, keys, G); else k_resolve<E, false><<<rg, 128, 0, st>>>(ctx->S, F, keys, G);
   ctx->launches++;
   }
-  if (F.rr0 > 0 || fused) { if (ctx->exact_shade) k_resolve00<E, E><<<1, 1, 0, st>>>(ctx->S, F, keys, G); else k_resolve00<E, false><<<1, 1, 0, st>>>(ctx->S, F, keys, G); ctx->launches++; } }
+  // k_shade_special resolves pixel (0,0) itself; only a G-buffer readback needs it STORED when it lies outside the rasterised rows
+  if (F.rr0 > 0 && (fr->flags & PRC_FRAME_KEEP_GBUFFER)) {
+    if (ctx->exact_shade) k_resolve00<E, E><<<1, 1, 0, st>>>(ctx->S, F, keys, G); else k_resolve00<E, false><<<1, 1, 0, st>>>(ctx->S, F, keys, G);
+    ctx->launches++;
+  } }
   }
   if (phases & 2) {
   { KTimer kt(ctx, PRC_K_SHADE);
   const AoConsts* aoc = (const AoConsts*)ctx->d_aoc.p;
-  if (ctx->exact_shade) k_shade_special<true><<<1, 32, 0, st>>>(ctx->S, F, aoc, keys, G, (uint32_t*)ctx->d_special.p);
-  else k_shade_special<false><<<1, 32, 0, st>>>(ctx->S, F, aoc, keys, G, (uint32_t*)ctx->d_special.p);
+  if (ctx->exact_shade) k_shade_special<E, E><<<1, 32, 0, st>>>(ctx->S, F, aoc, keys, G, (uint32_t*)ctx->d_special.p);
+  else k_shade_special<E, false><<<1, 32, 0, st>>>(ctx->S, F, aoc, keys, G, (uint32_t*)ctx->d_special.p);
   // With a readback pending the strip is shaded in PRC_SHADE_BANDS row bands, top image rows first; each band's
   // device->host DMA runs on the copy stream while the next band is shaded (only the last band's copy is exposed).
   const int rows = F.row1 - F.row0;

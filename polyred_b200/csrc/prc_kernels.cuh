@@ -7,7 +7,7 @@
 //   k_geom_raster<CAMERA>    same for the camera -> visibility keys (depth, ~draw sequence) by 64-bit atomicMax; clip queue
 //   k_clip_raster            Sutherland-Hodgman fan for triangles straddling the viewport
 //   k_bin_* / k_tile_raster  once per frame for every queued record (camera keys and shadow maps)
-//   k_resolve00, k_shade_special   pixel (0,0) (the uncovered-pixel quirk)
+//   k_shade_special          pixel (0,0) (the uncovered-pixel quirk)
 //   k_resolve_shade          key -> attributes -> Blinn-Phong + shadow lookup + gamma -> RGBA8 (image order), or
 //   k_resolve + k_shade      the same through the G-buffer (KEEP_GBUFFER, AO materials, split-phase multi-GPU frames)
 #pragma once
@@ -1317,21 +1317,24 @@ __device__ uint32_t shade_pixel(const DevScene& S, const DevFrame& F, const AoCo
 
 // special[0] = colour of pixel (0,0) (pre-gamma), special[1] = colour of every uncovered pixel (bug-list 3:
 // an uncovered pixel carries a zero Fragment, so shade() reads G(0,0) with MaterialID 0 — raster.go:326-332)
-template <bool E>
+template <bool E, bool ES>
 __global__ void k_shade_special(const __grid_constant__ DevScene S, const __grid_constant__ DevFrame F, const AoConsts* __restrict__ A, const unsigned long long* __restrict__ keys, GBuf G, uint32_t* special) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  if (keys[0] == 0) {
+  const unsigned long long key = keys[0];
+  if (key == 0) {
     special[0] = F.background;
     special[1] = F.background;
     return;
   }
+  // pixel (0,0) is resolved here (not read from the G-buffer): the same values, and no dependency on a resolve kernel
   Frag info;
-  gbuf_load(G, 0, info);
+  resolve_fragment<E, ES>(S, F, 0xFFFFFFFFu - (uint32_t)key, 0, 0, info);
+  info.nor.w = 0.0f; info.facenor.w = 0.0f; info.wpos.w = 1.0f;  // what a G-buffer round trip keeps (gbuf_load)
   info.ok = true; info.X = 0; info.Y = 0;
-  uint32_t c00 = shade_pixel<E>(S, F, A, G.ao_depth, info, 0, 0, info.mat);
+  uint32_t c00 = shade_pixel<ES>(S, F, A, G.ao_depth, info, 0, 0, info.mat);
   special[0] = c00;
   info.col = c00;  // UnsafeSet wrote the shaded colour back into fragments[(0,0)] (raster_screen.go:86)
-  special[1] = shade_pixel<E>(S, F, A, G.ao_depth, info, 0, 0, 0);
+  special[1] = shade_pixel<ES>(S, F, A, G.ao_depth, info, 0, 0, 0);
 }
 
 #ifndef PRC_SHADE_MIN_BLOCKS
@@ -1363,7 +1366,7 @@ __global__ void __launch_bounds__(128, PRC_SHADE_MIN_BLOCKS) k_shade(const __gri
 // attribute gathers of k_resolve are latency bound and the shading arithmetic of k_shade is issue bound; in one kernel
 // warps in either stage cover for each other. Used when nothing needs the G-buffer afterwards: no PRC_FRAME_KEEP_GBUFFER
 // and no ambient-occlusion material (AO reads its neighbours' depths, i.e. needs every pixel resolved first). Pixel (0,0)
-// is resolved beforehand by k_resolve00 for k_shade_special. Same device functions, same values as the two-kernel path.
+// is resolved by k_shade_special itself. Same device functions, same values as the two-kernel path.
 #ifndef PRC_FUSED_MIN_BLOCKS
 #define PRC_FUSED_MIN_BLOCKS 8
 #endif
