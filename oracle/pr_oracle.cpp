@@ -9,8 +9,9 @@
 // The Go reference cannot be compiled in this image (no Go toolchain, purego module absent),
 // so this oracle is pinned (a) bottom-up by the reference's own known-answer tests
 // (tests/golden/kat_*.json extracted from math/*_test.go, buffer/texture_test.go, ...) and
-// (b) top-down by the reference's committed MSAA(1) renders (internal/examples/out/ground.png,
-// perspect.png, gopher.png) — see tests/test_oracle_golden.py.
+// (b) top-down by the reference's committed renders: MSAA(1) internal/examples/out/ground.png, perspect.png,
+// gopher.png, the MSAA(2) bunny.png (supersampling, double-MSAA cull box, imageutil.Resize) and the benchmark's
+// shadow-map dump — see tests/test_oracle_golden.py.
 // NOT pinned by any reference fixture: the AO transcendental chain (Atan/Cos/Sin/Pow(.,10000))
 // and Log2 in the LOD formula use libm where Go uses its own routines ("parity unpinned" for
 // those two).
