@@ -250,16 +250,32 @@ def run_cuda(args):
     with torch.cuda.stream(stream):
         e0.record(stream)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step(fd, None)
+    if world == 1 and args.async_frames:
+        # frames stay on the device: submit them back to back (PRC_FRAME_ASYNC), one prc_sync inside the timed bracket; the
+        # per-class kernel timings come back summed over the K frames
+        fd.struct.flags |= A.PRC_FRAME_ASYNC
+        for _ in range(args.steps):
+            step(fd, None)
+        with torch.cuda.stream(stream):
+            e1.record(stream)
+        barrier()  # be.sync() finishes the asynchronous frames (raises if a queue overflowed: warm-up sized them)
+        wall = time.perf_counter() - t0
+        fd.struct.flags &= ~A.PRC_FRAME_ASYNC
         tm = be.timings()
         ksum += np.array(list(tm.kernel_ms))
         klaunch += np.array(list(tm.kernel_launches))
         launches += int(tm.gpu_launches)
-    with torch.cuda.stream(stream):
-        e1.record(stream)
-    barrier()
-    wall = time.perf_counter() - t0
+    else:
+        for _ in range(args.steps):
+            step(fd, None)
+            tm = be.timings()
+            ksum += np.array(list(tm.kernel_ms))
+            klaunch += np.array(list(tm.kernel_launches))
+            launches += int(tm.gpu_launches)
+        with torch.cuda.stream(stream):
+            e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
     dev_ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -316,6 +332,8 @@ def run_cuda(args):
         "mpixels_per_s": px * fps / 1e6, "frames_per_s": fps, "wall_ms_per_step": wall_ms / args.steps,
         "config": {"workload": f"{args.workload}: {wl['desc']}", "n_tris": int(n_tris), "n_valid_tris": n_valid, "width": w, "height": h,
                    "fma": os.environ.get("PRC_FMA", "mixed"), "l2": "inputs (1.1 GB scene, 0.9 GB frame buffers) larger than L2; no explicit flush",
+                   "submit": ("K frames back to back (PRC_FRAME_ASYNC), one prc_sync inside the timed bracket" if (world == 1 and args.async_frames)
+                              else "one synchronous call per frame"),
                    "partition": "1 GPU" if world == 1 else f"{world} screen strips + {len(units)} shadow shards (one in-place NCCL all-gather overlapped with the camera pass, one in-place all-gather of the image strips)"},
         "roofline": {"bound": "hbm", "kernel": ("resolve_shade (k_resolve_shade, one kernel)" if (dom == 7 and one_kernel_shade) else names[dom]), "achieved": achieved, "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s",
                      "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms,
@@ -378,6 +396,8 @@ def main():
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-resident-uniforms", dest="resident_uniforms", action="store_false")
+    ap.add_argument("--no-async-frames", dest="async_frames", action="store_false",
+                    help="device-resident leg: wait for every frame (prc_render) instead of submitting the K frames back to back")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -50,6 +50,7 @@ extern "C" {
 #define PRC_ERR_UNSUPPORTED -3  /* scene/option the path does not implement (no fallback) */
 #define PRC_ERR_NO_SCENE -4
 #define PRC_ERR_NCCL -5
+#define PRC_ERR_RETRY -6        /* prc_sync after PRC_FRAME_ASYNC frames: a queue overflowed, it has been grown; submit those frames again */
 
 /* prc_material.flags (material.Standard, material/material.go:23-30) */
 #define PRC_MAT_FLAT_SHADING 1u
@@ -71,6 +72,9 @@ extern "C" {
 #define PRC_FRAME_UNIFORMS_RESIDENT 32u /* the arrays behind objects/lights/shadow_trans/ambient/gamma are unchanged since
                                            the previous call on this ctx: skip their host->device copies (split-phase calls) */
 #define PRC_FRAME_BGRA 128u        /* render.PixelFormat(buffer.PixelFormatBGRA): colour bytes stored B,G,R,A (buffer/buffer.go:242-263) */
+#define PRC_FRAME_ASYNC 256u       /* prc_render only, with PRC_FRAME_NO_READBACK: enqueue the frame and return without waiting. Completion,
+                                     * timings (summed over the frames) and the queue-overflow check happen in prc_sync(); for callers that
+                                     * keep the frames on the device (present, multi-view batches) this removes the host bubble between frames */
 #define PRC_FRAME_SHADOW_RESET 64u /* zero the shadow maps at the start of this frame, stream-ordered: what Options()
                                      * does between views (render/options.go:125-141), without prc_shadow_reset's host sync */
 
@@ -265,6 +269,8 @@ int32_t prc_render_deferred(prc_ctx* ctx, const prc_frame* frame, uint8_t* rgba_
 int32_t prc_device_shadow_all(prc_ctx* ctx, uint64_t* dev_ptr, uint64_t* bytes, uint64_t* capacity);
 /* cudaStream_t the ctx launches on (as uint64) so the host can order NCCL after it. */
 int32_t prc_stream(prc_ctx* ctx, uint64_t* stream);
+/* Waits for everything submitted on this context. After PRC_FRAME_ASYNC frames it also finishes them (prc_get_timings then
+ * reports sums over those frames) and returns PRC_ERR_RETRY if one of them overflowed an internal queue. */
 int32_t prc_sync(prc_ctx* ctx);
 
 /* Arithmetic mode of this context, overriding the PRC_FMA environment variable read by prc_open:

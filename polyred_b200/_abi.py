@@ -11,6 +11,7 @@ PRC_ERR_CUDA = -2
 PRC_ERR_UNSUPPORTED = -3
 PRC_ERR_NO_SCENE = -4
 PRC_ERR_NCCL = -5
+PRC_ERR_RETRY = -6
 
 PRC_MAT_FLAT_SHADING = 1
 PRC_MAT_AMBIENT_OCCLUSION = 2
@@ -29,6 +30,7 @@ PRC_FRAME_NO_READBACK = 16
 PRC_FRAME_UNIFORMS_RESIDENT = 32
 PRC_FRAME_SHADOW_RESET = 64
 PRC_FRAME_BGRA = 128
+PRC_FRAME_ASYNC = 256
 
 F16 = C.c_float * 16
 F3 = C.c_float * 3

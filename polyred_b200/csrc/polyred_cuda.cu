@@ -71,6 +71,7 @@ struct prc_ctx {
   cudaEvent_t ev_band[PRC_SHADE_BANDS] = {}, ev_copied = nullptr;
   uint8_t* rb_dst = nullptr;  // page-locked destination of this frame's image (nullptr: no readback)
   // MSAA: the shaded frame is W x H = msaa x the output; k_resize writes the (W/msaa) x (H/msaa) frame that is handed back
+  int pending_async = 0;  // PRC_FRAME_ASYNC frames submitted since the last finish (their spans / overflow flag are still open)
   int msaa = 1;
   DBuf d_image_out, d_rz_cx, d_rz_sx, d_rz_cy, d_rz_sy;
   int rz_key[4] = {0, 0, 0, 0}, rz_flx = 0, rz_fly = 0;
@@ -747,6 +748,7 @@ int32_t prc_set_exact_fma(prc_ctx* ctx, int32_t exact) {
 
 int32_t prc_scene_upload(prc_ctx* ctx, const prc_scene* s) {
   if (!ctx) return PRC_ERR_INVALID;
+  if (ctx->pending_async) { const int32_t pr_ = prc_sync(ctx); if (pr_ != PRC_OK) return pr_; }  // finish asynchronous frames first
   if (!s || s->abi_version != PRC_ABI_VERSION) { ctx->err = "prc_scene: bad abi_version"; return PRC_ERR_INVALID; }
   if (s->n_tris >= (1ull << 29)) { ctx->err = "too many triangles (limit 2^29)"; return PRC_ERR_UNSUPPORTED; }
   if (s->n_objects >= (1u << 24)) { ctx->err = "too many objects (limit 2^24)"; return PRC_ERR_UNSUPPORTED; }
@@ -828,6 +830,7 @@ int32_t prc_scene_upload(prc_ctx* ctx, const prc_scene* s) {
 
 int32_t prc_shadow_reset(prc_ctx* ctx) {
   if (!ctx) return PRC_ERR_INVALID;
+  if (ctx->pending_async) { const int32_t pr_ = prc_sync(ctx); if (pr_ != PRC_OK) return pr_; }  // finish asynchronous frames first
   CK(cudaSetDevice(ctx->device));
   if (ctx->d_shadow_all.p) CK(cudaMemsetAsync(ctx->d_shadow_all.p, 0, ctx->d_shadow_all.cap, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -835,6 +838,7 @@ int32_t prc_shadow_reset(prc_ctx* ctx) {
 }
 
 static int32_t render_shadow_units(prc_ctx* ctx, const prc_frame* fr, const std::vector<ShadowUnit>& units) {
+  if (ctx->pending_async) { const int32_t pr_ = prc_sync(ctx); if (pr_ != PRC_OK) return pr_; }  // finish asynchronous frames first
   CK(cudaSetDevice(ctx->device));
   DevFrame F;
   int32_t r = build_frame(ctx, fr, F);
@@ -885,6 +889,7 @@ int32_t prc_render_shadow_units(prc_ctx* ctx, const prc_frame* fr, uint32_t n, c
 
 int32_t prc_render_main(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out) {
   if (!ctx) return PRC_ERR_INVALID;
+  if (ctx->pending_async) { const int32_t pr_ = prc_sync(ctx); if (pr_ != PRC_OK) return pr_; }  // finish asynchronous frames first
   CK(cudaSetDevice(ctx->device));
   DevFrame F;
   int32_t r = build_frame(ctx, fr, F);
@@ -913,6 +918,7 @@ int32_t prc_render_main(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out) {
 //   prc_render_deferred = shading (+ optional readback), synchronises and reports timings / queue overflow
 int32_t prc_render_forward(prc_ctx* ctx, const prc_frame* fr) {
   if (!ctx) return PRC_ERR_INVALID;
+  if (ctx->pending_async) { const int32_t pr_ = prc_sync(ctx); if (pr_ != PRC_OK) return pr_; }  // finish asynchronous frames first
   CK(cudaSetDevice(ctx->device));
   DevFrame F;
   int32_t r = build_frame(ctx, fr, F);
@@ -925,6 +931,7 @@ int32_t prc_render_forward(prc_ctx* ctx, const prc_frame* fr) {
 
 int32_t prc_render_deferred(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out) {
   if (!ctx) return PRC_ERR_INVALID;
+  if (ctx->pending_async) { const int32_t pr_ = prc_sync(ctx); if (pr_ != PRC_OK) return pr_; }  // finish asynchronous frames first
   CK(cudaSetDevice(ctx->device));
   DevFrame F;
   int32_t r = build_frame(ctx, fr, F);
@@ -948,10 +955,15 @@ int32_t prc_render_deferred(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out
 // the launches of one whole frame (shadow sweeps, camera pass, tile path, resolve, shading)
 static int32_t enqueue_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F) {
   const unsigned int rec = ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
-  ctx->launches = 0;
-  ctx->spans.clear();
-  ctx->ev_used = 0;
-  CK(cudaMemsetAsync(ctx->d_counters.p, 0, offsetof(Counters, n_valid), ctx->stream));
+  if (ctx->pending_async == 0) {
+    ctx->launches = 0;
+    ctx->spans.clear();
+    ctx->ev_used = 0;
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, offsetof(Counters, n_valid), ctx->stream));
+  } else {
+    // behind unfinished asynchronous frames: keep the sticky overflow flag / statistics, reset the per-pass counters only
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 16, ctx->stream));
+  }
   CK(cudaEventRecordWithFlags(ctx->ev[0], ctx->stream, rec));
   int32_t r = ctx->exact ? do_shadows<true>(ctx, fr, F, units_from_mask(fr, 0xFFFFFFFFu, 0, F.H), false)
                          : do_shadows<false>(ctx, fr, F, units_from_mask(fr, 0xFFFFFFFFu, 0, F.H), false);
@@ -973,6 +985,18 @@ int32_t prc_render(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out) {
   if (r != PRC_OK) return r;
   // (A CUDA-graph replay of the ~35 stream operations of a frame was measured: 1.894 vs 1.886 ms — the gaps between
   // the kernels are device-side launch latency, not host enqueue time, so the frame is launched directly.)
+  if (fr->flags & PRC_FRAME_ASYNC) {
+    if (!(fr->flags & PRC_FRAME_NO_READBACK) || (fr->flags & PRC_FRAME_KEEP_GBUFFER)) { ctx->err = "PRC_FRAME_ASYNC needs PRC_FRAME_NO_READBACK and no KEEP_GBUFFER"; return PRC_ERR_INVALID; }
+    r = enqueue_frame(ctx, fr, F);
+    if (r != PRC_OK) return r;
+    ctx->pending_async++;
+    if (ctx->ev_used > 8192) return prc_sync(ctx);  // bound the timing-event pool
+    return PRC_OK;
+  }
+  if (ctx->pending_async) {  // a synchronous frame behind asynchronous ones: finish those first
+    r = prc_sync(ctx);
+    if (r != PRC_OK) return r;
+  }
   for (int attempt = 0; attempt < 4; attempt++) {
     r = enqueue_frame(ctx, fr, F);
     if (r != PRC_OK) return r;
@@ -989,6 +1013,7 @@ int32_t prc_render(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out) {
 
 int32_t prc_read_gbuffer(prc_ctx* ctx, prc_gbuffer_host* g) {
   if (!ctx || !g) return PRC_ERR_INVALID;
+  if (ctx->pending_async) { const int32_t pr_ = prc_sync(ctx); if (pr_ != PRC_OK) return pr_; }  // finish asynchronous frames first
   if (!ctx->gbuffer_valid) { ctx->err = "no G-buffer (render a frame first)"; return PRC_ERR_INVALID; }
   CK(cudaSetDevice(ctx->device));
   const size_t n = (size_t)ctx->W * ctx->H;
@@ -1019,6 +1044,7 @@ int32_t prc_read_gbuffer(prc_ctx* ctx, prc_gbuffer_host* g) {
 
 int32_t prc_read_shadowmap(prc_ctx* ctx, uint32_t light, float* out) {
   if (!ctx || !out) return PRC_ERR_INVALID;
+  if (ctx->pending_async) { const int32_t pr_ = prc_sync(ctx); if (pr_ != PRC_OK) return pr_; }  // finish asynchronous frames first
   if (light >= ctx->shadow_ptr.size() || !ctx->shadow_ptr[light]) { ctx->err = "no such shadow map"; return PRC_ERR_INVALID; }
   CK(cudaSetDevice(ctx->device));
   CK(cudaMemcpy(out, ctx->shadow_ptr[light], (size_t)ctx->W * ctx->H * 4, cudaMemcpyDeviceToHost));
@@ -1027,6 +1053,7 @@ int32_t prc_read_shadowmap(prc_ctx* ctx, uint32_t light, float* out) {
 
 int32_t prc_get_timings(prc_ctx* ctx, prc_timings* out) {
   if (!ctx || !out) return PRC_ERR_INVALID;
+  if (ctx->pending_async) { const int32_t pr_ = prc_sync(ctx); if (pr_ != PRC_OK) return pr_; }  // finish asynchronous frames first
   *out = ctx->tm;
   return PRC_OK;
 }
@@ -1070,6 +1097,12 @@ int32_t prc_stream(prc_ctx* ctx, uint64_t* stream) {
 int32_t prc_sync(prc_ctx* ctx) {
   if (!ctx) return PRC_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
+  if (ctx->pending_async) {
+    ctx->pending_async = 0;
+    const int32_t r = finish_timings(ctx);  // synchronises; timings are sums over the asynchronous frames
+    if (r == PRC_RETRY) { ctx->err = "a queue overflowed during asynchronous frames (grown now): submit them again"; return PRC_ERR_RETRY; }
+    return r;
+  }
   CK(cudaStreamSynchronize(ctx->stream));
   return PRC_OK;
 }

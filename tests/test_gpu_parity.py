@@ -295,6 +295,48 @@ def test_bin_overflow_rerenders_frame(monkeypatch):
     assert st["rgba_px_diff"] == 0, st
 
 
+def test_async_frames(monkeypatch):
+    """PRC_FRAME_ASYNC: frames that stay on the device are submitted back to back; prc_sync finishes them (timings summed),
+    the frames are the ones a synchronous render gives, and a queue overflow inside the batch surfaces as PRC_ERR_RETRY
+    with the queue grown (the resubmitted batch then succeeds)."""
+    from polyred_b200 import _abi as A
+    from polyred_b200._lib import PolyredCudaError
+    s, cam = synth.mesh_scene(subdiv=40, with_ground=True, shadows=True, ao=False)
+    opts = [render.Camera(cam), render.Size(320, 200), render.Scene(s), render.ShadowMap(True), render.GammaCorrection(True)]
+    want = render.NewRenderer(*opts, render.CUDA(0)).Render().copy()
+    r = render.NewRenderer(*opts, render.CUDA(0))
+    be = r._backend
+    r._ensure_uploaded()
+    r.Render()  # one synchronous frame sizes the queues
+    per_frame = int(be.timings().gpu_launches)
+    fd = r.frame_desc(no_readback=True)
+    fd.struct.flags |= A.PRC_FRAME_ASYNC
+    for _ in range(3):
+        be.render(fd, None)
+    be.sync()
+    tm = be.timings()
+    assert int(tm.gpu_launches) == 3 * per_frame and sum(tm.kernel_launches) > 0
+    assert np.array_equal(r.Render(), want)  # a synchronous frame after the batch: same image (shadow maps only grow)
+    # overflow inside an asynchronous batch
+    monkeypatch.setenv("PRC_BINS_INIT", "16")
+    r2 = render.NewRenderer(*opts, render.CUDA(0))
+    r2._ensure_uploaded()
+    fd2 = r2.frame_desc(no_readback=True)
+    fd2.struct.flags |= A.PRC_FRAME_ASYNC
+    for attempt in range(6):
+        r2._backend.render(fd2, None)
+        r2._backend.render(fd2, None)
+        try:
+            r2._backend.sync()
+            break
+        except PolyredCudaError as e:
+            assert e.code == A.PRC_ERR_RETRY
+    else:
+        raise AssertionError("the queues never became large enough")
+    assert attempt >= 1  # the tiny bin array did overflow at least once
+    assert np.array_equal(r2.Render(), want)
+
+
 def test_errors_surface_no_fallback():
     from polyred_b200._lib import PolyredCudaError, CudaBackend
     from polyred_b200 import _abi as A
