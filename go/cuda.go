@@ -58,6 +58,7 @@ const (
 	prcFrameUniformsResident
 	prcFrameShadowReset
 	prcFrameBGRA
+	prcFrameAsync // with prcFrameNoReadback: enqueue only; prc_sync finishes (present path / view batches)
 )
 
 // ---- fixed-layout mirrors of include/polyred_cuda.h (little-endian, 8-byte aligned) ----
