@@ -61,44 +61,79 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed regions: NVML polled every 2 ms from a thread (the nvidia-smi
+    loop of the profiling recipe buffers its output, a 30 ms timed region would see one line); falls back to nvidia-smi."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.rows, self.windows, self.gpu = [], [], gpu_index  # rows: (t, sm_mhz, max_mhz, reason bitmask)
+        self.proc = self.thread = self.nvml = None
+        self._stop = False
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def poll():
+                while not self._stop:
+                    try:
+                        self.rows.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), mx, int(get_reasons(h))))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
         except Exception:
             self.proc = None
 
     def _read(self):
+        order = (0x8, 0x40, 0x20, 0x4)
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+            r = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                mask = sum(bit for bit, v in zip(order, r[2:6]) if v.lower().startswith("active"))
+                self.rows.append((time.perf_counter(), float(r[0]), float(r[1]), mask))
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+    def window(self, t0, t1):
+        """A timed region (perf_counter interval): the statistics are taken over the samples inside the windows."""
+        self.windows.append((t0, t1))
+
+    def stop(self):
+        self._stop = True
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (NVML and nvidia-smi unavailable)"], "samples": 0}
+        inside = [r for r in self.rows if any(a <= r[0] <= b for a, b in self.windows)]
+        rows = inside or self.rows
+        mask = 0
+        for r in rows:
+            mask |= r[3]
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": max(r[2] for r in rows),
+                "reasons": [n for n, bit in self.REASONS if mask & bit], "samples": len(rows),
+                "source": ("nvml" if self.nvml else "nvidia-smi") + (", samples inside the timed regions" if inside else ", whole run (none fell inside the timed regions)")}
 
 
 def build_scene(name):
@@ -260,6 +295,7 @@ def run_cuda(args):
             e1.record(stream)
         barrier()  # be.sync() finishes the asynchronous frames (raises if a queue overflowed: warm-up sized them)
         wall = time.perf_counter() - t0
+        sampler.window(t0, t0 + wall)
         fd.struct.flags &= ~A.PRC_FRAME_ASYNC
         tm = be.timings()
         ksum += np.array(list(tm.kernel_ms))
@@ -276,6 +312,7 @@ def run_cuda(args):
             e1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
+        sampler.window(t0, t0 + wall)
     dev_ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
 
