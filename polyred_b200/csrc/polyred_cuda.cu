@@ -499,86 +499,90 @@ static int32_t ensure_resize_tables(prc_ctx* ctx, int iw, int ih, int ow, int oh
 template <bool E>
 int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, int phases = 3 /* bit0: forward (+resolve), bit1: deferred */) {
   cudaStream_t st = ctx->stream;
-  const size_t npx = (size_t)F.W * F.H;
+  const unsigned long long* keys = (const unsigned long long*)ctx->d_keys.p;
+  const uint32_t* special = (const uint32_t*)ctx->d_special.p;
+  uint32_t* image = (uint32_t*)ctx->d_image.p;
+  const AoConsts* aoc = (const AoConsts*)ctx->d_aoc.p;
+  GBuf G{(float4*)ctx->d_ga.p, (float4*)ctx->d_gb.p, (float4*)ctx->d_gc.p, (float4*)ctx->d_gd.p, ctx->any_ao ? (float*)ctx->d_ao.p : nullptr};
+  // one kernel for resolve + shading when nothing reads the G-buffer afterwards (k_resolve_shade)
+  const bool fused = phases == 3 && !(fr->flags & PRC_FRAME_KEEP_GBUFFER) && !ctx->any_ao && getenv("PRC_NO_FUSED_SHADE") == nullptr;
+  const bool es = ctx->exact_shade;  // exact FMA in the shading-only arithmetic too (PRC_FMA=exact)
+
   if (phases & 1) {
     // clear the visibility keys of the rasterised rows (+ pixel (0,0))
     CK(cudaMemsetAsync((unsigned long long*)ctx->d_keys.p + (size_t)F.rr0 * F.W, 0, (size_t)(F.rr1 - F.rr0) * F.W * 8, st));
     if (F.rr0 > 0) CK(cudaMemsetAsync(ctx->d_keys.p, 0, 8, st));
-  }
-  (void)npx;
-  // one kernel for resolve + shading when nothing reads the G-buffer afterwards (k_resolve_shade)
-  const bool no_fused = getenv("PRC_NO_FUSED_SHADE") != nullptr;
-  const bool fused = phases == 3 && !(fr->flags & PRC_FRAME_KEEP_GBUFFER) && !ctx->any_ao && !no_fused;
-  GBuf G{(float4*)ctx->d_ga.p, (float4*)ctx->d_gb.p, (float4*)ctx->d_gc.p, (float4*)ctx->d_gd.p, ctx->any_ao ? (float*)ctx->d_ao.p : nullptr};
-  const unsigned long long* keys = (const unsigned long long*)ctx->d_keys.p;
-  if (phases & 1) {
-  GeomViews V0{};
-  V0.n = 1;
-  int32_t r = raster_pass<E, false>(ctx, F, V0);
-  if (r != PRC_OK) return r;
-  r = flush_large<E>(ctx, F);  // also rasterises what the shadow passes of this frame queued
-  if (r != PRC_OK) return r;
-  CK(cudaEventRecordWithFlags(ctx->ev[2], st, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
-  dim3 rg((F.W + 31) / 32, (F.rr1 - F.rr0 + 3) / 4);
-  { KTimer kt(ctx, PRC_K_RESOLVE);
-  if (!fused) {
-  if (ctx->exact_shade) k_resolve<E, E><<<rg, 128, 0, st>>>(ctx->S, F, keys, G); else k_resolve<E, false><<<rg, 128, 0, st>>>(ctx->S, F, keys, G);
-  ctx->launches++;
-  }
-  // k_shade_special resolves pixel (0,0) itself; only a G-buffer readback needs it STORED when it lies outside the rasterised rows
-  if (F.rr0 > 0 && (fr->flags & PRC_FRAME_KEEP_GBUFFER)) {
-    if (ctx->exact_shade) k_resolve00<E, E><<<1, 1, 0, st>>>(ctx->S, F, keys, G); else k_resolve00<E, false><<<1, 1, 0, st>>>(ctx->S, F, keys, G);
-    ctx->launches++;
-  } }
-  }
-  if (phases & 2) {
-  { KTimer kt(ctx, PRC_K_SHADE);
-  const AoConsts* aoc = (const AoConsts*)ctx->d_aoc.p;
-  if (ctx->exact_shade) k_shade_special<E, E><<<1, 32, 0, st>>>(ctx->S, F, aoc, keys, G, (uint32_t*)ctx->d_special.p);
-  else k_shade_special<E, false><<<1, 32, 0, st>>>(ctx->S, F, aoc, keys, G, (uint32_t*)ctx->d_special.p);
-  // With a readback pending the strip is shaded in PRC_SHADE_BANDS row bands, top image rows first; each band's
-  // device->host DMA runs on the copy stream while the next band is shaded (only the last band's copy is exposed).
-  const int rows = F.row1 - F.row0;
-  const int nb = (ctx->rb_dst && ctx->msaa == 1 && rows >= 64 * PRC_SHADE_BANDS) ? PRC_SHADE_BANDS : 1;
-  const int band = ((rows + nb - 1) / nb + 3) & ~3;
-  for (int b = 0; b < nb; b++) {
-    DevFrame Fb = F;
-    Fb.row1 = F.row1 - b * band;  // image row r = screen y = H-1-r: the highest screen rows are the first image rows
-    Fb.row0 = std::max(F.row0, Fb.row1 - band);
-    if (Fb.row0 >= Fb.row1) break;
-    dim3 sg((F.W + 31) / 32, (Fb.row1 - Fb.row0 + 3) / 4);
-    if (fused) {
-      if (ctx->exact_shade) k_resolve_shade<E, E><<<sg, 128, 0, st>>>(ctx->S, Fb, aoc, keys, (const uint32_t*)ctx->d_special.p, (uint32_t*)ctx->d_image.p);
-      else k_resolve_shade<E, false><<<sg, 128, 0, st>>>(ctx->S, Fb, aoc, keys, (const uint32_t*)ctx->d_special.p, (uint32_t*)ctx->d_image.p);
-    } else if (ctx->exact_shade) k_shade<true><<<sg, 128, 0, st>>>(ctx->S, Fb, aoc, keys, G, (const uint32_t*)ctx->d_special.p, (uint32_t*)ctx->d_image.p);
-    else k_shade<false><<<sg, 128, 0, st>>>(ctx->S, Fb, aoc, keys, G, (const uint32_t*)ctx->d_special.p, (uint32_t*)ctx->d_image.p);
-    ctx->launches++;
-    if (ctx->rb_dst && ctx->msaa == 1) {
-      const size_t off = (size_t)(F.H - Fb.row1) * F.W * 4, bytes = (size_t)(Fb.row1 - Fb.row0) * F.W * 4;
-      CK(cudaEventRecord(ctx->ev_band[b], st));
-      CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band[b], 0));
-      CK(cudaMemcpyAsync(ctx->rb_dst + off, (uint8_t*)ctx->d_image.p + off, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    GeomViews V0{};
+    V0.n = 1;
+    int32_t r = raster_pass<E, false>(ctx, F, V0);
+    if (r != PRC_OK) return r;
+    r = flush_large<E>(ctx, F);  // also rasterises what the shadow passes of this frame queued
+    if (r != PRC_OK) return r;
+    CK(cudaEventRecordWithFlags(ctx->ev[2], st, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
+    KTimer kt(ctx, PRC_K_RESOLVE);
+    if (!fused) {
+      const dim3 rg((F.W + 31) / 32, (F.rr1 - F.rr0 + 3) / 4);
+      if (es) k_resolve<E, E><<<rg, 128, 0, st>>>(ctx->S, F, keys, G);
+      else k_resolve<E, false><<<rg, 128, 0, st>>>(ctx->S, F, keys, G);
+      ctx->launches++;
+    }
+    // k_shade_special resolves pixel (0,0) itself; only a G-buffer readback needs it STORED when it lies outside the rasterised rows
+    if (F.rr0 > 0 && (fr->flags & PRC_FRAME_KEEP_GBUFFER)) {
+      if (es) k_resolve00<E, E><<<1, 1, 0, st>>>(ctx->S, F, keys, G);
+      else k_resolve00<E, false><<<1, 1, 0, st>>>(ctx->S, F, keys, G);
+      ctx->launches++;
     }
   }
-  if (ctx->rb_dst && ctx->msaa == 1) {  // the frame's stream ends after the last copy
-    CK(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
-    CK(cudaStreamWaitEvent(st, ctx->ev_copied, 0));
-  }
-  if (ctx->msaa > 1) {
-    // passAntialiasing (raster.go:377): r.outBuf = imageutil.Resize(cfg.Width, cfg.Height, CurrBuffer().Image())
-    const int ow = F.W / ctx->msaa, oh = F.H / ctx->msaa;
-    int32_t rr = ensure_resize_tables(ctx, F.W, F.H, ow, oh);
-    if (rr != PRC_OK) return rr;
-    ENSURE(ctx->d_image_out, (size_t)ow * oh * 4);
-    k_resize<<<dim3((ow + 31) / 32, (oh + 7) / 8), 256, 0, st>>>((const uint32_t*)ctx->d_image.p, F.W, F.H, (uint32_t*)ctx->d_image_out.p, ow, oh,
-                                                                 (const short*)ctx->d_rz_cx.p, (const int*)ctx->d_rz_sx.p, ctx->rz_flx,
-                                                                 (const short*)ctx->d_rz_cy.p, (const int*)ctx->d_rz_sy.p, ctx->rz_fly);
+
+  if (phases & 2) {
+    KTimer kt(ctx, PRC_K_SHADE);
+    if (es) k_shade_special<E, E><<<1, 32, 0, st>>>(ctx->S, F, aoc, keys, G, (uint32_t*)ctx->d_special.p);
+    else k_shade_special<E, false><<<1, 32, 0, st>>>(ctx->S, F, aoc, keys, G, (uint32_t*)ctx->d_special.p);
     ctx->launches++;
-    if (ctx->rb_dst) CK(cudaMemcpyAsync(ctx->rb_dst, ctx->d_image_out.p, (size_t)ow * oh * 4, cudaMemcpyDeviceToHost, st));
-  }
-  }
-  ctx->launches += 1;
-  ctx->gbuffer_valid = !fused;
+    // With a readback pending the strip is shaded in PRC_SHADE_BANDS row bands, top image rows first; each band's
+    // device->host DMA runs on the copy stream while the next band is shaded (only the last band's copy is exposed).
+    const bool banded_copy = ctx->rb_dst && ctx->msaa == 1;
+    const int rows = F.row1 - F.row0;
+    const int nb = (banded_copy && rows >= 64 * PRC_SHADE_BANDS) ? PRC_SHADE_BANDS : 1;
+    const int band = ((rows + nb - 1) / nb + 3) & ~3;
+    for (int b = 0; b < nb; b++) {
+      DevFrame Fb = F;
+      Fb.row1 = F.row1 - b * band;  // image row r = screen y = H-1-r: the highest screen rows are the first image rows
+      Fb.row0 = std::max(F.row0, Fb.row1 - band);
+      if (Fb.row0 >= Fb.row1) break;
+      const dim3 sg((F.W + 31) / 32, (Fb.row1 - Fb.row0 + 3) / 4);
+      if (fused) {
+        if (es) k_resolve_shade<E, E><<<sg, 128, 0, st>>>(ctx->S, Fb, aoc, keys, special, image);
+        else k_resolve_shade<E, false><<<sg, 128, 0, st>>>(ctx->S, Fb, aoc, keys, special, image);
+      } else {
+        if (es) k_shade<true><<<sg, 128, 0, st>>>(ctx->S, Fb, aoc, keys, G, special, image);
+        else k_shade<false><<<sg, 128, 0, st>>>(ctx->S, Fb, aoc, keys, G, special, image);
+      }
+      ctx->launches++;
+      if (banded_copy) {
+        const size_t off = (size_t)(F.H - Fb.row1) * F.W * 4, bytes = (size_t)(Fb.row1 - Fb.row0) * F.W * 4;
+        CK(cudaEventRecord(ctx->ev_band[b], st));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band[b], 0));
+        CK(cudaMemcpyAsync(ctx->rb_dst + off, (uint8_t*)ctx->d_image.p + off, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+      }
+    }
+    if (banded_copy) {  // the frame's stream ends after the last copy
+      CK(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+      CK(cudaStreamWaitEvent(st, ctx->ev_copied, 0));
+    }
+    if (ctx->msaa > 1) {
+      // passAntialiasing (raster.go:377): r.outBuf = imageutil.Resize(cfg.Width, cfg.Height, CurrBuffer().Image())
+      const int ow = F.W / ctx->msaa, oh = F.H / ctx->msaa;
+      const int32_t rr = ensure_resize_tables(ctx, F.W, F.H, ow, oh);
+      if (rr != PRC_OK) return rr;
+      ENSURE(ctx->d_image_out, (size_t)ow * oh * 4);
+      k_resize<<<dim3((ow + 31) / 32, (oh + 7) / 8), 256, 0, st>>>(image, F.W, F.H, (uint32_t*)ctx->d_image_out.p, ow, oh,
+                                                                   (const short*)ctx->d_rz_cx.p, (const int*)ctx->d_rz_sx.p, ctx->rz_flx,
+                                                                   (const short*)ctx->d_rz_cy.p, (const int*)ctx->d_rz_sy.p, ctx->rz_fly);
+      ctx->launches++;
+      if (ctx->rb_dst) CK(cudaMemcpyAsync(ctx->rb_dst, ctx->d_image_out.p, (size_t)ow * oh * 4, cudaMemcpyDeviceToHost, st));
+    }
+    ctx->gbuffer_valid = !fused;
   }
   CK(cudaGetLastError());
   return PRC_OK;
