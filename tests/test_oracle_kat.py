@@ -226,3 +226,56 @@ def test_fragment_shader_equivalence(oracle_lib):
         ref = _kernels_shade_float64(k, n, p, k["texture_rgba"])
         assert max(abs(a - b) for a, b in zip(cpu, ref)) <= 1, (n, p, cpu, ref)
         assert (got >> 24) == 255
+
+
+# ---- more of the reference's own known-answer tests, transcribed with their expected values ----
+def test_transform_context_model_matrices():
+    """math/context_test.go:13-82 (TestTransformationContext): scale, translate, re-scale, quarter turns about Y / X / Z."""
+    ctx = gm.TransformContext()
+    ctx.Scale(1, 2, 3)
+    ctx.Translate(1, 2, 3)
+    assert mat_eq(ctx.ModelMatrix(), gm.mat4(1, 0, 0, 1, 0, 2, 0, 2, 0, 0, 3, 3, 0, 0, 0, 1))
+    ctx.Scale(1, 2, 3)
+    assert mat_eq(ctx.ModelMatrix(), gm.mat4(1, 0, 0, 1, 0, 4, 0, 4, 0, 0, 9, 9, 0, 0, 0, 1))
+    half_pi = np.float32(math.pi / 2)
+    for axis, want in (((0, 1, 0), (0, 0, 1, 0, 0, 1, 0, 0, -1, 0, 0, 0, 0, 0, 0, 1)),
+                       ((1, 0, 0), (1, 0, 0, 0, 0, 0, -1, 0, 0, 1, 0, 0, 0, 0, 0, 1)),
+                       ((0, 0, 1), (0, -1, 0, 0, 1, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1))):
+        ctx.ResetContext()
+        ctx.Rotate(gm.v3(*axis), half_pi)
+        assert mat_eq(ctx.ModelMatrix(), gm.mat4(*want)), axis
+
+
+def test_quaternion_to_rotation_matrix():
+    """math/quaternion_test.go:13-70 (TestQuaternionToRotationMatrix): pi/3 about X, Y, Z."""
+    angle = np.float32(math.pi) / np.float32(3)
+    c, s = np.float32(math.cos(float(angle * np.float32(0.5)))), np.float32(math.sin(float(angle * np.float32(0.5))))
+    h = np.float32(0.8660254)
+    for u, want in (((1, 0, 0), (1, 0, 0, 0, 0, 0.5, -h, 0, 0, h, 0.5, 0, 0, 0, 0, 1)),
+                    ((0, 1, 0), (0.5, 0, h, 0, 0, 1, 0, 0, -h, 0, 0.5, 0, 0, 0, 0, 1)),
+                    ((0, 0, 1), (0.5, -h, 0, 0, h, 0.5, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1))):
+        q = gm.Quaternion(c, s * np.float32(u[0]), s * np.float32(u[1]), s * np.float32(u[2]))
+        assert mat_eq(q.to_romat(), gm.mat4(*want)), u
+
+
+def test_vec4_apply_dot_cross_unit_oracle_and_host(oracle_lib):
+    """math/vec_test.go: TestVec_Apply (:383-396), TestVec_Dot (:180-189), TestVec_Cross (:409-418), TestVec_Len/Unit
+    (:303-316, 337-351) for Vec4 - the operations every kernel is built from - on the oracle's restatement and the host mirror."""
+    L = oracle_lib
+    out4 = (C.c_float * 4)()
+    m = f32a(1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16)
+    L.orc_vec4_apply(fptr(f32a(1, 1, 1, 1)), fptr(m), out4)
+    assert list(out4) == [10, 26, 42, 58]
+    assert list(gm.v4_apply(np.array([1, 1, 1, 1], np.float32), gm.mat4(*range(1, 17)))) == [10, 26, 42, 58]
+    d = C.c_float()
+    L.orc_vec4_dot(fptr(f32a(1, 1, 2, 5)), fptr(f32a(2, 2, 2, 5)), C.byref(d))
+    assert d.value == 33.0
+    L.orc_vec4_cross(fptr(f32a(1, 0, 0, 0)), fptr(f32a(0, 1, 0, 0)), out4)
+    assert list(out4) == [0, 0, 1, 0]
+    assert list(gm.v3_cross(gm.v3(1, 0, 0), gm.v3(0, 1, 0))) == [0, 0, 1]
+    L.orc_vec4_unit(fptr(f32a(1, 1, 1, 0)), out4)
+    r3 = np.float32(1) / np.float32(math.sqrt(3.0))
+    assert mat_eq(list(out4), [r3, r3, r3, 0])
+    L.orc_vec4_unit(fptr(f32a(1, 1, 1, 1)), out4)
+    assert mat_eq(list(out4), [0.5, 0.5, 0.5, 0.5])
+    assert mat_eq(gm.v3_unit(gm.v3(1, 1, 1)), [r3, r3, r3])
