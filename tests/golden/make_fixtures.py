@@ -106,7 +106,7 @@ def copy_assets():
     os.makedirs(os.path.join(HERE, "assets", "bunny_textured"), exist_ok=True)
     for f in ("bunny.obj", "bunny.mtl", "bunny.png"):
         shutil.copy(f"{REF}/internal/testdata/{f}", os.path.join(HERE, "assets", "bunny_textured", f))
-    for src, dst in (("examples/out/ground.png", "ground.png"), ("examples/out/perspect.png", "perspect.png"), ("examples/out/gopher.png", "gopher.png"), ("examples/out/bunny.png", "bunny_msaa2.png"),
+    for src, dst in (("examples/out/ground.png", "ground.png"), ("examples/out/perspect.png", "perspect.png"), ("examples/out/gopher.png", "gopher.png"), ("examples/out/bunny.png", "bunny_msaa2.png"), ("examples/out/shadow.png", "shadow_msaa2.png"),
                      ("examples/benchmark/shadow-0.png", "benchmark_shadow-0.png")):
         shutil.copy(f"{REF}/internal/{src}", os.path.join(HERE, "ref_renders", dst))
     # benchmark.png: only its coverage (alpha) is a usable golden (rendered by older shading code)
