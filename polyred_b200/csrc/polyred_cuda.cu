@@ -163,7 +163,7 @@ uint32_t plain_mask(const float* m) {
 
 inline unsigned int cdiv(unsigned long long a, unsigned int b) { return (unsigned int)((a + b - 1) / b); }
 
-// ---- one raster pass (camera or one shadow light): geometry + in-thread small raster; large triangles and
+// ---- one raster pass (camera, or up to 8 shadow views in one sweep): geometry + small raster through the CTA queue; large triangles and
 // (camera only) triangles needing clipping are queued. No host round trip. -----------------------------------
 template <bool E, bool SHADOW>
 int32_t raster_pass(prc_ctx* ctx, const DevFrame& F, const GeomViews& Vin) {
@@ -763,7 +763,7 @@ int32_t prc_scene_upload(prc_ctx* ctx, const prc_scene* s) {
   CK(cudaSetDevice(ctx->device));
   ctx->has_scene = false;
   const uint64_t n = s->n_tris;
-  ENSURE(ctx->d_pos, n * 36 + 16);  // +16: the float4 staging loop may read up to the next 16-byte boundary
+  ENSURE(ctx->d_pos, n * 36 + 16);  // (+16: slack for vectorised reads of the last triangle)
   UPLOAD(ctx->d_pos, s->pos, n * 36);
   UPLOAD(ctx->d_nor, s->nor, n * 36);
   UPLOAD(ctx->d_uv, s->uv, n * 24);

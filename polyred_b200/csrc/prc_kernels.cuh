@@ -225,7 +225,7 @@ __device__ __forceinline__ V4 clip_pos(const ScreenTri& t, const float b[3]) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// in-thread rasterisation of one (small) screen triangle
+// rasterisation of one screen triangle's pixel box by the calling thread (clipped fans, pixel (0,0), queue-overflow fallback)
 // ---------------------------------------------------------------------------------------------
 template <bool E, bool SHADOW>
 __device__ __forceinline__ void raster_one(const BarySetup& bs, const V4& p1, const V4& p2, const V4& p3, int x0, int y0, int x1, int y1, uint32_t seq, int W,
