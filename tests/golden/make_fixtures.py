@@ -97,7 +97,7 @@ def extract_kats():
 def copy_assets():
     os.makedirs(os.path.join(HERE, "assets"), exist_ok=True)
     os.makedirs(os.path.join(HERE, "ref_renders"), exist_ok=True)
-    for f in ("ground.obj", "ground.mtl", "ground.png", "perspect.obj", "perspect.mtl", "uvgrid2.png", "bunny.obj", "pic.jpg"):
+    for f in ("ground.obj", "ground.mtl", "ground.png", "perspect.obj", "perspect.mtl", "uvgrid2.png", "bunny.obj", "pic.jpg", "dragon.obj"):
         shutil.copy(f"{REF}/internal/testdata/{f}", os.path.join(HERE, "assets", f))
     # bunny.mtl references a 0.7 MB texture the fixtures do not need: keep the material, drop the map
     mtl = open(f"{REF}/internal/testdata/bunny.mtl").read()
@@ -106,7 +106,7 @@ def copy_assets():
     os.makedirs(os.path.join(HERE, "assets", "bunny_textured"), exist_ok=True)
     for f in ("bunny.obj", "bunny.mtl", "bunny.png"):
         shutil.copy(f"{REF}/internal/testdata/{f}", os.path.join(HERE, "assets", "bunny_textured", f))
-    for src, dst in (("examples/out/ground.png", "ground.png"), ("examples/out/perspect.png", "perspect.png"), ("examples/out/gopher.png", "gopher.png"), ("examples/out/bunny.png", "bunny_msaa2.png"), ("examples/out/shadow.png", "shadow_msaa2.png"),
+    for src, dst in (("examples/out/ground.png", "ground.png"), ("examples/out/perspect.png", "perspect.png"), ("examples/out/gopher.png", "gopher.png"), ("examples/out/bunny.png", "bunny_msaa2.png"), ("examples/out/shadow.png", "shadow_msaa2.png"), ("examples/out/dragon.png", "dragon_msaa2.png"),
                      ("examples/benchmark/shadow-0.png", "benchmark_shadow-0.png")):
         shutil.copy(f"{REF}/internal/{src}", os.path.join(HERE, "ref_renders", dst))
     # benchmark.png: only its coverage (alpha) is a usable golden (rendered by older shading code)

@@ -136,6 +136,27 @@ def test_shadow_png_msaa2_two_casting_lights():
     assert int((d > 2).sum()) <= 4500 and int((d > 4).sum()) <= 200 and int((d > 8).sum()) <= 10
 
 
+def test_dragon_png_msaa2_normalized_group():
+    """internal/examples/dragon_test.go:18-60 -> examples/out/dragon.png: 9 266-face mesh without a .mtl (default
+    material), Scale/Translate then Group.Normalize (scene/group.go:47-64), 30-degree camera, MSAA(2). Alpha identical in
+    every pixel; every fully covered pixel within 3 LSB, 75 % identical."""
+    s = scene.Scene(light.Point(intensity=2, color=(255, 255, 255, 255), position=(-1.5, -1, 1)), light.Ambient(intensity=0.5))
+    m = model.Load(os.path.join(A, "dragon.obj"))
+    m.Scale(1.5, 1.5, 1.5)
+    m.Translate(0, -0.1, -0.15)
+    m.Normalize()
+    s.Add(m)
+    cam = camera.Perspective(position=(-3, 1.25, -2), target=(0, -0.1, -0.1), up=(0, 1, 0), fov=30, aspect=1, near=0.01, far=1000)
+    r = render.NewRenderer(render.Camera(cam), render.Size(500, 500), render.Scene(s), render.MSAA(2), render.ShadowMap(False),
+                           render._Backend(ob.OracleBackend(threads=4)))
+    img = r.Render()
+    gold = _golden("dragon_msaa2.png")
+    assert np.array_equal(img[..., 3], gold[..., 3]) and int((gold[..., 3] > 0).sum()) == 60133
+    full = gold[..., 3] == 255
+    d = np.abs(img[..., :3].astype(int) - gold[..., :3].astype(int)).max(axis=2)[full]
+    assert int(full.sum()) == 56081 and int(d.max()) <= 3 and int((d > 1).sum()) <= 1000 and int((d > 0).sum()) <= 15000
+
+
 def test_resize_restatements_agree():
     """imageutil.Resize: the oracle's C++ restatement (orc_resize, used for the MSAA downsample) against the numpy
     restatement that is pinned by the reference's mip-chain goldens (test_oracle_kat.py), on random images: integer
