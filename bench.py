@@ -180,7 +180,7 @@ def run_reference(args):
     sec = float(np.mean(times))
     val = tm.n_valid_tris / sec / 1e6
     line = {
-        "impl": "reference", "metric": "Mtris/s", "value": val, "unit": "Mtris/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": "Mtris/s", "value": val, "unit": "Mtris/s", "n_gpus": args.gpus, "gpus_used": 0, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "mpixels_per_s": w * h / sec / 1e6,
         "config": {"workload": f"{args.workload}: {wl['desc']}", "n_valid_tris": int(tm.n_valid_tris)},
