@@ -6,8 +6,10 @@ the committed outputs are what the tests read (the GPU box has no /root/referenc
                       buffer/texture_test.go (24 Texture.Query colours), math/interpolate_test.go,
                       math/mat_test.go, camera/camera_test.go, geometry/primitive/{box,triangle}_test.go
   assets/             the few small input assets those tests and the soft goldens need
-  ref_renders/        renders committed in the reference (soft goldens): MSAA(1) ground/perspect/gopher,
-                      MSAA(2) bunny (examples/out/bunny.png, internal/examples/bunny_test.go)
+  ref_renders/        renders committed in the reference (soft goldens): MSAA(1) ground / perspect / gopher
+                      (internal/examples/{ground,perspect,gopher}_test.go), MSAA(2) bunny / shadow / dragon
+                      (internal/examples/{bunny,shadow,dragon}_test.go), the benchmark's shadow-map dump and coverage
+                      (internal/examples/benchmark/)
   scene_gopher.npz    gopher.obj as flattened by polyred_b200.model.Load (the .obj is 2.6 MB of text)
 """
 import json
