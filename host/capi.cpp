@@ -118,6 +118,16 @@ int pth_render(void* r, uint8_t* out, char* err, int errlen) {
     return -1;
   }
 }
+int pth_render_view(void* r, uint8_t* out, char* err, int errlen) {  // zero-copy path (prc_host_image), copied out for the test
+  try {
+    render::FrameView v = static_cast<render::Renderer*>(r)->RenderView();
+    std::memcpy(out, v.pix, (size_t)v.w * v.h * 4);
+    return 0;
+  } catch (const std::exception& e) {
+    set_err(err, errlen, e);
+    return -1;
+  }
+}
 int pth_set_camera(void* r, void* cam, char* err, int errlen) {  // Options(Camera(c)): re-fits the light cameras, zeroes the shadow maps
   try {
     static_cast<render::Renderer*>(r)->Options({render::Camera(static_cast<Box<camera::Interface>*>(cam)->p)});

@@ -541,6 +541,13 @@ class Backend {
   void SceneUpload(const prc_scene& s) const { Check(scene_upload_(ctx_, &s), "scene_upload"); }
   void ShadowReset() const { Check(shadow_reset_(ctx_), "shadow_reset"); }
   void Render(const prc_frame& f, uint8_t* out) const { Check(render_(ctx_, &f, out), "render"); }
+  bool HasHostImage() const { return host_image_ != nullptr; }
+  // the last frame rendered with rgba_out == NULL, in place in the library's page-locked double buffer (prc_host_image)
+  const uint8_t* HostImage(uint64_t* bytes) const {
+    uint64_t p = 0;
+    Check(host_image_(ctx_, &p, bytes), "host_image");
+    return reinterpret_cast<const uint8_t*>((uintptr_t)p);
+  }
 
  private:
   void* lib_ = nullptr;
@@ -590,6 +597,10 @@ struct Frame {  // the *image.RGBA Render() returns: row 0 = top, stride 4*w
   int w = 0, h = 0;
   std::vector<uint8_t> pix;
 };
+struct FrameView {  // the same frame read in place: valid until two frames later, like the reference's double buffer (raster.go:86,201-206)
+  int w = 0, h = 0;
+  const uint8_t* pix = nullptr;
+};
 
 class Renderer {
  public:
@@ -618,6 +629,20 @@ class Renderer {
     out.pix.resize((size_t)out.w * out.h * 4);
     backend_->Render(frame_, out.pix.data());
     return out;
+  }
+  // Zero-copy variant: the frame stays in the library's page-locked buffer (what the Go shim wraps in an *image.RGBA)
+  FrameView RenderView() {
+    if (!cfg_.Scene || !cfg_.Camera) throw std::invalid_argument("render: Scene and Camera are required");
+    if (!backend_->HasHostImage()) throw std::logic_error("render: this backend has no host-image export");
+    ensureUploaded();
+    buildFrame();
+    backend_->Render(frame_, nullptr);
+    uint64_t bytes = 0;
+    FrameView v;
+    v.w = cfg_.Width; v.h = cfg_.Height;
+    v.pix = backend_->HostImage(&bytes);
+    if (bytes != (uint64_t)v.w * v.h * 4) throw std::logic_error("render: host image size mismatch");
+    return v;
   }
   // the uniforms of the last built frame (tests compare them with the other mirrors bit for bit)
   const prc_frame& LastFrame() const { return frame_; }

@@ -68,6 +68,8 @@ struct Ctx {
 
   // frame state
   int W = 0, H = 0;
+  std::vector<uint8_t> host_img[2];      // rgba_out == NULL: the frame is kept here, alternately (prc_host_image semantics)
+  int host_cur = 0;
   int msaa = 1;                          // render.MSAA(n): W, H above are already n times render.Size (raster.go:149)
   std::vector<Fragment> frags;           // FragmentBuffer.fragments, stored in SCREEN coords [y*W+x]
   std::vector<std::vector<f32>> shadow;  // shadowInfo.depths per light (render/shadow.go:26-31)
@@ -782,6 +784,11 @@ int32_t orc_render(orc_ctx* x, const prc_frame* fr, uint8_t* rgba_out) {
   if (fr->flags & PRC_FRAME_BGRA)  // PixelFormatBGRA: Set() stores the colour bytes as B,G,R,A (buffer.go:242-251)
     for (size_t j = 0; j < npx; j++) color[j] = (color[j] & 0xff00ff00u) | ((color[j] & 0xffu) << 16) | ((color[j] >> 16) & 0xffu);
   // buf.Image(): image row r = screen y = H-1-r (buffer.go:160-166, 225)
+  if (!rgba_out && !(fr->flags & PRC_FRAME_NO_READBACK)) {  // same contract as prc_render: read the frame through orc_host_image
+    c.host_cur ^= 1;
+    c.host_img[c.host_cur].resize((size_t)(W / c.msaa) * (H / c.msaa) * 4);
+    rgba_out = c.host_img[c.host_cur].data();
+  }
   if (rgba_out && c.msaa == 1)
     for (int r = 0; r < H; r++) std::memcpy(rgba_out + (size_t)r * W * 4, &color[(size_t)(H - 1 - r) * W], (size_t)W * 4);
   if (rgba_out && c.msaa > 1) {
@@ -792,6 +799,14 @@ int32_t orc_render(orc_ctx* x, const prc_frame* fr, uint8_t* rgba_out) {
   }
   auto ms = [](auto a, auto b) { return std::chrono::duration<float, std::milli>(b - a).count(); };
   c.tm.shadow_ms = ms(T0, T1); c.tm.forward_ms = ms(T1, T2); c.tm.shade_ms = ms(T2, T3); c.tm.total_ms = ms(T0, T3);
+  return PRC_OK;
+}
+
+int32_t orc_host_image(orc_ctx* x, uint64_t* host_ptr, uint64_t* bytes) {
+  Ctx& c = x->c;
+  if (c.host_img[c.host_cur].empty()) return PRC_ERR_INVALID;
+  *host_ptr = (uint64_t)(uintptr_t)c.host_img[c.host_cur].data();
+  *bytes = c.host_img[c.host_cur].size();
   return PRC_OK;
 }
 

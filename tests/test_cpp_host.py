@@ -46,6 +46,7 @@ def H():
     L.pth_camera_matrices.argtypes = [vp, vp, vp]
     L.pth_renderer_new.argtypes = [C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
     L.pth_render.argtypes = [vp, vp, C.c_char_p, C.c_int]
+    L.pth_render_view.argtypes = [vp, vp, C.c_char_p, C.c_int]
     L.pth_set_camera.argtypes = [vp, vp, C.c_char_p, C.c_int]
     L.pth_last_frame.argtypes = [vp]
     L.pth_renderer_free.argtypes = [vp]
@@ -224,6 +225,10 @@ def test_uniforms_and_frames_match_the_python_mirror(H, msaa):
     assert np.array_equal(np.ctypeslib.as_array(fc.ambient_intensity, (fc.n_ambient,)), np.ctypeslib.as_array(fp.ambient_intensity, (fp.n_ambient,)))
     # and the frame rendered from them
     assert np.array_equal(got, want) and int((want[..., 3] > 0).sum()) > 3000
+    # the zero-copy path (rgba_out = NULL + host_image) returns the same frame
+    got2 = np.zeros_like(want)
+    assert H.pth_render_view(r, _p(got2), err, 512) == 0, err.value
+    assert np.array_equal(got2, want)
     H.pth_renderer_free(r)
 
 
