@@ -239,12 +239,15 @@ def run_cuda(args):
     # ---- multi-GPU partition: screen strips + shadow (light, row-range) shards (polyred_b200/distributed.py) ----
     df = None
     units = []
+    pf = None  # --mgpu peer: frames over NVLink peer memory (prc_render_peer), submitted back to back, no collective
     if world > 1:
-        from polyred_b200.distributed import DistributedFrame
+        from polyred_b200.distributed import DistributedFrame, PeerFrames
         df = DistributedFrame(r, rank, world, local)
         df.prepare(fd)
         df.prepare(fd_e2e)
         units = df.units
+        if args.mgpu == "peer":
+            pf = PeerFrames(r, rank, world, local, root=0)
 
     def step(fdesc, host_out):
         if world == 1:
@@ -253,12 +256,19 @@ def run_cuda(args):
             be.render(fdesc, None)
             if host_out is not None:
                 host_out[0] = be.host_image(w, h)
+        elif pf is not None:
+            pf.submit(fdesc)
+            if host_out is not None:  # e2e: every frame is finished and read back to rank 0's host memory
+                pf.finish()
+                host_out[0] = pf.image(host=True)
         else:
             img = df.render(fdesc, host_out is not None)
             if host_out is not None:
                 host_out[0] = img
 
     def barrier():
+        if pf is not None:
+            pf.finish()  # completes the submitted frames on every rank (and re-submits them if a queue had to grow)
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
@@ -285,10 +295,11 @@ def run_cuda(args):
     with torch.cuda.stream(stream):
         e0.record(stream)
     t0 = time.perf_counter()
-    if world == 1 and args.async_frames:
+    if (world == 1 and args.async_frames) or pf is not None:
         # frames stay on the device: submit them back to back (PRC_FRAME_ASYNC), one prc_sync inside the timed bracket; the
         # per-class kernel timings come back summed over the K frames
-        fd.struct.flags |= A.PRC_FRAME_ASYNC
+        if pf is None:
+            fd.struct.flags |= A.PRC_FRAME_ASYNC
         for _ in range(args.steps):
             step(fd, None)
         with torch.cuda.stream(stream):
@@ -370,8 +381,11 @@ def run_cuda(args):
         "config": {"workload": f"{args.workload}: {wl['desc']}", "n_tris": int(n_tris), "n_valid_tris": n_valid, "width": w, "height": h,
                    "fma": os.environ.get("PRC_FMA", "mixed"), "l2": "inputs (1.1 GB scene, 0.9 GB frame buffers) larger than L2; no explicit flush",
                    "submit": ("K frames back to back (PRC_FRAME_ASYNC), one prc_sync inside the timed bracket" if (world == 1 and args.async_frames)
+                              else "K frames back to back (prc_render_peer), one prc_sync inside the timed bracket" if pf is not None
                               else "one synchronous call per frame"),
-                   "partition": "1 GPU" if world == 1 else f"{world} screen strips + {len(units)} shadow shards (one in-place NCCL all-gather overlapped with the camera pass, one in-place all-gather of the image strips)"},
+                   "partition": "1 GPU" if world == 1
+                   else f"{world} screen strips + {len(units)} shadow shards; non-empty shadow texels and image strips pushed over NVLink peer memory by the library (no collective, no host wait inside a frame), image on rank 0" if pf is not None
+                   else f"{world} screen strips + {len(units)} shadow shards (one in-place NCCL all-gather overlapped with the camera pass, one in-place all-gather of the image strips)"},
         "roofline": {"bound": "hbm", "kernel": ("resolve_shade (k_resolve_shade, one kernel)" if (dom == 7 and one_kernel_shade) else names[dom]), "achieved": achieved, "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s",
                      "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms,
                      "launches_per_step": float(klaunch[dom]) / args.steps},
@@ -435,6 +449,9 @@ def main():
     ap.add_argument("--no-resident-uniforms", dest="resident_uniforms", action="store_false")
     ap.add_argument("--no-async-frames", dest="async_frames", action="store_false",
                     help="device-resident leg: wait for every frame (prc_render) instead of submitting the K frames back to back")
+    ap.add_argument("--mgpu", default=os.environ.get("PRC_MGPU", "nccl"), choices=["nccl", "peer"],
+                    help="N > 1: 'nccl' = one frame at a time, shadow maps and image strips all-gathered with NCCL (measured in round 1); "
+                         "'peer' = frames submitted back to back, exchange pushed over NVLink peer memory by the library (prc_render_peer)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

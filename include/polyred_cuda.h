@@ -51,6 +51,7 @@ extern "C" {
 #define PRC_ERR_NO_SCENE -4
 #define PRC_ERR_NCCL -5
 #define PRC_ERR_RETRY -6        /* prc_sync after PRC_FRAME_ASYNC frames: a queue overflowed, it has been grown; submit those frames again */
+#define PRC_ERR_PEER -7         /* prc_sync after prc_render_peer frames: a wait for a peer rank timed out (the frames are invalid) */
 
 /* prc_material.flags (material.Standard, material/material.go:23-30) */
 #define PRC_MAT_FLAT_SHADING 1u
@@ -272,6 +273,39 @@ int32_t prc_stream(prc_ctx* ctx, uint64_t* stream);
 /* Waits for everything submitted on this context. After PRC_FRAME_ASYNC frames it also finishes them (prc_get_timings then
  * reports sums over those frames) and returns PRC_ERR_RETRY if one of them overflowed an internal queue. */
 int32_t prc_sync(prc_ctx* ctx);
+
+/* ---- multi-GPU frames over NVLink peer memory (no host wait and no collective inside a frame) --------------------------
+ * One process per GPU. Each rank exports its shadow buffer, image buffer and signal words (CUDA IPC), the host exchanges the
+ * handles (any transport: torch.distributed.all_gather_object in polyred_b200/distributed.py) and every rank connects.
+ * prc_render_peer then submits one frame of the group WITHOUT waiting on the host:
+ *   this rank's shadow units -> their non-empty texels are stored into every peer's maps -> camera pass for rows [row0,row1)
+ *   -> wait (on the device) for the peers' shadow rows -> shading -> the image strip is copied into the image of every
+ *   rank in `image_mask` (bit r = rank r receives the whole frame; north_star: rank 0, mask 1).
+ * Ranks are ordered by epoch words in peer memory (release/acquire at system scope); every rank must submit the same
+ * sequence of prc_render_peer calls with the same image_mask. Frames stay on the device (PRC_FRAME_NO_READBACK is implied;
+ * PRC_FRAME_KEEP_GBUFFER, PRC_FRAME_SHADOW_RESET and MSAA are rejected); a consumer's image of a frame stays valid until its
+ * next prc_render_peer (readers: the host after prc_sync, or work enqueued on prc_stream() before that call). prc_sync() finishes the submitted frames:
+ * PRC_ERR_RETRY = a queue overflowed on THIS rank (grown now; all ranks must agree to submit the frames again),
+ * PRC_ERR_PEER = a device-side wait for a peer gave up after 4 s.
+ * The result is the 1-GPU frame bit for bit: depth maxima do not depend on who rasterised which rows. */
+typedef struct prc_peer_handle {
+  uint32_t abi_version;
+  uint32_t device;        /* CUDA device ordinal of the exporting context */
+  uint64_t pid;           /* exporting process: within one process the pointers below are used directly */
+  uint64_t shadow_ptr, image_ptr, signals_ptr;  /* device addresses in the exporting process */
+  uint64_t shadow_off, image_off, signals_off;  /* offsets of those buffers inside their IPC allocations */
+  uint64_t shadow_bytes, image_bytes;           /* capacities; all ranks of a group must agree */
+  uint8_t shadow_ipc[64], image_ipc[64], signals_ipc[64]; /* cudaIpcMemHandle_t */
+} prc_peer_handle;
+
+/* Allocates this context's buffers for `frame` (size, casting lights), zeroes its signal words and fills `out`.
+ * Call on every rank, exchange, then prc_peer_connect; repeat after a change of frame size or light set. */
+int32_t prc_peer_export(prc_ctx* ctx, const prc_frame* frame, prc_peer_handle* out);
+/* `all` = the world's handles in rank order (all[rank] is this context's own). world <= 16. */
+int32_t prc_peer_connect(prc_ctx* ctx, uint32_t rank, uint32_t world, const prc_peer_handle* all);
+int32_t prc_peer_disconnect(prc_ctx* ctx);
+int32_t prc_render_peer(prc_ctx* ctx, const prc_frame* frame, uint32_t n_units, const uint32_t* light, const uint32_t* row0,
+                        const uint32_t* row1, uint32_t image_mask);
 
 /* Arithmetic mode of this context, overriding the PRC_FMA environment variable read by prc_open:
  * exact != 0 -> math.FMA[float32] emulated bit-exactly everywhere (float64 fma rounded to float32, math/math.go FMA),

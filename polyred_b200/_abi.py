@@ -12,6 +12,7 @@ PRC_ERR_UNSUPPORTED = -3
 PRC_ERR_NO_SCENE = -4
 PRC_ERR_NCCL = -5
 PRC_ERR_RETRY = -6
+PRC_ERR_PEER = -7
 
 PRC_MAT_FLAT_SHADING = 1
 PRC_MAT_AMBIENT_OCCLUSION = 2
@@ -151,6 +152,25 @@ class prc_timings(C.Structure):
         ("n_large_items", C.c_uint64),
         ("n_clipped", C.c_uint64),
         ("n_bin_entries", C.c_uint64),
+    ]
+
+
+class prc_peer_handle(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_uint32),
+        ("device", C.c_uint32),
+        ("pid", C.c_uint64),
+        ("shadow_ptr", C.c_uint64),
+        ("image_ptr", C.c_uint64),
+        ("signals_ptr", C.c_uint64),
+        ("shadow_off", C.c_uint64),
+        ("image_off", C.c_uint64),
+        ("signals_off", C.c_uint64),
+        ("shadow_bytes", C.c_uint64),
+        ("image_bytes", C.c_uint64),
+        ("shadow_ipc", C.c_uint8 * 64),
+        ("image_ipc", C.c_uint8 * 64),
+        ("signals_ipc", C.c_uint8 * 64),
     ]
 
 

@@ -52,10 +52,16 @@ def lib():
         L.prc_host_image.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.prc_stream.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.prc_sync.argtypes = [vp]
+        L.prc_peer_export.argtypes = [vp, C.POINTER(A.prc_frame), C.POINTER(A.prc_peer_handle)]
+        L.prc_peer_connect.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(A.prc_peer_handle)]
+        L.prc_peer_disconnect.argtypes = [vp]
+        L.prc_render_peer.argtypes = [vp, C.POINTER(A.prc_frame), C.c_uint32, vp, vp, vp, C.c_uint32]
+        L.prc_set_exact_fma.argtypes = [vp, C.c_int32]
         for name in ("prc_open", "prc_close", "prc_scene_upload", "prc_shadow_reset", "prc_render", "prc_read_gbuffer",
                      "prc_read_shadowmap", "prc_get_timings", "prc_device_image", "prc_device_shadowmap",
                      "prc_render_shadows", "prc_render_main", "prc_stream", "prc_sync", "prc_host_image", "prc_render_forward",
-                     "prc_render_deferred", "prc_device_shadow_all", "prc_render_shadow_units"):
+                     "prc_render_deferred", "prc_device_shadow_all", "prc_render_shadow_units", "prc_peer_export", "prc_peer_connect",
+                     "prc_peer_disconnect", "prc_render_peer", "prc_set_exact_fma"):
             getattr(L, name).restype = C.c_int32
         if L.prc_abi_version() != A.PRC_ABI_VERSION:
             raise PolyredCudaError(A.PRC_ERR_INVALID, "ABI version mismatch")
@@ -187,3 +193,29 @@ class CudaBackend(Backend):
 
     def sync(self):
         self._check(self.L.prc_sync(self.h))
+
+    # ---- frames over NVLink peer memory (include/polyred_cuda.h: prc_render_peer) ----
+    def peer_export(self, fd) -> bytes:
+        """This context's exchange handle as bytes (to be gathered from every rank by the host)."""
+        h = A.prc_peer_handle()
+        self._check(self.L.prc_peer_export(self.h, C.byref(fd.struct), C.byref(h)))
+        return bytes(h)
+
+    def peer_connect(self, rank: int, world: int, handles: list[bytes]):
+        arr = (A.prc_peer_handle * world)()
+        for k, b in enumerate(handles):
+            if len(b) != C.sizeof(A.prc_peer_handle):
+                raise PolyredCudaError(A.PRC_ERR_INVALID, "peer handle of the wrong size")
+            C.memmove(C.byref(arr[k]), b, len(b))
+        self._check(self.L.prc_peer_connect(self.h, rank, world, arr))
+
+    def peer_disconnect(self):
+        self._check(self.L.prc_peer_disconnect(self.h))
+
+    def render_peer(self, fd, units, image_mask: int = 1):
+        """Submit one frame of the group without waiting (units: this rank's [(light, row0, row1)])."""
+        n = len(units)
+        a = np.array(units, dtype=np.uint32).reshape(n, 3)
+        li, r0, r1 = (np.ascontiguousarray(a[:, k]) for k in range(3))
+        self._check(self.L.prc_render_peer(self.h, C.byref(fd.struct), n, li.ctypes.data if n else None, r0.ctypes.data if n else None,
+                                           r1.ctypes.data if n else None, image_mask))

@@ -7,7 +7,10 @@
 #include <string>
 #include <vector>
 
+#include <unistd.h>
+
 #include "prc_kernels.cuh"
+#include "prc_peer.cuh"
 
 #define PRC_SHADE_BANDS 8  // row bands of the shading pass when the frame is read back (copy of band k overlaps shading of band k+1)
 
@@ -86,9 +89,22 @@ struct prc_ctx {
   DevFrame h_frame{};
   bool capturing = false;
   uint32_t n_lights_alloc = 0;
+
+  // peer exchange (prc_peer_* / prc_render_peer): peers.world == 0 <=> not connected
+  DBuf d_peer_signals, d_peer_err;
+  PeerTable peers{};
+  uint8_t* peer_image[PRC_PEER_MAX] = {};
+  std::vector<void*> peer_opened;  // bases returned by cudaIpcOpenMemHandle
+  void *peer_shadow_self = nullptr, *peer_image_self = nullptr;  // the exported buffers (a reallocation invalidates the group)
+  uint32_t peer_epoch = 0, peer_image_mask = 0;
+  bool peer_image_held = false;  // this rank consumed the image of peer_epoch and has not released it to the pushers yet
 };
 
 namespace {
+
+// peer exchange (defined at the end of this file)
+void peer_release(prc_ctx* ctx);            // unmaps the peers' buffers
+int32_t peer_check(prc_ctx* ctx);           // after a synchronisation: did a device-side wait for a peer give up?
 
 #define PRC_RETRY 1
 #define CK(call)                                                                             \
@@ -722,6 +738,9 @@ int32_t prc_close(prc_ctx* ctx) {
   if (!ctx) return PRC_ERR_INVALID;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  peer_release(ctx);
+  free_buf(ctx->d_peer_signals);
+  free_buf(ctx->d_peer_err);
   DBuf* all[] = {&ctx->d_pos, &ctx->d_nor, &ctx->d_uv, &ctx->d_col, &ctx->d_mat, &ctx->d_meta, &ctx->d_mats, &ctx->d_objstart, &ctx->d_texfirst,
                  &ctx->d_lw, &ctx->d_lh, &ctx->d_loff, &ctx->d_tex, &ctx->d_keys, &ctx->d_ga, &ctx->d_gb, &ctx->d_gc, &ctx->d_gd, &ctx->d_ao,
                  &ctx->d_image, &ctx->d_special, &ctx->d_counters, &ctx->d_large, &ctx->d_clipq, &ctx->d_tilecount, &ctx->d_tilestart, &ctx->d_cursor,
@@ -1104,10 +1123,293 @@ int32_t prc_sync(prc_ctx* ctx) {
   if (ctx->pending_async) {
     ctx->pending_async = 0;
     const int32_t r = finish_timings(ctx);  // synchronises; timings are sums over the asynchronous frames
+    if (ctx->peers.world) {
+      const int32_t pr = peer_check(ctx);
+      if (pr != PRC_OK) return pr;
+    }
     if (r == PRC_RETRY) { ctx->err = "a queue overflowed during asynchronous frames (grown now): submit them again"; return PRC_ERR_RETRY; }
     return r;
   }
   CK(cudaStreamSynchronize(ctx->stream));
+  return PRC_OK;
+}
+
+}  // extern "C"
+
+// =====================================================================================================================
+// Multi-GPU frames over NVLink peer memory (include/polyred_cuda.h "prc_render_peer"; kernels in prc_peer.cuh).
+// The reference has no counterpart: the contract is "the same frame as one GPU, bit for bit".
+// =====================================================================================================================
+namespace {
+
+// offset of a device pointer inside its allocation: cudaIpcGetMemHandle exports the whole allocation block and
+// cudaIpcOpenMemHandle returns the block's base (small cudaMalloc buffers share blocks)
+int32_t alloc_offset(prc_ctx* ctx, const void* p, uint64_t* off) {
+  typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q));
+  if (!fn || q != cudaDriverEntryPointSuccess) { ctx->err = "cuMemGetAddressRange not available"; return PRC_ERR_CUDA; }
+  unsigned long long base = 0;
+  size_t size = 0;
+  if (((range_fn)fn)(&base, &size, (unsigned long long)(uintptr_t)p) != 0) { ctx->err = "cuMemGetAddressRange failed"; return PRC_ERR_CUDA; }
+  *off = (uint64_t)(uintptr_t)p - base;
+  return PRC_OK;
+}
+
+void peer_release(prc_ctx* ctx) {
+  for (void* b : ctx->peer_opened) cudaIpcCloseMemHandle(b);
+  ctx->peer_opened.clear();
+  ctx->peers = PeerTable{};
+  for (auto& p : ctx->peer_image) p = nullptr;
+  ctx->peer_shadow_self = ctx->peer_image_self = nullptr;
+  ctx->peer_epoch = 0;
+  ctx->peer_image_mask = 0;
+  ctx->peer_image_held = false;
+}
+
+int32_t peer_check(prc_ctx* ctx) {
+  unsigned int n = 0;
+  CK(cudaMemcpy(&n, ctx->d_peer_err.p, 4, cudaMemcpyDeviceToHost));
+  if (n) {
+    CK(cudaMemset(ctx->d_peer_err.p, 0, 4));
+    ctx->err = "a device-side wait for a peer rank timed out (" + std::to_string(n) + " waits): the frames submitted since the last prc_sync are invalid";
+    return PRC_ERR_PEER;
+  }
+  return PRC_OK;
+}
+
+inline void peer_wait(prc_ctx* ctx, uint32_t kind, uint32_t epoch, uint32_t mask) {
+  const PeerTable& P = ctx->peers;
+  if (!(mask & ~(1u << P.self))) return;
+  k_peer_wait<<<1, PRC_PEER_MAX, 0, ctx->stream>>>(P.signals[P.self], P.world, P.self, kind, epoch, mask, (unsigned int*)ctx->d_peer_err.p);
+  ctx->launches++;
+}
+
+inline void peer_signal(prc_ctx* ctx, uint32_t kind, uint32_t epoch, uint32_t mask) {
+  const PeerTable& P = ctx->peers;
+  if (!(mask & ~(1u << P.self))) return;
+  k_peer_signal<<<1, PRC_PEER_MAX, 0, ctx->stream>>>(P, kind, epoch, mask);
+  ctx->launches++;
+}
+
+template <bool E>
+int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, const std::vector<ShadowUnit>& units, uint32_t image_mask) {
+  const PeerTable& P = ctx->peers;
+  const uint32_t all = P.world >= 32 ? 0xFFFFFFFFu : ((1u << P.world) - 1u), me = 1u << P.self;
+  cudaStream_t st = ctx->stream;
+  // the image this rank consumed last frame goes back to the pushers: everything the caller enqueued on this stream (or
+  // finished on the host) before this call has read it
+  if (ctx->peer_image_held) {
+    peer_signal(ctx, PRC_SIG_IMAGE_FREE, ctx->peer_epoch, all);
+    ctx->peer_image_held = false;
+  }
+  const uint32_t e = ++ctx->peer_epoch;
+  if (ctx->pending_async == 0) {
+    ctx->launches = 0;
+    ctx->spans.clear();
+    ctx->ev_used = 0;
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, offsetof(Counters, n_valid), st));
+  } else {
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 16, st));  // behind unfinished frames: the overflow flag and the statistics are sticky
+  }
+  CK(cudaEventRecord(ctx->ev[0], st));
+  const bool shadows = (fr->flags & PRC_FRAME_SHADOWMAP) && ctx->n_cast_alloc > 0 && ctx->n_cast_alloc != 0xFFFFFFFFu;
+  if (shadows) {
+    // nobody may still be shading the previous frame from the maps this rank is about to store into
+    peer_wait(ctx, PRC_SIG_SHADED, e - 1, all);
+    int32_t r = do_shadows<E>(ctx, fr, F, units, true);
+    if (r != PRC_OK) return r;
+    PushUnits U{};
+    const size_t npx = (size_t)F.W * F.H;
+    bool vec4 = true;
+    for (const ShadowUnit& u : units) {
+      if (u.light >= fr->n_lights || !fr->lights[u.light].cast_shadow || u.r0 >= u.r1) continue;
+      if (U.n == 32) { ctx->err = "more than 32 shadow units in one prc_render_peer call"; return PRC_ERR_UNSUPPORTED; }
+      U.off[U.n] = (unsigned long long)(ctx->shadow_ptr[u.light] - (float*)ctx->d_shadow_all.p) + (unsigned long long)u.r0 * F.W;
+      U.cnt[U.n] = (unsigned long long)(u.r1 - u.r0) * F.W;
+      vec4 = vec4 && (U.off[U.n] % 4 == 0) && (U.cnt[U.n] % 4 == 0);
+      U.n++;
+    }
+    (void)npx;
+    if (U.n && P.world > 1) {
+      if (vec4) k_shadow_push<4><<<148 * 8, 256, 0, st>>>(P, U);
+      else k_shadow_push<1><<<148 * 8, 256, 0, st>>>(P, U);
+      ctx->launches++;
+    }
+    peer_signal(ctx, PRC_SIG_SHADOW, e, all);
+  }
+  CK(cudaEventRecord(ctx->ev[1], st));
+  ctx->rb_dst = nullptr;
+  int32_t r = do_main<E>(ctx, fr, F, 1);  // camera geometry + raster + resolve: needs no shadow map, overlaps the peers' pushes
+  if (r != PRC_OK) return r;
+  if (shadows) peer_wait(ctx, PRC_SIG_SHADOW, e, all);
+  r = do_main<E>(ctx, fr, F, 2);
+  if (r != PRC_OK) return r;
+  if (shadows) peer_signal(ctx, PRC_SIG_SHADED, e, all);
+  // image strip: screen rows [row0,row1) = image rows [H-row1, H-row0)
+  const size_t off = (size_t)(F.H - F.row1) * F.W * 4, bytes = (size_t)(F.row1 - F.row0) * F.W * 4;
+  const uint32_t consumers = image_mask & all;
+  if (consumers & ~me) {
+    peer_wait(ctx, PRC_SIG_IMAGE_FREE, e - 1, consumers);  // the consumers are done with the previous frame's image
+    for (uint32_t c = 0; c < P.world; c++)
+      if (((consumers >> c) & 1u) && c != P.self)
+        CK(cudaMemcpyAsync(ctx->peer_image[c] + off, (const uint8_t*)ctx->d_image.p + off, bytes, cudaMemcpyDefault, st));
+    peer_signal(ctx, PRC_SIG_IMAGE, e, consumers);
+  }
+  if (consumers & me) {
+    peer_wait(ctx, PRC_SIG_IMAGE, e, all);  // every strip has landed in this rank's image
+    ctx->peer_image_held = true;
+  }
+  CK(cudaEventRecord(ctx->ev[3], st));
+  CK(cudaGetLastError());
+  return PRC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t prc_peer_export(prc_ctx* ctx, const prc_frame* fr, prc_peer_handle* out) {
+  if (!ctx || !out) return PRC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->pending_async) { const int32_t pr_ = prc_sync(ctx); if (pr_ != PRC_OK) return pr_; }
+  peer_release(ctx);
+  DevFrame F;
+  int32_t r = build_frame(ctx, fr, F);  // allocates (and, for a new size / light set, zeroes) the shadow and image buffers
+  if (r != PRC_OK) return r;
+  ENSURE(ctx->d_peer_signals, (size_t)PRC_SIG_KINDS * PRC_PEER_MAX * 4);
+  ENSURE(ctx->d_peer_err, 16);
+  CK(cudaMemsetAsync(ctx->d_peer_signals.p, 0, (size_t)PRC_SIG_KINDS * PRC_PEER_MAX * 4, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_peer_err.p, 0, 16, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  memset(out, 0, sizeof(*out));
+  out->abi_version = PRC_ABI_VERSION;
+  out->device = (uint32_t)ctx->device;
+  out->pid = (uint64_t)getpid();
+  out->shadow_ptr = (uint64_t)(uintptr_t)ctx->d_shadow_all.p;
+  out->image_ptr = (uint64_t)(uintptr_t)ctx->d_image.p;
+  out->signals_ptr = (uint64_t)(uintptr_t)ctx->d_peer_signals.p;
+  out->shadow_bytes = ctx->d_shadow_all.cap;
+  out->image_bytes = ctx->d_image.cap;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "prc_peer_handle carries 64-byte IPC handles");
+  CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->shadow_ipc, ctx->d_shadow_all.p));
+  CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->image_ipc, ctx->d_image.p));
+  CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->signals_ipc, ctx->d_peer_signals.p));
+  if ((r = alloc_offset(ctx, ctx->d_shadow_all.p, &out->shadow_off)) != PRC_OK) return r;
+  if ((r = alloc_offset(ctx, ctx->d_image.p, &out->image_off)) != PRC_OK) return r;
+  if ((r = alloc_offset(ctx, ctx->d_peer_signals.p, &out->signals_off)) != PRC_OK) return r;
+  ctx->peer_shadow_self = ctx->d_shadow_all.p;
+  ctx->peer_image_self = ctx->d_image.p;
+  return PRC_OK;
+}
+
+int32_t prc_peer_connect(prc_ctx* ctx, uint32_t rank, uint32_t world, const prc_peer_handle* all) {
+  if (!ctx || !all) return PRC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if (world == 0 || world > PRC_PEER_MAX || rank >= world) { ctx->err = "prc_peer_connect: bad rank / world (at most 16 ranks)"; return PRC_ERR_INVALID; }
+  if (!ctx->peer_shadow_self || ctx->peer_shadow_self != ctx->d_shadow_all.p || ctx->peer_image_self != ctx->d_image.p) {
+    ctx->err = "prc_peer_connect: call prc_peer_export first";
+    return PRC_ERR_INVALID;
+  }
+  const prc_peer_handle& mine = all[rank];
+  if (mine.pid != (uint64_t)getpid() || mine.shadow_ptr != (uint64_t)(uintptr_t)ctx->d_shadow_all.p) { ctx->err = "prc_peer_connect: all[rank] is not this context's handle"; return PRC_ERR_INVALID; }
+  PeerTable T{};
+  T.world = world;
+  T.self = rank;
+  uint8_t* image[PRC_PEER_MAX] = {};
+  std::vector<void*> opened;
+  auto fail = [&](const std::string& msg) {
+    for (void* b : opened) cudaIpcCloseMemHandle(b);
+    ctx->err = msg;
+    return PRC_ERR_CUDA;
+  };
+  for (uint32_t p = 0; p < world; p++) {
+    const prc_peer_handle& h = all[p];
+    if (h.abi_version != PRC_ABI_VERSION) return fail("prc_peer_connect: bad abi_version in a peer handle");
+    if (h.shadow_bytes != mine.shadow_bytes || h.image_bytes != mine.image_bytes) return fail("prc_peer_connect: the ranks' frame buffers differ in size");
+    if (p == rank || h.pid == mine.pid) {
+      // same process (this rank, or another context of a single-process test harness): the pointers are valid as they are
+      if (p != rank && (int)h.device != ctx->device) {
+        const cudaError_t e = cudaDeviceEnablePeerAccess((int)h.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        (void)cudaGetLastError();
+      }
+      T.shadow[p] = (float*)(uintptr_t)h.shadow_ptr;
+      image[p] = (uint8_t*)(uintptr_t)h.image_ptr;
+      T.signals[p] = (uint32_t*)(uintptr_t)h.signals_ptr;
+      continue;
+    }
+    // another process: map its allocations (identical handles = buffers sharing one allocation block are mapped once)
+    const uint8_t* ipc[3] = {h.shadow_ipc, h.image_ipc, h.signals_ipc};
+    void* base[3] = {nullptr, nullptr, nullptr};
+    for (int k = 0; k < 3; k++) {
+      for (int j = 0; j < k; j++)
+        if (memcmp(ipc[k], ipc[j], 64) == 0) base[k] = base[j];
+      if (base[k]) continue;
+      cudaIpcMemHandle_t mh;
+      memcpy(&mh, ipc[k], 64);
+      const cudaError_t e = cudaIpcOpenMemHandle(&base[k], mh, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return fail(std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(p) + "): " + cudaGetErrorString(e));
+      opened.push_back(base[k]);
+    }
+    T.shadow[p] = (float*)((uint8_t*)base[0] + h.shadow_off);
+    image[p] = (uint8_t*)base[1] + h.image_off;
+    T.signals[p] = (uint32_t*)((uint8_t*)base[2] + h.signals_off);
+  }
+  ctx->peers = T;
+  for (uint32_t p = 0; p < PRC_PEER_MAX; p++) ctx->peer_image[p] = image[p];
+  ctx->peer_opened = opened;
+  ctx->peer_epoch = 0;
+  ctx->peer_image_mask = 0;
+  ctx->peer_image_held = false;
+  return PRC_OK;
+}
+
+int32_t prc_peer_disconnect(prc_ctx* ctx) {
+  if (!ctx) return PRC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  int32_t r = PRC_OK;
+  if (ctx->pending_async) r = prc_sync(ctx);
+  else CK(cudaStreamSynchronize(ctx->stream));
+  peer_release(ctx);
+  return r;
+}
+
+int32_t prc_render_peer(prc_ctx* ctx, const prc_frame* fr, uint32_t n, const uint32_t* light, const uint32_t* row0, const uint32_t* row1, uint32_t image_mask) {
+  if (!ctx) return PRC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->peers.world) { ctx->err = "prc_render_peer: not connected (prc_peer_export / prc_peer_connect)"; return PRC_ERR_INVALID; }
+  if (!fr || fr->abi_version != PRC_ABI_VERSION) { ctx->err = "prc_frame: bad abi_version"; return PRC_ERR_INVALID; }
+  if ((fr->flags & (PRC_FRAME_KEEP_GBUFFER | PRC_FRAME_SHADOW_RESET)) || fr->msaa > 1) {
+    ctx->err = "prc_render_peer: PRC_FRAME_KEEP_GBUFFER, PRC_FRAME_SHADOW_RESET and MSAA are not supported";
+    return PRC_ERR_UNSUPPORTED;
+  }
+  if (n && (!light || !row0 || !row1)) return PRC_ERR_INVALID;
+  if (ctx->peer_epoch && image_mask != ctx->peer_image_mask) { ctx->err = "prc_render_peer: image_mask must not change between frames of a connection"; return PRC_ERR_INVALID; }
+  DevFrame F;
+  int32_t r = build_frame(ctx, fr, F);
+  if (r != PRC_OK) return r;
+  if (ctx->d_shadow_all.p != ctx->peer_shadow_self || ctx->d_image.p != ctx->peer_image_self) {
+    // the frame size or the set of casting lights changed: the peers still map the old buffers
+    peer_release(ctx);
+    ctx->err = "prc_render_peer: the exported buffers were reallocated; export and connect again on every rank";
+    return PRC_ERR_INVALID;
+  }
+  std::vector<ShadowUnit> units;
+  for (uint32_t k = 0; k < n; k++) {
+    if (row1[k] > fr->height || row0[k] >= row1[k]) { ctx->err = "bad shadow row range"; return PRC_ERR_INVALID; }
+    units.push_back({light[k], (int)row0[k], (int)row1[k]});
+  }
+  ctx->peer_image_mask = image_mask;
+  r = ctx->exact ? enqueue_peer_frame<true>(ctx, fr, F, units, image_mask) : enqueue_peer_frame<false>(ctx, fr, F, units, image_mask);
+  if (r != PRC_OK) return r;
+  ctx->pending_async++;
+  if (ctx->ev_used > 8192) {
+    // bound the timing-event pool without a host wait: keep the events, drop the spans of the oldest frames
+    ctx->spans.clear();
+    ctx->ev_used = 0;
+  }
   return PRC_OK;
 }
 

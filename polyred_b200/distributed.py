@@ -10,6 +10,10 @@ range) shards dealt round-robin. Per frame:
   5. ONE in-place all-gather over the image buffer assembles the frame         (prc_device_image; equal strips)
 The result is bit-identical to the 1-GPU frame: atomicMax keys / depth maxima do not depend on who
 rasterised what, and every rank also rasterises pixel (0,0) (bug-list 3) and the AO halo rows.
+
+PeerFrames (below) is the same partition without a collective and without a host wait inside the frame:
+the ranks map each other's buffers (CUDA IPC over NVLink) and the library pushes shadow texels and image
+strips itself (prc_render_peer); torch.distributed only carries the handles and the retry vote.
 """
 from __future__ import annotations
 
@@ -98,3 +102,96 @@ class DistributedFrame:
                 return self._host_np
             self.stream.synchronize()
             return None
+
+
+class PeerFrames:
+    """Frames of an N-GPU group submitted back to back through prc_render_peer (include/polyred_cuda.h).
+
+    Every rank constructs one with the same renderer configuration and calls submit()/finish() in lockstep.
+    finish() returns after all submitted frames are complete on this rank; rank 0 (`root`) then holds the
+    whole image of the LAST frame on the device (image()), the other ranks hold their own strip only."""
+
+    def __init__(self, renderer, rank: int, world: int, device: int, root: int = 0, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        if group is None:
+            # host-only plumbing (64-byte handles, one retry vote per finish()): keep it off the GPUs when gloo is usable
+            try:
+                group = dist.new_group(backend="gloo")
+            except Exception:  # noqa: BLE001 - same outcome on every rank of a node; the default (NCCL) group works too
+                group = None
+        self.group = group
+        self.r, self.be = renderer, renderer._backend
+        self.rank, self.world, self.root = rank, world, root
+        self.device = torch.device("cuda", device)
+        c = renderer.cfg
+        self.w, self.h = c.Width, c.Height
+        sources, _ = c.Scene.Lights()
+        cast = [i for i, l in enumerate(sources) if l.cast_shadow] if c.ShadowMap else []
+        _, self.rows = partition.strips(self.h, world)
+        self.units = [(li, a, b) for li, a, b, owner in partition.shadow_units(self.h, world, cast) if owner == rank]
+        self.image_mask = 1 << root
+        self._submitted = []
+        self._host = self._host_np = None
+        self._connect(renderer.frame_desc(no_readback=True))
+
+    def _connect(self, fd):
+        handle = self.be.peer_export(self.prepare(fd))
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, handle, group=self.group)
+        self.be.peer_connect(self.rank, self.world, handles)
+        self.dist.barrier(group=self.group)  # nobody signals before everybody has zeroed its words and mapped its peers
+
+    def prepare(self, fd):
+        fd.struct.row0, fd.struct.row1 = self.rows[self.rank]
+        return fd
+
+    def submit(self, fd):
+        """Enqueue one frame; does not wait for the GPU or for the peers."""
+        self.be.render_peer(self.prepare(fd), self.units, self.image_mask)
+        self._submitted.append(fd)
+
+    def finish(self, max_retries: int = 3):
+        """Wait for the submitted frames. A queue overflow on ANY rank (the library has grown the queue) makes
+        every rank submit its frames again — the shadow maps only grow, so that is idempotent."""
+        from ._lib import PolyredCudaError
+        from . import _abi as A
+        for _ in range(max_retries + 1):
+            retry = 0
+            try:
+                self.be.sync()
+            except PolyredCudaError as e:
+                if e.code != A.PRC_ERR_RETRY:
+                    raise
+                retry = 1
+            votes = [0] * self.world
+            self.dist.all_gather_object(votes, retry, group=self.group)
+            if not any(votes):
+                self._submitted = []
+                return
+            again, self._submitted = self._submitted, []
+            for fd in again:
+                self.submit(fd)
+        raise PolyredCudaError(A.PRC_ERR_UNSUPPORTED, "PeerFrames: a queue kept overflowing")
+
+    def image(self, host: bool = True):
+        """The last frame on `root` (None elsewhere): (H, W, 4) u8 in page-locked host memory, or the device tensor."""
+        if self.rank != self.root:
+            return None
+        torch = self.torch
+        ptr, nbytes, _ = self.be.device_image()
+        dev = torch.as_tensor(_cai(ptr, nbytes), device=self.device)
+        if not host:
+            return dev.view(self.h, self.w, 4)
+        if self._host is None or self._host.numel() != nbytes:
+            self._host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+            self._host_np = self._host.numpy().reshape(self.h, self.w, 4)
+        stream = torch.cuda.ExternalStream(self.be.stream(), device=self.device)
+        with torch.cuda.stream(stream):
+            self._host.copy_(dev, non_blocking=True)
+        stream.synchronize()
+        return self._host_np
+
+    def close(self):
+        self.be.peer_disconnect()

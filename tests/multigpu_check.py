@@ -14,7 +14,7 @@ def main():
     import torch
     import torch.distributed as dist
     from polyred_b200 import render, synth
-    from polyred_b200.distributed import DistributedFrame
+    from polyred_b200.distributed import DistributedFrame, PeerFrames
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -29,11 +29,27 @@ def main():
         df = DistributedFrame(r, rank, world, local)
         for _ in range(2):
             out = df.render(df.prepare(r.frame_desc(no_readback=True)), True)
+        peer_out = None
+        if os.environ.get("PRC_CHECK_PEER", "1") != "0":
+            # the same frame through prc_render_peer (NVLink peer memory, no collective): three frames back to back
+            r2 = render.NewRenderer(*opts, render.CUDA(local))
+            r2._ensure_uploaded()
+            pf = PeerFrames(r2, rank, world, local, root=0)
+            for _ in range(3):
+                pf.submit(r2.frame_desc(no_readback=True))
+            pf.finish()
+            peer_out = pf.image(host=True)
+            dist.barrier()
+            pf.close()
         if rank == 0:
             ref = render.NewRenderer(*opts, render.CUDA(local)).Render()
             nd = int((np.abs(out.astype(int) - ref.astype(int)).max(axis=2) > 0).sum())
             print(f"[multigpu_check] {name} {w}x{h} world={world}: pixels differing from the 1-GPU frame = {nd}")
             ok = ok and nd == 0
+            if peer_out is not None:
+                nd = int((np.abs(peer_out.astype(int) - ref.astype(int)).max(axis=2) > 0).sum())
+                print(f"[multigpu_check] {name} {w}x{h} world={world} (peer memory): pixels differing from the 1-GPU frame = {nd}")
+                ok = ok and nd == 0
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:

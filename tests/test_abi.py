@@ -30,7 +30,7 @@ def declared_symbols():
 
 def test_every_declared_symbol_is_exported(lib):
     syms = declared_symbols()
-    assert len(syms) >= 17, syms
+    assert len(syms) >= 27, syms
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/polyred_cuda.h but not exported"
 
@@ -40,7 +40,7 @@ def test_abi_version(lib):
 
 
 def test_struct_layouts_match_header(tmp_path):
-    structs = ["prc_material", "prc_scene", "prc_object_xf", "prc_light", "prc_frame", "prc_gbuffer_host", "prc_timings"]
+    structs = ["prc_material", "prc_scene", "prc_object_xf", "prc_light", "prc_frame", "prc_gbuffer_host", "prc_timings", "prc_peer_handle"]
     prog = '#include <stdio.h>\n#include <stddef.h>\n#include "polyred_cuda.h"\nint main(){\n'
     for s in structs:
         prog += f'printf("{s} %zu\\n", sizeof({s}));\n'

@@ -1,0 +1,105 @@
+"""-m gpu: frames over NVLink peer memory (prc_render_peer) must equal the 1-GPU frame bit for bit.
+
+NOT YET RUN ON HARDWARE (written after round 1's GPU budget was spent): the tests are opt-in through
+PRC_TEST_PEER=1 so that the round-end `pytest -m gpu` exercises only verified paths. The multi-process form of
+the same check is tests/multigpu_check.py (torchrun, one process per GPU, CUDA IPC).
+
+  world = 1 : the whole protocol with no peer (waits and signals are skipped), 1 GPU
+  world = 2 : two contexts of ONE process on two GPUs (the library uses the peers' pointers directly instead of
+              IPC handles); frames are submitted to both contexts from this single host thread, which only works
+              because nothing in prc_render_peer waits on the host
+"""
+import os
+
+import numpy as np
+import pytest
+
+from polyred_b200 import _abi as A
+from polyred_b200 import partition, render, synth
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("PRC_TEST_PEER") != "1", reason="opt-in: PRC_TEST_PEER=1 (not yet verified on hardware)")]
+
+
+def _scene():
+    s, cam = synth.city_scene(n_objects=25, obj_stacks=20, obj_slices=20, ground_cells=60, tex_size=64)
+    return s, cam, 480, 272
+
+
+def _opts(s, cam, w, h):
+    return [render.Camera(cam), render.Size(w, h), render.Scene(s), render.ShadowMap(True), render.GammaCorrection(True)]
+
+
+def _device_image(be, w, h):
+    import torch
+    from polyred_b200.distributed import _cai
+    ptr, nbytes, _ = be.device_image()
+    return torch.as_tensor(_cai(ptr, nbytes), device=torch.device("cuda", be.device)).cpu().numpy().reshape(h, w, 4)
+
+
+def _group(s, cam, w, h, devices):
+    world = len(devices)
+    sources, _ = s.Lights()
+    cast = [i for i, l in enumerate(sources) if l.cast_shadow]
+    _, rows = partition.strips(h, world)
+    units = partition.shadow_units(h, world, cast)
+    rs, fds, handles = [], [], []
+    for k, dev in enumerate(devices):
+        r = render.NewRenderer(*_opts(s, cam, w, h), render.CUDA(dev))
+        r._ensure_uploaded()
+        fd = r.frame_desc(no_readback=True)
+        fd.struct.row0, fd.struct.row1 = rows[k]
+        handles.append(r._backend.peer_export(fd))
+        rs.append(r)
+        fds.append(fd)
+    for k, r in enumerate(rs):
+        r._backend.peer_connect(k, world, handles)
+    mine = [[(li, a, b) for li, a, b, owner in units if owner == k] for k in range(world)]
+    return rs, fds, mine
+
+
+def _run(devices, frames=3):
+    s, cam, w, h = _scene()
+    ref = render.NewRenderer(*_opts(s, cam, w, h), render.CUDA(devices[0])).Render().copy()
+    rs, fds, mine = _group(s, cam, w, h, devices)
+    for _ in range(frames):
+        for k, r in enumerate(rs):
+            r._backend.render_peer(fds[k], mine[k], 1)
+    for r in rs:
+        r._backend.sync()
+    out = _device_image(rs[0]._backend, w, h)
+    for r in rs:
+        r._backend.peer_disconnect()
+    return ref, out
+
+
+def test_peer_world1_equals_render(monkeypatch):
+    monkeypatch.setenv("PRC_FMA", "exact")
+    ref, out = _run([0])
+    assert int((ref != out).any(axis=2).sum()) == 0
+
+
+def test_peer_two_contexts_one_process(monkeypatch):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("PRC_FMA", "exact")
+    ref, out = _run([0, 1])
+    assert int((ref != out).any(axis=2).sum()) == 0
+
+
+def test_peer_rejects_unsupported_frames(monkeypatch):
+    from polyred_b200._lib import PolyredCudaError
+    s, cam, w, h = _scene()
+    rs, fds, mine = _group(s, cam, w, h, [0])
+    be = rs[0]._backend
+    fds[0].struct.flags |= A.PRC_FRAME_SHADOW_RESET
+    with pytest.raises(PolyredCudaError):
+        be.render_peer(fds[0], mine[0], 1)
+    fds[0].struct.flags &= ~A.PRC_FRAME_SHADOW_RESET
+    be.render_peer(fds[0], mine[0], 1)
+    with pytest.raises(PolyredCudaError):  # the consumer set is fixed for the lifetime of a connection
+        be.render_peer(fds[0], mine[0], 0)
+    be.sync()
+    be.peer_disconnect()
+    with pytest.raises(PolyredCudaError):
+        be.render_peer(fds[0], mine[0], 1)

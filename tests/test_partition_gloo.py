@@ -75,3 +75,84 @@ def test_two_rank_exchange_reassembles_the_frame():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(m and i for _, m, i in res), res
+
+
+class _FakeBackend:
+    """Stands in for CudaBackend on CPU: records the prc_render_peer calls; rank 1's first prc_sync reports a grown queue."""
+
+    def __init__(self, rank):
+        self.rank, self.calls, self.syncs, self.connected = rank, [], 0, None
+
+    def peer_export(self, fd):
+        from polyred_b200 import _abi as A
+        h = A.prc_peer_handle(abi_version=A.PRC_ABI_VERSION, device=self.rank, pid=os.getpid())
+        assert (fd.struct.row0, fd.struct.row1) != (0, 0)
+        return bytes(h)
+
+    def peer_connect(self, rank, world, handles):
+        self.connected = (rank, world, [len(b) for b in handles])
+
+    def render_peer(self, fd, units, image_mask):
+        self.calls.append((fd.tag, fd.struct.row0, fd.struct.row1, tuple(units), image_mask))
+
+    def sync(self):
+        from polyred_b200 import _abi as A
+        from polyred_b200._lib import PolyredCudaError
+        self.syncs += 1
+        if self.rank == 1 and self.syncs == 1:
+            raise PolyredCudaError(A.PRC_ERR_RETRY, "queue grown")
+
+    def peer_disconnect(self):
+        pass
+
+
+def _peer_worker(rank, world, port, q):
+    import types
+    from polyred_b200 import _abi as A
+    from polyred_b200 import light, scene
+    from polyred_b200.distributed import PeerFrames
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def frame(tag):
+        return types.SimpleNamespace(struct=A.prc_frame(abi_version=A.PRC_ABI_VERSION, width=40, height=100), tag=tag)
+
+    sc = scene.Scene(light.Point(cast_shadow=True), light.Point(), light.Point(cast_shadow=True))
+    be = _FakeBackend(rank)
+    r = types.SimpleNamespace(cfg=types.SimpleNamespace(Width=40, Height=100, Scene=sc, ShadowMap=True), _backend=be,
+                              frame_desc=lambda no_readback=True: frame("connect"))
+    pf = PeerFrames(r, rank, world, 0, root=0)
+    for k in range(3):
+        pf.submit(frame(k))
+    pf.finish()
+    q.put((rank, be.connected, be.calls, be.syncs, len(pf._submitted)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_frames_host_logic_two_ranks():
+    """PeerFrames (prc_render_peer driver): handles are gathered in rank order, every rank submits its own strip and
+    shadow units, and a queue overflow on ONE rank makes BOTH ranks submit the batch again (lockstep epochs)."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    import ctypes as C
+    from polyred_b200 import _abi as A
+    for rank, connected, calls, syncs, left in res:
+        assert connected == (rank, 2, [C.sizeof(A.prc_peer_handle)] * 2)
+        assert [c[0] for c in calls] == [0, 1, 2, 0, 1, 2] and syncs == 2 and left == 0  # one retry, on both ranks
+        assert all(c[4] == 1 for c in calls)  # the image goes to rank 0
+        rows = {(c[1], c[2]) for c in calls}
+        assert rows == {(50, 100)} if rank == 0 else rows == {(0, 50)}  # rank 0 owns the top image rows = the high screen rows
+        units = set(calls[0][3])
+        assert units == ({(0, 0, 100)} if rank == 0 else {(2, 0, 100)})  # lights 0 and 2 cast: one whole map per rank
