@@ -5,7 +5,7 @@ PRC_TEST_PEER=1 so that the round-end `pytest -m gpu` exercises only verified pa
 the same check is tests/multigpu_check.py (torchrun, one process per GPU, CUDA IPC).
 
   world = 1 : the whole protocol with no peer (waits and signals are skipped), 1 GPU
-  world = 2 : two contexts of ONE process on two GPUs (the library uses the peers' pointers directly instead of
+  world = 2 : two contexts of ONE process, on one GPU and on two GPUs (the library uses the peers' pointers directly instead of
               IPC handles); frames are submitted to both contexts from this single host thread, which only works
               because nothing in prc_render_peer waits on the host
 """
@@ -75,6 +75,21 @@ def _run(devices, frames=3):
 def test_peer_world1_equals_render(monkeypatch):
     monkeypatch.setenv("PRC_FMA", "exact")
     ref, out = _run([0])
+    assert int((ref != out).any(axis=2).sum()) == 0
+
+
+def test_peer_two_contexts_one_gpu(monkeypatch):
+    """Two ranks on ONE GPU (two contexts, two streams): the whole protocol — sparse shadow push, epoch signals, strip copy —
+    without needing a second device. The one-warp wait kernels leave the GPU free for the other context's kernels."""
+    monkeypatch.setenv("PRC_FMA", "exact")
+    ref, out = _run([0, 0])
+    assert int((ref != out).any(axis=2).sum()) == 0
+
+
+def test_peer_three_ranks_ragged_rows_one_gpu(monkeypatch):
+    """Strips and shadow shards that do not divide evenly (272 rows over 3 ranks; 4 maps over 3 ranks = units that span two lights)."""
+    monkeypatch.setenv("PRC_FMA", "mixed")
+    ref, out = _run([0, 0, 0], frames=2)
     assert int((ref != out).any(axis=2).sum()) == 0
 
 
