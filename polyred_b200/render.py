@@ -370,7 +370,36 @@ class Renderer:
             out = np.zeros((c.Height, c.Width, 4), np.uint8)
             self._backend.render(fd, out)
         self._last_frame = fd
+        if c.Debug:
+            self._debug_report()
         return out
+
+    def shadow_map_image(self, index: int) -> np.ndarray:
+        """The picture passShadows saves as shadow-<index>.png under render.Debug(true) (render/shadow.go:98-118):
+        pixel (i, j) = uint8(depths[i + (H-j-1)*W] * 255) in R, G and B, alpha 255."""
+        c = self.cfg
+        W, H = c.Width * c.MSAA, c.Height * c.MSAA
+        z = self._backend.read_shadowmap(index, W, H)[::-1]  # image row j = map row H-1-j
+        g = (z.astype(np.float32) * f32(255)).astype(np.int64).astype(np.uint8)  # Go's uint8(float32): truncation; depths lie in [0, 1]
+        return np.stack([g, g, g, np.full_like(g, 255)], axis=2)
+
+    def _debug_report(self, directory: str = "."):
+        """render.Debug(true): per-pass timings (profiling.Timed, raster.go:156-161) and one shadow-<i>.png per casting
+        light (shadow.go:98-118), written like the reference does into the working directory."""
+        import os
+        c = self.cfg
+        if hasattr(self._backend, "timings"):
+            t = self._backend.timings()
+            print(f"forward pass (shadow): {t.shadow_ms:.3f} ms\nforward pass (world): {t.forward_ms:.3f} ms\n"
+                  f"deferred pass (shading): {t.shade_ms:.3f} ms\nentire rendering: {t.total_ms:.3f} ms")
+        if c.ShadowMap:
+            from PIL import Image
+            sources, _ = c.Scene.Lights()
+            for i, l in enumerate(sources):
+                if l.cast_shadow:
+                    file = os.path.join(directory, f"shadow-{i}.png")
+                    print(f"saving (shadow map)... {file}")
+                    Image.fromarray(self.shadow_map_image(i), "RGBA").save(file)
 
 
 def ViewFrames(r: Renderer, cameras) -> list:

@@ -203,10 +203,28 @@ def test_benchmark_coverage_and_shadow_map_dump():
     gold_cov = np.unpackbits(z["covered"])[:960 * 540].reshape(540, 960).astype(bool)
     assert int(((img[..., 3] > 0) ^ gold_cov).sum()) == 0 and int(gold_cov.sum()) == 172805
     dump = _golden("benchmark_shadow-0.png")[..., 0]
-    sm = be.read_shadowmap(0, 960, 540)
-    mine = (sm[::-1] * np.float32(255)).astype(np.float32).astype(np.int64).astype(np.uint8)  # shadow.go:101-113
+    mine = r.shadow_map_image(0)  # what render.Debug(true) saves as shadow-0.png (shadow.go:98-118)
+    assert np.array_equal(mine[..., 0], mine[..., 1]) and np.array_equal(mine[..., 0], mine[..., 2]) and (mine[..., 3] == 255).all()
+    mine = mine[..., 0]
     assert int((dump > 0).sum()) == 29590
     assert int(((dump > 0) ^ (mine > 0)).sum()) == 0 and int(np.abs(dump.astype(int) - mine.astype(int)).max()) == 0
+
+
+def test_debug_option_dumps_shadow_maps(tmp_path, monkeypatch, capsys):
+    """render.Debug(true) (render/options.go:101-107): timings are printed and passShadows saves shadow-<i>.png for every
+    casting light into the working directory (render/shadow.go:98-118)."""
+    from PIL import Image
+    s, _ = _benchmark_scene()
+    cam = camera.Perspective(position=(0, 0.6, 0.9), fov=45, aspect=16 / 9, near=0.1, far=2)
+    be = ob.OracleBackend()
+    r = render.NewRenderer(render.Camera(cam), render.Size(192, 108), render.Scene(s), render.ShadowMap(True), render.Debug(True), render._Backend(be))
+    monkeypatch.chdir(tmp_path)
+    r.Render()
+    assert "saving (shadow map)... ./shadow-0.png" in capsys.readouterr().out
+    dump = np.asarray(Image.open(tmp_path / "shadow-0.png").convert("RGBA"))
+    assert dump.shape == (108, 192, 4) and np.array_equal(dump, r.shadow_map_image(0)) and int((dump[..., 0] > 0).sum()) > 500
+    z = be.read_shadowmap(0, 192, 108)
+    assert dump[10, 20, 0] == int(np.float32(z[108 - 1 - 10, 20]) * np.float32(255))  # pixel (i, j) = depths[i + (H-j-1)*W]
 
 
 def test_shadow_maps_persist_and_reset():
