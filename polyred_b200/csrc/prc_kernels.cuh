@@ -494,8 +494,37 @@ __device__ __forceinline__ void geom_classify(const DevScene& S, const DevFrame&
     return;
   }
   // candidate pixels of the box (render/raster.go:481-499 / render/shadow.go:191-215) -> CTA queue
+#if PRC_WARP_QUEUE
+  // Tuning variant (build with EXTRA=-DPRC_WARP_QUEUE=1, load with PRC_LIB; NOT the default and not yet measured): one
+  // shared-memory atomicAdd per converged group of lanes instead of one per lane — ncu charged the per-lane atomic 16 % of
+  // the kernel's stall samples for 2 % of its instructions. area <= 16 fits 5 bits: the exclusive prefix over the
+  // (arbitrary) set of converged lanes is five ballots; any grouping is correct, slots only have to be disjoint.
+  unsigned int base;
+  bool group_fits;
+  {
+    const unsigned int m = __activemask(), lt = (1u << (threadIdx.x & 31)) - 1u;
+    unsigned int pre = 0, tot = 0;
+#pragma unroll
+    for (int b = 0; b < 5; b++) {
+      const unsigned int bal = __ballot_sync(m, ((unsigned int)area >> b) & 1u);
+      pre += (unsigned int)__popc(bal & lt) << b;
+      tot += (unsigned int)__popc(bal) << b;
+    }
+    const int leader = __ffs(m) - 1;
+    unsigned int wb = 0;
+    if ((int)(threadIdx.x & 31) == leader) wb = atomicAdd(&sm.qn[qsel], tot);
+    wb = __shfl_sync(m, wb, leader);
+    base = wb + pre;
+    group_fits = wb + tot <= PRC_QCAP;
+    if (group_fits && (int)(threadIdx.x & 31) == leader) atomicMax(&sm.qv[qsel], wb + tot);  // one update of the valid length per group
+  }
+#else
   const unsigned int base = atomicAdd(&sm.qn[qsel], (unsigned int)area);
+#endif
   if (base + area <= PRC_QCAP) {
+#if PRC_WARP_QUEUE
+    if (!group_fits)
+#endif
     atomicMax(&sm.qv[qsel], base + area);
     sm.idx[threadIdx.x] = li;
     sm.box[threadIdx.x] = (uint32_t)x0 | ((uint32_t)y0 << 14) | ((uint32_t)(bw - 1) << 28);
