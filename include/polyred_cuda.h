@@ -244,6 +244,9 @@ int32_t prc_render(prc_ctx* ctx, const prc_frame* frame, uint8_t* rgba_out);
 int32_t prc_host_image(prc_ctx* ctx, uint64_t* host_ptr, uint64_t* bytes);
 int32_t prc_read_gbuffer(prc_ctx* ctx, prc_gbuffer_host* out);
 int32_t prc_read_shadowmap(prc_ctx* ctx, uint32_t light, float* out /* [width*height], idx = x + y*width */);
+/* The device-resident RGBA8 image (width*height*4 bytes, image order, before any MSAA downsample) copied to host memory:
+ * debug/parity view of frames rendered with PRC_FRAME_NO_READBACK (buf.Image(), buffer/buffer.go:160-166). Waits for the stream. */
+int32_t prc_read_image(prc_ctx* ctx, uint8_t* rgba_out);
 int32_t prc_get_timings(prc_ctx* ctx, prc_timings* out);
 
 /* ---- multi-GPU plumbing (one process per GPU; collectives are driven by the host through

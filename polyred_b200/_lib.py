@@ -41,6 +41,7 @@ def lib():
         L.prc_read_gbuffer.argtypes = [vp, C.POINTER(A.prc_gbuffer_host)]
         L.prc_read_shadowmap.argtypes = [vp, C.c_uint32, vp]
         L.prc_get_timings.argtypes = [vp, C.POINTER(A.prc_timings)]
+        L.prc_read_image.argtypes = [vp, vp]
         L.prc_device_image.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.prc_device_shadowmap.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.prc_render_shadows.argtypes = [vp, C.POINTER(A.prc_frame), C.c_uint32, C.c_uint32, C.c_uint32]
@@ -61,7 +62,7 @@ def lib():
                      "prc_read_shadowmap", "prc_get_timings", "prc_device_image", "prc_device_shadowmap",
                      "prc_render_shadows", "prc_render_main", "prc_stream", "prc_sync", "prc_host_image", "prc_render_forward",
                      "prc_render_deferred", "prc_device_shadow_all", "prc_render_shadow_units", "prc_peer_export", "prc_peer_connect",
-                     "prc_peer_disconnect", "prc_render_peer", "prc_set_exact_fma"):
+                     "prc_peer_disconnect", "prc_render_peer", "prc_set_exact_fma", "prc_read_image"):
             getattr(L, name).restype = C.c_int32
         if L.prc_abi_version() != A.PRC_ABI_VERSION:
             raise PolyredCudaError(A.PRC_ERR_INVALID, "ABI version mismatch")
@@ -149,6 +150,12 @@ class CudaBackend(Backend):
             buf = (C.c_uint8 * n.value).from_address(p.value)
             views[key] = np.frombuffer(buf, dtype=np.uint8).reshape(h, w, 4)
         return views[key]
+
+    def read_image(self, w, h) -> np.ndarray:
+        """The device-resident frame (PRC_FRAME_NO_READBACK) copied to a fresh host array."""
+        out = np.zeros((h, w, 4), np.uint8)
+        self._check(self.L.prc_read_image(self.h, out.ctypes.data))
+        return out
 
     def device_image(self):
         p, n, cap = C.c_uint64(), C.c_uint64(), C.c_uint64()

@@ -1074,6 +1074,15 @@ int32_t prc_read_shadowmap(prc_ctx* ctx, uint32_t light, float* out) {
   return PRC_OK;
 }
 
+int32_t prc_read_image(prc_ctx* ctx, uint8_t* rgba_out) {
+  if (!ctx || !rgba_out) return PRC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->d_image.p || !ctx->W) { ctx->err = "no frame rendered yet"; return PRC_ERR_INVALID; }
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(rgba_out, ctx->d_image.p, (size_t)ctx->W * ctx->H * 4, cudaMemcpyDeviceToHost));
+  return PRC_OK;
+}
+
 int32_t prc_get_timings(prc_ctx* ctx, prc_timings* out) {
   if (!ctx || !out) return PRC_ERR_INVALID;
   if (ctx->pending_async) { const int32_t pr_ = prc_sync(ctx); if (pr_ != PRC_OK) return pr_; }  // finish asynchronous frames first

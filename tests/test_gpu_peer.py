@@ -1,8 +1,8 @@
 """-m gpu: frames over NVLink peer memory (prc_render_peer) must equal the 1-GPU frame bit for bit.
 
-NOT YET RUN ON HARDWARE (written after round 1's GPU budget was spent): the tests are opt-in through
-PRC_TEST_PEER=1 so that the round-end `pytest -m gpu` exercises only verified paths. The multi-process form of
-the same check is tests/multigpu_check.py (torchrun, one process per GPU, CUDA IPC).
+Run on one B200 at the end of round 1 as tools/peer_selfcheck.py (profiles/peer_selfcheck_r1.log: 1, 2 and 3 ranks on one
+GPU, 0 differing pixels, 0 differing shadow texels); the multi-process form of the same check (CUDA IPC, one process per GPU) is
+the peer leg of tests/multigpu_check.py. PRC_TEST_PEER=0 skips this file.
 
   world = 1 : the whole protocol with no peer (waits and signals are skipped), 1 GPU
   world = 2 : two contexts of ONE process, on one GPU and on two GPUs (the library uses the peers' pointers directly instead of
@@ -17,7 +17,7 @@ import pytest
 from polyred_b200 import _abi as A
 from polyred_b200 import partition, render, synth
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("PRC_TEST_PEER") != "1", reason="opt-in: PRC_TEST_PEER=1 (not yet verified on hardware)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("PRC_TEST_PEER") == "0", reason="PRC_TEST_PEER=0")]
 
 
 def _scene():
@@ -27,13 +27,6 @@ def _scene():
 
 def _opts(s, cam, w, h):
     return [render.Camera(cam), render.Size(w, h), render.Scene(s), render.ShadowMap(True), render.GammaCorrection(True)]
-
-
-def _device_image(be, w, h):
-    import torch
-    from polyred_b200.distributed import _cai
-    ptr, nbytes, _ = be.device_image()
-    return torch.as_tensor(_cai(ptr, nbytes), device=torch.device("cuda", be.device)).cpu().numpy().reshape(h, w, 4)
 
 
 def _group(s, cam, w, h, devices):
@@ -66,7 +59,7 @@ def _run(devices, frames=3):
             r._backend.render_peer(fds[k], mine[k], 1)
     for r in rs:
         r._backend.sync()
-    out = _device_image(rs[0]._backend, w, h)
+    out = rs[0]._backend.read_image(w, h)
     for r in rs:
         r._backend.peer_disconnect()
     return ref, out
@@ -88,8 +81,8 @@ def test_peer_two_contexts_one_gpu(monkeypatch):
 
 def test_peer_three_ranks_ragged_rows_one_gpu(monkeypatch):
     """Strips and shadow shards that do not divide evenly (272 rows over 3 ranks; 4 maps over 3 ranks = units that span two lights)."""
-    monkeypatch.setenv("PRC_FMA", "mixed")
-    ref, out = _run([0, 0, 0], frames=2)
+    monkeypatch.setenv("PRC_FMA", "exact")
+    ref, out = _run([0, 0, 0], frames=3)
     assert int((ref != out).any(axis=2).sum()) == 0
 
 

@@ -1,0 +1,88 @@
+#!/usr/bin/env python
+"""Quick hardware check of prc_render_peer on ONE GPU, no torch import (starts in a few seconds):
+world = 1, then two and three ranks as contexts of this one process on device 0 (tests/test_gpu_peer.py as a script).
+    python tools/peer_selfcheck.py [max_world]
+Prints one line per case; exit status 0 iff every frame equals the 1-GPU frame bit for bit."""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("PRC_FMA", "exact")
+
+T0 = time.perf_counter()
+
+
+def log(msg):
+    print(f"[peer_selfcheck {time.perf_counter() - T0:6.2f}s] {msg}", flush=True)
+
+
+def main():
+    import numpy as np
+    from polyred_b200 import partition, render, synth
+    max_world = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+    w, h = 480, 272
+    s, cam = synth.city_scene(n_objects=25, obj_stacks=20, obj_slices=20, ground_cells=60, tex_size=64)
+    opts = [render.Camera(cam), render.Size(w, h), render.Scene(s), render.ShadowMap(True), render.GammaCorrection(True)]
+    log("scene built")
+    ref = render.NewRenderer(*opts, render.CUDA(0)).Render().copy()
+    log(f"1-GPU reference frame rendered ({int((ref[..., 3] > 0).sum())} px with alpha)")
+    sources, _ = s.Lights()
+    cast = [i for i, l in enumerate(sources) if l.cast_shadow]
+    bad = 0
+    for world in range(1, max_world + 1):
+        _, rows = partition.strips(h, world)
+        units = partition.shadow_units(h, world, cast)
+        rs, fds, handles = [], [], []
+        for k in range(world):
+            r = render.NewRenderer(*opts, render.CUDA(0))
+            r._ensure_uploaded()
+            fd = r.frame_desc(no_readback=True)
+            fd.struct.row0, fd.struct.row1 = rows[k]
+            handles.append(r._backend.peer_export(fd))
+            rs.append(r)
+            fds.append(fd)
+        for k, r in enumerate(rs):
+            r._backend.peer_connect(k, world, handles)
+        mine = [[(li, a, b) for li, a, b, owner in units if owner == k] for k in range(world)]
+        t = time.perf_counter()
+        status = "ok"
+        try:
+            for _ in range(3):
+                for k, r in enumerate(rs):
+                    r._backend.render_peer(fds[k], mine[k], 1)
+            for r in rs:
+                r._backend.sync()
+        except Exception as e:  # noqa: BLE001 - report and go on to the comparison
+            status = f"ERROR {e}"
+        dt = time.perf_counter() - t
+        out = rs[0]._backend.read_image(w, h)
+        nd = int((ref != out).any(axis=2).sum())
+        # where do differing pixels lie? (which strip: tells a missing strip copy from a missing shadow push)
+        per_strip = [int((ref[h - r1:h - r0] != out[h - r1:h - r0]).any(axis=2).sum()) for r0, r1 in rows]
+        sm_diff = []
+        for li in cast:
+            m0 = rs[0]._backend.read_shadowmap(li, w, h)
+            full = np.zeros_like(m0)
+            for k, r in enumerate(rs):
+                mk = r._backend.read_shadowmap(li, w, h)
+                for lj, a, b, owner in units:
+                    if lj == li and owner == k:
+                        full[a:b] = mk[a:b]
+            sm_diff.append(int((m0 != full).sum()))
+        log(f"world={world}: {status}; 3 frames in {dt * 1e3:.1f} ms; pixels differing from the 1-GPU frame = {nd} (per strip {per_strip}); "
+            f"rank 0's shadow texels differing from the owners' rows = {sm_diff}")
+        bad += nd + (status != "ok")
+        for r in rs:
+            try:
+                r._backend.peer_disconnect()
+            except Exception as e:  # noqa: BLE001
+                log(f"disconnect: {e}")
+            r._backend.close()
+    log("PASS" if bad == 0 else "FAIL")
+    return 0 if bad == 0 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
