@@ -1224,14 +1224,25 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
   }
   CK(cudaEventRecord(ctx->ev[0], st));
   const bool shadows = (fr->flags & PRC_FRAME_SHADOWMAP) && ctx->n_cast_alloc > 0 && ctx->n_cast_alloc != 0xFFFFFFFFu;
+  // PRC_PEER_ONE_FLUSH=1 (tuning, not yet measured): the large shadow triangles wait for the camera pass's tile path (one
+  // binning + tile-raster round per frame, as on one GPU) and the push follows it; default: the shadow phase flushes its own
+  // queue so that the push leaves before the camera pass.
+  static const bool one_flush = getenv("PRC_PEER_ONE_FLUSH") != nullptr && atoi(getenv("PRC_PEER_ONE_FLUSH")) != 0;
+  PushUnits U{};
+  bool vec4 = true;
+  auto push_and_signal = [&]() {
+    if (U.n && P.world > 1) {
+      if (vec4) k_shadow_push<4><<<148 * 8, 256, 0, st>>>(P, U);
+      else k_shadow_push<1><<<148 * 8, 256, 0, st>>>(P, U);
+      ctx->launches++;
+    }
+    peer_signal(ctx, PRC_SIG_SHADOW, e, all);
+  };
   if (shadows) {
     // nobody may still be shading the previous frame from the maps this rank is about to store into
     peer_wait(ctx, PRC_SIG_SHADED, e - 1, all);
-    int32_t r = do_shadows<E>(ctx, fr, F, units, true);
+    int32_t r = do_shadows<E>(ctx, fr, F, units, !one_flush);
     if (r != PRC_OK) return r;
-    PushUnits U{};
-    const size_t npx = (size_t)F.W * F.H;
-    bool vec4 = true;
     for (const ShadowUnit& u : units) {
       if (u.light >= fr->n_lights || !fr->lights[u.light].cast_shadow || u.r0 >= u.r1) continue;
       if (U.n == 32) { ctx->err = "more than 32 shadow units in one prc_render_peer call"; return PRC_ERR_UNSUPPORTED; }
@@ -1240,18 +1251,13 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
       vec4 = vec4 && (U.off[U.n] % 4 == 0) && (U.cnt[U.n] % 4 == 0);
       U.n++;
     }
-    (void)npx;
-    if (U.n && P.world > 1) {
-      if (vec4) k_shadow_push<4><<<148 * 8, 256, 0, st>>>(P, U);
-      else k_shadow_push<1><<<148 * 8, 256, 0, st>>>(P, U);
-      ctx->launches++;
-    }
-    peer_signal(ctx, PRC_SIG_SHADOW, e, all);
+    if (!one_flush) push_and_signal();
   }
   CK(cudaEventRecord(ctx->ev[1], st));
   ctx->rb_dst = nullptr;
   int32_t r = do_main<E>(ctx, fr, F, 1);  // camera geometry + raster + resolve: needs no shadow map, overlaps the peers' pushes
   if (r != PRC_OK) return r;
+  if (shadows && one_flush) push_and_signal();
   if (shadows) peer_wait(ctx, PRC_SIG_SHADOW, e, all);
   r = do_main<E>(ctx, fr, F, 2);
   if (r != PRC_OK) return r;
