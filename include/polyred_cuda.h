@@ -49,7 +49,7 @@ extern "C" {
 #define PRC_ERR_CUDA -2         /* CUDA runtime error, see prc_last_error */
 #define PRC_ERR_UNSUPPORTED -3  /* scene/option the path does not implement (no fallback) */
 #define PRC_ERR_NO_SCENE -4
-#define PRC_ERR_NCCL -5
+#define PRC_ERR_NCCL -5          /* reserved: collectives are driven by the host (torch.distributed), the library itself never calls NCCL */
 #define PRC_ERR_RETRY -6        /* prc_sync after PRC_FRAME_ASYNC frames: a queue overflowed, it has been grown; submit those frames again */
 #define PRC_ERR_PEER -7         /* prc_sync after prc_render_peer frames: a wait for a peer rank timed out (the frames are invalid) */
 

@@ -46,7 +46,7 @@ struct prc_ctx {
   // frame buffers
   int W = 0, H = 0;
   DBuf d_keys, d_ga, d_gb, d_gc, d_gd, d_ao, d_image, d_special, d_counters;
-  DBuf d_large, d_clipq, d_tilecount, d_tilestart, d_cursor, d_bins, d_active, d_chunksum, d_targets, d_frame_sh;
+  DBuf d_large, d_clipq, d_tilecount, d_tilestart, d_cursor, d_bins, d_active, d_chunksum, d_targets;
   uint32_t n_targets = 1;
   uint32_t target_of_light[64] = {0};
   bool light_affine[64] = {false};
@@ -178,6 +178,7 @@ uint32_t plain_mask(const float* m) {
 }
 
 inline unsigned int cdiv(unsigned long long a, unsigned int b) { return (unsigned int)((a + b - 1) / b); }
+inline size_t ipc_round(size_t bytes) { return (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1); }
 
 // ---- one raster pass (camera, or up to 8 shadow views in one sweep): geometry + small raster through the CTA queue; large triangles and
 // (camera only) triangles needing clipping are queued. No host round trip. -----------------------------------
@@ -287,7 +288,9 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
   ENSURE(ctx->d_keys, npx * 8);
   ENSURE(ctx->d_ga, npx * 16); ENSURE(ctx->d_gb, npx * 16); ENSURE(ctx->d_gc, npx * 16); ENSURE(ctx->d_gd, npx * 16);
   if (ctx->any_ao) ENSURE(ctx->d_ao, npx * 4);
-  ENSURE(ctx->d_image, npx * 4 + (size_t)64 * W * 4);  // slack: the multi-GPU image all-gather uses equal, padded strips
+  // slack: the multi-GPU image all-gather uses equal, padded strips. Whole 2 MiB pages: the buffer can be exported through CUDA
+  // IPC (prc_peer_export), which shares entire allocation blocks — an exported buffer must not share its block with others
+  ENSURE(ctx->d_image, ipc_round(npx * 4 + (size_t)64 * W * 4));
   ENSURE(ctx->d_special, 16);
   const int n_tiles = ((W + PRC_TILE - 1) / PRC_TILE) * ((H + PRC_TILE - 1) / PRC_TILE);
   // targets of the tile path: 0 = camera, 1 + k = k-th casting light
@@ -326,7 +329,7 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
     }
     if (!same) {  // new set of casting lights: fresh zero maps (what initShadowMaps does, shadow.go:87)
       realloc_shadow = true;
-      const size_t bytes = ((size_t)ncast * npx + (size_t)64 * W) * 4;  // slack: the all-gather chunks are padded
+      const size_t bytes = ipc_round(((size_t)ncast * npx + (size_t)64 * W) * 4);  // slack: the all-gather chunks are padded; whole 2 MiB pages (IPC export)
       ENSURE(ctx->d_shadow_all, bytes);
       CK(cudaMemsetAsync(ctx->d_shadow_all.p, 0, bytes, st));
       for (uint32_t i = 0, k = 0; i < fr->n_lights; i++) {
@@ -744,7 +747,7 @@ int32_t prc_close(prc_ctx* ctx) {
   DBuf* all[] = {&ctx->d_pos, &ctx->d_nor, &ctx->d_uv, &ctx->d_col, &ctx->d_mat, &ctx->d_meta, &ctx->d_mats, &ctx->d_objstart, &ctx->d_texfirst,
                  &ctx->d_lw, &ctx->d_lh, &ctx->d_loff, &ctx->d_tex, &ctx->d_keys, &ctx->d_ga, &ctx->d_gb, &ctx->d_gc, &ctx->d_gd, &ctx->d_ao,
                  &ctx->d_image, &ctx->d_special, &ctx->d_counters, &ctx->d_large, &ctx->d_clipq, &ctx->d_tilecount, &ctx->d_tilestart, &ctx->d_cursor,
-                 &ctx->d_bins, &ctx->d_active, &ctx->d_chunksum, &ctx->d_targets, &ctx->d_frame_sh, &ctx->d_xf, &ctx->d_lights, &ctx->d_ambient, &ctx->d_gamma, &ctx->d_frame, &ctx->d_aoc, &ctx->d_chunkbox, &ctx->d_vis, &ctx->d_cverts, &ctx->d_cvoff, &ctx->d_lidx, &ctx->d_image_out, &ctx->d_rz_cx, &ctx->d_rz_sx, &ctx->d_rz_cy, &ctx->d_rz_sy};
+                 &ctx->d_bins, &ctx->d_active, &ctx->d_chunksum, &ctx->d_targets, &ctx->d_xf, &ctx->d_lights, &ctx->d_ambient, &ctx->d_gamma, &ctx->d_frame, &ctx->d_aoc, &ctx->d_chunkbox, &ctx->d_vis, &ctx->d_cverts, &ctx->d_cvoff, &ctx->d_lidx, &ctx->d_image_out, &ctx->d_rz_cx, &ctx->d_rz_sx, &ctx->d_rz_cy, &ctx->d_rz_sy};
   for (DBuf* b : all) free_buf(*b);
   free_buf(ctx->d_shadow_all);
   for (auto& b : ctx->d_shadow_trans) free_buf(b);
@@ -1293,7 +1296,7 @@ int32_t prc_peer_export(prc_ctx* ctx, const prc_frame* fr, prc_peer_handle* out)
   DevFrame F;
   int32_t r = build_frame(ctx, fr, F);  // allocates (and, for a new size / light set, zeroes) the shadow and image buffers
   if (r != PRC_OK) return r;
-  ENSURE(ctx->d_peer_signals, (size_t)PRC_SIG_KINDS * PRC_PEER_MAX * 4);
+  ENSURE(ctx->d_peer_signals, ipc_round((size_t)PRC_SIG_KINDS * PRC_PEER_MAX * 4));  // its own 2 MiB block (see build_frame)
   ENSURE(ctx->d_peer_err, 16);
   CK(cudaMemsetAsync(ctx->d_peer_signals.p, 0, (size_t)PRC_SIG_KINDS * PRC_PEER_MAX * 4, ctx->stream));
   CK(cudaMemsetAsync(ctx->d_peer_err.p, 0, 16, ctx->stream));
