@@ -116,7 +116,7 @@ class PeerFrames:
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         if group is None:
-            # host-only plumbing (64-byte handles, one retry vote per finish()): keep it off the GPUs when gloo is usable
+            # host-only plumbing (272-byte handles, one status vote per finish()): keep it off the GPUs when gloo is usable
             try:
                 group = dist.new_group(backend="gloo")
             except Exception:  # noqa: BLE001 - same outcome on every rank of a node; the default (NCCL) group works too
@@ -137,11 +137,33 @@ class PeerFrames:
         self._connect(renderer.frame_desc(no_readback=True))
 
     def _connect(self, fd):
-        handle = self.be.peer_export(self.prepare(fd))
+        """Export, exchange, connect. Every rank performs the same two host collectives whatever happens locally, so a failure on
+        one rank (no peer access, IPC refused) surfaces as an exception on ALL ranks instead of a hang in a collective."""
+        from ._lib import PolyredCudaError
+        from . import _abi as A
+        err = handle = None
+        try:
+            handle = self.be.peer_export(self.prepare(fd))
+        except PolyredCudaError as e:
+            err = str(e)
         handles = [None] * self.world
         self.dist.all_gather_object(handles, handle, group=self.group)
-        self.be.peer_connect(self.rank, self.world, handles)
-        self.dist.barrier(group=self.group)  # nobody signals before everybody has zeroed its words and mapped its peers
+        if err is None and all(h is not None for h in handles):
+            try:
+                self.be.peer_connect(self.rank, self.world, handles)
+            except PolyredCudaError as e:
+                err = str(e)
+        elif err is None:
+            err = "a peer could not export its buffers"
+        # doubles as the barrier: nobody signals before everybody has zeroed its words and mapped its peers
+        errs = [None] * self.world
+        self.dist.all_gather_object(errs, err, group=self.group)
+        if any(e is not None for e in errs):
+            try:
+                self.be.peer_disconnect()
+            except PolyredCudaError:
+                pass
+            raise PolyredCudaError(A.PRC_ERR_PEER, "PeerFrames: connecting the ranks failed: " + "; ".join(f"rank {k}: {e}" for k, e in enumerate(errs) if e))
 
     def prepare(self, fd):
         fd.struct.row0, fd.struct.row1 = self.rows[self.rank]
@@ -158,16 +180,18 @@ class PeerFrames:
         from ._lib import PolyredCudaError
         from . import _abi as A
         for _ in range(max_retries + 1):
-            retry = 0
+            vote = (0, "")
             try:
                 self.be.sync()
             except PolyredCudaError as e:
-                if e.code != A.PRC_ERR_RETRY:
-                    raise
-                retry = 1
-            votes = [0] * self.world
-            self.dist.all_gather_object(votes, retry, group=self.group)
-            if not any(votes):
+                vote = (e.code, str(e))
+            votes = [None] * self.world
+            self.dist.all_gather_object(votes, vote, group=self.group)  # same collective on every rank, error or not
+            fatal = [(k, c, m) for k, (c, m) in enumerate(votes) if c not in (0, A.PRC_ERR_RETRY)]
+            if fatal:
+                self._submitted = []
+                raise PolyredCudaError(fatal[0][1], "PeerFrames: " + "; ".join(f"rank {k}: {m}" for k, _, m in fatal))
+            if not any(c for c, _ in votes):
                 self._submitted = []
                 return
             again, self._submitted = self._submitted, []

@@ -80,8 +80,9 @@ def test_two_rank_exchange_reassembles_the_frame():
 class _FakeBackend:
     """Stands in for CudaBackend on CPU: records the prc_render_peer calls; rank 1's first prc_sync reports a grown queue."""
 
-    def __init__(self, rank):
+    def __init__(self, rank, fail_connect=False, fail_sync=None):
         self.rank, self.calls, self.syncs, self.connected = rank, [], 0, None
+        self.fail_connect, self.fail_sync = fail_connect, fail_sync
 
     def peer_export(self, fd):
         from polyred_b200 import _abi as A
@@ -90,6 +91,10 @@ class _FakeBackend:
         return bytes(h)
 
     def peer_connect(self, rank, world, handles):
+        if self.fail_connect:
+            from polyred_b200 import _abi as A
+            from polyred_b200._lib import PolyredCudaError
+            raise PolyredCudaError(A.PRC_ERR_CUDA, "cudaIpcOpenMemHandle: refused")
         self.connected = (rank, world, [len(b) for b in handles])
 
     def render_peer(self, fd, units, image_mask):
@@ -99,6 +104,8 @@ class _FakeBackend:
         from polyred_b200 import _abi as A
         from polyred_b200._lib import PolyredCudaError
         self.syncs += 1
+        if self.fail_sync is not None:
+            raise PolyredCudaError(self.fail_sync, "a device-side wait for a peer rank timed out")
         if self.rank == 1 and self.syncs == 1:
             raise PolyredCudaError(A.PRC_ERR_RETRY, "queue grown")
 
@@ -126,7 +133,23 @@ def _peer_worker(rank, world, port, q):
     for k in range(3):
         pf.submit(frame(k))
     pf.finish()
-    q.put((rank, be.connected, be.calls, be.syncs, len(pf._submitted)))
+    # failures on ONE rank must surface on BOTH (every rank runs the same host collectives, error or not): no hang
+    from polyred_b200._lib import PolyredCudaError
+    r.group = pf.group
+    seen = []
+    try:
+        r._backend = _FakeBackend(rank, fail_connect=(rank == 1))
+        PeerFrames(r, rank, world, 0, root=0, group=pf.group)
+    except PolyredCudaError as e:
+        seen.append(("connect", e.code, "rank 1" in str(e)))
+    r._backend = _FakeBackend(rank, fail_sync=(A.PRC_ERR_PEER if rank == 0 else None))
+    pf2 = PeerFrames(r, rank, world, 0, root=0, group=pf.group)
+    pf2.submit(frame(7))
+    try:
+        pf2.finish()
+    except PolyredCudaError as e:
+        seen.append(("finish", e.code, "rank 0" in str(e)))
+    q.put((rank, be.connected, be.calls, be.syncs, len(pf._submitted), seen))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -148,7 +171,8 @@ def test_peer_frames_host_logic_two_ranks():
         assert p.exitcode == 0
     import ctypes as C
     from polyred_b200 import _abi as A
-    for rank, connected, calls, syncs, left in res:
+    for rank, connected, calls, syncs, left, seen in res:
+        assert seen == [("connect", A.PRC_ERR_PEER, True), ("finish", A.PRC_ERR_PEER, True)], seen
         assert connected == (rank, 2, [C.sizeof(A.prc_peer_handle)] * 2)
         assert [c[0] for c in calls] == [0, 1, 2, 0, 1, 2] and syncs == 2 and left == 0  # one retry, on both ranks
         assert all(c[4] == 1 for c in calls)  # the image goes to rank 0
