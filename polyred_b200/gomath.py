@@ -111,9 +111,12 @@ def identity():
 def mulm(m, n):
     """Mat4.MulM (math/mat4.go:201-220): each element ((a*b + c*d) + e*f) + g*h in float32."""
     m, n = _a(m), _a(n)
+    if m.ndim == 2 and n.ndim == 2:
+        # one matrix: all 16 elements at once (element [i, j] of every numpy operation is exactly that element's scalar operation)
+        return ((m[:, 0, None] * n[None, 0, :] + m[:, 1, None] * n[None, 1, :]) + m[:, 2, None] * n[None, 2, :]) + m[:, 3, None] * n[None, 3, :]
     shape = np.broadcast_shapes(m.shape, n.shape)
     out = np.empty(shape, dtype=np.float32)
-    for i in range(4):
+    for i in range(4):  # batches: 16 passes over contiguous-ish columns beat 7 broadcasts over 4x4 inner blocks
         for j in range(4):
             out[..., i, j] = m[..., i, 0] * n[..., 0, j] + m[..., i, 1] * n[..., 1, j] + m[..., i, 2] * n[..., 2, j] + m[..., i, 3] * n[..., 3, j]
     return out
@@ -160,24 +163,38 @@ _INV_TERMS = {
 }
 
 
-def _eval_terms(m, terms):
-    acc = None
+def _parse(terms):
+    """'+00.11.22 -...' -> (signs [T] of +-1, rows [T, F], cols [T, F])"""
+    sg, rr, cc = [], [], []
     for t in terms.split():
-        sign, facs = t[0], t[1:].split(".")
-        p = None
-        for fcode in facs:
-            e = m[..., int(fcode[0]), int(fcode[1])]
-            p = e if p is None else p * e
-        if acc is None:
-            acc = p if sign == "+" else -p
-        else:
-            acc = acc + p if sign == "+" else acc - p
-    return acc
+        sg.append(1.0 if t[0] == "+" else -1.0)
+        facs = t[1:].split(".")
+        rr.append([int(f[0]) for f in facs])
+        cc.append([int(f[1]) for f in facs])
+    return np.array(sg, np.float32), np.array(rr), np.array(cc)
+
+
+_DET_P = _parse(_DET_TERMS)
+# the 16 cofactor sums evaluated together: term k of every entry, entries in row-major order -> index arrays [6, 16, 3]
+_INV_P = [_parse(_INV_TERMS[(i, j)]) for i in range(4) for j in range(4)]
+_INV_SG = np.stack([p[0] for p in _INV_P], axis=1)   # [6, 16]
+_INV_R = np.stack([p[1] for p in _INV_P], axis=1)    # [6, 16, 3]
+_INV_C = np.stack([p[2] for p in _INV_P], axis=1)
 
 
 def det(m):
-    """Mat4.Det (math/mat4.go:233-247)."""
-    return _eval_terms(_a(m), _DET_TERMS)
+    """Mat4.Det (math/mat4.go:233-247): 24 signed products of four elements, each multiplied left to right, summed in the
+    reference's order. (x - p and x + (-p) are the same IEEE operation, so a term's sign is applied to its product.)"""
+    m = _a(m)
+    sg, rr, cc = _DET_P
+    p = m[..., rr[:, 0], cc[:, 0]]
+    for f in range(1, 4):
+        p = p * m[..., rr[:, f], cc[:, f]]
+    p = p * sg  # exact: multiplication by +-1
+    acc = p[..., 0]
+    for k in range(1, 24):
+        acc = acc + p[..., k]
+    return acc
 
 
 def inv(m):
@@ -187,16 +204,27 @@ def inv(m):
     if np.any(d == 0):
         raise ZeroDivisionError("zero determinant")
     dinv = f32(1) / d
-    out = np.empty_like(m)
-    for (i, j), terms in _INV_TERMS.items():
-        out[..., i, j] = dinv * _eval_terms(m, terms)
-    return out
+    acc = None
+    for k in range(6):  # term k of all 16 entries
+        p = m[..., _INV_R[k, :, 0], _INV_C[k, :, 0]] * m[..., _INV_R[k, :, 1], _INV_C[k, :, 1]] * m[..., _INV_R[k, :, 2], _INV_C[k, :, 2]]
+        p = p * _INV_SG[k]
+        acc = p if acc is None else acc + p
+    out = (np.asarray(dinv)[..., None] * acc).astype(np.float32)
+    return out.reshape(m.shape)
 
 
 def viewport_matrix(w, h):
     """math.ViewportMatrix (math/math.go:270-277)."""
     w, h = f32(w), f32(h)
     return mat4(w / f32(2), 0, 0, w / f32(2), 0, h / f32(2), 0, h / f32(2), 0, 0, 1, 0, 0, 0, 0, 1)
+
+
+# ----------------------------------------------------------------------------- scene-graph mutation epoch
+EPOCH = [0]  # bumped by every mutation of a TransformContext, a Group's object list or a Geometry's arrays
+
+
+def touch():
+    EPOCH[0] += 1
 
 
 # ----------------------------------------------------------------------------- quaternion / TransformContext
@@ -230,12 +258,18 @@ class TransformContext:
     def __init__(self):
         self.ResetContext()
 
+    def _touch(self):
+        """Every mutation bumps this context's version (a renderer sees WHICH matrices moved) and the process-wide epoch (a
+        renderer sees in O(1) that nothing moved at all, Scene.signature)."""
+        self._version = getattr(self, "_version", 0) + 1
+        touch()
+
     def ResetContext(self):
         self._context = identity()
         self._rotation = Quaternion(1, 0, 0, 0)
         self._internal = identity()
         self._need = False
-        self._version = getattr(self, "_version", 0) + 1  # bumped by every mutation: lets a renderer see that a model matrix moved
+        self._touch()
 
     def ModelMatrix(self):
         if self._need:
@@ -246,12 +280,12 @@ class TransformContext:
     def Scale(self, sx, sy, sz):
         self._internal = mulm(mat4(sx, 0, 0, 0, 0, sy, 0, 0, 0, 0, sz, 0, 0, 0, 0, 1), self._internal)
         self._need = True
-        self._version += 1
+        self._touch()
 
     def Translate(self, tx, ty, tz):
         self._internal = mulm(mat4(1, 0, 0, tx, 0, 1, 0, ty, 0, 0, 1, tz, 0, 0, 0, 1), self._internal)
         self._need = True
-        self._version += 1
+        self._touch()
 
     def Rotate(self, direction, angle):
         u = v3_unit(direction)
@@ -261,7 +295,7 @@ class TransformContext:
         q = Quaternion(cosa, sina * u[0], sina * u[1], sina * u[2])
         self._rotation = q.mul(self._rotation)
         self._need = True
-        self._version += 1
+        self._touch()
 
     def RotateX(self, angle):
         self.Rotate(v3(1, 0, 0), angle)

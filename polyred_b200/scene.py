@@ -15,6 +15,25 @@ f32 = np.float32
 _FMAX = np.finfo(np.float32).max
 
 
+class _Tracked(list):
+    """A Group's object list: every mutation bumps the scene-graph epoch (gm.EPOCH), so Scene.signature() can tell in O(1)
+    that nothing changed since it last walked the graph."""
+
+
+def _bumping(name):
+    base = getattr(list, name)
+
+    def f(self, *a, **k):
+        gm.touch()
+        return base(self, *a, **k)
+    f.__name__ = name
+    return f
+
+
+for _n in ("append", "extend", "insert", "remove", "pop", "clear", "sort", "reverse", "__setitem__", "__delitem__", "__iadd__", "__imul__"):
+    setattr(_Tracked, _n, _bumping(_n))
+
+
 class Geometry(gm.TransformContext):
     """geometry.Geometry: a triangle soup + the materials it owns (geometry/geometry.go:26-59).
 
@@ -30,6 +49,11 @@ class Geometry(gm.TransformContext):
         self.col = np.full((n, 3), 0xFFFFFFFF, np.uint32) if col is None else np.ascontiguousarray(col, dtype=np.uint32).reshape(n, 3)
         self.mat = np.zeros(n, np.int32) if mat is None else np.ascontiguousarray(mat, dtype=np.int32).reshape(n)
         self.materials = list(materials)
+
+    def __setattr__(self, name, value):
+        if name in ("pos", "nor", "uv", "col", "mat", "materials"):  # a new array object = new geometry for a renderer's cache
+            gm.touch()
+        object.__setattr__(self, name, value)
 
     def Triangles(self):
         return self.pos
@@ -52,7 +76,14 @@ class Group(gm.TransformContext):
 
     def __init__(self, *objects):
         super().__init__()
-        self.objects = list(objects)
+        self.objects = _Tracked(objects)
+
+    def __setattr__(self, name, value):
+        if name == "objects":
+            gm.touch()
+            if not isinstance(value, _Tracked):
+                value = _Tracked(value)
+        object.__setattr__(self, name, value)
 
     def Add(self, *objects):
         self.objects.extend(objects)
@@ -142,6 +173,10 @@ class Scene:
         added to / removed from the graph or a geometry gets new vertex arrays (=> re-flatten and re-upload); `transforms`
         changes when any TransformContext on the way to a leaf was scaled / translated / rotated (=> only the per-object
         matrices are recomputed; the triangle soup stays resident)."""
+        cached = getattr(self, "_sig_cache", None)
+        if cached is not None and cached[0] == gm.EPOCH[0]:
+            return cached[1]  # nothing in ANY scene graph was mutated since the last walk
+        epoch = gm.EPOCH[0]
         ids, ver = [], 0
 
         def walk(g):
@@ -157,7 +192,9 @@ class Scene:
                     if isinstance(o, Geometry):
                         ids.append(id(o.pos))
         walk(self.root)
-        return hash(tuple(ids)), ver
+        sig = (hash(tuple(ids)), ver)
+        self._sig_cache = (epoch, sig)
+        return sig
 
     def Center(self):
         """Scene.Center (scene/scene.go:49-52): centre of the root AABB — model-space AABBs of

@@ -152,6 +152,32 @@ def test_scene_cache_tracks_transforms_and_membership():
     assert np.array_equal(e, fresh)
 
 
+def test_scene_signature_is_cached_until_something_mutates():
+    """Scene.signature() walks the graph only after a mutation (process-wide epoch): transforms, Add(), direct edits of a
+    group's object list and replaced vertex arrays are all seen; an unchanged scene costs O(1) per frame."""
+    from polyred_b200 import gomath as gm
+    s, _ = synth.mesh_scene(subdiv=6)
+    geo = s.geometries()[0][0]
+    a = s.signature()
+    e0 = gm.EPOCH[0]
+    assert s.signature() == a and s._sig_cache[0] == e0 == gm.EPOCH[0]          # served from the cache
+    geo.RotateY(0.25)
+    b = s.signature()
+    assert b[0] == a[0] and b[1] != a[1]                                        # same members, moved transform
+    extra = synth.mesh_scene(subdiv=4)[0].geometries()[0][0]
+    s.root.objects.append(extra)                                                # not through Add()
+    c = s.signature()
+    assert c[0] != b[0]
+    s.root.objects.pop()
+    assert s.signature()[0] == b[0]
+    geo.pos = geo.pos.copy()                                                    # a new vertex array object
+    assert s.signature()[0] != b[0]
+    s.root.objects = [geo]                                                      # replaced list stays tracked
+    d = s.signature()
+    s.root.objects.append(extra)
+    assert s.signature()[0] != d[0]
+
+
 def test_pixel_format_bgra_swaps_red_and_blue():
     """render.PixelFormat(buffer.PixelFormatBGRA): the colour bytes are stored B,G,R,A (buffer/buffer.go:242-251)."""
     s, cam = synth.mesh_scene(subdiv=10)
