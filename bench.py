@@ -248,6 +248,7 @@ def run_cuda(args):
         units = df.units
         if args.mgpu == "peer":
             pf = PeerFrames(r, rank, world, local, root=0)
+            shared_host_image = pf.share_host_image()  # e2e leg: every GPU DMAs its own strip into one shared host image
 
     def step(fdesc, host_out):
         if world == 1:
@@ -257,10 +258,13 @@ def run_cuda(args):
             if host_out is not None:
                 host_out[0] = be.host_image(w, h)
         elif pf is not None:
-            pf.submit(fdesc)
-            if host_out is not None:  # e2e: every frame is finished and read back to rank 0's host memory
+            if host_out is None:
+                pf.submit(fdesc)  # device leg: strips gathered into rank 0's device image over NVLink
+            else:
+                # e2e: uniforms in (every rank), the frame out: each rank's strip over its own PCIe link into the shared host image
+                pf.submit(fdesc, gather=False)
                 pf.finish()
-                host_out[0] = pf.image(host=True)
+                host_out[0] = shared_host_image
         else:
             img = df.render(fdesc, host_out is not None)
             if host_out is not None:
@@ -394,7 +398,9 @@ def run_cuda(args):
         "kernel_ms_per_step": {names[k]: float(ksum[k]) / args.steps for k in range(8)},
         "e2e": {"value": n_valid * fps_e2e / 1e6, "unit": "Mtris/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(px * 4),
                 "ms_per_step": wall_e2e_ms / args.steps, "mpixels_per_s": px * fps_e2e / 1e6,
-                "note": "prc_render through the C ABI: host prc_frame (per-object matrices) in, host RGBA8 out; scene resident after one prc_scene_upload",
+                "note": ("prc_render_peer through the C ABI on every rank: host prc_frame (per-object matrices) in on every rank, host RGBA8 out as one shared-memory image "
+                         "that each GPU writes its strip into over its own PCIe link; scene resident after one prc_scene_upload per rank" if pf is not None else
+                         "prc_render through the C ABI: host prc_frame (per-object matrices) in, host RGBA8 out; scene resident after one prc_scene_upload"),
                 "scene_upload_once": {"bytes": int(sd.upload_bytes()), "seconds": t_upload}},
         "stats_last_frame": {"n_large_items": int(tm.n_large_items), "n_clipped": int(tm.n_clipped), "n_bin_entries": int(tm.n_bin_entries), "n_nan_frags": int(tm.n_nan_frags)},
         "gpu_launches": launches, "clocks": clocks, "scene_gen_seconds": tgen,

@@ -285,7 +285,7 @@ int32_t prc_sync(prc_ctx* ctx);
  *   -> wait (on the device) for the peers' shadow rows -> shading -> the image strip is copied into the image of every
  *   rank in `image_mask` (bit r = rank r receives the whole frame; north_star: rank 0, mask 1).
  * Ranks are ordered by epoch words in peer memory (release/acquire at system scope); every rank must submit the same
- * sequence of prc_render_peer calls with the same image_mask. Frames stay on the device (PRC_FRAME_NO_READBACK is implied;
+ * sequence of prc_render_peer calls, each with the same image_mask on every rank. Frames stay on the device (PRC_FRAME_NO_READBACK is implied;
  * PRC_FRAME_KEEP_GBUFFER, PRC_FRAME_SHADOW_RESET and MSAA are rejected); a consumer's image of a frame stays valid until its
  * next prc_render_peer (readers: the host after prc_sync, or work enqueued on prc_stream() before that call). prc_sync() finishes the submitted frames:
  * PRC_ERR_RETRY = a queue overflowed on THIS rank (grown now; all ranks must agree to submit the frames again),
@@ -309,6 +309,12 @@ int32_t prc_peer_connect(prc_ctx* ctx, uint32_t rank, uint32_t world, const prc_
 int32_t prc_peer_disconnect(prc_ctx* ctx);
 int32_t prc_render_peer(prc_ctx* ctx, const prc_frame* frame, uint32_t n_units, const uint32_t* light, const uint32_t* row0,
                         const uint32_t* row1, uint32_t image_mask);
+/* A caller-owned host image as the readback destination of prc_render_peer frames submitted WITHOUT PRC_FRAME_NO_READBACK:
+ * [ptr, ptr + bytes) is page-locked and every such frame's strip (image rows of [row0,row1)) is DMA'd into it band by band
+ * behind the shading kernels, complete after prc_sync. Meant for ONE shared-memory image mapped by every rank of a group:
+ * each GPU then delivers its own strip over its own PCIe link and no device-side gather is needed (image_mask = 0).
+ * ptr == NULL unregisters. */
+int32_t prc_set_host_image(prc_ctx* ctx, void* ptr, uint64_t bytes);
 
 /* Arithmetic mode of this context, overriding the PRC_FMA environment variable read by prc_open:
  * exact != 0 -> math.FMA[float32] emulated bit-exactly everywhere (float64 fma rounded to float32, math/math.go FMA),

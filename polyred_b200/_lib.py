@@ -58,11 +58,12 @@ def lib():
         L.prc_peer_disconnect.argtypes = [vp]
         L.prc_render_peer.argtypes = [vp, C.POINTER(A.prc_frame), C.c_uint32, vp, vp, vp, C.c_uint32]
         L.prc_set_exact_fma.argtypes = [vp, C.c_int32]
+        L.prc_set_host_image.argtypes = [vp, vp, C.c_uint64]
         for name in ("prc_open", "prc_close", "prc_scene_upload", "prc_shadow_reset", "prc_render", "prc_read_gbuffer",
                      "prc_read_shadowmap", "prc_get_timings", "prc_device_image", "prc_device_shadowmap",
                      "prc_render_shadows", "prc_render_main", "prc_stream", "prc_sync", "prc_host_image", "prc_render_forward",
                      "prc_render_deferred", "prc_device_shadow_all", "prc_render_shadow_units", "prc_peer_export", "prc_peer_connect",
-                     "prc_peer_disconnect", "prc_render_peer", "prc_set_exact_fma", "prc_read_image"):
+                     "prc_peer_disconnect", "prc_render_peer", "prc_set_exact_fma", "prc_read_image", "prc_set_host_image"):
             getattr(L, name).restype = C.c_int32
         if L.prc_abi_version() != A.PRC_ABI_VERSION:
             raise PolyredCudaError(A.PRC_ERR_INVALID, "ABI version mismatch")
@@ -218,6 +219,10 @@ class CudaBackend(Backend):
 
     def peer_disconnect(self):
         self._check(self.L.prc_peer_disconnect(self.h))
+
+    def set_host_image(self, address: int | None, nbytes: int = 0):
+        """Readback destination of prc_render_peer frames: a caller-owned host image (e.g. shared memory mapped by every rank)."""
+        self._check(self.L.prc_set_host_image(self.h, address, nbytes))
 
     def render_peer(self, fd, units, image_mask: int = 1):
         """Submit one frame of the group without waiting (units: this rank's [(light, row0, row1)])."""

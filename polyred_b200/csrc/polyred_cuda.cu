@@ -96,8 +96,11 @@ struct prc_ctx {
   uint8_t* peer_image[PRC_PEER_MAX] = {};
   std::vector<void*> peer_opened;  // bases returned by cudaIpcOpenMemHandle
   void *peer_shadow_self = nullptr, *peer_image_self = nullptr;  // the exported buffers (a reallocation invalidates the group)
-  uint32_t peer_epoch = 0, peer_image_mask = 0;
-  bool peer_image_held = false;  // this rank consumed the image of peer_epoch and has not released it to the pushers yet
+  uint32_t peer_epoch = 0;
+  uint8_t* ext_img = nullptr;    // caller-owned page-locked host image (prc_set_host_image)
+  bool defer_copy_join = false, copy_pending = false;  // see do_main: readback of peer frames overlaps the next frame's geometry
+  size_t ext_img_bytes = 0;
+  bool ext_img_registered = false;
 };
 
 namespace {
@@ -554,6 +557,10 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, int phases
   }
 
   if (phases & 2) {
+    if (ctx->copy_pending) {  // (peer frames) the previous frame's strip is still leaving through the copy stream: it reads d_image
+      CK(cudaStreamWaitEvent(st, ctx->ev_copied, 0));
+      ctx->copy_pending = false;
+    }
     KTimer kt(ctx, PRC_K_SHADE);
     if (es) k_shade_special<E, E><<<1, 32, 0, st>>>(ctx->S, F, aoc, keys, G, (uint32_t*)ctx->d_special.p);
     else k_shade_special<E, false><<<1, 32, 0, st>>>(ctx->S, F, aoc, keys, G, (uint32_t*)ctx->d_special.p);
@@ -587,7 +594,10 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, int phases
     }
     if (banded_copy) {  // the frame's stream ends after the last copy
       CK(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
-      CK(cudaStreamWaitEvent(st, ctx->ev_copied, 0));
+      // peer frames are submitted back to back: the NEXT frame's geometry may run under this copy, only its shading (which
+      // rewrites d_image) and prc_sync wait for it
+      if (ctx->defer_copy_join) ctx->copy_pending = true;
+      else CK(cudaStreamWaitEvent(st, ctx->ev_copied, 0));
     }
     if (ctx->msaa > 1) {
       // passAntialiasing (raster.go:377): r.outBuf = imageutil.Resize(cfg.Width, cfg.Height, CurrBuffer().Image())
@@ -645,6 +655,10 @@ int32_t readback_end(prc_ctx* ctx, const DevFrame& F, uint8_t* rgba_out) {
 
 int32_t finish_timings(prc_ctx* ctx) {
   CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->copy_pending) {  // a peer frame's strip readback runs on the copy stream
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    ctx->copy_pending = false;
+  }
   float a = 0, b = 0, c = 0, d = 0;
   cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
   cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
@@ -742,6 +756,7 @@ int32_t prc_close(prc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   peer_release(ctx);
+  if (ctx->ext_img && ctx->ext_img_registered) cudaHostUnregister(ctx->ext_img);
   free_buf(ctx->d_peer_signals);
   free_buf(ctx->d_peer_err);
   DBuf* all[] = {&ctx->d_pos, &ctx->d_nor, &ctx->d_uv, &ctx->d_col, &ctx->d_mat, &ctx->d_meta, &ctx->d_mats, &ctx->d_objstart, &ctx->d_texfirst,
@@ -1176,8 +1191,6 @@ void peer_release(prc_ctx* ctx) {
   for (auto& p : ctx->peer_image) p = nullptr;
   ctx->peer_shadow_self = ctx->peer_image_self = nullptr;
   ctx->peer_epoch = 0;
-  ctx->peer_image_mask = 0;
-  ctx->peer_image_held = false;
 }
 
 int32_t peer_check(prc_ctx* ctx) {
@@ -1210,13 +1223,11 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
   const PeerTable& P = ctx->peers;
   const uint32_t all = P.world >= 32 ? 0xFFFFFFFFu : ((1u << P.world) - 1u), me = 1u << P.self;
   cudaStream_t st = ctx->stream;
-  // the image this rank consumed last frame goes back to the pushers: everything the caller enqueued on this stream (or
-  // finished on the host) before this call has read it
-  if (ctx->peer_image_held) {
-    peer_signal(ctx, PRC_SIG_IMAGE_FREE, ctx->peer_epoch, all);
-    ctx->peer_image_held = false;
-  }
   const uint32_t e = ++ctx->peer_epoch;
+  // A rank that receives this frame's image tells the pushers its image buffer is free: whatever it held (the previous
+  // frame's image, if it was a consumer then) has been read by everything the caller enqueued on this stream, or finished
+  // on the host, before this call. Announcing "free up to e-1" per frame lets the consumer set change between frames.
+  if (image_mask & me) peer_signal(ctx, PRC_SIG_IMAGE_FREE, e - 1, all);
   if (ctx->pending_async == 0) {
     ctx->launches = 0;
     ctx->spans.clear();
@@ -1257,12 +1268,15 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
     if (!one_flush) push_and_signal();
   }
   CK(cudaEventRecord(ctx->ev[1], st));
-  ctx->rb_dst = nullptr;
+  // strip readback into the caller's (shared) host image, band by band behind the shading kernels
+  ctx->rb_dst = (!(fr->flags & PRC_FRAME_NO_READBACK) && ctx->ext_img) ? ctx->ext_img : nullptr;
   int32_t r = do_main<E>(ctx, fr, F, 1);  // camera geometry + raster + resolve: needs no shadow map, overlaps the peers' pushes
   if (r != PRC_OK) return r;
   if (shadows && one_flush) push_and_signal();
   if (shadows) peer_wait(ctx, PRC_SIG_SHADOW, e, all);
+  ctx->defer_copy_join = true;
   r = do_main<E>(ctx, fr, F, 2);
+  ctx->defer_copy_join = false;
   if (r != PRC_OK) return r;
   if (shadows) peer_signal(ctx, PRC_SIG_SHADED, e, all);
   // image strip: screen rows [row0,row1) = image rows [H-row1, H-row0)
@@ -1275,10 +1289,7 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
         CK(cudaMemcpyAsync(ctx->peer_image[c] + off, (const uint8_t*)ctx->d_image.p + off, bytes, cudaMemcpyDefault, st));
     peer_signal(ctx, PRC_SIG_IMAGE, e, consumers);
   }
-  if (consumers & me) {
-    peer_wait(ctx, PRC_SIG_IMAGE, e, all);  // every strip has landed in this rank's image
-    ctx->peer_image_held = true;
-  }
+  if (consumers & me) peer_wait(ctx, PRC_SIG_IMAGE, e, all);  // every strip has landed in this rank's image
   CK(cudaEventRecord(ctx->ev[3], st));
   CK(cudaGetLastError());
   return PRC_OK;
@@ -1379,8 +1390,29 @@ int32_t prc_peer_connect(prc_ctx* ctx, uint32_t rank, uint32_t world, const prc_
   for (uint32_t p = 0; p < PRC_PEER_MAX; p++) ctx->peer_image[p] = image[p];
   ctx->peer_opened = opened;
   ctx->peer_epoch = 0;
-  ctx->peer_image_mask = 0;
-  ctx->peer_image_held = false;
+  return PRC_OK;
+}
+
+int32_t prc_set_host_image(prc_ctx* ctx, void* ptr, uint64_t bytes) {
+  if (!ctx) return PRC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->pending_async) { const int32_t pr_ = prc_sync(ctx); if (pr_ != PRC_OK) return pr_; }
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->ext_img) {
+    if (ctx->ext_img_registered) cudaHostUnregister(ctx->ext_img);
+    ctx->ext_img = nullptr;
+    ctx->ext_img_bytes = 0;
+  }
+  if (!ptr) return PRC_OK;
+  {
+    // several contexts of ONE process may share the image (single-process tests): the first one registers it
+    const cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess && e != cudaErrorHostMemoryAlreadyRegistered) { ctx->err = std::string("cudaHostRegister: ") + cudaGetErrorString(e); return PRC_ERR_CUDA; }
+    (void)cudaGetLastError();
+    ctx->ext_img_registered = e == cudaSuccess;
+  }
+  ctx->ext_img = (uint8_t*)ptr;
+  ctx->ext_img_bytes = (size_t)bytes;
   return PRC_OK;
 }
 
@@ -1404,7 +1436,10 @@ int32_t prc_render_peer(prc_ctx* ctx, const prc_frame* fr, uint32_t n, const uin
     return PRC_ERR_UNSUPPORTED;
   }
   if (n && (!light || !row0 || !row1)) return PRC_ERR_INVALID;
-  if (ctx->peer_epoch && image_mask != ctx->peer_image_mask) { ctx->err = "prc_render_peer: image_mask must not change between frames of a connection"; return PRC_ERR_INVALID; }
+  if (!(fr->flags & PRC_FRAME_NO_READBACK) && ctx->ext_img && ctx->ext_img_bytes < (size_t)fr->width * fr->height * 4) {
+    ctx->err = "prc_render_peer: the host image registered with prc_set_host_image is smaller than the frame";
+    return PRC_ERR_INVALID;
+  }
   DevFrame F;
   int32_t r = build_frame(ctx, fr, F);
   if (r != PRC_OK) return r;
@@ -1419,7 +1454,6 @@ int32_t prc_render_peer(prc_ctx* ctx, const prc_frame* fr, uint32_t n, const uin
     if (row1[k] > fr->height || row0[k] >= row1[k]) { ctx->err = "bad shadow row range"; return PRC_ERR_INVALID; }
     units.push_back({light[k], (int)row0[k], (int)row1[k]});
   }
-  ctx->peer_image_mask = image_mask;
   r = ctx->exact ? enqueue_peer_frame<true>(ctx, fr, F, units, image_mask) : enqueue_peer_frame<false>(ctx, fr, F, units, image_mask);
   if (r != PRC_OK) return r;
   ctx->pending_async++;

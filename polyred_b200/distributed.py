@@ -169,10 +169,38 @@ class PeerFrames:
         fd.struct.row0, fd.struct.row1 = self.rows[self.rank]
         return fd
 
-    def submit(self, fd):
-        """Enqueue one frame; does not wait for the GPU or for the peers."""
-        self.be.render_peer(self.prepare(fd), self.units, self.image_mask)
-        self._submitted.append(fd)
+    def share_host_image(self):
+        """One host image in shared memory, mapped and page-locked by every rank (prc_set_host_image): frames submitted with
+        readback (frame_desc(no_readback=False)) then leave each GPU as its own strip over its own PCIe link, in parallel, and
+        need no device-side gather. Returns the (H, W, 4) u8 view (valid on every rank after finish())."""
+        from multiprocessing import shared_memory
+        from ._lib import PolyredCudaError
+        from . import _abi as A
+        nbytes = self.w * self.h * 4
+        name = err = None
+        if self.rank == self.root:
+            self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            name = self._shm.name
+        names = [None] * self.world
+        self.dist.all_gather_object(names, name, group=self.group)
+        try:
+            if self.rank != self.root:
+                self._shm = shared_memory.SharedMemory(name=names[self.root])
+            self._shm_np = np.ndarray((self.h, self.w, 4), np.uint8, buffer=self._shm.buf)
+            self.be.set_host_image(self._shm_np.ctypes.data, nbytes)
+        except (PolyredCudaError, OSError) as e:
+            err = str(e)
+        errs = [None] * self.world
+        self.dist.all_gather_object(errs, err, group=self.group)  # same collectives on every rank, error or not
+        if any(e is not None for e in errs):
+            raise PolyredCudaError(A.PRC_ERR_CUDA, "PeerFrames: sharing the host image failed: " + "; ".join(f"rank {k}: {e}" for k, e in enumerate(errs) if e))
+        return self._shm_np
+
+    def submit(self, fd, gather: bool = True):
+        """Enqueue one frame; does not wait for the GPU or for the peers. gather=False: no device-side gather of the strips
+        (frames that leave through the shared host image, share_host_image())."""
+        self.be.render_peer(self.prepare(fd), self.units, self.image_mask if gather else 0)
+        self._submitted.append((fd, gather))
 
     def finish(self, max_retries: int = 3):
         """Wait for the submitted frames. A queue overflow on ANY rank (the library has grown the queue) makes
@@ -195,8 +223,8 @@ class PeerFrames:
                 self._submitted = []
                 return
             again, self._submitted = self._submitted, []
-            for fd in again:
-                self.submit(fd)
+            for fd, gather in again:
+                self.submit(fd, gather)
         raise PolyredCudaError(A.PRC_ERR_UNSUPPORTED, "PeerFrames: a queue kept overflowing")
 
     def image(self, host: bool = True):
@@ -219,3 +247,11 @@ class PeerFrames:
 
     def close(self):
         self.be.peer_disconnect()
+        shm = getattr(self, "_shm", None)
+        if shm is not None:
+            self.be.set_host_image(None)
+            self._shm_np = None
+            shm.close()
+            if self.rank == self.root:
+                shm.unlink()
+            self._shm = None

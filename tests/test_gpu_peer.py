@@ -105,9 +105,31 @@ def test_peer_rejects_unsupported_frames(monkeypatch):
         be.render_peer(fds[0], mine[0], 1)
     fds[0].struct.flags &= ~A.PRC_FRAME_SHADOW_RESET
     be.render_peer(fds[0], mine[0], 1)
-    with pytest.raises(PolyredCudaError):  # the consumer set is fixed for the lifetime of a connection
-        be.render_peer(fds[0], mine[0], 0)
+    be.render_peer(fds[0], mine[0], 0)  # the consumer set may change from frame to frame
     be.sync()
     be.peer_disconnect()
     with pytest.raises(PolyredCudaError):
         be.render_peer(fds[0], mine[0], 1)
+
+
+@pytest.mark.skipif(os.environ.get("PRC_TEST_PEER_READBACK") != "1", reason="opt-in: prc_set_host_image has not been run on hardware yet (tools/peer_selfcheck.py covers it too)")
+def test_peer_strip_readback_into_one_host_image(monkeypatch):
+    """Every rank DMAs its own strip into ONE host image (prc_set_host_image), no device-side gather (image_mask = 0)."""
+    monkeypatch.setenv("PRC_FMA", "exact")
+    s, cam, w, h = _scene()
+    ref = render.NewRenderer(*_opts(s, cam, w, h), render.CUDA(0)).Render().copy()
+    rs, fds, mine = _group(s, cam, w, h, [0, 0])
+    host = np.zeros((h, w, 4), np.uint8)
+    for k, r in enumerate(rs):
+        r._backend.set_host_image(host.ctypes.data, host.nbytes)
+        fds[k].struct.flags &= ~A.PRC_FRAME_NO_READBACK
+    for _ in range(2):
+        for k, r in enumerate(rs):
+            r._backend.render_peer(fds[k], mine[k], 0)
+    for r in rs:
+        r._backend.sync()
+    assert int((ref != host).any(axis=2).sum()) == 0
+    for r in rs:
+        r._backend.set_host_image(None)
+        r._backend.peer_disconnect()
+

@@ -109,6 +109,9 @@ class _FakeBackend:
         if self.rank == 1 and self.syncs == 1:
             raise PolyredCudaError(A.PRC_ERR_RETRY, "queue grown")
 
+    def set_host_image(self, address, nbytes=0):
+        self.host_image = (address, nbytes)
+
     def peer_disconnect(self):
         pass
 
@@ -133,6 +136,15 @@ def _peer_worker(rank, world, port, q):
     for k in range(3):
         pf.submit(frame(k))
     pf.finish()
+    # one shared host image: every rank maps the same pages and "reads back" its own strip into them
+    img = pf.share_host_image()
+    r0, r1 = partition.image_rows(100, *pf.rows[rank])
+    img[r0:r1] = rank + 1
+    dist.barrier()
+    shared_ok = be.host_image == (img.ctypes.data, 100 * 40 * 4) and bool((img[:50] == 1).all()) and bool((img[50:] == 2).all())
+    dist.barrier()
+    pf.close()
+    assert be.host_image == (None, 0)
     # failures on ONE rank must surface on BOTH (every rank runs the same host collectives, error or not): no hang
     from polyred_b200._lib import PolyredCudaError
     r.group = pf.group
@@ -149,7 +161,7 @@ def _peer_worker(rank, world, port, q):
         pf2.finish()
     except PolyredCudaError as e:
         seen.append(("finish", e.code, "rank 0" in str(e)))
-    q.put((rank, be.connected, be.calls, be.syncs, len(pf._submitted), seen))
+    q.put((rank, be.connected, be.calls, be.syncs, len(pf._submitted), seen, shared_ok))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -171,7 +183,8 @@ def test_peer_frames_host_logic_two_ranks():
         assert p.exitcode == 0
     import ctypes as C
     from polyred_b200 import _abi as A
-    for rank, connected, calls, syncs, left, seen in res:
+    for rank, connected, calls, syncs, left, seen, shared_ok in res:
+        assert shared_ok
         assert seen == [("connect", A.PRC_ERR_PEER, True), ("finish", A.PRC_ERR_PEER, True)], seen
         assert connected == (rank, 2, [C.sizeof(A.prc_peer_handle)] * 2)
         assert [c[0] for c in calls] == [0, 1, 2, 0, 1, 2] and syncs == 2 and left == 0  # one retry, on both ranks

@@ -20,6 +20,7 @@ def log(msg):
 
 def main():
     import numpy as np
+    from polyred_b200 import _abi as A
     from polyred_b200 import partition, render, synth
     max_world = int(sys.argv[1]) if len(sys.argv) > 1 else 3
     w, h = 480, 272
@@ -74,6 +75,29 @@ def main():
         log(f"world={world}: {status}; 3 frames in {dt * 1e3:.1f} ms; pixels differing from the 1-GPU frame = {nd} (per strip {per_strip}); "
             f"rank 0's shadow texels differing from the owners' rows = {sm_diff}")
         bad += nd + (status != "ok")
+        # strips read back by every rank into ONE host image (prc_set_host_image), no device-side gather
+        host = np.zeros((h, w, 4), np.uint8)
+        status = "ok"
+        try:
+            for r in rs:
+                r._backend.set_host_image(host.ctypes.data, host.nbytes)
+            for k, r in enumerate(rs):
+                fds[k].struct.flags &= ~A.PRC_FRAME_NO_READBACK
+            for _ in range(2):
+                for k, r in enumerate(rs):
+                    r._backend.render_peer(fds[k], mine[k], 0)
+            for r in rs:
+                r._backend.sync()
+        except Exception as e:  # noqa: BLE001
+            status = f"ERROR {e}"
+        nd = int((ref != host).any(axis=2).sum())
+        log(f"world={world} strip readback into one host image: {status}; pixels differing = {nd}")
+        bad += nd + (status != "ok")
+        for r in rs:
+            try:
+                r._backend.set_host_image(None)
+            except Exception as e:  # noqa: BLE001
+                log(f"set_host_image(None): {e}")
         for r in rs:
             try:
                 r._backend.peer_disconnect()
