@@ -286,6 +286,20 @@ def run_cuda(args):
     for _ in range(max(3, args.warmup)):
         step(fd, None)
     barrier()
+    balance_log = None
+    if pf is not None and args.balance:
+        # peer-memory frames take any row ranges: move the strip / shadow-shard boundaries until every rank takes the same
+        # time (per-rank kernel times of two frames per round); the frame itself does not depend on the partition
+        balance_log = []
+        for _ in range(4):
+            for _ in range(2):
+                step(fd, None)
+            barrier()
+            costs = pf.rebalance()
+            balance_log.append({"shadow_ms": [round(c[0] / 2, 4) for c in costs], "main_ms": [round(c[1] / 2, 4) for c in costs]})
+        for _ in range(2):
+            step(fd, None)
+        barrier()
     if args.resident_uniforms:
         fd.struct.flags |= A.PRC_FRAME_UNIFORMS_RESIDENT
     n_valid = int(be.timings().n_valid_tris)
@@ -405,6 +419,10 @@ def run_cuda(args):
         "stats_last_frame": {"n_large_items": int(tm.n_large_items), "n_clipped": int(tm.n_clipped), "n_bin_entries": int(tm.n_bin_entries), "n_nan_frags": int(tm.n_nan_frags)},
         "gpu_launches": launches, "clocks": clocks, "scene_gen_seconds": tgen,
     }
+    if pf is not None:
+        line["config"]["strip_rows"] = [r1 - r0 for r0, r1 in pf.rows]
+        line["config"]["shadow_rows_per_rank"] = [b - a for a, b in zip(pf.sh_bounds, pf.sh_bounds[1:])]
+        line["balance_rounds"] = balance_log
     if args.cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args, wl, s, cam)
     emit(line)
@@ -455,6 +473,7 @@ def main():
     ap.add_argument("--no-resident-uniforms", dest="resident_uniforms", action="store_false")
     ap.add_argument("--no-async-frames", dest="async_frames", action="store_false",
                     help="device-resident leg: wait for every frame (prc_render) instead of submitting the K frames back to back")
+    ap.add_argument("--no-balance", dest="balance", action="store_false", help="--mgpu peer: keep equal strips / shadow shards")
     ap.add_argument("--mgpu", default=os.environ.get("PRC_MGPU", "nccl"), choices=["nccl", "peer"],
                     help="N > 1: 'nccl' = one frame at a time, shadow maps and image strips all-gathered with NCCL (measured in round 1); "
                          "'peer' = frames submitted back to back, exchange pushed over NVLink peer memory by the library (prc_render_peer)")

@@ -129,8 +129,11 @@ class PeerFrames:
         self.w, self.h = c.Width, c.Height
         sources, _ = c.Scene.Lights()
         cast = [i for i, l in enumerate(sources) if l.cast_shadow] if c.ShadowMap else []
-        _, self.rows = partition.strips(self.h, world)
-        self.units = [(li, a, b) for li, a, b, owner in partition.shadow_units(self.h, world, cast) if owner == rank]
+        # contiguous ranges of image rows / of the stacked shadow rows per rank: equal to begin with, rebalance() moves them
+        self.cast = cast
+        self.img_bounds = partition.equal_bounds(self.h, world)
+        self.sh_bounds = partition.equal_bounds(len(cast) * self.h, world)
+        self._apply_bounds()
         self.image_mask = 1 << root
         self._submitted = []
         self._host = self._host_np = None
@@ -168,6 +171,27 @@ class PeerFrames:
     def prepare(self, fd):
         fd.struct.row0, fd.struct.row1 = self.rows[self.rank]
         return fd
+
+    def _apply_bounds(self):
+        self.rows = partition.strips_from_bounds(self.h, self.img_bounds)
+        self.units = [(li, a, b) for li, a, b, owner in partition.shadow_units_from_bounds(self.h, self.cast, self.sh_bounds) if owner == self.rank]
+
+    def rebalance(self, damping: float = 0.7, min_rows: int = 16):
+        """Move the strip and shadow-shard boundaries so that every rank gets the same share of the time the last finished
+        frames took (per-rank kernel times from prc_get_timings: the shadow classes for the shards, everything else for the
+        strips). Any partition renders the same frame bit for bit, so this only moves work. Collective: call on every rank
+        after finish(); returns the per-rank (shadow ms, main ms) it balanced on."""
+        t = self.be.timings()
+        k = list(t.kernel_ms)
+        mine = (float(k[0] + k[4]), float(k[1] + k[2] + k[3] + k[5] + k[6] + k[7]))
+        costs = [None] * self.world
+        self.dist.all_gather_object(costs, mine, group=self.group)
+        if min(self.rows[r][1] - self.rows[r][0] for r in range(self.world)) > 0:
+            self.img_bounds = partition.balanced_bounds(self.img_bounds, [c[1] for c in costs], damping, min_rows)
+        if self.cast:
+            self.sh_bounds = partition.balanced_bounds(self.sh_bounds, [c[0] for c in costs], damping, min_rows)
+        self._apply_bounds()
+        return costs
 
     def share_host_image(self):
         """One host image in shared memory, mapped and page-locked by every rank (prc_set_host_image): frames submitted with

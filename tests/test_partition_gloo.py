@@ -31,6 +31,48 @@ def test_strips_and_units_cover_everything_once():
     assert partition.image_rows(2160, 0, 272) == (1888, 2160)
 
 
+def test_bounds_helpers_reproduce_the_equal_partition():
+    for h in (2160, 270, 100, 17):
+        for world in (1, 2, 3, 8):
+            _, rows = partition.strips(h, world)
+            assert partition.strips_from_bounds(h, partition.equal_bounds(h, world)) == rows
+            for cast in ([0, 2, 4, 6], [1], []):
+                assert partition.shadow_units_from_bounds(h, cast, partition.equal_bounds(len(cast) * h, world)) == partition.shadow_units(h, world, cast)
+
+
+def test_balanced_bounds_equalise_measured_cost():
+    """Load balancing of the peer-memory frames: boundaries move so that every rank gets the same share of the measured
+    time. Simulated frame: cost per image row = sky (cheap) at the top, dense geometry in the lower half, plus a fixed
+    per-rank cost the density model does not know about — repeated rebalancing must still converge."""
+    assert partition.balanced_bounds([0, 50, 100], [50, 150]) == [0, 67, 100]
+    assert partition.balanced_bounds([0, 25, 50, 75, 100], [1, 1, 10, 10]) == [0, 59, 72, 86, 100]
+    assert partition.balanced_bounds([0, 100], [3.0]) == [0, 100]
+    assert partition.balanced_bounds([0, 5, 10], [0.0, 0.0]) == [0, 5, 10]            # nothing measured: unchanged
+    b = partition.balanced_bounds([0, 25, 50, 75, 100], [0, 0, 0, 10], min_size=4)
+    assert b[0] == 0 and b[-1] == 100 and all(y - x >= 4 for x, y in zip(b, b[1:]))
+    h, world = 2160, 8
+    row_cost = np.where(np.arange(h) < 700, 0.02, 1.0) + 2.0 * np.exp(-((np.arange(h) - 1500) / 120.0) ** 2)  # image rows, top first
+    fixed = 30.0
+
+    def measure(bounds):
+        return [fixed + float(row_cost[a:b].sum()) for a, b in zip(bounds, bounds[1:])]
+
+    bounds = partition.equal_bounds(h, world)
+    first = measure(bounds)
+    for _ in range(6):
+        bounds = partition.balanced_bounds(bounds, measure(bounds), damping=0.7, min_size=16)
+        assert bounds[0] == 0 and bounds[-1] == h and all(y - x >= 16 for x, y in zip(bounds, bounds[1:]))
+    last = measure(bounds)
+    assert max(first) / (sum(first) / world) > 1.8                       # equal strips: the slowest rank takes ~2x the mean
+    assert max(last) / (sum(last) / world) < 1.08, (bounds, last)        # balanced: within 8 % of the mean
+    # stacked shadow rows: the units of a balanced partition still tile every light's rows exactly once
+    sb = partition.balanced_bounds(partition.equal_bounds(4 * 100, 3), [1.0, 5.0, 2.0])
+    units = partition.shadow_units_from_bounds(100, [0, 2, 4, 6], sb)
+    for li in (0, 2, 4, 6):
+        rows = sorted((a, b) for l, a, b, _ in units if l == li)
+        assert rows[0][0] == 0 and rows[-1][1] == 100 and all(x[1] == y[0] for x, y in zip(rows, rows[1:]))
+
+
 def _worker(rank, world, port, h, w, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -109,6 +151,13 @@ class _FakeBackend:
         if self.rank == 1 and self.syncs == 1:
             raise PolyredCudaError(A.PRC_ERR_RETRY, "queue grown")
 
+    def timings(self):
+        from polyred_b200 import _abi as A
+        t = A.prc_timings()
+        t.kernel_ms[0] = 1.0 + 3.0 * self.rank      # shadow sweep: rank 1 four times slower
+        t.kernel_ms[7] = 4.0 - 3.0 * self.rank      # shading: rank 0 four times slower
+        return t
+
     def set_host_image(self, address, nbytes=0):
         self.host_image = (address, nbytes)
 
@@ -136,6 +185,11 @@ def _peer_worker(rank, world, port, q):
     for k in range(3):
         pf.submit(frame(k))
     pf.finish()
+    # rebalance(): both ranks gather the same timings and derive the same new boundaries
+    costs = pf.rebalance(damping=1.0, min_rows=4)
+    rebalanced = (costs, pf.img_bounds, pf.sh_bounds, pf.rows[rank], pf.units)
+    pf.img_bounds, pf.sh_bounds = partition.equal_bounds(100, world), partition.equal_bounds(200, world)
+    pf._apply_bounds()
     # one shared host image: every rank maps the same pages and "reads back" its own strip into them
     img = pf.share_host_image()
     r0, r1 = partition.image_rows(100, *pf.rows[rank])
@@ -161,7 +215,7 @@ def _peer_worker(rank, world, port, q):
         pf2.finish()
     except PolyredCudaError as e:
         seen.append(("finish", e.code, "rank 0" in str(e)))
-    q.put((rank, be.connected, be.calls, be.syncs, len(pf._submitted), seen, shared_ok))
+    q.put((rank, be.connected, be.calls, be.syncs, len(pf._submitted), seen, shared_ok, rebalanced))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -183,8 +237,13 @@ def test_peer_frames_host_logic_two_ranks():
         assert p.exitcode == 0
     import ctypes as C
     from polyred_b200 import _abi as A
-    for rank, connected, calls, syncs, left, seen, shared_ok in res:
+    for rank, connected, calls, syncs, left, seen, shared_ok, rebalanced in res:
         assert shared_ok
+        costs, img_bounds, sh_bounds, my_rows, my_units = rebalanced
+        assert costs == [(1.0, 4.0), (4.0, 1.0)]
+        assert img_bounds == [0, 31, 100] and sh_bounds == [0, 138, 200]      # rank 0: fewer image rows, more shadow rows
+        assert my_rows == ((69, 100) if rank == 0 else (0, 69))
+        assert my_units == ([(0, 0, 100), (2, 0, 38)] if rank == 0 else [(2, 38, 100)])
         assert seen == [("connect", A.PRC_ERR_PEER, True), ("finish", A.PRC_ERR_PEER, True)], seen
         assert connected == (rank, 2, [C.sizeof(A.prc_peer_handle)] * 2)
         assert [c[0] for c in calls] == [0, 1, 2, 0, 1, 2] and syncs == 2 and left == 0  # one retry, on both ranks
