@@ -1224,10 +1224,6 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
   const uint32_t all = P.world >= 32 ? 0xFFFFFFFFu : ((1u << P.world) - 1u), me = 1u << P.self;
   cudaStream_t st = ctx->stream;
   const uint32_t e = ++ctx->peer_epoch;
-  // A rank that receives this frame's image tells the pushers its image buffer is free: whatever it held (the previous
-  // frame's image, if it was a consumer then) has been read by everything the caller enqueued on this stream, or finished
-  // on the host, before this call. Announcing "free up to e-1" per frame lets the consumer set change between frames.
-  if (image_mask & me) peer_signal(ctx, PRC_SIG_IMAGE_FREE, e - 1, all);
   if (ctx->pending_async == 0) {
     ctx->launches = 0;
     ctx->spans.clear();
@@ -1236,6 +1232,10 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
   } else {
     CK(cudaMemsetAsync(ctx->d_counters.p, 0, 16, st));  // behind unfinished frames: the overflow flag and the statistics are sticky
   }
+  // A rank that receives this frame's image tells the pushers its image buffer is free: whatever it held (the previous
+  // frame's image, if it was a consumer then) has been read by everything the caller enqueued on this stream, or finished
+  // on the host, before this call. Announcing "free up to e-1" per frame lets the consumer set change between frames.
+  if (image_mask & me) peer_signal(ctx, PRC_SIG_IMAGE_FREE, e - 1, all);
   CK(cudaEventRecord(ctx->ev[0], st));
   const bool shadows = (fr->flags & PRC_FRAME_SHADOWMAP) && ctx->n_cast_alloc > 0 && ctx->n_cast_alloc != 0xFFFFFFFFu;
   // PRC_PEER_ONE_FLUSH=1 (tuning, not yet measured): the large shadow triangles wait for the camera pass's tile path (one
