@@ -388,9 +388,10 @@ def run_cuda(args):
     frame_bytes = algorithmic_bytes(n_valid, n_tris, w, h, len(cast))
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this command (profiles/)
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
-    if world == 1 and args.workload == "C3" and os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(names[dom], {}).get("dram_bytes_per_launch")
+    import glob
+    tpaths = sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_r*.json")))  # the latest round's capture
+    if world == 1 and args.workload == "C3" and tpaths:
+        traffic = json.load(open(tpaths[-1])).get(names[dom], {}).get("dram_bytes_per_launch")
     h2d = fd.struct.n_objects * 128 + len(cast) * fd.struct.n_objects * 64 + len(sources) * 168 + 256 + 4 * fd.struct.n_ambient
     line = {
         "metric": "Mtris/s", "value": n_valid * fps / 1e6, "unit": "Mtris/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
