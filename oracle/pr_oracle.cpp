@@ -233,7 +233,7 @@ void draw_clipped(Ctx& c, const FrameU& u, const Vertex& t1, const Vertex& t2, c
         PixelLock lk(mt ? &c.locks[(size_t)y * c.W + x] : nullptr);
         if (!((!dst.ok) || z > dst.depth)) continue;  // DepthTest buffer.go:279
       }
-      if (std::isnan(z)) c.tm.n_nan_frags++;
+      if (std::isnan(z)) __atomic_fetch_add(&c.tm.n_nan_frags, 1, __ATOMIC_RELAXED);
 
       f32 wc1 = recipw[0] * bc[0], wc2 = recipw[1] * bc[1], wc3 = recipw[2] * bc[2];
       f32 norm = 1.0f;
@@ -324,6 +324,7 @@ void draw(Ctx& c, const FrameU& u, const Mat4& trans, const Mat4& normal, const 
   Vec4 pts[3] = {t1.pos, t2.pos, t3.pos};
   Vec4 clips[16];
   int nc = sutherland_hodgman(pts, 3, (f32)(c.msaa * c.W), (f32)(c.msaa * c.H), clips);  // raster.go:438-439
+  __atomic_fetch_add(&c.tm.n_clipped, 1, __ATOMIC_RELAXED);  // statistic only (compared with the CUDA path's count in the edge-case tests)
   for (int i = 2; i < nc; i++) {  // clipTriangle fan, clipping.go:73; parent's recipw reused (raster.go:440-443)
     Vertex a = clip_vertex(clips[0], t1, t2, t3);
     Vertex b = clip_vertex(clips[i - 1], t1, t2, t3);

@@ -62,6 +62,8 @@ def compare_frames(r_gpu, r_cpu, w, h, n_lights_cast=(), exact=True):
     st["rgba_max_diff"] = int(d.max())
     st["nan_gpu"] = int(r_gpu._backend.timings().n_nan_frags)
     st["nan_cpu"] = int(r_cpu._backend.timings().n_nan_frags)
+    st["clipped_gpu"] = int(r_gpu._backend.timings().n_clipped)   # triangles that went through clipTriangle (informational)
+    st["clipped_cpu"] = int(r_cpu._backend.timings().n_clipped)
     st["valid_gpu"] = int(r_gpu._backend.timings().n_valid_tris)
     st["valid_cpu"] = int(r_cpu._backend.timings().n_valid_tris)
     return st, img_g, img_c

@@ -39,3 +39,4 @@ def test_edge_scene_is_bit_exact(name):
         return
     assert_bit_exact(st)
     assert st["rgba_px_diff"] == 0 and st["nan_gpu"] == 0 and st["nan_cpu"] == 0, st
+    assert st["clipped_gpu"] == st["clipped_cpu"], st  # the same triangles took the clipTriangle path
