@@ -137,6 +137,26 @@ int pth_set_camera(void* r, void* cam, char* err, int errlen) {  // Options(Came
     return -1;
   }
 }
+// render.Debug(true) / the shadow-map picture it saves (render/shadow.go:98-118); w*h*4 bytes
+int pth_shadow_map_image(void* r, int index, uint8_t* out, char* err, int errlen) {
+  try {
+    render::Frame f = static_cast<render::Renderer*>(r)->ShadowMapImage(index);
+    std::memcpy(out, f.pix.data(), f.pix.size());
+    return 0;
+  } catch (const std::exception& e) { set_err(err, errlen, e); return -1; }
+}
+int pth_set_debug(void* r, int enable, char* err, int errlen) {
+  try {
+    static_cast<render::Renderer*>(r)->Options({render::Debug(enable != 0), render::Workers(4), render::BatchSize(64)});
+    return 0;
+  } catch (const std::exception& e) { set_err(err, errlen, e); return -1; }
+}
+int pth_set_blending(void* r, char* err, int errlen) {  // must throw: Blending is rejected, not ignored
+  try {
+    static_cast<render::Renderer*>(r)->Options({render::Blending([](RGBA, RGBA b) { return b; })});
+    return 0;
+  } catch (const std::exception& e) { set_err(err, errlen, e); return -1; }
+}
 const prc_frame* pth_last_frame(void* r) { return &static_cast<render::Renderer*>(r)->LastFrame(); }
 void pth_renderer_free(void* r) { delete static_cast<render::Renderer*>(r); }
 

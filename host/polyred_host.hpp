@@ -22,6 +22,7 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -523,6 +524,8 @@ class Backend {
     shadow_reset_ = (int32_t(*)(void*))sym("shadow_reset");
     render_ = (int32_t(*)(void*, const prc_frame*, uint8_t*))sym("render");
     host_image_ = (int32_t(*)(void*, uint64_t*, uint64_t*))sym("host_image", false);
+    get_timings_ = (int32_t(*)(void*, prc_timings*))sym("get_timings");
+    read_shadowmap_ = (int32_t(*)(void*, uint32_t, float*))sym("read_shadowmap");
     if (prefix == "prc_") {
       auto open = (int32_t(*)(int32_t, void**))sym("open");
       if (open(device, &ctx_) != 0 || !ctx_) throw std::runtime_error("polyred: prc_open failed (is a CUDA device visible? there is no CPU fallback)");
@@ -541,6 +544,12 @@ class Backend {
   void SceneUpload(const prc_scene& s) const { Check(scene_upload_(ctx_, &s), "scene_upload"); }
   void ShadowReset() const { Check(shadow_reset_(ctx_), "shadow_reset"); }
   void Render(const prc_frame& f, uint8_t* out) const { Check(render_(ctx_, &f, out), "render"); }
+  prc_timings Timings() const {
+    prc_timings t{};
+    Check(get_timings_(ctx_, &t), "get_timings");
+    return t;
+  }
+  void ReadShadowMap(uint32_t light, float* out) const { Check(read_shadowmap_(ctx_, light, out), "read_shadowmap"); }
   bool HasHostImage() const { return host_image_ != nullptr; }
   // the last frame rendered with rgba_out == NULL, in place in the library's page-locked double buffer (prc_host_image)
   const uint8_t* HostImage(uint64_t* bytes) const {
@@ -558,6 +567,8 @@ class Backend {
   int32_t (*shadow_reset_)(void*) = nullptr;
   int32_t (*render_)(void*, const prc_frame*, uint8_t*) = nullptr;
   int32_t (*host_image_)(void*, uint64_t*, uint64_t*) = nullptr;
+  int32_t (*get_timings_)(void*, prc_timings*) = nullptr;
+  int32_t (*read_shadowmap_)(void*, uint32_t, float*) = nullptr;
 };
 
 // ------------------------------------------------------------------------------------------------ render
@@ -572,6 +583,9 @@ struct option {  // render/options.go:16-33
   std::shared_ptr<camera::Interface> Camera;
   RGBA Background{0, 0, 0, 0};
   int Format = PixelFormatRGBA;
+  bool Debug = false;
+  int Workers = 0, BatchSize = 32;  // the CPU scheduler's knobs (options.go:109-120): accepted, there is no scheduler on this path
+  bool hasBlendFunc = false;
   int cudaDevice = -1;
   std::string libPath, libPrefix = "prc_";
 };
@@ -584,6 +598,12 @@ inline Option GammaCorrection(bool e) { return [=](option& o) { o.GammaCorrect =
 inline Option Background(RGBA c) { return [=](option& o) { o.Background = c; }; }
 inline Option MSAA(int n) { return [=](option& o) { o.MSAA = n; }; }
 inline Option PixelFormat(int f) { return [=](option& o) { o.Format = f; }; }
+inline Option Debug(bool e) { return [=](option& o) { o.Debug = e; }; }          // options.go:101-107
+inline Option Workers(int n) { return [=](option& o) { o.Workers = n; }; }      // options.go:115-120
+inline Option BatchSize(int n) { return [=](option& o) { o.BatchSize = n; }; }  // options.go:109-113
+// options.go:96-99. A blend function is host code called per pixel (raster_screen.go:83-85): it cannot run on this path, and it is
+// rejected rather than ignored.
+inline Option Blending(std::function<RGBA(RGBA, RGBA)> f) { return [=](option& o) { o.hasBlendFunc = (bool)f; }; }
 // Backend selection, the analogue of render.GPU(dev) (render/options.go:103-110)
 inline Option CUDA(int device, std::string lib_path = "libpolyred_cuda.so") {
   return [=](option& o) { o.cudaDevice = device; o.libPath = lib_path; o.libPrefix = "prc_"; };
@@ -628,6 +648,7 @@ class Renderer {
     out.w = cfg_.Width; out.h = cfg_.Height;
     out.pix.resize((size_t)out.w * out.h * 4);
     backend_->Render(frame_, out.pix.data());
+    if (cfg_.Debug) debugReport();
     return out;
   }
   // Zero-copy variant: the frame stays in the library's page-locked buffer (what the Go shim wraps in an *image.RGBA)
@@ -642,7 +663,25 @@ class Renderer {
     v.w = cfg_.Width; v.h = cfg_.Height;
     v.pix = backend_->HostImage(&bytes);
     if (bytes != (uint64_t)v.w * v.h * 4) throw std::logic_error("render: host image size mismatch");
+    if (cfg_.Debug) debugReport();
     return v;
+  }
+  // The picture passShadows saves under render.Debug(true) (render/shadow.go:98-118): pixel (i, j) = uint8(depths[i + (H-j-1)*W] * 255)
+  // in R, G and B, alpha 255.
+  Frame ShadowMapImage(int index) const {
+    Frame img;
+    img.w = cfg_.Width * cfg_.MSAA; img.h = cfg_.Height * cfg_.MSAA;
+    std::vector<float> z((size_t)img.w * img.h);
+    backend_->ReadShadowMap((uint32_t)index, z.data());
+    img.pix.resize(z.size() * 4);
+    for (int j = 0; j < img.h; j++)
+      for (int i = 0; i < img.w; i++) {
+        const uint8_t g = (uint8_t)(int)(z[(size_t)i + (size_t)(img.h - j - 1) * img.w] * 255.0f);  // depths lie in [0, 1]: Go's uint8(float32) truncates
+        uint8_t* p = &img.pix[((size_t)j * img.w + i) * 4];
+        p[0] = p[1] = p[2] = g;
+        p[3] = 255;
+      }
+    return img;
   }
   // the uniforms of the last built frame (tests compare them with the other mirrors bit for bit)
   const prc_frame& LastFrame() const { return frame_; }
@@ -654,6 +693,26 @@ class Renderer {
   void validate() const {
     if (cfg_.MSAA < 1 || cfg_.MSAA > 8) throw std::invalid_argument("render: MSAA must be in 1..8");
     if (cfg_.Format != PixelFormatRGBA && cfg_.Format != PixelFormatBGRA) throw std::invalid_argument("render: unknown PixelFormat");
+    if (cfg_.hasBlendFunc) throw std::invalid_argument("render: Blending is not on the CUDA path (SURVEY 8f-4)");
+  }
+  // render.Debug(true): the pass timings profiling.Timed prints (raster.go:156-161, 228, 277) and shadow-<i>.ppm per casting light
+  // (the reference saves shadow-<i>.png, shadow.go:98-118; same pixels, a container that needs no PNG encoder)
+  void debugReport() {
+    const prc_timings t = backend_->Timings();
+    std::printf("forward pass (shadow): %.3f ms\nforward pass (world): %.3f ms\ndeferred pass (shading): %.3f ms\nentire rendering: %.3f ms\n",
+                t.shadow_ms, t.forward_ms, t.shade_ms, t.total_ms);
+    if (!cfg_.ShadowMap) return;
+    for (size_t i = 0; i < flat_.sources.size(); i++) {
+      if (!flat_.sources[i]->cast_shadow) continue;
+      const std::string file = "shadow-" + std::to_string(i) + ".ppm";
+      std::printf("saving (shadow map)... %s\n", file.c_str());
+      const Frame img = ShadowMapImage((int)i);
+      if (FILE* f = std::fopen(file.c_str(), "wb")) {
+        std::fprintf(f, "P6\n%d %d\n255\n", img.w, img.h);
+        for (size_t k = 0; k < img.pix.size(); k += 4) std::fwrite(&img.pix[k], 1, 3, f);
+        std::fclose(f);
+      }
+    }
   }
   struct Flat {  // flattened scene = prc_scene (render/raster.go:241-270), built once per membership
     std::vector<scene::Geometry*> geos;

@@ -50,6 +50,9 @@ def H():
     L.pth_set_camera.argtypes = [vp, vp, C.c_char_p, C.c_int]
     L.pth_last_frame.argtypes = [vp]
     L.pth_renderer_free.argtypes = [vp]
+    L.pth_shadow_map_image.argtypes = [vp, C.c_int, vp, C.c_char_p, C.c_int]
+    L.pth_set_debug.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
+    L.pth_set_blending.argtypes = [vp, C.c_char_p, C.c_int]
     L.pth_mat4_inv.argtypes = [vp, vp]
     L.pth_mat4_mulm.argtypes = [vp, vp, vp]
     L.pth_mat4_det.argtypes = [vp]
@@ -229,6 +232,32 @@ def test_uniforms_and_frames_match_the_python_mirror(H, msaa):
     got2 = np.zeros_like(want)
     assert H.pth_render_view(r, _p(got2), err, 512) == 0, err.value
     assert np.array_equal(got2, want)
+    H.pth_renderer_free(r)
+
+
+def test_debug_option_and_shadow_map_dump_match_the_python_mirror(H, tmp_path, monkeypatch, capfd):
+    """render.Debug(true) (options.go:101-107, shadow.go:98-118) in the C++ host: the same shadow-map picture as the Python
+    mirror (which reproduces the reference's committed dump byte for byte), timings on stdout, shadow-<i>.ppm in the working
+    directory; Workers / BatchSize are accepted; Blending is rejected, not ignored."""
+    pr, r, keep = _build_both(H, 1)
+    want = pr.Render()
+    err = C.create_string_buffer(512)
+    monkeypatch.chdir(tmp_path)
+    assert H.pth_set_debug(r, 1, err, 512) == 0, err.value
+    got = np.zeros_like(want)
+    assert H.pth_render(r, _p(got), err, 512) == 0, err.value
+    assert np.array_equal(got, want)
+    out = capfd.readouterr().out
+    assert "entire rendering:" in out and "saving (shadow map)... shadow-1.ppm" in out      # light 1 is the casting point light
+    dump = pr.shadow_map_image(1)
+    img = np.zeros_like(dump)
+    assert H.pth_shadow_map_image(r, 1, _p(img), err, 512) == 0, err.value
+    assert np.array_equal(img, dump) and int((dump[..., 0] > 0).sum()) > 300
+    ppm = (tmp_path / "shadow-1.ppm").read_bytes()
+    head = b"P6\n160 100\n255\n"
+    assert ppm.startswith(head) and np.array_equal(np.frombuffer(ppm[len(head):], np.uint8).reshape(100, 160, 3), dump[..., :3])
+    assert not (tmp_path / "shadow-0.ppm").exists()                                           # the directional light casts nothing
+    assert H.pth_set_blending(r, err, 512) != 0 and b"Blending" in err.value
     H.pth_renderer_free(r)
 
 
