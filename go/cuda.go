@@ -22,6 +22,7 @@ import (
 	"poly.red/color"
 	"poly.red/geometry"
 	"poly.red/geometry/primitive"
+	"poly.red/internal/imageutil"
 	"poly.red/light"
 	"poly.red/material"
 	"poly.red/math"
@@ -114,7 +115,7 @@ type prcFrame struct {
 
 type cudaBackend struct {
 	lib                                                                  uintptr
-	fnOpen, fnClose, fnLastError, fnSceneUpload, fnShadowReset, fnRender, fnHostImage uintptr
+	fnOpen, fnClose, fnLastError, fnSceneUpload, fnShadowReset, fnRender, fnHostImage, fnReadShadowmap uintptr
 	ctx                                                                  uintptr
 
 	// flattened scene, kept alive while the library borrows it during prc_scene_upload
@@ -144,7 +145,8 @@ func openCUDA(device int) *cudaBackend {
 	}
 	b := &cudaBackend{lib: lib,
 		fnOpen: sym("prc_open"), fnClose: sym("prc_close"), fnLastError: sym("prc_last_error"),
-		fnSceneUpload: sym("prc_scene_upload"), fnShadowReset: sym("prc_shadow_reset"), fnRender: sym("prc_render"), fnHostImage: sym("prc_host_image")}
+		fnSceneUpload: sym("prc_scene_upload"), fnShadowReset: sym("prc_shadow_reset"), fnRender: sym("prc_render"), fnHostImage: sym("prc_host_image"),
+		fnReadShadowmap: sym("prc_read_shadowmap")}
 	if v, _, _ := purego.SyscallN(sym("prc_abi_version")); uint32(v) != prcABIVersion {
 		panic("render: libpolyred_cuda.so ABI version mismatch")
 	}
@@ -355,6 +357,28 @@ func (r *Renderer) renderCUDA() *image.RGBA {
 	rc, _, _ := purego.SyscallN(b.fnRender, b.ctx, uintptr(unsafe.Pointer(&f)), 0)
 	runtime.KeepAlive(objs); runtime.KeepAlive(lights); runtime.KeepAlive(amb); runtime.KeepAlive(shadowTrans)
 	b.check(rc, "prc_render")
+	if r.cfg.Debug && r.cfg.ShadowMap {
+		// render.Debug(true): passShadows saves shadow-<i>.png from shadowInfo.depths (shadow.go:98-118). The maps live in HBM;
+		// they are read back into the renderer's own depth slices (same size and index order, shadow.go:26-31,221-228) and
+		// dumped with the reference's loop.
+		for i, l := range ls {
+			if !l.CastShadow() {
+				continue
+			}
+			rc, _, _ := purego.SyscallN(b.fnReadShadowmap, b.ctx, uintptr(i), uintptr(unsafe.Pointer(unsafe.SliceData(r.shadowBufs[i].depths))))
+			b.check(rc, "prc_read_shadowmap")
+			img := image.NewRGBA(image.Rect(0, 0, w, h))
+			for x := 0; x < w; x++ {
+				for y := 0; y < h; y++ {
+					z := uint8(r.shadowBufs[i].depths[x+(h-y-1)*w] * 255)
+					img.SetRGBA(x, y, color.RGBA{z, z, z, 255})
+				}
+			}
+			file := fmt.Sprintf("shadow-%d.png", i)
+			fmt.Printf("saving (shadow map)... %s\n", file)
+			imageutil.Save(img, file)
+		}
+	}
 	var ptr, n uint64
 	rc, _, _ = purego.SyscallN(b.fnHostImage, b.ctx, uintptr(unsafe.Pointer(&ptr)), uintptr(unsafe.Pointer(&n)))
 	b.check(rc, "prc_host_image")
