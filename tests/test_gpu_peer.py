@@ -20,9 +20,9 @@ from polyred_b200 import partition, render, synth
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("PRC_TEST_PEER") == "0", reason="PRC_TEST_PEER=0")]
 
 
-def _scene():
+def _scene(w=480, h=272):
     s, cam = synth.city_scene(n_objects=25, obj_stacks=20, obj_slices=20, ground_cells=60, tex_size=64)
-    return s, cam, 480, 272
+    return s, cam, w, h
 
 
 def _opts(s, cam, w, h):
@@ -50,8 +50,8 @@ def _group(s, cam, w, h, devices):
     return rs, fds, mine
 
 
-def _run(devices, frames=3):
-    s, cam, w, h = _scene()
+def _run(devices, frames=3, size=(480, 272)):
+    s, cam, w, h = _scene(*size)
     ref = render.NewRenderer(*_opts(s, cam, w, h), render.CUDA(devices[0])).Render().copy()
     rs, fds, mine = _group(s, cam, w, h, devices)
     for _ in range(frames):
@@ -112,7 +112,18 @@ def test_peer_rejects_unsupported_frames(monkeypatch):
         be.render_peer(fds[0], mine[0], 1)
 
 
-@pytest.mark.skipif(os.environ.get("PRC_TEST_PEER_READBACK") != "1", reason="opt-in: prc_set_host_image has not been run on hardware yet (tools/peer_selfcheck.py covers it too)")
+_EXTRA = pytest.mark.skipif(os.environ.get("PRC_TEST_PEER_READBACK") != "1", reason="opt-in (PRC_TEST_PEER_READBACK=1): not run on hardware yet")
+
+
+@_EXTRA
+def test_peer_odd_frame_size_takes_the_scalar_push(monkeypatch):
+    """A frame width that is not a multiple of 4: the shards are not float4-aligned and k_shadow_push<1> runs."""
+    monkeypatch.setenv("PRC_FMA", "exact")
+    ref, out = _run([0, 0, 0], frames=2, size=(483, 271))
+    assert int((ref != out).any(axis=2).sum()) == 0
+
+
+@_EXTRA
 def test_peer_strip_readback_into_one_host_image(monkeypatch):
     """Every rank DMAs its own strip into ONE host image (prc_set_host_image), no device-side gather (image_mask = 0)."""
     monkeypatch.setenv("PRC_FMA", "exact")
