@@ -23,16 +23,20 @@ def main():
     from polyred_b200 import _abi as A
     from polyred_b200 import partition, render, synth
     max_world = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-    w, h = 480, 272
     s, cam = synth.city_scene(n_objects=25, obj_stacks=20, obj_slices=20, ground_cells=60, tex_size=64)
-    opts = [render.Camera(cam), render.Size(w, h), render.Scene(s), render.ShadowMap(True), render.GammaCorrection(True)]
     log("scene built")
-    ref = render.NewRenderer(*opts, render.CUDA(0)).Render().copy()
-    log(f"1-GPU reference frame rendered ({int((ref[..., 3] > 0).sum())} px with alpha)")
     sources, _ = s.Lights()
     cast = [i for i, l in enumerate(sources) if l.cast_shadow]
     bad = 0
-    for world in range(1, max_world + 1):
+    # every group size at a float4-aligned frame size, then the largest group at an odd size (scalar shadow push)
+    cases = [(world, 480, 272) for world in range(1, max_world + 1)] + [(max_world, 483, 271)]
+    refs = {}
+    for world, w, h in cases:
+        opts = [render.Camera(cam), render.Size(w, h), render.Scene(s), render.ShadowMap(True), render.GammaCorrection(True)]
+        if (w, h) not in refs:
+            refs[(w, h)] = render.NewRenderer(*opts, render.CUDA(0)).Render().copy()
+            log(f"1-GPU reference frame {w}x{h} rendered ({int((refs[(w, h)][..., 3] > 0).sum())} px with alpha)")
+        ref = refs[(w, h)]
         _, rows = partition.strips(h, world)
         units = partition.shadow_units(h, world, cast)
         rs, fds, handles = [], [], []
@@ -72,7 +76,7 @@ def main():
                     if lj == li and owner == k:
                         full[a:b] = mk[a:b]
             sm_diff.append(int((m0 != full).sum()))
-        log(f"world={world}: {status}; 3 frames in {dt * 1e3:.1f} ms; pixels differing from the 1-GPU frame = {nd} (per strip {per_strip}); "
+        log(f"world={world} {w}x{h}: {status}; 3 frames in {dt * 1e3:.1f} ms; pixels differing from the 1-GPU frame = {nd} (per strip {per_strip}); "
             f"rank 0's shadow texels differing from the owners' rows = {sm_diff}")
         bad += nd + (status != "ok")
         # strips read back by every rank into ONE host image (prc_set_host_image), no device-side gather
