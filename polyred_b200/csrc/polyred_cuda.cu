@@ -51,6 +51,7 @@ struct prc_ctx {
   uint32_t target_of_light[64] = {0};
   bool light_affine[64] = {false};
   DBuf d_xf, d_lights, d_ambient, d_gamma, d_frame, d_aoc, d_chunkbox, d_vis, d_cverts, d_cvoff, d_lidx;
+  DBuf d_chunklist;  // PRC_GEOM_PERSIST tuning build only
   uint32_t n_chunks = 0;
   uint64_t n_cverts = 0;  // distinct chunk-local vertices (k_chunk_dedupe)
   std::vector<DevLight> h_lights;    // host staging of the per-frame light table
@@ -210,12 +211,28 @@ int32_t raster_pass(prc_ctx* ctx, const DevFrame& F, const GeomViews& Vin) {
       ctx->launches++;
     }
   }
+#if PRC_GEOM_PERSIST
+  if (ctx->S.n_tris) {
+    // tuning build: persistent grid over the compacted list of visible chunks (see k_geom_raster)
+    ENSURE(ctx->d_chunklist, ((size_t)ctx->n_chunks + 4) * 4);
+    unsigned int* n_list = (unsigned int*)ctx->d_chunklist.p;  // [0] = count, the list starts at +4
+    CK(cudaMemsetAsync(n_list, 0, 4, st));
+    KTimer kt(ctx, SHADOW ? PRC_K_GEOM_SHADOW : PRC_K_GEOM_CAMERA);
+    k_chunk_compact<<<cdiv(ctx->n_chunks, 256), 256, 0, st>>>(V, SHADOW ? V.n : 1, ctx->n_chunks, n_list + 4, n_list);
+    V.list = n_list + 4;
+    V.n_list = n_list;
+    k_geom_raster<E, SHADOW><<<std::min<unsigned int>(148u * PRC_GEOM_MIN_BLOCKS, ctx->n_chunks), PRC_GEOM_THREADS, 0, st>>>(
+        ctx->S, F, V, keys, large, ctx->large_cap, clipq, ctx->clip_cap, cnt, (const DevFrame*)fb.p);
+    ctx->launches += 2;
+  }
+#else
   if (ctx->S.n_tris) {
     KTimer kt(ctx, SHADOW ? PRC_K_GEOM_SHADOW : PRC_K_GEOM_CAMERA);
     k_geom_raster<E, SHADOW><<<cdiv(ctx->S.n_tris, PRC_GEOM_THREADS), PRC_GEOM_THREADS, 0, st>>>(ctx->S, F, V, keys, large, ctx->large_cap, clipq, ctx->clip_cap,
                                                                                                      cnt, (const DevFrame*)fb.p);
     ctx->launches++;
   }
+#endif
   if (!SHADOW) {
     // fixed grid, reads its work count on the device (grid-stride loop)
     KTimer kt(ctx, PRC_K_CLIP);
@@ -756,6 +773,7 @@ int32_t prc_close(prc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   peer_release(ctx);
+  free_buf(ctx->d_chunklist);
   if (ctx->ext_img && ctx->ext_img_registered) cudaHostUnregister(ctx->ext_img);
   free_buf(ctx->d_peer_signals);
   free_buf(ctx->d_peer_err);

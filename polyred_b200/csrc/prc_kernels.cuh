@@ -344,6 +344,10 @@ struct GeomViews {
   int r0[8], r1[8];  // rows of the shadow map this view rasterises
   const unsigned char* vis[8];  // per view: [n_chunks] 0 = no triangle of this 256-triangle chunk can touch the view's rows / screen
   int any_vis;                  // some vis[v] is set
+#if PRC_GEOM_PERSIST
+  const unsigned int* list;     // chunks visible in at least one view, compacted by k_chunk_compact (any order)
+  const unsigned int* n_list;   // their number (device memory: no host round trip)
+#endif
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -551,10 +555,24 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_
                                                                      unsigned long long* keys, LargeRec* large, unsigned int large_cap,
                                                                      unsigned int* clipq, unsigned int clip_cap, Counters* cnt, const DevFrame* Fg) {
   __shared__ GeomSmem sm;
-  const unsigned long long tri64 = (unsigned long long)blockIdx.x * PRC_GEOM_THREADS + threadIdx.x;
+#if PRC_GEOM_PERSIST
+  // Tuning variant (EXTRA=-DPRC_GEOM_PERSIST=1, NOT the default, not yet measured): a few CTAs per SM loop over the compacted
+  // list of chunks that can touch some view, instead of one CTA per chunk that mostly reads its visibility byte and exits
+  // (multi-GPU strips and shadow shards: 39 k launches per pass on C3 for a few thousand visible chunks).
+  const unsigned int n_list = *V.n_list;
+  for (unsigned int it = blockIdx.x; it < n_list; it += gridDim.x) {
+  const unsigned int chunk = V.list[it];
+  __syncthreads();  // the previous chunk's shared vertices and queue are no longer read
+#define PRC_CHUNK_DONE continue
+#else
+  {
+  const unsigned int chunk = blockIdx.x;
+#define PRC_CHUNK_DONE return
+#endif
+  const unsigned long long tri64 = (unsigned long long)chunk * PRC_GEOM_THREADS + threadIdx.x;
   const unsigned int tri = (unsigned int)tri64;
   const uint32_t li = tri64 < S.n_tris ? __ldg(S.lidx + tri) : 0xFFFFFFFFu;
-  const uint32_t voff = __ldg(S.cvoff + blockIdx.x), nv = __ldg(S.cvoff + blockIdx.x + 1) - voff;
+  const uint32_t voff = __ldg(S.cvoff + chunk), nv = __ldg(S.cvoff + chunk + 1) - voff;
   const int n_views = SHADOW ? V.n : 1;
   const int trans_stride = SHADOW ? 16 : (int)(sizeof(prc_object_xf) / sizeof(float));
   // views this chunk can touch (k_chunk_cull; uniform over the CTA)
@@ -562,8 +580,8 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_
   if (V.any_vis) {
     todo = 0;
     for (int v = 0; v < n_views; v++)
-      if (V.vis[v] == nullptr || V.vis[v][blockIdx.x] != 0) todo |= 1u << v;
-    if (!todo) return;
+      if (V.vis[v] == nullptr || V.vis[v][chunk] != 0) todo |= 1u << v;
+    if (!todo) PRC_CHUNK_DONE;
   }
   if (threadIdx.x == 0) { sm.qn[0] = sm.qn[1] = 0; sm.qv[0] = sm.qv[1] = 0; }
   int v = __ffs(todo) - 1, buf = 0;
@@ -597,14 +615,29 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_
         const uint32_t bw = (box >> 28) + 1u, dy = (j * c_recip256[bw]) >> 8, dx = j - dy * bw;
         small_pixel<E, SHADOW>(sx[i0], sy[i0], sz[i0], sx[i1], sy[i1], sz[i1], sx[i2], sy[i2], sz[i2],
                                (int)((box & 0x3FFFu) + dx), (int)(((box >> 14) & 0x3FFFu) + dy),
-                               (blockIdx.x * PRC_GEOM_THREADS + t) * 8u, F.W, keys, smap, cnt);
+                               (chunk * PRC_GEOM_THREADS + t) * 8u, F.W, keys, smap, cnt);
       }
     }
     if (vn < 0) break;
     __syncthreads();
     v = vn; buf ^= 1;
   }
+  }
+#undef PRC_CHUNK_DONE
 }
+
+#if PRC_GEOM_PERSIST
+// The chunks at least one of the views can touch, compacted (warp-aggregated append; the order does not matter: depth
+// resolution by atomicMax is order-independent). vis[v] == nullptr: view v touches every chunk.
+__global__ void k_chunk_compact(GeomViews V, int n_views, uint32_t n_chunks, unsigned int* list, unsigned int* n_list) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool hit = false;
+  if (i < n_chunks)
+    for (int v = 0; v < n_views; v++)
+      if (V.vis[v] == nullptr || V.vis[v][i] != 0) hit = true;
+  if (hit) list[warp_push(n_list)] = i;
+}
+#endif
 
 // K2: triangles straddling the viewport: clip, fan, emit (raster.go:438-443)
 template <bool E>
