@@ -629,7 +629,7 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_
 #if PRC_GEOM_PERSIST
 // The chunks at least one of the views can touch, compacted (warp-aggregated append; the order does not matter: depth
 // resolution by atomicMax is order-independent). vis[v] == nullptr: view v touches every chunk.
-__global__ void k_chunk_compact(GeomViews V, int n_views, uint32_t n_chunks, unsigned int* list, unsigned int* n_list) {
+__global__ void k_chunk_compact(const __grid_constant__ GeomViews V, int n_views, uint32_t n_chunks, unsigned int* list, unsigned int* n_list) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool hit = false;
   if (i < n_chunks)
