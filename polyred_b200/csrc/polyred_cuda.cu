@@ -13,6 +13,7 @@
 #include "prc_peer.cuh"
 
 #define PRC_SHADE_BANDS 8  // row bands of the shading pass when the frame is read back (copy of band k overlaps shading of band k+1)
+#define PRC_SHADE_BANDS_MAX 32  // PRC_SHADE_BANDS=n in the environment overrides the default (tuning: a smaller last band = a shorter exposed copy)
 
 using namespace prc;
 
@@ -72,7 +73,8 @@ struct prc_ctx {
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   // readback overlapped with shading: the image leaves in row bands on a second stream while the next band is shaded
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_band[PRC_SHADE_BANDS] = {}, ev_copied = nullptr;
+  cudaEvent_t ev_band[PRC_SHADE_BANDS_MAX] = {}, ev_copied = nullptr;
+  int shade_bands = PRC_SHADE_BANDS;
   uint8_t* rb_dst = nullptr;  // page-locked destination of this frame's image (nullptr: no readback)
   // MSAA: the shaded frame is W x H = msaa x the output; k_resize writes the (W/msaa) x (H/msaa) frame that is handed back
   int pending_async = 0;  // PRC_FRAME_ASYNC frames submitted since the last finish (their spans / overflow flag are still open)
@@ -586,7 +588,7 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, int phases
     // device->host DMA runs on the copy stream while the next band is shaded (only the last band's copy is exposed).
     const bool banded_copy = ctx->rb_dst && ctx->msaa == 1;
     const int rows = F.row1 - F.row0;
-    const int nb = (banded_copy && rows >= 64 * PRC_SHADE_BANDS) ? PRC_SHADE_BANDS : 1;
+    const int nb = (banded_copy && rows >= 64 * ctx->shade_bands) ? ctx->shade_bands : 1;
     const int band = ((rows + nb - 1) / nb + 3) & ~3;
     for (int b = 0; b < nb; b++) {
       DevFrame Fb = F;
@@ -751,6 +753,7 @@ int32_t prc_open(int32_t device, prc_ctx** out) {
   const char* mode = getenv("PRC_FMA");
   ctx->exact = !(mode && strcmp(mode, "fast") == 0);
   ctx->exact_shade = mode && strcmp(mode, "exact") == 0;
+  if (const char* sb = getenv("PRC_SHADE_BANDS")) ctx->shade_bands = std::max(1, std::min(PRC_SHADE_BANDS_MAX, atoi(sb)));
   // AO constants (material/ao.go:28-32): a accumulates float32(Pi/4) in float32; Cos/Sin via float64.
   const float pi = 3.14159265358979323846f, q = pi / 4;
   float a = 0.0f;
