@@ -19,3 +19,13 @@ print(f"{sys.argv[1]:>12}: {d['ms_per_step']:.4f} ms/frame  e2e {d['e2e']['ms_pe
 PY
   done
 done
+# e2e only: row bands of the shading pass under the device->host copy (default 8)
+unset PRC_LIB
+for nb in 8 12 16 24; do
+  PRC_SHADE_BANDS=$nb python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/ab_bands_$nb.json 2> gpurun_out/ab_bands_$nb.err
+  python - "$nb" gpurun_out/ab_bands_$nb.json <<'PY'
+import json, sys
+d = json.load(open(sys.argv[2]))
+print(f"shade bands {sys.argv[1]:>3}: e2e {d['e2e']['ms_per_step']:.4f} ms/frame  (device {d['ms_per_step']:.4f})")
+PY
+done
