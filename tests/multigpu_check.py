@@ -29,7 +29,7 @@ def main():
         df = DistributedFrame(r, rank, world, local)
         for _ in range(2):
             out = df.render(df.prepare(r.frame_desc(no_readback=True)), True)
-        peer_out = None
+        peer_out = rebalanced_out = shared_out = None
         if os.environ.get("PRC_CHECK_PEER", "1") != "0":
             # the same frame through prc_render_peer (NVLink peer memory, no collective): three frames back to back
             r2 = render.NewRenderer(*opts, render.CUDA(local))
@@ -39,6 +39,21 @@ def main():
                 pf.submit(r2.frame_desc(no_readback=True))
             pf.finish()
             peer_out = pf.image(host=True)
+            if peer_out is not None:
+                peer_out = peer_out.copy()
+            # any partition must give the same frame: move the boundaries by the measured per-rank times, render again
+            costs = pf.rebalance(damping=1.0, min_rows=8)
+            for _ in range(2):
+                pf.submit(r2.frame_desc(no_readback=True))
+            pf.finish()
+            rebalanced_out = pf.image(host=True)
+            if rank == 0:
+                print(f"[multigpu_check] {name}: rebalanced strips {[b - a for a, b in pf.rows]} from per-rank (shadow, main) ms {[(round(c[0], 3), round(c[1], 3)) for c in costs]}")
+            # and the e2e form: every rank reads its own strip back into one shared host image, no device-side gather
+            shared = pf.share_host_image()
+            pf.submit(r2.frame_desc(no_readback=False), gather=False)
+            pf.finish()
+            shared_out = shared.copy() if rank == 0 else None
             dist.barrier()
             pf.close()
         if rank == 0:
@@ -47,9 +62,10 @@ def main():
             print(f"[multigpu_check] {name} {w}x{h} world={world}: pixels differing from the 1-GPU frame = {nd}")
             ok = ok and nd == 0
             if peer_out is not None:
-                nd = int((np.abs(peer_out.astype(int) - ref.astype(int)).max(axis=2) > 0).sum())
-                print(f"[multigpu_check] {name} {w}x{h} world={world} (peer memory): pixels differing from the 1-GPU frame = {nd}")
-                ok = ok and nd == 0
+                for label, img in (("peer memory", peer_out), ("peer memory, rebalanced strips", rebalanced_out), ("peer memory, strips read back into one shared host image", shared_out)):
+                    nd = int((np.abs(img.astype(int) - ref.astype(int)).max(axis=2) > 0).sum())
+                    print(f"[multigpu_check] {name} {w}x{h} world={world} ({label}): pixels differing from the 1-GPU frame = {nd}")
+                    ok = ok and nd == 0
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:
