@@ -172,6 +172,17 @@ class PeerFrames:
         fd.struct.row0, fd.struct.row1 = self.rows[self.rank]
         return fd
 
+    def options(self, *opts):
+        """Renderer.Options(...) for the whole group (render/options.go:125-141): e.g. a new camera re-fits the light cameras and
+        zeroes the shadow maps. Every rank calls it with the same options; no frame may be in flight on any rank while the
+        maps are zeroed (a peer's pushed texels would be lost), hence finish() before and a barrier after."""
+        self.finish()
+        self.r.Options(*opts)
+        self.r._ensure_uploaded()  # applies the pending shadow-map reset on this rank
+        self.be.sync()
+        done = [None] * self.world
+        self.dist.all_gather_object(done, True, group=self.group)
+
     def _apply_bounds(self):
         self.rows = partition.strips_from_bounds(self.h, self.img_bounds)
         self.units = [(li, a, b) for li, a, b, owner in partition.shadow_units_from_bounds(self.h, self.cast, self.sh_bounds) if owner == self.rank]
