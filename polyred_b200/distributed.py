@@ -177,7 +177,10 @@ class PeerFrames:
         zeroes the shadow maps. Every rank calls it with the same options; no frame may be in flight on any rank while the
         maps are zeroed (a peer's pushed texels would be lost), hence finish() before and a barrier after."""
         self.finish()
+        scene_before, sd = self.r.cfg.Scene, self.r._scene_desc
         self.r.Options(*opts)
+        if self.r.cfg.Scene is scene_before:
+            self.r._scene_desc = sd  # Options() drops the flattened scene; the geometry did not change (as in render.RenderViews)
         self.r._ensure_uploaded()  # applies the pending shadow-map reset on this rank
         self.be.sync()
         done = [None] * self.world
