@@ -40,3 +40,31 @@ def test_edge_scene_is_bit_exact(name):
     assert_bit_exact(st)
     assert st["rgba_px_diff"] == 0 and st["nan_gpu"] == 0 and st["nan_cpu"] == 0, st
     assert st["clipped_gpu"] == st["clipped_cpu"], st  # the same triangles took the clipTriangle path
+
+
+def test_testrender_msaa2_against_the_reference_render():
+    """The CUDA path against internal/testdata/render.png, the output of the reference's own TestRender (render/raster_test.go:
+    32-89: newscene(), 1920x1080, MSAA(2) = a 3840x2160 G-buffer): background mask identical in every pixel, at most a few dozen
+    bunny pixels off by more than 1 LSB — and the whole frame byte-identical to the oracle's (same checks as
+    test_oracle_golden.py::test_testrender_png_msaa2_newscene)."""
+    import oracle_binding as ob
+    from PIL import Image
+    from polyred_b200 import camera, gomath as gm, light, model, render, scene
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    s = scene.Scene(light.Point(intensity=5, color=(0, 0, 0, 255), position=(-2, 2.5, 6)), light.Ambient(intensity=0.5))
+    m = model.Load(os.path.join(G, "assets", "bunny_textured", "bunny.obj"))
+    m.Rotate(gm.v3(0, 1, 0), -np.float32(np.pi) / np.float32(6))
+    m.Scale(4, 4, 4)
+    m.Translate(0.1, 0, -0.2)
+    s.Add(m)
+    w, h = 1920, 1080
+    cam = camera.Perspective(position=(0, 1.5, 1), target=(0, 0, -0.5), up=(0, 1, 0), fov=45, aspect=np.float32(w) / np.float32(h), near=0.1, far=3)
+    opts = [render.Camera(cam), render.Size(w, h), render.Scene(s), render.MSAA(2), render.Background((0, 127, 255, 255))]
+    img = render.NewRenderer(*opts, render.CUDA(0)).Render()
+    gold = np.array(Image.open(os.path.join(G, "ref_renders", "testrender_msaa2.png")).convert("RGBA"))
+    bg_gold = (gold[..., :3] == np.array([0, 127, 255])).all(axis=2)
+    bg_mine = (img[..., :3] == np.array([0, 127, 255])).all(axis=2)
+    assert int((bg_gold ^ bg_mine).sum()) == 0
+    d = np.abs(img.astype(int) - gold.astype(int)).max(axis=2)
+    assert int(d.max()) <= 12 and int((d > 1).sum()) <= 60 and float((d == 0).mean()) >= 0.95
+    assert np.array_equal(img, render.NewRenderer(*opts, render._Backend(ob.OracleBackend(threads=4))).Render())
