@@ -10,8 +10,9 @@
 // so this oracle is pinned (a) bottom-up by the reference's own known-answer tests
 // (tests/golden/kat_*.json extracted from math/*_test.go, buffer/texture_test.go, ...) and
 // (b) top-down by the reference's committed renders: MSAA(1) internal/examples/out/ground.png, perspect.png,
-// gopher.png, the MSAA(2) bunny.png (supersampling, double-MSAA cull box, imageutil.Resize) and the benchmark's
-// shadow-map dump — see tests/test_oracle_golden.py.
+// gopher.png, the MSAA(2) bunny.png, shadow.png and dragon.png (supersampling, double-MSAA cull box, imageutil.Resize),
+// internal/testdata/render.png (the output of the reference's own TestRender: newscene() at 1920x1080, MSAA(2)) and the
+// benchmark's shadow-map dump — see tests/test_oracle_golden.py.
 // NOT pinned by any reference fixture: the AO transcendental chain (Atan/Cos/Sin/Pow(.,10000))
 // and Log2 in the LOD formula use libm where Go uses its own routines ("parity unpinned" for
 // those two).
