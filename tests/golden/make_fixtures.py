@@ -109,7 +109,8 @@ def copy_assets():
     for f in ("bunny.obj", "bunny.mtl", "bunny.png"):
         shutil.copy(f"{REF}/internal/testdata/{f}", os.path.join(HERE, "assets", "bunny_textured", f))
     for src, dst in (("examples/out/ground.png", "ground.png"), ("examples/out/perspect.png", "perspect.png"), ("examples/out/gopher.png", "gopher.png"), ("examples/out/bunny.png", "bunny_msaa2.png"), ("examples/out/shadow.png", "shadow_msaa2.png"), ("examples/out/dragon.png", "dragon_msaa2.png"),
-                     ("examples/benchmark/shadow-0.png", "benchmark_shadow-0.png"), ("testdata/render.png", "testrender_msaa2.png")):
+                     ("examples/benchmark/shadow-0.png", "benchmark_shadow-0.png"), ("testdata/render.png", "testrender_msaa2.png"),
+                     ("examples/out/plane.png", "plane_msaa2.png"), ("examples/out/normalize.png", "normalize_msaa2.png")):
         shutil.copy(f"{REF}/internal/{src}", os.path.join(HERE, "ref_renders", dst))
     # benchmark.png: only its coverage (alpha) is a usable golden (rendered by older shading code)
     from PIL import Image

@@ -133,6 +133,41 @@ def test_testrender_png_msaa2_newscene():
     assert int(d.max()) <= 12 and int((d > 1).sum()) <= 60 and float((d == 0).mean()) >= 0.95
 
 
+def _new_plane():
+    """model.NewPlane(1, 1) (model/plane.go:17-46): two triangles (v1,v2,v3), (v1,v3,v4) with per-vertex colours, MaterialID -1."""
+    v = {1: ((-0.5, 0, -0.5), (0, 1), 0xFF0000FF), 2: ((-0.5, 0, 0.5), (0, 0), 0xFF00FF00), 3: ((0.5, 0, 0.5), (1, 0), 0xFFFF0000), 4: ((0.5, 0, -0.5), (1, 1), 0xFF000000)}
+    tris = [(1, 2, 3), (1, 3, 4)]
+    pos = np.array([[v[i][0] for i in t] for t in tris], np.float32)
+    uv = np.array([[v[i][1] for i in t] for t in tris], np.float32)
+    col = np.array([[v[i][2] for i in t] for t in tris], np.uint32)
+    nor = np.tile(np.array([0, 1, 0], np.float32), (2, 3, 1))
+    return scene.Geometry(pos, nor, uv, col, np.full(2, -1, np.int32), [])
+
+
+def test_plane_and_normalize_png_vertex_colours():
+    """model/plane_test.go:21-38 -> examples/out/plane.png and scene/group_test.go:20-36 -> normalize.png: the only reference
+    renders of the VERTEX-COLOUR path (MaterialID -1: no material, shade() passes the interpolated colour through,
+    raster.go:330-333,546-551), once with a perspective camera (perspective-correct colour interpolation) and once with an
+    orthographic one after Scene.Normalize(). Background masks identical in every pixel; no channel differs by more than 1 LSB
+    (the colour is uint8(float32) truncated, raster.go:546-551 — the last-ulp differences of a render made on another
+    architecture flip 254.99998 / 255.0)."""
+    bg = (0x18, 0x18, 0x18, 255)  # color.FromHex("#181818")
+    s = scene.Scene(light.Point(intensity=1, color=(0, 128, 255, 255), position=(2, 2, 2)), _new_plane())
+    cam = camera.Perspective(position=(2, 2, 2), fov=45, aspect=1, near=0.1, far=10)
+    img = render.NewRenderer(render.Camera(cam), render.Size(500, 500), render.MSAA(2), render.Scene(s), render.Background(bg), render._Backend(ob.OracleBackend())).Render()
+    s2 = scene.Scene(_new_plane())
+    s2.root.Normalize()
+    cam2 = camera.Orthographic(position=(0, 1, 0), target=(0, 0, 0), up=(0, 0, -1), left=-1, right=1, bottom=-1, top=1, near=1, far=-1)
+    img2 = render.NewRenderer(render.Camera(cam2), render.Size(500, 500), render.MSAA(2), render.Scene(s2), render.Background(bg), render._Backend(ob.OracleBackend())).Render()
+    for name, mine, fg_px in (("plane_msaa2.png", img, 18612), ("normalize_msaa2.png", img2, 126736)):
+        gold = _golden(name)
+        d = np.abs(mine.astype(int) - gold.astype(int)).max(axis=2)
+        bg_gold, bg_mine = (gold[..., :3] == 0x18).all(axis=2), (mine[..., :3] == 0x18).all(axis=2)
+        assert int((bg_gold ^ bg_mine).sum()) == 0 and int((~bg_gold).sum()) == fg_px, name
+        assert int(d.max()) <= 1, name
+        assert len(np.unique(mine[~bg_mine].reshape(-1, 4), axis=0)) > 1000, name   # a colour gradient, not a flat fill
+
+
 def test_shadow_png_msaa2_two_casting_lights():
     """internal/examples/shadow_test.go:20-85 -> examples/out/shadow.png: textured bunny on the textured ground, TWO
     shadow-casting point lights, every material ReceiveShadow, MSAA(2). Alpha is identical in every pixel; of the 170 248
