@@ -1,0 +1,151 @@
+"""CPU: a model of the prc_render_peer protocol (polyred_b200/csrc/polyred_cuda.cu: enqueue_peer_frame) under random
+schedules. Every rank's stream executes the operations of its frames in order; waits block on the epoch words the peers
+write; the host of each rank submits at its own pace. The model checks what the device code relies on:
+
+  * no deadlock, whatever the interleaving of the ranks' GPUs and hosts (also when the set of image consumers changes from
+    frame to frame and when a rank's host runs many frames ahead of the others);
+  * when a rank shades frame e, every row of its copy of the shadow maps holds exactly the owner's frame-e state (no push
+    of frame e+1 has landed yet, none of frame e is missing);
+  * when a consumer reads the image of frame e, every strip in it is frame e's (no strip of e+1 has overwritten it);
+  * epoch words only ever increase.
+
+The operation list below is a transcription of enqueue_peer_frame; if the code changes, change it here too."""
+import random
+
+import pytest
+
+SHADOW, SHADED, IMAGE, IMAGE_FREE = range(4)
+
+
+def frame_ops(rank, world, e, mask, shadows=True):
+    """The stream operations of frame e on `rank` (enqueue_peer_frame, in order)."""
+    me, everyone = 1 << rank, (1 << world) - 1
+    others = everyone & ~me
+    ops = []
+    if mask & me:
+        ops.append(("signal", IMAGE_FREE, e - 1, others))
+    if shadows:
+        ops.append(("wait", SHADED, e - 1, others))
+        ops.append(("raster_shadow", e))
+        ops.append(("push", e))
+        ops.append(("signal", SHADOW, e, others))
+    ops.append(("forward", e))
+    if shadows:
+        ops.append(("wait", SHADOW, e, others))
+    ops.append(("shade", e))
+    if shadows:
+        ops.append(("signal", SHADED, e, others))
+    consumers = mask & everyone
+    if consumers & ~me:
+        ops.append(("wait", IMAGE_FREE, e - 1, consumers & ~me))
+        ops.append(("copy_strip", e, consumers & ~me))
+        ops.append(("signal", IMAGE, e, consumers & ~me))
+    if consumers & me:
+        ops.append(("wait", IMAGE, e, others))
+        ops.append(("read_image", e))  # a stream-ordered reader enqueued by the caller before the next frame
+    return ops
+
+
+def simulate(world, masks, seed, host_lookahead):
+    rng = random.Random(seed)
+    frames = len(masks)
+    words = [[[0] * world for _ in range(4)] for _ in range(world)]       # words[dst][kind][src]
+    maps = [[0] * world for _ in range(world)]                            # maps[holder][owner] = frame whose rows are in holder's copy
+    image = [[0] * world for _ in range(world)]                           # image[holder][strip owner]
+    reading = [None] * world                                              # frame a consumer's reader is looking at (None: idle)
+    queue = [[] for _ in range(world)]                                    # submitted, not yet executed
+    submitted = [0] * world                                               # frames submitted by each host
+    executed_frames = [0] * world
+    pc = [0] * world                                                      # ops executed inside the current queue head
+
+    def runnable(r):
+        if not queue[r]:
+            return False
+        op = queue[r][0]
+        if op[0] == "wait":
+            _, kind, epoch, mask = op
+            return all(words[r][kind][s] >= epoch for s in range(world) if (mask >> s) & 1)
+        return True
+
+    steps = 0
+    while any(queue) or any(s < frames for s in submitted):
+        steps += 1
+        assert steps < 200000
+        choices = [("gpu", r) for r in range(world) if runnable(r)]
+        # a host may run ahead of its own GPU by `host_lookahead` frames (bounded launch queue), independently of the others
+        choices += [("host", r) for r in range(world) if submitted[r] < frames and submitted[r] - executed_frames[r] < host_lookahead]
+        assert choices, f"deadlock: world={world} masks={masks} seed={seed} heads={[q[0] if q else None for q in queue]}"
+        what, r = rng.choice(choices)
+        if what == "host":
+            e = submitted[r] + 1
+            ops = frame_ops(r, world, e, masks[e - 1])
+            queue[r].extend(ops + [("frame_done", e)])
+            submitted[r] = e
+            continue
+        op = queue[r].pop(0)
+        kind = op[0]
+        if kind == "signal":
+            _, k, epoch, mask = op
+            for d in range(world):
+                if (mask >> d) & 1:
+                    assert words[d][k][r] <= epoch, "epoch words must not decrease"
+                    words[d][k][r] = epoch
+        elif kind == "raster_shadow":
+            maps[r][r] = op[1]
+        elif kind == "push":
+            for p in range(world):
+                if p != r:
+                    maps[p][r] = op[1]
+        elif kind == "shade":
+            e = op[1]
+            assert maps[r] == [e] * world, f"rank {r} shades frame {e} from shadow rows of frames {maps[r]}"
+            assert reading[r] is None or True
+            image[r][r] = e
+        elif kind == "copy_strip":
+            _, e, mask = op
+            for c in range(world):
+                if (mask >> c) & 1:
+                    image[c][r] = e
+        elif kind == "read_image":
+            e = op[1]
+            assert image[r] == [e] * world, f"consumer {r} reads frame {e} but its image holds strips of frames {image[r]}"
+        elif kind == "frame_done":
+            executed_frames[r] = op[1]
+    return steps
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 5, 8])
+def test_protocol_model_random_schedules(world):
+    rng = random.Random(1000 + world)
+    everyone = (1 << world) - 1
+    for trial in range(60 if world <= 3 else 25):
+        frames = rng.randint(1, 7)
+        style = trial % 4
+        if style == 0:
+            masks = [1] * frames                                  # north_star: the image goes to rank 0
+        elif style == 1:
+            masks = [everyone] * frames                           # every rank receives the image
+        elif style == 2:
+            masks = [0] * frames                                  # no device-side gather (strips leave through the shared host image)
+        else:
+            masks = [rng.randint(0, everyone) for _ in range(frames)]  # the consumer set changes from frame to frame
+        for lookahead in (1, 2, frames + 1):
+            simulate(world, masks, seed=rng.randint(0, 1 << 30), host_lookahead=lookahead)
+
+
+def test_model_detects_a_broken_protocol():
+    """The checker is not vacuous: without the SHADED wait a fast rank pushes frame e+1 into maps a slow rank still shades
+    frame e from, and some schedule exposes it."""
+    global frame_ops
+    good = frame_ops
+
+    def broken(rank, world, e, mask, shadows=True):
+        return [op for op in good(rank, world, e, mask, shadows) if not (op[0] == "wait" and op[1] == SHADED)]
+
+    frame_ops = broken
+    try:
+        with pytest.raises(AssertionError, match="shades frame"):
+            for seed in range(300):
+                simulate(3, [1, 1, 1, 1], seed=seed, host_lookahead=4)
+    finally:
+        frame_ops = good
