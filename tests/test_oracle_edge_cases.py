@@ -119,3 +119,30 @@ def test_shadow_scenes_write_shadow_maps_and_darken():
         ok = g["ok"].astype(bool)[::-1]
         assert (img[ok][:, :3].astype(int).sum(axis=1) <= plain[ok][:, :3].astype(int).sum(axis=1)).all()   # visibility only halves colours
         assert (img[ok][:, :3].astype(int).sum(axis=1) < plain[ok][:, :3].astype(int).sum(axis=1)).any()
+
+
+def test_ambient_occlusion_only_darkens_and_shadow_needs_receive_flag():
+    """The two property tests the reference has for these stages (gpu/shader/gpumath/kernels/ao_test.go:5-26: with the AO flag
+    off the colour is unchanged, with it on every channel ends in [0, original]; kernels/shadow_test.go:5-12: a fragment whose
+    material does not receive shadows keeps its colour), replayed on the oracle's CPU restatement of material/ao.go:20-73 and
+    render/raster.go:339-353."""
+    from polyred_b200 import synth
+
+    def frame(ao, shadows, recv=True):
+        s, cam = synth.mesh_scene(subdiv=24, with_ground=True, shadows=True, ao=ao)
+        if not recv:
+            for g, _ in s.geometries():
+                for m in g.materials:
+                    m.receive_shadow = False
+        be = ob.OracleBackend()
+        r = render.NewRenderer(render.Camera(cam), render.Size(160, 100), render.Scene(s), render.ShadowMap(shadows), render._Backend(be))
+        return r.Render(keep_gbuffer=True).astype(int), be.read_gbuffer(160, 100)["ok"].astype(bool)[::-1]
+
+    plain, ok = frame(ao=False, shadows=False)
+    with_ao, _ = frame(ao=True, shadows=False)
+    assert (with_ao[ok][:, :3] <= plain[ok][:, :3]).all() and (with_ao[ok][:, :3] < plain[ok][:, :3]).any()
+    assert np.array_equal(with_ao[..., 3], plain[..., 3])                                  # alpha untouched (ao.go:36)
+    shadowed, _ = frame(ao=False, shadows=True)
+    assert (shadowed[ok][:, :3] <= plain[ok][:, :3]).all() and (shadowed[ok][:, :3] < plain[ok][:, :3]).any()
+    not_receiving, _ = frame(ao=False, shadows=True, recv=False)
+    assert np.array_equal(not_receiving, plain)                                            # ShadowMap on, ReceiveShadow off: unchanged
