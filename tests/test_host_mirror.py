@@ -28,6 +28,69 @@ def test_traversal_order_and_matrix_chain():
     assert np.array_equal(geos[2][1], gm.mulm(g.ModelMatrix(), inner.ModelMatrix()))
 
 
+def test_reference_scene_graph_kats():
+    """scene/scene_test.go:19-193 (TestScene) and :331-363 (TestAddMultiple) replayed: the model matrix the iterator hands to
+    the renderer for every leaf as the graph is built up — root scaled and translated, a nested group with its own
+    transform, a group without one, a leaf added to the root later — and one object added several times."""
+    def mats(s):
+        out = []
+        s.IterObjects(lambda o, m: out.append((o, np.asarray(m, np.float32))))
+        return out
+
+    def m4(*v):
+        return np.array(v, np.float32).reshape(4, 4)
+
+    s = scene.Scene()
+    p1 = scene.Geometry(_tri())
+    g = s.Add(p1)                                     # Scene.Add returns the root group
+    assert [(o is p1, m.tolist()) for o, m in mats(s)] == [(True, np.eye(4, dtype=np.float32).tolist())]
+    g.Scale(2, 2, 2)
+    assert np.array_equal(mats(s)[0][1], m4(2, 0, 0, 0, 0, 2, 0, 0, 0, 0, 2, 0, 0, 0, 0, 1))
+    g.Translate(1, 2, 3)
+    root = m4(2, 0, 0, 1, 0, 2, 0, 2, 0, 0, 2, 3, 0, 0, 0, 1)
+    assert np.array_equal(mats(s)[0][1], root)
+    p2 = scene.Geometry(_tri())
+    g2 = scene.Group()
+    g2.Add(p2)
+    g.Add(g2)
+    g2.Scale(2, 2, 2)
+    g2.Translate(1, 1, 1)
+    got = mats(s)
+    assert [o for o, _ in got] == [p1, p2]
+    assert np.array_equal(got[0][1], root) and np.array_equal(got[1][1], m4(4, 0, 0, 3, 0, 4, 0, 4, 0, 0, 4, 5, 0, 0, 0, 1))
+    p3 = scene.Geometry(_tri())
+    g3 = scene.Group()
+    g3.Add(p3)
+    s.Add(g3)
+    got = mats(s)
+    assert [o for o, _ in got] == [p1, p2, p3] and np.array_equal(got[2][1], root)   # an untransformed group: the root's matrix
+    p4 = scene.Geometry(_tri())
+    s.Add(p4)
+    got = mats(s)
+    assert [o for o, _ in got] == [p1, p2, p3, p4] and np.array_equal(got[3][1], root)
+    assert g3.leaves() == [p3]
+    # TestAddMultiple: the same object added six times is drawn six times, a seventh time through a group
+    p = scene.Geometry(_tri())
+    s2 = scene.Scene()
+    for _ in range(6):
+        s2.Add(p)
+    assert len(mats(s2)) == 6
+    gg = scene.Group()
+    gg.Add(p)
+    s2.Add(gg)
+    assert len(mats(s2)) == 7 and len(s2.geometries()) == 7
+
+
+def test_reference_material_kats():
+    """material/pool_test.go:10-32 (TestDefault, TestNewBlinnPhong): the default material is the 1x1 blue texture with
+    Kd .7 / Ks .5 / shininess 30 (material/pool.go:15-29); NewBlinnPhong keeps the diffuse colour it is given."""
+    m = material.Default()
+    assert m.texture.image.shape == (1, 1, 4) and tuple(m.texture.image[0, 0]) == (0, 0, 255, 255)
+    assert m.diffuse == (179, 179, 179, 255) and m.specular == (128, 128, 128, 255) and float(m.shininess) == 30.0
+    want = (11, 22, 33, 255)
+    assert material.BlinnPhong(diffuse=want).diffuse == want
+
+
 def test_flat_material_table_matches_cpuForwardPass():
     """render/raster.go:252-262: flat id = base + local, negative ids stay negative, table = concatenation."""
     m0, m1, m2 = (material.BlinnPhong(texture=material.Texture.uniform((i, i, i, 255))) for i in (1, 2, 3))
