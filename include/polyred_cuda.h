@@ -285,8 +285,10 @@ int32_t prc_sync(prc_ctx* ctx);
  *   -> wait (on the device) for the peers' shadow rows -> shading -> the image strip is copied into the image of every
  *   rank in `image_mask` (bit r = rank r receives the whole frame; north_star: rank 0, mask 1).
  * Ranks are ordered by epoch words in peer memory (release/acquire at system scope); every rank must submit the same
- * sequence of prc_render_peer calls, each with the same image_mask on every rank. Frames stay on the device (PRC_FRAME_NO_READBACK is implied;
- * PRC_FRAME_KEEP_GBUFFER, PRC_FRAME_SHADOW_RESET and MSAA are rejected); a consumer's image of a frame stays valid until its
+ * sequence of prc_render_peer calls, each with the same image_mask on every rank. Frames stay on the device unless prc_set_host_image
+ * registered a host image (PRC_FRAME_KEEP_GBUFFER and PRC_FRAME_SHADOW_RESET are rejected; MSAA frames — strips must start and
+ * end on multiples of msaa — are downsampled per strip on the rank that shaded it, which shades `msaa` extra rows on either
+ * side for the filter, and need image_mask = 0: they leave through the host image); a consumer's image of a frame stays valid until its
  * next prc_render_peer (readers: the host after prc_sync, or work enqueued on prc_stream() before that call). prc_sync() finishes the submitted frames:
  * PRC_ERR_RETRY = a queue overflowed on THIS rank (grown now; all ranks must agree to submit the frames again),
  * PRC_ERR_PEER = a device-side wait for a peer gave up after 4 s.

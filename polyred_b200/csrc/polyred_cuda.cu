@@ -104,6 +104,10 @@ struct prc_ctx {
   bool defer_copy_join = false, copy_pending = false;  // see do_main: readback of peer frames overlaps the next frame's geometry
   size_t ext_img_bytes = 0;
   bool ext_img_registered = false;
+  // MSAA frames cut into strips (prc_render_peer only): the rank shades `msaa` extra supersampled rows on either side of the
+  // rows it owns — all the downsample filter reaches — and resizes only its own output rows; no exchange is needed
+  bool allow_msaa_strips = false;
+  int own_row0 = 0, own_row1 = 0;  // SCREEN rows (supersampled) whose output rows this context produces
 };
 
 namespace {
@@ -295,7 +299,9 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
   const size_t npx = (size_t)W * H;
   const int msaa = fr->msaa > 1 ? (int)fr->msaa : 1;
   if (msaa > 8 || W % msaa || H % msaa) { ctx->err = "msaa must be 1..8 and divide the frame size"; return PRC_ERR_INVALID; }
-  if (msaa > 1 && (fr->row0 != 0 || fr->row1 != fr->height)) { ctx->err = "MSAA with a partial row range (multi-GPU strips) is not supported"; return PRC_ERR_UNSUPPORTED; }
+  const bool msaa_strip = msaa > 1 && (fr->row0 != 0 || fr->row1 != fr->height);
+  if (msaa_strip && !ctx->allow_msaa_strips) { ctx->err = "MSAA with a partial row range is only supported by prc_render_peer"; return PRC_ERR_UNSUPPORTED; }
+  if (msaa_strip && (fr->row0 % msaa || fr->row1 % msaa)) { ctx->err = "MSAA strips must start and end on multiples of msaa"; return PRC_ERR_INVALID; }
   ctx->msaa = msaa;
   cudaStream_t st = ctx->stream;
   if (W != ctx->W || H != ctx->H || fr->n_lights != ctx->n_lights_alloc) {
@@ -418,10 +424,16 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
   F.W = W; F.H = H;
   F.cullW = (float)(msaa * W); F.cullH = (float)(msaa * H);
   F.row0 = fr->row0; F.row1 = fr->row1;
+  ctx->own_row0 = (int)fr->row0; ctx->own_row1 = (int)fr->row1;
+  if (msaa_strip) {
+    // output row y of imageutil.Resize reads supersampled rows [msaa*y - msaa, msaa*y + 2*msaa): shade that much beyond the strip
+    F.row0 = (uint32_t)std::max(0, (int)fr->row0 - msaa);
+    F.row1 = (uint32_t)std::min(H, (int)fr->row1 + msaa);
+  }
   // AO marches up to 99 pixels from the shaded pixel (material/ao.go:44-46): widen the rasterised rows
   const int halo = ctx->any_ao ? 100 : 0;
-  F.rr0 = std::max(0, (int)fr->row0 - halo);
-  F.rr1 = std::min(H, (int)fr->row1 + halo);
+  F.rr0 = std::max(0, (int)F.row0 - halo);
+  F.rr1 = std::min(H, (int)F.row1 + halo);
   F.flags = fr->flags;
   F.n_lights = fr->n_lights; F.n_ambient = fr->n_ambient;
   F.background = fr->background_rgba;
@@ -624,11 +636,25 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, int phases
       const int32_t rr = ensure_resize_tables(ctx, F.W, F.H, ow, oh);
       if (rr != PRC_OK) return rr;
       ENSURE(ctx->d_image_out, (size_t)ow * oh * 4);
-      k_resize<<<dim3((ow + 31) / 32, (oh + 7) / 8), 256, 0, st>>>(image, F.W, F.H, (uint32_t*)ctx->d_image_out.p, ow, oh,
-                                                                   (const short*)ctx->d_rz_cx.p, (const int*)ctx->d_rz_sx.p, ctx->rz_flx,
-                                                                   (const short*)ctx->d_rz_cy.p, (const int*)ctx->d_rz_sy.p, ctx->rz_fly);
-      ctx->launches++;
-      if (ctx->rb_dst) CK(cudaMemcpyAsync(ctx->rb_dst, ctx->d_image_out.p, (size_t)ow * oh * 4, cudaMemcpyDeviceToHost, st));
+      // output rows of the strip this context owns (image row r = screen y = H-1-r); the whole frame on one GPU
+      const int o0 = (F.H - ctx->own_row1) / ctx->msaa, o1 = (F.H - ctx->own_row0) / ctx->msaa;
+      if (o0 == 0 && o1 == oh) {
+        k_resize<<<dim3((ow + 31) / 32, (oh + 7) / 8), 256, 0, st>>>(image, F.W, F.H, (uint32_t*)ctx->d_image_out.p, ow, oh,
+                                                                     (const short*)ctx->d_rz_cx.p, (const int*)ctx->d_rz_sx.p, ctx->rz_flx,
+                                                                     (const short*)ctx->d_rz_cy.p, (const int*)ctx->d_rz_sy.p, ctx->rz_fly);
+        ctx->launches++;
+        if (ctx->rb_dst) CK(cudaMemcpyAsync(ctx->rb_dst, ctx->d_image_out.p, (size_t)ow * oh * 4, cudaMemcpyDeviceToHost, st));
+      } else if (o1 > o0) {
+        // a strip: the same kernel on the sub-range of output rows (its row tables and its output are offset, the
+        // supersampled input rows it reads are absolute and were shaded with the halo above)
+        k_resize<<<dim3((ow + 31) / 32, (o1 - o0 + 7) / 8), 256, 0, st>>>(
+            image, F.W, F.H, (uint32_t*)ctx->d_image_out.p + (size_t)o0 * ow, ow, o1 - o0, (const short*)ctx->d_rz_cx.p, (const int*)ctx->d_rz_sx.p,
+            ctx->rz_flx, (const short*)ctx->d_rz_cy.p + (size_t)o0 * ctx->rz_fly, (const int*)ctx->d_rz_sy.p + o0, ctx->rz_fly);
+        ctx->launches++;
+        if (ctx->rb_dst)
+          CK(cudaMemcpyAsync(ctx->rb_dst + (size_t)o0 * ow * 4, (const uint8_t*)ctx->d_image_out.p + (size_t)o0 * ow * 4, (size_t)(o1 - o0) * ow * 4,
+                             cudaMemcpyDeviceToHost, st));
+      }
     }
     ctx->gbuffer_valid = !fused;
   }
@@ -1326,7 +1352,9 @@ int32_t prc_peer_export(prc_ctx* ctx, const prc_frame* fr, prc_peer_handle* out)
   if (ctx->pending_async) { const int32_t pr_ = prc_sync(ctx); if (pr_ != PRC_OK) return pr_; }
   peer_release(ctx);
   DevFrame F;
+  ctx->allow_msaa_strips = true;
   int32_t r = build_frame(ctx, fr, F);  // allocates (and, for a new size / light set, zeroes) the shadow and image buffers
+  ctx->allow_msaa_strips = false;
   if (r != PRC_OK) return r;
   ENSURE(ctx->d_peer_signals, ipc_round((size_t)PRC_SIG_KINDS * PRC_PEER_MAX * 4));  // its own 2 MiB block (see build_frame)
   ENSURE(ctx->d_peer_err, 16);
@@ -1452,17 +1480,24 @@ int32_t prc_render_peer(prc_ctx* ctx, const prc_frame* fr, uint32_t n, const uin
   CK(cudaSetDevice(ctx->device));
   if (!ctx->peers.world) { ctx->err = "prc_render_peer: not connected (prc_peer_export / prc_peer_connect)"; return PRC_ERR_INVALID; }
   if (!fr || fr->abi_version != PRC_ABI_VERSION) { ctx->err = "prc_frame: bad abi_version"; return PRC_ERR_INVALID; }
-  if ((fr->flags & (PRC_FRAME_KEEP_GBUFFER | PRC_FRAME_SHADOW_RESET)) || fr->msaa > 1) {
-    ctx->err = "prc_render_peer: PRC_FRAME_KEEP_GBUFFER, PRC_FRAME_SHADOW_RESET and MSAA are not supported";
+  if (fr->flags & (PRC_FRAME_KEEP_GBUFFER | PRC_FRAME_SHADOW_RESET)) {
+    ctx->err = "prc_render_peer: PRC_FRAME_KEEP_GBUFFER and PRC_FRAME_SHADOW_RESET are not supported";
+    return PRC_ERR_UNSUPPORTED;
+  }
+  const uint32_t ms = fr->msaa > 1 ? fr->msaa : 1;
+  if (ms > 1 && image_mask != 0) {
+    ctx->err = "prc_render_peer: MSAA frames have no device-side gather (image_mask must be 0): the downsampled strips leave through prc_set_host_image";
     return PRC_ERR_UNSUPPORTED;
   }
   if (n && (!light || !row0 || !row1)) return PRC_ERR_INVALID;
-  if (!(fr->flags & PRC_FRAME_NO_READBACK) && ctx->ext_img && ctx->ext_img_bytes < (size_t)fr->width * fr->height * 4) {
+  if (!(fr->flags & PRC_FRAME_NO_READBACK) && ctx->ext_img && ctx->ext_img_bytes < (size_t)(fr->width / ms) * (fr->height / ms) * 4) {
     ctx->err = "prc_render_peer: the host image registered with prc_set_host_image is smaller than the frame";
     return PRC_ERR_INVALID;
   }
   DevFrame F;
+  ctx->allow_msaa_strips = true;
   int32_t r = build_frame(ctx, fr, F);
+  ctx->allow_msaa_strips = false;
   if (r != PRC_OK) return r;
   if (ctx->d_shadow_all.p != ctx->peer_shadow_self || ctx->d_image.p != ctx->peer_image_self) {
     // the frame size or the set of casting lights changed: the peers still map the old buffers

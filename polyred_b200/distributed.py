@@ -126,15 +126,18 @@ class PeerFrames:
         self.rank, self.world, self.root = rank, world, root
         self.device = torch.device("cuda", device)
         c = renderer.cfg
-        self.w, self.h = c.Width, c.Height
+        self.w, self.h = c.Width, c.Height          # the frame handed back (render.Size)
+        self.msaa = max(1, int(getattr(c, "MSAA", 1)))             # the frame buffer and the shadow maps are msaa times larger (raster.go:149)
+        self.hs = self.h * self.msaa
         sources, _ = c.Scene.Lights()
         cast = [i for i, l in enumerate(sources) if l.cast_shadow] if c.ShadowMap else []
-        # contiguous ranges of image rows / of the stacked shadow rows per rank: equal to begin with, rebalance() moves them
+        # contiguous ranges of OUTPUT image rows / of the stacked shadow rows per rank: equal to begin with, rebalance() moves them
         self.cast = cast
         self.img_bounds = partition.equal_bounds(self.h, world)
-        self.sh_bounds = partition.equal_bounds(len(cast) * self.h, world)
+        self.sh_bounds = partition.equal_bounds(len(cast) * self.hs, world)
         self._apply_bounds()
-        self.image_mask = 1 << root
+        # MSAA frames are downsampled per strip on the rank that shaded it and have no device-side gather (share_host_image())
+        self.image_mask = (1 << root) if self.msaa == 1 else 0
         self._submitted = []
         self._host = self._host_np = None
         self._connect(renderer.frame_desc(no_readback=True))
@@ -187,8 +190,9 @@ class PeerFrames:
         self.dist.all_gather_object(done, True, group=self.group)
 
     def _apply_bounds(self):
-        self.rows = partition.strips_from_bounds(self.h, self.img_bounds)
-        self.units = [(li, a, b) for li, a, b, owner in partition.shadow_units_from_bounds(self.h, self.cast, self.sh_bounds) if owner == self.rank]
+        m = self.msaa
+        self.rows = [(a * m, b * m) for a, b in partition.strips_from_bounds(self.h, self.img_bounds)]  # screen rows of the frame buffer
+        self.units = [(li, a, b) for li, a, b, owner in partition.shadow_units_from_bounds(self.hs, self.cast, self.sh_bounds) if owner == self.rank]
 
     def rebalance(self, damping: float = 0.7, min_rows: int = 16):
         """Move the strip and shadow-shard boundaries so that every rank gets the same share of the time the last finished
@@ -237,6 +241,10 @@ class PeerFrames:
     def submit(self, fd, gather: bool = True):
         """Enqueue one frame; does not wait for the GPU or for the peers. gather=False: no device-side gather of the strips
         (frames that leave through the shared host image, share_host_image())."""
+        if self.msaa > 1 and fd.struct.flags & 16 and gather:  # PRC_FRAME_NO_READBACK: an MSAA frame would stay scattered over the ranks
+            from ._lib import PolyredCudaError
+            from . import _abi as A
+            raise PolyredCudaError(A.PRC_ERR_UNSUPPORTED, "PeerFrames: MSAA frames leave through share_host_image() (frame_desc(no_readback=False), gather=False)")
         self.be.render_peer(self.prepare(fd), self.units, self.image_mask if gather else 0)
         self._submitted.append((fd, gather))
 

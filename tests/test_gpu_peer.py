@@ -144,3 +144,41 @@ def test_peer_strip_readback_into_one_host_image(monkeypatch):
         r._backend.set_host_image(None)
         r._backend.peer_disconnect()
 
+
+@_EXTRA
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_msaa_strips_downsample_locally(monkeypatch, world):
+    """render.MSAA(2) over strips: every rank shades `msaa` supersampled rows beyond its strip, runs imageutil.Resize on its own
+    output rows and reads them back into the one host image; no exchange. Must equal the 1-GPU MSAA frame byte for byte."""
+    monkeypatch.setenv("PRC_FMA", "exact")
+    s, cam, w, h = _scene(240, 136)
+    opts = _opts(s, cam, w, h) + [render.MSAA(2)]
+    ref = render.NewRenderer(*opts, render.CUDA(0)).Render().copy()
+    sources, _ = s.Lights()
+    cast = [i for i, l in enumerate(sources) if l.cast_shadow]
+    rows = [(a * 2, b * 2) for a, b in partition.strips_from_bounds(h, partition.equal_bounds(h, world))]
+    units = partition.shadow_units(h * 2, world, cast)
+    host = np.zeros((h, w, 4), np.uint8)
+    rs, fds = [], []
+    handles = []
+    for k in range(world):
+        r = render.NewRenderer(*opts, render.CUDA(0))
+        r._ensure_uploaded()
+        fd = r.frame_desc(no_readback=False)
+        fd.struct.row0, fd.struct.row1 = rows[k]
+        handles.append(r._backend.peer_export(fd))
+        rs.append(r)
+        fds.append(fd)
+    for k, r in enumerate(rs):
+        r._backend.peer_connect(k, world, handles)
+        r._backend.set_host_image(host.ctypes.data, host.nbytes)
+    for _ in range(2):
+        for k, r in enumerate(rs):
+            r._backend.render_peer(fds[k], [(li, a, b) for li, a, b, owner in units if owner == k], 0)
+    for r in rs:
+        r._backend.sync()
+    assert int((ref != host).any(axis=2).sum()) == 0
+    for r in rs:
+        r._backend.set_host_image(None)
+        r._backend.peer_disconnect()
+

@@ -248,3 +248,29 @@ def test_pixel_format_bgra_swaps_red_and_blue():
     rgba = render.NewRenderer(*opts, render._Backend(ob.OracleBackend())).Render()
     bgra = render.NewRenderer(*opts, render.PixelFormat(1), render._Backend(ob.OracleBackend())).Render()
     assert np.array_equal(bgra, rgba[..., [2, 1, 0, 3]]) and not np.array_equal(bgra, rgba)
+
+
+def test_msaa_strip_halo_covers_the_resize_filter():
+    """prc_render_peer shades `msaa` supersampled rows beyond a strip before it downsamples the strip's own output rows (MSAA
+    frames cut into strips need no exchange). That halo must contain every input row imageutil.Resize reads with a non-zero
+    coefficient (createWeights8, resize.go:143-164) for the strip's output rows — checked here for every MSAA factor and a range
+    of heights, and end to end: a strip-wise downsample with the halo equals the whole-frame Resize."""
+    from polyred_b200 import imageutil
+    for m in range(2, 9):
+        for out_h in (1, 2, 5, 17, 100, 135, 540):
+            coeffs, start, fl = imageutil._create_weights8(out_h, 2, np.float32(out_h * m) / np.float32(out_h))
+            rows = start[:, None] + np.arange(fl)[None, :]
+            used = coeffs != 0
+            y = np.arange(out_h)[:, None]
+            assert (rows[used] >= (m * y - m + 0 * rows)[used]).all() and (rows[used] < (m * y + 2 * m + 0 * rows)[used]).all(), (m, out_h)
+    rng = np.random.default_rng(9)
+    m, out_h, out_w = 2, 30, 16
+    big = rng.integers(0, 256, size=(out_h * m, out_w * m, 4), dtype=np.uint8)
+    want = imageutil.resize(out_w, out_h, big)
+    got = np.zeros_like(want)
+    for o0, o1 in ((0, 7), (7, 19), (19, 30)):                      # three strips of output rows
+        a, b = max(0, o0 * m - m), min(out_h * m, o1 * m + m)      # the rows a rank shades: its strip + the halo
+        masked = np.zeros_like(big)
+        masked[a:b] = big[a:b]                                     # everything else is garbage to this rank (zeros here)
+        got[o0:o1] = imageutil.resize(out_w, out_h, masked)[o0:o1]
+    assert np.array_equal(got, want)

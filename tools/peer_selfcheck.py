@@ -108,6 +108,45 @@ def main():
             except Exception as e:  # noqa: BLE001
                 log(f"disconnect: {e}")
             r._backend.close()
+    # MSAA(2) over strips: local downsample of each rank's own output rows, read back into one host image
+    w, h, m = 240, 136, 2
+    opts = [render.Camera(cam), render.Size(w, h), render.Scene(s), render.ShadowMap(True), render.GammaCorrection(True), render.MSAA(m)]
+    ref = render.NewRenderer(*opts, render.CUDA(0)).Render().copy()
+    for world in range(2, max_world + 1):
+        rows = [(a * m, b * m) for a, b in partition.strips_from_bounds(h, partition.equal_bounds(h, world))]
+        units = partition.shadow_units(h * m, world, cast)
+        host = np.zeros((h, w, 4), np.uint8)
+        rs, fds, handles = [], [], []
+        status = "ok"
+        try:
+            for k in range(world):
+                r = render.NewRenderer(*opts, render.CUDA(0))
+                r._ensure_uploaded()
+                fd = r.frame_desc(no_readback=False)
+                fd.struct.row0, fd.struct.row1 = rows[k]
+                handles.append(r._backend.peer_export(fd))
+                rs.append(r)
+                fds.append(fd)
+            for k, r in enumerate(rs):
+                r._backend.peer_connect(k, world, handles)
+                r._backend.set_host_image(host.ctypes.data, host.nbytes)
+            for _ in range(2):
+                for k, r in enumerate(rs):
+                    r._backend.render_peer(fds[k], [(li, a, b) for li, a, b, owner in units if owner == k], 0)
+            for r in rs:
+                r._backend.sync()
+        except Exception as e:  # noqa: BLE001
+            status = f"ERROR {e}"
+        nd = int((ref != host).any(axis=2).sum())
+        log(f"world={world} MSAA({m}) strips {w}x{h}: {status}; pixels differing from the 1-GPU MSAA frame = {nd}")
+        bad += nd + (status != "ok")
+        for r in rs:
+            try:
+                r._backend.set_host_image(None)
+                r._backend.peer_disconnect()
+            except Exception as e:  # noqa: BLE001
+                log(f"cleanup: {e}")
+            r._backend.close()
     log("PASS" if bad == 0 else "FAIL")
     return 0 if bad == 0 else 1
 
