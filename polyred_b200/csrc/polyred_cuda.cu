@@ -1356,6 +1356,13 @@ int32_t prc_peer_export(prc_ctx* ctx, const prc_frame* fr, prc_peer_handle* out)
   int32_t r = build_frame(ctx, fr, F);  // allocates (and, for a new size / light set, zeroes) the shadow and image buffers
   ctx->allow_msaa_strips = false;
   if (r != PRC_OK) return r;
+  if (ctx->msaa > 1) {
+    // the downsample tables are built here: building them inside the first frame would wait on the host for a stream that
+    // may itself be waiting for a peer
+    r = ensure_resize_tables(ctx, (int)fr->width, (int)fr->height, (int)fr->width / ctx->msaa, (int)fr->height / ctx->msaa);
+    if (r != PRC_OK) return r;
+    ENSURE(ctx->d_image_out, (size_t)(fr->width / ctx->msaa) * (fr->height / ctx->msaa) * 4);
+  }
   ENSURE(ctx->d_peer_signals, ipc_round((size_t)PRC_SIG_KINDS * PRC_PEER_MAX * 4));  // its own 2 MiB block (see build_frame)
   ENSURE(ctx->d_peer_err, 16);
   CK(cudaMemsetAsync(ctx->d_peer_signals.p, 0, (size_t)PRC_SIG_KINDS * PRC_PEER_MAX * 4, ctx->stream));
