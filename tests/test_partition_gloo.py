@@ -252,3 +252,18 @@ def test_peer_frames_host_logic_two_ranks():
         assert rows == {(50, 100)} if rank == 0 else rows == {(0, 50)}  # rank 0 owns the top image rows = the high screen rows
         units = set(calls[0][3])
         assert units == ({(0, 0, 100)} if rank == 0 else {(2, 0, 100)})  # lights 0 and 2 cast: one whole map per rank
+
+
+def test_peer_frames_msaa_rows_are_supersampled_and_aligned():
+    """With render.MSAA(m) the strips are cut in OUTPUT rows and handed to the library in frame-buffer rows (multiples of m, which
+    prc_render_peer requires); the shadow maps live at the supersampled size."""
+    from polyred_b200.distributed import PeerFrames
+    for m, h, world in ((2, 135, 4), (3, 50, 3), (1, 100, 8)):
+        pf = PeerFrames.__new__(PeerFrames)
+        pf.msaa, pf.h, pf.hs, pf.rank, pf.cast = m, h, h * m, 1, [0, 2]
+        pf.img_bounds = partition.balanced_bounds(partition.equal_bounds(h, world), [1.0 + k for k in range(world)])
+        pf.sh_bounds = partition.equal_bounds(2 * h * m, world)
+        pf._apply_bounds()
+        assert all(a % m == 0 and b % m == 0 for a, b in pf.rows)
+        assert sorted(pf.rows)[0][0] == 0 and sorted(pf.rows)[-1][1] == h * m and sum(b - a for a, b in pf.rows) == h * m
+        assert all(0 <= a < b <= h * m for _, a, b in pf.units) and sum(b - a for _, a, b in pf.units) == pf.sh_bounds[2] - pf.sh_bounds[1]
