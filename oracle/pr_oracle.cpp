@@ -232,7 +232,11 @@ void draw_clipped(Ctx& c, const FrameU& u, const Vertex& t1, const Vertex& t2, c
       Fragment& dst = c.frags[(size_t)y * c.W + x];
       {
         PixelLock lk(mt ? &c.locks[(size_t)y * c.W + x] : nullptr);
-        if (!((!dst.ok) || z > dst.depth)) continue;  // DepthTest buffer.go:279
+        // DepthTest buffer.go:279. Multithreaded mode only: at EQUAL depth the fragment drawn earlier wins whatever the arrival
+        // order, which is what the sequential pass (the parity oracle) produces — the reference itself is non-deterministic
+        // there with Workers > 1 (bug-list 11); the full-size parity test runs this mode and must not depend on thread timing.
+        const bool earlier = mt && dst.ok && z == dst.depth && ((int64_t)(tri + 1) * 8 + subidx) < ((int64_t)dst.tri * 8 + dst.sub);
+        if (!((!dst.ok) || z > dst.depth || earlier)) continue;
       }
       if (std::isnan(z)) __atomic_fetch_add(&c.tm.n_nan_frags, 1, __ATOMIC_RELAXED);
 
@@ -274,7 +278,9 @@ void draw_clipped(Ctx& c, const FrameU& u, const Vertex& t1, const Vertex& t2, c
       };
 
       PixelLock lk(mt ? &c.locks[(size_t)y * c.W + x] : nullptr);
-      if (dst.ok && z <= dst.depth) continue;  // Set buffer.go:230
+      if (dst.ok && z <= dst.depth &&
+          !(mt && z == dst.depth && ((int64_t)(tri + 1) * 8 + subidx) < ((int64_t)dst.tri * 8 + dst.sub)))
+        continue;  // Set buffer.go:230 (+ the deterministic tie rule of the multithreaded mode, see above)
       dst.ok = true;
       dst.X = x; dst.Y = y;
       dst.depth = z; dst.u = uvX; dst.v = uvY; dst.du = du; dst.dv = dv;

@@ -159,6 +159,40 @@ def test_oracle_is_deterministic_and_mt_mode_agrees_without_ties():
     assert (np.abs(a.astype(int) - c.astype(int)).max(axis=2) > 0).mean() < 0.01  # Workers>1 only differs at depth ties
 
 
+def test_oracle_mt_mode_equals_the_sequential_oracle_at_depth_ties():
+    """bug-list 11: with Workers > 1 the reference is non-deterministic where fragments tie in depth. The oracle's multithreaded
+    mode (CPU-baseline timing, full-size parity test) resolves a tie in favour of the fragment drawn earlier, i.e. exactly like
+    the sequential pass, whatever the thread timing: 6000 random coplanar triangles in two objects, 8 threads, several runs."""
+    rng = np.random.default_rng(3)
+
+    def tris(n):
+        c = rng.uniform(-1, 1, size=(n, 1, 2)).astype(np.float32)
+        d = rng.uniform(-0.15, 0.15, size=(n, 3, 2)).astype(np.float32)
+        p = np.concatenate([c + d, np.zeros((n, 3, 1), np.float32)], axis=2)
+        e1, e2 = p[:, 1] - p[:, 0], p[:, 2] - p[:, 0]
+        cw = (e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0]) < 0
+        p[cw] = p[cw][:, [0, 2, 1]]
+        return p
+
+    mat = material.BlinnPhong(texture=synth.checker_texture(64, seed=3))
+    s = scene.Scene(light.Point(intensity=3, position=(0, 0, 3)), light.Ambient(intensity=0.4),
+                    scene.Geometry(tris(3000), None, None, None, np.zeros(3000, np.int32), [mat]),
+                    scene.Geometry(tris(3000), None, None, None, np.zeros(3000, np.int32), [mat]))
+    cam = camera.Perspective(position=(0, 0, 3), fov=45, aspect=1, near=0.1, far=10)
+
+    def run(threads):
+        be = ob.OracleBackend(threads)
+        img = render.NewRenderer(render.Camera(cam), render.Size(256, 256), render.Scene(s), render._Backend(be)).Render(keep_gbuffer=True).copy()
+        return img, be.read_gbuffer(256, 256)
+
+    a, ga = run(1)
+    covered = ga["ok"].astype(bool)
+    assert covered.sum() > 40000
+    for _ in range(4):
+        b, gb = run(8)
+        assert np.array_equal(ga["tri"], gb["tri"]) and np.array_equal(ga["sub"], gb["sub"]) and np.array_equal(a, b)
+
+
 def test_view_frames_match_render_views_on_the_oracle():
     """ViewFrames() (PRC_FRAME_SHADOW_RESET, views submitted back to back) gives the frames RenderViews() gives
     (Options(Camera) + Render per view) — checked on the CPU oracle; the CUDA twin is in test_gpu_parity.py."""
