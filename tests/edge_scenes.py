@@ -86,6 +86,22 @@ def edge_scenes():
     g1 = _tri_geo(huge[:1], material.BlinnPhong(texture=_tex(64, 6)))
     g2 = _tri_geo(huge[1:], material.BlinnPhong(texture=_tex(64, 7)))
     out["screen_filling_and_depth_tie"] = (_lights(scene.Scene(g1, g2)), _cam(pos=(0, 0, 2.5)), 100, 64, dict(gamma=True))  # camera axis = plane normal
+    # thousands of random COPLANAR triangles in two objects: almost every covered pixel is an exact depth tie between several
+    # triangles, resolved by draw order (buffer.go:279) — on the CUDA path by the sequence half of the 64-bit visibility key
+    rng = np.random.default_rng(3)
+
+    def coplanar(n):
+        c = rng.uniform(-1, 1, size=(n, 1, 2)).astype(np.float32)
+        d = rng.uniform(-0.15, 0.15, size=(n, 3, 2)).astype(np.float32)
+        p = np.concatenate([c + d, np.zeros((n, 3, 1), np.float32)], axis=2)
+        e1, e2 = p[:, 1] - p[:, 0], p[:, 2] - p[:, 0]
+        cw = (e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0]) < 0
+        p[cw] = p[cw][:, [0, 2, 1]]
+        return p
+
+    tmat = material.BlinnPhong(texture=_tex())
+    out["coplanar_depth_ties"] = (_lights(scene.Scene(_tri_geo(coplanar(3000), tmat), _tri_geo(coplanar(3000), tmat))),
+                                  camera.Perspective(position=(0, 0, 3), fov=45, aspect=1, near=0.1, far=10), 256, 256, {})
     # pixel (0,0) covered, most pixels not: every uncovered pixel is shaded from G(0,0) with matTable[0] (bug-list 3)
     q = [[[-0.2, -0.2, 0], [0.2, -0.2, 0], [0, 0.2, 0]], [[-3, -3, 0], [1, -3, 0], [-3, 1, 0]]]
     out["pixel00_quirk"] = (scene.Scene(light.Ambient(intensity=1), _tri_geo(q, material.BlinnPhong(texture=material.Texture.uniform((10, 200, 30, 255))))),
