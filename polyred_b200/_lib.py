@@ -224,6 +224,18 @@ class CudaBackend(Backend):
         """Readback destination of prc_render_peer frames: a caller-owned host image (e.g. shared memory mapped by every rank)."""
         self._check(self.L.prc_set_host_image(self.h, address, nbytes))
 
+    @staticmethod
+    def unit_arrays(units):
+        """[(light, row0, row1)] -> the three contiguous uint32 arrays prc_render_peer takes (build once, submit many frames)."""
+        n = len(units)
+        a = np.array(units, dtype=np.uint32).reshape(n, 3)
+        return n, tuple(np.ascontiguousarray(a[:, k]) for k in range(3))
+
+    def render_peer_arrays(self, fd, n, arrays, image_mask: int = 1):
+        li, r0, r1 = arrays
+        self._check(self.L.prc_render_peer(self.h, C.byref(fd.struct), n, li.ctypes.data if n else None, r0.ctypes.data if n else None,
+                                           r1.ctypes.data if n else None, image_mask))
+
     def render_peer(self, fd, units, image_mask: int = 1):
         """Submit one frame of the group without waiting (units: this rank's [(light, row0, row1)])."""
         n = len(units)
