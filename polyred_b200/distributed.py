@@ -194,7 +194,8 @@ class PeerFrames:
         self.rows = [(a * m, b * m) for a, b in partition.strips_from_bounds(self.h, self.img_bounds)]  # screen rows of the frame buffer
         self.units = [(li, a, b) for li, a, b, owner in partition.shadow_units_from_bounds(self.hs, self.cast, self.sh_bounds) if owner == self.rank]
         # the arrays prc_render_peer takes, built once per partition (a frame at 8 GPUs is ~0.2 ms: host microseconds count)
-        self._unit_arrays = self.be.unit_arrays(self.units) if hasattr(self.be, "unit_arrays") else None
+        be = getattr(self, "be", None)
+        self._unit_arrays = be.unit_arrays(self.units) if hasattr(be, "unit_arrays") else None
 
     def rebalance(self, damping: float = 0.7, min_rows: int = 16):
         """Move the strip and shadow-shard boundaries so that every rank gets the same share of the time the last finished
