@@ -320,7 +320,16 @@ class Renderer:
                 cam = self._light_cams[i]
                 lv, lp = cam.ViewMatrix(), cam.ProjMatrix()
                 pl.view, pl.proj = _m16(lv), _m16(lp)
-                st = np.ascontiguousarray(gm.mulm(gm.mulm(lp, lv)[None], model).reshape(nobj, 16), dtype=np.float32)  # shadow.go:155
+                # shadow.go:155: lightProj.MulM(lightView).MulM(Model) per object. It depends on the light camera (re-fitted only by
+                # NewRenderer / Options) and the model matrices, not on the frame: cached per light until either changes
+                cache = sd.__dict__.setdefault("_shadow_trans", {})
+                key = (lv.tobytes(), lp.tobytes())
+                hit = cache.get(i)
+                if hit is not None and hit[0] is model and hit[1] == key:
+                    st = hit[2]
+                else:
+                    st = np.ascontiguousarray(gm.mulm(gm.mulm(lp, lv)[None], model).reshape(nobj, 16), dtype=np.float32)
+                    cache[i] = (model, key, st)
                 fd.keep.append(st)
                 pl.shadow_trans = st.ctypes.data_as(C.POINTER(C.c_float))
         fd.keep.append(lights)
