@@ -298,12 +298,20 @@ class Renderer:
                 sd._static_xf = (m_, gm.transpose(gm.inv(m_)))  # raster.go:243
                 sd._lights = c.Scene.Lights()
             model, normal = sd._static_xf
-            trans = gm.mulm(gm.mulm(proj, view)[None], model)  # raster.go:382
+            # raster.go:382: Proj.MulM(View).MulM(Model) per object; unchanged while neither the camera nor a model matrix moves
+            key = (view.tobytes(), proj.tobytes())
+            hit = getattr(sd, "_object_xf", None)
+            if hit is not None and hit[0] is model and hit[1] == key:
+                flat = hit[2]
+            else:
+                trans = gm.mulm(gm.mulm(proj, view)[None], model)
+                flat = np.ascontiguousarray(np.concatenate([trans.reshape(nobj, 16), normal.reshape(nobj, 16)], axis=1), dtype=np.float32)
+                sd._object_xf = (model, key, flat)
         else:
-            model = normal = trans = np.zeros((0, 4, 4), np.float32)
+            model = normal = np.zeros((0, 4, 4), np.float32)
+            flat = np.zeros((0, 32), np.float32)
             sd._lights = c.Scene.Lights()
         objs = (A.prc_object_xf * max(1, nobj))()
-        flat = np.concatenate([trans.reshape(nobj, 16), normal.reshape(nobj, 16)], axis=1).astype(np.float32) if nobj else np.zeros((0, 32), np.float32)
         C.memmove(objs, flat.ctypes.data, flat.nbytes)
         fd.keep.append(objs)
         sources, envs = sd._lights
@@ -318,7 +326,10 @@ class Renderer:
             pl.cast_shadow = 1 if (l.cast_shadow and c.ShadowMap) else 0
             if c.ShadowMap and l.cast_shadow:
                 cam = self._light_cams[i]
-                lv, lp = cam.ViewMatrix(), cam.ProjMatrix()
+                mats = getattr(cam, "_matrices", None)  # a light camera is immutable once initShadowMaps has fitted it
+                if mats is None:
+                    mats = cam._matrices = (cam.ViewMatrix(), cam.ProjMatrix())
+                lv, lp = mats
                 pl.view, pl.proj = _m16(lv), _m16(lp)
                 # shadow.go:155: lightProj.MulM(lightView).MulM(Model) per object. It depends on the light camera (re-fitted only by
                 # NewRenderer / Options) and the model matrices, not on the frame: cached per light until either changes
