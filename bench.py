@@ -355,6 +355,20 @@ def run_cuda(args):
     barrier()
     wall_e2e = time.perf_counter() - t0
 
+    # the same frames through the host mirror's Renderer.Render() (scene-graph walk, uniforms, prc_render, image in place): what a
+    # Python caller pays on top of the C-ABI call. Informational only; never allowed to break the bench line.
+    mirror_ms = None
+    if world == 1:
+        try:
+            for _ in range(2):
+                r.Render()
+            t1 = time.perf_counter()
+            for _ in range(args.steps):
+                r.Render()
+            mirror_ms = (time.perf_counter() - t1) * 1e3 / args.steps
+        except Exception as e:  # noqa: BLE001
+            print(f"Renderer.Render() leg skipped: {e}", file=sys.stderr)
+
     if dist is not None:
         tt = torch.tensor([dev_ms, wall * 1e3, wall_e2e * 1e3], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -416,7 +430,8 @@ def run_cuda(args):
                 "note": ("prc_render_peer through the C ABI on every rank: host prc_frame (per-object matrices) in on every rank, host RGBA8 out as one shared-memory image "
                          "that each GPU writes its strip into over its own PCIe link; scene resident after one prc_scene_upload per rank" if pf is not None else
                          "prc_render through the C ABI: host prc_frame (per-object matrices) in, host RGBA8 out; scene resident after one prc_scene_upload"),
-                "scene_upload_once": {"bytes": int(sd.upload_bytes()), "seconds": t_upload}},
+                "scene_upload_once": {"bytes": int(sd.upload_bytes()), "seconds": t_upload},
+                "python_renderer_render_ms_per_step": mirror_ms},
         "stats_last_frame": {"n_large_items": int(tm.n_large_items), "n_clipped": int(tm.n_clipped), "n_bin_entries": int(tm.n_bin_entries), "n_nan_frags": int(tm.n_nan_frags)},
         "gpu_launches": launches, "clocks": clocks, "scene_gen_seconds": tgen,
     }
