@@ -11,7 +11,12 @@ same through the C-ABI call with HOST buffers: per step the frame uniforms go ho
 RGBA8 image comes back device->host inside the timed region.
 N>1 (torchrun, one process per GPU): the frame is split into N horizontal screen strips, the Ls
 shadow maps are sharded (light x row range) and all-gathered with NCCL, the image strips are
-gathered to rank 0; `scaling` = "strong" (same frame, more GPUs).
+gathered to rank 0; `scaling` = "strong" (same frame, more GPUs). `--mgpu peer` runs the same
+partition through prc_render_peer instead (NVLink peer memory, frames back to back, strips balanced
+by measured time, e2e through one shared host image); `--mgpu nccl` is the default until the peer
+path has been timed on several devices.
+`e2e.python_renderer_render_ms_per_step` (N=1, informational): the same frame through the Python
+mirror's Renderer.Render(), i.e. including the host-side uniforms.
 """
 from __future__ import annotations
 
