@@ -267,3 +267,28 @@ def test_peer_frames_msaa_rows_are_supersampled_and_aligned():
         assert all(a % m == 0 and b % m == 0 for a, b in pf.rows)
         assert sorted(pf.rows)[0][0] == 0 and sorted(pf.rows)[-1][1] == h * m and sum(b - a for a, b in pf.rows) == h * m
         assert all(0 <= a < b <= h * m for _, a, b in pf.units) and sum(b - a for _, a, b in pf.units) == pf.sh_bounds[2] - pf.sh_bounds[1]
+
+
+def test_balanced_bounds_properties_hypothesis():
+    """Whatever the measured costs, the new boundaries cover the same range, never decrease, keep min_size rows per rank when
+    there is room, and a perfectly balanced partition of a uniform density is a fixed point."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(1, 9), st.integers(0, 5000), st.data())
+    def prop(n, total, data):
+        cuts = sorted(data.draw(st.lists(st.integers(0, total), min_size=n - 1, max_size=n - 1)))
+        bounds = [0] + cuts + [total]
+        cost = data.draw(st.lists(st.floats(0, 1e3, allow_nan=False, allow_infinity=False), min_size=n, max_size=n))
+        damping = data.draw(st.sampled_from([0.3, 0.7, 1.0]))
+        min_size = data.draw(st.sampled_from([1, 4, 16]))
+        new = partition.balanced_bounds(bounds, cost, damping, min_size)
+        assert len(new) == n + 1 and new[0] == 0 and new[-1] == total
+        assert all(a <= b for a, b in zip(new, new[1:]))
+        if sum(cost) > 0 and total >= n * min_size and n > 1 and total > 0:
+            assert all(b - a >= min_size for a, b in zip(new, new[1:])), (bounds, cost, new)
+
+    prop()
+    for n in (2, 3, 8):
+        eq = partition.equal_bounds(240 * n, n)
+        assert partition.balanced_bounds(eq, [5.0] * n) == eq
