@@ -328,6 +328,7 @@ def run_cuda(args):
         with torch.cuda.stream(stream):
             e1.record(stream)
         barrier()  # be.sync() finishes the asynchronous frames (raises if a queue overflowed: warm-up sized them)
+        peer_wait = be.peer_wait_ms() if pf is not None else None  # PRC_PEER_TRACE=1: where this rank idled for its peers
         wall = time.perf_counter() - t0
         sampler.window(t0, t0 + wall)
         fd.struct.flags &= ~A.PRC_FRAME_ASYNC
@@ -444,6 +445,7 @@ def run_cuda(args):
         line["config"]["strip_rows"] = [r1 - r0 for r0, r1 in pf.rows]
         line["config"]["shadow_rows_per_rank"] = [b - a for a, b in zip(pf.sh_bounds, pf.sh_bounds[1:])]
         line["balance_rounds"] = balance_log
+        line["peer_wait_ms_per_step_rank0"] = {k: v / args.steps for k, v in peer_wait.items()} if peer_wait else None
     if args.cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args, wl, s, cam)
     emit(line)

@@ -311,6 +311,10 @@ int32_t prc_peer_connect(prc_ctx* ctx, uint32_t rank, uint32_t world, const prc_
 int32_t prc_peer_disconnect(prc_ctx* ctx);
 int32_t prc_render_peer(prc_ctx* ctx, const prc_frame* frame, uint32_t n_units, const uint32_t* light, const uint32_t* row0,
                         const uint32_t* row1, uint32_t image_mask);
+/* With PRC_PEER_TRACE=1 in the environment at prc_peer_connect: milliseconds this context's stream spent in the device-side
+ * waits of the frames finished by the last prc_sync, per signal kind: [0] peers' shadow rows, [1] peers done shading the
+ * previous frame, [2] strips arriving in this rank's image, [3] consumers done with the previous image. Zeros otherwise. */
+int32_t prc_peer_wait_ms(prc_ctx* ctx, float out[4]);
 /* A caller-owned host image as the readback destination of prc_render_peer frames submitted WITHOUT PRC_FRAME_NO_READBACK:
  * [ptr, ptr + bytes) is page-locked and every such frame's strip (image rows of [row0,row1)) is DMA'd into it band by band
  * behind the shading kernels, complete after prc_sync. Meant for ONE shared-memory image mapped by every rank of a group:

@@ -59,11 +59,12 @@ def lib():
         L.prc_render_peer.argtypes = [vp, C.POINTER(A.prc_frame), C.c_uint32, vp, vp, vp, C.c_uint32]
         L.prc_set_exact_fma.argtypes = [vp, C.c_int32]
         L.prc_set_host_image.argtypes = [vp, vp, C.c_uint64]
+        L.prc_peer_wait_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]
         for name in ("prc_open", "prc_close", "prc_scene_upload", "prc_shadow_reset", "prc_render", "prc_read_gbuffer",
                      "prc_read_shadowmap", "prc_get_timings", "prc_device_image", "prc_device_shadowmap",
                      "prc_render_shadows", "prc_render_main", "prc_stream", "prc_sync", "prc_host_image", "prc_render_forward",
                      "prc_render_deferred", "prc_device_shadow_all", "prc_render_shadow_units", "prc_peer_export", "prc_peer_connect",
-                     "prc_peer_disconnect", "prc_render_peer", "prc_set_exact_fma", "prc_read_image", "prc_set_host_image"):
+                     "prc_peer_disconnect", "prc_render_peer", "prc_set_exact_fma", "prc_read_image", "prc_set_host_image", "prc_peer_wait_ms"):
             getattr(L, name).restype = C.c_int32
         if L.prc_abi_version() != A.PRC_ABI_VERSION:
             raise PolyredCudaError(A.PRC_ERR_INVALID, "ABI version mismatch")
@@ -235,6 +236,12 @@ class CudaBackend(Backend):
         li, r0, r1 = arrays
         self._check(self.L.prc_render_peer(self.h, C.byref(fd.struct), n, li.ctypes.data if n else None, r0.ctypes.data if n else None,
                                            r1.ctypes.data if n else None, image_mask))
+
+    def peer_wait_ms(self) -> dict:
+        """PRC_PEER_TRACE=1: where this rank's stream idled for its peers during the frames finished by the last sync()."""
+        out = (C.c_float * 4)()
+        self._check(self.L.prc_peer_wait_ms(self.h, C.byref(out)))
+        return dict(zip(("shadow_rows", "peers_shaded", "image_strips", "image_free"), (float(x) for x in out)))
 
     def render_peer(self, fd, units, image_mask: int = 1):
         """Submit one frame of the group without waiting (units: this rank's [(light, row0, row1)])."""

@@ -106,6 +106,11 @@ struct prc_ctx {
   bool ext_img_registered = false;
   // MSAA frames cut into strips (prc_render_peer only): the rank shades `msaa` extra supersampled rows on either side of the
   // rows it owns — all the downsample filter reaches — and resizes only its own output rows; no exchange is needed
+  // PRC_PEER_TRACE=1: CUDA-event brackets around the device-side waits, summed per signal kind by prc_sync (prc_peer_wait_ms):
+  // where a rank idles for its peers
+  bool peer_trace = false;
+  std::vector<prc_ctx::Span> peer_spans;
+  float peer_wait_ms[4] = {0, 0, 0, 0};
   bool allow_msaa_strips = false;
   int own_row0 = 0, own_row1 = 0;  // SCREEN rows (supersampled) whose output rows this context produces
 };
@@ -1241,6 +1246,13 @@ void peer_release(prc_ctx* ctx) {
 }
 
 int32_t peer_check(prc_ctx* ctx) {
+  for (int k = 0; k < 4; k++) ctx->peer_wait_ms[k] = 0;
+  for (auto& sp : ctx->peer_spans) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->evpool[sp.a], ctx->evpool[sp.b]) == cudaSuccess && sp.cls >= 0 && sp.cls < 4) ctx->peer_wait_ms[sp.cls] += ms;
+  }
+  ctx->peer_spans.clear();
+  (void)cudaGetLastError();
   unsigned int n = 0;
   CK(cudaMemcpy(&n, ctx->d_peer_err.p, 4, cudaMemcpyDeviceToHost));
   if (n) {
@@ -1254,8 +1266,19 @@ int32_t peer_check(prc_ctx* ctx) {
 inline void peer_wait(prc_ctx* ctx, uint32_t kind, uint32_t epoch, uint32_t mask) {
   const PeerTable& P = ctx->peers;
   if (!(mask & ~(1u << P.self))) return;
+  size_t a = 0;
+  if (ctx->peer_trace) {
+    while (ctx->evpool.size() < ctx->ev_used + 2) { cudaEvent_t e; cudaEventCreate(&e); ctx->evpool.push_back(e); }
+    a = ctx->ev_used;
+    ctx->ev_used += 2;
+    cudaEventRecord(ctx->evpool[a], ctx->stream);
+  }
   k_peer_wait<<<1, PRC_PEER_MAX, 0, ctx->stream>>>(P.signals[P.self], P.world, P.self, kind, epoch, mask, (unsigned int*)ctx->d_peer_err.p);
   ctx->launches++;
+  if (ctx->peer_trace) {
+    cudaEventRecord(ctx->evpool[a + 1], ctx->stream);
+    ctx->peer_spans.push_back({(int)kind, a, a + 1});
+  }
 }
 
 inline void peer_signal(prc_ctx* ctx, uint32_t kind, uint32_t epoch, uint32_t mask) {
@@ -1274,6 +1297,7 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
   if (ctx->pending_async == 0) {
     ctx->launches = 0;
     ctx->spans.clear();
+    ctx->peer_spans.clear();
     ctx->ev_used = 0;
     CK(cudaMemsetAsync(ctx->d_counters.p, 0, offsetof(Counters, n_valid), st));
   } else {
@@ -1443,6 +1467,8 @@ int32_t prc_peer_connect(prc_ctx* ctx, uint32_t rank, uint32_t world, const prc_
     T.signals[p] = (uint32_t*)((uint8_t*)base[2] + h.signals_off);
   }
   ctx->peers = T;
+  ctx->peer_trace = getenv("PRC_PEER_TRACE") != nullptr && atoi(getenv("PRC_PEER_TRACE")) != 0;
+  ctx->peer_spans.clear();
   for (uint32_t p = 0; p < PRC_PEER_MAX; p++) ctx->peer_image[p] = image[p];
   ctx->peer_opened = opened;
   ctx->peer_epoch = 0;
@@ -1523,8 +1549,15 @@ int32_t prc_render_peer(prc_ctx* ctx, const prc_frame* fr, uint32_t n, const uin
   if (ctx->ev_used > 8192) {
     // bound the timing-event pool without a host wait: keep the events, drop the spans of the oldest frames
     ctx->spans.clear();
+    ctx->peer_spans.clear();
     ctx->ev_used = 0;
   }
+  return PRC_OK;
+}
+
+int32_t prc_peer_wait_ms(prc_ctx* ctx, float out[4]) {
+  if (!ctx || !out) return PRC_ERR_INVALID;
+  for (int k = 0; k < 4; k++) out[k] = ctx->peer_wait_ms[k];
   return PRC_OK;
 }
 
