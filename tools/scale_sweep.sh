@@ -18,5 +18,10 @@ for n in $1; do
     tag=$n; [ "$mode" = "peer" ] && tag=${n}_peer
     timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29550 + n)) bench.py --gpus $n --steps $STEPS --warmup 5 --no-cpu-baseline --mgpu $mode > $OUT/scale_$tag.json 2> $OUT/scale_$tag.err
     python tools/bench_brief.py "N=$n/$mode" < $OUT/scale_$tag.json || tail -5 $OUT/scale_$tag.err
+    if [ "$mode" = "peer" ]; then
+      # a second, traced run (not a bench value): where rank 0 idles for its peers, and the balance rounds
+      PRC_PEER_TRACE=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29570 + n)) bench.py --gpus $n --steps $STEPS --warmup 5 --no-cpu-baseline --mgpu peer > $OUT/scale_${tag}_traced.json 2> $OUT/scale_${tag}_traced.err
+      python -c "import json,sys; d=json.load(open('$OUT/scale_${tag}_traced.json')); print('  traced:', round(d['ms_per_step'],4), 'ms; waits', d.get('peer_wait_ms_per_step_rank0'), '; strips', d['config'].get('strip_rows'), '; last balance round', (d.get('balance_rounds') or [None])[-1])" || true
+    fi
   done
 done
