@@ -89,6 +89,9 @@ struct prc_ctx {
   prc_timings tm{};
   unsigned long long launches = 0;
   bool gbuffer_valid = false, uniforms_valid = false, frame_uploaded = false;
+  // NaN mode (bug-list 8, see nan_first in prc_kernels.cuh): entered, with a re-render of the frame, when a camera pass reported a
+  // NaN-depth fragment; left at the next scene upload. d_keys then holds a second [H][W] u64 plane, the per-pixel first fragment.
+  bool nan_mode = false;
   DevFrame h_frame{};
   bool capturing = false;
   uint32_t n_lights_alloc = 0;
@@ -239,15 +242,24 @@ int32_t raster_pass(prc_ctx* ctx, const DevFrame& F, const GeomViews& Vin) {
 #else
   if (ctx->S.n_tris) {
     KTimer kt(ctx, SHADOW ? PRC_K_GEOM_SHADOW : PRC_K_GEOM_CAMERA);
-    k_geom_raster<E, SHADOW><<<cdiv(ctx->S.n_tris, PRC_GEOM_THREADS), PRC_GEOM_THREADS, 0, st>>>(ctx->S, F, V, keys, large, ctx->large_cap, clipq, ctx->clip_cap,
-                                                                                                     cnt, (const DevFrame*)fb.p);
+    const unsigned int grid = cdiv(ctx->S.n_tris, PRC_GEOM_THREADS);
+    bool done = false;
+    if constexpr (!SHADOW) {
+      if (ctx->nan_mode) {
+        k_geom_raster<E, false, true><<<grid, PRC_GEOM_THREADS, 0, st>>>(ctx->S, F, V, keys, large, ctx->large_cap, clipq, ctx->clip_cap, cnt, (const DevFrame*)fb.p);
+        done = true;
+      }
+    }
+    if (!done)
+      k_geom_raster<E, SHADOW><<<grid, PRC_GEOM_THREADS, 0, st>>>(ctx->S, F, V, keys, large, ctx->large_cap, clipq, ctx->clip_cap, cnt, (const DevFrame*)fb.p);
     ctx->launches++;
   }
 #endif
   if (!SHADOW) {
     // fixed grid, reads its work count on the device (grid-stride loop)
     KTimer kt(ctx, PRC_K_CLIP);
-    k_clip_raster<E><<<148 * 4, 128, 0, st>>>(ctx->S, F, clipq, keys, large, ctx->large_cap, cnt);
+    if (ctx->nan_mode) k_clip_raster<E, true><<<148 * 4, 128, 0, st>>>(ctx->S, F, clipq, keys, large, ctx->large_cap, cnt);
+    else k_clip_raster<E><<<148 * 4, 128, 0, st>>>(ctx->S, F, clipq, keys, large, ctx->large_cap, cnt);
     ctx->launches++;
   }
   CK(cudaGetLastError());
@@ -280,6 +292,10 @@ int32_t flush_large(prc_ctx* ctx, const DevFrame& F) {
   }
   {
     KTimer kt(ctx, PRC_K_TILE_CAMERA);
+    if (ctx->nan_mode)
+      k_tile_raster<E, true><<<148 * 8, PRC_TILE * PRC_TILE, 0, st>>>(large, tile_start, (unsigned int*)ctx->d_bins.p, tiles_x, n_tiles, F.W, F.H,
+                                                                       (unsigned long long*)ctx->d_keys.p, (const TileTargets*)ctx->d_targets.p, cnt, active_hdr + 4, active_hdr);
+    else
     k_tile_raster<E><<<148 * 8, PRC_TILE * PRC_TILE, 0, st>>>(large, tile_start, (unsigned int*)ctx->d_bins.p, tiles_x, n_tiles, F.W, F.H,
                                                                (unsigned long long*)ctx->d_keys.p, (const TileTargets*)ctx->d_targets.p, cnt, active_hdr + 4, active_hdr);
     ctx->launches++;
@@ -318,7 +334,7 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
     ctx->W = W; ctx->H = H; ctx->n_lights_alloc = fr->n_lights;
     ctx->gbuffer_valid = false;
   }
-  ENSURE(ctx->d_keys, npx * 8);
+  ENSURE(ctx->d_keys, npx * 8 * (ctx->nan_mode ? 2 : 1));
   ENSURE(ctx->d_ga, npx * 16); ENSURE(ctx->d_gb, npx * 16); ENSURE(ctx->d_gc, npx * 16); ENSURE(ctx->d_gd, npx * 16);
   if (ctx->any_ao) ENSURE(ctx->d_ao, npx * 4);
   // slack: the multi-GPU image all-gather uses equal, padded strips. Whole 2 MiB pages: the buffer can be exported through CUDA
@@ -439,6 +455,7 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
   const int halo = ctx->any_ao ? 100 : 0;
   F.rr0 = std::max(0, (int)F.row0 - halo);
   F.rr1 = std::min(H, (int)F.row1 + halo);
+  if (ctx->any_ao && F.rr0 <= 100) F.rr0 = 0;  // rows [0, 100) are needed for pixel (0,0)'s AO anyway (see do_main): keep one contiguous range
   F.flags = fr->flags;
   F.n_lights = fr->n_lights; F.n_ambient = fr->n_ambient;
   F.background = fr->background_rgba;
@@ -567,25 +584,52 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, int phases
   const bool es = ctx->exact_shade;  // exact FMA in the shading-only arithmetic too (PRC_FMA=exact)
 
   if (phases & 1) {
+    // Row ranges to rasterise and resolve: the strip (widened by the AO halo) and, for an upper strip of a frame with an AO
+    // material, rows [0, 100) as well — the colour of every uncovered pixel comes from shading pixel (0,0) (bug-list 3), whose
+    // AO rays read the depths of up to 99 rows / columns around it.
+    std::vector<std::pair<int, int>> ranges;
+    ranges.push_back({F.rr0, F.rr1});
+    if (ctx->any_ao && F.rr0 > 0) ranges.push_back({0, std::min(100, F.rr0)});
+    unsigned long long* first = (unsigned long long*)ctx->d_keys.p + (size_t)F.W * F.H;  // NaN mode: first fragment per pixel
     // clear the visibility keys of the rasterised rows (+ pixel (0,0))
-    CK(cudaMemsetAsync((unsigned long long*)ctx->d_keys.p + (size_t)F.rr0 * F.W, 0, (size_t)(F.rr1 - F.rr0) * F.W * 8, st));
-    if (F.rr0 > 0) CK(cudaMemsetAsync(ctx->d_keys.p, 0, 8, st));
-    GeomViews V0{};
-    V0.n = 1;
-    int32_t r = raster_pass<E, false>(ctx, F, V0);
+    for (const auto& rg : ranges) {
+      CK(cudaMemsetAsync((unsigned long long*)ctx->d_keys.p + (size_t)rg.first * F.W, 0, (size_t)(rg.second - rg.first) * F.W * 8, st));
+      if (ctx->nan_mode) CK(cudaMemsetAsync(first + (size_t)rg.first * F.W, 0xFF, (size_t)(rg.second - rg.first) * F.W * 8, st));
+    }
+    if (F.rr0 > 0 && ranges.size() == 1) {
+      CK(cudaMemsetAsync(ctx->d_keys.p, 0, 8, st));
+      if (ctx->nan_mode) CK(cudaMemsetAsync(first, 0xFF, 8, st));
+    }
+    for (const auto& rg : ranges) {
+      DevFrame Fr = F;
+      Fr.rr0 = rg.first; Fr.rr1 = rg.second;
+      GeomViews V0{};
+      V0.n = 1;
+      int32_t r = raster_pass<E, false>(ctx, Fr, V0);
+      if (r != PRC_OK) return r;
+    }
+    int32_t r = flush_large<E>(ctx, F);  // also rasterises what the shadow passes of this frame queued
     if (r != PRC_OK) return r;
-    r = flush_large<E>(ctx, F);  // also rasterises what the shadow passes of this frame queued
-    if (r != PRC_OK) return r;
+    if (ctx->nan_mode)
+      for (const auto& rg : ranges) {
+        const size_t i0 = (size_t)rg.first * F.W, i1 = (size_t)rg.second * F.W;
+        k_nan_fix<<<cdiv(i1 - i0, 256), 256, 0, st>>>((unsigned long long*)ctx->d_keys.p, first, i0, i1, (F.rr0 > 0 && ranges.size() == 1) ? 1 : 0);
+        ctx->launches++;
+      }
     CK(cudaEventRecordWithFlags(ctx->ev[2], st, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
     KTimer kt(ctx, PRC_K_RESOLVE);
     if (!fused) {
-      const dim3 rg((F.W + 31) / 32, (F.rr1 - F.rr0 + 3) / 4);
-      if (es) k_resolve<E, E><<<rg, 128, 0, st>>>(ctx->S, F, keys, G);
-      else k_resolve<E, false><<<rg, 128, 0, st>>>(ctx->S, F, keys, G);
-      ctx->launches++;
+      for (const auto& rg : ranges) {
+        DevFrame Fr = F;
+        Fr.rr0 = rg.first; Fr.rr1 = rg.second;
+        const dim3 rgd((F.W + 31) / 32, (Fr.rr1 - Fr.rr0 + 3) / 4);
+        if (es) k_resolve<E, E><<<rgd, 128, 0, st>>>(ctx->S, Fr, keys, G);
+        else k_resolve<E, false><<<rgd, 128, 0, st>>>(ctx->S, Fr, keys, G);
+        ctx->launches++;
+      }
     }
     // k_shade_special resolves pixel (0,0) itself; only a G-buffer readback needs it STORED when it lies outside the rasterised rows
-    if (F.rr0 > 0 && (fr->flags & PRC_FRAME_KEEP_GBUFFER)) {
+    if (F.rr0 > 0 && ranges.size() == 1 && (fr->flags & PRC_FRAME_KEEP_GBUFFER)) {
       if (es) k_resolve00<E, E><<<1, 1, 0, st>>>(ctx->S, F, keys, G);
       else k_resolve00<E, false><<<1, 1, 0, st>>>(ctx->S, F, keys, G);
       ctx->launches++;
@@ -718,7 +762,16 @@ int32_t finish_timings(prc_ctx* ctx) {
   ctx->tm.shadow_ms = a; ctx->tm.forward_ms = b; ctx->tm.shade_ms = c; ctx->tm.total_ms = d;
   ctx->tm.n_valid_tris = ctx->n_valid;
   CK(cudaMemcpy(ctx->h_counters, ctx->d_counters.p, sizeof(Counters), cudaMemcpyDeviceToHost));
-  ctx->tm.n_nan_frags = ctx->h_counters->n_nan;
+  ctx->tm.n_nan_frags = ctx->h_counters->n_nan + ctx->h_counters->n_nan_shadow;
+  if (ctx->h_counters->n_nan && !ctx->nan_mode && !getenv("PRC_NO_NAN_MODE")) {
+    // a NaN-depth fragment in the camera pass: whether it shows depends on the draw order (bug-list 8) — render the frame
+    // again with the first-fragment plane (the key buffer is reallocated by the next build_frame)
+    ctx->nan_mode = true;
+    ENSURE(ctx->d_keys, (size_t)ctx->W * ctx->H * 16);  // (the stream is idle: the frame is re-rendered from its key clear on)
+    ctx->spans.clear();
+    ctx->ev_used = 0;
+    return PRC_RETRY;
+  }
   if (ctx->h_counters->large_overflow) {
     ctx->spans.clear();
     ctx->ev_used = 0;
@@ -871,6 +924,7 @@ int32_t prc_scene_upload(prc_ctx* ctx, const prc_scene* s) {
   ENSURE(ctx->d_large, (size_t)ctx->large_cap * sizeof(LargeRec));
   ENSURE(ctx->d_clipq, (size_t)ctx->clip_cap * 4);
   ctx->any_ao = false;
+  ctx->nan_mode = false;
   for (uint32_t i = 0; i < s->n_materials; i++)
     if (!(s->materials[i].flags & PRC_MAT_NIL) && (s->materials[i].flags & PRC_MAT_AMBIENT_OCCLUSION)) ctx->any_ao = true;
   // Triangle.IsValid + object index, once per scene

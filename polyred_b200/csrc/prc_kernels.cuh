@@ -91,7 +91,8 @@ struct Counters {
   // per frame
   unsigned int large_overflow;  // a queue was too small: the frame is invalid and is re-rendered after growing
   unsigned int max_bins;        // largest n_bin_total of the frame (to size the bin array)
-  unsigned long long n_nan;
+  unsigned long long n_nan;         // NaN-depth fragments of the camera pass (bug-list 8; resolved by the first-fragment rule in NaN mode)
+  unsigned long long n_nan_shadow;  // NaN-depth fragments of the shadow passes (counted and dropped: the one stated deviation)
   unsigned long long stat_large, stat_clip, stat_bins;
   // per scene
   unsigned long long n_valid;
@@ -227,9 +228,19 @@ __device__ __forceinline__ V4 clip_pos(const ScreenTri& t, const float b[3]) {
 // ---------------------------------------------------------------------------------------------
 // rasterisation of one screen triangle's pixel box by the calling thread (clipped fans, pixel (0,0), queue-overflow fallback)
 // ---------------------------------------------------------------------------------------------
-template <bool E, bool SHADOW>
+// NaN mode (NM, camera pass only; bug-list 8, buffer/buffer.go:230,279): DepthTest passes for ANY depth when the pixel is
+// empty and `depth > NaN` is false for every later fragment, so a NaN-depth fragment that is the FIRST fragment of its pixel
+// in draw order stays for good, and a NaN-depth fragment that arrives later is dropped. The order-independent form: every
+// fragment also does atomicMin(first[pixel], seq << 1 | isnan(depth)); a pixel whose minimum has the NaN bit set shows that
+// fragment (k_nan_fix rewrites its key before the resolve). A context enters NaN mode — and re-renders the frame — when a
+// frame reported a NaN-depth fragment; frames without one (every benchmark and golden scene) never pay for it.
+__device__ __forceinline__ void nan_first(unsigned long long* first, size_t idx, uint32_t seq, float z) {
+  atomicMin(&first[idx], ((unsigned long long)seq << 1) | (isnan(z) ? 1ull : 0ull));
+}
+
+template <bool E, bool SHADOW, bool NM = false>
 __device__ __forceinline__ void raster_one(const BarySetup& bs, const V4& p1, const V4& p2, const V4& p3, int x0, int y0, int x1, int y1, uint32_t seq, int W,
-                                           unsigned long long* __restrict__ keys, float* __restrict__ smap, Counters* cnt) {
+                                           unsigned long long* __restrict__ keys, float* __restrict__ smap, Counters* cnt, unsigned long long* first = nullptr) {
   for (int y = y0; y <= y1; y++) {
     float py = (float)y + 0.5f;
     for (int x = x0; x <= x1; x++) {
@@ -238,8 +249,9 @@ __device__ __forceinline__ void raster_one(const BarySetup& bs, const V4& p1, co
       bary_eval<E>(bs, px, py, w1, w2, w3);
       if (w1 < -PRC_EPS || w2 < -PRC_EPS || w3 < -PRC_EPS) continue;
       float z = w1 * p1.z + w2 * p2.z + w3 * p3.z;
-      if (isnan(z)) { atomicAdd(&cnt->n_nan, 1ULL); continue; }
       size_t idx = (size_t)y * W + x;
+      if (NM && !SHADOW) nan_first(first, idx, seq, z);
+      if (isnan(z)) { atomicAdd(SHADOW ? &cnt->n_nan_shadow : &cnt->n_nan, 1ULL); continue; }
       if (SHADOW) {
         // shadowDepthTest (shadow.go:221-228): store iff !(z <= stored); stored starts at 0 and only grows,
         // so only z > 0 can ever be stored and positive floats order like their int bits.
@@ -254,21 +266,22 @@ __device__ __forceinline__ void raster_one(const BarySetup& bs, const V4& p1, co
 
 // pixel (0,0) is needed on every rank (uncovered pixels shade G(0,0), raster.go:326): when the raster rows do
 // not include row 0 it is evaluated separately.
-template <bool E>
-__device__ __forceinline__ void raster_pixel00(const V4& p1, const V4& p2, const V4& p3, uint32_t seq, unsigned long long* keys, Counters* cnt) {
+template <bool E, bool NM = false>
+__device__ __forceinline__ void raster_pixel00(const V4& p1, const V4& p2, const V4& p3, uint32_t seq, unsigned long long* keys, Counters* cnt, unsigned long long* first = nullptr) {
   int x0, y0, x1, y1;
   float a, b, c, d;
   if (!pixel_bbox(p1, p2, p3, 1, 0, 1, x0, y0, x1, y1, a, b, c, d)) return;
   BarySetup bs = bary_setup<E>(p1.x, p1.y, p2.x, p2.y, p3.x, p3.y);
-  raster_one<E, false>(bs, p1, p2, p3, 0, 0, 0, 0, seq, 1 << 30, keys, nullptr, cnt);
+  raster_one<E, false, NM>(bs, p1, p2, p3, 0, 0, 0, 0, seq, 1 << 30, keys, nullptr, cnt, first);
 }
 
-template <bool E, bool SHADOW>
+template <bool E, bool SHADOW, bool NM = false>
 __device__ __forceinline__ void emit_tri(const V4& p1, const V4& p2, const V4& p3, uint32_t seq, const DevFrame& F, int r0, int r1,
-                                         unsigned long long* keys, float* smap, LargeRec* large, unsigned int large_cap, uint32_t target, Counters* cnt) {
+                                         unsigned long long* keys, float* smap, LargeRec* large, unsigned int large_cap, uint32_t target, Counters* cnt,
+                                         unsigned long long* first = nullptr) {
   int x0, y0, x1, y1;
   float mnx, mny, mxx, mxy;
-  if (!SHADOW && r0 > 0) raster_pixel00<E>(p1, p2, p3, seq, keys, cnt);
+  if (!SHADOW && r0 > 0) raster_pixel00<E, NM>(p1, p2, p3, seq, keys, cnt, first);
   if (!pixel_bbox(p1, p2, p3, F.W, r0, r1, x0, y0, x1, y1, mnx, mny, mxx, mxy)) return;
   const BarySetup bs = bary_setup<E>(p1.x, p1.y, p2.x, p2.y, p3.x, p3.y);
   // exact-safe shrink of the reference's AABB+-1 loop (prc_prune.h)
@@ -279,7 +292,7 @@ __device__ __forceinline__ void emit_tri(const V4& p1, const V4& p2, const V4& p
   }
   int area = (x1 - x0 + 1) * (y1 - y0 + 1);
   if (area <= PRC_SMALL_MAX_PIXELS) {
-    raster_one<E, SHADOW>(bs, p1, p2, p3, x0, y0, x1, y1, seq, F.W, keys, smap, cnt);
+    raster_one<E, SHADOW, NM>(bs, p1, p2, p3, x0, y0, x1, y1, seq, F.W, keys, smap, cnt, first);
   } else {
     unsigned int slot = warp_push(&cnt->n_large);
     if (slot >= large_cap) { atomicExch(&cnt->large_overflow, 1u); return; }
@@ -294,7 +307,7 @@ __device__ __forceinline__ void emit_tri(const V4& p1, const V4& p2, const V4& p
 #ifndef PRC_GEOM_MIN_BLOCKS
 #define PRC_GEOM_MIN_BLOCKS 8  // 32 registers, full occupancy: measured 1.29 ms/frame vs 1.34 (6 CTAs, 40 regs) and 1.40 (5 CTAs, 48 regs); more resident CTAs hide the phase barriers
 #endif
-template <bool E, bool SHADOW>
+template <bool E, bool SHADOW, bool NM = false>
 // NOTE: takes the frame through a pointer to a DEVICE-RESIDENT copy. Passing the kernel-parameter struct by
 // reference to a non-inlined function makes every thread copy it to local memory at kernel entry (measured:
 // 1.76 GB of DRAM writes per launch).
@@ -314,8 +327,8 @@ __device__ __noinline__ void geom_generic(const DevFrame* __restrict__ Fg, const
     else atomicExch(&cnt->large_overflow, 1u);
     return;
   }
-  const int r0 = SHADOW ? vr0 : F.rr0, r1 = SHADOW ? vr1 : F.rr1;
-  emit_tri<E, SHADOW>(st.p1, st.p2, st.p3, tri * 8u, F, r0, r1, keys, smap, large, large_cap, target, cnt);
+  const int r0 = vr0, r1 = vr1;  // (the device-resident frame copy *Fg holds the strip's rows; a launch may cover another range)
+  emit_tri<E, SHADOW, NM>(st.p1, st.p2, st.p3, tri * 8u, F, r0, r1, keys, smap, large, large_cap, target, cnt, NM ? keys + (size_t)F.W * F.H : nullptr);
 }
 
 // Apply(Viewport).Pos() for the standard viewport matrix [a 0 0 b; 0 c 0 d; 0 0 1 0; 0 0 0 1] and a vertex whose
@@ -363,10 +376,10 @@ struct GeomViews {
 // Several shadow views share the vertex fetch; the camera pass is the same kernel with one view.
 // ---------------------------------------------------------------------------------------------
 #define PRC_QCAP 2048
-template <bool E, bool SHADOW>
+template <bool E, bool SHADOW, bool NM = false>
 __device__ __forceinline__ void small_pixel(const float p1x, const float p1y, const float p1z, const float p2x, const float p2y, const float p2z,
                                             const float p3x, const float p3y, const float p3z, const int x, const int y, const uint32_t seq, const int W,
-                                            unsigned long long* keys, float* smap, Counters* cnt) {
+                                            unsigned long long* keys, float* smap, Counters* cnt, unsigned long long* first = nullptr) {
   const BarySetup bs = bary_setup<E>(p1x, p1y, p2x, p2y, p3x, p3y);
   const float thr = 2e-7f * fabsf(bs.Sabc);
   const uint32_t sg = __float_as_uint(bs.Sabc);
@@ -391,8 +404,9 @@ __device__ __forceinline__ void small_pixel(const float p1x, const float p1y, co
   const float w1 = __fdiv_rn(Sbcp, bs.Sabc), w2 = __fdiv_rn(Sapc, bs.Sabc), w3 = __fdiv_rn(Sabp, bs.Sabc);
   if (w1 < -PRC_EPS || w2 < -PRC_EPS || w3 < -PRC_EPS) return;
   const float z = w1 * p1z + w2 * p2z + w3 * p3z;
-  if (isnan(z)) { atomicAdd(&cnt->n_nan, 1ULL); return; }
   const size_t idx = (size_t)y * W + x;
+  if (NM && !SHADOW) nan_first(first, idx, seq, z);
+  if (isnan(z)) { atomicAdd(SHADOW ? &cnt->n_nan_shadow : &cnt->n_nan, 1ULL); return; }
   // fire-and-forget reductions (RED.MAX): no pre-test load, so nothing waits on memory
   if (SHADOW) {
     if (z > 0.0f) atomicMax((int*)&smap[idx], __float_as_int(z));
@@ -431,7 +445,7 @@ __device__ __forceinline__ void geom_vertices(const DevScene& S, const DevFrame&
 }
 
 // phase 2 for one triangle
-template <bool E, bool SHADOW>
+template <bool E, bool SHADOW, bool NM = false>
 __device__ __forceinline__ void geom_classify(const DevScene& S, const DevFrame& F, GeomSmem& sm, const int buf, const int qsel, const uint32_t li, const unsigned int tri,
                                               const float* __restrict__ trans_base, const int trans_stride,
                                               unsigned long long* keys, float* smap, LargeRec* large, unsigned int large_cap, unsigned int* clipq,
@@ -442,7 +456,7 @@ __device__ __forceinline__ void geom_classify(const DevScene& S, const DevFrame&
   const float fin = p1x + p2x + p3x;  // NaN iff a vertex was flagged in phase 1 (finite coordinates are < 3e29: no overflow)
   if (fin != fin) {
     const uint32_t obj = __ldg(S.meta + tri) & 0x00FFFFFFu;
-    geom_generic<E, SHADOW>(Fg, trans_base + (size_t)obj * trans_stride, S.pos, tri, keys, smap, large, large_cap, target, clipq, clip_cap, cnt, vr0, vr1);
+    geom_generic<E, SHADOW, NM>(Fg, trans_base + (size_t)obj * trans_stride, S.pos, tri, keys, smap, large, large_cap, target, clipq, clip_cap, cnt, vr0, vr1);
     return;
   }
   const float p1y = sy[i0], p2y = sy[i1], p3y = sy[i2];
@@ -474,7 +488,7 @@ __device__ __forceinline__ void geom_classify(const DevScene& S, const DevFrame&
   }
   const int r0 = SHADOW ? vr0 : F.rr0, r1 = SHADOW ? vr1 : F.rr1;
   const uint32_t seq = tri * 8u;
-  if (!SHADOW && r0 > 0) raster_pixel00<E>(V4{p1x, p1y, p1z, 1.0f}, V4{p2x, p2y, p2z, 1.0f}, V4{p3x, p3y, p3z, 1.0f}, seq, keys, cnt);
+  if (!SHADOW && r0 > 0) raster_pixel00<E, NM>(V4{p1x, p1y, p1z, 1.0f}, V4{p2x, p2y, p2z, 1.0f}, V4{p3x, p3y, p3z, 1.0f}, seq, keys, cnt, NM ? keys + (size_t)F.W * F.H : nullptr);
   int x0, x1, y0, y1;
   if (prune_ok(mnx, mny, mxx, mxy, Sabc)) {
     // exact-safe shrink of the AABB+-1 loop (prc_prune.h). The pruned box [ceil(min-.5-M), floor(max-.5+M)] always lies
@@ -543,13 +557,14 @@ __device__ __forceinline__ void geom_classify(const DevScene& S, const DevFrame&
   } else {
     // queue full (many multi-pixel triangles in one chunk): this triangle's pixels in-thread
     for (int y = y0; y <= y1; y++)
-      for (int x = x0; x <= x1; x++) small_pixel<E, SHADOW>(p1x, p1y, p1z, p2x, p2y, p2z, p3x, p3y, p3z, x, y, seq, F.W, keys, smap, cnt);
+      for (int x = x0; x <= x1; x++)
+        small_pixel<E, SHADOW, NM>(p1x, p1y, p1z, p2x, p2y, p2z, p3x, p3y, p3z, x, y, seq, F.W, keys, smap, cnt, NM ? keys + (size_t)F.W * F.H : nullptr);
   }
 }
 
 // __grid_constant__: the per-view arrays are indexed with a run-time view number; without it the whole parameter
 // struct is copied to local memory by every thread (ncu: 11 % of the kernel's instructions, STL at entry).
-template <bool E, bool SHADOW>
+template <bool E, bool SHADOW, bool NM = false>
 __global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_raster(const __grid_constant__ DevScene S, const __grid_constant__ DevFrame F,
                                                                      const __grid_constant__ GeomViews V,
                                                                      unsigned long long* keys, LargeRec* large, unsigned int large_cap,
@@ -595,8 +610,8 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_
     float* smap = SHADOW ? V.smap[v] : nullptr;
     // ---- phase 2: one thread per triangle
     if (li != 0xFFFFFFFFu)
-      geom_classify<E, SHADOW>(S, F, sm, buf, buf, li, tri, trans_base, trans_stride, keys, smap, large, large_cap, clipq, clip_cap, cnt, Fg,
-                               SHADOW ? V.target[v] : 0u, SHADOW ? V.r0[v] : 0, SHADOW ? V.r1[v] : 0);
+      geom_classify<E, SHADOW, NM>(S, F, sm, buf, buf, li, tri, trans_base, trans_stride, keys, smap, large, large_cap, clipq, clip_cap, cnt, Fg,
+                               SHADOW ? V.target[v] : 0u, SHADOW ? V.r0[v] : F.rr0, SHADOW ? V.r1[v] : F.rr1);
     __syncthreads();
     // ---- phase 3 of this view (one thread per candidate pixel) overlapped with phase 1 of the next view (other buffer)
     const unsigned int nq = sm.qv[buf];
@@ -613,9 +628,9 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_
         const uint32_t ti = sm.idx[t], box = sm.box[t];
         const uint32_t i0 = ti & 1023u, i1 = (ti >> 10) & 1023u, i2 = (ti >> 20) & 1023u;
         const uint32_t bw = (box >> 28) + 1u, dy = (j * c_recip256[bw]) >> 8, dx = j - dy * bw;
-        small_pixel<E, SHADOW>(sx[i0], sy[i0], sz[i0], sx[i1], sy[i1], sz[i1], sx[i2], sy[i2], sz[i2],
-                               (int)((box & 0x3FFFu) + dx), (int)(((box >> 14) & 0x3FFFu) + dy),
-                               (chunk * PRC_GEOM_THREADS + t) * 8u, F.W, keys, smap, cnt);
+        small_pixel<E, SHADOW, NM>(sx[i0], sy[i0], sz[i0], sx[i1], sy[i1], sz[i1], sx[i2], sy[i2], sz[i2],
+                                   (int)((box & 0x3FFFu) + dx), (int)(((box >> 14) & 0x3FFFu) + dy),
+                                   (chunk * PRC_GEOM_THREADS + t) * 8u, F.W, keys, smap, cnt, NM ? keys + (size_t)F.W * F.H : nullptr);
       }
     }
     if (vn < 0) break;
@@ -640,7 +655,7 @@ __global__ void k_chunk_compact(const __grid_constant__ GeomViews V, int n_views
 #endif
 
 // K2: triangles straddling the viewport: clip, fan, emit (raster.go:438-443)
-template <bool E>
+template <bool E, bool NM = false>
 __global__ void k_clip_raster(DevScene S, DevFrame F, const unsigned int* __restrict__ clipq, unsigned long long* keys, LargeRec* large,
                               unsigned int large_cap, Counters* cnt) {
   const unsigned int n = cnt->n_clip;  // final: written by the preceding kernel on the same stream
@@ -663,7 +678,7 @@ __global__ void k_clip_raster(DevScene S, DevFrame F, const unsigned int* __rest
     clip_bary<E>(st, poly[k - 1], b1);
     clip_bary<E>(st, poly[k], b2);
     V4 q1 = clip_pos(st, b1), q2 = clip_pos(st, b2);
-    emit_tri<E, false>(q0, q1, q2, tri * 8u + (uint32_t)(k - 1), F, F.rr0, F.rr1, keys, nullptr, large, large_cap, 0u, cnt);
+    emit_tri<E, false, NM>(q0, q1, q2, tri * 8u + (uint32_t)(k - 1), F, F.rr0, F.rr1, keys, nullptr, large, large_cap, 0u, cnt, NM ? keys + (size_t)F.W * F.H : nullptr);
   }
   }
 }
@@ -779,7 +794,7 @@ struct TileRec {
   short bx0, by0, bx1, by1;
 };
 struct TileTargets { float* smap[33]; };  // [1 + k] = shadow map of the k-th casting light
-template <bool E>
+template <bool E, bool NM = false>
 __global__ void __launch_bounds__(PRC_TILE * PRC_TILE) k_tile_raster(const LargeRec* __restrict__ large, const unsigned int* __restrict__ tile_start,
                                                                       const unsigned int* __restrict__ bins, int tiles_x, int n_tiles, int W, int H,
                                                                       unsigned long long* keys, const TileTargets* __restrict__ targets, Counters* cnt,
@@ -796,7 +811,7 @@ __global__ void __launch_bounds__(PRC_TILE * PRC_TILE) k_tile_raster(const Large
     const float px = (float)x + 0.5f, py = (float)y + 0.5f;
     const bool live = x < W && y < H;
     const bool shadow = target != 0;
-    unsigned long long best = 0;
+    unsigned long long best = 0, firstv = ~0ull;
     float bestz = 0.0f;
     unsigned long long nan_local = 0;
     for (unsigned int base = b; base < e; base += 128) {
@@ -819,6 +834,7 @@ __global__ void __launch_bounds__(PRC_TILE * PRC_TILE) k_tile_raster(const Large
         bary_eval<E>(t.bs, px, py, w1, w2, w3);
         if (w1 < -PRC_EPS || w2 < -PRC_EPS || w3 < -PRC_EPS) continue;
         float z = w1 * t.z1 + w2 * t.z2 + w3 * t.z3;
+        if (NM && !shadow) firstv = min(firstv, ((unsigned long long)t.seq << 1) | (isnan(z) ? 1ull : 0ull));
         if (isnan(z)) { nan_local++; continue; }
         if (shadow) {
           if (z > bestz) bestz = z;
@@ -828,15 +844,29 @@ __global__ void __launch_bounds__(PRC_TILE * PRC_TILE) k_tile_raster(const Large
         }
       }
     }
-    if (nan_local) atomicAdd(&cnt->n_nan, nan_local);
+    if (nan_local) atomicAdd(shadow ? &cnt->n_nan_shadow : &cnt->n_nan, nan_local);
     if (!live) continue;
     const size_t idx = (size_t)y * W + x;
+    if (NM && firstv != ~0ull) atomicMin(&keys[(size_t)W * H + idx], firstv);
     if (shadow) {
       if (bestz > 0.0f) atomicMax((int*)&targets->smap[target][idx], __float_as_int(bestz));
     } else {
       if (best) atomicMax(&keys[idx], best);
     }
   }
+}
+
+// NaN mode: a pixel whose first fragment in draw order has a NaN depth shows that fragment (see nan_first). The key's depth
+// half is not read by the resolve (it recomputes the fragment from the sequence number), it only has to be non-zero.
+__global__ void k_nan_fix(unsigned long long* keys, const unsigned long long* __restrict__ first, size_t i0, size_t i1, int with00) {
+  const size_t i = i0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (with00 && blockIdx.x == 0 && threadIdx.x == 0) {
+    const unsigned long long v = first[0];
+    if (v != ~0ull && (v & 1ull)) keys[0] = (1ull << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(v >> 1));
+  }
+  if (i >= i1) return;
+  const unsigned long long v = first[i];
+  if (v != ~0ull && (v & 1ull)) keys[i] = (1ull << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(v >> 1));
 }
 
 // ---------------------------------------------------------------------------------------------

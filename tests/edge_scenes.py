@@ -62,10 +62,10 @@ def edge_scenes():
     out["sliver_collinear"] = (_lights(scene.Scene(_tri_geo([[[0, 0, 0], [1, 1, 0], [2, 2, 0]]], material.BlinnPhong(texture=_tex())))), _cam(), 64, 40,
                                dict(background=(1, 2, 3, 255)))
     # A triangle in the plane x = 0 seen edge-on by a camera in that plane: all three screen x are equal, Sabc is exactly 0,
-    # the barycentrics of the pixel centres on that line are 0/0 = NaN and pass the `< -eps` test, and the NaN depth wins over an empty pixel (bug-list 8). The CUDA path
-    # counts such fragments (prc_timings.n_nan_frags) and drops them — the one documented deviation (DESIGN.md 1, row a-9').
+    # the barycentrics of the pixel centres on that line are 0/0 = NaN and pass the `< -eps` test, and the NaN depth wins over an empty pixel (bug-list 8): reproduced by
+    # the CUDA path's NaN mode (prc_kernels.cuh nan_first / k_nan_fix).
     out["nan_depth_degenerate"] = (_lights(scene.Scene(_tri_geo([[[0, -0.5, 0], [0, 0.5, -1], [0, 0.2, 1]]], material.BlinnPhong(texture=_tex())))), _cam(aspect=65 / 40), 65, 40,
-                                   dict(background=(1, 2, 3, 255), known_deviation="nan_depth"))  # odd width: x = 32.5 is a pixel centre
+                                   dict(background=(1, 2, 3, 255), nan_depth=True))  # odd width: x = 32.5 is a pixel centre
     # negative material id: vertex colours pass through shade() untouched (raster.go:330-333), persp-correct interpolation
     col = np.array([[0xFF0000FF, 0xFF00FF00, 0xFFFF0000], [0xFF00FFFF, 0x80FFFFFF, 0xFF102030]], np.uint32)
     vc = [[[-1, -0.6, 0], [1, -0.7, -1.5], [0.1, 0.9, 0.4]], [[-0.9, 0.8, -0.5], [-0.2, 0.2, 0.8], [-1.2, -0.1, 0.2]]]

@@ -50,8 +50,8 @@ def _group(s, cam, w, h, devices):
     return rs, fds, mine
 
 
-def _run(devices, frames=3, size=(480, 272)):
-    s, cam, w, h = _scene(*size)
+def _run(devices, frames=3, size=(480, 272), scene=None):
+    s, cam, w, h = _scene(*size) if scene is None else (*scene, *size)
     ref = render.NewRenderer(*_opts(s, cam, w, h), render.CUDA(devices[0])).Render().copy()
     rs, fds, mine = _group(s, cam, w, h, devices)
     for _ in range(frames):
@@ -86,6 +86,21 @@ def test_peer_three_ranks_ragged_rows_one_gpu(monkeypatch):
     assert int((ref != out).any(axis=2).sum()) == 0
 
 
+def test_peer_ao_strips_pixel00_halo(monkeypatch):
+    """An AO material over strips much taller than the 100-row AO halo, with pixel (0,0) covered: the colour of every uncovered
+    pixel comes from shading pixel (0,0) (bug-list 3), whose AO rays read depths of rows 0..99 — every rank must have rasterised
+    and resolved those rows, not only its own strip."""
+    monkeypatch.setenv("PRC_FMA", "exact")
+    s, cam = synth.mesh_scene(subdiv=24, with_ground=True, shadows=True, ao=True, aspect=240 / 640)
+    ref, out = _run([0, 0, 0], frames=2, size=(240, 640), scene=(s, cam))
+    assert int((ref != out).any(axis=2).sum()) == 0
+    # the case is only meaningful when pixel (0,0) is covered and some pixels are not
+    g = render.NewRenderer(*_opts(s, cam, 240, 640), render.CUDA(0))
+    g.Render(keep_gbuffer=True)
+    ok = g._backend.read_gbuffer(240, 640)["ok"].reshape(640, 240)
+    assert ok[0, 0] == 1 and (ok == 0).any(), "test scene no longer exercises the pixel-(0,0) AO quirk"
+
+
 def test_peer_two_contexts_one_process(monkeypatch):
     import torch
     if torch.cuda.device_count() < 2:
@@ -112,10 +127,6 @@ def test_peer_rejects_unsupported_frames(monkeypatch):
         be.render_peer(fds[0], mine[0], 1)
 
 
-_EXTRA = pytest.mark.skipif(os.environ.get("PRC_TEST_PEER_READBACK") != "1", reason="opt-in (PRC_TEST_PEER_READBACK=1): not run on hardware yet")
-
-
-@_EXTRA
 def test_peer_odd_frame_size_takes_the_scalar_push(monkeypatch):
     """A frame width that is not a multiple of 4: the shards are not float4-aligned and k_shadow_push<1> runs."""
     monkeypatch.setenv("PRC_FMA", "exact")
@@ -123,7 +134,6 @@ def test_peer_odd_frame_size_takes_the_scalar_push(monkeypatch):
     assert int((ref != out).any(axis=2).sum()) == 0
 
 
-@_EXTRA
 def test_peer_strip_readback_into_one_host_image(monkeypatch):
     """Every rank DMAs its own strip into ONE host image (prc_set_host_image), no device-side gather (image_mask = 0)."""
     monkeypatch.setenv("PRC_FMA", "exact")
@@ -145,7 +155,6 @@ def test_peer_strip_readback_into_one_host_image(monkeypatch):
         r._backend.peer_disconnect()
 
 
-@_EXTRA
 @pytest.mark.parametrize("world", [2, 3])
 def test_peer_msaa_strips_downsample_locally(monkeypatch, world):
     """render.MSAA(2) over strips: every rank shades `msaa` supersampled rows beyond its strip, runs imageutil.Resize on its own
