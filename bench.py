@@ -10,11 +10,18 @@ resident in HBM and the image left on the device (CUDA events on the library's s
 same through the C-ABI call with HOST buffers: per step the frame uniforms go host->device and the
 RGBA8 image comes back device->host inside the timed region.
 N>1 (torchrun, one process per GPU): the frame is split into N horizontal screen strips, the Ls
-shadow maps are sharded (light x row range) and all-gathered with NCCL, the image strips are
-gathered to rank 0; `scaling` = "strong" (same frame, more GPUs). `--mgpu peer` runs the same
-partition through prc_render_peer instead (NVLink peer memory, frames back to back, strips balanced
-by measured time, e2e through one shared host image); `--mgpu nccl` is the default until the peer
-path has been timed on several devices.
+shadow maps are sharded (light x row range), `scaling` = "strong" (same frame, more GPUs).
+`--mgpu peer` (default): frames through prc_render_peer — the ranks map each other's buffers over
+NVLink (CUDA IPC), every rank pushes the non-empty texels of its shadow rows into its peers' maps and
+its image strip into rank 0's image, ordered by epoch words in peer memory; frames are submitted back to
+back with no host wait and no collective, strips balanced by measured time; e2e through one shared host
+image. `--mgpu nccl`: round 1's path (one frame at a time, shadow maps and image strips all-gathered with
+NCCL), kept for comparison. Every N>1 line carries `matches_1gpu`: the frame's CRC against rank 0's own
+1-GPU render of the same frame.
+Roofline: `roofline` = the dominant kernel against the measured HBM peak with SURVEY 8(d)'s algorithmic
+bytes (per rank at N>1: the bytes of the rows that rank owns); `shading_roofline` = the shading kernel
+against the FP32 FMA peak measured by prc_measure_fp32_peak in this run (SURVEY 8(d) flop per covered pixel);
+`frame_roofline` additionally states the covered pixels and a coverage-weighted fraction.
 `e2e.python_renderer_render_ms_per_step` (N=1, informational): the same frame through the Python
 mirror's Renderer.Render(), i.e. including the host-side uniforms.
 """
@@ -41,6 +48,11 @@ WORKLOADS = {
                                         n_materials=8, tex_size=256), shadow=True, gamma=True,
                desc="3840x2160, 10.0M-triangle synthetic scene (2M-tri ground heightfield + 1600 instanced 5000-tri meshes), 8 materials, "
                     "8 point lights, 4 shadow-casting, gamma"),
+    # the C3 scene from a camera inside the city: 85 % of the 4K frame is covered (the orbit camera of C3 leaves 75 % sky), so the
+    # shading pass is actually loaded; a second data point (`--workload C3-close`), the bench line stays C3
+    "C3-close": dict(w=3840, h=2160, gen=dict(n_objects=1600, obj_stacks=50, obj_slices=50, ground_cells=1000, n_lights=8, casting_every=2,
+                                              n_materials=8, tex_size=256, cam_radius=1.0, cam_height=0.9), shadow=True, gamma=True,
+                     desc="3840x2160, the C3 scene (10.0M triangles, 8 lights, 4 casting, gamma) seen from inside the city: ~85 % of the pixels covered"),
     # BASELINE configs[3]; not a bench line (the bench line is C3): `--workload C4 --no-cpu-baseline` records one data point
     "C4": dict(w=7680, h=4320, gen=dict(n_objects=18000, obj_stacks=50, obj_slices=50, ground_cells=2236, n_lights=1, casting_every=0,
                                         n_materials=8, tex_size=256), shadow=False, gamma=False,
@@ -152,16 +164,26 @@ def build_scene(name):
     return wl, s, cam, time.time() - t
 
 
-def algorithmic_bytes(n_valid, n_tris, w, h, n_cast):
+def algorithmic_bytes(n_tris, px, n_cast):
     """bytes/frame = 112 N + Ls 36 N + px (148 + 12 Ls)."""
-    px = w * h
     return 112 * n_tris + n_cast * 36 * n_tris + px * (148 + 12 * n_cast)
+
+
+def shading_flops(px_covered, n_lights, n_cast, ao=False):
+    """flop per lit pixel = 60 (texture query) + 110 per light + 70 per casting light (+ 28 000 with AO)."""
+    return px_covered * (60 + 110 * n_lights + 70 * n_cast + (28000 if ao else 0))
+
+
+def workload_config(name, wl, n_tris, n_valid):
+    """The `config` object — the same keys and values in both arms (the driver compares them)."""
+    return {"workload": f"{name}: {wl['desc']}", "n_tris": int(n_tris), "n_valid_tris": int(n_valid), "width": wl["w"], "height": wl["h"]}
 
 
 def run_reference(args):
     """The reference's own CPU implementation of the path, timed on the host cores: the oracle port
     (oracle/libpr_oracle.so, the C++ restatement of render/*.go) in its multithreaded mode — the Go
-    binary cannot be built in this image (no Go toolchain). Rank 0 only."""
+    binary cannot be built in this image (no Go toolchain). Rank 0 only. Each step renders the full frame
+    of the workload (about 1 s on 16 cores for C3), so the default K/W finish within a minute."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     import oracle_binding as ob
@@ -169,8 +191,6 @@ def run_reference(args):
     wl, s, cam, tgen = build_scene(args.workload)
     cores = os.cpu_count() or 1
     be = ob.OracleBackend(threads=cores)
-    # bounded sample: the same scene and lights at 1/4 x 1/4 of the pixels and (for C3) every 8th object,
-    # so one step is ~10-30 s of CPU work; throughput is reported on the sample's own triangles and pixels.
     w, h = wl["w"], wl["h"]
     r = render.NewRenderer(render.Camera(cam), render.Size(w, h), render.Scene(s), render.ShadowMap(wl["shadow"]),
                            render.GammaCorrection(wl["gamma"]), render._Backend(be))
@@ -188,24 +208,17 @@ def run_reference(args):
         "impl": "reference", "metric": "Mtris/s", "value": val, "unit": "Mtris/s", "n_gpus": args.gpus, "gpus_used": 0, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "mpixels_per_s": w * h / sec / 1e6,
-        "config": {"workload": f"{args.workload}: {wl['desc']}", "n_valid_tris": int(tm.n_valid_tris)},
+        "config": workload_config(args.workload, wl, r.scene_desc().n_tris, tm.n_valid_tris),
         "cpu_baseline": {"value": val, "unit": "Mtris/s", "cores": cores, "kind": "port",
-                         "sample": "full frame of the same workload, C++ restatement of the reference CPU path (not the Go binary), one task per 256 triangles / 32 pixels, per-pixel spinlocks"},
+                         "sample": "full frame of the same workload per step, C++ restatement of the reference CPU path (not the Go binary), one task per 256 triangles / 32 pixels, per-pixel spinlocks"},
         "e2e": {"value": val, "unit": "Mtris/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
 
 
-def cai(ptr, nbytes):
-    """A __cuda_array_interface__ view of library-owned device memory (for torch.distributed)."""
-    class _V:
-        pass
-    v = _V()
-    v.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-    return v
-
-
 def run_cuda(args):
+    import zlib
+
     import torch
     from polyred_b200 import _abi as A
     from polyred_b200 import render
@@ -221,6 +234,7 @@ def run_cuda(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     wl, s, cam, tgen = build_scene(args.workload)
     w, h = wl["w"], wl["h"]
+    px = w * h
     r = render.NewRenderer(render.Camera(cam), render.Size(w, h), render.Scene(s), render.ShadowMap(wl["shadow"]),
                            render.GammaCorrection(wl["gamma"]), render.CUDA(local))
     be = r._backend
@@ -229,31 +243,29 @@ def run_cuda(args):
     be.sync()
     t_upload = time.time() - t
     sources, _ = s.Lights()
-    cast = [i for i, l in enumerate(sources) if l.cast_shadow]
+    cast = [i for i, l in enumerate(sources) if l.cast_shadow] if wl["shadow"] else []
+    any_ao = any(getattr(m, "ambient_occlusion", False) for m in sd.materials)
     stream = torch.cuda.ExternalStream(be.stream(), device=torch.device("cuda", local))
+    fp32_peak = be.measure_fp32_peak()  # TFLOP/s, FMA micro-benchmark on this GPU, before anything is timed
 
     fd = r.frame_desc(no_readback=True)
-    if args.resident_uniforms:
-        # device-resident leg: the per-frame uniforms (object matrices, lights) are inputs already in HBM; the first
-        # warm-up frame uploads them, the timed frames reuse them (the e2e leg uploads them every frame)
-        pass
     fd_e2e = r.frame_desc(no_readback=False)
-    out = np.zeros((h, w, 4), np.uint8)
-    e2e_out = [None, out]
+    e2e_out = [None]
 
     # ---- multi-GPU partition: screen strips + shadow (light, row-range) shards (polyred_b200/distributed.py) ----
-    df = None
+    df = pf = None
     units = []
-    pf = None  # --mgpu peer: frames over NVLink peer memory (prc_render_peer), submitted back to back, no collective
     if world > 1:
         from polyred_b200.distributed import DistributedFrame, PeerFrames
-        df = DistributedFrame(r, rank, world, local)
-        df.prepare(fd)
-        df.prepare(fd_e2e)
-        units = df.units
         if args.mgpu == "peer":
+            # frames over NVLink peer memory (prc_render_peer), submitted back to back, no collective
             pf = PeerFrames(r, rank, world, local, root=0)
             shared_host_image = pf.share_host_image()  # e2e leg: every GPU DMAs its own strip into one shared host image
+        else:
+            df = DistributedFrame(r, rank, world, local)
+            df.prepare(fd)
+            df.prepare(fd_e2e)
+            units = df.units
 
     def step(fdesc, host_out):
         if world == 1:
@@ -266,9 +278,10 @@ def run_cuda(args):
             if host_out is None:
                 pf.submit(fdesc)  # device leg: strips gathered into rank 0's device image over NVLink
             else:
-                # e2e: uniforms in (every rank), the frame out: each rank's strip over its own PCIe link into the shared host image
+                # e2e: uniforms in (every rank), the frame out: each rank's strip over its own PCIe link into the shared host
+                # image; the frame is complete when every rank has passed the barrier
                 pf.submit(fdesc, gather=False)
-                pf.finish()
+                pf.finish(fast=True)
                 host_out[0] = shared_host_image
         else:
             img = df.render(fdesc, host_out is not None)
@@ -296,7 +309,7 @@ def run_cuda(args):
         # peer-memory frames take any row ranges: move the strip / shadow-shard boundaries until every rank takes the same
         # time (per-rank kernel times of two frames per round); the frame itself does not depend on the partition
         balance_log = []
-        for _ in range(4):
+        for _ in range(args.balance_rounds):
             for _ in range(2):
                 step(fd, None)
             barrier()
@@ -306,49 +319,62 @@ def run_cuda(args):
             step(fd, None)
         barrier()
     if args.resident_uniforms:
+        # device-resident leg: the per-frame uniforms (object matrices, lights) are inputs already in HBM; the warm-up
+        # frames uploaded them, the timed frames reuse them (the e2e leg uploads them every frame)
         fd.struct.flags |= A.PRC_FRAME_UNIFORMS_RESIDENT
     n_valid = int(be.timings().n_valid_tris)
 
     # ---- timed region 1: device-resident (value) ----
-    ksum = np.zeros(8)
-    klaunch = np.zeros(8, np.int64)
-    launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-    t0 = time.perf_counter()
-    if (world == 1 and args.async_frames) or pf is not None:
-        # frames stay on the device: submit them back to back (PRC_FRAME_ASYNC), one prc_sync inside the timed bracket; the
-        # per-class kernel timings come back summed over the K frames
-        if pf is None:
-            fd.struct.flags |= A.PRC_FRAME_ASYNC
-        for _ in range(args.steps):
-            step(fd, None)
+    back_to_back = (world == 1 and args.async_frames) or pf is not None
+
+    def timed_frames(k_frames, kernel_timers):
+        """K frames between two events on the library's stream; returns (device ms, wall s, timings of the K frames)."""
+        ksum, klaunch, launches = np.zeros(8), np.zeros(8, np.int64), 0
+        if not kernel_timers:
+            fd.struct.flags |= A.PRC_FRAME_NO_KERNEL_TIMERS
+        barrier()
         with torch.cuda.stream(stream):
-            e1.record(stream)
-        barrier()  # be.sync() finishes the asynchronous frames (raises if a queue overflowed: warm-up sized them)
-        peer_wait = be.peer_wait_ms() if pf is not None else None  # PRC_PEER_TRACE=1: where this rank idled for its peers
-        wall = time.perf_counter() - t0
-        sampler.window(t0, t0 + wall)
-        fd.struct.flags &= ~A.PRC_FRAME_ASYNC
-        tm = be.timings()
-        ksum += np.array(list(tm.kernel_ms))
-        klaunch += np.array(list(tm.kernel_launches))
-        launches += int(tm.gpu_launches)
-    else:
-        for _ in range(args.steps):
-            step(fd, None)
+            e0.record(stream)
+        t0 = time.perf_counter()
+        if back_to_back:
+            # frames stay on the device: submit them back to back, one prc_sync inside the timed bracket; the per-class
+            # kernel timings come back summed over the K frames
+            if pf is None:
+                fd.struct.flags |= A.PRC_FRAME_ASYNC
+            for _ in range(k_frames):
+                step(fd, None)
+            with torch.cuda.stream(stream):
+                e1.record(stream)
+            barrier()  # be.sync() finishes the asynchronous frames (raises if a queue overflowed: warm-up sized them)
+            fd.struct.flags &= ~A.PRC_FRAME_ASYNC
             tm = be.timings()
             ksum += np.array(list(tm.kernel_ms))
             klaunch += np.array(list(tm.kernel_launches))
             launches += int(tm.gpu_launches)
-        with torch.cuda.stream(stream):
-            e1.record(stream)
-        barrier()
+        else:
+            for _ in range(k_frames):
+                step(fd, None)
+                tm = be.timings()
+                ksum += np.array(list(tm.kernel_ms))
+                klaunch += np.array(list(tm.kernel_launches))
+                launches += int(tm.gpu_launches)
+            with torch.cuda.stream(stream):
+                e1.record(stream)
+            barrier()
         wall = time.perf_counter() - t0
-        sampler.window(t0, t0 + wall)
-    dev_ms = e0.elapsed_time(e1)
+        fd.struct.flags &= ~A.PRC_FRAME_NO_KERNEL_TIMERS
+        return e0.elapsed_time(e1), wall, t0, tm, ksum, klaunch, launches
+
+    # One GPU: the per-class event brackets stay on inside the timed region (they cost ~10 us of a 1.1 ms frame). N > 1: a
+    # frame is ~0.2 ms per rank, so the timed frames run without them and a second, untimed pass of K frames measures the classes.
+    dev_ms, wall, t0, tm, ksum, klaunch, launches = timed_frames(args.steps, kernel_timers=(world == 1))
+    sampler.window(t0, t0 + wall)
+    peer_wait = be.peer_wait_ms() if pf is not None else None  # PRC_PEER_TRACE=1: where this rank idled for its peers
+    kernel_pass = "inside the timed region"
+    if world > 1:
+        _, _, _, _, ksum, klaunch, _ = timed_frames(args.steps, kernel_timers=True)
+        kernel_pass = "a second pass of K frames with the event brackets on (the timed frames run without them)"
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- timed region 2: end to end through the C ABI with host buffers ----
@@ -360,6 +386,23 @@ def run_cuda(args):
         step(fd_e2e, e2e_out)
     barrier()
     wall_e2e = time.perf_counter() - t0
+
+    # ---- checks outside the timed regions: frame CRC (N > 1: against this rank's own 1-GPU render), covered pixels ----
+    frame_crc = matches = covered_px = None
+    if rank == 0:
+        img = np.ascontiguousarray(e2e_out[0]).copy()
+        frame_crc = zlib.crc32(img.tobytes())
+    if world > 1:
+        barrier()
+        if rank == 0:
+            r1 = render.NewRenderer(render.Camera(cam), render.Size(w, h), render.Scene(s), render.ShadowMap(wl["shadow"]),
+                                    render.GammaCorrection(wl["gamma"]), render.CUDA(local))
+            ref = r1.Render()
+            matches = bool(zlib.crc32(np.ascontiguousarray(ref).tobytes()) == frame_crc)
+            covered_px = int(r1._backend.covered_pixels(w, h)) if hasattr(r1._backend, "covered_pixels") else None
+            r1._backend.close()
+    elif hasattr(be, "covered_pixels"):
+        covered_px = int(be.covered_pixels(w, h))
 
     # the same frames through the host mirror's Renderer.Render() (scene-graph walk, uniforms, prc_render, image in place): what a
     # Python caller pays on top of the C-ABI call. Informational only; never allowed to break the bench line.
@@ -382,6 +425,8 @@ def run_cuda(args):
     else:
         wall_ms, wall_e2e_ms = wall * 1e3, wall_e2e * 1e3
     if rank != 0:
+        if pf is not None:
+            pf.close()
         if dist is not None:
             dist.destroy_process_group()
         return
@@ -390,46 +435,73 @@ def run_cuda(args):
     fps = 1e3 / ms
     fps_e2e = 1e3 / (wall_e2e_ms / args.steps)
     pk, pk_kind = peaks()
-    # dominant kernel of the frame
     names = A.KERNEL_CLASSES
-    dom = int(np.argmax(ksum))
     n_tris = sd.n_tris
-    px = w * h
-    n_fused = max(1, int(round(len(cast) * args.steps / max(1, klaunch[0]))))  # shadow lights sharing one sweep
-    # 1 GPU, no AO material, no KEEP_GBUFFER: resolve and shading run as ONE kernel (k_resolve_shade, timed in the "shade"
+    # ---- roofline of the dominant kernel class (this rank's launches, this rank's share of the algorithmic bytes) ----
+    dom = int(np.argmax(ksum))
+    if pf is not None:
+        own_rows = pf.rows[rank][1] - pf.rows[rank][0]
+        own_shadow_rows = pf.sh_bounds[rank + 1] - pf.sh_bounds[rank]
+    elif df is not None:
+        own_rows = df.rows[rank][1] - df.rows[rank][0]
+        own_shadow_rows = sum(b - a for _, a, b, owner in units if owner == rank)
+    else:
+        own_rows, own_shadow_rows = h, len(cast) * h
+    f_img = own_rows / h                                    # this rank's share of the screen rows
+    f_sh = own_shadow_rows / max(1, len(cast) * h)          # ... of the stacked shadow-map rows
+    sweeps = max(1, int(round(klaunch[0] / args.steps)))    # shadow sweeps per frame on this rank (up to 8 views share one)
+    # 1 GPU / peer frames without an AO material: resolve and shading run as ONE kernel (k_resolve_shade, timed in the "shade"
     # class); it is charged the algorithmic bytes of both stages, G-buffer round trip included
-    one_kernel_shade = world == 1 and not os.environ.get("PRC_NO_FUSED_SHADE") and not any(
-        getattr(m, "ambient_occlusion", False) for m in sd.materials)
-    shade_bytes = (64 + 4 + 4 * len(cast)) * px + ((8 + 64) * px if one_kernel_shade else 0)
-    per_launch_bytes = {0: n_fused * (36 * n_tris + 8 * px), 1: 112 * n_tris + 16 * px, 4: 8 * px, 5: 16 * px, 6: (8 + 64) * px, 7: shade_bytes}
-    alg = per_launch_bytes.get(dom, 0)
+    one_kernel_shade = (world == 1 or pf is not None) and not os.environ.get("PRC_NO_FUSED_SHADE") and not any_ao
+    shade_bytes = f_img * ((64 + 4 + 4 * len(cast)) * px + ((8 + 64) * px if one_kernel_shade else 0))
+    per_launch_bytes = {0: f_sh * len(cast) * (36 * n_tris + 8 * px) / sweeps, 1: f_img * (112 * n_tris + 16 * px), 6: f_img * (8 + 64) * px, 7: shade_bytes}
+    alg = per_launch_bytes.get(dom, 0.0)
+    launches_per_step = float(klaunch[dom]) / args.steps
     avg_ms = ksum[dom] / max(1, klaunch[dom])
     achieved = alg / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
-    frame_bytes = algorithmic_bytes(n_valid, n_tris, w, h, len(cast))
-    # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this command (profiles/)
-    traffic = None
+    frame_bytes = algorithmic_bytes(n_tris, px, len(cast))
+    covered_bytes = (112 * n_tris + len(cast) * 36 * n_tris + (8 + 8) * px + len(cast) * 12 * px + (128 + 4) * (covered_px if covered_px is not None else px)
+                     + 4 * (px - (covered_px if covered_px is not None else px)))
+    # DRAM traffic of the dominant kernel: from the committed `ncu --set full` capture of this command (profiles/), labelled
+    traffic = traffic_src = None
     import glob
     tpaths = sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_r*.json")))  # the latest round's capture
     if world == 1 and args.workload == "C3" and tpaths:
-        traffic = json.load(open(tpaths[-1])).get(names[dom], {}).get("dram_bytes_per_launch")
+        tj = json.load(open(tpaths[-1]))
+        traffic = tj.get(names[dom], {}).get("dram_bytes_per_launch")
+        traffic_src = f"{os.path.relpath(tpaths[-1], ROOT)} ({tj.get('_commit', 'commit not recorded')})"
+    shade_ms = float(ksum[7]) / args.steps
+    sflops = shading_flops((covered_px if covered_px is not None else px) * f_img, len(sources), len(cast), any_ao)
     h2d = fd.struct.n_objects * 128 + len(cast) * fd.struct.n_objects * 64 + len(sources) * 168 + 256 + 4 * fd.struct.n_ambient
     line = {
         "metric": "Mtris/s", "value": n_valid * fps / 1e6, "unit": "Mtris/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "mpixels_per_s": px * fps / 1e6, "frames_per_s": fps, "wall_ms_per_step": wall_ms / args.steps,
-        "config": {"workload": f"{args.workload}: {wl['desc']}", "n_tris": int(n_tris), "n_valid_tris": n_valid, "width": w, "height": h,
-                   "fma": os.environ.get("PRC_FMA", "mixed"), "l2": "inputs (1.1 GB scene, 0.9 GB frame buffers) larger than L2; no explicit flush",
-                   "submit": ("K frames back to back (PRC_FRAME_ASYNC), one prc_sync inside the timed bracket" if (world == 1 and args.async_frames)
-                              else "K frames back to back (prc_render_peer), one prc_sync inside the timed bracket" if pf is not None
-                              else "one synchronous call per frame"),
-                   "partition": "1 GPU" if world == 1
-                   else f"{world} screen strips + {len(units)} shadow shards; non-empty shadow texels and image strips pushed over NVLink peer memory by the library (no collective, no host wait inside a frame), image on rank 0" if pf is not None
-                   else f"{world} screen strips + {len(units)} shadow shards (one in-place NCCL all-gather overlapped with the camera pass, one in-place all-gather of the image strips)"},
+        "config": workload_config(args.workload, wl, n_tris, n_valid),
+        "run": {"fma": os.environ.get("PRC_FMA", "mixed"), "l2": "inputs (1.1 GB scene, 0.9 GB frame buffers) larger than L2; no explicit flush",
+                "submit": ("K frames back to back (PRC_FRAME_ASYNC), one prc_sync inside the timed bracket" if (world == 1 and args.async_frames)
+                           else "K frames back to back (prc_render_peer), one prc_sync inside the timed bracket" if pf is not None
+                           else "one synchronous call per frame"),
+                "partition": "1 GPU" if world == 1
+                else f"{world} screen strips + shadow shards by rows; non-empty shadow texels and image strips pushed over NVLink peer memory by the library (no collective, no host wait inside a frame), image on rank 0" if pf is not None
+                else f"{world} screen strips + {len(units)} shadow shards (one in-place NCCL all-gather overlapped with the camera pass, one in-place all-gather of the image strips)",
+                "kernel_timings": kernel_pass},
         "roofline": {"bound": "hbm", "kernel": ("resolve_shade (k_resolve_shade, one kernel)" if (dom == 7 and one_kernel_shade) else names[dom]), "achieved": achieved, "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s",
-                     "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms,
-                     "launches_per_step": float(klaunch[dom]) / args.steps},
-        "frame_roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": frame_bytes, "achieved": frame_bytes / (ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
-                           "frac": frame_bytes / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], "unit": "GB/s"},
+                     "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms,
+                     "launches_per_step": launches_per_step,
+                     "scope": "rank 0's launches against rank 0's share of the algorithmic bytes (rows it owns)" if world > 1 else "the whole frame on one GPU"},
+        "shading_roofline": {"bound": "fp32", "kernel": "resolve_shade" if one_kernel_shade else "shade", "algorithmic_flop_per_launch_set": sflops,
+                             "achieved": sflops / (shade_ms * 1e-3) / 1e12 if shade_ms > 0 else 0.0, "peak": fp32_peak, "unit": "TFLOP/s",
+                             "peak_kind": "measured in this run (prc_measure_fp32_peak: pure FMA chains, 2 flop each)",
+                             "frac": (sflops / (shade_ms * 1e-3) / 1e12 / fp32_peak) if (shade_ms > 0 and fp32_peak > 0) else 0.0,
+                             "ms_per_step": shade_ms,
+                             "note": "SURVEY 8(d) flop per COVERED pixel (60 + 110 L + 70 Ls); issue-slot and pipe utilisation of this kernel: profiles/ncu_shade_r2.txt"},
+        "frame_roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": frame_bytes, "achieved": frame_bytes / (ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"] * world,
+                           "frac": frame_bytes / (ms * 1e-3) / 1e9 / (pk["hbm_gbs"] * world), "unit": "GB/s", "covered_px": covered_px,
+                           "coverage": (covered_px / px) if covered_px is not None else None,
+                           "coverage_weighted_bytes_per_frame": covered_bytes,
+                           "coverage_weighted_frac": covered_bytes / (ms * 1e-3) / 1e9 / (pk["hbm_gbs"] * world),
+                           "note": "peak = N x the measured single-GPU HBM peak; coverage-weighted: the 128 B/px G-buffer round trip charged to covered pixels only"},
         "kernel_ms_per_step": {names[k]: float(ksum[k]) / args.steps for k in range(8)},
         "e2e": {"value": n_valid * fps_e2e / 1e6, "unit": "Mtris/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(px * 4),
                 "ms_per_step": wall_e2e_ms / args.steps, "mpixels_per_s": px * fps_e2e / 1e6,
@@ -438,14 +510,16 @@ def run_cuda(args):
                          "prc_render through the C ABI: host prc_frame (per-object matrices) in, host RGBA8 out; scene resident after one prc_scene_upload"),
                 "scene_upload_once": {"bytes": int(sd.upload_bytes()), "seconds": t_upload},
                 "python_renderer_render_ms_per_step": mirror_ms},
+        "frame_crc": frame_crc, "matches_1gpu": matches,
         "stats_last_frame": {"n_large_items": int(tm.n_large_items), "n_clipped": int(tm.n_clipped), "n_bin_entries": int(tm.n_bin_entries), "n_nan_frags": int(tm.n_nan_frags)},
         "gpu_launches": launches, "clocks": clocks, "scene_gen_seconds": tgen,
     }
     if pf is not None:
-        line["config"]["strip_rows"] = [r1 - r0 for r0, r1 in pf.rows]
-        line["config"]["shadow_rows_per_rank"] = [b - a for a, b in zip(pf.sh_bounds, pf.sh_bounds[1:])]
+        line["run"]["strip_rows"] = [r1_ - r0_ for r0_, r1_ in pf.rows]
+        line["run"]["shadow_rows_per_rank"] = [b_ - a_ for a_, b_ in zip(pf.sh_bounds, pf.sh_bounds[1:])]
         line["balance_rounds"] = balance_log
         line["peer_wait_ms_per_step_rank0"] = {k: v / args.steps for k, v in peer_wait.items()} if peer_wait else None
+        pf.close()
     if args.cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args, wl, s, cam)
     emit(line)
@@ -497,9 +571,10 @@ def main():
     ap.add_argument("--no-async-frames", dest="async_frames", action="store_false",
                     help="device-resident leg: wait for every frame (prc_render) instead of submitting the K frames back to back")
     ap.add_argument("--no-balance", dest="balance", action="store_false", help="--mgpu peer: keep equal strips / shadow shards")
-    ap.add_argument("--mgpu", default=os.environ.get("PRC_MGPU", "nccl"), choices=["nccl", "peer"],
-                    help="N > 1: 'nccl' = one frame at a time, shadow maps and image strips all-gathered with NCCL (measured in round 1); "
-                         "'peer' = frames submitted back to back, exchange pushed over NVLink peer memory by the library (prc_render_peer)")
+    ap.add_argument("--balance-rounds", type=int, default=10)
+    ap.add_argument("--mgpu", default=os.environ.get("PRC_MGPU", "peer"), choices=["nccl", "peer"],
+                    help="N > 1: 'peer' (default) = frames submitted back to back, exchange pushed over NVLink peer memory by the library "
+                         "(prc_render_peer); 'nccl' = round 1's path: one frame at a time, shadow maps and image strips all-gathered with NCCL")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

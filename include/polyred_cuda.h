@@ -76,6 +76,8 @@ extern "C" {
 #define PRC_FRAME_ASYNC 256u       /* prc_render only, with PRC_FRAME_NO_READBACK: enqueue the frame and return without waiting. Completion,
                                      * timings (summed over the frames) and the queue-overflow check happen in prc_sync(); for callers that
                                      * keep the frames on the device (present, multi-view batches) this removes the host bubble between frames */
+#define PRC_FRAME_NO_KERNEL_TIMERS 512u /* no per-kernel-class CUDA-event brackets for this frame (prc_timings.kernel_ms stays 0): an event
+                                        * pair costs ~2.6 us of stream time, which matters for the 0.2 ms frames of an 8-GPU group */
 #define PRC_FRAME_SHADOW_RESET 64u /* zero the shadow maps at the start of this frame, stream-ordered: what Options()
                                      * does between views (render/options.go:125-141), without prc_shadow_reset's host sync */
 
@@ -202,8 +204,8 @@ typedef struct prc_timings {
   uint64_t n_nan_frags;   /* fragments with NaN depth seen by the raster (bug-list 8), not resolved by key */
   uint64_t gpu_launches;  /* kernels launched by the last prc_render */
   /* per kernel class, CUDA-event time on the launching stream, summed over the frame:
-   * 0 geom+raster (shadow lights)  1 geom+raster (camera)  2 clip  3 binning (count+scan+fill)
-   * 4 tile raster (shadow)  5 tile raster (camera)  6 resolve  7 shade */
+   * 0 geom+raster (shadow lights)  1 geom+raster (camera)  2 clip  3 binning (count+scan+fill; only when a record needs the tile path)
+   * 4 medium raster (queued records, one warp each)  5 tile raster  6 resolve  7 shade */
   float kernel_ms[8];
   uint32_t kernel_launches[8];
   uint64_t n_large_items; /* triangles routed to the tile path, summed over the passes of the frame */
@@ -215,8 +217,8 @@ typedef struct prc_timings {
 #define PRC_K_GEOM_CAMERA 1
 #define PRC_K_CLIP 2
 #define PRC_K_BIN 3
-#define PRC_K_TILE_SHADOW 4
-#define PRC_K_TILE_CAMERA 5
+#define PRC_K_MEDIUM 4
+#define PRC_K_TILE 5
 #define PRC_K_RESOLVE 6
 #define PRC_K_SHADE 7
 
@@ -321,6 +323,13 @@ int32_t prc_peer_wait_ms(prc_ctx* ctx, float out[4]);
  * each GPU then delivers its own strip over its own PCIe link and no device-side gather is needed (image_mask = 0).
  * ptr == NULL unregisters. */
 int32_t prc_set_host_image(prc_ctx* ctx, void* ptr, uint64_t bytes);
+
+/* Number of covered pixels (Fragment.Ok, buffer/buffer.go:209-219) of the rows this context rasterised in its last frame —
+ * for the coverage-weighted roofline of the measurement harness. */
+int32_t prc_count_covered(prc_ctx* ctx, uint64_t* covered);
+/* Measured FP32 FMA throughput of this device in TFLOP/s (2 flop per FMA; a pure-FMA micro-benchmark, best of a few launches):
+ * the denominator of the shading kernels' roofline. No reference counterpart (measurement only). */
+int32_t prc_measure_fp32_peak(prc_ctx* ctx, double* tflops);
 
 /* Arithmetic mode of this context, overriding the PRC_FMA environment variable read by prc_open:
  * exact != 0 -> math.FMA[float32] emulated bit-exactly everywhere (float64 fma rounded to float32, math/math.go FMA),

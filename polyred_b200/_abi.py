@@ -32,6 +32,7 @@ PRC_FRAME_UNIFORMS_RESIDENT = 32
 PRC_FRAME_SHADOW_RESET = 64
 PRC_FRAME_BGRA = 128
 PRC_FRAME_ASYNC = 256
+PRC_FRAME_NO_KERNEL_TIMERS = 512
 
 F16 = C.c_float * 16
 F3 = C.c_float * 3
@@ -174,7 +175,7 @@ class prc_peer_handle(C.Structure):
     ]
 
 
-KERNEL_CLASSES = ("geom_raster_shadow", "geom_raster_camera", "clip", "binning", "tile_raster_shadow", "tile_raster_camera", "resolve", "shade")
+KERNEL_CLASSES = ("geom_raster_shadow", "geom_raster_camera", "clip", "binning", "medium_raster", "tile_raster", "resolve", "shade")
 
 
 def pack_rgba(c) -> int:

@@ -60,11 +60,14 @@ def lib():
         L.prc_set_exact_fma.argtypes = [vp, C.c_int32]
         L.prc_set_host_image.argtypes = [vp, vp, C.c_uint64]
         L.prc_peer_wait_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]
+        L.prc_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double)]
+        L.prc_count_covered.argtypes = [vp, C.POINTER(C.c_uint64)]
         for name in ("prc_open", "prc_close", "prc_scene_upload", "prc_shadow_reset", "prc_render", "prc_read_gbuffer",
                      "prc_read_shadowmap", "prc_get_timings", "prc_device_image", "prc_device_shadowmap",
                      "prc_render_shadows", "prc_render_main", "prc_stream", "prc_sync", "prc_host_image", "prc_render_forward",
                      "prc_render_deferred", "prc_device_shadow_all", "prc_render_shadow_units", "prc_peer_export", "prc_peer_connect",
-                     "prc_peer_disconnect", "prc_render_peer", "prc_set_exact_fma", "prc_read_image", "prc_set_host_image", "prc_peer_wait_ms"):
+                     "prc_peer_disconnect", "prc_render_peer", "prc_set_exact_fma", "prc_read_image", "prc_set_host_image", "prc_peer_wait_ms",
+                     "prc_measure_fp32_peak", "prc_count_covered"):
             getattr(L, name).restype = C.c_int32
         if L.prc_abi_version() != A.PRC_ABI_VERSION:
             raise PolyredCudaError(A.PRC_ERR_INVALID, "ABI version mismatch")
@@ -236,6 +239,18 @@ class CudaBackend(Backend):
         li, r0, r1 = arrays
         self._check(self.L.prc_render_peer(self.h, C.byref(fd.struct), n, li.ctypes.data if n else None, r0.ctypes.data if n else None,
                                            r1.ctypes.data if n else None, image_mask))
+
+    def covered_pixels(self, w=None, h=None) -> int:
+        """Covered pixels (visibility key set) of the last frame rendered by this context."""
+        out = C.c_uint64(0)
+        self._check(self.L.prc_count_covered(self.h, C.byref(out)))
+        return int(out.value)
+
+    def measure_fp32_peak(self) -> float:
+        """Measured FP32 FMA throughput of the device, TFLOP/s (the shading kernels' roofline denominator)."""
+        out = C.c_double(0.0)
+        self._check(self.L.prc_measure_fp32_peak(self.h, C.byref(out)))
+        return float(out.value)
 
     def peer_wait_ms(self) -> dict:
         """PRC_PEER_TRACE=1: where this rank's stream idled for its peers during the frames finished by the last sync()."""

@@ -52,7 +52,11 @@ struct prc_ctx {
   uint32_t target_of_light[64] = {0};
   bool light_affine[64] = {false};
   DBuf d_xf, d_lights, d_ambient, d_gamma, d_frame, d_aoc, d_chunkbox, d_vis, d_cverts, d_cvoff, d_lidx;
-  DBuf d_chunklist;  // PRC_GEOM_PERSIST tuning build only
+  DBuf d_chunklist;  // compacted list of the chunks a raster pass can touch (k_chunk_cull_views)
+  unsigned int* h_list_hint = nullptr;  // page-locked, device-visible: list length per raster pass of the last frame (grid sizing hint)
+  int pass_slot = 0;                    // raster passes enqueued so far in the current frame
+  bool no_chunk_cull = false, force_chunk_cull = false;  // PRC_NO_CHUNK_CULL / PRC_FORCE_CHUNK_CULL
+  bool need_bins = false;               // a frame queued a record too large for k_medium_raster: the binned tile path runs from then on
   uint32_t n_chunks = 0;
   uint64_t n_cverts = 0;  // distinct chunk-local vertices (k_chunk_dedupe)
   std::vector<DevLight> h_lights;    // host staging of the per-frame light table
@@ -94,6 +98,9 @@ struct prc_ctx {
   bool nan_mode = false;
   DevFrame h_frame{};
   bool capturing = false;
+  bool no_fused_shade = false;  // PRC_NO_FUSED_SHADE
+  bool ktimers = true;  // PRC_NO_KTIMERS=1: no per-kernel-class event brackets (prc_timings.kernel_ms stays 0)
+  bool ktimers_frame = true;  // ... for the frame being enqueued (PRC_FRAME_NO_KERNEL_TIMERS)
   uint32_t n_lights_alloc = 0;
 
   // peer exchange (prc_peer_* / prc_render_peer): peers.world == 0 <=> not connected
@@ -173,12 +180,14 @@ struct KTimer {
   size_t a;
   int cls;
   KTimer(prc_ctx* c, int k) : ctx(c), cls(k) {
+    if (!ctx->ktimers_frame) { cls = -1; return; }
     while (ctx->evpool.size() < ctx->ev_used + 2) { cudaEvent_t e; cudaEventCreate(&e); ctx->evpool.push_back(e); }
     a = ctx->ev_used;
     ctx->ev_used += 2;
     cudaEventRecordWithFlags(ctx->evpool[a], ctx->stream, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
   }
   ~KTimer() {
+    if (cls < 0) return;
     cudaEventRecordWithFlags(ctx->evpool[a + 1], ctx->stream, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
     ctx->spans.push_back({cls, a, a + 1});
   }
@@ -209,98 +218,124 @@ int32_t raster_pass(prc_ctx* ctx, const DevFrame& F, const GeomViews& Vin) {
   unsigned int* clipq = (unsigned int*)ctx->d_clipq.p;
   DBuf& fb = ctx->d_frame;  // device-resident copy of the frame for the rare generic path (uploaded by build_frame)
   GeomViews V = Vin;
-  if (ctx->S.n_tris && !getenv("PRC_NO_CHUNK_CULL")) {
-    // chunk culling pays when a view covers only part of the rows (multi-GPU strips / shadow shards)
-    const int nv = SHADOW ? V.n : 1;
-    for (int v = 0; v < nv; v++) {
-      const int r0 = SHADOW ? V.r0[v] : F.rr0, r1 = SHADOW ? V.r1[v] : F.rr1;
-      if (r0 <= 0 && r1 >= F.H && !getenv("PRC_FORCE_CHUNK_CULL")) continue;
-      unsigned char* vis = (unsigned char*)ctx->d_vis.p + (size_t)(SHADOW ? 1 + v : 0) * ctx->n_chunks;
-      const float* tb = SHADOW ? V.trans[v] : (const float*)ctx->d_xf.p;
-      k_chunk_cull<<<cdiv(ctx->n_chunks, 256), 256, 0, st>>>((const ChunkBox*)ctx->d_chunkbox.p, ctx->n_chunks, tb, SHADOW ? 16 : 32,
-                                                             (const float*)((const char*)fb.p + offsetof(DevFrame, viewport)), F.W, F.H, r0, r1,
-                                                             (!SHADOW && r0 > 0) ? 1 : 0, vis);
-      V.vis[v] = vis;
-      V.any_vis = 1;
+  bool list_mode = false;
+  unsigned int grid = cdiv(ctx->S.n_tris, PRC_GEOM_THREADS);
+  if (ctx->S.n_tris && !ctx->no_chunk_cull) {
+    // chunk culling pays when a view covers only part of the rows (multi-GPU strips / shadow shards): one launch tests every
+    // view of the pass and compacts the chunks some view can touch; the geometry grid then walks that list
+    CullViews C{};
+    C.n = SHADOW ? V.n : 1;
+    C.stride = SHADOW ? 16 : 32;
+    C.need_pixel00 = (!SHADOW && F.rr0 > 0) ? 1 : 0;
+    bool any_test = false;
+    for (int v = 0; v < C.n; v++) {
+      C.r0[v] = SHADOW ? V.r0[v] : F.rr0;
+      C.r1[v] = SHADOW ? V.r1[v] : F.rr1;
+      C.test[v] = (!(C.r0[v] <= 0 && C.r1[v] >= F.H) || ctx->force_chunk_cull) ? 1 : 0;
+      any_test = any_test || C.test[v];
+      C.trans[v] = SHADOW ? V.trans[v] : (const float*)ctx->d_xf.p;
+      C.vis[v] = (unsigned char*)ctx->d_vis.p + (size_t)(SHADOW ? 1 + v : 0) * ctx->n_chunks;
+    }
+    const int slot = ctx->pass_slot++;
+    if (any_test && slot < 16) {
+      ENSURE(ctx->d_chunklist, ((size_t)ctx->n_chunks + 4) * 4);
+      unsigned int* n_list = &cnt->n_list[slot];  // zeroed with the frame's counters
+      k_chunk_cull_views<<<cdiv(ctx->n_chunks, 256), 256, 0, st>>>((const ChunkBox*)ctx->d_chunkbox.p, ctx->n_chunks, C,
+                                                                   (const float*)((const char*)fb.p + offsetof(DevFrame, viewport)), F.W,
+                                                                   (unsigned int*)ctx->d_chunklist.p, n_list);
       ctx->launches++;
+      for (int v = 0; v < C.n; v++) V.vis[v] = C.vis[v];
+      V.any_vis = 1;
+      V.list = (const unsigned int*)ctx->d_chunklist.p;
+      V.n_list = n_list;
+      V.n_list_hint = ctx->h_list_hint ? ctx->h_list_hint + slot : nullptr;
+      list_mode = true;
+      // grid from the list length of the previous frame's pass in this slot (0 = not known yet: one CTA per chunk)
+      const unsigned int hint = ctx->h_list_hint ? ctx->h_list_hint[slot] : 0u;
+      if (hint) grid = std::min(grid, std::max(148u * 2u, hint + hint / 8u + 32u));
+      V.list_from = grid;
     }
   }
-#if PRC_GEOM_PERSIST
-  if (ctx->S.n_tris) {
-    // tuning build: persistent grid over the compacted list of visible chunks (see k_geom_raster)
-    ENSURE(ctx->d_chunklist, ((size_t)ctx->n_chunks + 4) * 4);
-    unsigned int* n_list = (unsigned int*)ctx->d_chunklist.p;  // [0] = count, the list starts at +4
-    CK(cudaMemsetAsync(n_list, 0, 4, st));
+  {
+    // (one event bracket per pass: an event pair costs ~2.6 us of stream time, so the clip kernel — a fixed grid that finds an
+    // empty queue on most frames — is timed inside the camera pass's bracket; the "clip" class stays 0)
     KTimer kt(ctx, SHADOW ? PRC_K_GEOM_SHADOW : PRC_K_GEOM_CAMERA);
-    k_chunk_compact<<<cdiv(ctx->n_chunks, 256), 256, 0, st>>>(V, SHADOW ? V.n : 1, ctx->n_chunks, n_list + 4, n_list);
-    V.list = n_list + 4;
-    V.n_list = n_list;
-    k_geom_raster<E, SHADOW><<<std::min<unsigned int>(148u * PRC_GEOM_MIN_BLOCKS, ctx->n_chunks), PRC_GEOM_THREADS, 0, st>>>(
-        ctx->S, F, V, keys, large, ctx->large_cap, clipq, ctx->clip_cap, cnt, (const DevFrame*)fb.p);
-    ctx->launches += 2;
-  }
-#else
   if (ctx->S.n_tris) {
-    KTimer kt(ctx, SHADOW ? PRC_K_GEOM_SHADOW : PRC_K_GEOM_CAMERA);
-    const unsigned int grid = cdiv(ctx->S.n_tris, PRC_GEOM_THREADS);
+    const DevFrame* Fg = (const DevFrame*)fb.p;
+    const bool tail = list_mode && grid < cdiv(ctx->S.n_tris, PRC_GEOM_THREADS);  // the list may have outgrown the hinted grid
+#define PRC_LAUNCH_GEOM(NM_, LIST_, GRID_) \
+  k_geom_raster<E, SHADOW, NM_, LIST_><<<GRID_, PRC_GEOM_THREADS, 0, st>>>(ctx->S, F, V, keys, large, ctx->large_cap, clipq, ctx->clip_cap, cnt, Fg)
     bool done = false;
     if constexpr (!SHADOW) {
       if (ctx->nan_mode) {
-        k_geom_raster<E, false, true><<<grid, PRC_GEOM_THREADS, 0, st>>>(ctx->S, F, V, keys, large, ctx->large_cap, clipq, ctx->clip_cap, cnt, (const DevFrame*)fb.p);
+        if (list_mode) { PRC_LAUNCH_GEOM(true, 1, grid); if (tail) PRC_LAUNCH_GEOM(true, 2, 148u); } else PRC_LAUNCH_GEOM(true, 0, grid);
         done = true;
       }
     }
-    if (!done)
-      k_geom_raster<E, SHADOW><<<grid, PRC_GEOM_THREADS, 0, st>>>(ctx->S, F, V, keys, large, ctx->large_cap, clipq, ctx->clip_cap, cnt, (const DevFrame*)fb.p);
-    ctx->launches++;
+    if (!done) {
+      if (list_mode) { PRC_LAUNCH_GEOM(false, 1, grid); if (tail) PRC_LAUNCH_GEOM(false, 2, 148u); } else PRC_LAUNCH_GEOM(false, 0, grid);
+    }
+#undef PRC_LAUNCH_GEOM
+    ctx->launches += tail ? 2 : 1;
   }
-#endif
   if (!SHADOW) {
     // fixed grid, reads its work count on the device (grid-stride loop)
-    KTimer kt(ctx, PRC_K_CLIP);
-    if (ctx->nan_mode) k_clip_raster<E, true><<<148 * 4, 128, 0, st>>>(ctx->S, F, clipq, keys, large, ctx->large_cap, cnt);
-    else k_clip_raster<E><<<148 * 4, 128, 0, st>>>(ctx->S, F, clipq, keys, large, ctx->large_cap, cnt);
+    if (ctx->nan_mode) k_clip_raster<E, true><<<148, 128, 0, st>>>(ctx->S, F, clipq, keys, large, ctx->large_cap, cnt);
+    else k_clip_raster<E><<<148, 128, 0, st>>>(ctx->S, F, clipq, keys, large, ctx->large_cap, cnt);
     ctx->launches++;
+  }
   }
   CK(cudaGetLastError());
   return PRC_OK;
 }
 
-// ---- tile path, once per frame (or per phase in the split multi-GPU API) for everything queued so far --------
+// ---- everything queued so far (camera keys and shadow maps), once per frame (or per phase in the split multi-GPU API): records up
+// to PRC_MEDIUM_MAX_PIXELS by k_medium_raster, larger ones through the binned tile path — which is only launched once a frame
+// has reported such a record (ctx->need_bins, sticky; the reporting frame is re-rendered like a queue overflow) --------
 template <bool E>
 int32_t flush_large(prc_ctx* ctx, const DevFrame& F) {
   cudaStream_t st = ctx->stream;
   Counters* cnt = (Counters*)ctx->d_counters.p;
-  const int tiles_x = (F.W + PRC_TILE - 1) / PRC_TILE, tiles_y = (F.H + PRC_TILE - 1) / PRC_TILE;
-  const int n_tiles = tiles_x * tiles_y, n_vt = n_tiles * (int)ctx->n_targets;
-  const unsigned int n_chunks = (unsigned int)((n_vt + 1 + 4095) / 4096);
-  unsigned int* tile_count = (unsigned int*)ctx->d_tilecount.p;
-  unsigned int* tile_start = (unsigned int*)ctx->d_tilestart.p;
-  unsigned int* cursor = (unsigned int*)ctx->d_cursor.p;
-  unsigned int* active_hdr = (unsigned int*)ctx->d_active.p;
   LargeRec* large = (LargeRec*)ctx->d_large.p;
-  CK(cudaMemsetAsync(tile_count, 0, (size_t)n_chunks * 4096 * 4, st));
-  CK(cudaMemsetAsync(active_hdr, 0, 16, st));
   {
-    KTimer kt(ctx, PRC_K_BIN);
-    k_bin_count<<<148 * 4, 256, 0, st>>>(large, cnt, ctx->large_cap, tiles_x, n_tiles, tile_count);
-    k_scan_sums<<<n_chunks, 1024, 0, st>>>(tile_count, (unsigned int*)ctx->d_chunksum.p, cnt);
-    k_scan_apply<<<n_chunks, 1024, 0, st>>>(tile_count, tile_start, cursor, (const unsigned int*)ctx->d_chunksum.p, cnt, ctx->bins_cap, ctx->large_cap,
-                                            active_hdr + 4, active_hdr);
-    k_bin_fill<<<148 * 4, 256, 0, st>>>(large, cnt, ctx->large_cap, tiles_x, n_tiles, cursor, (unsigned int*)ctx->d_bins.p, ctx->bins_cap);
-    ctx->launches += 4;
-  }
-  {
-    KTimer kt(ctx, PRC_K_TILE_CAMERA);
+    KTimer kt(ctx, PRC_K_MEDIUM);
     if (ctx->nan_mode)
-      k_tile_raster<E, true><<<148 * 8, PRC_TILE * PRC_TILE, 0, st>>>(large, tile_start, (unsigned int*)ctx->d_bins.p, tiles_x, n_tiles, F.W, F.H,
-                                                                       (unsigned long long*)ctx->d_keys.p, (const TileTargets*)ctx->d_targets.p, cnt, active_hdr + 4, active_hdr);
+      k_medium_raster<E, true><<<148 * 2, 256, 0, st>>>(large, cnt, ctx->large_cap, F.W, F.H, (unsigned long long*)ctx->d_keys.p, (const TileTargets*)ctx->d_targets.p, ctx->need_bins ? 1 : 0);
     else
-    k_tile_raster<E><<<148 * 8, PRC_TILE * PRC_TILE, 0, st>>>(large, tile_start, (unsigned int*)ctx->d_bins.p, tiles_x, n_tiles, F.W, F.H,
-                                                               (unsigned long long*)ctx->d_keys.p, (const TileTargets*)ctx->d_targets.p, cnt, active_hdr + 4, active_hdr);
+      k_medium_raster<E><<<148 * 2, 256, 0, st>>>(large, cnt, ctx->large_cap, F.W, F.H, (unsigned long long*)ctx->d_keys.p, (const TileTargets*)ctx->d_targets.p, ctx->need_bins ? 1 : 0);
     ctx->launches++;
   }
-  // the queue is consumed: the next phase starts an empty one (stats were accumulated by k_scan_apply)
+  if (ctx->need_bins) {
+    const int tiles_x = (F.W + PRC_TILE - 1) / PRC_TILE, tiles_y = (F.H + PRC_TILE - 1) / PRC_TILE;
+    const int n_tiles = tiles_x * tiles_y, n_vt = n_tiles * (int)ctx->n_targets;
+    const unsigned int n_chunks = (unsigned int)((n_vt + 1 + 4095) / 4096);
+    unsigned int* tile_count = (unsigned int*)ctx->d_tilecount.p;
+    unsigned int* tile_start = (unsigned int*)ctx->d_tilestart.p;
+    unsigned int* cursor = (unsigned int*)ctx->d_cursor.p;
+    unsigned int* active_hdr = (unsigned int*)ctx->d_active.p;
+    CK(cudaMemsetAsync(tile_count, 0, (size_t)n_chunks * 4096 * 4, st));
+    CK(cudaMemsetAsync(active_hdr, 0, 16, st));
+    {
+      KTimer kt(ctx, PRC_K_BIN);
+      k_bin_count<<<148 * 4, 256, 0, st>>>(large, cnt, ctx->large_cap, tiles_x, n_tiles, tile_count);
+      k_scan_sums<<<n_chunks, 1024, 0, st>>>(tile_count, (unsigned int*)ctx->d_chunksum.p, cnt);
+      k_scan_apply<<<n_chunks, 1024, 0, st>>>(tile_count, tile_start, cursor, (const unsigned int*)ctx->d_chunksum.p, cnt, ctx->bins_cap, ctx->large_cap,
+                                              active_hdr + 4, active_hdr);
+      k_bin_fill<<<148 * 4, 256, 0, st>>>(large, cnt, ctx->large_cap, tiles_x, n_tiles, cursor, (unsigned int*)ctx->d_bins.p, ctx->bins_cap);
+      ctx->launches += 4;
+    }
+    {
+      KTimer kt(ctx, PRC_K_TILE);
+      if (ctx->nan_mode)
+        k_tile_raster<E, true><<<148 * 8, PRC_TILE * PRC_TILE, 0, st>>>(large, tile_start, (unsigned int*)ctx->d_bins.p, tiles_x, n_tiles, F.W, F.H,
+                                                                         (unsigned long long*)ctx->d_keys.p, (const TileTargets*)ctx->d_targets.p, cnt, active_hdr + 4, active_hdr);
+      else
+        k_tile_raster<E><<<148 * 8, PRC_TILE * PRC_TILE, 0, st>>>(large, tile_start, (unsigned int*)ctx->d_bins.p, tiles_x, n_tiles, F.W, F.H,
+                                                                   (unsigned long long*)ctx->d_keys.p, (const TileTargets*)ctx->d_targets.p, cnt, active_hdr + 4, active_hdr);
+      ctx->launches++;
+    }
+  }
+  // the queue is consumed: the next phase starts an empty one (stats were accumulated by the kernels above)
   CK(cudaMemsetAsync(cnt, 0, 16, st));
   CK(cudaGetLastError());
   return PRC_OK;
@@ -324,6 +359,7 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
   if (msaa_strip && !ctx->allow_msaa_strips) { ctx->err = "MSAA with a partial row range is only supported by prc_render_peer"; return PRC_ERR_UNSUPPORTED; }
   if (msaa_strip && (fr->row0 % msaa || fr->row1 % msaa)) { ctx->err = "MSAA strips must start and end on multiples of msaa"; return PRC_ERR_INVALID; }
   ctx->msaa = msaa;
+  ctx->ktimers_frame = ctx->ktimers && !(fr->flags & PRC_FRAME_NO_KERNEL_TIMERS);
   cudaStream_t st = ctx->stream;
   if (W != ctx->W || H != ctx->H || fr->n_lights != ctx->n_lights_alloc) {
     // resetBufs + initShadowMaps: new size => fresh (zero) shadow maps
@@ -572,7 +608,8 @@ static int32_t ensure_resize_tables(prc_ctx* ctx, int iw, int ih, int ow, int oh
 }
 
 template <bool E>
-int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, int phases = 3 /* bit0: forward (+resolve), bit1: deferred */) {
+int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
+                int phases = 7 /* bit0: camera raster passes, bit2: queued records + resolve, bit1: deferred shading */, int fuse = -1) {
   cudaStream_t st = ctx->stream;
   const unsigned long long* keys = (const unsigned long long*)ctx->d_keys.p;
   const uint32_t* special = (const uint32_t*)ctx->d_special.p;
@@ -580,17 +617,19 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, int phases
   const AoConsts* aoc = (const AoConsts*)ctx->d_aoc.p;
   GBuf G{(float4*)ctx->d_ga.p, (float4*)ctx->d_gb.p, (float4*)ctx->d_gc.p, (float4*)ctx->d_gd.p, ctx->any_ao ? (float*)ctx->d_ao.p : nullptr};
   // one kernel for resolve + shading when nothing reads the G-buffer afterwards (k_resolve_shade)
-  const bool fused = phases == 3 && !(fr->flags & PRC_FRAME_KEEP_GBUFFER) && !ctx->any_ao && getenv("PRC_NO_FUSED_SHADE") == nullptr;
+  // (a caller that enqueues the phases one by one — peer frames — says so with fuse = 1: nothing reads the G-buffer in between)
+  const bool fused = (phases == 7 || fuse == 1) && !(fr->flags & PRC_FRAME_KEEP_GBUFFER) && !ctx->any_ao && !ctx->no_fused_shade;
   const bool es = ctx->exact_shade;  // exact FMA in the shading-only arithmetic too (PRC_FMA=exact)
 
+  // Row ranges to rasterise and resolve: the strip (widened by the AO halo) and, for an upper strip of a frame with an AO
+  // material, rows [0, 100) as well — the colour of every uncovered pixel comes from shading pixel (0,0) (bug-list 3), whose
+  // AO rays read the depths of up to 99 rows / columns around it.
+  std::vector<std::pair<int, int>> ranges;
+  ranges.push_back({F.rr0, F.rr1});
+  if (ctx->any_ao && F.rr0 > 0) ranges.push_back({0, std::min(100, F.rr0)});
+  unsigned long long* first = (unsigned long long*)ctx->d_keys.p + (size_t)F.W * F.H;  // NaN mode: first fragment per pixel
+
   if (phases & 1) {
-    // Row ranges to rasterise and resolve: the strip (widened by the AO halo) and, for an upper strip of a frame with an AO
-    // material, rows [0, 100) as well — the colour of every uncovered pixel comes from shading pixel (0,0) (bug-list 3), whose
-    // AO rays read the depths of up to 99 rows / columns around it.
-    std::vector<std::pair<int, int>> ranges;
-    ranges.push_back({F.rr0, F.rr1});
-    if (ctx->any_ao && F.rr0 > 0) ranges.push_back({0, std::min(100, F.rr0)});
-    unsigned long long* first = (unsigned long long*)ctx->d_keys.p + (size_t)F.W * F.H;  // NaN mode: first fragment per pixel
     // clear the visibility keys of the rasterised rows (+ pixel (0,0))
     for (const auto& rg : ranges) {
       CK(cudaMemsetAsync((unsigned long long*)ctx->d_keys.p + (size_t)rg.first * F.W, 0, (size_t)(rg.second - rg.first) * F.W * 8, st));
@@ -608,6 +647,9 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, int phases
       int32_t r = raster_pass<E, false>(ctx, Fr, V0);
       if (r != PRC_OK) return r;
     }
+  }
+
+  if (phases & 4) {
     int32_t r = flush_large<E>(ctx, F);  // also rasterises what the shadow passes of this frame queued
     if (r != PRC_OK) return r;
     if (ctx->nan_mode)
@@ -617,6 +659,8 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, int phases
         ctx->launches++;
       }
     CK(cudaEventRecordWithFlags(ctx->ev[2], st, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
+    const bool stores00 = F.rr0 > 0 && ranges.size() == 1 && (fr->flags & PRC_FRAME_KEEP_GBUFFER);
+    if (!fused || stores00) {
     KTimer kt(ctx, PRC_K_RESOLVE);
     if (!fused) {
       for (const auto& rg : ranges) {
@@ -629,10 +673,11 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, int phases
       }
     }
     // k_shade_special resolves pixel (0,0) itself; only a G-buffer readback needs it STORED when it lies outside the rasterised rows
-    if (F.rr0 > 0 && ranges.size() == 1 && (fr->flags & PRC_FRAME_KEEP_GBUFFER)) {
+    if (stores00) {
       if (es) k_resolve00<E, E><<<1, 1, 0, st>>>(ctx->S, F, keys, G);
       else k_resolve00<E, false><<<1, 1, 0, st>>>(ctx->S, F, keys, G);
       ctx->launches++;
+    }
     }
   }
 
@@ -763,33 +808,44 @@ int32_t finish_timings(prc_ctx* ctx) {
   ctx->tm.n_valid_tris = ctx->n_valid;
   CK(cudaMemcpy(ctx->h_counters, ctx->d_counters.p, sizeof(Counters), cudaMemcpyDeviceToHost));
   ctx->tm.n_nan_frags = ctx->h_counters->n_nan + ctx->h_counters->n_nan_shadow;
+  // Conditions that invalidate the frame and are cured by rendering it again (every caller loops on PRC_RETRY; frames submitted
+  // back to back surface it as PRC_ERR_RETRY from prc_sync). All of them are handled in one go.
+  bool retry = false;
   if (ctx->h_counters->n_nan && !ctx->nan_mode && !getenv("PRC_NO_NAN_MODE")) {
-    // a NaN-depth fragment in the camera pass: whether it shows depends on the draw order (bug-list 8) — render the frame
-    // again with the first-fragment plane (the key buffer is reallocated by the next build_frame)
+    // a NaN-depth fragment in the camera pass: whether it shows depends on the draw order (bug-list 8) — NaN mode adds the
+    // first-fragment plane behind the keys (the stream is idle here; the frame is re-rendered from its key clear on)
     ctx->nan_mode = true;
-    ENSURE(ctx->d_keys, (size_t)ctx->W * ctx->H * 16);  // (the stream is idle: the frame is re-rendered from its key clear on)
-    ctx->spans.clear();
-    ctx->ev_used = 0;
-    return PRC_RETRY;
+    ENSURE(ctx->d_keys, (size_t)ctx->W * ctx->H * 16);
+    retry = true;
+  }
+  if (ctx->h_counters->need_bins && !ctx->need_bins) {
+    // a queued record was too large for k_medium_raster and the binned tile path was off: switch it on for good
+    ctx->need_bins = true;
+    retry = true;
   }
   if (ctx->h_counters->large_overflow) {
-    ctx->spans.clear();
-    ctx->ev_used = 0;
-    bool grown = false;
-    if (ctx->h_counters->max_bins > ctx->bins_cap) {  // grow the bin array; the caller re-renders the frame
+    if (ctx->h_counters->max_bins > ctx->bins_cap) {  // grow the bin array
       ENSURE(ctx->d_bins, (size_t)ctx->h_counters->max_bins * 5);
       ctx->bins_cap = (unsigned int)(ctx->d_bins.cap / 4);
-      grown = true;
+      retry = true;
     }
     if (ctx->h_counters->stat_large > ctx->large_cap) {  // large-triangle queue (stat_large = records pushed over the frame)
       const size_t want = (size_t)ctx->h_counters->stat_large * 5 / 4 + 1024;
       ENSURE(ctx->d_large, want * sizeof(LargeRec));
       ctx->large_cap = (unsigned int)std::min<size_t>(ctx->d_large.cap / sizeof(LargeRec), 0xFFFFFFF0u);
-      grown = true;
+      retry = true;
     }
-    if (grown) return PRC_RETRY;
-    ctx->err = "internal queue overflow (large/clip queue)";
-    return PRC_ERR_UNSUPPORTED;
+    if (!retry) {
+      ctx->spans.clear();
+      ctx->ev_used = 0;
+      ctx->err = "internal queue overflow (large/clip queue)";
+      return PRC_ERR_UNSUPPORTED;
+    }
+  }
+  if (retry) {
+    ctx->spans.clear();
+    ctx->ev_used = 0;
+    return PRC_RETRY;
   }
   ctx->tm.gpu_launches = ctx->launches;
   ctx->tm.n_large_items = ctx->h_counters->stat_large; ctx->tm.n_clipped = ctx->h_counters->stat_clip; ctx->tm.n_bin_entries = ctx->h_counters->stat_bins;
@@ -837,6 +893,13 @@ int32_t prc_open(int32_t device, prc_ctx** out) {
   const char* mode = getenv("PRC_FMA");
   ctx->exact = !(mode && strcmp(mode, "fast") == 0);
   ctx->exact_shade = mode && strcmp(mode, "exact") == 0;
+  if (cudaHostAlloc((void**)&ctx->h_list_hint, 16 * sizeof(unsigned int), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) memset(ctx->h_list_hint, 0, 16 * sizeof(unsigned int));
+  else { ctx->h_list_hint = nullptr; (void)cudaGetLastError(); }
+  ctx->no_fused_shade = getenv("PRC_NO_FUSED_SHADE") != nullptr;
+  ctx->no_chunk_cull = getenv("PRC_NO_CHUNK_CULL") != nullptr;
+  ctx->force_chunk_cull = getenv("PRC_FORCE_CHUNK_CULL") != nullptr;
+  ctx->need_bins = getenv("PRC_FORCE_BINS") != nullptr;
+  ctx->ktimers = !(getenv("PRC_NO_KTIMERS") && atoi(getenv("PRC_NO_KTIMERS")) != 0);
   if (const char* sb = getenv("PRC_SHADE_BANDS")) ctx->shade_bands = std::max(1, std::min(PRC_SHADE_BANDS_MAX, atoi(sb)));
   // AO constants (material/ao.go:28-32): a accumulates float32(Pi/4) in float32; Cos/Sin via float64.
   const float pi = 3.14159265358979323846f, q = pi / 4;
@@ -873,6 +936,7 @@ int32_t prc_close(prc_ctx* ctx) {
   for (auto& b : ctx->d_shadow_trans) free_buf(b);
   for (auto& p : ctx->h_img) if (p) { cudaHostUnregister(p); free(p); }
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+  if (ctx->h_list_hint) cudaFreeHost(ctx->h_list_hint);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   for (auto& e : ctx->evpool) cudaEventDestroy(e);
   for (auto& e : ctx->ev_band) if (e) cudaEventDestroy(e);
@@ -994,6 +1058,7 @@ static int32_t render_shadow_units(prc_ctx* ctx, const prc_frame* fr, const std:
     if (u.r1 > (int)fr->height || u.r0 < 0 || u.r0 >= u.r1) { ctx->err = "bad shadow row range"; return PRC_ERR_INVALID; }
   for (int attempt = 0; attempt < 4; attempt++) {
     ctx->launches = 0;
+    ctx->pass_slot = 0;
     CK(cudaMemsetAsync(ctx->d_counters.p, 0, offsetof(Counters, n_valid), ctx->stream));
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     r = ctx->exact ? do_shadows<true>(ctx, fr, F, units, true) : do_shadows<false>(ctx, fr, F, units, true);
@@ -1001,8 +1066,9 @@ static int32_t render_shadow_units(prc_ctx* ctx, const prc_frame* fr, const std:
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (!ctx->h_counters->large_overflow) return PRC_OK;
+    if (!ctx->h_counters->large_overflow && !(ctx->h_counters->need_bins && !ctx->need_bins)) return PRC_OK;
     bool grown = false;
+    if (ctx->h_counters->need_bins && !ctx->need_bins) { ctx->need_bins = true; grown = true; }
     if (ctx->h_counters->max_bins > ctx->bins_cap) {
       ENSURE(ctx->d_bins, (size_t)ctx->h_counters->max_bins * 5);
       ctx->bins_cap = (unsigned int)(ctx->d_bins.cap / 4);
@@ -1044,7 +1110,8 @@ int32_t prc_render_main(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out) {
   r = readback_begin(ctx, fr);
   if (r != PRC_OK) return r;
   for (int attempt = 0; attempt < 4; attempt++) {
-    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 16 + 8, ctx->stream));
+    ctx->pass_slot = 8;  // (the split-phase shadow call of this frame used the first slots)
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, offsetof(Counters, n_nan), ctx->stream));
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     r = ctx->exact ? do_main<true>(ctx, fr, F) : do_main<false>(ctx, fr, F);
     if (r != PRC_OK) return r;
@@ -1071,9 +1138,10 @@ int32_t prc_render_forward(prc_ctx* ctx, const prc_frame* fr) {
   int32_t r = build_frame(ctx, fr, F);
   if (r != PRC_OK) return r;
   ctx->rb_dst = nullptr;
-  CK(cudaMemsetAsync(ctx->d_counters.p, 0, 16 + 8, ctx->stream));
+  ctx->pass_slot = 8;
+  CK(cudaMemsetAsync(ctx->d_counters.p, 0, offsetof(Counters, n_nan), ctx->stream));
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-  return ctx->exact ? do_main<true>(ctx, fr, F, 1) : do_main<false>(ctx, fr, F, 1);
+  return ctx->exact ? do_main<true>(ctx, fr, F, 5) : do_main<false>(ctx, fr, F, 5);
 }
 
 int32_t prc_render_deferred(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out) {
@@ -1102,14 +1170,15 @@ int32_t prc_render_deferred(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out
 // the launches of one whole frame (shadow sweeps, camera pass, tile path, resolve, shading)
 static int32_t enqueue_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F) {
   const unsigned int rec = ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
+  ctx->pass_slot = 0;
   if (ctx->pending_async == 0) {
     ctx->launches = 0;
     ctx->spans.clear();
     ctx->ev_used = 0;
     CK(cudaMemsetAsync(ctx->d_counters.p, 0, offsetof(Counters, n_valid), ctx->stream));
   } else {
-    // behind unfinished asynchronous frames: keep the sticky overflow flag / statistics, reset the per-pass counters only
-    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 16, ctx->stream));
+    // behind unfinished asynchronous frames: keep the sticky overflow flag / statistics, reset the per-pass counters and list lengths only
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, offsetof(Counters, large_overflow), ctx->stream));
   }
   CK(cudaEventRecordWithFlags(ctx->ev[0], ctx->stream, rec));
   int32_t r = ctx->exact ? do_shadows<true>(ctx, fr, F, units_from_mask(fr, 0xFFFFFFFFu, 0, F.H), false)
@@ -1260,7 +1329,7 @@ int32_t prc_sync(prc_ctx* ctx) {
       const int32_t pr = peer_check(ctx);
       if (pr != PRC_OK) return pr;
     }
-    if (r == PRC_RETRY) { ctx->err = "a queue overflowed during asynchronous frames (grown now): submit them again"; return PRC_ERR_RETRY; }
+    if (r == PRC_RETRY) { ctx->err = "frames submitted back to back must be submitted again (a queue overflowed and was grown, or the binned tile path / NaN mode was switched on)"; return PRC_ERR_RETRY; }
     return r;
   }
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1342,46 +1411,22 @@ inline void peer_signal(prc_ctx* ctx, uint32_t kind, uint32_t epoch, uint32_t ma
   ctx->launches++;
 }
 
+// One frame of the group on this rank, enqueued without waiting for anything:
+//   camera pass (needs no shadow map; runs while slower peers still shade the previous frame) -> wait until nobody reads the
+//   previous frame's maps -> this rank's shadow units -> ONE pass over the queued records of both (k_medium_raster [+ bins]) -> push
+//   the non-empty texels of the owned rows into every peer's maps, signal -> wait for the peers' rows -> fused resolve + shading ->
+//   signal, copy the strip to the image consumers.
 template <bool E>
 int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, const std::vector<ShadowUnit>& units, uint32_t image_mask) {
   const PeerTable& P = ctx->peers;
   const uint32_t all = P.world >= 32 ? 0xFFFFFFFFu : ((1u << P.world) - 1u), me = 1u << P.self;
   cudaStream_t st = ctx->stream;
-  const uint32_t e = ++ctx->peer_epoch;
-  if (ctx->pending_async == 0) {
-    ctx->launches = 0;
-    ctx->spans.clear();
-    ctx->peer_spans.clear();
-    ctx->ev_used = 0;
-    CK(cudaMemsetAsync(ctx->d_counters.p, 0, offsetof(Counters, n_valid), st));
-  } else {
-    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 16, st));  // behind unfinished frames: the overflow flag and the statistics are sticky
-  }
-  // A rank that receives this frame's image tells the pushers its image buffer is free: whatever it held (the previous
-  // frame's image, if it was a consumer then) has been read by everything the caller enqueued on this stream, or finished
-  // on the host, before this call. Announcing "free up to e-1" per frame lets the consumer set change between frames.
-  if (image_mask & me) peer_signal(ctx, PRC_SIG_IMAGE_FREE, e - 1, all);
-  CK(cudaEventRecord(ctx->ev[0], st));
   const bool shadows = (fr->flags & PRC_FRAME_SHADOWMAP) && ctx->n_cast_alloc > 0 && ctx->n_cast_alloc != 0xFFFFFFFFu;
-  // PRC_PEER_ONE_FLUSH=1 (tuning, not yet measured): the large shadow triangles wait for the camera pass's tile path (one
-  // binning + tile-raster round per frame, as on one GPU) and the push follows it; default: the shadow phase flushes its own
-  // queue so that the push leaves before the camera pass.
-  static const bool one_flush = getenv("PRC_PEER_ONE_FLUSH") != nullptr && atoi(getenv("PRC_PEER_ONE_FLUSH")) != 0;
+  // everything that can fail is checked before the epoch advances: a rank that bailed out mid-frame would leave its peers
+  // waiting for signals that never come
   PushUnits U{};
   bool vec4 = true;
-  auto push_and_signal = [&]() {
-    if (U.n && P.world > 1) {
-      if (vec4) k_shadow_push<4><<<148 * 8, 256, 0, st>>>(P, U);
-      else k_shadow_push<1><<<148 * 8, 256, 0, st>>>(P, U);
-      ctx->launches++;
-    }
-    peer_signal(ctx, PRC_SIG_SHADOW, e, all);
-  };
-  if (shadows) {
-    // nobody may still be shading the previous frame from the maps this rank is about to store into
-    peer_wait(ctx, PRC_SIG_SHADED, e - 1, all);
-    int32_t r = do_shadows<E>(ctx, fr, F, units, !one_flush);
-    if (r != PRC_OK) return r;
+  if (shadows)
     for (const ShadowUnit& u : units) {
       if (u.light >= fr->n_lights || !fr->lights[u.light].cast_shadow || u.r0 >= u.r1) continue;
       if (U.n == 32) { ctx->err = "more than 32 shadow units in one prc_render_peer call"; return PRC_ERR_UNSUPPORTED; }
@@ -1390,17 +1435,46 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
       vec4 = vec4 && (U.off[U.n] % 4 == 0) && (U.cnt[U.n] % 4 == 0);
       U.n++;
     }
-    if (!one_flush) push_and_signal();
+  const uint32_t e = ++ctx->peer_epoch;
+  ctx->pass_slot = 0;
+  if (ctx->pending_async == 0) {
+    ctx->launches = 0;
+    ctx->spans.clear();
+    ctx->peer_spans.clear();
+    ctx->ev_used = 0;
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, offsetof(Counters, n_valid), st));
+  } else {
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, offsetof(Counters, large_overflow), st));  // behind unfinished frames: the overflow flag and the statistics are sticky
   }
-  CK(cudaEventRecord(ctx->ev[1], st));
+  // A rank that receives this frame's image tells the pushers its image buffer is free: whatever it held (the previous
+  // frame's image, if it was a consumer then) has been read by everything the caller enqueued on this stream, or finished
+  // on the host, before this call. Announcing "free up to e-1" per frame lets the consumer set change between frames.
+  if (image_mask & me) peer_signal(ctx, PRC_SIG_IMAGE_FREE, e - 1, all);
+  CK(cudaEventRecord(ctx->ev[0], st));
   // strip readback into the caller's (shared) host image, band by band behind the shading kernels
   ctx->rb_dst = (!(fr->flags & PRC_FRAME_NO_READBACK) && ctx->ext_img) ? ctx->ext_img : nullptr;
-  int32_t r = do_main<E>(ctx, fr, F, 1);  // camera geometry + raster + resolve: needs no shadow map, overlaps the peers' pushes
+  int32_t r = do_main<E>(ctx, fr, F, 1, 1);  // camera raster passes
   if (r != PRC_OK) return r;
-  if (shadows && one_flush) push_and_signal();
-  if (shadows) peer_wait(ctx, PRC_SIG_SHADOW, e, all);
+  CK(cudaEventRecord(ctx->ev[1], st));
+  if (shadows) {
+    // nobody may still be shading the previous frame from the maps this rank is about to store into
+    peer_wait(ctx, PRC_SIG_SHADED, e - 1, all);
+    r = do_shadows<E>(ctx, fr, F, units, false);
+    if (r != PRC_OK) return r;
+  }
+  r = do_main<E>(ctx, fr, F, 4, 1);  // queued records of the camera AND the shadow passes; G-buffer resolve when the frame is not fused
+  if (r != PRC_OK) return r;
+  if (shadows) {
+    if (U.n && P.world > 1) {
+      if (vec4) k_shadow_push<4><<<148 * 4, 256, 0, st>>>(P, U);
+      else k_shadow_push<1><<<148 * 4, 256, 0, st>>>(P, U);
+      ctx->launches++;
+    }
+    peer_signal(ctx, PRC_SIG_SHADOW, e, all);
+    peer_wait(ctx, PRC_SIG_SHADOW, e, all);
+  }
   ctx->defer_copy_join = true;
-  r = do_main<E>(ctx, fr, F, 2);
+  r = do_main<E>(ctx, fr, F, 2, 1);
   ctx->defer_copy_join = false;
   if (r != PRC_OK) return r;
   if (shadows) peer_signal(ctx, PRC_SIG_SHADED, e, all);
@@ -1606,6 +1680,48 @@ int32_t prc_render_peer(prc_ctx* ctx, const prc_frame* fr, uint32_t n, const uin
     ctx->peer_spans.clear();
     ctx->ev_used = 0;
   }
+  return PRC_OK;
+}
+
+int32_t prc_count_covered(prc_ctx* ctx, uint64_t* covered) {
+  if (!ctx || !covered) return PRC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->pending_async) { const int32_t pr_ = prc_sync(ctx); if (pr_ != PRC_OK) return pr_; }
+  if (!ctx->d_keys.p || !ctx->W) { ctx->err = "no frame rendered yet"; return PRC_ERR_INVALID; }
+  ENSURE(ctx->d_special, 16);
+  unsigned long long* out = (unsigned long long*)ctx->d_special.p + 1;  // (the second half of the 16-byte `special` block is free between frames)
+  CK(cudaMemsetAsync(out, 0, 8, ctx->stream));
+  k_count_covered<<<148 * 8, 256, 0, ctx->stream>>>((const unsigned long long*)ctx->d_keys.p, (size_t)ctx->W * ctx->H, out);
+  unsigned long long v = 0;
+  CK(cudaMemcpyAsync(&v, out, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *covered = v;
+  return PRC_OK;
+}
+
+int32_t prc_measure_fp32_peak(prc_ctx* ctx, double* tflops) {
+  if (!ctx || !tflops) return PRC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->pending_async) { const int32_t pr_ = prc_sync(ctx); if (pr_ != PRC_OK) return pr_; }
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  ENSURE(ctx->d_special, 16);
+  const int iters = 4096, grid = 148 * 8 * 4;
+  double best = 0.0;
+  for (int rep = 0; rep < 6; rep++) {  // first repetitions warm the clocks up
+    CK(cudaEventRecord(a, ctx->stream));
+    k_fma_peak<<<grid, 256, 0, ctx->stream>>>((float*)ctx->d_special.p, iters, 0.999f, 1e-3f);
+    CK(cudaEventRecord(b, ctx->stream));
+    CK(cudaEventSynchronize(b));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    const double tf = 2.0 * 16.0 * iters * 256.0 * grid / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  *tflops = best;
   return PRC_OK;
 }
 

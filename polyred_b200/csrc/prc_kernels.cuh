@@ -87,10 +87,14 @@ struct Counters {
   unsigned int n_large;
   unsigned int n_clip;
   unsigned int n_bin_total;
-  unsigned int _pad;
+  unsigned int n_huge;          // queued records too large for k_medium_raster (they need the binned tile path)
+  // per frame, also reset between frames submitted back to back: length of the compacted chunk list of the frame's k-th raster pass
+  unsigned int n_list[16];
   // per frame
   unsigned int large_overflow;  // a queue was too small: the frame is invalid and is re-rendered after growing
   unsigned int max_bins;        // largest n_bin_total of the frame (to size the bin array)
+  unsigned int need_bins;       // a huge record was queued while the binned tile path was switched off: re-render with it
+  unsigned int _pad;
   unsigned long long n_nan;         // NaN-depth fragments of the camera pass (bug-list 8; resolved by the first-fragment rule in NaN mode)
   unsigned long long n_nan_shadow;  // NaN-depth fragments of the shadow passes (counted and dropped: the one stated deviation)
   unsigned long long stat_large, stat_clip, stat_bins;
@@ -357,10 +361,12 @@ struct GeomViews {
   int r0[8], r1[8];  // rows of the shadow map this view rasterises
   const unsigned char* vis[8];  // per view: [n_chunks] 0 = no triangle of this 256-triangle chunk can touch the view's rows / screen
   int any_vis;                  // some vis[v] is set
-#if PRC_GEOM_PERSIST
-  const unsigned int* list;     // chunks visible in at least one view, compacted by k_chunk_compact (any order)
-  const unsigned int* n_list;   // their number (device memory: no host round trip)
-#endif
+  // LIST launches (partial-row views: multi-GPU strips / shadow shards): chunks visible in at least one view, compacted by
+  // k_chunk_cull_views (any order), and their number (device memory: no host round trip)
+  const unsigned int* list;
+  const unsigned int* n_list;
+  unsigned int* n_list_hint;    // page-locked host word: the host sizes the NEXT frame's grid from it (a hint, never needed for correctness)
+  unsigned int list_from;       // LIST == 2 (tail launch): first list position not covered by the direct launch
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -422,6 +428,7 @@ struct GeomSmem {
   uint32_t box[PRC_GEOM_THREADS];  // x0 | y0 << 14 | (box width - 1) << 28 of its pixel box
   unsigned short q[PRC_QCAP];      // candidate = triangle slot | pixel number within the box << 8
   unsigned int qn[2], qv[2];       // reserved / valid entries, alternating between consecutive views
+  unsigned int it;                 // LIST launches: the CTA's position in the chunk list (kept out of the 32 registers)
 };
 __constant__ unsigned short c_recip256[17] = {0, 256, 128, 86, 64, 52, 43, 37, 32, 29, 26, 24, 22, 20, 19, 18, 16};  // ceil(256 / bw): (j * r) >> 8 == j / bw for j < 16
 
@@ -512,37 +519,9 @@ __device__ __forceinline__ void geom_classify(const DevScene& S, const DevFrame&
     return;
   }
   // candidate pixels of the box (render/raster.go:481-499 / render/shadow.go:191-215) -> CTA queue
-#if PRC_WARP_QUEUE
-  // Tuning variant (build with EXTRA=-DPRC_WARP_QUEUE=1, load with PRC_LIB; NOT the default and not yet measured): one
-  // shared-memory atomicAdd per converged group of lanes instead of one per lane — ncu charged the per-lane atomic 16 % of
-  // the kernel's stall samples for 2 % of its instructions. area <= 16 fits 5 bits: the exclusive prefix over the
-  // (arbitrary) set of converged lanes is five ballots; any grouping is correct, slots only have to be disjoint.
-  unsigned int base;
-  bool group_fits;
-  {
-    const unsigned int m = __activemask(), lt = (1u << (threadIdx.x & 31)) - 1u;
-    unsigned int pre = 0, tot = 0;
-#pragma unroll
-    for (int b = 0; b < 5; b++) {
-      const unsigned int bal = __ballot_sync(m, ((unsigned int)area >> b) & 1u);
-      pre += (unsigned int)__popc(bal & lt) << b;
-      tot += (unsigned int)__popc(bal) << b;
-    }
-    const int leader = __ffs(m) - 1;
-    unsigned int wb = 0;
-    if ((int)(threadIdx.x & 31) == leader) wb = atomicAdd(&sm.qn[qsel], tot);
-    wb = __shfl_sync(m, wb, leader);
-    base = wb + pre;
-    group_fits = wb + tot <= PRC_QCAP;
-    if (group_fits && (int)(threadIdx.x & 31) == leader) atomicMax(&sm.qv[qsel], wb + tot);  // one update of the valid length per group
-  }
-#else
+  // (one shared-memory atomic per lane: a warp-aggregated reservation — five ballots for the prefix — measured 8 % slower, round 2)
   const unsigned int base = atomicAdd(&sm.qn[qsel], (unsigned int)area);
-#endif
   if (base + area <= PRC_QCAP) {
-#if PRC_WARP_QUEUE
-    if (!group_fits)
-#endif
     atomicMax(&sm.qv[qsel], base + area);
     sm.idx[threadIdx.x] = li;
     sm.box[threadIdx.x] = (uint32_t)x0 | ((uint32_t)y0 << 14) | ((uint32_t)(bw - 1) << 28);
@@ -564,26 +543,27 @@ __device__ __forceinline__ void geom_classify(const DevScene& S, const DevFrame&
 
 // __grid_constant__: the per-view arrays are indexed with a run-time view number; without it the whole parameter
 // struct is copied to local memory by every thread (ncu: 11 % of the kernel's instructions, STL at entry).
-template <bool E, bool SHADOW, bool NM = false>
+template <bool E, bool SHADOW, bool NM = false, int LIST = 0>
 __global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_raster(const __grid_constant__ DevScene S, const __grid_constant__ DevFrame F,
                                                                      const __grid_constant__ GeomViews V,
                                                                      unsigned long long* keys, LargeRec* large, unsigned int large_cap,
                                                                      unsigned int* clipq, unsigned int clip_cap, Counters* cnt, const DevFrame* Fg) {
   __shared__ GeomSmem sm;
-#if PRC_GEOM_PERSIST
-  // Tuning variant (EXTRA=-DPRC_GEOM_PERSIST=1, NOT the default, not yet measured): a few CTAs per SM loop over the compacted
-  // list of chunks that can touch some view, instead of one CTA per chunk that mostly reads its visibility byte and exits
-  // (multi-GPU strips and shadow shards: 39 k launches per pass on C3 for a few thousand visible chunks).
-  const unsigned int n_list = *V.n_list;
-  for (unsigned int it = blockIdx.x; it < n_list; it += gridDim.x) {
-  const unsigned int chunk = V.list[it];
-  __syncthreads();  // the previous chunk's shared vertices and queue are no longer read
-#define PRC_CHUNK_DONE continue
-#else
-  {
-  const unsigned int chunk = blockIdx.x;
-#define PRC_CHUNK_DONE return
-#endif
+  // LIST launches take their chunks from the compacted list of chunks that can touch some view (k_chunk_cull_views) instead of
+  // launching one CTA per chunk that mostly reads its visibility byte and exits — on C3 a strip or shadow shard of an 8-GPU
+  // frame touches a few thousand of the 39 063 chunks, and the empty CTAs alone cost 0.04 ms per pass (measured, round 2).
+  //   LIST == 1  CTA b handles list[b]; the host sizes the grid from the previous frame's list length (n_list_hint) plus a margin
+  //   LIST == 2  a small tail launch (stride loop) for list positions >= list_from, i.e. when the list outgrew that grid —
+  //              normally it finds nothing. (A stride loop in the main launch cost 25 % at 32 registers: measured, round 2.)
+  if (LIST == 1 && blockIdx.x == 0 && threadIdx.x == 0 && V.n_list_hint) *V.n_list_hint = *V.n_list;
+  if (LIST == 1 && blockIdx.x >= *V.n_list) return;
+  if (LIST == 2 && threadIdx.x == 0) sm.it = V.list_from + blockIdx.x;
+  for (;;) {
+  if (LIST == 2) {
+    __syncthreads();  // sm.it is set; the previous chunk's shared vertices and queue are no longer read
+    if (sm.it >= *V.n_list) return;
+  }
+  const unsigned int chunk = LIST == 1 ? V.list[blockIdx.x] : LIST == 2 ? V.list[sm.it] : blockIdx.x;
   const unsigned long long tri64 = (unsigned long long)chunk * PRC_GEOM_THREADS + threadIdx.x;
   const unsigned int tri = (unsigned int)tri64;
   const uint32_t li = tri64 < S.n_tris ? __ldg(S.lidx + tri) : 0xFFFFFFFFu;
@@ -596,7 +576,12 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_
     todo = 0;
     for (int v = 0; v < n_views; v++)
       if (V.vis[v] == nullptr || V.vis[v][chunk] != 0) todo |= 1u << v;
-    if (!todo) PRC_CHUNK_DONE;
+    if (!todo) {
+      if (LIST != 2) return;
+      __syncthreads();  // every thread has read sm.it
+      if (threadIdx.x == 0) sm.it += gridDim.x;
+      continue;
+    }
   }
   if (threadIdx.x == 0) { sm.qn[0] = sm.qn[1] = 0; sm.qv[0] = sm.qv[1] = 0; }
   int v = __ffs(todo) - 1, buf = 0;
@@ -637,22 +622,11 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_
     __syncthreads();
     v = vn; buf ^= 1;
   }
+    if (LIST != 2) break;
+    __syncthreads();  // every thread is done with this chunk (and has read sm.it)
+    if (threadIdx.x == 0) sm.it += gridDim.x;
   }
-#undef PRC_CHUNK_DONE
 }
-
-#if PRC_GEOM_PERSIST
-// The chunks at least one of the views can touch, compacted (warp-aggregated append; the order does not matter: depth
-// resolution by atomicMax is order-independent). vis[v] == nullptr: view v touches every chunk.
-__global__ void k_chunk_compact(const __grid_constant__ GeomViews V, int n_views, uint32_t n_chunks, unsigned int* list, unsigned int* n_list) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool hit = false;
-  if (i < n_chunks)
-    for (int v = 0; v < n_views; v++)
-      if (V.vis[v] == nullptr || V.vis[v][i] != 0) hit = true;
-  if (hit) list[warp_push(n_list)] = i;
-}
-#endif
 
 // K2: triangles straddling the viewport: clip, fan, emit (raster.go:438-443)
 template <bool E, bool NM = false>
@@ -688,11 +662,15 @@ __global__ void k_clip_raster(DevScene S, DevFrame F, const unsigned int* __rest
 // target (camera keys or a shadow map); bins are indexed by virtual tile = target * n_tiles + tile.
 //   k_bin_count -> k_scan_sums -> k_scan_apply (+ list of non-empty virtual tiles) -> k_bin_fill -> k_tile_raster
 // ---------------------------------------------------------------------------------------------
+#define PRC_MEDIUM_MAX_PIXELS 4096  // pixel-box area up to which a queued record is rasterised by one warp (k_medium_raster); larger: binned tile path
+__device__ __forceinline__ bool rec_is_huge(const LargeRec& r) { return ((int)r.bx1 - r.bx0 + 1) * ((int)r.by1 - r.by0 + 1) > PRC_MEDIUM_MAX_PIXELS; }
+
 __global__ void k_bin_count(const LargeRec* __restrict__ large, const Counters* cnt, unsigned int cap, int tiles_x, int n_tiles, unsigned int* tile_count) {
   const unsigned int n = min(cnt->n_large, cap);
   const unsigned int lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; warp < n; warp += nwarps) {
     const LargeRec r = large[warp];
+    if (!rec_is_huge(r)) continue;  // rasterised by k_medium_raster
     unsigned int* tc = tile_count + (size_t)r.target * n_tiles;
     const int tx0 = r.bx0 / PRC_TILE, tx1 = r.bx1 / PRC_TILE, ty0 = r.by0 / PRC_TILE, ty1 = r.by1 / PRC_TILE;
     const int nx = tx1 - tx0 + 1, nt = nx * (ty1 - ty0 + 1);
@@ -727,7 +705,7 @@ __device__ __forceinline__ unsigned int block_scan_1024(unsigned int local, unsi
 }
 __global__ void __launch_bounds__(1024) k_scan_sums(const unsigned int* __restrict__ in, unsigned int* chunk_sum, const Counters* cnt) {
   __shared__ unsigned int warp_sum[33];
-  if (cnt->n_large == 0) return;
+  if (cnt->n_huge == 0) return;
   const uint4 v = *reinterpret_cast<const uint4*>(in + (size_t)blockIdx.x * 4096 + threadIdx.x * 4);
   unsigned int total;
   block_scan_1024(v.x + v.y + v.z + v.w, warp_sum, total);
@@ -738,8 +716,8 @@ __global__ void __launch_bounds__(1024) k_scan_apply(const unsigned int* __restr
                                                       unsigned int* active, unsigned int* n_active) {
   __shared__ unsigned int warp_sum[33];
   __shared__ unsigned int base_s, grand_s;
-  if (cnt->n_large == 0) {  // nothing queued this frame: n_active stays 0 (host memset)
-    if (blockIdx.x == 0 && threadIdx.x == 0) { cnt->n_bin_total = 0; cnt->stat_clip += cnt->n_clip; }
+  if (cnt->n_huge == 0) {  // nothing for the tile path this frame: n_active stays 0 (host memset)
+    if (blockIdx.x == 0 && threadIdx.x == 0) cnt->n_bin_total = 0;
     return;
   }
   // offset of this chunk = sum of the previous chunk sums (gridDim.x <= 1024 chunks)
@@ -766,8 +744,8 @@ __global__ void __launch_bounds__(1024) k_scan_apply(const unsigned int* __restr
     const unsigned int total = grand_s;
     cnt->n_bin_total = total;
     if (total > cnt->max_bins) cnt->max_bins = total;
-    if (total > bins_cap || cnt->n_large > large_cap) cnt->large_overflow = 1u;
-    cnt->stat_large += cnt->n_large; cnt->stat_clip += cnt->n_clip; cnt->stat_bins += total;
+    if (total > bins_cap) cnt->large_overflow = 1u;
+    cnt->stat_bins += total;  // (stat_large / stat_clip and the queue-overflow test: k_medium_raster)
   }
 }
 __global__ void k_bin_fill(const LargeRec* __restrict__ large, const Counters* cnt, unsigned int cap, int tiles_x, int n_tiles, unsigned int* cursor,
@@ -777,6 +755,7 @@ __global__ void k_bin_fill(const LargeRec* __restrict__ large, const Counters* c
   const unsigned int lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; warp < n; warp += nwarps) {
     const LargeRec r = large[warp];
+    if (!rec_is_huge(r)) continue;
     unsigned int* cur = cursor + (size_t)r.target * n_tiles;
     const int tx0 = r.bx0 / PRC_TILE, tx1 = r.bx1 / PRC_TILE, ty0 = r.by0 / PRC_TILE, ty1 = r.by1 / PRC_TILE;
     const int nx = tx1 - tx0 + 1, nt = nx * (ty1 - ty0 + 1);
@@ -787,13 +766,63 @@ __global__ void k_bin_fill(const LargeRec* __restrict__ large, const Counters* c
   }
 }
 
+struct TileTargets { float* smap[33]; };  // [1 + k] = shadow map of the k-th casting light
+
+// Queued records (pixel box > 16 px) up to PRC_MEDIUM_MAX_PIXELS: one warp per record walks the clamped pixel box, 32 pixels at
+// a time, with the tile raster's arithmetic (bary_setup / bary_eval) and reduces straight into the target. On C3 that is every
+// queued record (47 520 per frame, 1.45 tiles each): the binned tile path — five dependent launches whose fixed cost
+// (0.034 ms of a 1.14 ms frame, 0.055 ms of an 8-GPU rank's 0.27 ms) exceeded their work — then never runs. Records above the limit
+// (a ground quad filling the screen) are counted in n_huge and left to the bins; if those are switched off (`bins_on` = 0:
+// no huge record seen so far) the frame is flagged and re-rendered with them, like a queue overflow.
+template <bool E, bool NM = false>
+__global__ void __launch_bounds__(256) k_medium_raster(const LargeRec* __restrict__ large, Counters* cnt, unsigned int cap, int W, int H,
+                                                       unsigned long long* keys, const TileTargets* __restrict__ targets, int bins_on) {
+  const unsigned int n_all = cnt->n_large, n = min(n_all, cap);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    cnt->stat_large += n_all; cnt->stat_clip += cnt->n_clip;
+    if (n_all > cap) cnt->large_overflow = 1u;
+  }
+  const unsigned int lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
+  unsigned long long nan_cam = 0, nan_sh = 0;
+  for (unsigned int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += nwarps) {
+    const LargeRec r = large[w];
+    if (rec_is_huge(r)) {
+      if (lane == 0) {
+        atomicAdd(&cnt->n_huge, 1u);
+        if (!bins_on) cnt->need_bins = 1u;
+      }
+      continue;
+    }
+    const BarySetup bs = bary_setup<E>(r.x1, r.y1, r.x2, r.y2, r.x3, r.y3);
+    const int bw = r.bx1 - r.bx0 + 1, area = bw * (r.by1 - r.by0 + 1);
+    const bool shadow = r.target != 0;
+    float* smap = shadow ? targets->smap[r.target] : nullptr;
+    for (int p = (int)lane; p < area; p += 32) {
+      const int dy = p / bw, x = r.bx0 + (p - dy * bw), y = r.by0 + dy;
+      float w1, w2, w3;
+      bary_eval<E>(bs, (float)x + 0.5f, (float)y + 0.5f, w1, w2, w3);
+      if (w1 < -PRC_EPS || w2 < -PRC_EPS || w3 < -PRC_EPS) continue;
+      const float z = w1 * r.z1 + w2 * r.z2 + w3 * r.z3;
+      const size_t idx = (size_t)y * W + x;
+      if (NM && !shadow) nan_first(keys + (size_t)W * H, idx, r.seq, z);
+      if (isnan(z)) { if (shadow) nan_sh++; else nan_cam++; continue; }
+      if (shadow) {
+        if (z > 0.0f) atomicMax((int*)&smap[idx], __float_as_int(z));
+      } else {
+        atomicMax(&keys[idx], ((unsigned long long)depth_key(z) << 32) | (unsigned long long)(0xFFFFFFFFu - r.seq));
+      }
+    }
+  }
+  if (nan_cam) atomicAdd(&cnt->n_nan, nan_cam);
+  if (nan_sh) atomicAdd(&cnt->n_nan_shadow, nan_sh);
+}
+
 struct TileRec {
   BarySetup bs;
   float z1, z2, z3;
   uint32_t seq;
   short bx0, by0, bx1, by1;
 };
-struct TileTargets { float* smap[33]; };  // [1 + k] = shadow map of the k-th casting light
 template <bool E, bool NM = false>
 __global__ void __launch_bounds__(PRC_TILE * PRC_TILE) k_tile_raster(const LargeRec* __restrict__ large, const unsigned int* __restrict__ tile_start,
                                                                       const unsigned int* __restrict__ bins, int tiles_x, int n_tiles, int W, int H,
@@ -1573,39 +1602,57 @@ __global__ void __launch_bounds__(256) k_chunk_aabb(const float* __restrict__ po
   }
 }
 
-// trans_base: [n_obj] matrices with `stride` floats between objects (F.xf -> 32, shadow_trans -> 16)
-__global__ void k_chunk_cull(const ChunkBox* __restrict__ boxes, uint32_t n_chunks, const float* __restrict__ trans_base, int stride,
-                             const float* __restrict__ viewport, int W, int H, int r0, int r1, int need_pixel00, unsigned char* vis) {
+// m: the object's matrix of this view (F.xf[obj].trans or shadow_trans[obj])
+__device__ __forceinline__ bool chunk_visible(const ChunkBox& b, const float* __restrict__ m, const float* __restrict__ viewport, int W, int r0, int r1, int need_pixel00) {
+  float xmin = 3.4e38f, xmax = -3.4e38f, ymin = 3.4e38f, ymax = -3.4e38f, wmin = 3.4e38f, wmax = -3.4e38f;
+  bool finite = true;
+  for (int k = 0; k < 8; k++) {
+    const float x = (k & 1) ? b.mx[0] : b.mn[0], y = (k & 2) ? b.mx[1] : b.mn[1], z = (k & 4) ? b.mx[2] : b.mn[2];
+    const float cx = m[0] * x + m[1] * y + m[2] * z + m[3], cy = m[4] * x + m[5] * y + m[6] * z + m[7];
+    const float cw = m[12] * x + m[13] * y + m[14] * z + m[15];
+    // Apply(Viewport).Pos(): sx = (vp00*cx + vp03*cw)/cw
+    const float sx = (viewport[0] * cx + viewport[3] * cw) / cw, sy = (viewport[5] * cy + viewport[7] * cw) / cw;
+    finite = finite && fabsf(sx) < 1e30f && fabsf(sy) < 1e30f;
+    xmin = fminf(xmin, sx); xmax = fmaxf(xmax, sx); ymin = fminf(ymin, sy); ymax = fmaxf(ymax, sy);
+    wmin = fminf(wmin, cw); wmax = fmaxf(wmax, cw);
+  }
+  // all corners strictly on one side of w = 0, with head-room against rounding
+  const float wabs = fmaxf(fabsf(wmin), fabsf(wmax));
+  const bool one_side = (wmin > 1e-4f * wabs && wmin > 0.0f) || (wmax < -1e-4f * wabs && wmax < 0.0f);
+  if (!(finite && one_side)) return true;
+  const float mx_ = 4.0f + 1e-3f * fmaxf(fmaxf(fabsf(xmin), fabsf(xmax)), fmaxf(fabsf(ymin), fabsf(ymax)));
+  const bool hit_rows = ymax + mx_ >= (float)r0 && ymin - mx_ <= (float)r1;
+  const bool hit_cols = xmax + mx_ >= 0.0f && xmin - mx_ <= (float)W;
+  const bool hit00 = need_pixel00 && xmin - mx_ <= 1.0f && ymin - mx_ <= 1.0f && xmax + mx_ >= 0.0f && ymax + mx_ >= 0.0f;
+  return (hit_rows && hit_cols) || hit00;
+}
+
+// All views of one raster pass in one launch: per view the visibility byte of every chunk, and the compacted list of the chunks
+// some view can touch (warp-aggregated append; any order: depth resolution by atomicMax is order-independent).
+struct CullViews {
+  int n;
+  const float* trans[8];   // per view: [n_obj] matrices, `stride` floats apart (F.xf -> 32, shadow_trans -> 16)
+  int stride;
+  int r0[8], r1[8];
+  int test[8];             // 0: the view takes every chunk (all rows, culling not forced)
+  int need_pixel00;
+  unsigned char* vis[8];
+};
+__global__ void __launch_bounds__(256) k_chunk_cull_views(const ChunkBox* __restrict__ boxes, uint32_t n_chunks, const __grid_constant__ CullViews C,
+                                                          const float* __restrict__ viewport, int W, unsigned int* list, unsigned int* n_list) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_chunks) return;
-  const ChunkBox b = boxes[i];
-  unsigned char v = 1;
-  if (!b.mixed && b.mn[0] > -3e38f && b.mx[0] < 3e38f && b.mn[1] > -3e38f && b.mx[1] < 3e38f && b.mn[2] > -3e38f && b.mx[2] < 3e38f) {
-    const float* m = trans_base + (size_t)b.obj * stride;
-    float xmin = 3.4e38f, xmax = -3.4e38f, ymin = 3.4e38f, ymax = -3.4e38f, wmin = 3.4e38f, wmax = -3.4e38f;
-    bool finite = true;
-    for (int k = 0; k < 8; k++) {
-      const float x = (k & 1) ? b.mx[0] : b.mn[0], y = (k & 2) ? b.mx[1] : b.mn[1], z = (k & 4) ? b.mx[2] : b.mn[2];
-      const float cx = m[0] * x + m[1] * y + m[2] * z + m[3], cy = m[4] * x + m[5] * y + m[6] * z + m[7];
-      const float cw = m[12] * x + m[13] * y + m[14] * z + m[15];
-      // Apply(Viewport).Pos(): sx = (vp00*cx + vp03*cw)/cw
-      const float sx = (viewport[0] * cx + viewport[3] * cw) / cw, sy = (viewport[5] * cy + viewport[7] * cw) / cw;
-      finite = finite && fabsf(sx) < 1e30f && fabsf(sy) < 1e30f;
-      xmin = fminf(xmin, sx); xmax = fmaxf(xmax, sx); ymin = fminf(ymin, sy); ymax = fmaxf(ymax, sy);
-      wmin = fminf(wmin, cw); wmax = fmaxf(wmax, cw);
-    }
-    // all corners strictly on one side of w = 0, with head-room against rounding
-    const float wabs = fmaxf(fabsf(wmin), fabsf(wmax));
-    const bool one_side = (wmin > 1e-4f * wabs && wmin > 0.0f) || (wmax < -1e-4f * wabs && wmax < 0.0f);
-    if (finite && one_side) {
-      const float mx_ = 4.0f + 1e-3f * fmaxf(fmaxf(fabsf(xmin), fabsf(xmax)), fmaxf(fabsf(ymin), fabsf(ymax)));
-      const bool hit_rows = ymax + mx_ >= (float)r0 && ymin - mx_ <= (float)r1;
-      const bool hit_cols = xmax + mx_ >= 0.0f && xmin - mx_ <= (float)W;
-      const bool hit00 = need_pixel00 && xmin - mx_ <= 1.0f && ymin - mx_ <= 1.0f && xmax + mx_ >= 0.0f && ymax + mx_ >= 0.0f;
-      v = ((hit_rows && hit_cols) || hit00) ? 1 : 0;
+  bool any = false;
+  if (i < n_chunks) {
+    const ChunkBox b = boxes[i];
+    const bool testable = !b.mixed && b.mn[0] > -3e38f && b.mx[0] < 3e38f && b.mn[1] > -3e38f && b.mx[1] < 3e38f && b.mn[2] > -3e38f && b.mx[2] < 3e38f;
+    for (int v = 0; v < C.n; v++) {
+      bool vis = true;
+      if (C.test[v] && testable) vis = chunk_visible(b, C.trans[v] + (size_t)b.obj * C.stride, viewport, W, C.r0[v], C.r1[v], C.need_pixel00);
+      C.vis[v][i] = vis ? 1 : 0;
+      any = any || vis;
     }
   }
-  vis[i] = v;
+  if (any) list[warp_push(n_list)] = i;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1703,6 +1750,30 @@ __global__ void k_validate(const float* __restrict__ pos, const uint64_t* __rest
   }
   meta[i] = lo | (valid ? 0u : 0x80000000u);
   if (valid) atomicAdd(n_valid, 1ULL);
+}
+
+// covered pixels of the last frame (visibility key != 0), for the coverage-weighted roofline of the measurement harness
+__global__ void __launch_bounds__(256) k_count_covered(const unsigned long long* __restrict__ keys, size_t n, unsigned long long* out) {
+  unsigned int c = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) c += keys[i] != 0 ? 1u : 0u;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+
+// FP32 FMA micro-benchmark (the roofline of the shading kernels is the FP32 pipe, measured on the box because
+// MEASURED_PEAKS.json has no FP32 entry): 16 independent chains per thread, `iters` x 16 FMAs, nothing else in the loop.
+__global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float a, float b) {
+  float x[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) x[k] = (float)(threadIdx.x + k) * 1e-3f;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = __fmaf_rn(x[k], a, b);
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 16; k++) s += x[k];
+  if (s == 123.456f) out[0] = s;  // never true: keeps the chains alive
 }
 
 }  // namespace prc

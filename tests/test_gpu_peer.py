@@ -53,12 +53,22 @@ def _group(s, cam, w, h, devices):
 def _run(devices, frames=3, size=(480, 272), scene=None):
     s, cam, w, h = _scene(*size) if scene is None else (*scene, *size)
     ref = render.NewRenderer(*_opts(s, cam, w, h), render.CUDA(devices[0])).Render().copy()
+    from polyred_b200._lib import PolyredCudaError
     rs, fds, mine = _group(s, cam, w, h, devices)
-    for _ in range(frames):
-        for k, r in enumerate(rs):
-            r._backend.render_peer(fds[k], mine[k], 1)
-    for r in rs:
-        r._backend.sync()
+    for attempt in range(4):
+        for _ in range(frames):
+            for k, r in enumerate(rs):
+                r._backend.render_peer(fds[k], mine[k], 1)
+        again = False
+        for r in rs:
+            try:
+                r._backend.sync()
+            except PolyredCudaError as e:  # a queue grew / the binned tile path or NaN mode was switched on: every rank submits again
+                assert e.code == A.PRC_ERR_RETRY
+                again = True
+        if not again:
+            break
+    assert not again
     out = rs[0]._backend.read_image(w, h)
     for r in rs:
         r._backend.peer_disconnect()

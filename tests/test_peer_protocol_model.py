@@ -24,13 +24,12 @@ def frame_ops(rank, world, e, mask, shadows=True):
     ops = []
     if mask & me:
         ops.append(("signal", IMAGE_FREE, e - 1, others))
+    ops.append(("forward", e))  # the camera pass needs no shadow map: it runs while slower peers still shade frame e-1
     if shadows:
         ops.append(("wait", SHADED, e - 1, others))
         ops.append(("raster_shadow", e))
         ops.append(("push", e))
         ops.append(("signal", SHADOW, e, others))
-    ops.append(("forward", e))
-    if shadows:
         ops.append(("wait", SHADOW, e, others))
     ops.append(("shade", e))
     if shadows:

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Multi-GPU probe of the peer-memory path (run under gpurun --gpus N): bit-identity check, then bench.py --mgpu peer in a few
 # variants (default library, traced, tuning builds given as extra arguments: name=path pairs).
-# usage: tools/peer_probe.sh N [steps] [name=lib.so ...]
+# usage: tools/peer_probe.sh N [steps] [name=ENV=VAL,ENV=VAL ...]   e.g. persist=PRC_LIB=polyred_b200/csrc/variants/lib_persist.so
 N=$1; STEPS=${2:-40}; shift 2
 OUT=gpurun_out
 mkdir -p $OUT
@@ -24,6 +24,7 @@ timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 grep "multigpu_check\|Error\|error" $OUT/multigpu_check_$N.log | head -20
 run default A=1
 run traced PRC_PEER_TRACE=1
-for kv in "$@"; do
-  run "${kv%%=*}" PRC_LIB=$PWD/${kv#*=}
+for kv in "$@"; do   # name=ENV1=V1,ENV2=V2 (a value starting with lib: is a library path relative to the repo)
+  name=${kv%%=*}; envs=${kv#*=}
+  run "$name" $(echo "$envs" | tr ',' ' ' | sed "s#PRC_LIB=#PRC_LIB=$PWD/#")
 done
