@@ -314,7 +314,7 @@ def run_cuda(args):
                 step(fd, None)
             barrier()
             costs = pf.rebalance()
-            balance_log.append({"shadow_ms": [round(c[0] / 2, 4) for c in costs], "main_ms": [round(c[1] / 2, 4) for c in costs]})
+            balance_log.append({"raster_ms": [round(c[0] / 2, 4) for c in costs], "shade_ms": [round(c[1] / 2, 4) for c in costs]})
         for _ in range(2):
             step(fd, None)
         barrier()
@@ -440,21 +440,20 @@ def run_cuda(args):
     # ---- roofline of the dominant kernel class (this rank's launches, this rank's share of the algorithmic bytes) ----
     dom = int(np.argmax(ksum))
     if pf is not None:
-        own_rows = pf.rows[rank][1] - pf.rows[rank][0]
-        own_shadow_rows = pf.sh_bounds[rank + 1] - pf.sh_bounds[rank]
+        # peer groups: the raster passes take 1/N of the triangles (every row), the shading its strip of rows
+        f_img = (pf.rows[rank][1] - pf.rows[rank][0]) / h
+        f_sh = f_cam = 1.0 / world
     elif df is not None:
-        own_rows = df.rows[rank][1] - df.rows[rank][0]
-        own_shadow_rows = sum(b - a for _, a, b, owner in units if owner == rank)
+        f_img = f_cam = (df.rows[rank][1] - df.rows[rank][0]) / h       # this rank's share of the screen rows
+        f_sh = sum(b - a for _, a, b, owner in units if owner == rank) / max(1, len(cast) * h)  # ... of the stacked shadow-map rows
     else:
-        own_rows, own_shadow_rows = h, len(cast) * h
-    f_img = own_rows / h                                    # this rank's share of the screen rows
-    f_sh = own_shadow_rows / max(1, len(cast) * h)          # ... of the stacked shadow-map rows
+        f_img = f_sh = f_cam = 1.0
     sweeps = max(1, int(round(klaunch[0] / args.steps)))    # shadow sweeps per frame on this rank (up to 8 views share one)
     # 1 GPU / peer frames without an AO material: resolve and shading run as ONE kernel (k_resolve_shade, timed in the "shade"
     # class); it is charged the algorithmic bytes of both stages, G-buffer round trip included
     one_kernel_shade = (world == 1 or pf is not None) and not os.environ.get("PRC_NO_FUSED_SHADE") and not any_ao
     shade_bytes = f_img * ((64 + 4 + 4 * len(cast)) * px + ((8 + 64) * px if one_kernel_shade else 0))
-    per_launch_bytes = {0: f_sh * len(cast) * (36 * n_tris + 8 * px) / sweeps, 1: f_img * (112 * n_tris + 16 * px), 6: f_img * (8 + 64) * px, 7: shade_bytes}
+    per_launch_bytes = {0: f_sh * len(cast) * (36 * n_tris + 8 * px) / sweeps, 1: f_cam * (112 * n_tris + 16 * px), 6: f_img * (8 + 64) * px, 7: shade_bytes}
     alg = per_launch_bytes.get(dom, 0.0)
     launches_per_step = float(klaunch[dom]) / args.steps
     avg_ms = ksum[dom] / max(1, klaunch[dom])
@@ -483,7 +482,7 @@ def run_cuda(args):
                            else "K frames back to back (prc_render_peer), one prc_sync inside the timed bracket" if pf is not None
                            else "one synchronous call per frame"),
                 "partition": "1 GPU" if world == 1
-                else f"{world} screen strips + shadow shards by rows; non-empty shadow texels and image strips pushed over NVLink peer memory by the library (no collective, no host wait inside a frame), image on rank 0" if pf is not None
+                else f"raster passes (camera + all shadow lights): 1/{world} of the triangles per rank into private buffers, merged into the peers with atomicMax over NVLink peer memory (shadow texels into every rank, visibility keys into the rank shading the row); shading: {world} screen strips balanced by measured time; image strips copied to rank 0; no collective, no host wait inside a frame" if pf is not None
                 else f"{world} screen strips + {len(units)} shadow shards (one in-place NCCL all-gather overlapped with the camera pass, one in-place all-gather of the image strips)",
                 "kernel_timings": kernel_pass},
         "roofline": {"bound": "hbm", "kernel": ("resolve_shade (k_resolve_shade, one kernel)" if (dom == 7 and one_kernel_shade) else names[dom]), "achieved": achieved, "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s",
@@ -516,7 +515,6 @@ def run_cuda(args):
     }
     if pf is not None:
         line["run"]["strip_rows"] = [r1_ - r0_ for r0_, r1_ in pf.rows]
-        line["run"]["shadow_rows_per_rank"] = [b_ - a_ for a_, b_ in zip(pf.sh_bounds, pf.sh_bounds[1:])]
         line["balance_rounds"] = balance_log
         line["peer_wait_ms_per_step_rank0"] = {k: v / args.steps for k, v in peer_wait.items()} if peer_wait else None
         pf.close()

@@ -215,7 +215,8 @@ typedef struct prc_timings {
 
 #define PRC_K_GEOM_SHADOW 0
 #define PRC_K_GEOM_CAMERA 1
-#define PRC_K_CLIP 2
+#define PRC_K_CLIP 2      /* (timed inside the camera pass's bracket) */
+#define PRC_K_EXCHANGE 2  /* peer groups: k_peer_push */
 #define PRC_K_BIN 3
 #define PRC_K_MEDIUM 4
 #define PRC_K_TILE 5
@@ -303,6 +304,8 @@ typedef struct prc_peer_handle {
   uint64_t shadow_off, image_off, signals_off;  /* offsets of those buffers inside their IPC allocations */
   uint64_t shadow_bytes, image_bytes;           /* capacities; all ranks of a group must agree */
   uint8_t shadow_ipc[64], image_ipc[64], signals_ipc[64]; /* cudaIpcMemHandle_t */
+  uint64_t mkeys_ptr, mkeys_off, mkeys_bytes;   /* the merged visibility-key planes (2 frame parities + 2 NaN-mode planes) */
+  uint8_t mkeys_ipc[64];
 } prc_peer_handle;
 
 /* Allocates this context's buffers for `frame` (size, casting lights), zeroes its signal words and fills `out`.
@@ -311,8 +314,10 @@ int32_t prc_peer_export(prc_ctx* ctx, const prc_frame* frame, prc_peer_handle* o
 /* `all` = the world's handles in rank order (all[rank] is this context's own). world <= 16. */
 int32_t prc_peer_connect(prc_ctx* ctx, uint32_t rank, uint32_t world, const prc_peer_handle* all);
 int32_t prc_peer_disconnect(prc_ctx* ctx);
-int32_t prc_render_peer(prc_ctx* ctx, const prc_frame* frame, uint32_t n_units, const uint32_t* light, const uint32_t* row0,
-                        const uint32_t* row1, uint32_t image_mask);
+/* row0[p], row1[p]: the strip of screen rows rank p shades, for every rank of the group (n_ranks = world; this rank's entry
+ * must equal frame->row0/row1; every strip needs at least one row). */
+int32_t prc_render_peer(prc_ctx* ctx, const prc_frame* frame, uint32_t n_ranks, const uint32_t* row0, const uint32_t* row1,
+                        uint32_t image_mask);
 /* With PRC_PEER_TRACE=1 in the environment at prc_peer_connect: milliseconds this context's stream spent in the device-side
  * waits of the frames finished by the last prc_sync, per signal kind: [0] peers' shadow rows, [1] peers done shading the
  * previous frame, [2] strips arriving in this rank's image, [3] consumers done with the previous image. Zeros otherwise. */
@@ -324,6 +329,15 @@ int32_t prc_peer_wait_ms(prc_ctx* ctx, float out[4]);
  * ptr == NULL unregisters. */
 int32_t prc_set_host_image(prc_ctx* ctx, void* ptr, uint64_t bytes);
 
+/* Sticky per-context render state that a frame can switch on (the reporting frame is re-rendered, PRC_ERR_RETRY for frames submitted
+ * back to back): NaN mode (a camera pass produced a NaN-depth fragment: the first-fragment plane of bug-list 8 is maintained from then
+ * on) and the binned tile path (a queued triangle was too large for the one-warp raster). The ranks of a peer group must agree on
+ * NaN mode — the first fragment of a pixel may come from any rank — so after a PRC_ERR_RETRY the host ORs the ranks' states and
+ * sets the result on every rank before the frames are submitted again (polyred_b200/distributed.py PeerFrames.finish). */
+#define PRC_STATE_NAN_MODE 1u
+#define PRC_STATE_TILE_PATH 2u
+int32_t prc_frame_state(prc_ctx* ctx, uint32_t* state);
+int32_t prc_set_frame_state(prc_ctx* ctx, uint32_t state);
 /* Number of covered pixels (Fragment.Ok, buffer/buffer.go:209-219) of the rows this context rasterised in its last frame —
  * for the coverage-weighted roofline of the measurement harness. */
 int32_t prc_count_covered(prc_ctx* ctx, uint64_t* covered);

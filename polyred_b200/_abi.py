@@ -172,10 +172,14 @@ class prc_peer_handle(C.Structure):
         ("shadow_ipc", C.c_uint8 * 64),
         ("image_ipc", C.c_uint8 * 64),
         ("signals_ipc", C.c_uint8 * 64),
+        ("mkeys_ptr", C.c_uint64),
+        ("mkeys_off", C.c_uint64),
+        ("mkeys_bytes", C.c_uint64),
+        ("mkeys_ipc", C.c_uint8 * 64),
     ]
 
 
-KERNEL_CLASSES = ("geom_raster_shadow", "geom_raster_camera", "clip", "binning", "medium_raster", "tile_raster", "resolve", "shade")
+KERNEL_CLASSES = ("geom_raster_shadow", "geom_raster_camera", "peer_push", "binning", "medium_raster", "tile_raster", "resolve", "shade")
 
 
 def pack_rgba(c) -> int:

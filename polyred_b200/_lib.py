@@ -56,7 +56,9 @@ def lib():
         L.prc_peer_export.argtypes = [vp, C.POINTER(A.prc_frame), C.POINTER(A.prc_peer_handle)]
         L.prc_peer_connect.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(A.prc_peer_handle)]
         L.prc_peer_disconnect.argtypes = [vp]
-        L.prc_render_peer.argtypes = [vp, C.POINTER(A.prc_frame), C.c_uint32, vp, vp, vp, C.c_uint32]
+        L.prc_render_peer.argtypes = [vp, C.POINTER(A.prc_frame), C.c_uint32, vp, vp, C.c_uint32]
+        L.prc_frame_state.argtypes = [vp, C.POINTER(C.c_uint32)]
+        L.prc_set_frame_state.argtypes = [vp, C.c_uint32]
         L.prc_set_exact_fma.argtypes = [vp, C.c_int32]
         L.prc_set_host_image.argtypes = [vp, vp, C.c_uint64]
         L.prc_peer_wait_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]
@@ -67,7 +69,7 @@ def lib():
                      "prc_render_shadows", "prc_render_main", "prc_stream", "prc_sync", "prc_host_image", "prc_render_forward",
                      "prc_render_deferred", "prc_device_shadow_all", "prc_render_shadow_units", "prc_peer_export", "prc_peer_connect",
                      "prc_peer_disconnect", "prc_render_peer", "prc_set_exact_fma", "prc_read_image", "prc_set_host_image", "prc_peer_wait_ms",
-                     "prc_measure_fp32_peak", "prc_count_covered"):
+                     "prc_measure_fp32_peak", "prc_count_covered", "prc_frame_state", "prc_set_frame_state"):
             getattr(L, name).restype = C.c_int32
         if L.prc_abi_version() != A.PRC_ABI_VERSION:
             raise PolyredCudaError(A.PRC_ERR_INVALID, "ABI version mismatch")
@@ -229,16 +231,28 @@ class CudaBackend(Backend):
         self._check(self.L.prc_set_host_image(self.h, address, nbytes))
 
     @staticmethod
-    def unit_arrays(units):
-        """[(light, row0, row1)] -> the three contiguous uint32 arrays prc_render_peer takes (build once, submit many frames)."""
-        n = len(units)
-        a = np.array(units, dtype=np.uint32).reshape(n, 3)
-        return n, tuple(np.ascontiguousarray(a[:, k]) for k in range(3))
+    def row_arrays(rows):
+        """[(row0, row1)] of every rank -> the two contiguous uint32 arrays prc_render_peer takes (build once, submit many frames)."""
+        a = np.array(rows, dtype=np.uint32).reshape(len(rows), 2)
+        return len(rows), (np.ascontiguousarray(a[:, 0]), np.ascontiguousarray(a[:, 1]))
 
     def render_peer_arrays(self, fd, n, arrays, image_mask: int = 1):
-        li, r0, r1 = arrays
-        self._check(self.L.prc_render_peer(self.h, C.byref(fd.struct), n, li.ctypes.data if n else None, r0.ctypes.data if n else None,
-                                           r1.ctypes.data if n else None, image_mask))
+        r0, r1 = arrays
+        self._check(self.L.prc_render_peer(self.h, C.byref(fd.struct), n, r0.ctypes.data, r1.ctypes.data, image_mask))
+
+    def render_peer(self, fd, rows, image_mask: int = 1):
+        """Submit one frame of the group without waiting. rows: the strip (row0, row1) of EVERY rank, in rank order (this rank's
+        entry must be fd's row0/row1)."""
+        n, arrays = self.row_arrays(rows)
+        self.render_peer_arrays(fd, n, arrays, image_mask)
+
+    def frame_state(self) -> int:
+        out = C.c_uint32(0)
+        self._check(self.L.prc_frame_state(self.h, C.byref(out)))
+        return int(out.value)
+
+    def set_frame_state(self, state: int):
+        self._check(self.L.prc_set_frame_state(self.h, state))
 
     def covered_pixels(self, w=None, h=None) -> int:
         """Covered pixels (visibility key set) of the last frame rendered by this context."""
@@ -257,11 +271,3 @@ class CudaBackend(Backend):
         out = (C.c_float * 4)()
         self._check(self.L.prc_peer_wait_ms(self.h, C.byref(out)))
         return dict(zip(("shadow_rows", "peers_shaded", "image_strips", "image_free"), (float(x) for x in out)))
-
-    def render_peer(self, fd, units, image_mask: int = 1):
-        """Submit one frame of the group without waiting (units: this rank's [(light, row0, row1)])."""
-        n = len(units)
-        a = np.array(units, dtype=np.uint32).reshape(n, 3)
-        li, r0, r1 = (np.ascontiguousarray(a[:, k]) for k in range(3))
-        self._check(self.L.prc_render_peer(self.h, C.byref(fd.struct), n, li.ctypes.data if n else None, r0.ctypes.data if n else None,
-                                           r1.ctypes.data if n else None, image_mask))

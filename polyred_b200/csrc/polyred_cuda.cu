@@ -66,6 +66,14 @@ struct prc_ctx {
   // multi-GPU exchange is a single in-place all-gather; shadow_ptr[i] is light i's map or nullptr
   DBuf d_shadow_all;
   std::vector<float*> shadow_ptr;
+  // Peer groups (prc_render_peer): the raster passes of a rank cover its share of the triangles and write PRIVATE buffers — d_keys
+  // and d_shadow_mine (same layout as d_shadow_all) — which k_peer_push merges into every rank's d_shadow_all / d_mkeys
+  // (merged visibility keys: 2 frame parities x [H][W], + 2 NaN-mode planes); shading reads the merged ones.
+  DBuf d_shadow_mine, d_mkeys;
+  bool peer_private = false;               // connected: raster targets are the private buffers
+  uint32_t part_rank = 0, part_world = 1;  // while a peer frame's raster passes are enqueued: this rank's share of the chunks
+  unsigned long long* keys_shade = nullptr;   // while a peer frame is enqueued: the merged key plane of this frame (nullptr: d_keys)
+  unsigned long long* first_shade = nullptr;  // ... and its NaN-mode plane
   uint32_t n_cast_alloc = 0;
   unsigned int large_cap = 0, clip_cap = 0, bins_cap = 0;
   AoConsts ao{};
@@ -174,6 +182,30 @@ void free_buf(DBuf& b) {
   b.cap = 0;
 }
 
+// where the shadow raster of light i writes: the map itself, or this rank's private copy in a peer group
+inline float* raster_map(prc_ctx* ctx, uint32_t i) {
+  float* m = ctx->shadow_ptr[i];
+  if (!m || !ctx->peer_private) return m;
+  return (float*)ctx->d_shadow_mine.p + (m - (float*)ctx->d_shadow_all.p);
+}
+
+// Rows a context rasterises / resolves for the strip [row0, row1) it shades (screen rows of the frame buffer): the strip widened by
+// the MSAA filter reach and the AO halo, and — for an upper strip of a frame with an AO material — rows [0, ax1) as well (see do_main)
+inline void row_needs(bool any_ao, int msaa, bool msaa_strip, int H, int row0, int row1, int& s0, int& s1, int& rr0, int& rr1, int& ax1) {
+  s0 = row0; s1 = row1;
+  if (msaa_strip) {
+    // output row y of imageutil.Resize reads supersampled rows [msaa*y - msaa, msaa*y + 2*msaa): shade that much beyond the strip
+    s0 = std::max(0, row0 - msaa);
+    s1 = std::min(H, row1 + msaa);
+  }
+  // AO marches up to 99 pixels from the shaded pixel (material/ao.go:44-46): widen the rasterised rows
+  const int halo = any_ao ? 100 : 0;
+  rr0 = std::max(0, s0 - halo);
+  rr1 = std::min(H, s1 + halo);
+  if (any_ao && rr0 <= 100) rr0 = 0;  // rows [0, 100) are needed for pixel (0,0)'s AO anyway: keep one contiguous range
+  ax1 = (any_ao && rr0 > 0) ? std::min(100, rr0) : 0;
+}
+
 // CUDA-event bracket around one kernel class (timed on the launching stream)
 struct KTimer {
   prc_ctx* ctx;
@@ -220,7 +252,16 @@ int32_t raster_pass(prc_ctx* ctx, const DevFrame& F, const GeomViews& Vin) {
   GeomViews V = Vin;
   bool list_mode = false;
   unsigned int grid = cdiv(ctx->S.n_tris, PRC_GEOM_THREADS);
-  if (ctx->S.n_tris && !ctx->no_chunk_cull) {
+  const bool part = ctx->part_world > 1;  // a rank of a peer group: its share of the chunks, every row
+  if (part) {
+    const unsigned int nb = cdiv(ctx->n_chunks, PRC_PART_BLOCK);  // blocks of chunks, dealt round-robin
+    const unsigned int mine = ctx->part_rank < nb ? cdiv(nb - ctx->part_rank, ctx->part_world) : 0u;
+    grid = std::max(1u, mine * PRC_PART_BLOCK);
+    V.part_first = ctx->part_rank * PRC_PART_BLOCK;
+    V.part_stride = ctx->part_world * PRC_PART_BLOCK;
+    V.n_chunks = ctx->n_chunks;
+  }
+  if (ctx->S.n_tris && !ctx->no_chunk_cull && !part) {
     // chunk culling pays when a view covers only part of the rows (multi-GPU strips / shadow shards): one launch tests every
     // view of the pass and compacts the chunks some view can touch; the geometry grid then walks that list
     CullViews C{};
@@ -268,12 +309,16 @@ int32_t raster_pass(prc_ctx* ctx, const DevFrame& F, const GeomViews& Vin) {
     bool done = false;
     if constexpr (!SHADOW) {
       if (ctx->nan_mode) {
-        if (list_mode) { PRC_LAUNCH_GEOM(true, 1, grid); if (tail) PRC_LAUNCH_GEOM(true, 2, 148u); } else PRC_LAUNCH_GEOM(true, 0, grid);
+        if (list_mode) { PRC_LAUNCH_GEOM(true, 1, grid); if (tail) PRC_LAUNCH_GEOM(true, 2, 148u); }
+        else if (part) PRC_LAUNCH_GEOM(true, 3, grid);
+        else PRC_LAUNCH_GEOM(true, 0, grid);
         done = true;
       }
     }
     if (!done) {
-      if (list_mode) { PRC_LAUNCH_GEOM(false, 1, grid); if (tail) PRC_LAUNCH_GEOM(false, 2, 148u); } else PRC_LAUNCH_GEOM(false, 0, grid);
+      if (list_mode) { PRC_LAUNCH_GEOM(false, 1, grid); if (tail) PRC_LAUNCH_GEOM(false, 2, 148u); }
+      else if (part) PRC_LAUNCH_GEOM(false, 3, grid);
+      else PRC_LAUNCH_GEOM(false, 0, grid);
     }
 #undef PRC_LAUNCH_GEOM
     ctx->launches += tail ? 2 : 1;
@@ -470,7 +515,7 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
   if (!resident) {
     ctx->h_targets = TileTargets{};
     for (uint32_t i = 0; i < fr->n_lights && i < 64; i++)
-      if (ctx->target_of_light[i]) ctx->h_targets.smap[ctx->target_of_light[i]] = ctx->shadow_ptr[i];
+      if (ctx->target_of_light[i]) ctx->h_targets.smap[ctx->target_of_light[i]] = raster_map(ctx, i);
     UPLOAD(ctx->d_targets, &ctx->h_targets, sizeof(TileTargets));
   }
   if (!resident) {
@@ -480,18 +525,12 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
   ctx->uniforms_valid = true;
   F.W = W; F.H = H;
   F.cullW = (float)(msaa * W); F.cullH = (float)(msaa * H);
-  F.row0 = fr->row0; F.row1 = fr->row1;
   ctx->own_row0 = (int)fr->row0; ctx->own_row1 = (int)fr->row1;
-  if (msaa_strip) {
-    // output row y of imageutil.Resize reads supersampled rows [msaa*y - msaa, msaa*y + 2*msaa): shade that much beyond the strip
-    F.row0 = (uint32_t)std::max(0, (int)fr->row0 - msaa);
-    F.row1 = (uint32_t)std::min(H, (int)fr->row1 + msaa);
+  {
+    int s0, s1, rr0, rr1, ax1;
+    row_needs(ctx->any_ao, msaa, msaa_strip, H, (int)fr->row0, (int)fr->row1, s0, s1, rr0, rr1, ax1);
+    F.row0 = s0; F.row1 = s1; F.rr0 = rr0; F.rr1 = rr1;
   }
-  // AO marches up to 99 pixels from the shaded pixel (material/ao.go:44-46): widen the rasterised rows
-  const int halo = ctx->any_ao ? 100 : 0;
-  F.rr0 = std::max(0, (int)F.row0 - halo);
-  F.rr1 = std::min(H, (int)F.row1 + halo);
-  if (ctx->any_ao && F.rr0 <= 100) F.rr0 = 0;  // rows [0, 100) are needed for pixel (0,0)'s AO anyway (see do_main): keep one contiguous range
   F.flags = fr->flags;
   F.n_lights = fr->n_lights; F.n_ambient = fr->n_ambient;
   F.background = fr->background_rgba;
@@ -541,7 +580,7 @@ int32_t do_shadows(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, const s
     if (i >= fr->n_lights || !fr->lights[i].cast_shadow || u.r0 >= u.r1) continue;
     if (ctx->light_affine[i & 63]) V.affine |= 1u << V.n;
     V.trans[V.n] = (const float*)ctx->d_shadow_trans[i].p;
-    V.smap[V.n] = ctx->shadow_ptr[i];
+    V.smap[V.n] = raster_map(ctx, i);
     V.target[V.n] = ctx->target_of_light[i];
     V.r0[V.n] = u.r0;
     V.r1[V.n] = u.r1;
@@ -609,16 +648,19 @@ static int32_t ensure_resize_tables(prc_ctx* ctx, int iw, int ih, int ow, int oh
 
 template <bool E>
 int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
-                int phases = 7 /* bit0: camera raster passes, bit2: queued records + resolve, bit1: deferred shading */, int fuse = -1) {
+                int phases = 15 /* bit0: camera raster passes, bit2: queued records, bit3: NaN fix + G-buffer resolve, bit1: deferred shading */,
+                int fuse = -1) {
   cudaStream_t st = ctx->stream;
-  const unsigned long long* keys = (const unsigned long long*)ctx->d_keys.p;
+  // the raster passes write d_keys; resolve and shading read the same plane, or — peer frames — the merged plane of the group
+  unsigned long long* keys_w = ctx->keys_shade ? ctx->keys_shade : (unsigned long long*)ctx->d_keys.p;
+  const unsigned long long* keys = keys_w;
   const uint32_t* special = (const uint32_t*)ctx->d_special.p;
   uint32_t* image = (uint32_t*)ctx->d_image.p;
   const AoConsts* aoc = (const AoConsts*)ctx->d_aoc.p;
   GBuf G{(float4*)ctx->d_ga.p, (float4*)ctx->d_gb.p, (float4*)ctx->d_gc.p, (float4*)ctx->d_gd.p, ctx->any_ao ? (float*)ctx->d_ao.p : nullptr};
   // one kernel for resolve + shading when nothing reads the G-buffer afterwards (k_resolve_shade)
   // (a caller that enqueues the phases one by one — peer frames — says so with fuse = 1: nothing reads the G-buffer in between)
-  const bool fused = (phases == 7 || fuse == 1) && !(fr->flags & PRC_FRAME_KEEP_GBUFFER) && !ctx->any_ao && !ctx->no_fused_shade;
+  const bool fused = (phases == 15 || fuse == 1) && !(fr->flags & PRC_FRAME_KEEP_GBUFFER) && !ctx->any_ao && !ctx->no_fused_shade;
   const bool es = ctx->exact_shade;  // exact FMA in the shading-only arithmetic too (PRC_FMA=exact)
 
   // Row ranges to rasterise and resolve: the strip (widened by the AO halo) and, for an upper strip of a frame with an AO
@@ -652,12 +694,17 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
   if (phases & 4) {
     int32_t r = flush_large<E>(ctx, F);  // also rasterises what the shadow passes of this frame queued
     if (r != PRC_OK) return r;
-    if (ctx->nan_mode)
+  }
+
+  if (phases & 8) {
+    if (ctx->nan_mode) {
+      const unsigned long long* first_s = ctx->first_shade ? ctx->first_shade : first;
       for (const auto& rg : ranges) {
         const size_t i0 = (size_t)rg.first * F.W, i1 = (size_t)rg.second * F.W;
-        k_nan_fix<<<cdiv(i1 - i0, 256), 256, 0, st>>>((unsigned long long*)ctx->d_keys.p, first, i0, i1, (F.rr0 > 0 && ranges.size() == 1) ? 1 : 0);
+        k_nan_fix<<<cdiv(i1 - i0, 256), 256, 0, st>>>(keys_w, first_s, i0, i1, (F.rr0 > 0 && ranges.size() == 1) ? 1 : 0);
         ctx->launches++;
       }
+    }
     CK(cudaEventRecordWithFlags(ctx->ev[2], st, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
     const bool stores00 = F.rr0 > 0 && ranges.size() == 1 && (fr->flags & PRC_FRAME_KEEP_GBUFFER);
     if (!fused || stores00) {
@@ -933,6 +980,8 @@ int32_t prc_close(prc_ctx* ctx) {
                  &ctx->d_bins, &ctx->d_active, &ctx->d_chunksum, &ctx->d_targets, &ctx->d_xf, &ctx->d_lights, &ctx->d_ambient, &ctx->d_gamma, &ctx->d_frame, &ctx->d_aoc, &ctx->d_chunkbox, &ctx->d_vis, &ctx->d_cverts, &ctx->d_cvoff, &ctx->d_lidx, &ctx->d_image_out, &ctx->d_rz_cx, &ctx->d_rz_sx, &ctx->d_rz_cy, &ctx->d_rz_sy};
   for (DBuf* b : all) free_buf(*b);
   free_buf(ctx->d_shadow_all);
+  free_buf(ctx->d_shadow_mine);
+  free_buf(ctx->d_mkeys);
   for (auto& b : ctx->d_shadow_trans) free_buf(b);
   for (auto& p : ctx->h_img) if (p) { cudaHostUnregister(p); free(p); }
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -1044,6 +1093,7 @@ int32_t prc_shadow_reset(prc_ctx* ctx) {
   if (ctx->pending_async) { const int32_t pr_ = prc_sync(ctx); if (pr_ != PRC_OK) return pr_; }  // finish asynchronous frames first
   CK(cudaSetDevice(ctx->device));
   if (ctx->d_shadow_all.p) CK(cudaMemsetAsync(ctx->d_shadow_all.p, 0, ctx->d_shadow_all.cap, ctx->stream));
+  if (ctx->d_shadow_mine.p) CK(cudaMemsetAsync(ctx->d_shadow_mine.p, 0, ctx->d_shadow_mine.cap, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return PRC_OK;
 }
@@ -1141,7 +1191,7 @@ int32_t prc_render_forward(prc_ctx* ctx, const prc_frame* fr) {
   ctx->pass_slot = 8;
   CK(cudaMemsetAsync(ctx->d_counters.p, 0, offsetof(Counters, n_nan), ctx->stream));
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-  return ctx->exact ? do_main<true>(ctx, fr, F, 5) : do_main<false>(ctx, fr, F, 5);
+  return ctx->exact ? do_main<true>(ctx, fr, F, 13) : do_main<false>(ctx, fr, F, 13);
 }
 
 int32_t prc_render_deferred(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out) {
@@ -1363,6 +1413,8 @@ void peer_release(prc_ctx* ctx) {
   for (void* b : ctx->peer_opened) cudaIpcCloseMemHandle(b);
   ctx->peer_opened.clear();
   ctx->peers = PeerTable{};
+  ctx->peer_private = false;
+  ctx->uniforms_valid = false;
   for (auto& p : ctx->peer_image) p = nullptr;
   ctx->peer_shadow_self = ctx->peer_image_self = nullptr;
   ctx->peer_epoch = 0;
@@ -1411,30 +1463,21 @@ inline void peer_signal(prc_ctx* ctx, uint32_t kind, uint32_t epoch, uint32_t ma
   ctx->launches++;
 }
 
-// One frame of the group on this rank, enqueued without waiting for anything:
-//   camera pass (needs no shadow map; runs while slower peers still shade the previous frame) -> wait until nobody reads the
-//   previous frame's maps -> this rank's shadow units -> ONE pass over the queued records of both (k_medium_raster [+ bins]) -> push
-//   the non-empty texels of the owned rows into every peer's maps, signal -> wait for the peers' rows -> fused resolve + shading ->
-//   signal, copy the strip to the image consumers.
+// One frame of the group on this rank, enqueued without waiting for anything (prc_peer.cuh has the partition):
+//   clear the private keys and the NEXT frame's merged plane -> camera pass and fused shadow sweep over this rank's share of the
+//   triangles (private buffers; no peer is involved, so this runs while slower peers still shade the previous frame) -> queued
+//   records -> wait until nobody reads the previous frame's merged maps -> k_peer_push -> signal, wait for the peers' pushes ->
+//   fused resolve + shading of the strip from the merged buffers -> signal, copy the strip to the image consumers.
+// The merged key planes alternate with the frame parity: plane (e+1)&1 is cleared at the start of frame e, after this rank's shading
+// of frame e-1 (stream order) and before any peer can push frame e+1 (a peer pushes e+1 only after it has seen this rank's
+// SHADOW(e), which follows the clear in this stream).
 template <bool E>
-int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, const std::vector<ShadowUnit>& units, uint32_t image_mask) {
+int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F, const PushJob& needs, uint32_t image_mask) {
   const PeerTable& P = ctx->peers;
   const uint32_t all = P.world >= 32 ? 0xFFFFFFFFu : ((1u << P.world) - 1u), me = 1u << P.self;
   cudaStream_t st = ctx->stream;
   const bool shadows = (fr->flags & PRC_FRAME_SHADOWMAP) && ctx->n_cast_alloc > 0 && ctx->n_cast_alloc != 0xFFFFFFFFu;
-  // everything that can fail is checked before the epoch advances: a rank that bailed out mid-frame would leave its peers
-  // waiting for signals that never come
-  PushUnits U{};
-  bool vec4 = true;
-  if (shadows)
-    for (const ShadowUnit& u : units) {
-      if (u.light >= fr->n_lights || !fr->lights[u.light].cast_shadow || u.r0 >= u.r1) continue;
-      if (U.n == 32) { ctx->err = "more than 32 shadow units in one prc_render_peer call"; return PRC_ERR_UNSUPPORTED; }
-      U.off[U.n] = (unsigned long long)(ctx->shadow_ptr[u.light] - (float*)ctx->d_shadow_all.p) + (unsigned long long)u.r0 * F.W;
-      U.cnt[U.n] = (unsigned long long)(u.r1 - u.r0) * F.W;
-      vec4 = vec4 && (U.off[U.n] % 4 == 0) && (U.cnt[U.n] % 4 == 0);
-      U.n++;
-    }
+  const size_t npx = (size_t)F.W * F.H;
   const uint32_t e = ++ctx->peer_epoch;
   ctx->pass_slot = 0;
   if (ctx->pending_async == 0) {
@@ -1451,31 +1494,58 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
   // on the host, before this call. Announcing "free up to e-1" per frame lets the consumer set change between frames.
   if (image_mask & me) peer_signal(ctx, PRC_SIG_IMAGE_FREE, e - 1, all);
   CK(cudaEventRecord(ctx->ev[0], st));
+  // merged planes of this frame (read by resolve / shading) and of the next one (cleared now)
+  unsigned long long* mk = (unsigned long long*)ctx->d_mkeys.p;
+  unsigned long long* plane_cur = mk + (size_t)(e & 1u) * npx;
+  unsigned long long* plane_next = mk + (size_t)((e + 1u) & 1u) * npx;
+  unsigned long long* first_cur = mk + (size_t)(2u + (e & 1u)) * npx;
+  unsigned long long* first_next = mk + (size_t)(2u + ((e + 1u) & 1u)) * npx;
+  {
+    const int r0s[2] = {F.rr0, 0}, r1s[2] = {F.rr1, needs.ax1[P.self]};
+    for (int k = 0; k < 2; k++) {
+      if (r1s[k] <= r0s[k]) continue;
+      CK(cudaMemsetAsync(plane_next + (size_t)r0s[k] * F.W, 0, (size_t)(r1s[k] - r0s[k]) * F.W * 8, st));
+      if (ctx->nan_mode) CK(cudaMemsetAsync(first_next + (size_t)r0s[k] * F.W, 0xFF, (size_t)(r1s[k] - r0s[k]) * F.W * 8, st));
+    }
+    CK(cudaMemsetAsync(plane_next, 0, 8, st));  // pixel (0,0) is merged into every rank
+    if (ctx->nan_mode) CK(cudaMemsetAsync(first_next, 0xFF, 8, st));
+  }
   // strip readback into the caller's (shared) host image, band by band behind the shading kernels
   ctx->rb_dst = (!(fr->flags & PRC_FRAME_NO_READBACK) && ctx->ext_img) ? ctx->ext_img : nullptr;
-  int32_t r = do_main<E>(ctx, fr, F, 1, 1);  // camera raster passes
-  if (r != PRC_OK) return r;
+  // ---- raster passes: this rank's share of the triangles, every row, private targets
+  DevFrame Fr = F;
+  Fr.rr0 = 0; Fr.rr1 = F.H;
+  ctx->part_rank = P.self; ctx->part_world = P.world;
+  ctx->keys_shade = nullptr; ctx->first_shade = nullptr;
+  int32_t r = do_main<E>(ctx, fr, Fr, 1, 1);
   CK(cudaEventRecord(ctx->ev[1], st));
-  if (shadows) {
-    // nobody may still be shading the previous frame from the maps this rank is about to store into
-    peer_wait(ctx, PRC_SIG_SHADED, e - 1, all);
-    r = do_shadows<E>(ctx, fr, F, units, false);
-    if (r != PRC_OK) return r;
-  }
-  r = do_main<E>(ctx, fr, F, 4, 1);  // queued records of the camera AND the shadow passes; G-buffer resolve when the frame is not fused
+  if (r == PRC_OK && shadows) r = do_shadows<E>(ctx, fr, Fr, units_from_mask(fr, 0xFFFFFFFFu, 0, F.H), false);
+  if (r == PRC_OK) r = do_main<E>(ctx, fr, Fr, 4, 1);  // queued records of the camera AND the shadow passes
+  ctx->part_rank = 0; ctx->part_world = 1;
   if (r != PRC_OK) return r;
-  if (shadows) {
-    if (U.n && P.world > 1) {
-      if (vec4) k_shadow_push<4><<<148 * 4, 256, 0, st>>>(P, U);
-      else k_shadow_push<1><<<148 * 4, 256, 0, st>>>(P, U);
-      ctx->launches++;
-    }
-    peer_signal(ctx, PRC_SIG_SHADOW, e, all);
-    peer_wait(ctx, PRC_SIG_SHADOW, e, all);
+  // ---- exchange
+  if (shadows) peer_wait(ctx, PRC_SIG_SHADED, e - 1, all);  // nobody may still be shading the previous frame from the maps about to be merged into
+  {
+    PushJob J = needs;
+    J.sh_mine = shadows ? (const float*)ctx->d_shadow_mine.p : nullptr;
+    J.n_sh = shadows ? (unsigned long long)ctx->n_cast_alloc * npx : 0ull;
+    J.k_mine = (const unsigned long long*)ctx->d_keys.p;
+    J.k_off = (unsigned long long)(plane_cur - mk);
+    J.W = F.W; J.ky0 = 0; J.ky1 = F.H;
+    J.f_mine = ctx->nan_mode ? (const unsigned long long*)ctx->d_keys.p + npx : nullptr;
+    J.f_off = (unsigned long long)(first_cur - mk);
+    KTimer kt(ctx, PRC_K_EXCHANGE);
+    k_peer_push<<<148 * 8, 256, 0, st>>>(P, J);
+    ctx->launches++;
   }
+  peer_signal(ctx, PRC_SIG_SHADOW, e, all);
+  peer_wait(ctx, PRC_SIG_SHADOW, e, all);
+  // ---- resolve + shading of the strip from the merged buffers
+  ctx->keys_shade = plane_cur; ctx->first_shade = first_cur;
   ctx->defer_copy_join = true;
-  r = do_main<E>(ctx, fr, F, 2, 1);
+  r = do_main<E>(ctx, fr, F, 8 | 2, 1);
   ctx->defer_copy_join = false;
+  ctx->keys_shade = nullptr; ctx->first_shade = nullptr;
   if (r != PRC_OK) return r;
   if (shadows) peer_signal(ctx, PRC_SIG_SHADED, e, all);
   // image strip: screen rows [row0,row1) = image rows [H-row1, H-row0)
@@ -1515,6 +1585,16 @@ int32_t prc_peer_export(prc_ctx* ctx, const prc_frame* fr, prc_peer_handle* out)
     if (r != PRC_OK) return r;
     ENSURE(ctx->d_image_out, (size_t)(fr->width / ctx->msaa) * (fr->height / ctx->msaa) * 4);
   }
+  // private shadow maps (raster target of this rank) and the merged key planes: 2 frame parities + 2 NaN-mode planes
+  ENSURE(ctx->d_shadow_mine, ctx->d_shadow_all.cap);
+  CK(cudaMemsetAsync(ctx->d_shadow_mine.p, 0, ctx->d_shadow_mine.cap, ctx->stream));
+  {
+    const size_t npx_ = (size_t)fr->width * fr->height;
+    ENSURE(ctx->d_mkeys, ipc_round(npx_ * 8 * 4));
+    CK(cudaMemsetAsync(ctx->d_mkeys.p, 0, npx_ * 8 * 2, ctx->stream));
+    CK(cudaMemsetAsync((unsigned long long*)ctx->d_mkeys.p + npx_ * 2, 0xFF, npx_ * 8 * 2, ctx->stream));
+    ENSURE(ctx->d_keys, npx_ * 16);  // room for the private NaN-mode plane, so that entering NaN mode never reallocates
+  }
   ENSURE(ctx->d_peer_signals, ipc_round((size_t)PRC_SIG_KINDS * PRC_PEER_MAX * 4));  // its own 2 MiB block (see build_frame)
   ENSURE(ctx->d_peer_err, 16);
   CK(cudaMemsetAsync(ctx->d_peer_signals.p, 0, (size_t)PRC_SIG_KINDS * PRC_PEER_MAX * 4, ctx->stream));
@@ -1527,12 +1607,16 @@ int32_t prc_peer_export(prc_ctx* ctx, const prc_frame* fr, prc_peer_handle* out)
   out->shadow_ptr = (uint64_t)(uintptr_t)ctx->d_shadow_all.p;
   out->image_ptr = (uint64_t)(uintptr_t)ctx->d_image.p;
   out->signals_ptr = (uint64_t)(uintptr_t)ctx->d_peer_signals.p;
+  out->mkeys_ptr = (uint64_t)(uintptr_t)ctx->d_mkeys.p;
   out->shadow_bytes = ctx->d_shadow_all.cap;
   out->image_bytes = ctx->d_image.cap;
+  out->mkeys_bytes = ctx->d_mkeys.cap;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "prc_peer_handle carries 64-byte IPC handles");
   CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->shadow_ipc, ctx->d_shadow_all.p));
   CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->image_ipc, ctx->d_image.p));
   CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->signals_ipc, ctx->d_peer_signals.p));
+  CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->mkeys_ipc, ctx->d_mkeys.p));
+  if ((r = alloc_offset(ctx, ctx->d_mkeys.p, &out->mkeys_off)) != PRC_OK) return r;
   if ((r = alloc_offset(ctx, ctx->d_shadow_all.p, &out->shadow_off)) != PRC_OK) return r;
   if ((r = alloc_offset(ctx, ctx->d_image.p, &out->image_off)) != PRC_OK) return r;
   if ((r = alloc_offset(ctx, ctx->d_peer_signals.p, &out->signals_off)) != PRC_OK) return r;
@@ -1564,7 +1648,7 @@ int32_t prc_peer_connect(prc_ctx* ctx, uint32_t rank, uint32_t world, const prc_
   for (uint32_t p = 0; p < world; p++) {
     const prc_peer_handle& h = all[p];
     if (h.abi_version != PRC_ABI_VERSION) return fail("prc_peer_connect: bad abi_version in a peer handle");
-    if (h.shadow_bytes != mine.shadow_bytes || h.image_bytes != mine.image_bytes) return fail("prc_peer_connect: the ranks' frame buffers differ in size");
+    if (h.shadow_bytes != mine.shadow_bytes || h.image_bytes != mine.image_bytes || h.mkeys_bytes != mine.mkeys_bytes) return fail("prc_peer_connect: the ranks' frame buffers differ in size");
     if (p == rank || h.pid == mine.pid) {
       // same process (this rank, or another context of a single-process test harness): the pointers are valid as they are
       if (p != rank && (int)h.device != ctx->device) {
@@ -1575,12 +1659,13 @@ int32_t prc_peer_connect(prc_ctx* ctx, uint32_t rank, uint32_t world, const prc_
       T.shadow[p] = (float*)(uintptr_t)h.shadow_ptr;
       image[p] = (uint8_t*)(uintptr_t)h.image_ptr;
       T.signals[p] = (uint32_t*)(uintptr_t)h.signals_ptr;
+      T.mkeys[p] = (unsigned long long*)(uintptr_t)h.mkeys_ptr;
       continue;
     }
     // another process: map its allocations (identical handles = buffers sharing one allocation block are mapped once)
-    const uint8_t* ipc[3] = {h.shadow_ipc, h.image_ipc, h.signals_ipc};
-    void* base[3] = {nullptr, nullptr, nullptr};
-    for (int k = 0; k < 3; k++) {
+    const uint8_t* ipc[4] = {h.shadow_ipc, h.image_ipc, h.signals_ipc, h.mkeys_ipc};
+    void* base[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < 4; k++) {
       for (int j = 0; j < k; j++)
         if (memcmp(ipc[k], ipc[j], 64) == 0) base[k] = base[j];
       if (base[k]) continue;
@@ -1593,8 +1678,11 @@ int32_t prc_peer_connect(prc_ctx* ctx, uint32_t rank, uint32_t world, const prc_
     T.shadow[p] = (float*)((uint8_t*)base[0] + h.shadow_off);
     image[p] = (uint8_t*)base[1] + h.image_off;
     T.signals[p] = (uint32_t*)((uint8_t*)base[2] + h.signals_off);
+    T.mkeys[p] = (unsigned long long*)((uint8_t*)base[3] + h.mkeys_off);
   }
   ctx->peers = T;
+  ctx->peer_private = true;
+  ctx->uniforms_valid = false;  // the raster targets changed: the next frame uploads its tables again
   ctx->peer_trace = getenv("PRC_PEER_TRACE") != nullptr && atoi(getenv("PRC_PEER_TRACE")) != 0;
   ctx->peer_spans.clear();
   for (uint32_t p = 0; p < PRC_PEER_MAX; p++) ctx->peer_image[p] = image[p];
@@ -1636,7 +1724,7 @@ int32_t prc_peer_disconnect(prc_ctx* ctx) {
   return r;
 }
 
-int32_t prc_render_peer(prc_ctx* ctx, const prc_frame* fr, uint32_t n, const uint32_t* light, const uint32_t* row0, const uint32_t* row1, uint32_t image_mask) {
+int32_t prc_render_peer(prc_ctx* ctx, const prc_frame* fr, uint32_t n_ranks, const uint32_t* row0, const uint32_t* row1, uint32_t image_mask) {
   if (!ctx) return PRC_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
   if (!ctx->peers.world) { ctx->err = "prc_render_peer: not connected (prc_peer_export / prc_peer_connect)"; return PRC_ERR_INVALID; }
@@ -1650,7 +1738,8 @@ int32_t prc_render_peer(prc_ctx* ctx, const prc_frame* fr, uint32_t n, const uin
     ctx->err = "prc_render_peer: MSAA frames have no device-side gather (image_mask must be 0): the downsampled strips leave through prc_set_host_image";
     return PRC_ERR_UNSUPPORTED;
   }
-  if (n && (!light || !row0 || !row1)) return PRC_ERR_INVALID;
+  if (n_ranks != ctx->peers.world || !row0 || !row1) { ctx->err = "prc_render_peer: row0/row1 must list the strip of every rank of the group"; return PRC_ERR_INVALID; }
+  if (row0[ctx->peers.self] != fr->row0 || row1[ctx->peers.self] != fr->row1) { ctx->err = "prc_render_peer: frame.row0/row1 differ from this rank's entry of row0/row1"; return PRC_ERR_INVALID; }
   if (!(fr->flags & PRC_FRAME_NO_READBACK) && ctx->ext_img && ctx->ext_img_bytes < (size_t)(fr->width / ms) * (fr->height / ms) * 4) {
     ctx->err = "prc_render_peer: the host image registered with prc_set_host_image is smaller than the frame";
     return PRC_ERR_INVALID;
@@ -1666,12 +1755,15 @@ int32_t prc_render_peer(prc_ctx* ctx, const prc_frame* fr, uint32_t n, const uin
     ctx->err = "prc_render_peer: the exported buffers were reallocated; export and connect again on every rank";
     return PRC_ERR_INVALID;
   }
-  std::vector<ShadowUnit> units;
-  for (uint32_t k = 0; k < n; k++) {
-    if (row1[k] > fr->height || row0[k] >= row1[k]) { ctx->err = "bad shadow row range"; return PRC_ERR_INVALID; }
-    units.push_back({light[k], (int)row0[k], (int)row1[k]});
+  // which rows every rank resolves (all ranks derive the same table from the same strips and the same scene)
+  PushJob needs{};
+  for (uint32_t p = 0; p < n_ranks; p++) {
+    if (row1[p] > fr->height || row0[p] >= row1[p]) { ctx->err = "prc_render_peer: bad strip (every rank needs at least one row)"; return PRC_ERR_INVALID; }
+    const bool strip = ms > 1 && (row0[p] != 0 || row1[p] != fr->height);
+    int s0, s1;
+    row_needs(ctx->any_ao, (int)ms, strip, (int)fr->height, (int)row0[p], (int)row1[p], s0, s1, needs.rr0[p], needs.rr1[p], needs.ax1[p]);
   }
-  r = ctx->exact ? enqueue_peer_frame<true>(ctx, fr, F, units, image_mask) : enqueue_peer_frame<false>(ctx, fr, F, units, image_mask);
+  r = ctx->exact ? enqueue_peer_frame<true>(ctx, fr, F, needs, image_mask) : enqueue_peer_frame<false>(ctx, fr, F, needs, image_mask);
   if (r != PRC_OK) return r;
   ctx->pending_async++;
   if (ctx->ev_used > 8192) {
@@ -1680,6 +1772,25 @@ int32_t prc_render_peer(prc_ctx* ctx, const prc_frame* fr, uint32_t n, const uin
     ctx->peer_spans.clear();
     ctx->ev_used = 0;
   }
+  return PRC_OK;
+}
+
+int32_t prc_frame_state(prc_ctx* ctx, uint32_t* state) {
+  if (!ctx || !state) return PRC_ERR_INVALID;
+  *state = (ctx->nan_mode ? PRC_STATE_NAN_MODE : 0u) | (ctx->need_bins ? PRC_STATE_TILE_PATH : 0u);
+  return PRC_OK;
+}
+
+int32_t prc_set_frame_state(prc_ctx* ctx, uint32_t state) {
+  if (!ctx) return PRC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->pending_async) { const int32_t pr_ = prc_sync(ctx); if (pr_ != PRC_OK && pr_ != PRC_ERR_RETRY) return pr_; }
+  if ((state & PRC_STATE_NAN_MODE) && !ctx->nan_mode) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->nan_mode = true;
+    if (ctx->W && ctx->H) ENSURE(ctx->d_keys, (size_t)ctx->W * ctx->H * 16);
+  }
+  if (state & PRC_STATE_TILE_PATH) ctx->need_bins = true;
   return PRC_OK;
 }
 

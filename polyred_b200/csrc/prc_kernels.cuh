@@ -367,7 +367,11 @@ struct GeomViews {
   const unsigned int* n_list;
   unsigned int* n_list_hint;    // page-locked host word: the host sizes the NEXT frame's grid from it (a hint, never needed for correctness)
   unsigned int list_from;       // LIST == 2 (tail launch): first list position not covered by the direct launch
+  // LIST == 3 (a rank of a multi-GPU group takes its share of the triangles): blocks of PRC_PART_BLOCK chunks dealt round-robin,
+  // CTA b handles chunk part_first + (b / PRC_PART_BLOCK) * part_stride + b % PRC_PART_BLOCK
+  unsigned int part_first, part_stride, n_chunks;
 };
+#define PRC_PART_BLOCK 16
 
 // ---------------------------------------------------------------------------------------------
 // K1: one CTA per 256-triangle chunk, three phases per view, all operands in shared memory.
@@ -555,6 +559,7 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_
   //   LIST == 1  CTA b handles list[b]; the host sizes the grid from the previous frame's list length (n_list_hint) plus a margin
   //   LIST == 2  a small tail launch (stride loop) for list positions >= list_from, i.e. when the list outgrew that grid —
   //              normally it finds nothing. (A stride loop in the main launch cost 25 % at 32 registers: measured, round 2.)
+  //   LIST == 3  no list: this rank's share of the chunks (see GeomViews.part_first)
   if (LIST == 1 && blockIdx.x == 0 && threadIdx.x == 0 && V.n_list_hint) *V.n_list_hint = *V.n_list;
   if (LIST == 1 && blockIdx.x >= *V.n_list) return;
   if (LIST == 2 && threadIdx.x == 0) sm.it = V.list_from + blockIdx.x;
@@ -563,7 +568,9 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_
     __syncthreads();  // sm.it is set; the previous chunk's shared vertices and queue are no longer read
     if (sm.it >= *V.n_list) return;
   }
-  const unsigned int chunk = LIST == 1 ? V.list[blockIdx.x] : LIST == 2 ? V.list[sm.it] : blockIdx.x;
+  const unsigned int chunk = LIST == 1 ? V.list[blockIdx.x] : LIST == 2 ? V.list[sm.it]
+                             : LIST == 3 ? V.part_first + (blockIdx.x / PRC_PART_BLOCK) * V.part_stride + (blockIdx.x % PRC_PART_BLOCK) : blockIdx.x;
+  if (LIST == 3 && chunk >= V.n_chunks) return;
   const unsigned long long tri64 = (unsigned long long)chunk * PRC_GEOM_THREADS + threadIdx.x;
   const unsigned int tri = (unsigned int)tri64;
   const uint32_t li = tri64 < S.n_tris ? __ldg(S.lidx + tri) : 0xFFFFFFFFu;

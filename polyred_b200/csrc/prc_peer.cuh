@@ -1,11 +1,15 @@
 // prc_peer.cuh — the multi-GPU exchange of one frame over NVLink peer memory (no reference counterpart: polyred has no
 // multi-GPU path; the parity oracle of this file is "the same frame as one GPU").
 //
-// Every rank (one process per GPU) maps its peers' shadow buffer, image buffer and signal words (CUDA IPC) and the frame
-// stays on the device end to end:
-//   * shadow rows a rank rasterised are PUSHED into every peer's copy of the stacked maps by k_shadow_push — only texels
-//     that hold a depth (a shadow map is mostly zeros: 1.6-5 % written on C3), instead of an all-gather of every byte;
-//   * a rank's shaded image strip is copied into the root's image (copy engine, peer-to-peer);
+// Partition ("sort-last" for the geometry, screen strips for the shading; scene replicated on every GPU):
+//   * every rank runs the geometry + raster passes — the camera pass and the fused sweep over all shadow-casting lights, the same
+//     kernels and launch shape as on one GPU — over ITS SHARE OF THE TRIANGLES (16-chunk blocks dealt round-robin), into private
+//     full-frame visibility keys and private shadow maps. (Round 1 cut the raster passes by screen rows instead: on C3 half of
+//     all triangles project into one eighth of the rows, and a rank's pass cost 0.11 ms of the 0.175 ms one GPU needs.)
+//   * k_peer_push then merges what the rank produced into its peers over NVLink with atomicMax: non-empty shadow texels into
+//     EVERY rank's maps (every pixel can look up any texel), non-empty visibility keys into the rank(s) that shade that row.
+//     Depth maxima / key maxima do not depend on who contributes what, so the merged buffers equal the 1-GPU buffers bit for bit.
+//   * every rank shades its strip of rows from the merged keys and maps, and copies the strip into the root's image.
 //   * ordering between ranks is by monotone epoch words written with st.release.sys into the PEER's memory
 //     (k_peer_signal) and awaited with ld.acquire.sys by a one-warp kernel on the consumer's stream (k_peer_wait), so the
 //     host never waits inside a frame and frames can be submitted back to back.
@@ -21,7 +25,7 @@ namespace prc {
 
 // signal words of one rank, written by its peers: word [kind][source rank] holds the last epoch the source finished
 enum PeerSignal : uint32_t {
-  PRC_SIG_SHADOW = 0,    // source's shadow rows of this epoch are in my maps
+  PRC_SIG_SHADOW = 0,    // source's shadow texels and visibility keys of this epoch are merged into my buffers
   PRC_SIG_SHADED = 1,    // source no longer reads its shadow maps of this epoch (its shading is done)
   PRC_SIG_IMAGE = 2,     // source's image strip of this epoch is in my image
   PRC_SIG_IMAGE_FREE = 3,  // source (an image consumer) is done with the image of this epoch
@@ -29,16 +33,25 @@ enum PeerSignal : uint32_t {
 };
 
 struct PeerTable {
-  float* shadow[PRC_PEER_MAX];     // stacked shadow maps of every rank (own entry = local pointer)
+  float* shadow[PRC_PEER_MAX];     // merged stacked shadow maps of every rank (own entry = local pointer)
   uint32_t* signals[PRC_PEER_MAX];  // [PRC_SIG_KINDS][PRC_PEER_MAX] words of every rank
+  unsigned long long* mkeys[PRC_PEER_MAX];  // merged visibility keys of every rank: 2 frame parities x [H][W] (x2 with the NaN-mode plane)
   uint32_t world, self;
 };
 
-struct PushUnits {
-  // up to 32 (offset, count) float ranges of the stacked maps owned by this rank (one per shadow unit)
-  unsigned long long off[32];
-  unsigned long long cnt[32];
-  uint32_t n;
+// what one k_peer_push launch merges into the peers
+struct PushJob {
+  // shadow maps: `n_sh` floats of this rank's private stacked maps -> every rank's merged maps
+  const float* sh_mine;
+  unsigned long long n_sh;
+  // visibility keys of the rows [ky0, ky1): private plane -> the merged plane (this frame's parity) of every rank that needs the row
+  const unsigned long long* k_mine;
+  unsigned long long k_off;      // offset of this frame's parity plane inside mkeys[], in keys
+  int W, ky0, ky1;
+  int rr0[PRC_PEER_MAX], rr1[PRC_PEER_MAX], ax1[PRC_PEER_MAX];  // rank p resolves rows [rr0, rr1) and [0, ax1) (+ pixel (0,0), always)
+  // NaN mode: first-fragment plane, merged with atomicMin (nullptr otherwise); f_off = offset of the merged plane
+  const unsigned long long* f_mine;
+  unsigned long long f_off;
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
@@ -82,30 +95,50 @@ __global__ void k_peer_signal(PeerTable P, uint32_t kind, uint32_t epoch, uint32
   st_release_sys(P.signals[dst] + kind * PRC_PEER_MAX + P.self, epoch);
 }
 
-// Pushes the non-empty texels of the rows this rank owns into every peer's maps. The owner is the only rank that
-// rasterises those rows and its values only grow (shadowDepthTest keeps the maximum, render/shadow.go:221-228), so a peer's
-// texel is always an older value of the owner's: a plain store of the current value is the all-gather's result.
-// Depth 0 is "nothing stored" (maps start at 0 and only z > 0 is ever kept), so zero texels are skipped.
-template <int VEC>
-__global__ void __launch_bounds__(256) k_shadow_push(PeerTable P, PushUnits U) {
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  const float* __restrict__ mine = P.shadow[P.self];
-  for (uint32_t u = 0; u < U.n; u++) {
-    const unsigned long long base = U.off[u], n = U.cnt[u];
-    if (VEC == 4) {
-      const float4* __restrict__ src = reinterpret_cast<const float4*>(mine + base);
-      for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n / 4; i += stride) {
-        const float4 v = __ldg(src + i);
-        if (v.x == 0.0f && v.y == 0.0f && v.z == 0.0f && v.w == 0.0f) continue;
-        for (uint32_t p = 0; p < P.world; p++)
-          if (p != P.self) reinterpret_cast<float4*>(P.shadow[p] + base)[i] = v;
+// Merges what this rank rasterised into its peers (and into its own merged buffers) — see the file header. Shadow depths are
+// positive floats, which order like their int bits; depth 0 / key 0 is "nothing stored" and is skipped (a shadow map is
+// 95-98 % zeros on C3, the key plane of a rank holds the fragments of 1/N of the triangles). The reductions are
+// fire-and-forget (RED over NVLink), 16 bytes are tested per load.
+__global__ void __launch_bounds__(256) k_peer_push(const __grid_constant__ PeerTable P, const __grid_constant__ PushJob J) {
+  const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (unsigned long long)gridDim.x * blockDim.x;
+  // ---- shadow texels -> every rank
+  {
+    const float4* __restrict__ src = reinterpret_cast<const float4*>(J.sh_mine);
+    for (unsigned long long i = tid; i < J.n_sh / 4; i += stride) {
+      const float4 v = __ldg(src + i);
+      if (v.x == 0.0f && v.y == 0.0f && v.z == 0.0f && v.w == 0.0f) continue;
+      const float e[4] = {v.x, v.y, v.z, v.w};
+      for (uint32_t p = 0; p < P.world; p++) {
+        int* dst = reinterpret_cast<int*>(P.shadow[p]) + i * 4;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (e[k] != 0.0f) atomicMax(dst + k, __float_as_int(e[k]));
       }
-    } else {
-      for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float v = __ldg(mine + base + i);
-        if (v == 0.0f) continue;
-        for (uint32_t p = 0; p < P.world; p++)
-          if (p != P.self) P.shadow[p][base + i] = v;
+    }
+    for (unsigned long long i = (J.n_sh / 4) * 4 + tid; i < J.n_sh; i += stride) {
+      const float v = __ldg(J.sh_mine + i);
+      if (v == 0.0f) continue;
+      for (uint32_t p = 0; p < P.world; p++) atomicMax(reinterpret_cast<int*>(P.shadow[p]) + i, __float_as_int(v));
+    }
+  }
+  // ---- visibility keys -> the ranks that resolve the row
+  if (J.k_mine) {
+    const unsigned long long i0 = (unsigned long long)J.ky0 * J.W, i1 = (unsigned long long)J.ky1 * J.W;
+    for (unsigned long long i = i0 + tid * 2; i < i1; i += stride * 2) {
+      unsigned long long k2[2] = {J.k_mine[i], i + 1 < i1 ? J.k_mine[i + 1] : 0ull};
+      unsigned long long f2[2] = {~0ull, ~0ull};
+      if (J.f_mine) { f2[0] = J.f_mine[i]; if (i + 1 < i1) f2[1] = J.f_mine[i + 1]; }
+      if (!(k2[0] | k2[1]) && (f2[0] & f2[1]) == ~0ull) continue;
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        if (!k2[k] && f2[k] == ~0ull) continue;
+        const unsigned long long idx = i + k;
+        const int y = (int)(idx / (unsigned long long)J.W);
+        for (uint32_t p = 0; p < P.world; p++) {
+          if (!((y >= J.rr0[p] && y < J.rr1[p]) || y < J.ax1[p] || idx == 0)) continue;
+          if (k2[k]) atomicMax(P.mkeys[p] + J.k_off + idx, k2[k]);
+          if (f2[k] != ~0ull) atomicMin(P.mkeys[p] + J.f_off + idx, f2[k]);
+        }
       }
     }
   }

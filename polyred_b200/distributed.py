@@ -11,9 +11,12 @@ range) shards dealt round-robin. Per frame:
 The result is bit-identical to the 1-GPU frame: atomicMax keys / depth maxima do not depend on who
 rasterised what, and every rank also rasterises pixel (0,0) (bug-list 3) and the AO halo rows.
 
-PeerFrames (below) is the same partition without a collective and without a host wait inside the frame:
-the ranks map each other's buffers (CUDA IPC over NVLink) and the library pushes shadow texels and image
-strips itself (prc_render_peer); torch.distributed only carries the handles and the retry vote.
+PeerFrames (below) drives prc_render_peer, the default multi-GPU path: no collective and no host wait inside the
+frame. The ranks map each other's buffers (CUDA IPC over NVLink); every rank rasterises ITS SHARE OF THE TRIANGLES
+(camera pass + all shadow lights, full frame) into private buffers, the library merges them into the peers
+with atomicMax over NVLink (shadow texels into every rank, visibility keys into the rank that shades the row),
+every rank shades its strip and copies it into rank 0's image (csrc/prc_peer.cuh). torch.distributed only carries
+the handles and the retry vote.
 """
 from __future__ import annotations
 
@@ -130,11 +133,15 @@ class PeerFrames:
         self.msaa = max(1, int(getattr(c, "MSAA", 1)))             # the frame buffer and the shadow maps are msaa times larger (raster.go:149)
         self.hs = self.h * self.msaa
         sources, _ = c.Scene.Lights()
-        cast = [i for i, l in enumerate(sources) if l.cast_shadow] if c.ShadowMap else []
-        # contiguous ranges of OUTPUT image rows / of the stacked shadow rows per rank: equal to begin with, rebalance() moves them
-        self.cast = cast
+        self.cast = [i for i, l in enumerate(sources) if l.cast_shadow] if c.ShadowMap else []
+        if self.h < world:
+            # (every rank sees the same h and world: all of them raise, none is left waiting in a collective)
+            from ._lib import PolyredCudaError
+            from . import _abi as A
+            raise PolyredCudaError(A.PRC_ERR_INVALID, f"PeerFrames: a frame of {self.h} rows cannot be cut into {world} strips")
+        # contiguous ranges of OUTPUT image rows per rank (the shading partition): equal to begin with, rebalance() moves them.
+        # The raster passes are partitioned by triangles inside the library and need no bounds.
         self.img_bounds = partition.equal_bounds(self.h, world)
-        self.sh_bounds = partition.equal_bounds(len(cast) * self.hs, world)
         self._apply_bounds()
         # MSAA frames are downsampled per strip on the rank that shaded it and have no device-side gather (share_host_image())
         self.image_mask = (1 << root) if self.msaa == 1 else 0
@@ -191,26 +198,22 @@ class PeerFrames:
 
     def _apply_bounds(self):
         m = self.msaa
-        self.rows = [(a * m, b * m) for a, b in partition.strips_from_bounds(self.h, self.img_bounds)]  # screen rows of the frame buffer
-        self.units = [(li, a, b) for li, a, b, owner in partition.shadow_units_from_bounds(self.hs, self.cast, self.sh_bounds) if owner == self.rank]
+        self.rows = [(a * m, b * m) for a, b in partition.strips_from_bounds(self.h, self.img_bounds)]  # screen rows of the frame buffer, every rank
         # the arrays prc_render_peer takes, built once per partition (a frame at 8 GPUs is ~0.2 ms: host microseconds count)
         be = getattr(self, "be", None)
-        self._unit_arrays = be.unit_arrays(self.units) if hasattr(be, "unit_arrays") else None
+        self._row_arrays = be.row_arrays(self.rows) if hasattr(be, "row_arrays") else None
 
     def rebalance(self, damping: float = 0.7, min_rows: int = 16):
-        """Move the strip and shadow-shard boundaries so that every rank gets the same share of the time the last finished
-        frames took (per-rank kernel times from prc_get_timings: the shadow classes for the shards, everything else for the
-        strips). Any partition renders the same frame bit for bit, so this only moves work. Collective: call on every rank
-        after finish(); returns the per-rank (shadow ms, main ms) it balanced on."""
+        """Move the strip boundaries so that every rank gets the same share of the time the last finished frames spent in the
+        row-partitioned kernels (resolve + shading, from prc_get_timings; the raster passes are partitioned by triangles and
+        cost every rank the same). Any partition renders the same frame bit for bit, so this only moves work. Collective: call
+        on every rank after finish(); returns the per-rank (raster ms, shading ms) it balanced on."""
         t = self.be.timings()
         k = list(t.kernel_ms)
-        mine = (float(k[0] + k[4]), float(k[1] + k[2] + k[3] + k[5] + k[6] + k[7]))
+        mine = (float(k[0] + k[1] + k[2] + k[3] + k[4] + k[5]), float(k[6] + k[7]))
         costs = [None] * self.world
         self.dist.all_gather_object(costs, mine, group=self.group)
-        if min(self.rows[r][1] - self.rows[r][0] for r in range(self.world)) > 0:
-            self.img_bounds = partition.balanced_bounds(self.img_bounds, [c[1] for c in costs], damping, min_rows)
-        if self.cast:
-            self.sh_bounds = partition.balanced_bounds(self.sh_bounds, [c[0] for c in costs], damping, min_rows)
+        self.img_bounds = partition.balanced_bounds(self.img_bounds, [c[1] for c in costs], damping, min_rows)
         self._apply_bounds()
         return costs
 
@@ -248,10 +251,10 @@ class PeerFrames:
             from ._lib import PolyredCudaError
             from . import _abi as A
             raise PolyredCudaError(A.PRC_ERR_UNSUPPORTED, "PeerFrames: MSAA frames leave through share_host_image() (frame_desc(no_readback=False), gather=False)")
-        if self._unit_arrays is not None:
-            self.be.render_peer_arrays(self.prepare(fd), self._unit_arrays[0], self._unit_arrays[1], self.image_mask if gather else 0)
+        if self._row_arrays is not None:
+            self.be.render_peer_arrays(self.prepare(fd), self._row_arrays[0], self._row_arrays[1], self.image_mask if gather else 0)
         else:
-            self.be.render_peer(self.prepare(fd), self.units, self.image_mask if gather else 0)
+            self.be.render_peer(self.prepare(fd), self.rows, self.image_mask if gather else 0)
         self._submitted.append((fd, gather))
 
     def _shm_votes(self, vote):
@@ -273,17 +276,19 @@ class PeerFrames:
         self._bar_phase += 1
         bar, ph = self._bar, self._bar_phase
         bar[self.rank, 1] = vote[0]
+        bar[self.rank, 3] = vote[2]
         bar[self.rank, 0] = ph          # (x86: stores are not reordered with older stores)
         col = bar[:, 0]
         while int(col.min()) < ph:
             pass
         codes = [int(c) for c in bar[:, 1]]
+        states = [int(c) for c in bar[:, 3]]
         # nobody may overwrite its code for the next phase before everybody has read this one: second half of the barrier
         bar[self.rank, 2] = ph
         col2 = bar[:, 2]
         while int(col2.min()) < ph:
             pass
-        return [(c, "" if c == 0 else f"error {c} (see that rank's log)") for c in codes]
+        return [(c, "" if c == 0 else f"error {c} (see that rank's log)", st) for c, st in zip(codes, states)]
 
     def finish(self, max_retries: int = 3, fast: bool = False):
         """Wait for the submitted frames. A queue overflow on ANY rank (the library has grown the queue) makes
@@ -297,18 +302,25 @@ class PeerFrames:
                 self.be.sync()
             except PolyredCudaError as e:
                 vote = (e.code, str(e))
+            vote = (*vote, self.be.frame_state() if hasattr(self.be, "frame_state") else 0)
             if fast:
                 votes = self._shm_votes(vote)
             else:
                 votes = [None] * self.world
                 self.dist.all_gather_object(votes, vote, group=self.group)  # same collective on every rank, error or not
-            fatal = [(k, c, m) for k, (c, m) in enumerate(votes) if c not in (0, A.PRC_ERR_RETRY)]
+            fatal = [(k, c, m) for k, (c, m, _) in enumerate(votes) if c not in (0, A.PRC_ERR_RETRY)]
             if fatal:
                 self._submitted = []
                 raise PolyredCudaError(fatal[0][1], "PeerFrames: " + "; ".join(f"rank {k}: {m}" for k, _, m in fatal))
-            if not any(c for c, _ in votes):
+            if not any(c for c, _, _ in votes):
                 self._submitted = []
                 return
+            # the ranks must agree on NaN mode (the first fragment of a pixel may come from any rank's triangles)
+            state = 0
+            for _, _, st in votes:
+                state |= st
+            if hasattr(self.be, "set_frame_state"):
+                self.be.set_frame_state(state)
             again, self._submitted = self._submitted, []
             for fd, gather in again:
                 self.submit(fd, gather)

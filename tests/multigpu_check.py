@@ -48,7 +48,7 @@ def main():
             pf.finish()
             rebalanced_out = pf.image(host=True)
             if rank == 0:
-                print(f"[multigpu_check] {name}: rebalanced strips {[b - a for a, b in pf.rows]} from per-rank (shadow, main) ms {[(round(c[0], 3), round(c[1], 3)) for c in costs]}")
+                print(f"[multigpu_check] {name}: rebalanced strips {[b - a for a, b in pf.rows]} from per-rank (raster, shading) ms {[(round(c[0], 3), round(c[1], 3)) for c in costs]}")
             # and the e2e form: every rank reads its own strip back into one shared host image, no device-side gather
             shared = pf.share_host_image()
             pf.submit(r2.frame_desc(no_readback=False), gather=False)

@@ -31,10 +31,7 @@ def _opts(s, cam, w, h):
 
 def _group(s, cam, w, h, devices):
     world = len(devices)
-    sources, _ = s.Lights()
-    cast = [i for i, l in enumerate(sources) if l.cast_shadow]
     _, rows = partition.strips(h, world)
-    units = partition.shadow_units(h, world, cast)
     rs, fds, handles = [], [], []
     for k, dev in enumerate(devices):
         r = render.NewRenderer(*_opts(s, cam, w, h), render.CUDA(dev))
@@ -46,7 +43,7 @@ def _group(s, cam, w, h, devices):
         fds.append(fd)
     for k, r in enumerate(rs):
         r._backend.peer_connect(k, world, handles)
-    mine = [[(li, a, b) for li, a, b, owner in units if owner == k] for k in range(world)]
+    mine = [rows] * world  # every call carries the strips of all ranks
     return rs, fds, mine
 
 
@@ -68,6 +65,11 @@ def _run(devices, frames=3, size=(480, 272), scene=None):
                 again = True
         if not again:
             break
+        state = 0
+        for r in rs:
+            state |= r._backend.frame_state()
+        for r in rs:
+            r._backend.set_frame_state(state)  # the ranks must agree on NaN mode (distributed.PeerFrames.finish does the same)
     assert not again
     out = rs[0]._backend.read_image(w, h)
     for r in rs:
@@ -173,10 +175,7 @@ def test_peer_msaa_strips_downsample_locally(monkeypatch, world):
     s, cam, w, h = _scene(240, 136)
     opts = _opts(s, cam, w, h) + [render.MSAA(2)]
     ref = render.NewRenderer(*opts, render.CUDA(0)).Render().copy()
-    sources, _ = s.Lights()
-    cast = [i for i, l in enumerate(sources) if l.cast_shadow]
     rows = [(a * 2, b * 2) for a, b in partition.strips_from_bounds(h, partition.equal_bounds(h, world))]
-    units = partition.shadow_units(h * 2, world, cast)
     host = np.zeros((h, w, 4), np.uint8)
     rs, fds = [], []
     handles = []
@@ -193,7 +192,7 @@ def test_peer_msaa_strips_downsample_locally(monkeypatch, world):
         r._backend.set_host_image(host.ctypes.data, host.nbytes)
     for _ in range(2):
         for k, r in enumerate(rs):
-            r._backend.render_peer(fds[k], [(li, a, b) for li, a, b, owner in units if owner == k], 0)
+            r._backend.render_peer(fds[k], rows, 0)
     for r in rs:
         r._backend.sync()
     assert int((ref != host).any(axis=2).sum()) == 0

@@ -139,8 +139,14 @@ class _FakeBackend:
             raise PolyredCudaError(A.PRC_ERR_CUDA, "cudaIpcOpenMemHandle: refused")
         self.connected = (rank, world, [len(b) for b in handles])
 
-    def render_peer(self, fd, units, image_mask):
-        self.calls.append((fd.tag, fd.struct.row0, fd.struct.row1, tuple(units), image_mask))
+    def render_peer(self, fd, rows, image_mask):
+        self.calls.append((fd.tag, fd.struct.row0, fd.struct.row1, tuple(rows), image_mask))
+
+    def frame_state(self):
+        return 1 if (self.rank == 1 and self.syncs >= 1) else 0  # rank 1 entered NaN mode with its retry
+
+    def set_frame_state(self, state):
+        self.state_set = state
 
     def sync(self):
         from polyred_b200 import _abi as A
@@ -154,7 +160,7 @@ class _FakeBackend:
     def timings(self):
         from polyred_b200 import _abi as A
         t = A.prc_timings()
-        t.kernel_ms[0] = 1.0 + 3.0 * self.rank      # shadow sweep: rank 1 four times slower
+        t.kernel_ms[0] = 1.0 + 3.0 * self.rank      # raster passes (partitioned by triangles: not what the strips are balanced on)
         t.kernel_ms[7] = 4.0 - 3.0 * self.rank      # shading: rank 0 four times slower
         return t
 
@@ -187,8 +193,8 @@ def _peer_worker(rank, world, port, q):
     pf.finish()
     # rebalance(): both ranks gather the same timings and derive the same new boundaries
     costs = pf.rebalance(damping=1.0, min_rows=4)
-    rebalanced = (costs, pf.img_bounds, pf.sh_bounds, pf.rows[rank], pf.units)
-    pf.img_bounds, pf.sh_bounds = partition.equal_bounds(100, world), partition.equal_bounds(200, world)
+    rebalanced = (costs, pf.img_bounds, pf.rows[rank], getattr(be, "state_set", None))
+    pf.img_bounds = partition.equal_bounds(100, world)
     pf._apply_bounds()
     # one shared host image: every rank maps the same pages and "reads back" its own strip into them
     img = pf.share_host_image()
@@ -221,8 +227,9 @@ def _peer_worker(rank, world, port, q):
 
 
 def test_peer_frames_host_logic_two_ranks():
-    """PeerFrames (prc_render_peer driver): handles are gathered in rank order, every rank submits its own strip and
-    shadow units, and a queue overflow on ONE rank makes BOTH ranks submit the batch again (lockstep epochs)."""
+    """PeerFrames (prc_render_peer driver): handles are gathered in rank order, every rank submits its own strip together with
+    the strips of all ranks, and a retry on ONE rank makes BOTH ranks submit the batch again (lockstep epochs) after agreeing on
+    the sticky frame state (NaN mode)."""
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
@@ -239,19 +246,18 @@ def test_peer_frames_host_logic_two_ranks():
     from polyred_b200 import _abi as A
     for rank, connected, calls, syncs, left, seen, shared_ok, rebalanced in res:
         assert shared_ok
-        costs, img_bounds, sh_bounds, my_rows, my_units = rebalanced
+        costs, img_bounds, my_rows, state_set = rebalanced
         assert costs == [(1.0, 4.0), (4.0, 1.0)]
-        assert img_bounds == [0, 31, 100] and sh_bounds == [0, 138, 200]      # rank 0: fewer image rows, more shadow rows
+        assert img_bounds == [0, 31, 100]      # rank 0 shades four times slower: fewer image rows
         assert my_rows == ((69, 100) if rank == 0 else (0, 69))
-        assert my_units == ([(0, 0, 100), (2, 0, 38)] if rank == 0 else [(2, 38, 100)])
+        assert state_set == 1                  # rank 1's NaN mode was set on both ranks before the frames were submitted again
         assert seen == [("connect", A.PRC_ERR_PEER, True), ("finish", A.PRC_ERR_PEER, True)], seen
         assert connected == (rank, 2, [C.sizeof(A.prc_peer_handle)] * 2)
         assert [c[0] for c in calls] == [0, 1, 2, 0, 1, 2] and syncs == 2 and left == 0  # one retry, on both ranks
         assert all(c[4] == 1 for c in calls)  # the image goes to rank 0
         rows = {(c[1], c[2]) for c in calls}
         assert rows == {(50, 100)} if rank == 0 else rows == {(0, 50)}  # rank 0 owns the top image rows = the high screen rows
-        units = set(calls[0][3])
-        assert units == ({(0, 0, 100)} if rank == 0 else {(2, 0, 100)})  # lights 0 and 2 cast: one whole map per rank
+        assert calls[0][3] == ((50, 100), (0, 50))  # every call carries the strips of ALL ranks, in rank order
 
 
 def test_peer_frames_msaa_rows_are_supersampled_and_aligned():
@@ -262,11 +268,9 @@ def test_peer_frames_msaa_rows_are_supersampled_and_aligned():
         pf = PeerFrames.__new__(PeerFrames)
         pf.msaa, pf.h, pf.hs, pf.rank, pf.cast = m, h, h * m, 1, [0, 2]
         pf.img_bounds = partition.balanced_bounds(partition.equal_bounds(h, world), [1.0 + k for k in range(world)])
-        pf.sh_bounds = partition.equal_bounds(2 * h * m, world)
         pf._apply_bounds()
         assert all(a % m == 0 and b % m == 0 for a, b in pf.rows)
         assert sorted(pf.rows)[0][0] == 0 and sorted(pf.rows)[-1][1] == h * m and sum(b - a for a, b in pf.rows) == h * m
-        assert all(0 <= a < b <= h * m for _, a, b in pf.units) and sum(b - a for _, a, b in pf.units) == pf.sh_bounds[2] - pf.sh_bounds[1]
 
 
 def test_balanced_bounds_properties_hypothesis():

@@ -15,7 +15,7 @@ d = json.load(open(sys.argv[2]))
 k = {a: round(b, 4) for a, b in d["kernel_ms_per_step"].items()}
 print(f"[{sys.argv[1]}] N={d['n_gpus']} dev {d['ms_per_step']:.4f} ms  wall {d['wall_ms_per_step']:.4f}  e2e {d['e2e']['ms_per_step']:.3f}  launches/frame {d['gpu_launches'] / d['steps']:.0f}")
 print("   kernels(rank0):", k, "sum", round(sum(k.values()), 4))
-print("   waits:", d.get("peer_wait_ms_per_step_rank0"), "strips", d["config"].get("strip_rows"), "shadow rows", d["config"].get("shadow_rows_per_rank"))
+print("   waits:", d.get("peer_wait_ms_per_step_rank0"), "strips", d["run"].get("strip_rows"), "matches_1gpu", d.get("matches_1gpu"))
 b = d.get("balance_rounds") or []
 if b: print("   last balance:", b[-1])
 PY
