@@ -69,9 +69,11 @@ struct prc_ctx {
   // Peer groups (prc_render_peer): the raster passes of a rank cover its share of the triangles and write PRIVATE buffers — d_keys
   // and d_shadow_mine (same layout as d_shadow_all) — which k_peer_push merges into every rank's d_shadow_all / d_mkeys
   // (merged visibility keys: 2 frame parities x [H][W], + 2 NaN-mode planes); shading reads the merged ones.
-  DBuf d_shadow_mine, d_mkeys;
+  DBuf d_shadow_mine, d_mkeys, d_dirty;  // d_dirty: row flags of the private buffers (Counters.dirty)
+  bool skip_key_clear = false;            // peer frames: k_peer_push leaves the private key plane empty (clear-on-read)
   bool peer_private = false;               // connected: raster targets are the private buffers
   uint32_t part_rank = 0, part_world = 1;  // while a peer frame's raster passes are enqueued: this rank's share of the chunks
+  bool part_active = false;
   unsigned long long* keys_shade = nullptr;   // while a peer frame is enqueued: the merged key plane of this frame (nullptr: d_keys)
   unsigned long long* first_shade = nullptr;  // ... and its NaN-mode plane
   uint32_t n_cast_alloc = 0;
@@ -252,7 +254,7 @@ int32_t raster_pass(prc_ctx* ctx, const DevFrame& F, const GeomViews& Vin) {
   GeomViews V = Vin;
   bool list_mode = false;
   unsigned int grid = cdiv(ctx->S.n_tris, PRC_GEOM_THREADS);
-  const bool part = ctx->part_world > 1;  // a rank of a peer group: its share of the chunks, every row
+  const bool part = ctx->part_active;  // a rank of a peer group: its share of the chunks, every row
   if (part) {
     const unsigned int nb = cdiv(ctx->n_chunks, PRC_PART_BLOCK);  // blocks of chunks, dealt round-robin
     const unsigned int mine = ctx->part_rank < nb ? cdiv(nb - ctx->part_rank, ctx->part_world) : 0u;
@@ -260,6 +262,7 @@ int32_t raster_pass(prc_ctx* ctx, const DevFrame& F, const GeomViews& Vin) {
     V.part_first = ctx->part_rank * PRC_PART_BLOCK;
     V.part_stride = ctx->part_world * PRC_PART_BLOCK;
     V.n_chunks = ctx->n_chunks;
+    V.dirty = (unsigned char*)ctx->d_dirty.p;
   }
   if (ctx->S.n_tris && !ctx->no_chunk_cull && !part) {
     // chunk culling pays when a view covers only part of the rows (multi-GPU strips / shadow shards): one launch tests every
@@ -673,11 +676,12 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
 
   if (phases & 1) {
     // clear the visibility keys of the rasterised rows (+ pixel (0,0))
+    if (!ctx->skip_key_clear)
     for (const auto& rg : ranges) {
       CK(cudaMemsetAsync((unsigned long long*)ctx->d_keys.p + (size_t)rg.first * F.W, 0, (size_t)(rg.second - rg.first) * F.W * 8, st));
       if (ctx->nan_mode) CK(cudaMemsetAsync(first + (size_t)rg.first * F.W, 0xFF, (size_t)(rg.second - rg.first) * F.W * 8, st));
     }
-    if (F.rr0 > 0 && ranges.size() == 1) {
+    if (F.rr0 > 0 && ranges.size() == 1 && !ctx->skip_key_clear) {
       CK(cudaMemsetAsync(ctx->d_keys.p, 0, 8, st));
       if (ctx->nan_mode) CK(cudaMemsetAsync(first, 0xFF, 8, st));
     }
@@ -982,6 +986,7 @@ int32_t prc_close(prc_ctx* ctx) {
   free_buf(ctx->d_shadow_all);
   free_buf(ctx->d_shadow_mine);
   free_buf(ctx->d_mkeys);
+  free_buf(ctx->d_dirty);
   for (auto& b : ctx->d_shadow_trans) free_buf(b);
   for (auto& p : ctx->h_img) if (p) { cudaHostUnregister(p); free(p); }
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -1042,7 +1047,7 @@ int32_t prc_scene_upload(prc_ctx* ctx, const prc_scene* s) {
     if (!(s->materials[i].flags & PRC_MAT_NIL) && (s->materials[i].flags & PRC_MAT_AMBIENT_OCCLUSION)) ctx->any_ao = true;
   // Triangle.IsValid + object index, once per scene
   Counters* cnt = (Counters*)ctx->d_counters.p;
-  CK(cudaMemsetAsync(cnt, 0, sizeof(Counters), ctx->stream));
+  CK(cudaMemsetAsync(cnt, 0, offsetof(Counters, dirty), ctx->stream));
   if (n) k_validate<<<cdiv(n, 256), 256, 0, ctx->stream>>>((const float*)ctx->d_pos.p, (const uint64_t*)ctx->d_objstart.p, s->n_objects, n,
                                                            (uint32_t*)ctx->d_meta.p, &cnt->n_valid);
   ctx->n_chunks = cdiv(n, PRC_GEOM_THREADS);
@@ -1244,6 +1249,7 @@ static int32_t enqueue_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& 
 int32_t prc_render(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out) {
   if (!ctx) return PRC_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
+  if (ctx->peer_private) { ctx->err = "this context is connected to a peer group (its raster targets are the group's private buffers): prc_peer_disconnect first"; return PRC_ERR_INVALID; }
   DevFrame F;
   int32_t r = build_frame(ctx, fr, F);
   if (r != PRC_OK) return r;
@@ -1413,6 +1419,10 @@ void peer_release(prc_ctx* ctx) {
   for (void* b : ctx->peer_opened) cudaIpcCloseMemHandle(b);
   ctx->peer_opened.clear();
   ctx->peers = PeerTable{};
+  if (ctx->peer_private && ctx->d_counters.p) {  // back to one GPU: nothing marks rows any more
+    cudaMemsetAsync((char*)ctx->d_counters.p + offsetof(Counters, dirty), 0, sizeof(unsigned char*), ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+  }
   ctx->peer_private = false;
   ctx->uniforms_valid = false;
   for (auto& p : ctx->peer_image) p = nullptr;
@@ -1515,24 +1525,27 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
   // ---- raster passes: this rank's share of the triangles, every row, private targets
   DevFrame Fr = F;
   Fr.rr0 = 0; Fr.rr1 = F.H;
-  ctx->part_rank = P.self; ctx->part_world = P.world;
+  ctx->part_rank = P.self; ctx->part_world = P.world; ctx->part_active = true;  // (a group of one runs the same code path)
   ctx->keys_shade = nullptr; ctx->first_shade = nullptr;
+  ctx->skip_key_clear = true;  // empty since the last push
   int32_t r = do_main<E>(ctx, fr, Fr, 1, 1);
+  ctx->skip_key_clear = false;
   CK(cudaEventRecord(ctx->ev[1], st));
   if (r == PRC_OK && shadows) r = do_shadows<E>(ctx, fr, Fr, units_from_mask(fr, 0xFFFFFFFFu, 0, F.H), false);
   if (r == PRC_OK) r = do_main<E>(ctx, fr, Fr, 4, 1);  // queued records of the camera AND the shadow passes
-  ctx->part_rank = 0; ctx->part_world = 1;
+  ctx->part_rank = 0; ctx->part_world = 1; ctx->part_active = false;
   if (r != PRC_OK) return r;
   // ---- exchange
   if (shadows) peer_wait(ctx, PRC_SIG_SHADED, e - 1, all);  // nobody may still be shading the previous frame from the maps about to be merged into
   {
     PushJob J = needs;
-    J.sh_mine = shadows ? (const float*)ctx->d_shadow_mine.p : nullptr;
-    J.n_sh = shadows ? (unsigned long long)ctx->n_cast_alloc * npx : 0ull;
-    J.k_mine = (const unsigned long long*)ctx->d_keys.p;
+    J.W = F.W; J.H = F.H;
+    J.n_sh = shadows ? ctx->n_cast_alloc : 0u;
+    J.dirty = (unsigned char*)ctx->d_dirty.p;
+    J.sh_mine = (float*)ctx->d_shadow_mine.p;
+    J.k_mine = (unsigned long long*)ctx->d_keys.p;
     J.k_off = (unsigned long long)(plane_cur - mk);
-    J.W = F.W; J.ky0 = 0; J.ky1 = F.H;
-    J.f_mine = ctx->nan_mode ? (const unsigned long long*)ctx->d_keys.p + npx : nullptr;
+    J.f_mine = ctx->nan_mode ? (unsigned long long*)ctx->d_keys.p + npx : nullptr;
     J.f_off = (unsigned long long)(first_cur - mk);
     KTimer kt(ctx, PRC_K_EXCHANGE);
     k_peer_push<<<148 * 8, 256, 0, st>>>(P, J);
@@ -1594,6 +1607,15 @@ int32_t prc_peer_export(prc_ctx* ctx, const prc_frame* fr, prc_peer_handle* out)
     CK(cudaMemsetAsync(ctx->d_mkeys.p, 0, npx_ * 8 * 2, ctx->stream));
     CK(cudaMemsetAsync((unsigned long long*)ctx->d_mkeys.p + npx_ * 2, 0xFF, npx_ * 8 * 2, ctx->stream));
     ENSURE(ctx->d_keys, npx_ * 16);  // room for the private NaN-mode plane, so that entering NaN mode never reallocates
+    // the private planes start empty and are emptied again by every push (clear-on-read): keys 0, first-fragment plane ~0
+    CK(cudaMemsetAsync(ctx->d_keys.p, 0, npx_ * 8, ctx->stream));
+    CK(cudaMemsetAsync((unsigned long long*)ctx->d_keys.p + npx_, 0xFF, npx_ * 8, ctx->stream));
+    ENSURE(ctx->d_dirty, (size_t)33 * fr->height);
+    CK(cudaMemsetAsync(ctx->d_dirty.p, 0, (size_t)33 * fr->height, ctx->stream));
+    struct { unsigned char* p; int h; } dd = {(unsigned char*)ctx->d_dirty.p, (int)fr->height};
+    CK(cudaMemcpyAsync((char*)ctx->d_counters.p + offsetof(Counters, dirty), &dd.p, sizeof(dd.p), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync((char*)ctx->d_counters.p + offsetof(Counters, dirty_h), &dd.h, sizeof(dd.h), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // dd is a stack object
   }
   ENSURE(ctx->d_peer_signals, ipc_round((size_t)PRC_SIG_KINDS * PRC_PEER_MAX * 4));  // its own 2 MiB block (see build_frame)
   ENSURE(ctx->d_peer_err, 16);

@@ -100,7 +100,15 @@ struct Counters {
   unsigned long long stat_large, stat_clip, stat_bins;
   // per scene
   unsigned long long n_valid;
+  // Peer groups: row flags [1 + casting lights][H] (target 0 = camera keys) set by whatever writes a fragment into this rank's
+  // private buffers, so that k_peer_push only scans (and clears) rows that hold something. nullptr outside a peer group.
+  unsigned char* dirty;
+  int dirty_h;
 };
+__device__ __forceinline__ void mark_dirty(const Counters* cnt, uint32_t target, int y) {  // not for the hot path (a dependent global load)
+  unsigned char* d = cnt->dirty;
+  if (d) d[(size_t)target * cnt->dirty_h + y] = 1;
+}
 
 // warp-aggregated slot reservation: one atomicAdd per warp for all lanes that reach this point together
 __device__ __forceinline__ unsigned int warp_push(unsigned int* counter) {
@@ -244,7 +252,8 @@ __device__ __forceinline__ void nan_first(unsigned long long* first, size_t idx,
 
 template <bool E, bool SHADOW, bool NM = false>
 __device__ __forceinline__ void raster_one(const BarySetup& bs, const V4& p1, const V4& p2, const V4& p3, int x0, int y0, int x1, int y1, uint32_t seq, int W,
-                                           unsigned long long* __restrict__ keys, float* __restrict__ smap, Counters* cnt, unsigned long long* first = nullptr) {
+                                           unsigned long long* __restrict__ keys, float* __restrict__ smap, Counters* cnt, unsigned long long* first = nullptr,
+                                           uint32_t target = 0) {
   for (int y = y0; y <= y1; y++) {
     float py = (float)y + 0.5f;
     for (int x = x0; x <= x1; x++) {
@@ -255,7 +264,8 @@ __device__ __forceinline__ void raster_one(const BarySetup& bs, const V4& p1, co
       float z = w1 * p1.z + w2 * p2.z + w3 * p3.z;
       size_t idx = (size_t)y * W + x;
       if (NM && !SHADOW) nan_first(first, idx, seq, z);
-      if (isnan(z)) { atomicAdd(SHADOW ? &cnt->n_nan_shadow : &cnt->n_nan, 1ULL); continue; }
+      if (isnan(z)) { atomicAdd(SHADOW ? &cnt->n_nan_shadow : &cnt->n_nan, 1ULL); if (NM && !SHADOW) mark_dirty(cnt, 0, y); continue; }
+      mark_dirty(cnt, target, y);
       if (SHADOW) {
         // shadowDepthTest (shadow.go:221-228): store iff !(z <= stored); stored starts at 0 and only grows,
         // so only z > 0 can ever be stored and positive floats order like their int bits.
@@ -296,7 +306,7 @@ __device__ __forceinline__ void emit_tri(const V4& p1, const V4& p2, const V4& p
   }
   int area = (x1 - x0 + 1) * (y1 - y0 + 1);
   if (area <= PRC_SMALL_MAX_PIXELS) {
-    raster_one<E, SHADOW, NM>(bs, p1, p2, p3, x0, y0, x1, y1, seq, F.W, keys, smap, cnt, first);
+    raster_one<E, SHADOW, NM>(bs, p1, p2, p3, x0, y0, x1, y1, seq, F.W, keys, smap, cnt, first, target);
   } else {
     unsigned int slot = warp_push(&cnt->n_large);
     if (slot >= large_cap) { atomicExch(&cnt->large_overflow, 1u); return; }
@@ -370,6 +380,7 @@ struct GeomViews {
   // LIST == 3 (a rank of a multi-GPU group takes its share of the triangles): blocks of PRC_PART_BLOCK chunks dealt round-robin,
   // CTA b handles chunk part_first + (b / PRC_PART_BLOCK) * part_stride + b % PRC_PART_BLOCK
   unsigned int part_first, part_stride, n_chunks;
+  unsigned char* dirty;         // LIST == 3: Counters.dirty (row flags of the private targets)
 };
 #define PRC_PART_BLOCK 16
 
@@ -386,10 +397,11 @@ struct GeomViews {
 // Several shadow views share the vertex fetch; the camera pass is the same kernel with one view.
 // ---------------------------------------------------------------------------------------------
 #define PRC_QCAP 2048
-template <bool E, bool SHADOW, bool NM = false>
+template <bool E, bool SHADOW, bool NM = false, bool PEER = false>
 __device__ __forceinline__ void small_pixel(const float p1x, const float p1y, const float p1z, const float p2x, const float p2y, const float p2z,
                                             const float p3x, const float p3y, const float p3z, const int x, const int y, const uint32_t seq, const int W,
-                                            unsigned long long* keys, float* smap, Counters* cnt, unsigned long long* first = nullptr) {
+                                            unsigned long long* keys, float* smap, Counters* cnt, unsigned long long* first = nullptr,
+                                            unsigned char* dirty_rows = nullptr) {
   const BarySetup bs = bary_setup<E>(p1x, p1y, p2x, p2y, p3x, p3y);
   const float thr = 2e-7f * fabsf(bs.Sabc);
   const uint32_t sg = __float_as_uint(bs.Sabc);
@@ -416,6 +428,7 @@ __device__ __forceinline__ void small_pixel(const float p1x, const float p1y, co
   const float z = w1 * p1z + w2 * p2z + w3 * p3z;
   const size_t idx = (size_t)y * W + x;
   if (NM && !SHADOW) nan_first(first, idx, seq, z);
+  if (PEER && (!SHADOW || z > 0.0f || (NM && isnan(z)))) dirty_rows[y] = 1;  // peer groups: this row of the private buffer holds something
   if (isnan(z)) { atomicAdd(SHADOW ? &cnt->n_nan_shadow : &cnt->n_nan, 1ULL); return; }
   // fire-and-forget reductions (RED.MAX): no pre-test load, so nothing waits on memory
   if (SHADOW) {
@@ -456,11 +469,12 @@ __device__ __forceinline__ void geom_vertices(const DevScene& S, const DevFrame&
 }
 
 // phase 2 for one triangle
-template <bool E, bool SHADOW, bool NM = false>
+template <bool E, bool SHADOW, bool NM = false, bool PEER = false>
 __device__ __forceinline__ void geom_classify(const DevScene& S, const DevFrame& F, GeomSmem& sm, const int buf, const int qsel, const uint32_t li, const unsigned int tri,
                                               const float* __restrict__ trans_base, const int trans_stride,
                                               unsigned long long* keys, float* smap, LargeRec* large, unsigned int large_cap, unsigned int* clipq,
-                                              unsigned int clip_cap, Counters* cnt, const DevFrame* Fg, uint32_t target, const int vr0, const int vr1) {
+                                              unsigned int clip_cap, Counters* cnt, const DevFrame* Fg, uint32_t target, const int vr0, const int vr1,
+                                              unsigned char* dirty_rows = nullptr) {
   const uint32_t i0 = li & 1023u, i1 = (li >> 10) & 1023u, i2 = (li >> 20) & 1023u;
   const float* sx = sm.x[buf]; const float* sy = sm.y[buf]; const float* sz = sm.z[buf];
   const float p1x = sx[i0], p2x = sx[i1], p3x = sx[i2];
@@ -541,7 +555,7 @@ __device__ __forceinline__ void geom_classify(const DevScene& S, const DevFrame&
     // queue full (many multi-pixel triangles in one chunk): this triangle's pixels in-thread
     for (int y = y0; y <= y1; y++)
       for (int x = x0; x <= x1; x++)
-        small_pixel<E, SHADOW, NM>(p1x, p1y, p1z, p2x, p2y, p2z, p3x, p3y, p3z, x, y, seq, F.W, keys, smap, cnt, NM ? keys + (size_t)F.W * F.H : nullptr);
+        small_pixel<E, SHADOW, NM, PEER>(p1x, p1y, p1z, p2x, p2y, p2z, p3x, p3y, p3z, x, y, seq, F.W, keys, smap, cnt, NM ? keys + (size_t)F.W * F.H : nullptr, dirty_rows);
   }
 }
 
@@ -600,10 +614,12 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_
   for (;;) {
     const float* trans_base = SHADOW ? V.trans[v] : reinterpret_cast<const float*>(F.xf);
     float* smap = SHADOW ? V.smap[v] : nullptr;
+    // peer groups: the row flags of this view's private target (see Counters.dirty); V.dirty is uniform, no dependent load per fragment
+    unsigned char* dirty_rows = LIST == 3 ? V.dirty + (size_t)(SHADOW ? V.target[v] : 0u) * F.H : nullptr;
     // ---- phase 2: one thread per triangle
     if (li != 0xFFFFFFFFu)
-      geom_classify<E, SHADOW, NM>(S, F, sm, buf, buf, li, tri, trans_base, trans_stride, keys, smap, large, large_cap, clipq, clip_cap, cnt, Fg,
-                               SHADOW ? V.target[v] : 0u, SHADOW ? V.r0[v] : F.rr0, SHADOW ? V.r1[v] : F.rr1);
+      geom_classify<E, SHADOW, NM, LIST == 3>(S, F, sm, buf, buf, li, tri, trans_base, trans_stride, keys, smap, large, large_cap, clipq, clip_cap, cnt, Fg,
+                                              SHADOW ? V.target[v] : 0u, SHADOW ? V.r0[v] : F.rr0, SHADOW ? V.r1[v] : F.rr1, dirty_rows);
     __syncthreads();
     // ---- phase 3 of this view (one thread per candidate pixel) overlapped with phase 1 of the next view (other buffer)
     const unsigned int nq = sm.qv[buf];
@@ -620,9 +636,9 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_
         const uint32_t ti = sm.idx[t], box = sm.box[t];
         const uint32_t i0 = ti & 1023u, i1 = (ti >> 10) & 1023u, i2 = (ti >> 20) & 1023u;
         const uint32_t bw = (box >> 28) + 1u, dy = (j * c_recip256[bw]) >> 8, dx = j - dy * bw;
-        small_pixel<E, SHADOW, NM>(sx[i0], sy[i0], sz[i0], sx[i1], sy[i1], sz[i1], sx[i2], sy[i2], sz[i2],
-                                   (int)((box & 0x3FFFu) + dx), (int)(((box >> 14) & 0x3FFFu) + dy),
-                                   (chunk * PRC_GEOM_THREADS + t) * 8u, F.W, keys, smap, cnt, NM ? keys + (size_t)F.W * F.H : nullptr);
+        small_pixel<E, SHADOW, NM, LIST == 3>(sx[i0], sy[i0], sz[i0], sx[i1], sy[i1], sz[i1], sx[i2], sy[i2], sz[i2],
+                                              (int)((box & 0x3FFFu) + dx), (int)(((box >> 14) & 0x3FFFu) + dy),
+                                              (chunk * PRC_GEOM_THREADS + t) * 8u, F.W, keys, smap, cnt, NM ? keys + (size_t)F.W * F.H : nullptr, dirty_rows);
       }
     }
     if (vn < 0) break;
@@ -812,7 +828,8 @@ __global__ void __launch_bounds__(256) k_medium_raster(const LargeRec* __restric
       const float z = w1 * r.z1 + w2 * r.z2 + w3 * r.z3;
       const size_t idx = (size_t)y * W + x;
       if (NM && !shadow) nan_first(keys + (size_t)W * H, idx, r.seq, z);
-      if (isnan(z)) { if (shadow) nan_sh++; else nan_cam++; continue; }
+      if (isnan(z)) { if (shadow) nan_sh++; else { nan_cam++; if (NM) mark_dirty(cnt, 0, y); } continue; }
+      mark_dirty(cnt, r.target, y);
       if (shadow) {
         if (z > 0.0f) atomicMax((int*)&smap[idx], __float_as_int(z));
       } else {
@@ -883,6 +900,7 @@ __global__ void __launch_bounds__(PRC_TILE * PRC_TILE) k_tile_raster(const Large
     if (nan_local) atomicAdd(shadow ? &cnt->n_nan_shadow : &cnt->n_nan, nan_local);
     if (!live) continue;
     const size_t idx = (size_t)y * W + x;
+    if ((shadow ? bestz > 0.0f : best != 0) || (NM && firstv != ~0ull)) mark_dirty(cnt, (uint32_t)target, y);
     if (NM && firstv != ~0ull) atomicMin(&keys[(size_t)W * H + idx], firstv);
     if (shadow) {
       if (bestz > 0.0f) atomicMax((int*)&targets->smap[target][idx], __float_as_int(bestz));

@@ -41,16 +41,15 @@ struct PeerTable {
 
 // what one k_peer_push launch merges into the peers
 struct PushJob {
-  // shadow maps: `n_sh` floats of this rank's private stacked maps -> every rank's merged maps
-  const float* sh_mine;
-  unsigned long long n_sh;
-  // visibility keys of the rows [ky0, ky1): private plane -> the merged plane (this frame's parity) of every rank that needs the row
-  const unsigned long long* k_mine;
+  int W, H;
+  uint32_t n_sh;                 // casting lights: rows [H, (1 + n_sh) H) of the row space are shadow rows (light k: [(1+k) H, (2+k) H))
+  unsigned char* dirty;          // [(1 + n_sh) H] row flags of this rank's private buffers (Counters.dirty), cleared here
+  float* sh_mine;                // private stacked shadow maps [n_sh][H][W], zeroed where read (clear-on-read)
+  unsigned long long* k_mine;    // private key plane [H][W], zeroed where read
   unsigned long long k_off;      // offset of this frame's parity plane inside mkeys[], in keys
-  int W, ky0, ky1;
   int rr0[PRC_PEER_MAX], rr1[PRC_PEER_MAX], ax1[PRC_PEER_MAX];  // rank p resolves rows [rr0, rr1) and [0, ax1) (+ pixel (0,0), always)
-  // NaN mode: first-fragment plane, merged with atomicMin (nullptr otherwise); f_off = offset of the merged plane
-  const unsigned long long* f_mine;
+  // NaN mode: first-fragment plane, merged with atomicMin (nullptr otherwise; reset to ~0 where read); f_off = offset of the merged plane
+  unsigned long long* f_mine;
   unsigned long long f_off;
 };
 
@@ -96,48 +95,43 @@ __global__ void k_peer_signal(PeerTable P, uint32_t kind, uint32_t epoch, uint32
 }
 
 // Merges what this rank rasterised into its peers (and into its own merged buffers) — see the file header. Shadow depths are
-// positive floats, which order like their int bits; depth 0 / key 0 is "nothing stored" and is skipped (a shadow map is
-// 95-98 % zeros on C3, the key plane of a rank holds the fragments of 1/N of the triangles). The reductions are
-// fire-and-forget (RED over NVLink), 16 bytes are tested per load.
+// positive floats, which order like their int bits; depth 0 / key 0 is "nothing stored" and is skipped. Only rows flagged by the
+// raster kernels are read (on C3 the scene covers a quarter of the screen rows and of each light's rows), and what is read
+// is reset, so the private buffers are empty again for the next frame without a clearing pass. The reductions are
+// fire-and-forget (RED over NVLink). One CTA per flagged row at a time.
 __global__ void __launch_bounds__(256) k_peer_push(const __grid_constant__ PeerTable P, const __grid_constant__ PushJob J) {
-  const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (unsigned long long)gridDim.x * blockDim.x;
-  // ---- shadow texels -> every rank
-  {
-    const float4* __restrict__ src = reinterpret_cast<const float4*>(J.sh_mine);
-    for (unsigned long long i = tid; i < J.n_sh / 4; i += stride) {
-      const float4 v = __ldg(src + i);
-      if (v.x == 0.0f && v.y == 0.0f && v.z == 0.0f && v.w == 0.0f) continue;
-      const float e[4] = {v.x, v.y, v.z, v.w};
-      for (uint32_t p = 0; p < P.world; p++) {
-        int* dst = reinterpret_cast<int*>(P.shadow[p]) + i * 4;
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-          if (e[k] != 0.0f) atomicMax(dst + k, __float_as_int(e[k]));
+  const int n_rows = (int)(1u + J.n_sh) * J.H;
+  for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    if (!J.dirty[row]) continue;  // (uniform over the CTA)
+    __syncthreads();              // every thread has read the flag
+    if (threadIdx.x == 0) J.dirty[row] = 0;
+    if (row >= J.H) {
+      // ---- a shadow row -> every rank's merged maps
+      const size_t base = (size_t)(row - J.H) * J.W;
+      for (int x = threadIdx.x; x < J.W; x += blockDim.x) {
+        const float v = J.sh_mine[base + x];
+        if (v == 0.0f) continue;
+        J.sh_mine[base + x] = 0.0f;
+        for (uint32_t p = 0; p < P.world; p++) atomicMax(reinterpret_cast<int*>(P.shadow[p]) + base + x, __float_as_int(v));
       }
-    }
-    for (unsigned long long i = (J.n_sh / 4) * 4 + tid; i < J.n_sh; i += stride) {
-      const float v = __ldg(J.sh_mine + i);
-      if (v == 0.0f) continue;
-      for (uint32_t p = 0; p < P.world; p++) atomicMax(reinterpret_cast<int*>(P.shadow[p]) + i, __float_as_int(v));
-    }
-  }
-  // ---- visibility keys -> the ranks that resolve the row
-  if (J.k_mine) {
-    const unsigned long long i0 = (unsigned long long)J.ky0 * J.W, i1 = (unsigned long long)J.ky1 * J.W;
-    for (unsigned long long i = i0 + tid * 2; i < i1; i += stride * 2) {
-      unsigned long long k2[2] = {J.k_mine[i], i + 1 < i1 ? J.k_mine[i + 1] : 0ull};
-      unsigned long long f2[2] = {~0ull, ~0ull};
-      if (J.f_mine) { f2[0] = J.f_mine[i]; if (i + 1 < i1) f2[1] = J.f_mine[i + 1]; }
-      if (!(k2[0] | k2[1]) && (f2[0] & f2[1]) == ~0ull) continue;
-#pragma unroll
-      for (int k = 0; k < 2; k++) {
-        if (!k2[k] && f2[k] == ~0ull) continue;
-        const unsigned long long idx = i + k;
-        const int y = (int)(idx / (unsigned long long)J.W);
+    } else {
+      // ---- a row of visibility keys -> the ranks that resolve it (pixel (0,0): every rank)
+      const int y = row;
+      uint32_t dst = 0;
+      for (uint32_t p = 0; p < P.world; p++)
+        if ((y >= J.rr0[p] && y < J.rr1[p]) || y < J.ax1[p]) dst |= 1u << p;
+      const size_t base = (size_t)y * J.W;
+      for (int x = threadIdx.x; x < J.W; x += blockDim.x) {
+        const unsigned long long k = J.k_mine[base + x];
+        const unsigned long long f = J.f_mine ? J.f_mine[base + x] : ~0ull;
+        if (!k && f == ~0ull) continue;
+        if (k) J.k_mine[base + x] = 0ull;
+        if (f != ~0ull) J.f_mine[base + x] = ~0ull;
+        const uint32_t d = (base + x == 0) ? ((1u << P.world) - 1u) : dst;
         for (uint32_t p = 0; p < P.world; p++) {
-          if (!((y >= J.rr0[p] && y < J.rr1[p]) || y < J.ax1[p] || idx == 0)) continue;
-          if (k2[k]) atomicMax(P.mkeys[p] + J.k_off + idx, k2[k]);
-          if (f2[k] != ~0ull) atomicMin(P.mkeys[p] + J.f_off + idx, f2[k]);
+          if (!((d >> p) & 1u)) continue;
+          if (k) atomicMax(P.mkeys[p] + J.k_off + base + x, k);
+          if (f != ~0ull) atomicMin(P.mkeys[p] + J.f_off + base + x, f);
         }
       }
     }
