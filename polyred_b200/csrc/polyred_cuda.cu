@@ -87,6 +87,8 @@ struct prc_ctx {
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   // readback overlapped with shading: the image leaves in row bands on a second stream while the next band is shaded
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t copy_stream2 = nullptr;  // peer frames: the shadow sweep runs here, beside the camera pass on `stream`
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_band[PRC_SHADE_BANDS_MAX] = {}, ev_copied = nullptr;
   int shade_bands = PRC_SHADE_BANDS;
   uint8_t* rb_dst = nullptr;  // page-locked destination of this frame's image (nullptr: no readback)
@@ -214,7 +216,7 @@ struct KTimer {
   size_t a;
   int cls;
   KTimer(prc_ctx* c, int k) : ctx(c), cls(k) {
-    if (!ctx->ktimers_frame) { cls = -1; return; }
+    if (!ctx->ktimers_frame || k < 0) { cls = -1; return; }
     while (ctx->evpool.size() < ctx->ev_used + 2) { cudaEvent_t e; cudaEventCreate(&e); ctx->evpool.push_back(e); }
     a = ctx->ev_used;
     ctx->ev_used += 2;
@@ -737,10 +739,13 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
       CK(cudaStreamWaitEvent(st, ctx->ev_copied, 0));
       ctx->copy_pending = false;
     }
+    {
+      KTimer kts(ctx, getenv("PRC_TIME_SPECIAL") ? PRC_K_RESOLVE : -1);
+      if (es) k_shade_special<E, E><<<1, 32, 0, st>>>(ctx->S, F, aoc, keys, G, (uint32_t*)ctx->d_special.p);
+      else k_shade_special<E, false><<<1, 32, 0, st>>>(ctx->S, F, aoc, keys, G, (uint32_t*)ctx->d_special.p);
+      ctx->launches++;
+    }
     KTimer kt(ctx, PRC_K_SHADE);
-    if (es) k_shade_special<E, E><<<1, 32, 0, st>>>(ctx->S, F, aoc, keys, G, (uint32_t*)ctx->d_special.p);
-    else k_shade_special<E, false><<<1, 32, 0, st>>>(ctx->S, F, aoc, keys, G, (uint32_t*)ctx->d_special.p);
-    ctx->launches++;
     // With a readback pending the strip is shaded in PRC_SHADE_BANDS row bands, top image rows first; each band's
     // device->host DMA runs on the copy stream while the next band is shaded (only the last band's copy is exposed).
     const bool banded_copy = ctx->rb_dst && ctx->msaa == 1;
@@ -934,6 +939,9 @@ int32_t prc_open(int32_t device, prc_ctx** out) {
   ctx->device = device;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PRC_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PRC_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PRC_ERR_CUDA; }
+  cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   for (auto& e : ctx->ev) cudaEventCreate(&e);
   for (auto& e : ctx->ev_band) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming);
@@ -996,6 +1004,9 @@ int32_t prc_close(prc_ctx* ctx) {
   for (auto& e : ctx->ev_band) if (e) cudaEventDestroy(e);
   if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return PRC_OK;
@@ -1528,10 +1539,23 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
   ctx->part_rank = P.self; ctx->part_world = P.world; ctx->part_active = true;  // (a group of one runs the same code path)
   ctx->keys_shade = nullptr; ctx->first_shade = nullptr;
   ctx->skip_key_clear = true;  // empty since the last push
-  int32_t r = do_main<E>(ctx, fr, Fr, 1, 1);
+  // The camera pass and the shadow sweep are independent (different targets, one shared queue filled by atomics) and, at 1/N of
+  // the triangles, each is only a few waves of CTAs long: they run on two streams so that one fills the other's tail.
+  static const bool two_streams = !(getenv("PRC_PEER_ONE_STREAM") != nullptr && atoi(getenv("PRC_PEER_ONE_STREAM")) != 0);
+  int32_t r = PRC_OK;
+  if (shadows && two_streams) {
+    CK(cudaEventRecord(ctx->ev_fork, st));
+    CK(cudaStreamWaitEvent(ctx->copy_stream2, ctx->ev_fork, 0));
+    ctx->stream = ctx->copy_stream2;
+    r = do_shadows<E>(ctx, fr, Fr, units_from_mask(fr, 0xFFFFFFFFu, 0, F.H), false);
+    cudaEventRecord(ctx->ev_join, ctx->copy_stream2);
+    ctx->stream = st;
+  }
+  if (r == PRC_OK) r = do_main<E>(ctx, fr, Fr, 1, 1);
   ctx->skip_key_clear = false;
   CK(cudaEventRecord(ctx->ev[1], st));
-  if (r == PRC_OK && shadows) r = do_shadows<E>(ctx, fr, Fr, units_from_mask(fr, 0xFFFFFFFFu, 0, F.H), false);
+  if (shadows && two_streams) CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+  else if (r == PRC_OK && shadows) r = do_shadows<E>(ctx, fr, Fr, units_from_mask(fr, 0xFFFFFFFFu, 0, F.H), false);
   if (r == PRC_OK) r = do_main<E>(ctx, fr, Fr, 4, 1);  // queued records of the camera AND the shadow passes
   ctx->part_rank = 0; ctx->part_world = 1; ctx->part_active = false;
   if (r != PRC_OK) return r;
@@ -1547,6 +1571,8 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
     J.k_off = (unsigned long long)(plane_cur - mk);
     J.f_mine = ctx->nan_mode ? (unsigned long long*)ctx->d_keys.p + npx : nullptr;
     J.f_off = (unsigned long long)(first_cur - mk);
+    static const bool full_push = getenv("PRC_PEER_FULL_PUSH") != nullptr && atoi(getenv("PRC_PEER_FULL_PUSH")) != 0;
+    J.full = full_push ? 1 : 0;
     KTimer kt(ctx, PRC_K_EXCHANGE);
     k_peer_push<<<148 * 8, 256, 0, st>>>(P, J);
     ctx->launches++;

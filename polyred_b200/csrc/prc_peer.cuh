@@ -51,6 +51,7 @@ struct PushJob {
   // NaN mode: first-fragment plane, merged with atomicMin (nullptr otherwise; reset to ~0 where read); f_off = offset of the merged plane
   unsigned long long* f_mine;
   unsigned long long f_off;
+  int full;                      // PRC_PEER_FULL_PUSH: send every non-empty shadow texel, also those the peers provably hold
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
@@ -106,12 +107,18 @@ __global__ void __launch_bounds__(256) k_peer_push(const __grid_constant__ PeerT
     __syncthreads();              // every thread has read the flag
     if (threadIdx.x == 0) J.dirty[row] = 0;
     if (row >= J.H) {
-      // ---- a shadow row -> every rank's merged maps
+      // ---- a shadow row -> every rank's merged maps. A depth that does not exceed what this rank's own merged map holds is
+      // not sent: every value in a merged map arrived by a push that goes to ALL ranks (and completes before its sender's
+      // signal, which every rank awaits before shading), so the peers hold — or are about to hold — at least that value.
+      // The maps are persistent and only grow (render/shadow.go:221-228), so for a scene that does not move the exchange
+      // shrinks to the texels that changed; PRC_PEER_FULL_PUSH=1 sends every non-empty texel every frame (`full`).
       const size_t base = (size_t)(row - J.H) * J.W;
+      const float* __restrict__ merged = P.shadow[P.self] + base;
       for (int x = threadIdx.x; x < J.W; x += blockDim.x) {
         const float v = J.sh_mine[base + x];
         if (v == 0.0f) continue;
         J.sh_mine[base + x] = 0.0f;
+        if (!J.full && !(v > merged[x])) continue;
         for (uint32_t p = 0; p < P.world; p++) atomicMax(reinterpret_cast<int*>(P.shadow[p]) + base + x, __float_as_int(v));
       }
     } else {
