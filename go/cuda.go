@@ -5,8 +5,9 @@
 // passed as uintptr, floats only inside fixed-layout structs (include/polyred_cuda.h).
 //
 // NOT compiled in the build image of polyred-b200 (no Go toolchain there); the same logic is mirrored
-// and tested in Python (polyred_b200/render.py). See INTEGRATION.md for the three one-line hooks this file
-// needs in options.go / raster.go.
+// and tested in Python (polyred_b200/render.py), and tests/test_abi.py checks the struct layouts below
+// against the C header with Go's alignment rules. See INTEGRATION.md for the reference-side patch (the hooks
+// in options.go / raster.go and the one accessor in buffer/texture.go this file needs).
 package render
 
 import (
@@ -32,9 +33,15 @@ import (
 
 // CUDA selects the B200 backend for the whole render pass. It mirrors GPU(dev) (options.go:103-110); the
 // renderer then never touches the CPU passes and never falls back: errors panic with the library message.
-func CUDA(device int) Option {
+// Several devices = every frame is rendered by all of them (a device group inside the library, prc_group_*:
+// raster passes partitioned by triangles, shading by screen strips, merged over NVLink) and is the one-device
+// frame bit for bit; no devices = device 0.
+func CUDA(devices ...int) Option {
 	return func(o *option) {
-		o.cudaDevice = device
+		if len(devices) == 0 {
+			devices = []int{0}
+		}
+		o.cudaDevices = append([]int(nil), devices...)
 		o.useCUDA = true
 		o.forceCPU = true // do not auto-open a Metal device (raster.go:110-122)
 	}
@@ -114,12 +121,14 @@ type prcFrame struct {
 }
 
 type cudaBackend struct {
-	lib                                                                  uintptr
+	lib                                                                                               uintptr
 	fnOpen, fnClose, fnLastError, fnSceneUpload, fnShadowReset, fnRender, fnHostImage, fnReadShadowmap uintptr
-	ctx                                                                  uintptr
+	fnGroupCtx                                                                                        uintptr
+	ctx                                                                                               uintptr // prc_group*
 
-	// flattened scene, kept alive while the library borrows it during prc_scene_upload
+	// what was flattened and uploaded: the scene and a signature of its membership (see sceneSignature)
 	uploadedFor *scene.Scene
+	uploadedSig uint64
 	nObjects    int
 }
 
@@ -131,7 +140,7 @@ func mat16(m math.Mat4[float32]) [16]float32 {
 	return [16]float32{m.X00, m.X01, m.X02, m.X03, m.X10, m.X11, m.X12, m.X13, m.X20, m.X21, m.X22, m.X23, m.X30, m.X31, m.X32, m.X33}
 }
 
-func openCUDA(device int) *cudaBackend {
+func openCUDA(devices []int) *cudaBackend {
 	lib, err := purego.Dlopen("libpolyred_cuda.so", purego.RTLD_NOW|purego.RTLD_GLOBAL)
 	if err != nil {
 		panic(fmt.Errorf("render: CUDA backend requested but libpolyred_cuda.so cannot be loaded: %w", err))
@@ -143,18 +152,58 @@ func openCUDA(device int) *cudaBackend {
 		}
 		return p
 	}
+	// the group calls have the signatures of the single-context ones; a group of one device IS the single context
 	b := &cudaBackend{lib: lib,
-		fnOpen: sym("prc_open"), fnClose: sym("prc_close"), fnLastError: sym("prc_last_error"),
-		fnSceneUpload: sym("prc_scene_upload"), fnShadowReset: sym("prc_shadow_reset"), fnRender: sym("prc_render"), fnHostImage: sym("prc_host_image"),
-		fnReadShadowmap: sym("prc_read_shadowmap")}
+		fnOpen: sym("prc_group_open"), fnClose: sym("prc_group_close"), fnLastError: sym("prc_group_last_error"),
+		fnSceneUpload: sym("prc_group_scene_upload"), fnShadowReset: sym("prc_group_shadow_reset"), fnRender: sym("prc_group_render"),
+		fnHostImage: sym("prc_group_host_image"), fnGroupCtx: sym("prc_group_ctx"), fnReadShadowmap: sym("prc_read_shadowmap")}
 	if v, _, _ := purego.SyscallN(sym("prc_abi_version")); uint32(v) != prcABIVersion {
 		panic("render: libpolyred_cuda.so ABI version mismatch")
 	}
-	if rc, _, _ := purego.SyscallN(b.fnOpen, uintptr(device), uintptr(unsafe.Pointer(&b.ctx))); int32(rc) != 0 {
-		panic(fmt.Errorf("render: prc_open(device %d) failed with %d (no CPU fallback)", device, int32(rc)))
+	devs := make([]int32, len(devices))
+	for i, d := range devices {
+		devs[i] = int32(d)
+	}
+	rc, _, _ := purego.SyscallN(b.fnOpen, uintptr(unsafe.Pointer(unsafe.SliceData(devs))), uintptr(len(devs)), uintptr(unsafe.Pointer(&b.ctx)))
+	runtime.KeepAlive(devs)
+	if int32(rc) != 0 {
+		panic(fmt.Errorf("render: prc_group_open(devices %v) failed with %d (no CPU fallback)", devices, int32(rc)))
 	}
 	runtime.SetFinalizer(b, func(b *cudaBackend) { purego.SyscallN(b.fnClose, b.ctx) })
 	return b
+}
+
+// sceneSignature changes when the scene's membership does: which geometries it holds, in which order, with how many
+// triangles and which materials (FNV-1a over pointers and counts). Model matrices are not part of it: the per-object
+// uniforms are rebuilt from the scene graph every frame, so a moved TransformContext never needs a re-upload. Vertex data
+// edited IN PLACE is not detected (as little as the reference detects it between NewRenderer and Render for its
+// buffered meshes): call Options(Scene(s)) again to force the upload.
+func sceneSignature(s *scene.Scene) uint64 {
+	h := uint64(14695981039346656037)
+	mix := func(v uint64) {
+		for i := 0; i < 8; i++ {
+			h ^= (v >> (8 * i)) & 0xff
+			h *= 1099511628211
+		}
+	}
+	scene.IterObjects(s, func(g *geometry.Geometry, _ math.Mat4[float32]) bool {
+		mix(uint64(uintptr(unsafe.Pointer(g))))
+		ts := g.Triangles()
+		mix(uint64(len(ts)))
+		if len(ts) > 0 {
+			mix(uint64(uintptr(unsafe.Pointer(ts[0]))))
+		}
+		for _, m := range g.Materials() {
+			if bp, _ := m.(*material.BlinnPhong); bp != nil {
+				mix(uint64(uintptr(unsafe.Pointer(bp))))
+				mix(uint64(uintptr(unsafe.Pointer(bp.Texture))))
+			} else {
+				mix(0)
+			}
+		}
+		return true
+	})
+	return h
 }
 
 func (b *cudaBackend) check(rc uintptr, what string) {
@@ -190,7 +239,12 @@ func (b *cudaBackend) uploadScene(s *scene.Scene) {
 		for _, m := range g.Materials() {
 			bp, _ := m.(*material.BlinnPhong)
 			pm := prcMaterial{Texture: -1, Flags: prcMatNil}
-			if bp != nil && bp.Texture != nil {
+			if bp != nil && bp.Texture == nil {
+				// FragmentShader dereferences m.Texture (shader/blinn_cpu.go:30-36): the reference panics there. No defined
+				// result => an error, never a silent change of appearance.
+				panic("render: BlinnPhong material without a texture (the CPU path nil-dereferences it, shader/blinn_cpu.go:30)")
+			}
+			if bp != nil {
 				pm = prcMaterial{Diffuse: rgba(bp.Diffuse), Specular: rgba(bp.Specular), Shininess: bp.Shininess}
 				if bp.FlatShading {
 					pm.Flags |= prcMatFlat
@@ -256,8 +310,8 @@ func (b *cudaBackend) uploadScene(s *scene.Scene) {
 	runtime.KeepAlive(pos); runtime.KeepAlive(nor); runtime.KeepAlive(uv); runtime.KeepAlive(col); runtime.KeepAlive(mat)
 	runtime.KeepAlive(objStart); runtime.KeepAlive(mats); runtime.KeepAlive(texFirst); runtime.KeepAlive(levelW)
 	runtime.KeepAlive(levelH); runtime.KeepAlive(levelOff); runtime.KeepAlive(texData)
-	b.check(rc, "prc_scene_upload")
-	b.uploadedFor, b.nObjects = s, len(objStart)-1
+	b.check(rc, "prc_group_scene_upload")
+	b.uploadedFor, b.uploadedSig, b.nObjects = s, sceneSignature(s), len(objStart)-1
 }
 
 // renderCUDA is (*Renderer).Render() for the CUDA backend (raster.go:155-199): it computes the same
@@ -266,18 +320,18 @@ func (b *cudaBackend) uploadScene(s *scene.Scene) {
 func (r *Renderer) renderCUDA() *image.RGBA {
 	b := r.cuda
 	if b == nil {
-		b = openCUDA(r.cfg.cudaDevice)
+		b = openCUDA(r.cfg.cudaDevices)
 		r.cuda = b
 	}
 	if r.cfg.BlendFunc != nil {
 		panic("render: CUDA backend does not support Blending")
 	}
-	if b.uploadedFor != r.cfg.Scene {
-		b.uploadScene(r.cfg.Scene)
+	if b.uploadedFor != r.cfg.Scene || b.uploadedSig != sceneSignature(r.cfg.Scene) {
+		b.uploadScene(r.cfg.Scene) // a new scene, or objects were added / removed / replaced (SURVEY 8f-2)
 	}
 	if r.cudaShadowDirty { // set by initShadowMaps (NewRenderer / Options): fresh zero maps (shadow.go:87)
 		rc, _, _ := purego.SyscallN(b.fnShadowReset, b.ctx)
-		b.check(rc, "prc_shadow_reset")
+		b.check(rc, "prc_group_shadow_reset")
 		r.cudaShadowDirty = false
 	}
 	// the frame buffer is MSAA times render.Size (resetBufs, raster.go:149); the library resizes back (raster.go:377)
@@ -356,7 +410,7 @@ func (r *Renderer) renderCUDA() *image.RGBA {
 	// (zero copy). Like the reference's own double buffer (raster.go:86,201-206) it is valid until two frames later.
 	rc, _, _ := purego.SyscallN(b.fnRender, b.ctx, uintptr(unsafe.Pointer(&f)), 0)
 	runtime.KeepAlive(objs); runtime.KeepAlive(lights); runtime.KeepAlive(amb); runtime.KeepAlive(shadowTrans)
-	b.check(rc, "prc_render")
+	b.check(rc, "prc_group_render")
 	if r.cfg.Debug && r.cfg.ShadowMap {
 		// render.Debug(true): passShadows saves shadow-<i>.png from shadowInfo.depths (shadow.go:98-118). The maps live in HBM;
 		// they are read back into the renderer's own depth slices (same size and index order, shadow.go:26-31,221-228) and
@@ -365,7 +419,10 @@ func (r *Renderer) renderCUDA() *image.RGBA {
 			if !l.CastShadow() {
 				continue
 			}
-			rc, _, _ := purego.SyscallN(b.fnReadShadowmap, b.ctx, uintptr(i), uintptr(unsafe.Pointer(unsafe.SliceData(r.shadowBufs[i].depths))))
+			var ctx0 uintptr // every rank of a group holds the merged maps: read rank 0's
+			rc, _, _ := purego.SyscallN(b.fnGroupCtx, b.ctx, 0, uintptr(unsafe.Pointer(&ctx0)))
+			b.check(rc, "prc_group_ctx")
+			rc, _, _ = purego.SyscallN(b.fnReadShadowmap, ctx0, uintptr(i), uintptr(unsafe.Pointer(unsafe.SliceData(r.shadowBufs[i].depths))))
 			b.check(rc, "prc_read_shadowmap")
 			img := image.NewRGBA(image.Rect(0, 0, w, h))
 			for x := 0; x < w; x++ {
@@ -381,7 +438,7 @@ func (r *Renderer) renderCUDA() *image.RGBA {
 	}
 	var ptr, n uint64
 	rc, _, _ = purego.SyscallN(b.fnHostImage, b.ctx, uintptr(unsafe.Pointer(&ptr)), uintptr(unsafe.Pointer(&n)))
-	b.check(rc, "prc_host_image")
+	b.check(rc, "prc_group_host_image")
 	ow, oh := r.cfg.Width, r.cfg.Height
 	r.outBuf = &image.RGBA{Pix: unsafe.Slice((*uint8)(unsafe.Pointer(uintptr(ptr))), int(n)), Stride: 4 * ow, Rect: image.Rect(0, 0, ow, oh)}
 	r.passGPU["forward"], r.passGPU["deferred"], r.passGPU["gamma"] = true, true, true

@@ -241,6 +241,13 @@ int32_t prc_shadow_reset(prc_ctx* ctx);
  * (row r = screen y = height-1-r, buffer.go:160-166, 225). With row0/row1 set, only image
  * rows of that strip are written. */
 int32_t prc_render(prc_ctx* ctx, const prc_frame* frame, uint8_t* rgba_out);
+/* A batch of views of the uploaded scene (BASELINE configs[4]; what a caller of the reference writes as a loop of
+ * Renderer.Options(render.Camera(c)) + Render(), render/options.go:125-141): frames[v] is the complete prc_frame of view v (its own
+ * camera, light cameras and per-object matrices; PRC_FRAME_SHADOW_RESET when the view re-fits the light cameras, as Options() does),
+ * rgba_out[v] the caller-owned image of view v (rgba_out or an entry may be NULL: that view is not copied out). The views are
+ * submitted back to back: view v+1's uniforms are uploaded and its geometry runs while view v is copied to the host.
+ * PRC_FRAME_ASYNC / KEEP_GBUFFER / UNIFORMS_RESIDENT are rejected. prc_get_timings then reports sums over the views. */
+int32_t prc_render_batch(prc_ctx* ctx, uint32_t n_views, const prc_frame* frames, uint8_t* const* rgba_out);
 /* Zero-copy result: with rgba_out == NULL the frame is left in one of two library-owned page-locked host images
  * used alternately (the reference's double buffer, render/raster.go:86,201-206: the returned *image.RGBA aliases
  * the buffer until two frames later). Returns that image (width*height*4 bytes, image order). */
@@ -328,6 +335,9 @@ int32_t prc_peer_wait_ms(prc_ctx* ctx, float out[4]);
  * each GPU then delivers its own strip over its own PCIe link and no device-side gather is needed (image_mask = 0).
  * ptr == NULL unregisters. */
 int32_t prc_set_host_image(prc_ctx* ctx, void* ptr, uint64_t bytes);
+/* The frames submitted from now on are read back to ptr + offset of the registered range: several images inside ONE registration
+ * (page-locking is expensive), e.g. two used alternately like the reference's double buffer (render/raster.go:86,201-206). */
+int32_t prc_set_host_image_offset(prc_ctx* ctx, uint64_t offset);
 
 /* Sticky per-context render state that a frame can switch on (the reporting frame is re-rendered, PRC_ERR_RETRY for frames submitted
  * back to back): NaN mode (a camera pass produced a NaN-depth fragment: the first-fragment plane of bug-list 8 is maintained from then
@@ -344,6 +354,39 @@ int32_t prc_count_covered(prc_ctx* ctx, uint64_t* covered);
 /* Measured FP32 FMA throughput of this device in TFLOP/s (2 flop per FMA; a pure-FMA micro-benchmark, best of a few launches):
  * the denominator of the shading kernels' roofline. No reference counterpart (measurement only). */
 int32_t prc_measure_fp32_peak(prc_ctx* ctx, double* tflops);
+
+/* ---- device groups: ONE process, one context per device, one submit thread per device inside the library ----------------
+ * What `render.CUDA(devices ...int)` binds when it is given more than one device: the multi-device
+ * counterpart of render.GPU(dev) (render/options.go:103-110; the reference's gpu.Open takes one device, gpu/device.go:77-89).
+ * A group owns its contexts; the calls below mirror the single-context ones and hide the whole peer protocol above
+ * (export / connect over cudaDeviceEnablePeerAccess, the strip partition and its load balancing, the retry vote):
+ *   prc_group_render       one frame over all devices = prc_render_peer on every context from the group's own threads:
+ *                          raster passes partitioned by triangles, shading by screen strips balanced by measured time, every
+ *                          device DMAs its strip into ONE page-locked host image (rgba_out may be NULL: read it in place through
+ *                          prc_group_host_image). frame->row0/row1 must be 0/height. The result is the 1-GPU frame bit for bit.
+ *                          With PRC_FRAME_NO_READBACK the strips are gathered into context 0's device image instead
+ *                          (prc_group_ctx(g, 0) + prc_device_image), and with PRC_FRAME_ASYNC on top the call does not wait:
+ *                          prc_group_sync finishes the frames (PRC_ERR_RETRY = submit them again, as for prc_sync).
+ *   prc_group_render_views a batch of views dealt round-robin to the devices (view v on device v mod n), each device running
+ *                          prc_render_batch on its share: no exchange at all (BASELINE configs[4]).
+ * A device may be listed more than once (several contexts of one GPU: how the single-GPU tests exercise the protocol).
+ * Every call returns 0 or a PRC_ERR_* code; prc_group_last_error names the failing rank. One call at a time per group. */
+typedef struct prc_group prc_group;
+int32_t prc_group_open(const int32_t* devices, uint32_t n, prc_group** out);
+int32_t prc_group_close(prc_group* g);
+const char* prc_group_last_error(prc_group* g);
+uint32_t prc_group_size(prc_group* g);
+/* The context of rank `rank` (owned by the group) for the read-only / debug calls: prc_get_timings, prc_read_shadowmap,
+ * prc_device_image, prc_peer_wait_ms. */
+int32_t prc_group_ctx(prc_group* g, uint32_t rank, prc_ctx** out);
+int32_t prc_group_scene_upload(prc_group* g, const prc_scene* scene); /* replicated on every device, uploads run in parallel */
+int32_t prc_group_shadow_reset(prc_group* g);
+int32_t prc_group_render(prc_group* g, const prc_frame* frame, uint8_t* rgba_out);
+int32_t prc_group_sync(prc_group* g);
+int32_t prc_group_host_image(prc_group* g, uint64_t* host_ptr, uint64_t* bytes);
+/* The strip (screen rows [row0, row1)) every rank shaded in the last frame; arrays of prc_group_size entries. */
+int32_t prc_group_strips(prc_group* g, uint32_t* row0, uint32_t* row1);
+int32_t prc_group_render_views(prc_group* g, uint32_t n_views, const prc_frame* frames, uint8_t* const* rgba_out);
 
 /* Arithmetic mode of this context, overriding the PRC_FMA environment variable read by prc_open:
  * exact != 0 -> math.FMA[float32] emulated bit-exactly everywhere (float64 fma rounded to float32, math/math.go FMA),

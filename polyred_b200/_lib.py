@@ -64,6 +64,26 @@ def lib():
         L.prc_peer_wait_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]
         L.prc_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double)]
         L.prc_count_covered.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.prc_render_batch.argtypes = [vp, C.c_uint32, C.POINTER(A.prc_frame), C.POINTER(vp)]
+        L.prc_set_host_image_offset.argtypes = [vp, C.c_uint64]
+        # device groups (one process, one context per device)
+        L.prc_group_open.argtypes = [C.POINTER(C.c_int32), C.c_uint32, C.POINTER(vp)]
+        L.prc_group_close.argtypes = [vp]
+        L.prc_group_last_error.argtypes = [vp]
+        L.prc_group_last_error.restype = C.c_char_p
+        L.prc_group_size.argtypes = [vp]
+        L.prc_group_size.restype = C.c_uint32
+        L.prc_group_ctx.argtypes = [vp, C.c_uint32, C.POINTER(vp)]
+        L.prc_group_scene_upload.argtypes = [vp, C.POINTER(A.prc_scene)]
+        L.prc_group_shadow_reset.argtypes = [vp]
+        L.prc_group_render.argtypes = [vp, C.POINTER(A.prc_frame), vp]
+        L.prc_group_sync.argtypes = [vp]
+        L.prc_group_host_image.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.prc_group_strips.argtypes = [vp, vp, vp]
+        L.prc_group_render_views.argtypes = [vp, C.c_uint32, C.POINTER(A.prc_frame), C.POINTER(vp)]
+        for name in ("prc_render_batch", "prc_set_host_image_offset", "prc_group_open", "prc_group_close", "prc_group_ctx", "prc_group_scene_upload",
+                     "prc_group_shadow_reset", "prc_group_render", "prc_group_sync", "prc_group_host_image", "prc_group_strips", "prc_group_render_views"):
+            getattr(L, name).restype = C.c_int32
         for name in ("prc_open", "prc_close", "prc_scene_upload", "prc_shadow_reset", "prc_render", "prc_read_gbuffer",
                      "prc_read_shadowmap", "prc_get_timings", "prc_device_image", "prc_device_shadowmap",
                      "prc_render_shadows", "prc_render_main", "prc_stream", "prc_sync", "prc_host_image", "prc_render_forward",
@@ -254,6 +274,10 @@ class CudaBackend(Backend):
     def set_frame_state(self, state: int):
         self._check(self.L.prc_set_frame_state(self.h, state))
 
+    def render_batch(self, fds, outs=None):
+        """prc_render_batch: the views `fds` (FrameDescs) submitted back to back; outs[v] = (H, W, 4) u8 array or None."""
+        _render_views(self.L.prc_render_batch, self, fds, outs)
+
     def covered_pixels(self, w=None, h=None) -> int:
         """Covered pixels (visibility key set) of the last frame rendered by this context."""
         out = C.c_uint64(0)
@@ -271,3 +295,79 @@ class CudaBackend(Backend):
         out = (C.c_float * 4)()
         self._check(self.L.prc_peer_wait_ms(self.h, C.byref(out)))
         return dict(zip(("shadow_rows", "peers_shaded", "image_strips", "image_free"), (float(x) for x in out)))
+
+
+def _render_views(fn, backend, fds, outs):
+    n = len(fds)
+    frames = (A.prc_frame * max(1, n))()
+    for v, fd in enumerate(fds):
+        C.memmove(C.byref(frames[v]), C.byref(fd.struct), C.sizeof(A.prc_frame))
+    ptrs = (C.c_void_p * max(1, n))()
+    for v in range(n):
+        o = outs[v] if outs is not None else None
+        ptrs[v] = o.ctypes.data if o is not None else None
+    backend._check(fn(backend.h, n, frames, ptrs))
+
+
+class GroupBackend(Backend):
+    """A device group behind the C ABI (include/polyred_cuda.h prc_group_*): one process, one context per device, one submit
+    thread per device inside the library. Same surface as CudaBackend; render() produces the 1-GPU frame bit for bit."""
+
+    prefix = "prc_group"
+
+    def __init__(self, devices):
+        L = lib()
+        devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = L.prc_group_open(devs, len(devices), C.byref(h))
+        if rc != 0:
+            raise PolyredCudaError(rc, f"prc_group_open(devices={list(devices)}) failed (are the CUDA devices visible? there is no CPU fallback)")
+        super().__init__(L, h)
+        self.devices = [int(d) for d in devices]
+
+    def size(self) -> int:
+        return int(self.L.prc_group_size(self.h))
+
+    def rank(self, k: int) -> "CudaBackend":
+        """Rank k's context as a (non-owning) CudaBackend, for the read-only / debug calls."""
+        c = C.c_void_p()
+        self._check(self.L.prc_group_ctx(self.h, k, C.byref(c)))
+        b = CudaBackend.__new__(CudaBackend)
+        Backend.__init__(b, self.L, c)
+        b.device = self.devices[k]
+        b.close = lambda: None  # owned by the group
+        return b
+
+    def host_image(self, w, h) -> np.ndarray:
+        """The last frame, in place in the group's page-locked double buffer (valid during the next render(), like the reference's)."""
+        p, n = C.c_uint64(), C.c_uint64()
+        self._check(self.L.prc_group_host_image(self.h, C.byref(p), C.byref(n)))
+        key = (p.value, n.value, w, h)
+        views = self.__dict__.setdefault("_host_views", {})
+        if key not in views:
+            buf = (C.c_uint8 * n.value).from_address(p.value)
+            views[key] = np.frombuffer(buf, dtype=np.uint8).reshape(h, w, 4)
+        return views[key]
+
+    def sync(self):
+        self._check(self.L.prc_group_sync(self.h))
+
+    def strips(self):
+        n = self.size()
+        r0, r1 = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        self._check(self.L.prc_group_strips(self.h, r0.ctypes.data, r1.ctypes.data))
+        return list(zip(r0.tolist(), r1.tolist()))
+
+    def timings(self):
+        """Rank 0's timings (per-rank: rank(k).timings())."""
+        return self.rank(0).timings()
+
+    def read_shadowmap(self, light, w, h):
+        return self.rank(0).read_shadowmap(light, w, h)  # every rank holds the merged maps
+
+    def read_gbuffer(self, w, h):
+        raise PolyredCudaError(A.PRC_ERR_UNSUPPORTED, "a group frame keeps no G-buffer (PRC_FRAME_KEEP_GBUFFER is a single-context debug option)")
+
+    def render_batch(self, fds, outs=None):
+        """prc_group_render_views: view v on device v mod n, every device running prc_render_batch on its share."""
+        _render_views(self.L.prc_group_render_views, self, fds, outs)

@@ -92,6 +92,11 @@ struct prc_ctx {
   cudaEvent_t ev_band[PRC_SHADE_BANDS_MAX] = {}, ev_copied = nullptr;
   int shade_bands = PRC_SHADE_BANDS;
   uint8_t* rb_dst = nullptr;  // page-locked destination of this frame's image (nullptr: no readback)
+  // prc_render_batch: page-locked staging of the per-view uniforms, two halves used alternately (see upload())
+  uint8_t* stage = nullptr;
+  size_t stage_cap = 0, stage_off = 0, stage_end = 0;
+  bool stage_on = false;
+  cudaEvent_t ev_view[2] = {nullptr, nullptr};
   // MSAA: the shaded frame is W x H = msaa x the output; k_resize writes the (W/msaa) x (H/msaa) frame that is handed back
   int pending_async = 0;  // PRC_FRAME_ASYNC frames submitted since the last finish (their spans / overflow flag are still open)
   int msaa = 1;
@@ -124,7 +129,7 @@ struct prc_ctx {
   uint32_t peer_epoch = 0;
   uint8_t* ext_img = nullptr;    // caller-owned page-locked host image (prc_set_host_image)
   bool defer_copy_join = false, copy_pending = false;  // see do_main: readback of peer frames overlaps the next frame's geometry
-  size_t ext_img_bytes = 0;
+  size_t ext_img_bytes = 0, ext_img_off = 0;  // ext_img_off: prc_set_host_image_offset (double-buffered host images inside one registration)
   bool ext_img_registered = false;
   // MSAA frames cut into strips (prc_render_peer only): the rank shades `msaa` extra supersampled rows on either side of the
   // rows it owns — all the downsample filter reaches — and resizes only its own output rows; no exchange is needed
@@ -171,7 +176,16 @@ int32_t ensure(prc_ctx* ctx, DBuf& b, size_t bytes) {
 
 int32_t upload(prc_ctx* ctx, DBuf& b, const void* src, size_t bytes) {
   ENSURE(b, bytes);
-  if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (!bytes) return PRC_OK;
+  if (ctx->stage_on && ctx->stage_off + bytes <= ctx->stage_end) {
+    // view batches: a copy from pageable memory makes the driver wait for the stream before it stages the data, which would
+    // serialise every view's uniforms behind the previous view's kernels — stage them in page-locked memory here instead
+    memcpy(ctx->stage + ctx->stage_off, src, bytes);
+    CK(cudaMemcpyAsync(b.p, ctx->stage + ctx->stage_off, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stage_off += (bytes + 255) & ~(size_t)255;
+    return PRC_OK;
+  }
+  CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return PRC_OK;
 }
 #define UPLOAD(buf, src, bytes)                    \
@@ -421,7 +435,13 @@ int32_t build_frame(prc_ctx* ctx, const prc_frame* fr, DevFrame& F) {
     ctx->gbuffer_valid = false;
   }
   ENSURE(ctx->d_keys, npx * 8 * (ctx->nan_mode ? 2 : 1));
-  ENSURE(ctx->d_ga, npx * 16); ENSURE(ctx->d_gb, npx * 16); ENSURE(ctx->d_gc, npx * 16); ENSURE(ctx->d_gd, npx * 16);
+  for (DBuf* g : {&ctx->d_ga, &ctx->d_gb, &ctx->d_gc, &ctx->d_gd}) {
+    // zeroed once when (re)allocated: the resolve only writes covered pixels and prc_read_gbuffer copies whole planes
+    // (compute-sanitizer initcheck flagged the never-written texels of that debug read)
+    const size_t before = g->p ? g->cap : 0;
+    ENSURE(*g, npx * 16);
+    if (g->cap != before) CK(cudaMemsetAsync(g->p, 0, g->cap, st));
+  }
   if (ctx->any_ao) ENSURE(ctx->d_ao, npx * 4);
   // slack: the multi-GPU image all-gather uses equal, padded strips. Whole 2 MiB pages: the buffer can be exported through CUDA
   // IPC (prc_peer_export), which shares entire allocation blocks — an exported buffer must not share its block with others
@@ -823,6 +843,7 @@ int32_t readback_begin(prc_ctx* ctx, const prc_frame* fr) {
   const uint32_t ms = fr->msaa > 1 ? fr->msaa : 1;
   const size_t total = (size_t)(fr->width / ms) * (fr->height / ms) * 4;  // the frame handed back (after the MSAA downsample)
   if (ctx->h_img_cap < total) {
+    CK(cudaStreamSynchronize(ctx->stream));  // (a view batch may still be copying into the old images)
     for (auto& p : ctx->h_img) { if (p) { cudaHostUnregister(p); free(p); } p = nullptr; }
     for (auto& p : ctx->h_img) {
       // first-touched by this thread (NUMA-local), then page-locked
@@ -998,6 +1019,8 @@ int32_t prc_close(prc_ctx* ctx) {
   for (auto& b : ctx->d_shadow_trans) free_buf(b);
   for (auto& p : ctx->h_img) if (p) { cudaHostUnregister(p); free(p); }
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+  if (ctx->stage) cudaFreeHost(ctx->stage);
+  for (auto& e : ctx->ev_view) if (e) cudaEventDestroy(e);
   if (ctx->h_list_hint) cudaFreeHost(ctx->h_list_hint);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   for (auto& e : ctx->evpool) cudaEventDestroy(e);
@@ -1294,6 +1317,85 @@ int32_t prc_render(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out) {
   return PRC_ERR_UNSUPPORTED;
 }
 
+// A batch of views (BASELINE configs[4]): every view is a whole Render() with its own uniforms. The views are submitted back to
+// back; view v's uniforms are staged in page-locked memory and uploaded behind view v-1's kernels, and while the GPU renders view v
+// the host copies view v-1 out of the library's page-locked double buffer into the caller's memory.
+int32_t prc_render_batch(prc_ctx* ctx, uint32_t n, const prc_frame* frames, uint8_t* const* rgba_out) {
+  if (!ctx) return PRC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return PRC_OK;
+  if (!frames) { ctx->err = "prc_render_batch: frames is NULL"; return PRC_ERR_INVALID; }
+  if (ctx->peer_private) { ctx->err = "this context is connected to a peer group: prc_peer_disconnect first"; return PRC_ERR_INVALID; }
+  if (ctx->pending_async) { const int32_t pr_ = prc_sync(ctx); if (pr_ != PRC_OK) return pr_; }
+  size_t half = 0;
+  for (uint32_t v = 0; v < n; v++) {
+    const prc_frame& fr = frames[v];
+    if (fr.abi_version != PRC_ABI_VERSION) { ctx->err = "prc_frame: bad abi_version"; return PRC_ERR_INVALID; }
+    if (fr.flags & (PRC_FRAME_ASYNC | PRC_FRAME_KEEP_GBUFFER | PRC_FRAME_UNIFORMS_RESIDENT)) {
+      ctx->err = "prc_render_batch: PRC_FRAME_ASYNC, PRC_FRAME_KEEP_GBUFFER and PRC_FRAME_UNIFORMS_RESIDENT are not supported";
+      return PRC_ERR_INVALID;
+    }
+    size_t need = (size_t)fr.n_objects * sizeof(prc_object_xf) + (size_t)fr.n_lights * sizeof(DevLight) + sizeof(TileTargets) + (size_t)fr.n_ambient * 4 + 256 +
+                  sizeof(DevFrame) + 256 * 8;
+    for (uint32_t i = 0; i < fr.n_lights && fr.lights; i++)
+      if (fr.lights[i].cast_shadow) need += (size_t)fr.n_objects * 64 + 256;
+    half = std::max(half, need);
+  }
+  half = (half + 4095) & ~(size_t)4095;
+  if (ctx->stage_cap < 2 * half) {
+    if (ctx->stage) cudaFreeHost(ctx->stage);
+    ctx->stage = nullptr; ctx->stage_cap = 0;
+    CK(cudaMallocHost((void**)&ctx->stage, 2 * half));
+    ctx->stage_cap = 2 * half;
+  }
+  for (auto& e : ctx->ev_view)
+    if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  auto abandon = [&](int32_t code) {  // a view failed to enqueue: finish what is in flight, drop the batch's timing state
+    ctx->stage_on = false;
+    cudaStreamSynchronize(ctx->stream);
+    ctx->pending_async = 0;
+    ctx->spans.clear();
+    ctx->ev_used = 0;
+    return code;
+  };
+  for (int attempt = 0; attempt < 4; attempt++) {
+    uint8_t* src[2] = {nullptr, nullptr};
+    size_t bytes[2] = {0, 0};
+    for (uint32_t v = 0; v < n; v++) {
+      const prc_frame* fr = &frames[v];
+      ctx->stage_on = true;
+      ctx->stage_off = (v & 1u) * half;
+      ctx->stage_end = ctx->stage_off + half;
+      DevFrame F;
+      int32_t r = build_frame(ctx, fr, F);
+      ctx->stage_on = false;
+      if (r != PRC_OK) return abandon(r);
+      if ((r = readback_begin(ctx, fr)) != PRC_OK) return abandon(r);
+      ctx->pending_async = v ? 1 : 0;  // (views after the first keep the batch's sticky overflow flag and statistics, see enqueue_frame)
+      if (ctx->ev_used > 8192) { ctx->spans.clear(); ctx->ev_used = 0; }  // bound the timing-event pool: drop the oldest views' spans
+      if ((r = enqueue_frame(ctx, fr, F)) != PRC_OK) return abandon(r);
+      if (cudaEventRecord(ctx->ev_view[v & 1u], ctx->stream) != cudaSuccess) return abandon(PRC_ERR_CUDA);
+      const uint32_t ms = fr->msaa > 1 ? fr->msaa : 1;
+      src[v & 1u] = ctx->rb_dst;
+      bytes[v & 1u] = (size_t)(fr->width / ms) * (fr->height / ms) * 4;
+      if (v > 0) {
+        const uint32_t p = (v - 1) & 1u;
+        if (cudaEventSynchronize(ctx->ev_view[p]) != cudaSuccess) return abandon(PRC_ERR_CUDA);
+        if (rgba_out && rgba_out[v - 1] && src[p]) memcpy(rgba_out[v - 1], src[p], bytes[p]);
+      }
+    }
+    const uint32_t p = (n - 1) & 1u;
+    if (cudaEventSynchronize(ctx->ev_view[p]) != cudaSuccess) return abandon(PRC_ERR_CUDA);
+    ctx->pending_async = 0;
+    const int32_t r = finish_timings(ctx);  // timings and statistics are sums over the views
+    if (r == PRC_RETRY) continue;           // a queue overflowed in some view: every view again (idempotent, the maps only grow or are reset per view)
+    if (r == PRC_OK && rgba_out && rgba_out[n - 1] && src[p]) memcpy(rgba_out[n - 1], src[p], bytes[p]);
+    return r;
+  }
+  ctx->err = "bin array kept overflowing";
+  return PRC_ERR_UNSUPPORTED;
+}
+
 int32_t prc_read_gbuffer(prc_ctx* ctx, prc_gbuffer_host* g) {
   if (!ctx || !g) return PRC_ERR_INVALID;
   if (ctx->pending_async) { const int32_t pr_ = prc_sync(ctx); if (pr_ != PRC_OK) return pr_; }  // finish asynchronous frames first
@@ -1532,7 +1634,7 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
     if (ctx->nan_mode) CK(cudaMemsetAsync(first_next, 0xFF, 8, st));
   }
   // strip readback into the caller's (shared) host image, band by band behind the shading kernels
-  ctx->rb_dst = (!(fr->flags & PRC_FRAME_NO_READBACK) && ctx->ext_img) ? ctx->ext_img : nullptr;
+  ctx->rb_dst = (!(fr->flags & PRC_FRAME_NO_READBACK) && ctx->ext_img) ? ctx->ext_img + ctx->ext_img_off : nullptr;
   // ---- raster passes: this rank's share of the triangles, every row, private targets
   DevFrame Fr = F;
   Fr.rr0 = 0; Fr.rr1 = F.H;
@@ -1636,8 +1738,8 @@ int32_t prc_peer_export(prc_ctx* ctx, const prc_frame* fr, prc_peer_handle* out)
     // the private planes start empty and are emptied again by every push (clear-on-read): keys 0, first-fragment plane ~0
     CK(cudaMemsetAsync(ctx->d_keys.p, 0, npx_ * 8, ctx->stream));
     CK(cudaMemsetAsync((unsigned long long*)ctx->d_keys.p + npx_, 0xFF, npx_ * 8, ctx->stream));
-    ENSURE(ctx->d_dirty, (size_t)33 * fr->height);
-    CK(cudaMemsetAsync(ctx->d_dirty.p, 0, (size_t)33 * fr->height, ctx->stream));
+    ENSURE(ctx->d_dirty, (size_t)33 * fr->height * PRC_DIRTY_STRIDE);
+    CK(cudaMemsetAsync(ctx->d_dirty.p, 0, (size_t)33 * fr->height * PRC_DIRTY_STRIDE, ctx->stream));
     struct { unsigned char* p; int h; } dd = {(unsigned char*)ctx->d_dirty.p, (int)fr->height};
     CK(cudaMemcpyAsync((char*)ctx->d_counters.p + offsetof(Counters, dirty), &dd.p, sizeof(dd.p), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync((char*)ctx->d_counters.p + offsetof(Counters, dirty_h), &dd.h, sizeof(dd.h), cudaMemcpyHostToDevice, ctx->stream));
@@ -1748,6 +1850,7 @@ int32_t prc_set_host_image(prc_ctx* ctx, void* ptr, uint64_t bytes) {
     if (ctx->ext_img_registered) cudaHostUnregister(ctx->ext_img);
     ctx->ext_img = nullptr;
     ctx->ext_img_bytes = 0;
+    ctx->ext_img_off = 0;
   }
   if (!ptr) return PRC_OK;
   {
@@ -1759,6 +1862,14 @@ int32_t prc_set_host_image(prc_ctx* ctx, void* ptr, uint64_t bytes) {
   }
   ctx->ext_img = (uint8_t*)ptr;
   ctx->ext_img_bytes = (size_t)bytes;
+  ctx->ext_img_off = 0;
+  return PRC_OK;
+}
+
+int32_t prc_set_host_image_offset(prc_ctx* ctx, uint64_t offset) {
+  if (!ctx) return PRC_ERR_INVALID;
+  if (!ctx->ext_img || offset >= ctx->ext_img_bytes) { ctx->err = "prc_set_host_image_offset: no host image registered, or the offset lies outside it"; return PRC_ERR_INVALID; }
+  ctx->ext_img_off = (size_t)offset;  // host-side state read when the next frame is enqueued: no wait needed
   return PRC_OK;
 }
 
@@ -1788,7 +1899,7 @@ int32_t prc_render_peer(prc_ctx* ctx, const prc_frame* fr, uint32_t n_ranks, con
   }
   if (n_ranks != ctx->peers.world || !row0 || !row1) { ctx->err = "prc_render_peer: row0/row1 must list the strip of every rank of the group"; return PRC_ERR_INVALID; }
   if (row0[ctx->peers.self] != fr->row0 || row1[ctx->peers.self] != fr->row1) { ctx->err = "prc_render_peer: frame.row0/row1 differ from this rank's entry of row0/row1"; return PRC_ERR_INVALID; }
-  if (!(fr->flags & PRC_FRAME_NO_READBACK) && ctx->ext_img && ctx->ext_img_bytes < (size_t)(fr->width / ms) * (fr->height / ms) * 4) {
+  if (!(fr->flags & PRC_FRAME_NO_READBACK) && ctx->ext_img && ctx->ext_img_bytes < ctx->ext_img_off + (size_t)(fr->width / ms) * (fr->height / ms) * 4) {
     ctx->err = "prc_render_peer: the host image registered with prc_set_host_image is smaller than the frame";
     return PRC_ERR_INVALID;
   }

@@ -105,9 +105,13 @@ struct Counters {
   unsigned char* dirty;
   int dirty_h;
 };
+// One flag per 32-byte sector: with the flags packed (H bytes = 17 cache lines for a 4K frame) every fragment of a pass stored into
+// the same few L2 lines, and those stores serialised — measured at 2 GPUs: the camera pass over half of the triangles took 0.140 ms
+// against 0.174 ms for all of them on one GPU.
+#define PRC_DIRTY_STRIDE 32
 __device__ __forceinline__ void mark_dirty(const Counters* cnt, uint32_t target, int y) {  // not for the hot path (a dependent global load)
   unsigned char* d = cnt->dirty;
-  if (d) d[(size_t)target * cnt->dirty_h + y] = 1;
+  if (d) d[((size_t)target * cnt->dirty_h + y) * PRC_DIRTY_STRIDE] = 1;
 }
 
 // warp-aggregated slot reservation: one atomicAdd per warp for all lanes that reach this point together
@@ -428,7 +432,7 @@ __device__ __forceinline__ void small_pixel(const float p1x, const float p1y, co
   const float z = w1 * p1z + w2 * p2z + w3 * p3z;
   const size_t idx = (size_t)y * W + x;
   if (NM && !SHADOW) nan_first(first, idx, seq, z);
-  if (PEER && (!SHADOW || z > 0.0f || (NM && isnan(z)))) dirty_rows[y] = 1;  // peer groups: this row of the private buffer holds something
+  if (PEER && (!SHADOW || z > 0.0f || (NM && isnan(z)))) dirty_rows[(size_t)y * PRC_DIRTY_STRIDE] = 1;  // peer groups: this row of the private buffer holds something
   if (isnan(z)) { atomicAdd(SHADOW ? &cnt->n_nan_shadow : &cnt->n_nan, 1ULL); return; }
   // fire-and-forget reductions (RED.MAX): no pre-test load, so nothing waits on memory
   if (SHADOW) {
@@ -615,7 +619,7 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_
     const float* trans_base = SHADOW ? V.trans[v] : reinterpret_cast<const float*>(F.xf);
     float* smap = SHADOW ? V.smap[v] : nullptr;
     // peer groups: the row flags of this view's private target (see Counters.dirty); V.dirty is uniform, no dependent load per fragment
-    unsigned char* dirty_rows = LIST == 3 ? V.dirty + (size_t)(SHADOW ? V.target[v] : 0u) * F.H : nullptr;
+    unsigned char* dirty_rows = LIST == 3 ? V.dirty + (size_t)(SHADOW ? V.target[v] : 0u) * F.H * PRC_DIRTY_STRIDE : nullptr;
     // ---- phase 2: one thread per triangle
     if (li != 0xFFFFFFFFu)
       geom_classify<E, SHADOW, NM, LIST == 3>(S, F, sm, buf, buf, li, tri, trans_base, trans_stride, keys, smap, large, large_cap, clipq, clip_cap, cnt, Fg,
@@ -954,6 +958,36 @@ __device__ __forceinline__ V4 unproject_std(const DevFrame& F, const V4& p) {
   return o;
 }
 
+// Out-of-line literal sequences of the resolve stage (rare inputs; the hot kernels are instruction-cache bound, see query_bilinear_wide).
+// The kernels take their parameter structs as __grid_constant__, so passing their addresses does not copy them to local memory.
+template <bool E>
+__device__ __noinline__ ScreenTri tri_setup_literal(const DevFrame* F, const float* __restrict__ trans, float p0, float p1, float p2, float p3, float p4, float p5,
+                                                    float p6, float p7, float p8) {
+  const float p[9] = {p0, p1, p2, p3, p4, p5, p6, p7, p8};
+  ScreenTri st;
+  tri_setup<E>(trans, F->viewport, F->pm_viewport, F->cullW, F->cullH, p, true, st);
+  return st;
+}
+template <bool EA>
+__device__ __noinline__ V4 unproject_literal(const DevFrame* F, V4 p) {  // raster.go:467-469
+  return apply4m<EA>(apply4m<EA>(apply4m<EA>(p, F->viewport_inv, F->pm_viewport_inv), F->proj_inv, F->pm_proj_inv), F->view_inv, F->pm_view_inv);
+}
+// The screen triangle of the resolve stage. With the standard viewport matrix and finite, non-zero clip z / w the transform is the
+// one phase 1 of k_geom_raster runs (Mat4.MulV, viewport_pos_std — bit for bit the reference's Apply(Viewport).Pos(), proof there);
+// anything else takes the literal tri_setup, as the triangle did in the geometry pass (geom_generic).
+template <bool E>
+__device__ __forceinline__ void resolve_screen_tri(const DevFrame& F, const float* __restrict__ trans, const float* p, ScreenTri& st) {
+  if (F.vp_std) {
+    const V4 a = mulv(trans, V4{p[0], p[1], p[2], 1.0f}), b = mulv(trans, V4{p[3], p[4], p[5], 1.0f}), c = mulv(trans, V4{p[6], p[7], p[8], 1.0f});
+    if (viewport_pos_std<E>(F.viewport, a, st.p1) && viewport_pos_std<E>(F.viewport, b, st.p2) && viewport_pos_std<E>(F.viewport, c, st.p3) &&
+        fabsf(st.p1.x) + fabsf(st.p1.y) + fabsf(st.p1.z) + fabsf(st.p2.x) + fabsf(st.p2.y) + fabsf(st.p2.z) + fabsf(st.p3.x) + fabsf(st.p3.y) + fabsf(st.p3.z) < 3e29f) {
+      st.cw1 = a.w; st.cw2 = b.w; st.cw3 = c.w;
+      return;
+    }
+  }
+  st = tri_setup_literal<E>(&F, trans, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8]);
+}
+
 // FAN = false: the caller guarantees seq & 7 == 0 (an unclipped triangle) and the clipper is compiled out.
 template <bool E, bool EA, bool FAN>
 __device__ __forceinline__ void resolve_fragment_impl(const DevScene& S, const DevFrame& F, uint32_t seq, int x, int y, Frag& f) {
@@ -965,7 +999,7 @@ __device__ __forceinline__ void resolve_fragment_impl(const DevScene& S, const D
 #pragma unroll
   for (int k = 0; k < 9; k++) p[k] = __ldg(S.pos + (size_t)tri * 9 + k);
   ScreenTri st;
-  tri_setup<E>(trans, F.viewport, F.pm_viewport, F.cullW, F.cullH, p, true, st);
+  resolve_screen_tri<E>(F, trans, p, st);
   const bool persp = (F.flags & PRC_FRAME_PERSPECT) != 0;
   float rw1 = 1.0f, rw2 = 1.0f, rw3 = 1.0f;
   if (persp) { rw1 = __fdiv_rn(-1.0f, st.cw1); rw2 = __fdiv_rn(-1.0f, st.cw2); rw3 = __fdiv_rn(-1.0f, st.cw3); }
@@ -1012,9 +1046,13 @@ __device__ __forceinline__ void resolve_fragment_impl(const DevScene& S, const D
     // identities (FMA(0, v, c) = c, FMA(m, v, +-0) = m*v for finite v); same values, only the sign of an exact zero can differ
     m1 = unproject_std(F, v[0].pos); m2 = unproject_std(F, v[1].pos); m3 = unproject_std(F, v[2].pos);
   } else {
-    m1 = apply4m<EA>(apply4m<EA>(apply4m<EA>(v[0].pos, F.viewport_inv, F.pm_viewport_inv), F.proj_inv, F.pm_proj_inv), F.view_inv, F.pm_view_inv);
-    m2 = apply4m<EA>(apply4m<EA>(apply4m<EA>(v[1].pos, F.viewport_inv, F.pm_viewport_inv), F.proj_inv, F.pm_proj_inv), F.view_inv, F.pm_view_inv);
-    m3 = apply4m<EA>(apply4m<EA>(apply4m<EA>(v[2].pos, F.viewport_inv, F.pm_viewport_inv), F.proj_inv, F.pm_proj_inv), F.view_inv, F.pm_view_inv);
+    if (EA) {  // exact mode: this IS the hot path, keep it inline
+      m1 = apply4m<EA>(apply4m<EA>(apply4m<EA>(v[0].pos, F.viewport_inv, F.pm_viewport_inv), F.proj_inv, F.pm_proj_inv), F.view_inv, F.pm_view_inv);
+      m2 = apply4m<EA>(apply4m<EA>(apply4m<EA>(v[1].pos, F.viewport_inv, F.pm_viewport_inv), F.proj_inv, F.pm_proj_inv), F.view_inv, F.pm_view_inv);
+      m3 = apply4m<EA>(apply4m<EA>(apply4m<EA>(v[2].pos, F.viewport_inv, F.pm_viewport_inv), F.proj_inv, F.pm_proj_inv), F.view_inv, F.pm_view_inv);
+    } else {
+      m1 = unproject_literal<EA>(&F, v[0].pos); m2 = unproject_literal<EA>(&F, v[1].pos); m3 = unproject_literal<EA>(&F, v[2].pos);
+    }
   }
   f.facenor = unit4<EA>(cross4<EA>(sub4(m2, m1), sub4(m3, m1)));
   BarySetup bs = bary_setup<E>(v[0].pos.x, v[0].pos.y, v[1].pos.x, v[1].pos.y, v[2].pos.x, v[2].pos.y);
@@ -1130,7 +1168,21 @@ __device__ __forceinline__ uint32_t rgba_at(const DevScene& S, uint32_t lvl, lon
   if (x < 0 || y < 0 || x >= w || y >= h) return 0u;
   return __ldg(reinterpret_cast<const uint32_t*>(S.tex_data + S.level_off[lvl]) + (size_t)y * w + x);
 }
-__device__ uint32_t query_bilinear(const DevScene& S, uint32_t lvl, float u, float v) {
+// the literal 64-bit sequence (negative, huge or NaN texel coordinates: wild UVs), out of line — the kernels that shade are
+// instruction-cache bound (ncu: 22 % of k_resolve_shade's stall samples were instruction fetches at 11 152 SASS instructions)
+__device__ __noinline__ uint32_t query_bilinear_wide(const DevScene* Sp, uint32_t lvl, float x, float y, float x0, float y0) {
+  const DevScene& S = *Sp;
+  const long long dx = S.level_w[lvl], dy = S.level_h[lvl];
+  long long i = go_int(x0), j = go_int(y0);
+  uint32_t p1 = rgba_at(S, lvl, i, j);
+  uint32_t p2 = (i < dx - 1) ? rgba_at(S, lvl, i + 1, j) : p1;
+  uint32_t i1 = lerpc(p1, p2, x - x0);
+  uint32_t p3 = (j < dy - 1) ? rgba_at(S, lvl, i, j + 1) : p1;
+  uint32_t p4 = (i < dx - 1 && j < dy - 1) ? rgba_at(S, lvl, i + 1, j + 1) : p1;
+  uint32_t i2 = lerpc(p3, p4, x - x0);
+  return lerpc(i1, i2, y - y0);
+}
+__device__ __forceinline__ uint32_t query_bilinear(const DevScene& S, uint32_t lvl, float u, float v) {
   const uint32_t wx = S.level_w[lvl], wy = S.level_h[lvl];
   if (wx == 1 && wy == 1) return rgba_at(S, lvl, 0, 0);
   float x = u * ((float)wx - 1.0f), y = v * ((float)wy - 1.0f);
@@ -1147,15 +1199,7 @@ __device__ uint32_t query_bilinear(const DevScene& S, uint32_t lvl, float u, flo
     const float tx = x - x0;
     return lerpc(lerpc(p1, p2, tx), lerpc(p3, p4, tx), y - y0);
   }
-  const long long dx = wx, dy = wy;
-  long long i = go_int(x0), j = go_int(y0);
-  uint32_t p1 = rgba_at(S, lvl, i, j);
-  uint32_t p2 = (i < dx - 1) ? rgba_at(S, lvl, i + 1, j) : p1;
-  uint32_t i1 = lerpc(p1, p2, x - x0);
-  uint32_t p3 = (j < dy - 1) ? rgba_at(S, lvl, i, j + 1) : p1;
-  uint32_t p4 = (i < dx - 1 && j < dy - 1) ? rgba_at(S, lvl, i + 1, j + 1) : p1;
-  uint32_t i2 = lerpc(p3, p4, x - x0);
-  return lerpc(i1, i2, y - y0);
+  return query_bilinear_wide(&S, lvl, x, y, x0, y0);
 }
 __device__ __forceinline__ void go_modf(float f, float& ip, float& fp) {
   ip = truncf(f);
@@ -1179,19 +1223,26 @@ __device__ uint32_t tex_query(const DevScene& S, const prc_material& m, float lo
   }
   if (lod < 0.0f) lod = 0.0f;
   else if (lod >= (float)nlev) lod = (float)(nlev - 1);
-  if (lod <= 1.0f) return query_bilinear(S, first, u, v);
-  lod -= 1.0f;
-  long long h = go_int(floorf(lod));
-  long long l = h + 1;
-  if (l >= nlev) return query_bilinear(S, first + (uint32_t)h, u, v);
-  float p = lod - (float)h;
-  if (approx_eq(p, 0.0f)) return query_bilinear(S, first + (uint32_t)h, u, v);
-  uint32_t L1 = query_bilinear(S, first + (uint32_t)h, u, v);
-  uint32_t L2 = query_bilinear(S, first + (uint32_t)l, u, v);
-  return lerpc(L1, L2, p);
+  // texture.go:118-137: one level (bilinear) or two (trilinear); ONE inlined copy of the bilinear fetch serves both
+  uint32_t lv = first;
+  float p = 0.0f;
+  bool two = false;
+  if (lod > 1.0f) {
+    lod -= 1.0f;
+    const long long h = go_int(floorf(lod));
+    lv = first + (uint32_t)h;
+    if (h + 1 < nlev) {
+      p = lod - (float)h;
+      two = !approx_eq(p, 0.0f);
+    }
+  }
+  uint32_t L[2] = {0u, 0u};
+#pragma unroll 1
+  for (int k = 0; k < (two ? 2 : 1); k++) L[k] = query_bilinear(S, lv + (uint32_t)k, u, v);
+  return two ? lerpc(L[0], L[1], p) : L[0];
 }
 // math.Log2 via float64 (math/math.go:122-124); Go: Frexp, exact for powers of two, else Log(frac)*(1/Ln2)+exp
-__device__ __forceinline__ float go_log2(float x) {
+__device__ __noinline__ float go_log2(float x) {
   int e;
   double fr = frexp((double)x, &e);
   if (fr == 0.5) return (float)(e - 1);
@@ -1308,6 +1359,11 @@ __device__ uint32_t fragment_shader(const DevScene& S, const DevFrame& F, const 
          (go_u8(clampf((float)chan(col, 3), 0.0f, 255.0f)) << 24);
 }
 
+// the literal three Apply calls of shadingVisibility (shadow.go:238-243), out of line (see query_bilinear_wide)
+template <bool E>
+__device__ __noinline__ V4 light_screen_generic(const DevFrame* F, const DevLight* l, V4 world) {
+  return pos4(apply4m<E>(apply4m<E>(apply4m<E>(world, l->view, l->pm_view), l->proj, l->pm_proj), F->viewport, F->pm_viewport));
+}
 template <bool E>
 __device__ bool shading_visibility(const DevFrame& F, const DevLight& l, const V4& world) {
   if (!l.cast_shadow) return true;
@@ -1331,7 +1387,7 @@ __device__ bool shading_visibility(const DevFrame& F, const DevLight& l, const V
       sc = V4{fma32<false>(vp[0], px, vp[3]), fma32<false>(vp[5], py, vp[7]), pz, 1.0f};
     }
   } else {
-    sc = pos4(apply4m<E>(apply4m<E>(apply4m<E>(world, l.view, l.pm_view), l.proj, l.pm_proj), F.viewport, F.pm_viewport));
+    sc = light_screen_generic<E>(&F, &l, world);
   }
   if (fabsf(sc.x) < 5e8f && fabsf(sc.y) * (float)F.W < 1.5e9f) {  // 32-bit fast path: int(x) + int(y)*W cannot overflow
     const int idx = __float2int_rz(sc.x) + __float2int_rz(sc.y) * F.W;

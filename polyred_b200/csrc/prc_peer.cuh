@@ -43,7 +43,7 @@ struct PeerTable {
 struct PushJob {
   int W, H;
   uint32_t n_sh;                 // casting lights: rows [H, (1 + n_sh) H) of the row space are shadow rows (light k: [(1+k) H, (2+k) H))
-  unsigned char* dirty;          // [(1 + n_sh) H] row flags of this rank's private buffers (Counters.dirty), cleared here
+  unsigned char* dirty;          // [(1 + n_sh) H][PRC_DIRTY_STRIDE] row flags (one per 32-byte sector) of this rank's private buffers (Counters.dirty), cleared here
   float* sh_mine;                // private stacked shadow maps [n_sh][H][W], zeroed where read (clear-on-read)
   unsigned long long* k_mine;    // private key plane [H][W], zeroed where read
   unsigned long long k_off;      // offset of this frame's parity plane inside mkeys[], in keys
@@ -103,9 +103,9 @@ __global__ void k_peer_signal(PeerTable P, uint32_t kind, uint32_t epoch, uint32
 __global__ void __launch_bounds__(256) k_peer_push(const __grid_constant__ PeerTable P, const __grid_constant__ PushJob J) {
   const int n_rows = (int)(1u + J.n_sh) * J.H;
   for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
-    if (!J.dirty[row]) continue;  // (uniform over the CTA)
+    if (!J.dirty[(size_t)row * PRC_DIRTY_STRIDE]) continue;  // (uniform over the CTA)
     __syncthreads();              // every thread has read the flag
-    if (threadIdx.x == 0) J.dirty[row] = 0;
+    if (threadIdx.x == 0) J.dirty[(size_t)row * PRC_DIRTY_STRIDE] = 0;
     if (row >= J.H) {
       // ---- a shadow row -> every rank's merged maps. A depth that does not exceed what this rank's own merged map holds is
       // not sent: every value in a merged map arrived by a push that goes to ALL ranks (and completes before its sender's

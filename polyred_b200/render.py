@@ -99,9 +99,11 @@ def PixelFormat(fmt):
     return lambda o: setattr(o, "Format", int(fmt))
 
 
-def CUDA(device: int = 0):
-    """Backend selection, the analogue of render.GPU(dev) (render/options.go:103-110)."""
-    return lambda o: setattr(o, "CUDADevice", int(device))
+def CUDA(*devices: int):
+    """Backend selection, the analogue of render.GPU(dev) (render/options.go:103-110). Several devices = one frame over all of
+    them (a device group inside the library, include/polyred_cuda.h prc_group_*): the same image, bit for bit."""
+    devs = [int(d) for d in devices] or [0]
+    return lambda o: setattr(o, "CUDADevice", devs[0] if len(devs) == 1 else tuple(devs))
 
 
 def _Backend(b):
@@ -207,8 +209,9 @@ class Renderer:
         if self._backend is None:
             if self.cfg.CUDADevice is None:
                 raise ValueError("render: no backend selected — pass render.CUDA(device); this package has no CPU renderer")
-            from ._lib import CudaBackend
-            self._backend = CudaBackend(self.cfg.CUDADevice)
+            from ._lib import CudaBackend, GroupBackend
+            dev = self.cfg.CUDADevice
+            self._backend = GroupBackend(dev) if isinstance(dev, tuple) else CudaBackend(dev)
         self._validate()
         if self.cfg.Scene is not None and self.cfg.ShadowMap:
             self.initShadowMaps()
@@ -443,6 +446,16 @@ def RenderViews(r: Renderer, cameras) -> list:
     Options(Camera(c)) exactly as a reference caller would, which re-fits the light cameras to the new view
     frustum and zeroes the shadow maps (render/options.go:125-141, bug-list 5), then Render(). The flattened
     scene stays resident in HBM across views."""
+    if hasattr(r._backend, "render_batch") and not r.cfg.Debug:
+        # one call for the whole batch (prc_render_batch / prc_group_render_views): the views are submitted back to back, the
+        # zeroing of the shadow maps that Options() does between views travels as PRC_FRAME_SHADOW_RESET
+        r._ensure_uploaded()
+        fds = ViewFrames(r, cameras)
+        outs = [np.zeros((r.cfg.Height, r.cfg.Width, 4), np.uint8) for _ in fds]
+        r._backend.render_batch(fds, outs)
+        if fds:
+            r._last_frame = fds[-1]
+        return outs
     out = []
     for cam in cameras:
         sd = r._scene_desc
