@@ -1586,6 +1586,31 @@ inline void peer_signal(prc_ctx* ctx, uint32_t kind, uint32_t epoch, uint32_t ma
   ctx->launches++;
 }
 
+// signal, then wait, in one launch (k_peer_signal_wait); falls back to the single kernels when one half is empty
+inline void peer_signal_wait(prc_ctx* ctx, uint32_t sig_kind, uint32_t sig_epoch, uint32_t sig_mask, uint32_t wait_kind, uint32_t wait_epoch, uint32_t wait_mask) {
+  const PeerTable& P = ctx->peers;
+  const uint32_t others = ~(1u << P.self);
+  static const bool fuse = !(getenv("PRC_PEER_NO_FUSED_SIGNALS") != nullptr && atoi(getenv("PRC_PEER_NO_FUSED_SIGNALS")) != 0);
+  if (!fuse || !(sig_mask & others) || !(wait_mask & others)) {
+    peer_signal(ctx, sig_kind, sig_epoch, sig_mask);
+    peer_wait(ctx, wait_kind, wait_epoch, wait_mask);
+    return;
+  }
+  size_t a = 0;
+  if (ctx->peer_trace) {
+    while (ctx->evpool.size() < ctx->ev_used + 2) { cudaEvent_t e; cudaEventCreate(&e); ctx->evpool.push_back(e); }
+    a = ctx->ev_used;
+    ctx->ev_used += 2;
+    cudaEventRecord(ctx->evpool[a], ctx->stream);
+  }
+  k_peer_signal_wait<<<1, PRC_PEER_MAX, 0, ctx->stream>>>(P, sig_kind, sig_epoch, sig_mask, wait_kind, wait_epoch, wait_mask, (unsigned int*)ctx->d_peer_err.p);
+  ctx->launches++;
+  if (ctx->peer_trace) {
+    cudaEventRecord(ctx->evpool[a + 1], ctx->stream);
+    ctx->peer_spans.push_back({(int)wait_kind, a, a + 1});
+  }
+}
+
 // One frame of the group on this rank, enqueued without waiting for anything (prc_peer.cuh has the partition):
 //   clear the private keys and the NEXT frame's merged plane -> camera pass and fused shadow sweep over this rank's share of the
 //   triangles (private buffers; no peer is involved, so this runs while slower peers still shade the previous frame) -> queued
@@ -1601,6 +1626,10 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
   cudaStream_t st = ctx->stream;
   const bool shadows = (fr->flags & PRC_FRAME_SHADOWMAP) && ctx->n_cast_alloc > 0 && ctx->n_cast_alloc != 0xFFFFFFFFu;
   const size_t npx = (size_t)F.W * F.H;
+  if ((size_t)(1u + (shadows ? ctx->n_cast_alloc : 0u)) * F.H * ((F.W + PRC_DIRTY_SEG - 1) / PRC_DIRTY_SEG) * PRC_DIRTY_STRIDE > ctx->d_dirty.cap) {
+    ctx->err = "prc_render_peer: the frame has more shadow-casting lights than the group was exported for; export and connect again";
+    return PRC_ERR_INVALID;
+  }
   const uint32_t e = ++ctx->peer_epoch;
   ctx->pass_slot = 0;
   if (ctx->pending_async == 0) {
@@ -1644,6 +1673,28 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
   // The camera pass and the shadow sweep are independent (different targets, one shared queue filled by atomics) and, at 1/N of
   // the triangles, each is only a few waves of CTAs long: they run on two streams so that one fills the other's tail.
   static const bool two_streams = !(getenv("PRC_PEER_ONE_STREAM") != nullptr && atoi(getenv("PRC_PEER_ONE_STREAM")) != 0);
+  static const bool early_push = !(getenv("PRC_PEER_NO_EARLY_PUSH") != nullptr && atoi(getenv("PRC_PEER_NO_EARLY_PUSH")) != 0);
+  static const bool full_push = getenv("PRC_PEER_FULL_PUSH") != nullptr && atoi(getenv("PRC_PEER_FULL_PUSH")) != 0;
+  // k_peer_push (prc_peer.cuh) merges the flagged 256-pixel segments of this rank's private buffers into the peers
+  PushJob J0 = needs;
+  J0.W = F.W; J0.H = F.H;
+  J0.n_sh = shadows ? ctx->n_cast_alloc : 0u;
+  J0.dirty = (unsigned char*)ctx->d_dirty.p;
+  J0.nseg = (F.W + PRC_DIRTY_SEG - 1) / PRC_DIRTY_SEG;
+  J0.sh_mine = (float*)ctx->d_shadow_mine.p;
+  J0.k_mine = (unsigned long long*)ctx->d_keys.p;
+  J0.k_off = (unsigned long long)(plane_cur - mk);
+  J0.f_mine = ctx->nan_mode ? (unsigned long long*)ctx->d_keys.p + npx : nullptr;
+  J0.f_off = (unsigned long long)(first_cur - mk);
+  J0.full = full_push ? 1 : 0;
+  auto launch_push = [&](long long seg0, long long seg1) {
+    PushJob J = J0;
+    J.seg0 = seg0; J.seg1 = seg1;
+    // one CTA per batch of PRC_PUSH_BATCH segment flags; a grid of at most 148 x 8 CTAs strides over the rest
+    const unsigned int grid = (unsigned int)std::min<long long>(148 * 8, std::max<long long>(1, (seg1 - seg0 + PRC_PUSH_BATCH - 1) / PRC_PUSH_BATCH));
+    k_peer_push<<<grid, 256, 0, ctx->stream>>>(P, J);
+    ctx->launches++;
+  };
   int32_t r = PRC_OK;
   if (shadows && two_streams) {
     CK(cudaEventRecord(ctx->ev_fork, st));
@@ -1655,32 +1706,27 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
   }
   if (r == PRC_OK) r = do_main<E>(ctx, fr, Fr, 1, 1);
   ctx->skip_key_clear = false;
+  if (r == PRC_OK && early_push && P.world > 1) {
+    // The visibility keys of the camera pass leave NOW, under the shadow sweep that is still running on the other stream: the merge
+    // of ~0.6 M keys per rank is 0.04 ms of reductions over NVLink, whatever the number of ranks, and the camera pass is the shorter
+    // of the two. No wait is needed first: the peers cleared this frame's key plane before they signalled SHADOW(e-1), which this
+    // rank awaited before it shaded frame e-1. What the queued records add to the key plane later goes with the second push.
+    KTimer kt(ctx, PRC_K_EXCHANGE);
+    launch_push(0, (long long)J0.H * J0.nseg);
+  }
   CK(cudaEventRecord(ctx->ev[1], st));
   if (shadows && two_streams) CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
   else if (r == PRC_OK && shadows) r = do_shadows<E>(ctx, fr, Fr, units_from_mask(fr, 0xFFFFFFFFu, 0, F.H), false);
   if (r == PRC_OK) r = do_main<E>(ctx, fr, Fr, 4, 1);  // queued records of the camera AND the shadow passes
   ctx->part_rank = 0; ctx->part_world = 1; ctx->part_active = false;
   if (r != PRC_OK) return r;
-  // ---- exchange
+  // ---- exchange: what the queued records added to the key plane, and the shadow planes
   if (shadows) peer_wait(ctx, PRC_SIG_SHADED, e - 1, all);  // nobody may still be shading the previous frame from the maps about to be merged into
   {
-    PushJob J = needs;
-    J.W = F.W; J.H = F.H;
-    J.n_sh = shadows ? ctx->n_cast_alloc : 0u;
-    J.dirty = (unsigned char*)ctx->d_dirty.p;
-    J.sh_mine = (float*)ctx->d_shadow_mine.p;
-    J.k_mine = (unsigned long long*)ctx->d_keys.p;
-    J.k_off = (unsigned long long)(plane_cur - mk);
-    J.f_mine = ctx->nan_mode ? (unsigned long long*)ctx->d_keys.p + npx : nullptr;
-    J.f_off = (unsigned long long)(first_cur - mk);
-    static const bool full_push = getenv("PRC_PEER_FULL_PUSH") != nullptr && atoi(getenv("PRC_PEER_FULL_PUSH")) != 0;
-    J.full = full_push ? 1 : 0;
     KTimer kt(ctx, PRC_K_EXCHANGE);
-    k_peer_push<<<148 * 8, 256, 0, st>>>(P, J);
-    ctx->launches++;
+    launch_push(0, (long long)(1u + J0.n_sh) * J0.H * J0.nseg);
   }
-  peer_signal(ctx, PRC_SIG_SHADOW, e, all);
-  peer_wait(ctx, PRC_SIG_SHADOW, e, all);
+  peer_signal_wait(ctx, PRC_SIG_SHADOW, e, all, PRC_SIG_SHADOW, e, all);
   // ---- resolve + shading of the strip from the merged buffers
   ctx->keys_shade = plane_cur; ctx->first_shade = first_cur;
   ctx->defer_copy_join = true;
@@ -1688,12 +1734,14 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
   ctx->defer_copy_join = false;
   ctx->keys_shade = nullptr; ctx->first_shade = nullptr;
   if (r != PRC_OK) return r;
-  if (shadows) peer_signal(ctx, PRC_SIG_SHADED, e, all);
   // image strip: screen rows [row0,row1) = image rows [H-row1, H-row0)
   const size_t off = (size_t)(F.H - F.row1) * F.W * 4, bytes = (size_t)(F.row1 - F.row0) * F.W * 4;
   const uint32_t consumers = image_mask & all;
-  if (consumers & ~me) {
-    peer_wait(ctx, PRC_SIG_IMAGE_FREE, e - 1, consumers);  // the consumers are done with the previous frame's image
+  if (!(consumers & ~me)) {
+    if (shadows) peer_signal(ctx, PRC_SIG_SHADED, e, all);
+  } else {
+    // "my shading is done" and "wait until the consumers are done with the previous frame's image" in one launch
+    peer_signal_wait(ctx, PRC_SIG_SHADED, e, shadows ? all : 0u, PRC_SIG_IMAGE_FREE, e - 1, consumers);
     for (uint32_t c = 0; c < P.world; c++)
       if (((consumers >> c) & 1u) && c != P.self)
         CK(cudaMemcpyAsync(ctx->peer_image[c] + off, (const uint8_t*)ctx->d_image.p + off, bytes, cudaMemcpyDefault, st));
@@ -1738,8 +1786,10 @@ int32_t prc_peer_export(prc_ctx* ctx, const prc_frame* fr, prc_peer_handle* out)
     // the private planes start empty and are emptied again by every push (clear-on-read): keys 0, first-fragment plane ~0
     CK(cudaMemsetAsync(ctx->d_keys.p, 0, npx_ * 8, ctx->stream));
     CK(cudaMemsetAsync((unsigned long long*)ctx->d_keys.p + npx_, 0xFF, npx_ * 8, ctx->stream));
-    ENSURE(ctx->d_dirty, (size_t)33 * fr->height * PRC_DIRTY_STRIDE);
-    CK(cudaMemsetAsync(ctx->d_dirty.p, 0, (size_t)33 * fr->height * PRC_DIRTY_STRIDE, ctx->stream));
+    // segment flags of the private buffers: [1 + casting lights][H][ceil(W / 256)] flags, one per 32-byte sector
+    const size_t dirty_bytes = (size_t)(1u + (ctx->n_cast_alloc == 0xFFFFFFFFu ? 0u : ctx->n_cast_alloc)) * fr->height * ((fr->width + PRC_DIRTY_SEG - 1) / PRC_DIRTY_SEG) * PRC_DIRTY_STRIDE;
+    ENSURE(ctx->d_dirty, dirty_bytes);
+    CK(cudaMemsetAsync(ctx->d_dirty.p, 0, ctx->d_dirty.cap, ctx->stream));
     struct { unsigned char* p; int h; } dd = {(unsigned char*)ctx->d_dirty.p, (int)fr->height};
     CK(cudaMemcpyAsync((char*)ctx->d_counters.p + offsetof(Counters, dirty), &dd.p, sizeof(dd.p), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync((char*)ctx->d_counters.p + offsetof(Counters, dirty_h), &dd.h, sizeof(dd.h), cudaMemcpyHostToDevice, ctx->stream));

@@ -105,13 +105,16 @@ struct Counters {
   unsigned char* dirty;
   int dirty_h;
 };
-// One flag per 32-byte sector: with the flags packed (H bytes = 17 cache lines for a 4K frame) every fragment of a pass stored into
-// the same few L2 lines, and those stores serialised — measured at 2 GPUs: the camera pass over half of the triangles took 0.140 ms
-// against 0.174 ms for all of them on one GPU.
+// Flags of the private buffers of a peer-group rank: one per 256-pixel SEGMENT of a row, and one flag per 32-byte sector — with
+// the flags packed (H bytes = 17 cache lines for a 4K frame) every fragment of a pass stored into the same few L2 lines and those
+// stores serialised (measured at 2 GPUs: the camera pass over half of the triangles took 0.140 ms against 0.174 ms for all of
+// them on one GPU; 0.099 ms with one flag per sector).
 #define PRC_DIRTY_STRIDE 32
-__device__ __forceinline__ void mark_dirty(const Counters* cnt, uint32_t target, int y) {  // not for the hot path (a dependent global load)
+#define PRC_DIRTY_SEG 256
+__device__ __forceinline__ int dirty_nseg(int W) { return (W + PRC_DIRTY_SEG - 1) / PRC_DIRTY_SEG; }
+__device__ __forceinline__ void mark_dirty(const Counters* cnt, uint32_t target, int x, int y, int W) {  // not for the hot path (a dependent global load)
   unsigned char* d = cnt->dirty;
-  if (d) d[((size_t)target * cnt->dirty_h + y) * PRC_DIRTY_STRIDE] = 1;
+  if (d) d[(((size_t)target * cnt->dirty_h + y) * dirty_nseg(W) + (x / PRC_DIRTY_SEG)) * PRC_DIRTY_STRIDE] = 1;
 }
 
 // warp-aggregated slot reservation: one atomicAdd per warp for all lanes that reach this point together
@@ -268,8 +271,8 @@ __device__ __forceinline__ void raster_one(const BarySetup& bs, const V4& p1, co
       float z = w1 * p1.z + w2 * p2.z + w3 * p3.z;
       size_t idx = (size_t)y * W + x;
       if (NM && !SHADOW) nan_first(first, idx, seq, z);
-      if (isnan(z)) { atomicAdd(SHADOW ? &cnt->n_nan_shadow : &cnt->n_nan, 1ULL); if (NM && !SHADOW) mark_dirty(cnt, 0, y); continue; }
-      mark_dirty(cnt, target, y);
+      if (isnan(z)) { atomicAdd(SHADOW ? &cnt->n_nan_shadow : &cnt->n_nan, 1ULL); if (NM && !SHADOW) mark_dirty(cnt, 0, x, y, W); continue; }
+      mark_dirty(cnt, target, x, y, W);
       if (SHADOW) {
         // shadowDepthTest (shadow.go:221-228): store iff !(z <= stored); stored starts at 0 and only grows,
         // so only z > 0 can ever be stored and positive floats order like their int bits.
@@ -432,7 +435,7 @@ __device__ __forceinline__ void small_pixel(const float p1x, const float p1y, co
   const float z = w1 * p1z + w2 * p2z + w3 * p3z;
   const size_t idx = (size_t)y * W + x;
   if (NM && !SHADOW) nan_first(first, idx, seq, z);
-  if (PEER && (!SHADOW || z > 0.0f || (NM && isnan(z)))) dirty_rows[(size_t)y * PRC_DIRTY_STRIDE] = 1;  // peer groups: this row of the private buffer holds something
+  if (PEER && (!SHADOW || z > 0.0f || (NM && isnan(z)))) dirty_rows[((size_t)y * dirty_nseg(W) + (x / PRC_DIRTY_SEG)) * PRC_DIRTY_STRIDE] = 1;  // peer groups: this row of the private buffer holds something
   if (isnan(z)) { atomicAdd(SHADOW ? &cnt->n_nan_shadow : &cnt->n_nan, 1ULL); return; }
   // fire-and-forget reductions (RED.MAX): no pre-test load, so nothing waits on memory
   if (SHADOW) {
@@ -619,7 +622,7 @@ __global__ void __launch_bounds__(PRC_GEOM_THREADS, PRC_GEOM_MIN_BLOCKS) k_geom_
     const float* trans_base = SHADOW ? V.trans[v] : reinterpret_cast<const float*>(F.xf);
     float* smap = SHADOW ? V.smap[v] : nullptr;
     // peer groups: the row flags of this view's private target (see Counters.dirty); V.dirty is uniform, no dependent load per fragment
-    unsigned char* dirty_rows = LIST == 3 ? V.dirty + (size_t)(SHADOW ? V.target[v] : 0u) * F.H * PRC_DIRTY_STRIDE : nullptr;
+    unsigned char* dirty_rows = LIST == 3 ? V.dirty + (size_t)(SHADOW ? V.target[v] : 0u) * F.H * dirty_nseg(F.W) * PRC_DIRTY_STRIDE : nullptr;
     // ---- phase 2: one thread per triangle
     if (li != 0xFFFFFFFFu)
       geom_classify<E, SHADOW, NM, LIST == 3>(S, F, sm, buf, buf, li, tri, trans_base, trans_stride, keys, smap, large, large_cap, clipq, clip_cap, cnt, Fg,
@@ -832,8 +835,8 @@ __global__ void __launch_bounds__(256) k_medium_raster(const LargeRec* __restric
       const float z = w1 * r.z1 + w2 * r.z2 + w3 * r.z3;
       const size_t idx = (size_t)y * W + x;
       if (NM && !shadow) nan_first(keys + (size_t)W * H, idx, r.seq, z);
-      if (isnan(z)) { if (shadow) nan_sh++; else { nan_cam++; if (NM) mark_dirty(cnt, 0, y); } continue; }
-      mark_dirty(cnt, r.target, y);
+      if (isnan(z)) { if (shadow) nan_sh++; else { nan_cam++; if (NM) mark_dirty(cnt, 0, x, y, W); } continue; }
+      mark_dirty(cnt, r.target, x, y, W);
       if (shadow) {
         if (z > 0.0f) atomicMax((int*)&smap[idx], __float_as_int(z));
       } else {
@@ -904,7 +907,7 @@ __global__ void __launch_bounds__(PRC_TILE * PRC_TILE) k_tile_raster(const Large
     if (nan_local) atomicAdd(shadow ? &cnt->n_nan_shadow : &cnt->n_nan, nan_local);
     if (!live) continue;
     const size_t idx = (size_t)y * W + x;
-    if ((shadow ? bestz > 0.0f : best != 0) || (NM && firstv != ~0ull)) mark_dirty(cnt, (uint32_t)target, y);
+    if ((shadow ? bestz > 0.0f : best != 0) || (NM && firstv != ~0ull)) mark_dirty(cnt, (uint32_t)target, x, y, W);
     if (NM && firstv != ~0ull) atomicMin(&keys[(size_t)W * H + idx], firstv);
     if (shadow) {
       if (bestz > 0.0f) atomicMax((int*)&targets->smap[target][idx], __float_as_int(bestz));

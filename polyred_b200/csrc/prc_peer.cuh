@@ -43,7 +43,8 @@ struct PeerTable {
 struct PushJob {
   int W, H;
   uint32_t n_sh;                 // casting lights: rows [H, (1 + n_sh) H) of the row space are shadow rows (light k: [(1+k) H, (2+k) H))
-  unsigned char* dirty;          // [(1 + n_sh) H][PRC_DIRTY_STRIDE] row flags (one per 32-byte sector) of this rank's private buffers (Counters.dirty), cleared here
+  unsigned char* dirty;          // [(1 + n_sh) H][nseg][PRC_DIRTY_STRIDE] segment flags of this rank's private buffers (Counters.dirty), cleared here
+  int nseg;                      // 256-pixel segments per row = ceil(W / PRC_DIRTY_SEG) of this rank's private buffers (Counters.dirty), cleared here
   float* sh_mine;                // private stacked shadow maps [n_sh][H][W], zeroed where read (clear-on-read)
   unsigned long long* k_mine;    // private key plane [H][W], zeroed where read
   unsigned long long k_off;      // offset of this frame's parity plane inside mkeys[], in keys
@@ -51,6 +52,7 @@ struct PushJob {
   // NaN mode: first-fragment plane, merged with atomicMin (nullptr otherwise; reset to ~0 where read); f_off = offset of the merged plane
   unsigned long long* f_mine;
   unsigned long long f_off;
+  long long seg0, seg1;          // segments this launch scans: [0, H nseg) = the key plane, [H nseg, (1 + n_sh) H nseg) = the shadow planes
   int full;                      // PRC_PEER_FULL_PUSH: send every non-empty shadow texel, also those the peers provably hold
 };
 
@@ -95,53 +97,144 @@ __global__ void k_peer_signal(PeerTable P, uint32_t kind, uint32_t epoch, uint32
   st_release_sys(P.signals[dst] + kind * PRC_PEER_MAX + P.self, epoch);
 }
 
+// k_peer_signal followed by k_peer_wait as ONE launch (every launch on a frame's critical path costs 2-4 us of a ~0.2 ms 8-GPU
+// frame): thread t publishes `sig_epoch` to rank t, then waits for rank t's word. The threads are independent, so this is exactly
+// the two kernels back to back.
+__global__ void k_peer_signal_wait(PeerTable P, uint32_t sig_kind, uint32_t sig_epoch, uint32_t sig_mask, uint32_t wait_kind, uint32_t wait_epoch,
+                                   uint32_t wait_mask, unsigned int* __restrict__ timeouts) {
+  const uint32_t t = threadIdx.x;
+  const bool peer = t < P.world && t != P.self;
+  if (peer && ((sig_mask >> t) & 1u)) {
+    __threadfence_system();
+    st_release_sys(P.signals[t] + sig_kind * PRC_PEER_MAX + P.self, sig_epoch);
+  }
+  __syncwarp();  // (one warp) every signal is on its way before any lane starts to spin
+  if (!peer || !((wait_mask >> t) & 1u)) return;
+  const uint32_t* w = P.signals[P.self] + wait_kind * PRC_PEER_MAX + t;
+  const unsigned long long t0 = global_ns();
+  unsigned int spins = 0;
+  while ((int32_t)(ld_acquire_sys(w) - wait_epoch) < 0) {
+    if ((++spins & 1023u) == 0 && global_ns() - t0 > PRC_PEER_TIMEOUT_NS) {
+      atomicAdd(timeouts, 1u);
+      return;
+    }
+    __nanosleep(64);
+  }
+}
+
 // Merges what this rank rasterised into its peers (and into its own merged buffers) — see the file header. Shadow depths are
-// positive floats, which order like their int bits; depth 0 / key 0 is "nothing stored" and is skipped. Only rows flagged by the
-// raster kernels are read (on C3 the scene covers a quarter of the screen rows and of each light's rows), and what is read
-// is reset, so the private buffers are empty again for the next frame without a clearing pass. The reductions are
-// fire-and-forget (RED over NVLink). One CTA per flagged row at a time.
-__global__ void __launch_bounds__(256) k_peer_push(const __grid_constant__ PeerTable P, const __grid_constant__ PushJob J) {
-  const int n_rows = (int)(1u + J.n_sh) * J.H;
-  for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
-    if (!J.dirty[(size_t)row * PRC_DIRTY_STRIDE]) continue;  // (uniform over the CTA)
-    __syncthreads();              // every thread has read the flag
-    if (threadIdx.x == 0) J.dirty[(size_t)row * PRC_DIRTY_STRIDE] = 0;
-    if (row >= J.H) {
-      // ---- a shadow row -> every rank's merged maps. A depth that does not exceed what this rank's own merged map holds is
-      // not sent: every value in a merged map arrived by a push that goes to ALL ranks (and completes before its sender's
-      // signal, which every rank awaits before shading), so the peers hold — or are about to hold — at least that value.
-      // The maps are persistent and only grow (render/shadow.go:221-228), so for a scene that does not move the exchange
-      // shrinks to the texels that changed; PRC_PEER_FULL_PUSH=1 sends every non-empty texel every frame (`full`).
-      const size_t base = (size_t)(row - J.H) * J.W;
-      const float* __restrict__ merged = P.shadow[P.self] + base;
-      for (int x = threadIdx.x; x < J.W; x += blockDim.x) {
-        const float v = J.sh_mine[base + x];
+// positive floats, which order like their int bits; depth 0 / key 0 is "nothing stored" and is skipped. The raster kernels flag
+// every 256-pixel SEGMENT of a row they write (on C3 the scene covers a quarter of the screen), only flagged segments are read,
+// and what is read is reset, so the private buffers are empty again for the next frame without a clearing pass. The reductions
+// are fire-and-forget (RED over NVLink). One warp per batch of 32 segments: the lanes read 32 flags at once, then the warp walks
+// the flagged segments with all loads of a segment issued before the first reduction (round 2: the first version walked whole
+// rows with one dependent load per iteration and took 0.048 ms per frame whatever the number of ranks).
+__device__ __forceinline__ void push_shadow_texel(const PeerTable& P, size_t i, float v, float merged, int full) {
+  // A depth that does not exceed what this rank's own merged map holds is not sent: every value in a merged map arrived by a
+  // push that goes to ALL ranks (and completes before its sender's signal, which every rank awaits before shading), so the peers
+  // hold — or are about to hold — at least that value. The maps are persistent and only grow (render/shadow.go:221-228), so for
+  // a scene that does not move the exchange shrinks to the texels that changed; PRC_PEER_FULL_PUSH=1 sends every non-empty
+  // texel every frame (`full`).
+  if (v == 0.0f || (!full && !(v > merged))) return;
+  for (uint32_t p = 0; p < P.world; p++) atomicMax(reinterpret_cast<int*>(P.shadow[p]) + i, __float_as_int(v));
+}
+__device__ __forceinline__ void push_key(const PeerTable& P, const PushJob& J, size_t i, unsigned long long k, unsigned long long f, uint32_t dst) {
+  if (!k && f == ~0ull) return;
+  const uint32_t d = (i == 0) ? ((P.world >= 32u) ? 0xFFFFFFFFu : ((1u << P.world) - 1u)) : dst;  // pixel (0,0): every rank
+  for (uint32_t p = 0; p < P.world; p++) {
+    if (!((d >> p) & 1u)) continue;
+    if (k) atomicMax(P.mkeys[p] + J.k_off + i, k);
+    if (f != ~0ull) atomicMin(P.mkeys[p] + J.f_off + i, f);
+  }
+}
+// one flagged segment, handled by one warp: every load of the segment is issued before the first reduction
+__device__ __forceinline__ void push_segment(const PeerTable& P, const PushJob& J, long long sg, int lane, bool vec) {
+  const int n_seg_row = J.nseg;
+  const int row = (int)(sg / n_seg_row), x0 = (int)(sg - (long long)row * n_seg_row) * PRC_DIRTY_SEG;
+  const int nx = min(PRC_DIRTY_SEG, J.W - x0);
+  if (row >= J.H) {
+    // ---- 256 shadow texels -> every rank's merged maps
+    const size_t base = (size_t)(row - J.H) * J.W + x0;
+    const float* __restrict__ merged = P.shadow[P.self] + base;
+    float* mine = J.sh_mine + base;
+    if (vec && nx == PRC_DIRTY_SEG) {
+      const float4 v0 = reinterpret_cast<const float4*>(mine)[lane], v1 = reinterpret_cast<const float4*>(mine)[lane + 32];
+      const float4 m0 = reinterpret_cast<const float4*>(merged)[lane], m1 = reinterpret_cast<const float4*>(merged)[lane + 32];
+      if (v0.x != 0.0f || v0.y != 0.0f || v0.z != 0.0f || v0.w != 0.0f) reinterpret_cast<float4*>(mine)[lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (v1.x != 0.0f || v1.y != 0.0f || v1.z != 0.0f || v1.w != 0.0f) reinterpret_cast<float4*>(mine)[lane + 32] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      const size_t i0 = base + (size_t)lane * 4, i1 = i0 + 128;
+      push_shadow_texel(P, i0, v0.x, m0.x, J.full); push_shadow_texel(P, i0 + 1, v0.y, m0.y, J.full);
+      push_shadow_texel(P, i0 + 2, v0.z, m0.z, J.full); push_shadow_texel(P, i0 + 3, v0.w, m0.w, J.full);
+      push_shadow_texel(P, i1, v1.x, m1.x, J.full); push_shadow_texel(P, i1 + 1, v1.y, m1.y, J.full);
+      push_shadow_texel(P, i1 + 2, v1.z, m1.z, J.full); push_shadow_texel(P, i1 + 3, v1.w, m1.w, J.full);
+    } else {
+      for (int x = lane; x < nx; x += 32) {
+        const float v = mine[x];
         if (v == 0.0f) continue;
-        J.sh_mine[base + x] = 0.0f;
-        if (!J.full && !(v > merged[x])) continue;
-        for (uint32_t p = 0; p < P.world; p++) atomicMax(reinterpret_cast<int*>(P.shadow[p]) + base + x, __float_as_int(v));
+        mine[x] = 0.0f;
+        push_shadow_texel(P, base + x, v, merged[x], J.full);
+      }
+    }
+  } else {
+    // ---- 256 visibility keys -> the ranks that resolve this row (pixel (0,0): every rank)
+    const int y = row;
+    uint32_t dst = 0;
+    for (uint32_t p = 0; p < P.world; p++)
+      if ((y >= J.rr0[p] && y < J.rr1[p]) || y < J.ax1[p]) dst |= 1u << p;
+    const size_t base = (size_t)y * J.W + x0;
+    unsigned long long* mine = J.k_mine + base;
+    if (vec && nx == PRC_DIRTY_SEG && !J.f_mine) {
+      ulonglong2 k[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) k[j] = reinterpret_cast<const ulonglong2*>(mine)[lane + 32 * j];
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (k[j].x | k[j].y) reinterpret_cast<ulonglong2*>(mine)[lane + 32 * j] = make_ulonglong2(0ull, 0ull);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const size_t i = base + (size_t)(lane + 32 * j) * 2;
+        push_key(P, J, i, k[j].x, ~0ull, dst);
+        push_key(P, J, i + 1, k[j].y, ~0ull, dst);
       }
     } else {
-      // ---- a row of visibility keys -> the ranks that resolve it (pixel (0,0): every rank)
-      const int y = row;
-      uint32_t dst = 0;
-      for (uint32_t p = 0; p < P.world; p++)
-        if ((y >= J.rr0[p] && y < J.rr1[p]) || y < J.ax1[p]) dst |= 1u << p;
-      const size_t base = (size_t)y * J.W;
-      for (int x = threadIdx.x; x < J.W; x += blockDim.x) {
-        const unsigned long long k = J.k_mine[base + x];
+      for (int x = lane; x < nx; x += 32) {
+        const unsigned long long k = mine[x];
         const unsigned long long f = J.f_mine ? J.f_mine[base + x] : ~0ull;
         if (!k && f == ~0ull) continue;
-        if (k) J.k_mine[base + x] = 0ull;
+        if (k) mine[x] = 0ull;
         if (f != ~0ull) J.f_mine[base + x] = ~0ull;
-        const uint32_t d = (base + x == 0) ? ((1u << P.world) - 1u) : dst;
-        for (uint32_t p = 0; p < P.world; p++) {
-          if (!((d >> p) & 1u)) continue;
-          if (k) atomicMax(P.mkeys[p] + J.k_off + base + x, k);
-          if (f != ~0ull) atomicMin(P.mkeys[p] + J.f_off + base + x, f);
+        push_key(P, J, base + x, k, f, dst);
+      }
+    }
+  }
+}
+// A CTA takes batches of PRC_PUSH_BATCH segment flags: 64 threads read (and clear) one flag each and compact the flagged segments
+// into shared memory, then the CTA's 8 warps share that list. (First segment version: one warp per 32 flags walking its flagged
+// segments alone — up to 32 dependent round trips to memory per warp, 0.077 ms at 2 GPUs; whole rows before that: 0.048 ms.)
+#define PRC_PUSH_BATCH 64
+__global__ void __launch_bounds__(256) k_peer_push(const __grid_constant__ PeerTable P, const __grid_constant__ PushJob J) {
+  __shared__ unsigned int list[PRC_PUSH_BATCH];
+  __shared__ unsigned int n_list;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long n_seg = J.seg1;  // this launch merges the segments [seg0, seg1): the key plane alone, or every plane
+  const bool vec = (J.W & 3) == 0;  // 16-byte loads need rows of whole float4 / ulonglong2
+  for (long long s0 = J.seg0 + (long long)blockIdx.x * PRC_PUSH_BATCH; s0 < n_seg; s0 += (long long)gridDim.x * PRC_PUSH_BATCH) {
+    if (threadIdx.x == 0) n_list = 0;
+    __syncthreads();
+    if (threadIdx.x < PRC_PUSH_BATCH) {
+      const long long sl = s0 + threadIdx.x;
+      if (sl < n_seg) {
+        unsigned char* flag = J.dirty + (size_t)sl * PRC_DIRTY_STRIDE;
+        if (*flag != 0) {
+          *flag = 0;
+          list[atomicAdd(&n_list, 1u)] = threadIdx.x;
         }
       }
     }
+    __syncthreads();
+    const unsigned int n = n_list;
+    for (unsigned int i = warp; i < n; i += 8) push_segment(P, J, s0 + list[i], lane, vec);
+    __syncthreads();  // the list is rewritten by the next batch
   }
 }
 

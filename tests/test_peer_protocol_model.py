@@ -24,11 +24,16 @@ def frame_ops(rank, world, e, mask, shadows=True):
     ops = []
     if mask & me:
         ops.append(("signal", IMAGE_FREE, e - 1, others))
+    ops.append(("clear_next_keys", e))  # the merged key plane of frame e+1 (the planes alternate with the frame parity)
     ops.append(("forward", e))  # the camera pass needs no shadow map: it runs while slower peers still shade frame e-1
+    ops.append(("push_keys", e))  # early key push: no wait (the peers cleared plane e&1 before they signalled SHADOW(e-1))
     if shadows:
-        ops.append(("wait", SHADED, e - 1, others))
         ops.append(("raster_shadow", e))
+        ops.append(("wait", SHADED, e - 1, others))
         ops.append(("push", e))
+        ops.append(("push_keys", e))  # what the queued records added
+        ops.append(("signal", SHADOW, e, others))
+        ops.append(("wait", SHADOW, e, others))
         ops.append(("signal", SHADOW, e, others))
         ops.append(("wait", SHADOW, e, others))
     ops.append(("shade", e))
@@ -51,6 +56,7 @@ def simulate(world, masks, seed, host_lookahead):
     words = [[[0] * world for _ in range(4)] for _ in range(world)]       # words[dst][kind][src]
     maps = [[0] * world for _ in range(world)]                            # maps[holder][owner] = frame whose rows are in holder's copy
     image = [[0] * world for _ in range(world)]                           # image[holder][strip owner]
+    keys = [[dict(), dict()] for _ in range(world)]                       # keys[holder][parity] = {pusher: frame} of the merged key planes
     reading = [None] * world                                              # frame a consumer's reader is looking at (None: idle)
     queue = [[] for _ in range(world)]                                    # submitted, not yet executed
     submitted = [0] * world                                               # frames submitted by each host
@@ -89,6 +95,17 @@ def simulate(world, masks, seed, host_lookahead):
                 if (mask >> d) & 1:
                     assert words[d][k][r] <= epoch, "epoch words must not decrease"
                     words[d][k][r] = epoch
+        elif kind == "clear_next_keys":
+            e = op[1]
+            plane = keys[r][(e + 1) & 1]
+            assert all(f < e + 1 for f in plane.values()), f"rank {r} clears keys of frame {e + 1} that a peer has already pushed"
+            plane.clear()
+        elif kind == "push_keys":
+            e = op[1]
+            for p in range(world):
+                plane = keys[p][e & 1]
+                assert all(f == e for f in plane.values()), f"rank {r} pushes keys of frame {e} into a plane of rank {p} that still holds {plane}"
+                plane[r] = e
         elif kind == "raster_shadow":
             maps[r][r] = op[1]
         elif kind == "push":
@@ -98,6 +115,7 @@ def simulate(world, masks, seed, host_lookahead):
         elif kind == "shade":
             e = op[1]
             assert maps[r] == [e] * world, f"rank {r} shades frame {e} from shadow rows of frames {maps[r]}"
+            assert keys[r][e & 1] == {p: e for p in range(world)}, f"rank {r} shades frame {e} from keys {keys[r][e & 1]}"
             assert reading[r] is None or True
             image[r][r] = e
         elif kind == "copy_strip":
