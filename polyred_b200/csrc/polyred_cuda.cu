@@ -116,6 +116,8 @@ struct prc_ctx {
   DevFrame h_frame{};
   bool capturing = false;
   bool no_fused_shade = false;  // PRC_NO_FUSED_SHADE
+  bool two_streams = false;     // PRC_TWO_STREAMS=1: one-GPU frames run the shadow sweep beside the camera pass (second stream), as peer frames do
+  bool stage_single = false;    // PRC_STAGE_UNIFORMS=1: a synchronous prc_render stages its uniforms in page-locked memory (one memcpy + async DMAs)
   bool ktimers = true;  // PRC_NO_KTIMERS=1: no per-kernel-class event brackets (prc_timings.kernel_ms stays 0)
   bool ktimers_frame = true;  // ... for the frame being enqueued (PRC_FRAME_NO_KERNEL_TIMERS)
   uint32_t n_lights_alloc = 0;
@@ -127,6 +129,9 @@ struct prc_ctx {
   std::vector<void*> peer_opened;  // bases returned by cudaIpcOpenMemHandle
   void *peer_shadow_self = nullptr, *peer_image_self = nullptr;  // the exported buffers (a reallocation invalidates the group)
   uint32_t peer_epoch = 0;
+  // rows of this rank's two merged key planes that the last frame of that parity received keys for ([rr0, rr1) and [0, ax1)):
+  // exactly these are cleared before the plane is used again, so a plane is all zero whatever strips the next frame brings
+  int plane_rows[2][3] = {{0, 0, 0}, {0, 0, 0}};
   uint8_t* ext_img = nullptr;    // caller-owned page-locked host image (prc_set_host_image)
   bool defer_copy_join = false, copy_pending = false;  // see do_main: readback of peer frames overlaps the next frame's geometry
   size_t ext_img_bytes = 0, ext_img_off = 0;  // ext_img_off: prc_set_host_image_offset (double-buffered host images inside one registration)
@@ -981,6 +986,8 @@ int32_t prc_open(int32_t device, prc_ctx** out) {
   ctx->need_bins = getenv("PRC_FORCE_BINS") != nullptr;
   ctx->ktimers = !(getenv("PRC_NO_KTIMERS") && atoi(getenv("PRC_NO_KTIMERS")) != 0);
   if (const char* sb = getenv("PRC_SHADE_BANDS")) ctx->shade_bands = std::max(1, std::min(PRC_SHADE_BANDS_MAX, atoi(sb)));
+  ctx->two_streams = getenv("PRC_TWO_STREAMS") != nullptr && atoi(getenv("PRC_TWO_STREAMS")) != 0;
+  ctx->stage_single = getenv("PRC_STAGE_UNIFORMS") != nullptr && atoi(getenv("PRC_STAGE_UNIFORMS")) != 0;
   // AO constants (material/ao.go:28-32): a accumulates float32(Pi/4) in float32; Cos/Sin via float64.
   const float pi = 3.14159265358979323846f, q = pi / 4;
   float a = 0.0f;
@@ -1270,8 +1277,28 @@ static int32_t enqueue_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& 
     CK(cudaMemsetAsync(ctx->d_counters.p, 0, offsetof(Counters, large_overflow), ctx->stream));
   }
   CK(cudaEventRecordWithFlags(ctx->ev[0], ctx->stream, rec));
-  int32_t r = ctx->exact ? do_shadows<true>(ctx, fr, F, units_from_mask(fr, 0xFFFFFFFFu, 0, F.H), false)
-                         : do_shadows<false>(ctx, fr, F, units_from_mask(fr, 0xFFFFFFFFu, 0, F.H), false);
+  int32_t r;
+  if (ctx->two_streams && !ctx->capturing && (fr->flags & PRC_FRAME_SHADOWMAP) && !(fr->flags & PRC_FRAME_KEEP_GBUFFER)) {
+    // (tuning) the shadow sweep and the camera pass write different targets and share only the atomically filled record queue:
+    // side by side on two streams each fills the other's tail waves; the queued records are rasterised after the join
+    cudaStream_t st = ctx->stream;
+    CK(cudaEventRecord(ctx->ev_fork, st));
+    CK(cudaStreamWaitEvent(ctx->copy_stream2, ctx->ev_fork, 0));
+    ctx->stream = ctx->copy_stream2;
+    r = ctx->exact ? do_shadows<true>(ctx, fr, F, units_from_mask(fr, 0xFFFFFFFFu, 0, F.H), false)
+                   : do_shadows<false>(ctx, fr, F, units_from_mask(fr, 0xFFFFFFFFu, 0, F.H), false);
+    cudaEventRecord(ctx->ev_join, ctx->copy_stream2);
+    ctx->stream = st;
+    if (r == PRC_OK) r = ctx->exact ? do_main<true>(ctx, fr, F, 1, 1) : do_main<false>(ctx, fr, F, 1, 1);
+    CK(cudaEventRecordWithFlags(ctx->ev[1], st, rec));
+    CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    if (r == PRC_OK) r = ctx->exact ? do_main<true>(ctx, fr, F, 4 | 8 | 2, 1) : do_main<false>(ctx, fr, F, 4 | 8 | 2, 1);
+    if (r != PRC_OK) return r;
+    CK(cudaEventRecordWithFlags(ctx->ev[3], st, rec));
+    return PRC_OK;
+  }
+  r = ctx->exact ? do_shadows<true>(ctx, fr, F, units_from_mask(fr, 0xFFFFFFFFu, 0, F.H), false)
+                 : do_shadows<false>(ctx, fr, F, units_from_mask(fr, 0xFFFFFFFFu, 0, F.H), false);
   if (r != PRC_OK) return r;
   CK(cudaEventRecordWithFlags(ctx->ev[1], ctx->stream, rec));
   r = ctx->exact ? do_main<true>(ctx, fr, F) : do_main<false>(ctx, fr, F);
@@ -1285,7 +1312,27 @@ int32_t prc_render(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out) {
   CK(cudaSetDevice(ctx->device));
   if (ctx->peer_private) { ctx->err = "this context is connected to a peer group (its raster targets are the group's private buffers): prc_peer_disconnect first"; return PRC_ERR_INVALID; }
   DevFrame F;
+  const bool stage = ctx->stage_single && fr && !(fr->flags & (PRC_FRAME_ASYNC | PRC_FRAME_UNIFORMS_RESIDENT)) && ctx->pending_async == 0;
+  if (stage) {
+    // (tuning) a synchronous frame: nothing of the previous call is in flight, so ONE page-locked staging area takes the uniforms
+    // with a host memcpy and the DMAs run behind the first launches — each copy from pageable memory is staged by the driver
+    // before the call returns, six times per frame
+    size_t need = (size_t)fr->n_objects * sizeof(prc_object_xf) + (size_t)fr->n_lights * sizeof(DevLight) + sizeof(TileTargets) + (size_t)fr->n_ambient * 4 + 256 +
+                  sizeof(DevFrame) + 256 * 8;
+    for (uint32_t i = 0; i < fr->n_lights && fr->lights; i++)
+      if (fr->lights[i].cast_shadow) need += (size_t)fr->n_objects * 64 + 256;
+    need = (need + 4095) & ~(size_t)4095;
+    if (ctx->stage_cap < need) {
+      CK(cudaStreamSynchronize(ctx->stream));
+      if (ctx->stage) cudaFreeHost(ctx->stage);
+      ctx->stage = nullptr; ctx->stage_cap = 0;
+      CK(cudaMallocHost((void**)&ctx->stage, need));
+      ctx->stage_cap = need;
+    }
+    ctx->stage_on = true; ctx->stage_off = 0; ctx->stage_end = ctx->stage_cap;
+  }
   int32_t r = build_frame(ctx, fr, F);
+  ctx->stage_on = false;
   if (r != PRC_OK) return r;
   r = readback_begin(ctx, fr);
   if (r != PRC_OK) return r;
@@ -1541,6 +1588,7 @@ void peer_release(prc_ctx* ctx) {
   for (auto& p : ctx->peer_image) p = nullptr;
   ctx->peer_shadow_self = ctx->peer_image_self = nullptr;
   ctx->peer_epoch = 0;
+  memset(ctx->plane_rows, 0, sizeof(ctx->plane_rows));
 }
 
 int32_t peer_check(prc_ctx* ctx) {
@@ -1653,7 +1701,13 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
   unsigned long long* first_cur = mk + (size_t)(2u + (e & 1u)) * npx;
   unsigned long long* first_next = mk + (size_t)(2u + ((e + 1u) & 1u)) * npx;
   {
-    const int r0s[2] = {F.rr0, 0}, r1s[2] = {F.rr1, needs.ax1[P.self]};
+    // The plane of frame e+1 last received keys in frame e-1, for the rows this rank resolved THEN (the strips move between frames:
+    // re-balancing). Clearing this frame's rows instead left the keys of an older camera in rows the rank lost and later regained.
+    int* pr = ctx->plane_rows[(e + 1u) & 1u];
+    const int r0s[2] = {pr[0], 0}, r1s[2] = {pr[1], pr[2]};
+    pr[0] = pr[1] = pr[2] = 0;
+    int* pc = ctx->plane_rows[e & 1u];  // what this frame's plane receives
+    pc[0] = F.rr0; pc[1] = F.rr1; pc[2] = needs.ax1[P.self];
     for (int k = 0; k < 2; k++) {
       if (r1s[k] <= r0s[k]) continue;
       CK(cudaMemsetAsync(plane_next + (size_t)r0s[k] * F.W, 0, (size_t)(r1s[k] - r0s[k]) * F.W * 8, st));
@@ -1888,6 +1942,7 @@ int32_t prc_peer_connect(prc_ctx* ctx, uint32_t rank, uint32_t world, const prc_
   for (uint32_t p = 0; p < PRC_PEER_MAX; p++) ctx->peer_image[p] = image[p];
   ctx->peer_opened = opened;
   ctx->peer_epoch = 0;
+  memset(ctx->plane_rows, 0, sizeof(ctx->plane_rows));  // prc_peer_export zeroed both planes
   return PRC_OK;
 }
 

@@ -113,6 +113,46 @@ def test_peer_ao_strips_pixel00_halo(monkeypatch):
     assert ok[0, 0] == 1 and (ok == 0).any(), "test scene no longer exercises the pixel-(0,0) AO quirk"
 
 
+def test_peer_strips_move_back_and_forth_under_a_moving_camera():
+    """Re-balancing moves the strip boundaries between frames while the camera moves: a row that a rank loses and regains two
+    frames later must not still hold the visibility keys it received for the OLD camera (the merged key planes alternate with
+    the frame parity and are cleared where the previous frame of that parity wrote, not where the current strip lies)."""
+    from polyred_b200._lib import PolyredCudaError
+    s, cam, w, h = _scene()
+    cams = [synth.orbit_camera(0.35 * k, aspect=w / h) for k in range(7)]
+    parts = [[(136, 272), (0, 136)], [(48, 272), (0, 48)], [(200, 272), (0, 200)]]
+    one = render.NewRenderer(*_opts(s, cam, w, h), render.CUDA(0))
+    one._ensure_uploaded()
+    rs, fds, _ = _group(s, cam, w, h, [0, 0])
+    for k, c in enumerate(cams):
+        rows = parts[k % 2] if k < 4 else parts[(k % 2) * 2]  # A B A B | A C A: every boundary is crossed in both directions
+        one.cfg.Camera = c   # (no Options(): the light cameras stay, the persistent maps keep growing - on both sides)
+        want = one.Render().copy()
+        for attempt in range(4):
+            for j, r in enumerate(rs):
+                r.cfg.Camera = c
+                fd = r.frame_desc(no_readback=True)
+                fd.struct.row0, fd.struct.row1 = rows[j]
+                r._backend.render_peer(fd, rows, 1)
+            again, state = False, 0
+            for r in rs:
+                try:
+                    r._backend.sync()
+                except PolyredCudaError as e:
+                    assert e.code == A.PRC_ERR_RETRY
+                    again = True
+                state |= r._backend.frame_state()
+            if not again:
+                break
+            for r in rs:
+                r._backend.set_frame_state(state)
+        assert not again
+        got = rs[0]._backend.read_image(w, h)
+        assert int((got != want).any(axis=2).sum()) == 0, f"frame {k} (strips {rows}) differs from the one-context frame"
+    for r in rs:
+        r._backend.peer_disconnect()
+
+
 def test_peer_two_contexts_one_process(monkeypatch):
     import torch
     if torch.cuda.device_count() < 2:
