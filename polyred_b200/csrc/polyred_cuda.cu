@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -117,6 +118,7 @@ struct prc_ctx {
   bool capturing = false;
   bool no_fused_shade = false;  // PRC_NO_FUSED_SHADE
   bool two_streams = false;     // PRC_TWO_STREAMS=1: one-GPU frames run the shadow sweep beside the camera pass (second stream), as peer frames do
+  bool zero_copy_out = false;   // PRC_ZERO_COPY_OUT=1: the shading kernels store the frame into the page-locked host image themselves (no device->host copies)
   bool stage_single = false;    // PRC_STAGE_UNIFORMS=1: a synchronous prc_render stages its uniforms in page-locked memory (one memcpy + async DMAs)
   bool ktimers = true;  // PRC_NO_KTIMERS=1: no per-kernel-class event brackets (prc_timings.kernel_ms stays 0)
   bool ktimers_frame = true;  // ... for the frame being enqueued (PRC_FRAME_NO_KERNEL_TIMERS)
@@ -773,7 +775,13 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
     KTimer kt(ctx, PRC_K_SHADE);
     // With a readback pending the strip is shaded in PRC_SHADE_BANDS row bands, top image rows first; each band's
     // device->host DMA runs on the copy stream while the next band is shaded (only the last band's copy is exposed).
-    const bool banded_copy = ctx->rb_dst && ctx->msaa == 1;
+    bool banded_copy = ctx->rb_dst && ctx->msaa == 1;
+    uint32_t* host_image = nullptr;
+    if (banded_copy && ctx->zero_copy_out) {
+      void* dp = nullptr;
+      if (cudaHostGetDevicePointer(&dp, ctx->rb_dst, 0) == cudaSuccess && dp) { host_image = (uint32_t*)dp; banded_copy = false; }
+      else (void)cudaGetLastError();
+    }
     const int rows = F.row1 - F.row0;
     const int nb = (banded_copy && rows >= 64 * ctx->shade_bands) ? ctx->shade_bands : 1;
     const int band = ((rows + nb - 1) / nb + 3) & ~3;
@@ -784,11 +792,11 @@ int32_t do_main(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
       if (Fb.row0 >= Fb.row1) break;
       const dim3 sg((F.W + 31) / 32, (Fb.row1 - Fb.row0 + 3) / 4);
       if (fused) {
-        if (es) k_resolve_shade<E, E><<<sg, 128, 0, st>>>(ctx->S, Fb, aoc, keys, special, image);
-        else k_resolve_shade<E, false><<<sg, 128, 0, st>>>(ctx->S, Fb, aoc, keys, special, image);
+        if (es) k_resolve_shade<E, E><<<sg, 128, 0, st>>>(ctx->S, Fb, aoc, keys, special, image, host_image);
+        else k_resolve_shade<E, false><<<sg, 128, 0, st>>>(ctx->S, Fb, aoc, keys, special, image, host_image);
       } else {
-        if (es) k_shade<true><<<sg, 128, 0, st>>>(ctx->S, Fb, aoc, keys, G, special, image);
-        else k_shade<false><<<sg, 128, 0, st>>>(ctx->S, Fb, aoc, keys, G, special, image);
+        if (es) k_shade<true><<<sg, 128, 0, st>>>(ctx->S, Fb, aoc, keys, G, special, image, host_image);
+        else k_shade<false><<<sg, 128, 0, st>>>(ctx->S, Fb, aoc, keys, G, special, image, host_image);
       }
       ctx->launches++;
       if (banded_copy) {
@@ -856,7 +864,7 @@ int32_t readback_begin(prc_ctx* ctx, const prc_frame* fr) {
       if (posix_memalign(&q, 4096, (total + 4095) & ~(size_t)4095) != 0) { ctx->err = "out of host memory"; return PRC_ERR_CUDA; }
       memset(q, 0, total);
       p = (uint8_t*)q;
-      CK(cudaHostRegister(p, (total + 4095) & ~(size_t)4095, cudaHostRegisterDefault));
+      CK(cudaHostRegister(p, (total + 4095) & ~(size_t)4095, cudaHostRegisterMapped));  // mapped: PRC_ZERO_COPY_OUT stores into it from the shading kernel
     }
     ctx->h_img_cap = total;
   }
@@ -987,6 +995,7 @@ int32_t prc_open(int32_t device, prc_ctx** out) {
   ctx->ktimers = !(getenv("PRC_NO_KTIMERS") && atoi(getenv("PRC_NO_KTIMERS")) != 0);
   if (const char* sb = getenv("PRC_SHADE_BANDS")) ctx->shade_bands = std::max(1, std::min(PRC_SHADE_BANDS_MAX, atoi(sb)));
   ctx->two_streams = getenv("PRC_TWO_STREAMS") != nullptr && atoi(getenv("PRC_TWO_STREAMS")) != 0;
+  ctx->zero_copy_out = getenv("PRC_ZERO_COPY_OUT") != nullptr && atoi(getenv("PRC_ZERO_COPY_OUT")) != 0;
   ctx->stage_single = getenv("PRC_STAGE_UNIFORMS") != nullptr && atoi(getenv("PRC_STAGE_UNIFORMS")) != 0;
   // AO constants (material/ao.go:28-32): a accumulates float32(Pi/4) in float32; Cos/Sin via float64.
   const float pi = 3.14159265358979323846f, q = pi / 4;
@@ -1575,6 +1584,48 @@ int32_t alloc_offset(prc_ctx* ctx, const void* p, uint64_t* off) {
   return PRC_OK;
 }
 
+// Loads every kernel of this library into the current context NOW. CUDA 12 loads a kernel lazily at its first launch, and that load
+// may synchronise the whole context. Ranks that share one device (several contexts of one process on one GPU: the single-GPU form
+// of the group tests) share its primary context: rank B's first launch of some kernel then waits for everything running on the
+// device, including rank A's one-warp wait kernel, which spins for a signal rank B has not enqueued yet — B is stuck in the load —
+// until the wait gives up after PRC_PEER_TIMEOUT_NS (seen as PRC_ERR_PEER in tests/test_gpu_group.py, first on an 8-GPU box:
+// whether it happens is a race between the two submit threads). Called by prc_peer_connect, i.e. before any wait kernel exists.
+// Ranks on different devices (the real thing) were never affected: a load synchronises its own context only.
+void preload_kernels() {
+  static std::mutex mu;
+  static std::vector<int> done;
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return; }
+  if (getenv("PRC_NO_PRELOAD")) return;  // (to reproduce the stall: tests/test_gpu_group.py, first test)
+  std::lock_guard<std::mutex> lk(mu);
+  for (int d : done)
+    if (d == dev) return;
+  done.push_back(dev);
+  typedef int (*get_module_fn)(void**, void*);
+  typedef int (*count_fn)(unsigned int*, void*);
+  typedef int (*enum_fn)(void**, unsigned int, void*);
+  typedef int (*load_fn)(void*);
+  void *f_mod = nullptr, *f_cnt = nullptr, *f_enum = nullptr, *f_load = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  bool ok = cudaGetDriverEntryPoint("cuFuncGetModule", &f_mod, cudaEnableDefault, &q) == cudaSuccess && f_mod && q == cudaDriverEntryPointSuccess;
+  ok = ok && cudaGetDriverEntryPoint("cuModuleGetFunctionCount", &f_cnt, cudaEnableDefault, &q) == cudaSuccess && f_cnt && q == cudaDriverEntryPointSuccess;
+  ok = ok && cudaGetDriverEntryPoint("cuModuleEnumerateFunctions", &f_enum, cudaEnableDefault, &q) == cudaSuccess && f_enum && q == cudaDriverEntryPointSuccess;
+  ok = ok && cudaGetDriverEntryPoint("cuFuncLoad", &f_load, cudaEnableDefault, &q) == cudaSuccess && f_load && q == cudaDriverEntryPointSuccess;
+  cudaFunction_t fn = nullptr;
+  ok = ok && cudaGetFuncBySymbol(&fn, (const void*)k_peer_wait) == cudaSuccess && fn;
+  void* mod = nullptr;
+  unsigned int n = 0;
+  ok = ok && ((get_module_fn)f_mod)(&mod, (void*)fn) == 0 && mod && ((count_fn)f_cnt)(&n, mod) == 0 && n > 0;
+  if (ok) {
+    std::vector<void*> fns(n, nullptr);
+    if (((enum_fn)f_enum)(fns.data(), n, mod) == 0)
+      for (void* f : fns)
+        if (f) (void)((load_fn)f_load)(f);
+  }
+  (void)cudaGetLastError();
+  if (getenv("PRC_DEBUG_PRELOAD")) fprintf(stderr, "[polyred_cuda] preload_kernels(device %d): %s, %u functions\n", dev, ok ? "loaded" : "driver entry points unavailable", n);
+}
+
 void peer_release(prc_ctx* ctx) {
   for (void* b : ctx->peer_opened) cudaIpcCloseMemHandle(b);
   ctx->peer_opened.clear();
@@ -1887,6 +1938,7 @@ int32_t prc_peer_connect(prc_ctx* ctx, uint32_t rank, uint32_t world, const prc_
     ctx->err = "prc_peer_connect: call prc_peer_export first";
     return PRC_ERR_INVALID;
   }
+  preload_kernels();
   const prc_peer_handle& mine = all[rank];
   if (mine.pid != (uint64_t)getpid() || mine.shadow_ptr != (uint64_t)(uintptr_t)ctx->d_shadow_all.p) { ctx->err = "prc_peer_connect: all[rank] is not this context's handle"; return PRC_ERR_INVALID; }
   PeerTable T{};
@@ -1960,7 +2012,7 @@ int32_t prc_set_host_image(prc_ctx* ctx, void* ptr, uint64_t bytes) {
   if (!ptr) return PRC_OK;
   {
     // several contexts of ONE process may share the image (single-process tests): the first one registers it
-    const cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+    const cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
     if (e != cudaSuccess && e != cudaErrorHostMemoryAlreadyRegistered) { ctx->err = std::string("cudaHostRegister: ") + cudaGetErrorString(e); return PRC_ERR_CUDA; }
     (void)cudaGetLastError();
     ctx->ext_img_registered = e == cudaSuccess;

@@ -6,6 +6,7 @@
 // "the same frame as one context, bit for bit" (tests/test_gpu_group.py).
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdlib>
@@ -48,6 +49,7 @@ struct prc_group {
   std::vector<uint32_t> row0, row1;  // screen rows of the frame buffer per rank (what prc_render_peer takes)
   uint64_t frames_since_connect = 0;
   bool balance = true;
+  int stagger_ms = 0;  // PRC_GROUP_STAGGER_MS (tests): rank r submits every frame r x this many ms late, so that its peers are already waiting for it
   // page-locked host images shared by all contexts (each DMAs its own strip): TWO images inside one registration, used alternately
   // like the reference's double buffer (render/raster.go:86,201-206): a frame read in place stays valid during the next Render()
   uint8_t* host_img = nullptr;
@@ -313,6 +315,7 @@ int32_t prc_group_open(const int32_t* devices, uint32_t n, prc_group** out) {
   }
   const char* b = getenv("PRC_GROUP_BALANCE");
   g->balance = !(b && atoi(b) == 0);
+  if (const char* sg = getenv("PRC_GROUP_STAGGER_MS")) g->stagger_ms = std::max(0, std::min(1000, atoi(sg)));
   if (n > 1)
     for (uint32_t r = 0; r < n; r++) {
       g->workers.push_back(new Worker());
@@ -422,6 +425,7 @@ int32_t prc_group_render(prc_group* g, const prc_frame* fr, uint8_t* rgba_out) {
       if (!measure && n > 1) f.flags |= PRC_FRAME_NO_KERNEL_TIMERS;
       f.row0 = g->row0[r];
       f.row1 = g->row1[r];
+      if (g->stagger_ms && r) std::this_thread::sleep_for(std::chrono::milliseconds((long)g->stagger_ms * r));
       int32_t rc = prc_render_peer(g->ctx[r], &f, n, g->row0.data(), g->row1.data(), on_device ? 1u : 0u);
       if (rc != PRC_OK || async) return rc;
       return prc_sync(g->ctx[r]);

@@ -1547,7 +1547,7 @@ __global__ void k_shade_special(const __grid_constant__ DevScene S, const __grid
 #endif
 template <bool E>
 __global__ void __launch_bounds__(128, PRC_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DevScene S, const __grid_constant__ DevFrame F, const AoConsts* __restrict__ A, const unsigned long long* __restrict__ keys, GBuf G,
-                                               const uint32_t* __restrict__ special, uint32_t* __restrict__ image) {
+                                               const uint32_t* __restrict__ special, uint32_t* __restrict__ image, uint32_t* __restrict__ host_image = nullptr) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = F.row0 + blockIdx.y * 4 + (threadIdx.x >> 5);
   if (x >= F.W || y >= F.row1) return;
@@ -1565,6 +1565,9 @@ __global__ void __launch_bounds__(128, PRC_SHADE_MIN_BLOCKS) k_shade(const __gri
     col = (uint32_t)F.gamma[chan(col, 0)] | ((uint32_t)F.gamma[chan(col, 1)] << 8) | ((uint32_t)F.gamma[chan(col, 2)] << 16) | (col & 0xff000000u);
   if (F.flags & PRC_FRAME_BGRA) col = __byte_perm(col, 0, 0x3012);  // PixelFormatBGRA: bytes B,G,R,A (buffer.go:242-251)
   image[(size_t)(F.H - 1 - y) * F.W + x] = col;  // image row r = screen y = H-1-r (buffer.go:225)
+  // zero-copy readback: the same pixel straight into the caller-visible page-locked image (a warp writes one 128-byte line),
+  // so the frame crosses PCIe while it is being shaded instead of in copies that start when a band is done
+  if (host_image) __stcs(host_image + (size_t)(F.H - 1 - y) * F.W + x, col);
 }
 
 // K3+K4 fused: visibility key -> attributes -> colour in one kernel, without the 64 B/pixel G-buffer round trip. The
@@ -1577,7 +1580,7 @@ __global__ void __launch_bounds__(128, PRC_SHADE_MIN_BLOCKS) k_shade(const __gri
 #endif
 template <bool E, bool ES>
 __global__ void __launch_bounds__(128, PRC_FUSED_MIN_BLOCKS) k_resolve_shade(const __grid_constant__ DevScene S, const __grid_constant__ DevFrame F, const AoConsts* __restrict__ A, const unsigned long long* __restrict__ keys,
-                                                       const uint32_t* __restrict__ special, uint32_t* __restrict__ image) {
+                                                       const uint32_t* __restrict__ special, uint32_t* __restrict__ image, uint32_t* __restrict__ host_image = nullptr) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = F.row0 + blockIdx.y * 4 + (threadIdx.x >> 5);
   if (x >= F.W || y >= F.row1) return;
@@ -1597,6 +1600,9 @@ __global__ void __launch_bounds__(128, PRC_FUSED_MIN_BLOCKS) k_resolve_shade(con
     col = (uint32_t)F.gamma[chan(col, 0)] | ((uint32_t)F.gamma[chan(col, 1)] << 8) | ((uint32_t)F.gamma[chan(col, 2)] << 16) | (col & 0xff000000u);
   if (F.flags & PRC_FRAME_BGRA) col = __byte_perm(col, 0, 0x3012);  // PixelFormatBGRA: bytes B,G,R,A (buffer.go:242-251)
   image[(size_t)(F.H - 1 - y) * F.W + x] = col;  // image row r = screen y = H-1-r (buffer.go:225)
+  // zero-copy readback: the same pixel straight into the caller-visible page-locked image (a warp writes one 128-byte line),
+  // so the frame crosses PCIe while it is being shaded instead of in copies that start when a band is done
+  if (host_image) __stcs(host_image + (size_t)(F.H - 1 - y) * F.W + x, col);
 }
 
 // ---------------------------------------------------------------------------------------------

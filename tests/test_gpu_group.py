@@ -43,6 +43,21 @@ def _device_sets():
     return sets
 
 
+def test_group_rank_that_submits_late_does_not_stall_the_group(monkeypatch):
+    """Kept FIRST in this file: it should be the first peer frame of the process. Rank 1 submits every frame 40 ms after rank 0
+    (PRC_GROUP_STAGGER_MS), so rank 0's one-warp wait kernel is already spinning on the shared GPU when rank 1 launches each of
+    its kernels for the first time. With CUDA's lazy module loading such a first launch may synchronise the whole context - i.e.
+    wait for the spinning kernel, which waits for rank 1: the wait then gave up after 4 s and the frame failed with PRC_ERR_PEER
+    (round 2, first seen on an 8-GPU box). prc_peer_connect now loads every kernel of the library before the first frame."""
+    monkeypatch.setenv("PRC_GROUP_STAGGER_MS", "40")
+    s, cam, w, h = _city()
+    ref = render.NewRenderer(*_opts(s, cam, w, h), render.CUDA(0)).Render().copy()
+    r = render.NewRenderer(*_opts(s, cam, w, h), render.CUDA(0, 0))
+    for k in range(4):
+        assert np.array_equal(r.Render(), ref), f"group frame {k + 1} differs"
+    r._backend.close()
+
+
 @pytest.mark.parametrize("devices", _device_sets() if os.environ.get("PRC_TEST_GROUP", "1") != "0" else [])
 def test_group_frame_equals_the_one_context_frame(devices):
     s, cam, w, h = _city()
