@@ -20,6 +20,11 @@ from polyred_b200 import partition, render, synth
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("PRC_TEST_PEER") == "0", reason="PRC_TEST_PEER=0")]
 
 
+def _n_devices():
+    from polyred_b200 import _lib
+    return int(_lib.lib().prc_device_count())
+
+
 def _scene(w=480, h=272):
     s, cam = synth.city_scene(n_objects=25, obj_stacks=20, obj_slices=20, ground_cells=60, tex_size=64)
     return s, cam, w, h
@@ -240,3 +245,25 @@ def test_peer_msaa_strips_downsample_locally(monkeypatch, world):
         r._backend.set_host_image(None)
         r._backend.peer_disconnect()
 
+
+
+def test_multi_process_frames_equal_the_one_gpu_frame():
+    """tests/multigpu_check.py under torchrun, one process per GPU (CUDA IPC + NVLink peer memory, and the NCCL path of round 1):
+    every N-GPU frame — equal strips, re-balanced strips, strips read back into one shared host image, a moving camera with
+    alternating partitions — must equal rank 0's own 1-GPU frame bit for bit. Needs two GPUs (the driver's test box has one;
+    the logs of the 2- and 8-GPU runs are profiles/multigpu_check_{2,8}_r2.log)."""
+    import subprocess
+    import sys
+    n = _n_devices()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    n = 8 if n >= 8 else 4 if n >= 4 else 2
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+                        "--master-port", str(29400 + os.getpid() % 500), os.path.join(root, "tests", "multigpu_check.py")],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    if os.environ.get("PRC_MULTIGPU_LOG"):  # keep the run's output (tools/r2_call_j.sh -> profiles/)
+        with open(os.environ["PRC_MULTIGPU_LOG"], "w") as f:
+            f.write(p.stdout + p.stderr)
+    lines = [l for l in p.stdout.splitlines() if l.startswith("[multigpu_check]") and "pixels differing" in l]
+    assert p.returncode == 0 and lines and all(l.rstrip().endswith("= 0") for l in lines), p.stdout[-3000:] + p.stderr[-3000:]
