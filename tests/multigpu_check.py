@@ -48,6 +48,8 @@ def main():
                 pf.submit(r2.frame_desc(no_readback=True))
             pf.finish()
             rebalanced_out = pf.image(host=True)
+            if rebalanced_out is not None:
+                rebalanced_out = rebalanced_out.copy()  # image() hands out one reused page-locked buffer
             if rank == 0:
                 print(f"[multigpu_check] {name}: rebalanced strips {[b - a for a, b in pf.rows]} from per-rank (raster, shading) ms {[(round(c[0], 3), round(c[1], 3)) for c in costs]}")
             # and the e2e form: every rank reads its own strip back into one shared host image, no device-side gather
