@@ -131,6 +131,7 @@ struct prc_ctx {
   std::vector<void*> peer_opened;  // bases returned by cudaIpcOpenMemHandle
   void *peer_shadow_self = nullptr, *peer_image_self = nullptr;  // the exported buffers (a reallocation invalidates the group)
   uint32_t peer_epoch = 0;
+  unsigned long long peer_timeout_ns = PRC_PEER_TIMEOUT_NS;  // PRC_PEER_TIMEOUT_MS
   // rows of this rank's two merged key planes that the last frame of that parity received keys for ([rr0, rr1) and [0, ax1)):
   // exactly these are cleared before the plane is used again, so a plane is all zero whatever strips the next frame brings
   int plane_rows[2][3] = {{0, 0, 0}, {0, 0, 0}};
@@ -994,6 +995,7 @@ int32_t prc_open(int32_t device, prc_ctx** out) {
   ctx->need_bins = getenv("PRC_FORCE_BINS") != nullptr;
   ctx->ktimers = !(getenv("PRC_NO_KTIMERS") && atoi(getenv("PRC_NO_KTIMERS")) != 0);
   if (const char* sb = getenv("PRC_SHADE_BANDS")) ctx->shade_bands = std::max(1, std::min(PRC_SHADE_BANDS_MAX, atoi(sb)));
+  if (const char* pt = getenv("PRC_PEER_TIMEOUT_MS")) ctx->peer_timeout_ns = (unsigned long long)std::max(1, atoi(pt)) * 1000000ull;
   ctx->two_streams = getenv("PRC_TWO_STREAMS") != nullptr && atoi(getenv("PRC_TWO_STREAMS")) != 0;
   ctx->zero_copy_out = getenv("PRC_ZERO_COPY_OUT") != nullptr && atoi(getenv("PRC_ZERO_COPY_OUT")) != 0;
   ctx->stage_single = getenv("PRC_STAGE_UNIFORMS") != nullptr && atoi(getenv("PRC_STAGE_UNIFORMS")) != 0;
@@ -1670,7 +1672,7 @@ inline void peer_wait(prc_ctx* ctx, uint32_t kind, uint32_t epoch, uint32_t mask
     ctx->ev_used += 2;
     cudaEventRecord(ctx->evpool[a], ctx->stream);
   }
-  k_peer_wait<<<1, PRC_PEER_MAX, 0, ctx->stream>>>(P.signals[P.self], P.world, P.self, kind, epoch, mask, (unsigned int*)ctx->d_peer_err.p);
+  k_peer_wait<<<1, PRC_PEER_MAX, 0, ctx->stream>>>(P.signals[P.self], P.world, P.self, kind, epoch, mask, (unsigned int*)ctx->d_peer_err.p, ctx->peer_timeout_ns);
   ctx->launches++;
   if (ctx->peer_trace) {
     cudaEventRecord(ctx->evpool[a + 1], ctx->stream);
@@ -1702,7 +1704,7 @@ inline void peer_signal_wait(prc_ctx* ctx, uint32_t sig_kind, uint32_t sig_epoch
     ctx->ev_used += 2;
     cudaEventRecord(ctx->evpool[a], ctx->stream);
   }
-  k_peer_signal_wait<<<1, PRC_PEER_MAX, 0, ctx->stream>>>(P, sig_kind, sig_epoch, sig_mask, wait_kind, wait_epoch, wait_mask, (unsigned int*)ctx->d_peer_err.p);
+  k_peer_signal_wait<<<1, PRC_PEER_MAX, 0, ctx->stream>>>(P, sig_kind, sig_epoch, sig_mask, wait_kind, wait_epoch, wait_mask, (unsigned int*)ctx->d_peer_err.p, ctx->peer_timeout_ns);
   ctx->launches++;
   if (ctx->peer_trace) {
     cudaEventRecord(ctx->evpool[a + 1], ctx->stream);
@@ -1801,6 +1803,22 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
     ctx->launches++;
   };
   int32_t r = PRC_OK;
+  // A frame that fails while it is being enqueued (a launch or allocation error) has already advanced this rank's epoch, and its
+  // peers will wait for this frame's signals: publish them, so that the peers finish at once instead of spinning until the wait
+  // times out. The frame is invalid on every rank; this rank's caller gets the error and drops the connection
+  // (prc_group_render disconnects, PeerFrames.finish() votes).
+  auto fail = [&](int32_t code) {
+    ctx->stream = st;
+    ctx->part_rank = 0; ctx->part_world = 1; ctx->part_active = false;
+    ctx->skip_key_clear = false; ctx->defer_copy_join = false;
+    ctx->keys_shade = nullptr; ctx->first_shade = nullptr;
+    (void)cudaGetLastError();
+    peer_signal(ctx, PRC_SIG_SHADOW, e, all);
+    if (shadows) peer_signal(ctx, PRC_SIG_SHADED, e, all);
+    peer_signal(ctx, PRC_SIG_IMAGE, e, image_mask & all);
+    (void)cudaGetLastError();
+    return code;
+  };
   if (shadows && two_streams) {
     CK(cudaEventRecord(ctx->ev_fork, st));
     CK(cudaStreamWaitEvent(ctx->copy_stream2, ctx->ev_fork, 0));
@@ -1824,7 +1842,7 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
   else if (r == PRC_OK && shadows) r = do_shadows<E>(ctx, fr, Fr, units_from_mask(fr, 0xFFFFFFFFu, 0, F.H), false);
   if (r == PRC_OK) r = do_main<E>(ctx, fr, Fr, 4, 1);  // queued records of the camera AND the shadow passes
   ctx->part_rank = 0; ctx->part_world = 1; ctx->part_active = false;
-  if (r != PRC_OK) return r;
+  if (r != PRC_OK) return fail(r);
   // ---- exchange: what the queued records added to the key plane, and the shadow planes
   if (shadows) peer_wait(ctx, PRC_SIG_SHADED, e - 1, all);  // nobody may still be shading the previous frame from the maps about to be merged into
   {
@@ -1838,7 +1856,7 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
   r = do_main<E>(ctx, fr, F, 8 | 2, 1);
   ctx->defer_copy_join = false;
   ctx->keys_shade = nullptr; ctx->first_shade = nullptr;
-  if (r != PRC_OK) return r;
+  if (r != PRC_OK) return fail(r);
   // image strip: screen rows [row0,row1) = image rows [H-row1, H-row0)
   const size_t off = (size_t)(F.H - F.row1) * F.W * 4, bytes = (size_t)(F.row1 - F.row0) * F.W * 4;
   const uint32_t consumers = image_mask & all;

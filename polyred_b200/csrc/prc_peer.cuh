@@ -21,7 +21,7 @@
 namespace prc {
 
 #define PRC_PEER_MAX 16              // ranks in one exchange group (one NVSwitch domain)
-#define PRC_PEER_TIMEOUT_NS 4000000000ull
+#define PRC_PEER_TIMEOUT_NS 4000000000ull  // default; PRC_PEER_TIMEOUT_MS in the environment of prc_open overrides it (a host that may stall longer between submits)
 
 // signal words of one rank, written by its peers: word [kind][source rank] holds the last epoch the source finished
 enum PeerSignal : uint32_t {
@@ -73,14 +73,14 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // Waits until signal word [kind][src] of THIS rank has reached `epoch`, for every src != self in `mask`.
 // One thread per source rank; <<<1, PRC_PEER_MAX>>>.
 __global__ void k_peer_wait(const uint32_t* __restrict__ my_signals, uint32_t world, uint32_t self, uint32_t kind, uint32_t epoch, uint32_t mask,
-                            unsigned int* __restrict__ timeouts) {
+                            unsigned int* __restrict__ timeouts, unsigned long long timeout_ns) {
   const uint32_t src = threadIdx.x;
   if (src >= world || src == self || !((mask >> src) & 1u)) return;
   const uint32_t* w = my_signals + kind * PRC_PEER_MAX + src;
   const unsigned long long t0 = global_ns();
   unsigned int spins = 0;
   while ((int32_t)(ld_acquire_sys(w) - epoch) < 0) {  // epochs are compared modulo 2^32
-    if ((++spins & 1023u) == 0 && global_ns() - t0 > PRC_PEER_TIMEOUT_NS) {
+    if ((++spins & 1023u) == 0 && global_ns() - t0 > timeout_ns) {
       atomicAdd(timeouts, 1u);
       return;
     }
@@ -101,7 +101,7 @@ __global__ void k_peer_signal(PeerTable P, uint32_t kind, uint32_t epoch, uint32
 // frame): thread t publishes `sig_epoch` to rank t, then waits for rank t's word. The threads are independent, so this is exactly
 // the two kernels back to back.
 __global__ void k_peer_signal_wait(PeerTable P, uint32_t sig_kind, uint32_t sig_epoch, uint32_t sig_mask, uint32_t wait_kind, uint32_t wait_epoch,
-                                   uint32_t wait_mask, unsigned int* __restrict__ timeouts) {
+                                   uint32_t wait_mask, unsigned int* __restrict__ timeouts, unsigned long long timeout_ns) {
   const uint32_t t = threadIdx.x;
   const bool peer = t < P.world && t != P.self;
   if (peer && ((sig_mask >> t) & 1u)) {
@@ -114,7 +114,7 @@ __global__ void k_peer_signal_wait(PeerTable P, uint32_t sig_kind, uint32_t sig_
   const unsigned long long t0 = global_ns();
   unsigned int spins = 0;
   while ((int32_t)(ld_acquire_sys(w) - wait_epoch) < 0) {
-    if ((++spins & 1023u) == 0 && global_ns() - t0 > PRC_PEER_TIMEOUT_NS) {
+    if ((++spins & 1023u) == 0 && global_ns() - t0 > timeout_ns) {
       atomicAdd(timeouts, 1u);
       return;
     }

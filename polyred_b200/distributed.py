@@ -2,7 +2,7 @@
 
 The reference has no multi-GPU path. Partition (north_star): the scene is replicated, the
 screen is cut into N equal horizontal strips, the Ls shadow maps are cut into (light, row
-range) shards dealt round-robin. Per frame:
+range) shards, one contiguous chunk of the stacked rows per rank. Per frame:
   1. every rank rasterises its chunk of the stacked shadow maps                (prc_render_shadows)
   2. ONE in-place NCCL all-gather over the library's contiguous shadow buffer  (prc_device_shadow_all), asynchronous
   3. meanwhile: camera geometry + raster + resolve for this rank's strip       (prc_render_forward)
@@ -43,6 +43,16 @@ class DistributedFrame:
         self.w, self.h = c.Width, c.Height
         sources, _ = c.Scene.Lights()
         self.cast = [i for i, l in enumerate(sources) if l.cast_shadow] if c.ShadowMap else []
+        # validated here, on EVERY rank alike (same h, world and options everywhere): a rank that raised alone later — the
+        # library rejects an empty strip — would leave the others waiting in the all-gather
+        from ._lib import PolyredCudaError
+        from . import _abi as A
+        if max(1, int(getattr(c, "MSAA", 1))) != 1:
+            raise PolyredCudaError(A.PRC_ERR_UNSUPPORTED, "DistributedFrame: MSAA frames are cut into strips by PeerFrames / prc_group_render only")
+        if world < 1 or partition.strips(self.h, world)[1][-1][0] >= partition.strips(self.h, world)[1][-1][1]:
+            raise PolyredCudaError(A.PRC_ERR_INVALID, f"DistributedFrame: {self.h} rows cannot be cut into {world} equal non-empty strips")
+        if self.cast and len(self.cast) * self.h < world:
+            raise PolyredCudaError(A.PRC_ERR_INVALID, f"DistributedFrame: {len(self.cast)} shadow maps of {self.h} rows cannot be cut into {world} shards")
         self.img_chunk, self.rows = partition.strips(self.h, world)
         self.chunk, _ = partition.shadow_chunks(self.h, world, len(self.cast))
         self.units = partition.shadow_units(self.h, world, self.cast)
@@ -68,8 +78,9 @@ class DistributedFrame:
         torch, be, w, h = self.torch, self.be, self.w, self.h
         with torch.cuda.stream(self.stream):  # NCCL orders itself after / before the library's stream
             work = None
+            mine = [(li, a, b) for li, a, b, owner in self.units if owner == self.rank]
             if self.cast:
-                be.render_shadow_units(fd, [(li, a, b) for li, a, b, owner in self.units if owner == self.rank])
+                be.render_shadow_units(fd, mine)  # (no library call — and no uniform upload — when this rank owns no unit)
                 ptr, nbytes, cap = be.device_shadow_all()
                 cb = self.chunk * w * 4
                 assert cb * self.world <= cap, "shadow buffer padding too small for this world size"
@@ -81,8 +92,8 @@ class DistributedFrame:
                     work = None
             from . import _abi as A
             flags = fd.struct.flags
-            if self.cast:
-                fd.struct.flags = flags | A.PRC_FRAME_UNIFORMS_RESIDENT  # uploaded by prc_render_shadows above
+            if mine:
+                fd.struct.flags = flags | A.PRC_FRAME_UNIFORMS_RESIDENT  # uploaded by prc_render_shadow_units above
             be.render_forward(fd)      # camera geometry + raster + resolve overlap the exchange
             if work is not None:
                 work.wait()

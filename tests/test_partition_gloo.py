@@ -296,3 +296,26 @@ def test_balanced_bounds_properties_hypothesis():
     for n in (2, 3, 8):
         eq = partition.equal_bounds(240 * n, n)
         assert partition.balanced_bounds(eq, [5.0] * n) == eq
+
+
+def test_distributed_frame_rejects_impossible_partitions_on_every_rank():
+    """equal strips of ceil(H/world) rows leave trailing ranks an EMPTY strip when H is small, and only those
+    ranks failed (inside the library) while the others sat in the all-gather. The constructor now refuses such a partition —
+    and MSAA, and more ranks than shadow rows — from the configuration alone, i.e. on every rank alike, before any CUDA call."""
+    import types
+    import pytest
+    from polyred_b200._lib import PolyredCudaError
+    from polyred_b200.distributed import DistributedFrame
+
+    def fake(h, msaa=1, n_cast=1):
+        lights = [types.SimpleNamespace(cast_shadow=True) for _ in range(n_cast)]
+        cfg = types.SimpleNamespace(Width=64, Height=h, MSAA=msaa, ShadowMap=True, Scene=types.SimpleNamespace(Lights=lambda: (lights, [])))
+        return types.SimpleNamespace(cfg=cfg, _backend=None)
+
+    for rank in range(8):  # 9 rows over 8 ranks: strips of 2 rows, ranks 5..7 would be empty
+        with pytest.raises(PolyredCudaError, match="non-empty strips"):
+            DistributedFrame(fake(9), rank, 8, 0)
+    with pytest.raises(PolyredCudaError, match="MSAA"):
+        DistributedFrame(fake(64, msaa=2), 0, 2, 0)
+    with pytest.raises(PolyredCudaError, match="non-empty strips"):
+        DistributedFrame(fake(3), 0, 4, 0)
