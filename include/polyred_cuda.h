@@ -78,6 +78,11 @@ extern "C" {
                                      * keep the frames on the device (present, multi-view batches) this removes the host bubble between frames */
 #define PRC_FRAME_NO_KERNEL_TIMERS 512u /* no per-kernel-class CUDA-event brackets for this frame (prc_timings.kernel_ms stays 0): an event
                                         * pair costs ~2.6 us of stream time, which matters for the 0.2 ms frames of an 8-GPU group */
+#define PRC_FRAME_IMAGE_AT_SYNC 1024u /* prc_render_peer, on a rank that receives the gathered image (image_mask): do not wait INSIDE the stream for
+                                       * the peers' strips. The wait (and the "image buffer free" announcement that follows it) runs beside the
+                                       * stream, so this rank's next frame starts while the strips of this one still arrive over NVLink (29 MB
+                                       * into rank 0 at 8 GPUs = 0.04 ms of a 0.28 ms frame). The gathered image is then complete after
+                                       * prc_sync — not for work enqueued on prc_stream() — and stays valid until the next prc_render_peer */
 #define PRC_FRAME_SHADOW_RESET 64u /* zero the shadow maps at the start of this frame, stream-ordered: what Options()
                                      * does between views (render/options.go:125-141), without prc_shadow_reset's host sync */
 
@@ -299,7 +304,7 @@ int32_t prc_sync(prc_ctx* ctx);
  * registered a host image (PRC_FRAME_KEEP_GBUFFER and PRC_FRAME_SHADOW_RESET are rejected; MSAA frames — strips must start and
  * end on multiples of msaa — are downsampled per strip on the rank that shaded it, which shades `msaa` extra rows on either
  * side for the filter, and need image_mask = 0: they leave through the host image); a consumer's image of a frame stays valid until its
- * next prc_render_peer (readers: the host after prc_sync, or work enqueued on prc_stream() before that call). prc_sync() finishes the submitted frames:
+ * next prc_render_peer (readers: the host after prc_sync, or — unless the frame carried PRC_FRAME_IMAGE_AT_SYNC — work enqueued on prc_stream() before that call). prc_sync() finishes the submitted frames:
  * PRC_ERR_RETRY = a queue overflowed on THIS rank (grown now; all ranks must agree to submit the frames again),
  * PRC_ERR_PEER = a device-side wait for a peer gave up after 4 s.
  * The result is the 1-GPU frame bit for bit: depth maxima do not depend on who rasterised which rows. */

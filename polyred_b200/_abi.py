@@ -33,6 +33,7 @@ PRC_FRAME_SHADOW_RESET = 64
 PRC_FRAME_BGRA = 128
 PRC_FRAME_ASYNC = 256
 PRC_FRAME_NO_KERNEL_TIMERS = 512
+PRC_FRAME_IMAGE_AT_SYNC = 1024
 
 F16 = C.c_float * 16
 F3 = C.c_float * 3

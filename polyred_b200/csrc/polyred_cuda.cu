@@ -89,6 +89,11 @@ struct prc_ctx {
   // readback overlapped with shading: the image leaves in row bands on a second stream while the next band is shaded
   cudaStream_t copy_stream = nullptr;
   cudaStream_t copy_stream2 = nullptr;  // peer frames: the shadow sweep runs here, beside the camera pass on `stream`
+  // PRC_FRAME_IMAGE_AT_SYNC: an image consumer waits for its peers' strips on img_stream, beside the frame's stream
+  cudaStream_t img_stream = nullptr;
+  cudaEvent_t ev_own_shaded = nullptr, ev_image_done = nullptr;
+  bool img_pending = false;        // img_stream holds waits of frames not yet finished by prc_sync
+  bool late_free_pending = false;  // the previous frame's "image free" announcement is img_stream's job (not the next frame's first operation)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_band[PRC_SHADE_BANDS_MAX] = {}, ev_copied = nullptr;
   int shade_bands = PRC_SHADE_BANDS;
@@ -889,6 +894,10 @@ int32_t finish_timings(prc_ctx* ctx) {
     CK(cudaStreamSynchronize(ctx->copy_stream));
     ctx->copy_pending = false;
   }
+  if (ctx->img_pending) {  // PRC_FRAME_IMAGE_AT_SYNC: the peers' strips of the last frames (the side stream's waits also end by timeout)
+    CK(cudaStreamSynchronize(ctx->img_stream));
+    ctx->img_pending = false;
+  }
   float a = 0, b = 0, c = 0, d = 0;
   cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
   cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
@@ -975,6 +984,9 @@ int32_t prc_open(int32_t device, prc_ctx** out) {
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PRC_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PRC_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PRC_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&ctx->img_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PRC_ERR_CUDA; }
+  cudaEventCreateWithFlags(&ctx->ev_own_shaded, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_image_done, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   for (auto& e : ctx->ev) cudaEventCreate(&e);
@@ -1046,6 +1058,9 @@ int32_t prc_close(prc_ctx* ctx) {
   if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
+  if (ctx->img_stream) cudaStreamDestroy(ctx->img_stream);
+  if (ctx->ev_own_shaded) cudaEventDestroy(ctx->ev_own_shaded);
+  if (ctx->ev_image_done) cudaEventDestroy(ctx->ev_image_done);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   cudaStreamDestroy(ctx->stream);
@@ -1629,6 +1644,8 @@ void preload_kernels() {
 }
 
 void peer_release(prc_ctx* ctx) {
+  if (ctx->img_stream) cudaStreamSynchronize(ctx->img_stream);
+  ctx->img_pending = false; ctx->late_free_pending = false;
   for (void* b : ctx->peer_opened) cudaIpcCloseMemHandle(b);
   ctx->peer_opened.clear();
   ctx->peers = PeerTable{};
@@ -1745,7 +1762,10 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
   // A rank that receives this frame's image tells the pushers its image buffer is free: whatever it held (the previous
   // frame's image, if it was a consumer then) has been read by everything the caller enqueued on this stream, or finished
   // on the host, before this call. Announcing "free up to e-1" per frame lets the consumer set change between frames.
-  if (image_mask & me) peer_signal(ctx, PRC_SIG_IMAGE_FREE, e - 1, all);
+  // (after a PRC_FRAME_IMAGE_AT_SYNC frame that this rank received, the side stream announces "free up to e-1" itself, once the
+  // strips of e-1 have landed; announcing it here, earlier, would let a peer overwrite rows whose e-1 strip is still in flight)
+  if ((image_mask & me) && !ctx->late_free_pending) peer_signal(ctx, PRC_SIG_IMAGE_FREE, e - 1, all);
+  ctx->late_free_pending = false;
   CK(cudaEventRecord(ctx->ev[0], st));
   // merged planes of this frame (read by resolve / shading) and of the next one (cleared now)
   unsigned long long* mk = (unsigned long long*)ctx->d_mkeys.p;
@@ -1851,6 +1871,9 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
   }
   peer_signal_wait(ctx, PRC_SIG_SHADOW, e, all, PRC_SIG_SHADOW, e, all);
   // ---- resolve + shading of the strip from the merged buffers
+  // (a previous PRC_FRAME_IMAGE_AT_SYNC frame: its strips must have landed before this frame's shading writes the image — normally long
+  // satisfied; it only matters when the strips moved between the two frames)
+  if (ctx->img_pending) CK(cudaStreamWaitEvent(st, ctx->ev_image_done, 0));
   ctx->keys_shade = plane_cur; ctx->first_shade = first_cur;
   ctx->defer_copy_join = true;
   r = do_main<E>(ctx, fr, F, 8 | 2, 1);
@@ -1870,7 +1893,23 @@ int32_t enqueue_peer_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F,
         CK(cudaMemcpyAsync(ctx->peer_image[c] + off, (const uint8_t*)ctx->d_image.p + off, bytes, cudaMemcpyDefault, st));
     peer_signal(ctx, PRC_SIG_IMAGE, e, consumers);
   }
-  if (consumers & me) peer_wait(ctx, PRC_SIG_IMAGE, e, all);  // every strip has landed in this rank's image
+  if (consumers & me) {
+    if ((fr->flags & PRC_FRAME_IMAGE_AT_SYNC) && (all & ~me)) {
+      // beside the stream: own strip shaded (and copied to the other consumers) -> wait for the peers' strips -> "image free up to e"
+      // -> ev_image_done. This rank's next frame does not wait for any of it; prc_sync does.
+      CK(cudaEventRecord(ctx->ev_own_shaded, st));
+      CK(cudaStreamWaitEvent(ctx->img_stream, ctx->ev_own_shaded, 0));
+      ctx->stream = ctx->img_stream;
+      peer_wait(ctx, PRC_SIG_IMAGE, e, all);
+      peer_signal(ctx, PRC_SIG_IMAGE_FREE, e, all);
+      ctx->stream = st;
+      CK(cudaEventRecord(ctx->ev_image_done, ctx->img_stream));
+      ctx->img_pending = true;
+      ctx->late_free_pending = true;
+    } else {
+      peer_wait(ctx, PRC_SIG_IMAGE, e, all);  // every strip has landed in this rank's image
+    }
+  }
   CK(cudaEventRecord(ctx->ev[3], st));
   CK(cudaGetLastError());
   return PRC_OK;

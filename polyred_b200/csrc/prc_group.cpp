@@ -423,6 +423,7 @@ int32_t prc_group_render(prc_group* g, const prc_frame* fr, uint8_t* rgba_out) {
       prc_frame f = *fr;
       f.flags &= ~(uint32_t)PRC_FRAME_ASYNC;
       if (!measure && n > 1) f.flags |= PRC_FRAME_NO_KERNEL_TIMERS;
+      if (async) f.flags |= PRC_FRAME_IMAGE_AT_SYNC;  // frames submitted back to back: rank 0 does not stop for the strips of each one (prc_group_sync does)
       f.row0 = g->row0[r];
       f.row1 = g->row1[r];
       if (g->stagger_ms && r) std::this_thread::sleep_for(std::chrono::milliseconds((long)g->stagger_ms * r));

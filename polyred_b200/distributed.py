@@ -262,10 +262,18 @@ class PeerFrames:
             from ._lib import PolyredCudaError
             from . import _abi as A
             raise PolyredCudaError(A.PRC_ERR_UNSUPPORTED, "PeerFrames: MSAA frames leave through share_host_image() (frame_desc(no_readback=False), gather=False)")
-        if self._row_arrays is not None:
-            self.be.render_peer_arrays(self.prepare(fd), self._row_arrays[0], self._row_arrays[1], self.image_mask if gather else 0)
-        else:
-            self.be.render_peer(self.prepare(fd), self.rows, self.image_mask if gather else 0)
+        from . import _abi as A
+        flags = fd.struct.flags
+        if gather and self.image_mask and (flags & A.PRC_FRAME_NO_READBACK):
+            # the gathered image is read after finish() (image()): root need not stop inside every frame for its peers' strips
+            fd.struct.flags = flags | A.PRC_FRAME_IMAGE_AT_SYNC
+        try:
+            if self._row_arrays is not None:
+                self.be.render_peer_arrays(self.prepare(fd), self._row_arrays[0], self._row_arrays[1], self.image_mask if gather else 0)
+            else:
+                self.be.render_peer(self.prepare(fd), self.rows, self.image_mask if gather else 0)
+        finally:
+            fd.struct.flags = flags
         self._submitted.append((fd, gather))
 
     def _shm_votes(self, vote):

@@ -82,3 +82,92 @@ def test_product_code_never_references_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "libpr_oracle" not in txt and "oracle_binding" not in txt and "orc_" not in txt, os.path.join(dirpath, f)
+
+
+# ---- the Go shim (go/cuda.go) cannot be compiled here (no Go toolchain): its fixed-layout mirrors are checked by computing the
+# ---- layout Go gives them (gc, amd64: natural alignment, fields in declaration order) and comparing with the C compiler's ----
+GO_SIZES = {"uint32": (4, 4), "int32": (4, 4), "float32": (4, 4), "uint64": (8, 8), "int64": (8, 8), "uintptr": (8, 8), "unsafe.Pointer": (8, 8),
+            "uint8": (1, 1), "byte": (1, 1), "uint16": (2, 2), "int16": (2, 2)}
+
+
+def _go_structs():
+    src = open(os.path.join(ROOT, "go", "cuda.go")).read()
+    src = re.sub(r"//[^\n]*", "", src)
+    out = {}
+    for name, body in re.findall(r"type\s+(prc\w+)\s+struct\s*\{(.*?)\}", src, flags=re.S):
+        fields = []
+        for decl in re.split(r"[\n;]", body):
+            decl = decl.strip()
+            if not decl:
+                continue
+            m = re.match(r"^([\w\s,]+?)\s+((?:\[\d+\])?[\w.]+)$", decl)
+            assert m, (name, decl)
+            names, ty = [n.strip() for n in m.group(1).split(",")], m.group(2)
+            a = re.match(r"\[(\d+)\](.+)", ty)
+            size, align = GO_SIZES[a.group(2) if a else ty]
+            if a:
+                size *= int(a.group(1))
+            for n in names:
+                fields.append((n, size, align))
+        out[name] = fields
+    return out
+
+
+def _go_layout(fields):
+    off, maxal, res = 0, 1, []
+    for n, size, align in fields:
+        off = (off + align - 1) // align * align
+        res.append((n, off, size))
+        off += size
+        maxal = max(maxal, align)
+    return res, (off + maxal - 1) // maxal * maxal
+
+
+def test_go_shim_struct_layouts_match_header(tmp_path):
+    """go/cuda.go had only ever been checked by eye. Every mirrored struct must have the C struct's size and the
+    same sequence of field offsets (names differ; blank Go fields are the C padding members), and the frame-flag constants
+    (1 << iota) must equal the header's values."""
+    pairs = {"prcMaterial": "prc_material", "prcScene": "prc_scene", "prcObjectXf": "prc_object_xf", "prcLight": "prc_light", "prcFrame": "prc_frame"}
+    go = _go_structs()
+    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "polyred_cuda.h"\nint main(){\n'
+    for g, c in pairs.items():
+        assert g in go, f"go/cuda.go no longer declares {g}"
+        prog += f'printf("{c} %zu\\n", sizeof({c}));\n'
+        for name, _ in getattr(A, c)._fields_:
+            prog += f'printf("{c}.{name} %zu\\n", offsetof({c}, {name}));\n'
+    prog += "return 0;}\n"
+    src = tmp_path / "golayout.c"
+    src.write_text(prog)
+    exe = tmp_path / "golayout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    out = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for g, c in pairs.items():
+        layout, size = _go_layout(go[g])
+        assert size == int(out[c]), (g, size, out[c])
+        c_offsets = [int(out[f"{c}.{name}"]) for name, _ in getattr(A, c)._fields_]
+        go_named = [off for n, off, _ in layout if n != "_"]
+        # every C member starts where a Go field starts; Go may split nothing and may only add blank padding fields
+        c_named = [o for (name, _), o in zip(getattr(A, c)._fields_, c_offsets) if not name.startswith("_")]
+        assert go_named == c_named, (g, go_named, c_named)
+    # frame flags: const ( prcFramePerspect = 1 << iota ... )
+    gosrc = open(os.path.join(ROOT, "go", "cuda.go")).read()
+    block = re.search(r"const \(\s*prcFramePerspect = 1 << iota(.*?)\)", gosrc, flags=re.S).group(1)
+    names = ["prcFramePerspect"] + re.findall(r"^\s*(prcFrame\w+)", block, flags=re.M)
+    want = {"prcFramePerspect": A.PRC_FRAME_PERSPECT, "prcFrameShadowMap": A.PRC_FRAME_SHADOWMAP, "prcFrameGamma": A.PRC_FRAME_GAMMA,
+            "prcFrameKeepGBuffer": A.PRC_FRAME_KEEP_GBUFFER, "prcFrameNoReadback": A.PRC_FRAME_NO_READBACK,
+            "prcFrameUniformsResident": A.PRC_FRAME_UNIFORMS_RESIDENT, "prcFrameShadowReset": A.PRC_FRAME_SHADOW_RESET,
+            "prcFrameBGRA": A.PRC_FRAME_BGRA, "prcFrameAsync": A.PRC_FRAME_ASYNC}
+    for i, n in enumerate(names):
+        assert want[n] == 1 << i, (n, i)
+
+
+def test_python_constants_match_header():
+    """Every PRC_* #define with an integer value in include/polyred_cuda.h equals the constant of the same name in _abi.py."""
+    src = open(HEADER).read()
+    n = 0
+    for name, val in re.findall(r"^#define\s+(PRC_[A-Z0-9_]+)\s+(-?\d+)u?\b", src, flags=re.M):
+        if hasattr(A, name):
+            assert getattr(A, name) == int(val), name
+            n += 1
+    assert n >= 20
+    assert A.PRC_FRAME_IMAGE_AT_SYNC == 1024

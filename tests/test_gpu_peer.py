@@ -52,11 +52,13 @@ def _group(s, cam, w, h, devices):
     return rs, fds, mine
 
 
-def _run(devices, frames=3, size=(480, 272), scene=None):
+def _run(devices, frames=3, size=(480, 272), scene=None, extra_flags=0):
     s, cam, w, h = _scene(*size) if scene is None else (*scene, *size)
     ref = render.NewRenderer(*_opts(s, cam, w, h), render.CUDA(devices[0])).Render().copy()
     from polyred_b200._lib import PolyredCudaError
     rs, fds, mine = _group(s, cam, w, h, devices)
+    for fd in fds:
+        fd.struct.flags |= extra_flags
     for attempt in range(4):
         for _ in range(frames):
             for k, r in enumerate(rs):
@@ -100,6 +102,16 @@ def test_peer_three_ranks_ragged_rows_one_gpu(monkeypatch):
     """Strips and shadow shards that do not divide evenly (272 rows over 3 ranks; 4 maps over 3 ranks = units that span two lights)."""
     monkeypatch.setenv("PRC_FMA", "exact")
     ref, out = _run([0, 0, 0], frames=3)
+    assert int((ref != out).any(axis=2).sum()) == 0
+
+
+def test_peer_image_complete_at_sync(monkeypatch):
+    """PRC_FRAME_IMAGE_AT_SYNC: the consumer (rank 0) waits for its peers' strips beside its stream and starts its next frame at
+    once; after prc_sync its image holds the last frame, all strips of it. Five frames back to back, three ranks."""
+    monkeypatch.setenv("PRC_FMA", "exact")
+    ref, out = _run([0, 0, 0], frames=5, extra_flags=A.PRC_FRAME_IMAGE_AT_SYNC)
+    assert int((ref != out).any(axis=2).sum()) == 0
+    ref, out = _run([0, 0], frames=1, extra_flags=A.PRC_FRAME_IMAGE_AT_SYNC)
     assert int((ref != out).any(axis=2).sum()) == 0
 
 

@@ -17,12 +17,14 @@ import pytest
 SHADOW, SHADED, IMAGE, IMAGE_FREE = range(4)
 
 
-def frame_ops(rank, world, e, mask, shadows=True):
-    """The stream operations of frame e on `rank` (enqueue_peer_frame, in order)."""
+def frame_ops(rank, world, e, mask, shadows=True, late=False, prev_late=False):
+    """The stream operations of frame e on `rank` (enqueue_peer_frame, in order): (main stream ops, side stream ops).
+    late = PRC_FRAME_IMAGE_AT_SYNC (a consumer waits for its peers' strips beside the stream); prev_late = this rank received
+    frame e-1 that way (its "image free" announcement and its image-complete event belong to the side stream)."""
     me, everyone = 1 << rank, (1 << world) - 1
     others = everyone & ~me
-    ops = []
-    if mask & me:
+    ops, side = [], []
+    if (mask & me) and not prev_late:
         ops.append(("signal", IMAGE_FREE, e - 1, others))
     ops.append(("clear_next_keys", e))  # the merged key plane of frame e+1 (the planes alternate with the frame parity)
     ops.append(("forward", e))  # the camera pass needs no shadow map: it runs while slower peers still shade frame e-1
@@ -36,6 +38,8 @@ def frame_ops(rank, world, e, mask, shadows=True):
         ops.append(("wait", SHADOW, e, others))
         ops.append(("signal", SHADOW, e, others))
         ops.append(("wait", SHADOW, e, others))
+    if prev_late:
+        ops.append(("await", ("image_done", e - 1)))  # the previous frame's strips have landed before this shading writes the image
     ops.append(("shade", e))
     if shadows:
         ops.append(("signal", SHADED, e, others))
@@ -45,49 +49,66 @@ def frame_ops(rank, world, e, mask, shadows=True):
         ops.append(("copy_strip", e, consumers & ~me))
         ops.append(("signal", IMAGE, e, consumers & ~me))
     if consumers & me:
-        ops.append(("wait", IMAGE, e, others))
-        ops.append(("read_image", e))  # a stream-ordered reader enqueued by the caller before the next frame
-    return ops
+        if late and others:
+            ops.append(("record", ("own_shaded", e)))
+            side.append(("await", ("own_shaded", e)))
+            side.append(("wait", IMAGE, e, others))
+            side.append(("read_image", e))  # complete here, and until a frame e+1 is submitted (what prc_sync hands out)
+            side.append(("signal", IMAGE_FREE, e, others))
+            side.append(("record", ("image_done", e)))
+        else:
+            ops.append(("wait", IMAGE, e, others))
+            ops.append(("read_image", e))  # a stream-ordered reader enqueued by the caller before the next frame
+    return ops, side
 
 
-def simulate(world, masks, seed, host_lookahead):
+def simulate(world, masks, seed, host_lookahead, late=None, starve=None):
+    """late: per-frame booleans (PRC_FRAME_IMAGE_AT_SYNC on the consumers of that frame); None = never.
+    starve = (rank, queue): that stream only runs when nothing else can (an adversarial schedule)."""
     rng = random.Random(seed)
     frames = len(masks)
+    late = late or [False] * frames
     words = [[[0] * world for _ in range(4)] for _ in range(world)]       # words[dst][kind][src]
     maps = [[0] * world for _ in range(world)]                            # maps[holder][owner] = frame whose rows are in holder's copy
     image = [[0] * world for _ in range(world)]                           # image[holder][strip owner]
     keys = [[dict(), dict()] for _ in range(world)]                       # keys[holder][parity] = {pusher: frame} of the merged key planes
-    reading = [None] * world                                              # frame a consumer's reader is looking at (None: idle)
-    queue = [[] for _ in range(world)]                                    # submitted, not yet executed
+    queue = [[[], []] for _ in range(world)]                              # per rank: [main stream, side stream], submitted and not yet executed
+    events = set()                                                        # (rank, name) recorded
     submitted = [0] * world                                               # frames submitted by each host
     executed_frames = [0] * world
-    pc = [0] * world                                                      # ops executed inside the current queue head
+    was_late_consumer = [False] * world
 
-    def runnable(r):
-        if not queue[r]:
+    def runnable(r, q):
+        if not queue[r][q]:
             return False
-        op = queue[r][0]
+        op = queue[r][q][0]
         if op[0] == "wait":
             _, kind, epoch, mask = op
             return all(words[r][kind][s] >= epoch for s in range(world) if (mask >> s) & 1)
+        if op[0] == "await":
+            return (r, op[1]) in events
         return True
 
     steps = 0
-    while any(queue) or any(s < frames for s in submitted):
+    while any(q for rq in queue for q in rq) or any(s < frames for s in submitted):
         steps += 1
-        assert steps < 200000
-        choices = [("gpu", r) for r in range(world) if runnable(r)]
+        assert steps < 400000
+        choices = [("gpu", r, q) for r in range(world) for q in (0, 1) if runnable(r, q)]
         # a host may run ahead of its own GPU by `host_lookahead` frames (bounded launch queue), independently of the others
-        choices += [("host", r) for r in range(world) if submitted[r] < frames and submitted[r] - executed_frames[r] < host_lookahead]
-        assert choices, f"deadlock: world={world} masks={masks} seed={seed} heads={[q[0] if q else None for q in queue]}"
-        what, r = rng.choice(choices)
+        choices += [("host", r, 0) for r in range(world) if submitted[r] < frames and submitted[r] - executed_frames[r] < host_lookahead]
+        if starve is not None and any(c[1:] != starve or c[0] == "host" for c in choices):
+            choices = [c for c in choices if c[1:] != starve or c[0] == "host"]
+        assert choices, f"deadlock: world={world} masks={masks} late={late} seed={seed} heads={[[q[0] if q else None for q in rq] for rq in queue]}"
+        what, r, q = rng.choice(choices)
         if what == "host":
             e = submitted[r] + 1
-            ops = frame_ops(r, world, e, masks[e - 1])
-            queue[r].extend(ops + [("frame_done", e)])
+            ops, side = frame_ops(r, world, e, masks[e - 1], late=late[e - 1], prev_late=was_late_consumer[r])
+            was_late_consumer[r] = bool(side)
+            queue[r][0].extend(ops + [("frame_done", e)])
+            queue[r][1].extend(side)
             submitted[r] = e
             continue
-        op = queue[r].pop(0)
+        op = queue[r][q].pop(0)
         kind = op[0]
         if kind == "signal":
             _, k, epoch, mask = op
@@ -95,6 +116,8 @@ def simulate(world, masks, seed, host_lookahead):
                 if (mask >> d) & 1:
                     assert words[d][k][r] <= epoch, "epoch words must not decrease"
                     words[d][k][r] = epoch
+        elif kind == "record":
+            events.add((r, op[1]))
         elif kind == "clear_next_keys":
             e = op[1]
             plane = keys[r][(e + 1) & 1]
@@ -116,12 +139,12 @@ def simulate(world, masks, seed, host_lookahead):
             e = op[1]
             assert maps[r] == [e] * world, f"rank {r} shades frame {e} from shadow rows of frames {maps[r]}"
             assert keys[r][e & 1] == {p: e for p in range(world)}, f"rank {r} shades frame {e} from keys {keys[r][e & 1]}"
-            assert reading[r] is None or True
             image[r][r] = e
         elif kind == "copy_strip":
             _, e, mask = op
             for c in range(world):
                 if (mask >> c) & 1:
+                    assert image[c][r] <= e, "a strip of an older frame overwrites a newer one"
                     image[c][r] = e
         elif kind == "read_image":
             e = op[1]
@@ -148,6 +171,9 @@ def test_protocol_model_random_schedules(world):
             masks = [rng.randint(0, everyone) for _ in range(frames)]  # the consumer set changes from frame to frame
         for lookahead in (1, 2, frames + 1):
             simulate(world, masks, seed=rng.randint(0, 1 << 30), host_lookahead=lookahead)
+            # PRC_FRAME_IMAGE_AT_SYNC on every frame, and switched on and off from frame to frame
+            simulate(world, masks, seed=rng.randint(0, 1 << 30), host_lookahead=lookahead, late=[True] * frames)
+            simulate(world, masks, seed=rng.randint(0, 1 << 30), host_lookahead=lookahead, late=[rng.random() < 0.5 for _ in range(frames)])
 
 
 def test_model_detects_a_broken_protocol():
@@ -156,8 +182,9 @@ def test_model_detects_a_broken_protocol():
     global frame_ops
     good = frame_ops
 
-    def broken(rank, world, e, mask, shadows=True):
-        return [op for op in good(rank, world, e, mask, shadows) if not (op[0] == "wait" and op[1] == SHADED)]
+    def broken(rank, world, e, mask, shadows=True, late=False, prev_late=False):
+        ops, side = good(rank, world, e, mask, shadows, late, prev_late)
+        return [op for op in ops if not (op[0] == "wait" and op[1] == SHADED)], side
 
     frame_ops = broken
     try:
@@ -202,3 +229,28 @@ def test_key_planes_stay_clean_when_strips_move_back_and_forth():
         assert _plane_rows_model(strips, H, "last_written") is None, strips
     # the checker is not vacuous: clearing the CURRENT strip's rows leaves stale keys in a row lost and regained two frames later
     assert _plane_rows_model([(0, 40), (0, 10), (0, 40)], H, "current_strip") == (3, 10)
+
+
+def test_model_detects_an_early_image_free_announcement():
+    """PRC_FRAME_IMAGE_AT_SYNC: "image free up to e" must come from the side stream, after the strips of frame e have landed. If
+    the consumer's next frame announced it as its first operation (what frames without the flag do), a fast peer's strip of frame
+    e+1 could land while a slow peer's strip of frame e is still on its way: the image handed out for e would be mixed."""
+    global frame_ops
+    good = frame_ops
+
+    def broken(rank, world, e, mask, shadows=True, late=False, prev_late=False):
+        ops, side = good(rank, world, e, mask, shadows, late, prev_late)
+        if (mask & (1 << rank)) and prev_late:
+            ops = [("signal", IMAGE_FREE, e - 1, ((1 << world) - 1) & ~(1 << rank))] + ops
+        return ops, side
+
+    frame_ops = broken
+    try:
+        with pytest.raises(AssertionError, match="reads frame"):
+            for seed in range(100):  # rank 0's side stream is starved: it runs only when every other stream is blocked
+                simulate(3, [1, 1, 1, 1], seed=seed, host_lookahead=4, late=[True] * 4, starve=(0, 1))
+    finally:
+        frame_ops = good
+    for seed in range(300):  # the real operation list passes the same adversarial schedules (and with the main stream starved)
+        simulate(3, [1, 1, 1, 1], seed=seed, host_lookahead=4, late=[True] * 4, starve=(0, 1))
+        simulate(3, [1, 1, 1, 1], seed=seed, host_lookahead=4, late=[True] * 4, starve=(0, 0))
