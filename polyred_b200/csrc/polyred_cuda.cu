@@ -1289,6 +1289,23 @@ int32_t prc_render_deferred(prc_ctx* ctx, const prc_frame* fr, uint8_t* rgba_out
   return r;
 }
 
+// The key clear of do_main (phase 1), issued on `s`: the rasterised rows (+ the AO rows of pixel (0,0), + pixel (0,0) itself).
+static int32_t clear_keys(prc_ctx* ctx, const DevFrame& F, cudaStream_t s) {
+  unsigned long long* keys = (unsigned long long*)ctx->d_keys.p;
+  unsigned long long* first = keys + (size_t)F.W * F.H;
+  int r0s[2] = {F.rr0, 0}, r1s[2] = {F.rr1, (ctx->any_ao && F.rr0 > 0) ? std::min(100, F.rr0) : 0};
+  for (int k = 0; k < 2; k++) {
+    if (r1s[k] <= r0s[k]) continue;
+    CK(cudaMemsetAsync(keys + (size_t)r0s[k] * F.W, 0, (size_t)(r1s[k] - r0s[k]) * F.W * 8, s));
+    if (ctx->nan_mode) CK(cudaMemsetAsync(first + (size_t)r0s[k] * F.W, 0xFF, (size_t)(r1s[k] - r0s[k]) * F.W * 8, s));
+  }
+  if (F.rr0 > 0 && r1s[1] == 0) {
+    CK(cudaMemsetAsync(keys, 0, 8, s));
+    if (ctx->nan_mode) CK(cudaMemsetAsync(first, 0xFF, 8, s));
+  }
+  return PRC_OK;
+}
+
 // the launches of one whole frame (shadow sweeps, camera pass, tile path, resolve, shading)
 static int32_t enqueue_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& F) {
   const unsigned int rec = ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
@@ -1323,11 +1340,27 @@ static int32_t enqueue_frame(prc_ctx* ctx, const prc_frame* fr, const DevFrame& 
     CK(cudaEventRecordWithFlags(ctx->ev[3], st, rec));
     return PRC_OK;
   }
+  // The 66 MB key clear of a 4K frame (0.02 ms) is only needed by the camera pass: it runs on a second stream under the shadow
+  // sweep, which never touches the keys (forked here = behind the previous frame's shading, joined before the camera pass).
+  static const bool early_clear_on = !(getenv("PRC_NO_EARLY_CLEAR") != nullptr && atoi(getenv("PRC_NO_EARLY_CLEAR")) != 0);
+  const bool early_clear = early_clear_on && !ctx->capturing && (fr->flags & PRC_FRAME_SHADOWMAP) && ctx->n_cast_alloc > 0 && ctx->n_cast_alloc != 0xFFFFFFFFu;
+  if (early_clear) {
+    CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream2, ctx->ev_fork, 0));
+    r = clear_keys(ctx, F, ctx->copy_stream2);
+    if (r != PRC_OK) return r;
+    CK(cudaEventRecord(ctx->ev_join, ctx->copy_stream2));
+  }
   r = ctx->exact ? do_shadows<true>(ctx, fr, F, units_from_mask(fr, 0xFFFFFFFFu, 0, F.H), false)
                  : do_shadows<false>(ctx, fr, F, units_from_mask(fr, 0xFFFFFFFFu, 0, F.H), false);
   if (r != PRC_OK) return r;
   CK(cudaEventRecordWithFlags(ctx->ev[1], ctx->stream, rec));
+  if (early_clear) {
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    ctx->skip_key_clear = true;
+  }
   r = ctx->exact ? do_main<true>(ctx, fr, F) : do_main<false>(ctx, fr, F);
+  ctx->skip_key_clear = false;
   if (r != PRC_OK) return r;
   CK(cudaEventRecordWithFlags(ctx->ev[3], ctx->stream, rec));
   return PRC_OK;
