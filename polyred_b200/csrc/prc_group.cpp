@@ -316,11 +316,12 @@ int32_t prc_group_open(const int32_t* devices, uint32_t n, prc_group** out) {
   const char* b = getenv("PRC_GROUP_BALANCE");
   g->balance = !(b && atoi(b) == 0);
   if (const char* sg = getenv("PRC_GROUP_STAGGER_MS")) g->stagger_ms = std::max(0, std::min(1000, atoi(sg)));
-  if (n > 1)
-    for (uint32_t r = 0; r < n; r++) {
-      g->workers.push_back(new Worker());
-      g->workers[r]->th = std::thread(worker_main, g, r);
-    }
+  if (n > 1) {
+    // all Worker objects first, then the threads: a worker reads g->workers[rank] as soon as it starts, and a push_back for the
+    // next worker could reallocate the vector under it (found by ThreadSanitizer, tests/test_group_host_native.py)
+    for (uint32_t r = 0; r < n; r++) g->workers.push_back(new Worker());
+    for (uint32_t r = 0; r < n; r++) g->workers[r]->th = std::thread(worker_main, g, r);
+  }
   *out = g;
   return PRC_OK;
 }
