@@ -9,15 +9,14 @@ A step = one `Render()` of the frame. `value` = valid scene triangles x frames/s
 resident in HBM and the image left on the device (CUDA events on the library's stream); `e2e` = the
 same through the C-ABI call with HOST buffers: per step the frame uniforms go host->device and the
 RGBA8 image comes back device->host inside the timed region.
-N>1 (torchrun, one process per GPU): the frame is split into N horizontal screen strips, the Ls
-shadow maps are sharded (light x row range), `scaling` = "strong" (same frame, more GPUs).
-`--mgpu peer` (default): frames through prc_render_peer — the ranks map each other's buffers over
-NVLink (CUDA IPC), every rank pushes the non-empty texels of its shadow rows into its peers' maps and
-its image strip into rank 0's image, ordered by epoch words in peer memory; frames are submitted back to
-back with no host wait and no collective, strips balanced by measured time; e2e through one shared host
-image. `--mgpu nccl`: round 1's path (one frame at a time, shadow maps and image strips all-gathered with
-NCCL), kept for comparison. Every N>1 line carries `matches_1gpu`: the frame's CRC against rank 0's own
-1-GPU render of the same frame.
+N>1 (torchrun, one process per GPU), `scaling` = "strong" (the same frame on more GPUs). `--mgpu peer` (default): frames
+through prc_render_peer — every rank rasterises ITS SHARE OF THE TRIANGLES (camera pass + all shadow lights) into private
+buffers, one kernel merges them into the peers over NVLink peer memory (CUDA IPC; RED.MAX on visibility keys and shadow
+depths), every rank shades a strip of rows balanced by measured time and copies it into rank 0's image; ordering by epoch words
+in peer memory, frames submitted back to back with no host wait and no collective; e2e through one
+shared host image that each GPU writes its strip into. `--mgpu nccl`: round 1's path (screen strips + shadow shards, shadow
+maps and image strips all-gathered with NCCL, one frame at a time), kept for comparison. Every N>1 line carries
+`matches_1gpu`: the frame's CRC against rank 0's own 1-GPU render of the same frame.
 Roofline: `roofline` = the dominant kernel against the measured HBM peak with SURVEY 8(d)'s algorithmic
 bytes (per rank at N>1: the bytes of the rows that rank owns); `shading_roofline` = the shading kernel
 against the FP32 FMA peak measured by prc_measure_fp32_peak in this run (SURVEY 8(d) flop per covered pixel);
