@@ -171,3 +171,41 @@ def test_python_constants_match_header():
             n += 1
     assert n >= 20
     assert A.PRC_FRAME_IMAGE_AT_SYNC == 1024
+
+
+def test_go_shim_binds_only_exported_symbols_with_the_declared_arity(lib):
+    """Every symbol name go/cuda.go passes to purego.Dlsym is exported by the library, and every purego.SyscallN call on it passes
+    as many arguments as the C declaration has parameters (a typo or a stale call shape would only show at run time in Go)."""
+    gosrc = open(os.path.join(ROOT, "go", "cuda.go")).read()
+    names = sorted(set(re.findall(r'"(prc_[a-z0-9_]+)"', gosrc)))
+    assert len(names) >= 9, names
+    for n in names:
+        assert hasattr(lib, n), f"go/cuda.go binds {n}, which libpolyred_cuda.so does not export"
+    # arity: the C prototypes
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    arity = {}
+    for name, params in re.findall(r"\b(prc_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr):
+        params = params.strip()
+        arity[name] = 0 if params in ("", "void") else params.count(",") + 1
+    # which struct field holds which symbol: fnX: sym("prc_...")
+    field = dict(re.findall(r"(fn[A-Za-z]+):\s*sym\(\"(prc_[a-z0-9_]+)\"\)", gosrc))
+    assert len(field) >= 8, field
+    checked = 0
+    for m in re.finditer(r"purego\.SyscallN\(\s*(?:b|r\.cuda)\.(fn[A-Za-z]+)", gosrc):
+        fn = m.group(1)
+        if fn not in field:
+            continue
+        depth, n_args, i = 1, 0, m.end()  # walk to the parenthesis that closes SyscallN( , counting top-level commas
+        while depth > 0:
+            ch = gosrc[i]
+            if ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                depth -= 1
+            elif ch == "," and depth == 1:
+                n_args += 1
+            i += 1
+        assert n_args == arity[field[fn]], f"go/cuda.go calls {field[fn]} with {n_args} arguments, the header declares {arity[field[fn]]}"
+        checked += 1
+    calls = checked
+    assert checked >= 6, (checked, calls)
