@@ -67,6 +67,8 @@ const (
 	prcFrameShadowReset
 	prcFrameBGRA
 	prcFrameAsync // with prcFrameNoReadback: enqueue only; prc_sync finishes (present path / view batches)
+	prcFrameNoKernelTimers
+	prcFrameImageAtSync // device groups set it themselves on asynchronous frames (include/polyred_cuda.h)
 )
 
 // ---- fixed-layout mirrors of include/polyred_cuda.h (little-endian, 8-byte aligned) ----

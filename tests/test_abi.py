@@ -156,7 +156,9 @@ def test_go_shim_struct_layouts_match_header(tmp_path):
     want = {"prcFramePerspect": A.PRC_FRAME_PERSPECT, "prcFrameShadowMap": A.PRC_FRAME_SHADOWMAP, "prcFrameGamma": A.PRC_FRAME_GAMMA,
             "prcFrameKeepGBuffer": A.PRC_FRAME_KEEP_GBUFFER, "prcFrameNoReadback": A.PRC_FRAME_NO_READBACK,
             "prcFrameUniformsResident": A.PRC_FRAME_UNIFORMS_RESIDENT, "prcFrameShadowReset": A.PRC_FRAME_SHADOW_RESET,
-            "prcFrameBGRA": A.PRC_FRAME_BGRA, "prcFrameAsync": A.PRC_FRAME_ASYNC}
+            "prcFrameBGRA": A.PRC_FRAME_BGRA, "prcFrameAsync": A.PRC_FRAME_ASYNC, "prcFrameNoKernelTimers": A.PRC_FRAME_NO_KERNEL_TIMERS,
+            "prcFrameImageAtSync": A.PRC_FRAME_IMAGE_AT_SYNC}
+    assert len(names) == len(want), names
     for i, n in enumerate(names):
         assert want[n] == 1 << i, (n, i)
 
