@@ -151,7 +151,7 @@ def test_go_shim_struct_layouts_match_header(tmp_path):
         assert go_named == c_named, (g, go_named, c_named)
     # frame flags: const ( prcFramePerspect = 1 << iota ... )
     gosrc = open(os.path.join(ROOT, "go", "cuda.go")).read()
-    block = re.search(r"const \(\s*prcFramePerspect = 1 << iota(.*?)\)", gosrc, flags=re.S).group(1)
+    block = re.search(r"const \(\s*prcFramePerspect = 1 << iota(.*?)\)", re.sub(r"//[^\n]*", "", gosrc), flags=re.S).group(1)
     names = ["prcFramePerspect"] + re.findall(r"^\s*(prcFrame\w+)", block, flags=re.M)
     want = {"prcFramePerspect": A.PRC_FRAME_PERSPECT, "prcFrameShadowMap": A.PRC_FRAME_SHADOWMAP, "prcFrameGamma": A.PRC_FRAME_GAMMA,
             "prcFrameKeepGBuffer": A.PRC_FRAME_KEEP_GBUFFER, "prcFrameNoReadback": A.PRC_FRAME_NO_READBACK,
