@@ -25,6 +25,13 @@ import numpy as np
 from . import partition
 
 
+import os as _os
+
+# PRC_PEER_NO_LATE_IMAGE=1: gathered device frames keep the wait for the peers' strips inside the consumer's stream (A/B switch for
+# PRC_FRAME_IMAGE_AT_SYNC, include/polyred_cuda.h)
+_NO_LATE_IMAGE = _os.environ.get("PRC_PEER_NO_LATE_IMAGE", "0") not in ("", "0")
+
+
 def _cai(ptr, nbytes):
     class _V:
         pass
@@ -264,7 +271,7 @@ class PeerFrames:
             raise PolyredCudaError(A.PRC_ERR_UNSUPPORTED, "PeerFrames: MSAA frames leave through share_host_image() (frame_desc(no_readback=False), gather=False)")
         from . import _abi as A
         flags = fd.struct.flags
-        if gather and self.image_mask and (flags & A.PRC_FRAME_NO_READBACK):
+        if gather and self.image_mask and (flags & A.PRC_FRAME_NO_READBACK) and not _NO_LATE_IMAGE:
             # the gathered image is read after finish() (image()): root need not stop inside every frame for its peers' strips
             fd.struct.flags = flags | A.PRC_FRAME_IMAGE_AT_SYNC
         try:
