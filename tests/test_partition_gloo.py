@@ -140,7 +140,7 @@ class _FakeBackend:
         self.connected = (rank, world, [len(b) for b in handles])
 
     def render_peer(self, fd, rows, image_mask):
-        self.calls.append((fd.tag, fd.struct.row0, fd.struct.row1, tuple(rows), image_mask))
+        self.calls.append((fd.tag, fd.struct.row0, fd.struct.row1, tuple(rows), image_mask, int(fd.struct.flags)))
 
     def frame_state(self):
         return 1 if (self.rank == 1 and self.syncs >= 1) else 0  # rank 1 entered NaN mode with its retry
@@ -181,16 +181,21 @@ def _peer_worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
 
     def frame(tag):
-        return types.SimpleNamespace(struct=A.prc_frame(abi_version=A.PRC_ABI_VERSION, width=40, height=100), tag=tag)
+        return types.SimpleNamespace(struct=A.prc_frame(abi_version=A.PRC_ABI_VERSION, width=40, height=100, flags=A.PRC_FRAME_NO_READBACK), tag=tag)
 
     sc = scene.Scene(light.Point(cast_shadow=True), light.Point(), light.Point(cast_shadow=True))
     be = _FakeBackend(rank)
     r = types.SimpleNamespace(cfg=types.SimpleNamespace(Width=40, Height=100, Scene=sc, ShadowMap=True), _backend=be,
                               frame_desc=lambda no_readback=True: frame("connect"))
     pf = PeerFrames(r, rank, world, 0, root=0)
-    for k in range(3):
-        pf.submit(frame(k))
+    mine = [frame(k) for k in range(3)]
+    for f in mine:
+        pf.submit(f)
     pf.finish()
+    # gathered device frames carry PRC_FRAME_IMAGE_AT_SYNC into the library (rank 0 does not stop for its peers' strips inside
+    # every frame; image() is read after finish()), and the caller's frame keeps the flags it came with
+    assert all(c[5] & A.PRC_FRAME_IMAGE_AT_SYNC for c in be.calls), be.calls
+    assert all(f.struct.flags == A.PRC_FRAME_NO_READBACK for f in mine)
     # rebalance(): both ranks gather the same timings and derive the same new boundaries
     costs = pf.rebalance(damping=1.0, min_rows=4)
     rebalanced = (costs, pf.img_bounds, pf.rows[rank], getattr(be, "state_set", None))
